@@ -1,0 +1,181 @@
+"""Batch container + packed graph store feeding the device-side collate.
+
+``Batch`` carries exactly the attributes the reference modules read from a PyG
+batch (topological_training/models.py:44-52, lightpath_training/models.py:27,35;
+``num_graphs`` at topological_training/train.py:117), plus the offsets PyG keeps
+as ``ptr`` and the edge offsets our collate knows for free (``edge_ptr``).
+
+``PackedGraphStore`` replaces one-pickle-per-graph + ``Dataset.__getitem__`` +
+PyG's collate: all graphs live in flat
+arrays in HBM and ``collate`` is one kernel launch (csrc/graph_index.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_FIELDS = ("x", "edge_index", "edge_attr", "batch", "node_ids", "y", "ptr", "edge_ptr")
+
+
+class Batch:
+    """Minimal stand-in for ``torch_geometric.data.Batch``."""
+
+    def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, node_ids=None,
+                 y=None, ptr=None, edge_ptr=None, num_graphs: Optional[int] = None):
+        self.x, self.edge_index, self.edge_attr = x, edge_index, edge_attr
+        self.batch, self.node_ids, self.y = batch, node_ids, y
+        self.ptr, self.edge_ptr = ptr, edge_ptr
+        self.num_graphs = num_graphs
+        self._cache = {}          # per-batch CSR etc. built lazily by the ops layer
+
+    # -- PyG-like conveniences ------------------------------------------------
+    @property
+    def num_nodes(self) -> int:
+        if self.batch is not None:
+            return int(self.batch.shape[0])
+        if self.x is not None:
+            return int(self.x.shape[0])
+        return int(self.node_ids.shape[0])
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.edge_index.shape[1])
+
+    def to(self, device, non_blocking: bool = False) -> "Batch":
+        kw = {k: (getattr(self, k).to(device, non_blocking=non_blocking)
+                  if getattr(self, k) is not None else None) for k in _FIELDS}
+        return Batch(num_graphs=self.num_graphs, **kw)
+
+    def pin_memory(self) -> "Batch":
+        kw = {k: (getattr(self, k).pin_memory() if getattr(self, k) is not None else None)
+              for k in _FIELDS}
+        return Batch(num_graphs=self.num_graphs, **kw)
+
+    def cpu(self) -> "Batch":
+        return self.to("cpu")
+
+    def nbytes(self, fields: Sequence[str] = _FIELDS) -> int:
+        return sum(getattr(self, k).numel() * getattr(self, k).element_size()
+                   for k in fields if getattr(self, k) is not None)
+
+    def __repr__(self):
+        parts = [f"{k}={tuple(getattr(self, k).shape)}" for k in _FIELDS if getattr(self, k) is not None]
+        return f"Batch(num_graphs={self.num_graphs}, " + ", ".join(parts) + ")"
+
+
+class PackedGraphStore:
+    """All graphs of a dataset as flat arrays.
+
+    node_ptr/edge_ptr [G+1] int64; edge_src/edge_dst [E_tot] int32 graph-local ids in
+    ``from_networkx`` order (grouped by source); node_feat [N_tot,F]
+    or None (topological: ``x=None`` -> embeddings, topological_training/dataset.py:107);
+    edge_feat [E_tot,D] or None; y [G,3].
+    """
+
+    def __init__(self, node_ptr, edge_ptr, edge_src, edge_dst, node_feat=None, edge_feat=None, y=None):
+        self.node_ptr, self.edge_ptr = node_ptr.to(torch.int64), edge_ptr.to(torch.int64)
+        self.edge_src, self.edge_dst = edge_src.to(torch.int32), edge_dst.to(torch.int32)
+        self.node_feat, self.edge_feat, self.y = node_feat, edge_feat, y
+        self._node_ptr_host = self.node_ptr.cpu().numpy()
+        self._edge_ptr_host = self.edge_ptr.cpu().numpy()
+        self._arange = None
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self._node_ptr_host.shape[0] - 1)
+
+    @property
+    def device(self):
+        return self.node_ptr.device
+
+    def to(self, device) -> "PackedGraphStore":
+        mv = lambda t: None if t is None else t.to(device)
+        return PackedGraphStore(mv(self.node_ptr), mv(self.edge_ptr), mv(self.edge_src), mv(self.edge_dst),
+                                mv(self.node_feat), mv(self.edge_feat), mv(self.y))
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.node_ptr, self.edge_ptr, self.edge_src, self.edge_dst, self.node_feat,
+                    self.edge_feat, self.y) if t is not None)
+
+    # -- device-side collate ---------------------------------------------------
+    def collate(self, ids: Union[range, slice, torch.Tensor, Sequence[int]]) -> Batch:
+        """Collates graphs ``ids`` into one :class:`Batch` on the store's CUDA device
+        with one launch of ``qot_collate``; no device->host synchronisation."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("PackedGraphStore.collate runs on the GPU: move the store with .to('cuda')")
+        lib = _lib.lib()
+        nph, eph = self._node_ptr_host, self._edge_ptr_host
+        if isinstance(ids, slice):
+            ids = range(*ids.indices(self.num_graphs))
+        if isinstance(ids, range) and ids.step == 1:
+            g0, g1 = ids.start, ids.stop
+            B = g1 - g0
+            N, E = int(nph[g1] - nph[g0]), int(eph[g1] - eph[g0])
+            if self._arange is None or self._arange.numel() < self.num_graphs:
+                self._arange = torch.arange(self.num_graphs, dtype=torch.int64, device=dev)
+            gids = self._arange[g0:g1]
+            optr = self.node_ptr[g0:g1 + 1] - self.node_ptr[g0]
+            oeptr = self.edge_ptr[g0:g1 + 1] - self.edge_ptr[g0]
+        else:
+            ids_np = np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else list(ids), dtype=np.int64)
+            B = int(ids_np.shape[0])
+            cn = np.zeros(B + 1, dtype=np.int64)
+            ce = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(nph[ids_np + 1] - nph[ids_np], out=cn[1:])
+            np.cumsum(eph[ids_np + 1] - eph[ids_np], out=ce[1:])
+            N, E = int(cn[-1]), int(ce[-1])
+            packed = torch.from_numpy(np.concatenate([ids_np, cn, ce])).to(dev, non_blocking=True)
+            gids, optr, oeptr = packed[:B], packed[B:2 * B + 1], packed[2 * B + 1:]
+        F = self.node_feat.shape[1] if self.node_feat is not None else 0
+        D = self.edge_feat.shape[1] if self.edge_feat is not None else 0
+        Y = self.y.shape[1] if self.y is not None else 0
+        x = torch.empty(N, F, dtype=torch.float32, device=dev) if F else None
+        ei = torch.empty(2, E, dtype=torch.int64, device=dev)
+        ea = torch.empty(E, D, dtype=torch.float32, device=dev) if D else None
+        bt = torch.empty(N, dtype=torch.int64, device=dev)
+        nid = torch.empty(N, dtype=torch.int64, device=dev) if not F else None
+        y = torch.empty(B, Y, dtype=torch.float32, device=dev) if Y else None
+        st = _lib.QotStore(_lib.ptr(self.node_ptr), _lib.ptr(self.edge_ptr), _lib.ptr(self.edge_src),
+                           _lib.ptr(self.edge_dst), _lib.ptr(self.node_feat), _lib.ptr(self.edge_feat),
+                           _lib.ptr(self.y), F, D, Y)
+        optr = optr.contiguous()
+        oeptr = oeptr.contiguous()
+        _lib.check(lib.qot_collate(C.byref(st), _lib.ptr(gids.contiguous()), B, _lib.ptr(optr), _lib.ptr(oeptr),
+                                   N, E, _lib.ptr(x), _lib.ptr(ei), _lib.ptr(ea), _lib.ptr(bt),
+                                   _lib.ptr(nid), _lib.ptr(y), _lib.stream()), "qot_collate")
+        return Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
+                     ptr=optr, edge_ptr=oeptr, num_graphs=B)
+
+    # -- host-side view of a contiguous range (what a host DataLoader would hand over)
+    def host_batch(self, g0: int, g1: int, pin: bool = False) -> Batch:
+        """Batch of graphs [g0,g1) as HOST tensors in the reference's layout (the
+        buffers a user of the reference passes to ``data.to(device)``)."""
+        if self.device.type != "cpu":
+            raise RuntimeError("host_batch needs a host-resident store")
+        n0, n1 = int(self._node_ptr_host[g0]), int(self._node_ptr_host[g1])
+        e0, e1 = int(self._edge_ptr_host[g0]), int(self._edge_ptr_host[g1])
+        B = g1 - g0
+        ptr = self.node_ptr[g0:g1 + 1] - n0
+        eptr = self.edge_ptr[g0:g1 + 1] - e0
+        counts_e = (eptr[1:] - eptr[:-1])
+        off = torch.repeat_interleave(ptr[:-1], counts_e)
+        ei = torch.stack([self.edge_src[e0:e1].to(torch.int64) + off,
+                          self.edge_dst[e0:e1].to(torch.int64) + off])
+        counts_n = ptr[1:] - ptr[:-1]
+        bt = torch.repeat_interleave(torch.arange(B, dtype=torch.int64), counts_n)
+        x = self.node_feat[n0:n1].clone() if self.node_feat is not None else None
+        nid = None
+        if x is None:
+            nid = torch.arange(n1 - n0, dtype=torch.int64) - torch.repeat_interleave(ptr[:-1], counts_n)
+        ea = self.edge_feat[e0:e1].clone() if self.edge_feat is not None else None
+        y = self.y[g0:g1].clone() if self.y is not None else None
+        b = Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
+                  ptr=ptr.clone(), edge_ptr=eptr.clone(), num_graphs=B)
+        return b.pin_memory() if pin else b

@@ -1,0 +1,109 @@
+// Shared host/device helpers for libqot_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/qot_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libqot_b200 targets sm_100a (B200) only"
+#endif
+
+namespace qot {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);   // api.cu (thread-local message)
+
+#define QOT_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::qot::set_error(__VA_ARGS__);              \
+      return QOT_E_BADARG;                        \
+    }                                             \
+  } while (0)
+
+#define QOT_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      ::qot::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                       cudaGetErrorString(e_));                                     \
+      return QOT_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define QOT_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    cudaError_t e_ = cudaPeekAtLastError();                                         \
+    if (e_ != cudaSuccess) {                                                        \
+      ::qot::set_error("%s:%d launch -> %s", __FILE__, __LINE__,                    \
+                       cudaGetErrorString(e_));                                     \
+      return QOT_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+constexpr int kNumSMs = 148;            // B200: 2 dies x 74 SMs
+constexpr unsigned kFull = 0xffffffffu;
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Carves aligned sub-buffers out of the caller's workspace.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return r;
+  }
+};
+
+// Device-wide exclusive scan of n int32 values (out has n+1 entries, out[n] = total).
+// `add` is added to every input element before scanning (self-loop reservation).
+size_t scan_workspace_bytes(int64_t n);
+int exclusive_scan_i32(const int32_t* in, int32_t add, int32_t* out, int64_t n, void* ws,
+                       cudaStream_t stream);
+
+#ifdef __CUDACC__
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+// Sum over aligned groups of G lanes (G power of two <= 32); every lane gets the result.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// streaming 128-bit loads that do not pollute L1 (read-once operands)
+__device__ __forceinline__ int4 ldg_stream_v4(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ longlong2 ldg_stream_l2(const void* p) {
+  longlong2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];"
+               : "=l"(r.x), "=l"(r.y)
+               : "l"(p));
+  return r;
+}
+#endif
+
+}  // namespace qot

@@ -1,0 +1,107 @@
+"""LightpathGNN on the B200 kernels -- drop-in for lightpath_training/models.py:7-45.
+
+Same constructor, ``forward(data) -> (out [L,3], lut_batch [L])``, same
+``ValueError("No LUT node found in the batch.")`` and the same state_dict names as
+the shipped checkpoints (``conv1.lin.weight``, ``conv1.att_src``, ``conv1.att_dst``,
+``conv1.bias``, ``norm1.module.*``, ``mlp.0.*``, ``mlp.3.*``), so
+``lightpath_training/test.py:63`` loads ``models/model_N.pth`` with strict=True.
+
+eval(): one fused launch chain (csrc/lightpath_infer.cu).
+train(): GAT forward -> batch statistics -> LUT head, with the matching backward
+kernels (csrc/lightpath_train.cu) through ``torch.autograd.Function``.
+"""
+from __future__ import annotations
+
+import torch
+from torch.nn import Dropout, LeakyReLU, Linear
+
+from .. import ops
+from ..nn import BatchNorm, GATConv
+
+
+class LightpathGNN(torch.nn.Module):
+    def __init__(self, in_channels, hidden_channels, output_dim, is_lut_index, dropout_p=0.5):
+        super().__init__()
+        self.conv1 = GATConv(in_channels, hidden_channels, heads=4, concat=True)
+        self.norm1 = BatchNorm(hidden_channels * 4)
+        self.mlp = torch.nn.Sequential(
+            Linear(hidden_channels * 4, hidden_channels),
+            LeakyReLU(),
+            Dropout(p=dropout_p),
+            Linear(hidden_channels, output_dim),
+        )
+        self.is_lut_index = is_lut_index
+        self._prepared = None
+        self._prepared_key = None
+
+    # ------------------------------------------------------------------ eval
+    def _eval_params(self):
+        bn = self.norm1.module
+        return {
+            "lin_w": self.conv1.lin.weight, "att_src": self.conv1.att_src, "att_dst": self.conv1.att_dst,
+            "conv_bias": self.conv1.bias, "bn_w": bn.weight, "bn_b": bn.bias,
+            "bn_mean": bn.running_mean, "bn_var": bn.running_var,
+            "mlp_w1": self.mlp[0].weight, "mlp_b1": self.mlp[0].bias,
+            "mlp_w2": self.mlp[3].weight, "mlp_b2": self.mlp[3].bias,
+        }
+
+    def prepared(self) -> torch.Tensor:
+        """Folded eval-mode parameters, rebuilt only when a tensor changed."""
+        ps = self._eval_params()
+        key = tuple((t.data_ptr(), t._version) for t in ps.values())
+        if self._prepared is None or key != self._prepared_key:
+            self._prepared = ops.lightpath_prepare(ps, self.norm1.module.eps, self.is_lut_index)
+            self._prepared_key = key
+        return self._prepared
+
+    def forward_device(self, data, out=None) -> ops.LightpathInferOut:
+        """Eval forward without any host synchronisation: returns capacity-sized device
+        buffers plus the device-side row count (CUDA-graph capturable)."""
+        gptr = ops.batch_graph_ptr(data)
+        eptr = getattr(data, "edge_ptr", None)
+        if eptr is None:
+            cache = ops.batch_cache(data)
+            if "eptr" not in cache:
+                cache["eptr"] = ops.edge_ptr(data.edge_index, data.batch, gptr.numel() - 1)
+            eptr = cache["eptr"][0]
+        return ops.lightpath_infer(data.x, data.edge_index, gptr, eptr, self.prepared(),
+                                   self.is_lut_index, out)
+
+    def _forward_eval(self, data):
+        self._check_supported()
+        res = self.forward_device(data)
+        if getattr(data, "edge_ptr", None) is not None:
+            n_lut = int(res.n_lut.item())
+        else:
+            # one D2H for both the row count and the "edges grouped by graph" check
+            n_lut, ungrouped = torch.cat([res.n_lut, ops.batch_cache(data)["eptr"][1]]).tolist()
+            if ungrouped:
+                return self._forward_general(data)   # CSR path handles any edge order
+        if n_lut == 0:
+            raise ValueError("No LUT node found in the batch.")
+        return res.out[:n_lut], res.lut_batch[:n_lut]
+
+    def _check_supported(self):
+        c = self.conv1
+        if (c.in_channels, c.out_channels, c.heads) != (5, 32, 4) or self.mlp[0].out_features != 32 \
+                or self.mlp[3].out_features != 3:
+            raise RuntimeError("libqot_b200 implements the reference LightpathGNN shape only: "
+                               "in_channels=5, hidden_channels=32, heads=4, output_dim=3")
+
+    # ----------------------------------------------------------- train/general
+    def _forward_general(self, data):
+        self._check_supported()
+        h = self.conv1(data.x, data.edge_index)
+        out, lut_batch = ops.lut_bn_head(
+            h, data.x, data.batch, self.is_lut_index, self.norm1.module,
+            self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias,
+            self.training, self.mlp[2].p if self.training else 0.0)
+        return out, lut_batch
+
+    def forward(self, data):
+        if not data.x.is_cuda:
+            raise RuntimeError("LightpathGNN (B200) needs the batch on a CUDA device; there is no CPU path")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.training or needs_grad:
+            return self._forward_general(data)
+        return self._forward_eval(data)

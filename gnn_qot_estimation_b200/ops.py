@@ -1,0 +1,601 @@
+"""Thin Python layer over the C ABI: tensor-in/tensor-out wrappers and the
+``torch.autograd.Function``s the two modules are assembled from.
+
+Every function here launches hand-written sm_100a kernels from libqot_b200.so on
+torch's current stream.  Nothing falls back to PyTorch ops for the arithmetic;
+torch only allocates the tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+EDGE_HID = 8          # QOT_EDGE_HID
+CSR_DROP_SELF = 1
+CSR_ADD_SELF = 2
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gnn_qot_estimation_b200 runs on CUDA tensors only (no CPU fallback): "
+                               "move the batch and the model to a B200 with .to('cuda')")
+
+
+def _f32(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def _i64(t):
+    return t if (t.dtype == torch.int64 and t.is_contiguous()) else t.to(torch.int64).contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# integer side
+# --------------------------------------------------------------------------- #
+class CSR(NamedTuple):
+    rowptr: torch.Tensor   # [N+1] int32
+    nbr: torch.Tensor      # [E'] int32 (source for by=1, destination for by=0)
+    eid: torch.Tensor      # [E'] int32 original edge id (E + node for appended self loops)
+    status: torch.Tensor   # [1] int32, non-zero on device when an index was out of range
+
+
+def build_csr(edge_index: torch.Tensor, num_nodes: int, by: int = 1, flags: int = 0) -> CSR:
+    """Stable CSR of ``edge_index`` grouped by row ``by`` (1 = destination)."""
+    _require_cuda(edge_index)
+    edge_index = _i64(edge_index)
+    E = int(edge_index.shape[1])
+    N = int(num_nodes)
+    dev = edge_index.device
+    Ep = E + (N if flags & CSR_ADD_SELF else 0)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(Ep, dtype=torch.int32, device=dev)
+    eid = torch.empty(Ep, dtype=torch.int32, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    nb = L.qot_csr_workspace_bytes(N, E)
+    ws = _lib.workspace(nb, dev)
+    check(L.qot_build_csr(ptr(edge_index), E, N, by, flags, ptr(rowptr), ptr(nbr), ptr(eid), ptr(status),
+                          ptr(ws), ws.numel(), stream()), "qot_build_csr")
+    return CSR(rowptr, nbr, eid, status)
+
+
+def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
+    _require_cuda(batch)
+    batch = _i64(batch)
+    out = torch.empty(num_graphs + 1, dtype=torch.int64, device=batch.device)
+    check(_lib.lib().qot_graph_ptr(ptr(batch), batch.numel(), num_graphs, ptr(out), stream()), "qot_graph_ptr")
+    return out
+
+
+def edge_ptr(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: int):
+    """Edge offsets per graph + a device status flag (non-zero when the edges are not
+    grouped by graph)."""
+    _require_cuda(edge_index, batch)
+    edge_index, batch = _i64(edge_index), _i64(batch)
+    out = torch.empty(num_graphs + 1, dtype=torch.int64, device=batch.device)
+    status = torch.empty(1, dtype=torch.int32, device=batch.device)
+    check(_lib.lib().qot_edge_ptr(ptr(edge_index), edge_index.shape[1], ptr(batch), batch.numel(),
+                                  num_graphs, ptr(out), ptr(status), stream()), "qot_edge_ptr")
+    return out, status
+
+
+def batch_num_graphs(data) -> int:
+    """``data.num_graphs`` when the batch object carries it (PyG's and ours do), else
+    ``batch.max()+1`` as the reference's global_mean_pool does (one host sync)."""
+    B = getattr(data, "num_graphs", None)
+    if B is None:
+        B = int(data.batch.max().item()) + 1 if data.batch.numel() else 0
+    return int(B)
+
+
+def batch_cache(data) -> dict:
+    """Per-batch cache of derived index structures (graph offsets, CSR, transposed
+    CSR) -- built once per batch object, shared by both conv layers and the backward."""
+    cache = getattr(data, "_cache", None)
+    if cache is None:
+        cache = {}
+        try:
+            setattr(data, "_cache", cache)
+        except Exception:   # foreign batch object refusing attributes: rebuild each call
+            pass
+    return cache
+
+
+def batch_graph_ptr(data) -> torch.Tensor:
+    cache = batch_cache(data)
+    if "gptr" in cache:
+        return cache["gptr"]
+    p = getattr(data, "ptr", None)
+    if p is None or not p.is_cuda or p.dtype != torch.int64:
+        p = graph_ptr(data.batch, batch_num_graphs(data))
+    cache["gptr"] = p.contiguous()
+    return cache["gptr"]
+
+
+# --------------------------------------------------------------------------- #
+# LightpathGNN fused inference
+# --------------------------------------------------------------------------- #
+def lightpath_prepare(params: dict, bn_eps: float, is_lut_index: int) -> torch.Tensor:
+    """Folds the eval-mode parameters (see qot_lightpath_prepare)."""
+    L = _lib.lib()
+    ts = {k: _f32(v.detach()) for k, v in params.items()}
+    _require_cuda(*ts.values())
+    st = _lib.QotLightpathParams(
+        ptr(ts["lin_w"]), ptr(ts["att_src"]), ptr(ts["att_dst"]), ptr(ts["conv_bias"]),
+        ptr(ts["bn_w"]), ptr(ts["bn_b"]), ptr(ts["bn_mean"]), ptr(ts["bn_var"]),
+        ptr(ts["mlp_w1"]), ptr(ts["mlp_b1"]), ptr(ts["mlp_w2"]), ptr(ts["mlp_b2"]),
+        float(bn_eps), int(is_lut_index))
+    out = torch.empty(L.qot_lightpath_prepared_floats(), dtype=torch.float32, device=ts["lin_w"].device)
+    check(L.qot_lightpath_prepare(C.byref(st), ptr(out), stream()), "qot_lightpath_prepare")
+    return out
+
+
+class LightpathInferOut(NamedTuple):
+    out: torch.Tensor         # [cap,3]; rows [0,L) valid
+    lut_batch: torch.Tensor   # [cap] int64
+    lut_node: torch.Tensor    # [cap] int32
+    n_lut: torch.Tensor       # [1] int32 on device
+
+
+def lightpath_infer(x, edge_index, gptr, eptr, prepared, is_lut_index: int,
+                    out: Optional[LightpathInferOut] = None) -> LightpathInferOut:
+    """Launches the fused eval forward; returns device buffers without any host sync."""
+    _require_cuda(x, edge_index, gptr, eptr, prepared)
+    x, edge_index = _f32(x), _i64(edge_index)
+    N, E, B = int(x.shape[0]), int(edge_index.shape[1]), int(gptr.numel() - 1)
+    dev = x.device
+    if out is None:
+        out = LightpathInferOut(torch.empty(max(N, 1), 3, dtype=torch.float32, device=dev),
+                                torch.empty(max(N, 1), dtype=torch.int64, device=dev),
+                                torch.empty(max(N, 1), dtype=torch.int32, device=dev),
+                                torch.empty(1, dtype=torch.int32, device=dev))
+    L = _lib.lib()
+    ws = _lib.workspace(L.qot_lightpath_infer_workspace_bytes(N, B), dev)
+    check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), N, B, ptr(prepared),
+                                int(is_lut_index), ptr(out.out), ptr(out.lut_batch), ptr(out.lut_node),
+                                ptr(out.n_lut), ptr(ws), ws.numel(), stream()), "qot_lightpath_infer")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# graph index shared by the layers of one forward/backward
+# --------------------------------------------------------------------------- #
+class GraphIndex:
+    """Lazily built, cached index structures of one batch: the destination-sorted CSR
+    (forward), its GAT variant (self loops replaced) and the source-sorted transposed
+    CSR (deterministic scatter of the backward)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        _require_cuda(edge_index)
+        self.edge_index = _i64(edge_index)
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(edge_index.shape[1])
+        self._csr = self._csr_gat = self._csr_t = None
+
+    @property
+    def csr(self) -> CSR:
+        if self._csr is None:
+            self._csr = build_csr(self.edge_index, self.num_nodes, by=1, flags=0)
+        return self._csr
+
+    @property
+    def csr_gat(self) -> CSR:
+        if self._csr_gat is None:
+            self._csr_gat = build_csr(self.edge_index, self.num_nodes, by=1,
+                                      flags=CSR_DROP_SELF | CSR_ADD_SELF)
+        return self._csr_gat
+
+    @property
+    def csr_t(self) -> CSR:
+        if self._csr_t is None:
+            self._csr_t = build_csr(self.edge_index, self.num_nodes, by=0, flags=0)
+        return self._csr_t
+
+
+def batch_graph(data, num_nodes: int) -> GraphIndex:
+    cache = batch_cache(data)
+    g = cache.get("graph")
+    if g is None or g.num_nodes != num_nodes or g.edge_index.data_ptr() != data.edge_index.data_ptr():
+        g = GraphIndex(data.edge_index, num_nodes)
+        cache["graph"] = g
+    return g
+
+
+def _ws(nbytes, dev):
+    return _lib.workspace(nbytes, dev)
+
+
+# --------------------------------------------------------------------------- #
+# GATConv (general path)
+# --------------------------------------------------------------------------- #
+class _GatConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lin_w, att_src, att_dst, bias, graph: GraphIndex):
+        L = _lib.lib()
+        x = _f32(x)
+        N, dev = x.shape[0], x.device
+        csr = graph.csr_gat
+        need = any(t.requires_grad for t in (lin_w, att_src, att_dst, bias))
+        h = torch.empty(N, 128, dtype=torch.float32, device=dev)
+        z = torch.empty(N, 20, dtype=torch.float32, device=dev) if need else None
+        smax = torch.empty(N, 4, dtype=torch.float32, device=dev) if need else None
+        sden = torch.empty(N, 4, dtype=torch.float32, device=dev) if need else None
+        w, a_s, a_d, b = _f32(lin_w.detach()), _f32(att_src.detach()), _f32(att_dst.detach()), _f32(bias.detach())
+        check(L.qot_gat_fwd(ptr(x), ptr(csr.rowptr), ptr(csr.nbr), N, ptr(w), ptr(a_s), ptr(a_d), ptr(b),
+                            ptr(h), ptr(z), ptr(smax), ptr(sden), stream()), "qot_gat_fwd")
+        if need:
+            ctx.save_for_backward(x, w, a_s, a_d, z, smax, sden)
+            ctx.csr = csr
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        L = _lib.lib()
+        x, w, a_s, a_d, z, smax, sden = ctx.saved_tensors
+        csr = ctx.csr
+        N, dev = x.shape[0], x.device
+        dh = _f32(dh)
+        dW = torch.empty_like(w)
+        das = torch.empty_like(a_s)
+        dad = torch.empty_like(a_d)
+        db = torch.empty(128, dtype=torch.float32, device=dev)
+        ws = _ws(L.qot_gat_bwd_workspace_bytes(N), dev)
+        check(L.qot_gat_bwd(ptr(x), ptr(csr.rowptr), ptr(csr.nbr), N, ptr(w), ptr(a_s), ptr(a_d), ptr(z),
+                            ptr(smax), ptr(sden), ptr(dh), ptr(dW), ptr(das), ptr(dad), ptr(db),
+                            ptr(ws), ws.numel(), stream()), "qot_gat_bwd")
+        return None, dW, das, dad, db, None
+
+
+def gat_conv(x, graph: GraphIndex, lin_w, att_src, att_dst, bias) -> torch.Tensor:
+    _require_cuda(x, lin_w)
+    return _GatConvFn.apply(x, lin_w, att_src, att_dst, bias, graph)
+
+
+# --------------------------------------------------------------------------- #
+# BatchNorm statistics, LUT readout + MLP head
+# --------------------------------------------------------------------------- #
+def bn_batch_stats(h, running_mean=None, running_var=None, momentum: float = 0.1):
+    L = _lib.lib()
+    h = _f32(h)
+    N, C = h.shape
+    mean = torch.empty(C, dtype=torch.float32, device=h.device)
+    var = torch.empty(C, dtype=torch.float32, device=h.device)
+    ws = _ws(L.qot_bn_stats_workspace_bytes(N, C), h.device)
+    check(L.qot_bn_stats(ptr(h), N, C, ptr(mean), ptr(var), ptr(running_mean), ptr(running_var),
+                         float(momentum), ptr(ws), ws.numel(), stream()), "qot_bn_stats")
+    return mean, var
+
+
+def lut_select(x, batch, is_lut_index: int):
+    """Ordered LUT compaction; one host sync for the row count (the reference's
+    boolean indexing synchronises twice)."""
+    L = _lib.lib()
+    x = _f32(x)
+    N, F = x.shape
+    dev = x.device
+    node = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    lb = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    n_lut = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = _ws(L.qot_lut_select_workspace_bytes(N), dev)
+    check(L.qot_lut_select(ptr(x), N, F, int(is_lut_index), ptr(_i64(batch)), ptr(node), ptr(lb), ptr(n_lut),
+                           ptr(ws), ws.numel(), stream()), "qot_lut_select")
+    n = int(n_lut.item())
+    return node[:n], lb[:n], n
+
+
+class _LutHeadFn(torch.autograd.Function):
+    """BN(given statistics) -> ReLU -> LUT rows -> Linear -> LeakyReLU -> (dropout) -> Linear."""
+
+    @staticmethod
+    def forward(ctx, h, lut_node, mean, var, eps, bn_w, bn_b, W1, b1, W2, b2, hmask, batch_stats):
+        L = _lib.lib()
+        nL, dev = lut_node.numel(), h.device
+        y = torch.empty(nL, 128, dtype=torch.float32, device=dev)
+        hid = torch.empty(nL, 32, dtype=torch.float32, device=dev)
+        out = torch.empty(nL, 3, dtype=torch.float32, device=dev)
+        ts = [_f32(t.detach()) for t in (bn_w, bn_b, W1, b1, W2, b2)]
+        check(L.qot_lut_head_fwd(ptr(h), ptr(lut_node), nL, ptr(mean), ptr(var), float(eps), ptr(ts[0]), ptr(ts[1]),
+                                 ptr(ts[2]), ptr(ts[3]), ptr(ts[4]), ptr(ts[5]), ptr(hmask), ptr(y), ptr(hid),
+                                 ptr(out), stream()), "qot_lut_head_fwd")
+        ctx.save_for_backward(h, lut_node, mean, var, ts[0], ts[2], ts[4], y, hid, hmask)
+        ctx.eps, ctx.batch_stats = float(eps), bool(batch_stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        h, lut_node, mean, var, bn_w, W1, W2, y, hid, hmask = ctx.saved_tensors
+        dev = h.device
+        nL, (N, C) = lut_node.numel(), h.shape
+        dout = _f32(dout)
+        dy = torch.empty(nL, 128, dtype=torch.float32, device=dev)
+        dW1, db1 = torch.empty_like(W1), torch.empty(32, dtype=torch.float32, device=dev)
+        dW2, db2 = torch.empty_like(W2), torch.empty(3, dtype=torch.float32, device=dev)
+        ws = _ws(L.qot_lut_head_bwd_workspace_bytes(nL), dev)
+        check(L.qot_lut_head_bwd(ptr(dout), ptr(y), ptr(hid), ptr(hmask), nL, ptr(W1), ptr(W2), ptr(dy),
+                                 ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), ws.numel(), stream()),
+              "qot_lut_head_bwd")
+        dh = torch.empty_like(h)
+        dbn_w = torch.empty(C, dtype=torch.float32, device=dev)
+        dbn_b = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = _ws(L.qot_bn_bwd_workspace_bytes(N, nL, C), dev)
+        check(L.qot_bn_bwd_sparse(ptr(h), ptr(mean), ptr(var), ctx.eps, ptr(bn_w), ptr(dy), ptr(lut_node),
+                                  nL, N, C, int(ctx.batch_stats), ptr(dh), ptr(dbn_w), ptr(dbn_b),
+                                  ptr(ws), ws.numel(), stream()), "qot_bn_bwd_sparse")
+        return dh, None, None, None, None, dbn_w, dbn_b, dW1, db1, dW2, db2, None, None
+
+
+def lut_bn_head(h, x_feat, batch, is_lut_index, bn: torch.nn.BatchNorm1d, W1, b1, W2, b2,
+                training: bool, dropout_p: float = 0.0):
+    """norm1 -> relu -> LUT readout -> mlp of lightpath_training/models.py:31-43.
+    Raises ``ValueError("No LUT node found in the batch.")`` like the reference."""
+    _require_cuda(h, x_feat, batch)
+    lut_node, lut_batch, n = lut_select(x_feat, batch, is_lut_index)
+    if n == 0:
+        raise ValueError("No LUT node found in the batch.")
+    if training:
+        mean, var = bn_batch_stats(h.detach(), bn.running_mean, bn.running_var,
+                                   bn.momentum if bn.momentum is not None else 0.1)
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+    else:
+        mean, var = bn.running_mean, bn.running_var
+    hmask = None
+    if training and dropout_p > 0.0:
+        keep = 1.0 - dropout_p
+        hmask = (torch.rand(n, 32, device=h.device) < keep).to(torch.float32) / keep
+    out = _LutHeadFn.apply(_f32(h), lut_node, mean, var, bn.eps, bn.weight, bn.bias, W1, b1, W2, b2,
+                           hmask, training)
+    return out, lut_batch
+
+
+def batch_norm(x, bn: torch.nn.BatchNorm1d, training: bool):
+    raise NotImplementedError(
+        "stand-alone BatchNorm over all rows is not on the reference hot path: LightpathGNN fuses "
+        "norm1 with the LUT readout (ops.lut_bn_head)")
+
+
+# --------------------------------------------------------------------------- #
+# dense node-wise projection  y = x[ids] W^T + b   (exact fp32)
+# --------------------------------------------------------------------------- #
+def _ids_csr(ids: torch.Tensor, num_rows: int) -> CSR:
+    """CSR of positions grouped by id (deterministic embedding backward)."""
+    n = ids.numel()
+    pair = torch.stack([torch.arange(n, dtype=torch.int64, device=ids.device), ids])
+    # rows are ids (by=1 groups by the second row); the CSR may have more nodes than rows
+    return build_csr(pair, max(num_rows, n), by=1, flags=0)
+
+
+class _NodeLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids, W, b):
+        L = _lib.lib()
+        x = _f32(x)
+        W_ = _f32(W.detach())
+        b_ = _f32(b.detach()) if b is not None else None
+        M = ids.numel() if ids is not None else x.shape[0]
+        K, Nc = x.shape[1], W_.shape[0]
+        y = torch.empty(M, Nc, dtype=torch.float32, device=x.device)
+        check(L.qot_gemm(ptr(x), K, 1, ptr(ids), ptr(W_), 1, K, ptr(b_), ptr(y), Nc, M, Nc, K, stream()),
+              "qot_gemm")
+        ctx.save_for_backward(x, ids, W_)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, ids, W = ctx.saved_tensors
+        dy = _f32(dy)
+        dev = dy.device
+        M, Nc = dy.shape
+        K = W.shape[1]
+        dx = dW = db = None
+        need_x, _, need_w, need_b = ctx.needs_input_grad
+        if need_x:
+            dxr = torch.empty(M, K, dtype=torch.float32, device=dev)        # dy @ W
+            check(L.qot_gemm(ptr(dy), Nc, 1, None, ptr(W), K, 1, None, ptr(dxr), K, M, K, Nc, stream()), "qot_gemm")
+            if ids is None:
+                dx = dxr
+            else:
+                V = x.shape[0]
+                csr = _ids_csr(ids, V)
+                dx = torch.empty(V, K, dtype=torch.float32, device=dev)
+                check(L.qot_segment_sum(ptr(dxr), ptr(csr.rowptr), ptr(csr.eid), V, K, ptr(dx), stream()),
+                      "qot_segment_sum")
+        if need_w:
+            xr = x if ids is None else _gather_rows(x, ids)
+            dW = torch.empty(Nc, K, dtype=torch.float32, device=dev)         # dy^T @ x
+            ws = _ws(L.qot_wgrad_workspace_bytes(M, Nc, K), dev)
+            check(L.qot_wgrad(ptr(dy), Nc, ptr(xr), K, M, Nc, K, ptr(dW), K, ptr(ws), ws.numel(), stream()),
+                  "qot_wgrad")
+        if need_b and ctx.has_bias:
+            db = torch.empty(Nc, dtype=torch.float32, device=dev)
+            ws = _ws(L.qot_colsum_workspace_bytes(M, Nc), dev)
+            check(L.qot_colsum(ptr(dy), Nc, M, Nc, ptr(db), ptr(ws), ws.numel(), stream()), "qot_colsum")
+        return dx, None, dW, db
+
+
+def _gather_rows(x, ids):
+    """x[ids] through the gemm kernel's gather path with an identity right operand would
+    waste flops; a [K,K] identity product is still tiny at K<=256, and keeps the arithmetic
+    in libqot_b200."""
+    L = _lib.lib()
+    K = x.shape[1]
+    eye = torch.eye(K, dtype=torch.float32, device=x.device)
+    out = torch.empty(ids.numel(), K, dtype=torch.float32, device=x.device)
+    check(L.qot_gemm(ptr(x), K, 1, ptr(ids), ptr(eye), K, 1, None, ptr(out), K, ids.numel(), K, K, stream()),
+          "qot_gemm")
+    return out
+
+
+def node_linear(x, W, b=None, ids=None):
+    _require_cuda(x, W)
+    return _NodeLinearFn.apply(x, _i64(ids) if ids is not None else None, W, b)
+
+
+# --------------------------------------------------------------------------- #
+# TransformerConv / NNConv edge phases
+# --------------------------------------------------------------------------- #
+class _TConvEdgeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkvs, edge_attr, We, graph: GraphIndex, slope: float):
+        L = _lib.lib()
+        N, H4 = qkvs.shape
+        H = H4 // 4
+        dev = qkvs.device
+        csr = graph.csr
+        edge_attr = _f32(edge_attr)
+        We_ = _f32(We.detach())
+        need = qkvs.requires_grad or We.requires_grad
+        out = torch.empty(N, H, dtype=torch.float32, device=dev)
+        E = graph.num_edges
+        logit = torch.empty(max(E, 1), dtype=torch.float32, device=dev) if need else None
+        rmax = torch.empty(max(N, 1), dtype=torch.float32, device=dev) if need else None
+        rden = torch.empty(max(N, 1), dtype=torch.float32, device=dev) if need else None
+        check(L.qot_tconv_fwd(ptr(qkvs), ptr(csr.rowptr), ptr(csr.nbr), ptr(csr.eid), ptr(edge_attr), ptr(We_),
+                              N, H, float(slope), ptr(out), ptr(logit), ptr(rmax), ptr(rden), stream()),
+              "qot_tconv_fwd")
+        if need:
+            ctx.save_for_backward(qkvs, edge_attr, We_, out, logit, rmax, rden)
+            ctx.graph, ctx.slope = graph, float(slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        qkvs, edge_attr, We, out, logit, rmax, rden = ctx.saved_tensors
+        g = ctx.graph
+        csr, csr_t = g.csr, g.csr_t
+        N, H4 = qkvs.shape
+        H, E, dev = H4 // 4, g.num_edges, qkvs.device
+        dout = _f32(dout)
+        dqkvs = torch.empty_like(qkvs)
+        dWe = torch.empty_like(We)
+        ws = _ws(L.qot_tconv_bwd_workspace_bytes(N, E, H), dev)
+        check(L.qot_tconv_bwd(ptr(qkvs), ptr(csr.rowptr), ptr(csr.nbr), ptr(csr.eid), ptr(csr_t.rowptr),
+                              ptr(csr_t.nbr), ptr(csr_t.eid), ptr(edge_attr), ptr(We), ptr(out), ptr(dout),
+                              ptr(logit), ptr(rmax), ptr(rden), N, E, H, ctx.slope, ptr(dqkvs), ptr(dWe),
+                              ptr(ws), ws.numel(), stream()), "qot_tconv_bwd")
+        return dqkvs, None, dWe, None, None
+
+
+def transformer_conv(x, node_ids, graph: GraphIndex, edge_attr, Wq, bq, Wk, bk, Wv, bv, We, Ws, bs,
+                     slope: float = 1.0):
+    """TransformerConv (+ fused embedding lookup when ``node_ids`` is given and ``x`` is
+    the embedding table; + fused leaky_relu when slope != 1)."""
+    Wcat = torch.cat([Wq, Wk, Wv, Ws], dim=0)          # [4H,H]; autograd splits the gradient
+    bcat = torch.cat([bq, bk, bv, bs], dim=0)
+    qkvs = node_linear(x, Wcat, bcat, ids=node_ids)
+    return _TConvEdgeFn.apply(qkvs, edge_attr, We, graph, slope)
+
+
+class _NNConvEdgeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, yr, edge_attr, W1, b1, bias, graph: GraphIndex, slope: float):
+        L = _lib.lib()
+        N = yr.shape[0]
+        H = yr.shape[1] // (EDGE_HID + 2)
+        dev = yr.device
+        csr = graph.csr
+        edge_attr = _f32(edge_attr)
+        W1_, b1_, bias_ = _f32(W1.detach()), _f32(b1.detach()), _f32(bias.detach())
+        out = torch.empty(N, H, dtype=torch.float32, device=dev)
+        check(L.qot_nnconv_fwd(ptr(yr), ptr(csr.rowptr), ptr(csr.nbr), ptr(csr.eid), ptr(edge_attr), ptr(W1_),
+                               ptr(b1_), ptr(bias_), N, H, float(slope), ptr(out), stream()), "qot_nnconv_fwd")
+        ctx.save_for_backward(yr, edge_attr, W1_, b1_, out)
+        ctx.graph, ctx.slope = graph, float(slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        yr, edge_attr, W1, b1, out = ctx.saved_tensors
+        g = ctx.graph
+        csr, csr_t = g.csr, g.csr_t
+        N = yr.shape[0]
+        H = yr.shape[1] // (EDGE_HID + 2)
+        E, dev = g.num_edges, yr.device
+        dout = _f32(dout)
+        dyr = torch.empty_like(yr)
+        dW1, db1 = torch.empty_like(W1), torch.empty_like(b1)
+        dbias = torch.empty(H, dtype=torch.float32, device=dev)
+        ws = _ws(L.qot_nnconv_bwd_workspace_bytes(N, E, H), dev)
+        check(L.qot_nnconv_bwd(ptr(yr), ptr(csr.rowptr), ptr(csr.nbr), ptr(csr.eid), ptr(csr_t.rowptr),
+                               ptr(csr_t.nbr), ptr(csr_t.eid), ptr(edge_attr), ptr(W1), ptr(b1), ptr(out),
+                               ptr(dout), N, E, H, ctx.slope, ptr(dyr), ptr(dW1), ptr(db1), ptr(dbias),
+                               ptr(ws), ws.numel(), stream()), "qot_nnconv_bwd")
+        return dyr, None, dW1, db1, dbias, None, None
+
+
+def nnconv_mean(x, graph: GraphIndex, edge_attr, W1, b1, W2, b2, Wroot, bias, slope: float = 1.0):
+    """NNConv(aggr='mean') in factorised form: one node-wise projection
+    yr = x [P_0 .. P_7 | P_b | Wroot^T]  then the edge kernel."""
+    H = x.shape[1]
+    K = EDGE_HID
+    # Pcat[i, k*H+o] = W2[i*H+o, k];  slab K: b2[i*H+o];  slab K+1: Wroot[o,i]   (tensor
+    # reshuffles only -- autograd routes dPcat back to W2 / b2 / Wroot)
+    Pcat = torch.cat([W2.view(H, H, K).permute(0, 2, 1).reshape(H, K * H), b2.view(H, H), Wroot.t()], dim=1)
+    yr = node_linear(x, Pcat.t().contiguous(), None)      # W argument is [out,in]
+    return _NNConvEdgeFn.apply(yr, edge_attr, W1, b1, bias, graph, slope)
+
+
+# --------------------------------------------------------------------------- #
+# global_mean_pool + MLP head
+# --------------------------------------------------------------------------- #
+class _PoolMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gptr, W1, b1, W2, b2, hmask):
+        L = _lib.lib()
+        x = _f32(x)
+        N, H = x.shape
+        B, dev = gptr.numel() - 1, x.device
+        ts = [_f32(t.detach()) for t in (W1, b1, W2, b2)]
+        pooled = torch.empty(B, H, dtype=torch.float32, device=dev)
+        hid = torch.empty(B, H, dtype=torch.float32, device=dev)
+        out = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        check(L.qot_pool_mlp_fwd(ptr(x), ptr(gptr), B, H, ptr(ts[0]), ptr(ts[1]), ptr(ts[2]), ptr(ts[3]),
+                                 ptr(hmask), ptr(pooled), ptr(hid), ptr(out), stream()), "qot_pool_mlp_fwd")
+        ctx.save_for_backward(gptr, ts[0], ts[2], pooled, hid, hmask)
+        ctx.N = N
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        gptr, W1, W2, pooled, hid, hmask = ctx.saved_tensors
+        B, H = pooled.shape
+        dev, N = pooled.device, ctx.N
+        dout = _f32(dout)
+        dx = torch.empty(N, H, dtype=torch.float32, device=dev)
+        dW1, db1 = torch.empty_like(W1), torch.empty(H, dtype=torch.float32, device=dev)
+        dW2, db2 = torch.empty_like(W2), torch.empty(3, dtype=torch.float32, device=dev)
+        ws = _ws(L.qot_pool_mlp_bwd_workspace_bytes(B, H), dev)
+        check(L.qot_pool_mlp_bwd(ptr(dout), ptr(pooled), ptr(hid), ptr(hmask), ptr(gptr), N, B, H, ptr(W1),
+                                 ptr(W2), ptr(dx), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), ws.numel(),
+                                 stream()), "qot_pool_mlp_bwd")
+        return dx, None, dW1, db1, dW2, db2, None
+
+
+def pool_mlp(x, gptr, W1, b1, W2, b2, training: bool = False, dropout_p: float = 0.0):
+    """global_mean_pool -> Linear -> LeakyReLU -> Dropout -> Linear
+    (topological_training/models.py:61-63)."""
+    _require_cuda(x, gptr)
+    hmask = None
+    if training and dropout_p > 0.0:
+        keep = 1.0 - dropout_p
+        hmask = (torch.rand(gptr.numel() - 1, x.shape[1], device=x.device) < keep).to(torch.float32) / keep
+    if W2.shape[0] != 3:
+        raise RuntimeError("libqot_b200 pool_mlp: out_channels must be 3 (osnr, snr, ber)")
+    return _PoolMlpFn.apply(x, gptr, W1, b1, W2, b2, hmask)
+
+
+def mean_pool(x, gptr):
+    """global_mean_pool alone: segment mean via the pooling kernel's first phase."""
+    raise NotImplementedError("stand-alone global_mean_pool is fused with the MLP head (ops.pool_mlp)")

@@ -1,0 +1,62 @@
+"""TopologicalGNN on the B200 kernels -- drop-in for topological_training/models.py:6-64.
+
+Same constructor (``num_nodes, hidden_channels, out_channels, edge_dim, dropout_p``),
+``forward(data) -> [B,3]`` and state_dict names as the shipped checkpoint
+(``node_embeddings.weight``, ``conv1.lin_*``, ``conv2.nn.0/2.*``, ``conv2.lin.weight``,
+``conv2.bias``, ``mlp.0/3.*``), so ``topological_training/test.py:69`` loads
+``models/model_N.pth`` with strict=True.
+
+Launch chain per forward: CSR build (once per batch, cached) -> [embedding +
+q|k|v|skip projection] -> TransformerConv edge kernel (+leaky_relu) -> NNConv
+projection -> NNConv edge kernel (+leaky_relu) -> pool + MLP head.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Dropout, LeakyReLU, Linear, ReLU
+from torch.nn import Sequential as Seq
+
+from .. import ops
+from ..nn import NNConv, TransformerConv
+
+LEAKY = 0.01   # F.leaky_relu default slope (models.py:54,58)
+
+
+class TopologicalGNN(torch.nn.Module):
+    def __init__(self, num_nodes, hidden_channels, out_channels, edge_dim, dropout_p=0.5):
+        super().__init__()
+        self.node_embeddings = torch.nn.Embedding(num_nodes, hidden_channels)
+        self.conv1 = TransformerConv(hidden_channels, hidden_channels, edge_dim=edge_dim)
+        nn = Seq(
+            Linear(edge_dim, edge_dim * 2),
+            ReLU(),
+            Linear(edge_dim * 2, hidden_channels * hidden_channels),
+        )
+        self.conv2 = NNConv(in_channels=hidden_channels, out_channels=hidden_channels, nn=nn, aggr="mean")
+        self.mlp = torch.nn.Sequential(
+            Linear(hidden_channels, hidden_channels),
+            LeakyReLU(),
+            Dropout(p=dropout_p),
+            Linear(hidden_channels, out_channels),
+        )
+        self.dropout = torch.nn.Dropout(p=dropout_p)
+
+    def forward(self, data):
+        x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
+        if not edge_index.is_cuda:
+            raise RuntimeError("TopologicalGNN (B200) needs the batch on a CUDA device; there is no CPU path")
+        node_ids = None
+        if x is None or x.numel() == 0:            # models.py:51-52: embedding branch
+            x, node_ids = self.node_embeddings.weight, data.node_ids
+            n = int(node_ids.shape[0])
+        else:
+            n = int(x.shape[0])
+        graph = ops.batch_graph(data, n)
+        x = self.conv1(x, edge_index, edge_attr, graph=graph, node_ids=node_ids, slope=LEAKY)
+        x = self.dropout(x)
+        x = self.conv2(x, edge_index, edge_attr, graph=graph, slope=LEAKY)
+        x = self.dropout(x)
+        gptr = ops.batch_graph_ptr(data)
+        return ops.pool_mlp(x, gptr, self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight,
+                            self.mlp[3].bias, self.training, self.mlp[2].p)

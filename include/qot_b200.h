@@ -1,0 +1,315 @@
+/*
+ * qot_b200.h -- C ABI of libqot_b200.so: the B200 (sm_100a) kernels behind the
+ * message-passing hot path of santiagolmedo/gnn_qot_estimation.
+ *
+ * The reference has no FFI: its "plugin API" for this path is the Python
+ * nn.Module contract of TopologicalGNN (topological_training/models.py:6-64) and
+ * LightpathGNN (lightpath_training/models.py:7-45), whose arithmetic lives in
+ * PyTorch Geometric layers.  Each entry point below replaces the PyG call named
+ * in its comment; gnn_qot_estimation_b200/ binds them with ctypes and keeps the
+ * reference's module names/constructors/forward(data) on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates, frees or retains memory;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises, so every call is CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = QOT_E_* ; qot_last_error() gives a thread-local
+ *     message for the most recent failure on the calling thread;
+ *   - features are fp32, API indices int64 (as the reference tensors are), internal
+ *     CSR indices int32;
+ *   - results are deterministic: segments are sorted, reductions have a fixed
+ *     order, no floating-point atomics anywhere.
+ */
+#ifndef QOT_B200_H_
+#define QOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QOT_OK 0
+#define QOT_E_BADARG (-1)      /* null pointer / negative size / unsupported shape */
+#define QOT_E_WORKSPACE (-2)   /* workspace too small */
+#define QOT_E_CUDA (-3)        /* a CUDA runtime call or launch failed */
+
+#define QOT_EDGE_DIM 4         /* edge_attr width (topological_training/train.py:52) */
+#define QOT_EDGE_HID 8         /* edge-MLP hidden = 2*edge_dim (models.py:21)        */
+#define QOT_GAT_IN 5           /* lightpath node features (lightpath dataset.py:45)  */
+#define QOT_GAT_HEADS 4        /* lightpath_training/models.py:13                    */
+#define QOT_GAT_C 32           /* hidden_channels per head (train.py:52)             */
+#define QOT_GAT_HC 128         /* heads * C                                          */
+#define QOT_OUT 3              /* osnr, snr, ber                                     */
+
+const char* qot_last_error(void);
+int qot_version(void);
+
+/* ------------------------------------------------------------------------ */
+/* (1) collate + CSR: replaces torch_geometric.loader.DataLoader's            */
+/*     Batch.from_data_list (topological_training/train.py:93-95,             */
+/*     lightpath_training/train.py:94-96) and the scatter-by-index inside     */
+/*     PyG's MessagePassing.propagate.                                        */
+/* ------------------------------------------------------------------------ */
+
+/* A packed graph store (all graphs of a dataset, flat arrays in HBM). */
+typedef struct {
+  const int64_t* node_ptr;   /* [G+1] node offsets                              */
+  const int64_t* edge_ptr;   /* [G+1] directed-edge offsets                     */
+  const int32_t* edge_src;   /* [E_tot] graph-local source id                   */
+  const int32_t* edge_dst;   /* [E_tot] graph-local target id                   */
+  const float* node_feat;    /* [N_tot, node_dim] or NULL (topological: x=None) */
+  const float* edge_feat;    /* [E_tot, edge_dim] or NULL (lightpath)           */
+  const float* y;            /* [G, y_dim]                                      */
+  int32_t node_dim, edge_dim, y_dim;
+} qot_store_t;
+
+/* Collate `B` graphs `graph_ids[b]` of the store into one batch.
+ * out_ptr/out_eptr [B+1] int64 must already hold the batch-local node / edge
+ * offsets (the host owns a copy of node_ptr/edge_ptr and computes them while
+ * sizing the outputs -- no device->host sync).  Writes
+ *   x [N,node_dim], edge_index [2,E] int64 (offset by the running node count),
+ *   edge_attr [E,edge_dim], batch [N] int64, node_ids [N] int64 (0..n_g-1 per
+ *   graph, topological_training/dataset.py:78), y [B,y_dim].
+ * Any output pointer may be NULL to skip it. */
+int qot_collate(const qot_store_t* store, const int64_t* graph_ids, int64_t B,
+                const int64_t* out_ptr, const int64_t* out_eptr, int64_t N, int64_t E,
+                float* x, int64_t* edge_index, float* edge_attr, int64_t* batch,
+                int64_t* node_ids, float* y, void* stream);
+
+/* Workspace for qot_build_csr / qot_lightpath_infer etc. */
+size_t qot_csr_workspace_bytes(int64_t N, int64_t E);
+
+/* Group the E edges of edge_index [2,E] (int64) by row `by` (1 = by destination,
+ * the forward CSR; 0 = by source, the transposed CSR the backward kernels use),
+ * STABLE in the original edge order.  flags: bit0 = drop self loops, bit1 = append
+ * one self loop per node as the last entry of its row (GATConv's
+ * remove_self_loops + add_self_loops; appended loops get eid = E + node).
+ *   rowptr [N+1] int32, nbr [E'] int32 (the other endpoint), eid [E'] int32
+ *   (original edge id), E' <= E + N.
+ * status (optional, int32[1]) is set non-zero on device if an index is out of
+ * range [0,N). */
+int qot_build_csr(const int64_t* edge_index, int64_t E, int64_t N, int by, int flags,
+                  int32_t* rowptr, int32_t* nbr, int32_t* eid, int32_t* status,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* gptr [B+1] int64 from a sorted `batch` [N] (== PyG Batch.ptr): gptr[g] = first
+ * node whose graph id is >= g. */
+int qot_graph_ptr(const int64_t* batch, int64_t N, int64_t B, int64_t* gptr, void* stream);
+
+/* eptr [B+1] int64: first edge whose source node lies in a graph >= g.  Valid when
+ * the edges of edge_index [2,E] are grouped by graph in ascending order (every
+ * collate emits them so); status[0] (int32) is set non-zero otherwise. */
+int qot_edge_ptr(const int64_t* edge_index, int64_t E, const int64_t* batch, int64_t N,
+                 int64_t B, int64_t* eptr, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* dense node-wise projections (FP32-exact FFMA tiles)                        */
+/* ------------------------------------------------------------------------ */
+
+/* C[M,Nc] (ldc) = op(A)[M,K] * op(B)[K,Nc] (+ bias[Nc]) with arbitrary element
+ * strides: A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
+ * gather (optional int64 [M]): row m of A is read at row gather[m] (embedding
+ * lookup, topological_training/models.py:52).  Replaces the addmm calls inside
+ * TransformerConv / NNConv. */
+int qot_gemm(const float* A, int64_t a_rs, int64_t a_cs, const int64_t* gather,
+             const float* B, int64_t b_rs, int64_t b_cs, const float* bias,
+             float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, void* stream);
+
+/* Deterministic weight gradient: C[Mo,No] (ldc) = sum_r A[r,Mo]^T * B[r,No] over
+ * R rows (row-major A [R,lda], B [R,ldb]); two-stage fixed-order reduction.
+ * gather (optional int64 [R]) scatters by row: C[gather[r], :] += B[r, :] is NOT
+ * supported here -- see qot_embedding_bwd. */
+size_t qot_wgrad_workspace_bytes(int64_t R, int64_t Mo, int64_t No);
+int qot_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t R,
+              int64_t Mo, int64_t No, float* C, int64_t ldc,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* colsum[Nc] = sum_r A[r, :Nc]  (bias gradients), fixed order. */
+size_t qot_colsum_workspace_bytes(int64_t R, int64_t Nc);
+int qot_colsum(const float* A, int64_t lda, int64_t R, int64_t Nc, float* out,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* out[r,:] = sum over p in [rowptr[r],rowptr[r+1]) of X[idx[p],:]  (H % 4 == 0).
+ * With the CSR of node_ids this is the deterministic embedding backward
+ * (topological_training/models.py:52): dEmb[v] = sum of dX rows whose id is v. */
+int qot_segment_sum(const float* X, const int32_t* rowptr, const int32_t* idx, int64_t R,
+                    int64_t H, float* out, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* (2) TransformerConv edge phase (topological_training/models.py:15-17,53)   */
+/* ------------------------------------------------------------------------ */
+/* qkvs [N,4H] = [q | k | v | skip] node projections (qot_gemm).  For each
+ * destination row i of the CSR:  a_ij = q_i.(k_j + We a_ij)/sqrt(H);
+ * alpha = softmax_i(a) (denominator + 1e-16);  out_i = sum alpha (v_j + We a_ij)
+ * + skip_i;  then leaky_relu(slope) if slope != 1  (models.py:54).
+ * Saves logit [E'] (CSR order), rmax [N], rden [N] for the backward when non-NULL. */
+int qot_tconv_fwd(const float* qkvs, const int32_t* rowptr, const int32_t* src,
+                  const int32_t* eid, const float* edge_attr, const float* We,
+                  int64_t N, int64_t H, float slope, float* out, float* logit,
+                  float* rmax, float* rden, void* stream);
+
+/* Backward of qot_tconv_fwd.  dout [N,H] is the gradient w.r.t. the activated
+ * output; `out` is the saved activated output (for the leaky_relu mask).
+ * Produces dqkvs [N,4H] (gradient of the node projections) and dWe [H,4].
+ * Needs the transposed CSR (t_rowptr/t_dst/t_eid from qot_build_csr(by=0)) and
+ * pos_of_eid [E] (CSR slot of each original edge). */
+size_t qot_tconv_bwd_workspace_bytes(int64_t N, int64_t E, int64_t H);
+int qot_tconv_bwd(const float* qkvs, const int32_t* rowptr, const int32_t* src,
+                  const int32_t* eid, const int32_t* t_rowptr, const int32_t* t_dst,
+                  const int32_t* t_eid, const float* edge_attr, const float* We,
+                  const float* out, const float* dout, const float* logit,
+                  const float* rmax, const float* rden, int64_t N, int64_t E, int64_t H,
+                  float slope, float* dqkvs, float* dWe,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* (2) NNConv(aggr=mean) edge phase (topological_training/models.py:20-30,57) */
+/* ------------------------------------------------------------------------ */
+/* Factorised form:  yr [N,(K+2)H], K = QOT_EDGE_HID:
+ * slabs k<K: x P_k, slab K: x P_b (bias of the edge MLP's last layer), slab K+1:
+ * x Wroot^T.  out_i = mean_j sum_k hh_e[k] yr[j,k,:] + yr[i,K+1,:] + bias, with
+ * hh_e = [relu(W1 a_e + b1), 1]; then leaky_relu(slope). */
+int qot_nnconv_fwd(const float* yr, const int32_t* rowptr, const int32_t* src,
+                   const int32_t* eid, const float* edge_attr, const float* W1,
+                   const float* b1, const float* bias, int64_t N, int64_t H, float slope,
+                   float* out, void* stream);
+
+/* Backward: dyr [N,(K+2)H], dW1 [K,4], db1 [K], dbias [H]. */
+size_t qot_nnconv_bwd_workspace_bytes(int64_t N, int64_t E, int64_t H);
+int qot_nnconv_bwd(const float* yr, const int32_t* rowptr, const int32_t* src,
+                   const int32_t* eid, const int32_t* t_rowptr, const int32_t* t_dst,
+                   const int32_t* t_eid, const float* edge_attr, const float* W1,
+                   const float* b1, const float* out, const float* dout,
+                   int64_t N, int64_t E, int64_t H, float slope,
+                   float* dyr, float* dW1, float* db1, float* dbias,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* (3) global_mean_pool + MLP head (topological_training/models.py:33-38,61-63) */
+/* ------------------------------------------------------------------------ */
+/* pooled [B,H] (saved for backward), hid [B,H] pre-activation (saved), out [B,3].
+ * head: Linear(H,H) - LeakyReLU(0.01) - Linear(H,3). */
+int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t B, int64_t H,
+                     const float* W1, const float* b1, const float* W2, const float* b2,
+                     const float* hmask, float* pooled, float* hid, float* out, void* stream);
+
+size_t qot_pool_mlp_bwd_workspace_bytes(int64_t B, int64_t H);
+/* dx [N,H] (every node of graph g gets dpooled_g / n_g), dW1,db1,dW2,db2.
+ * hmask (optional [B,H]) = dropout keep-mask/scale applied to the hidden
+ * activation (NULL = none). */
+int qot_pool_mlp_bwd(const float* dout, const float* pooled, const float* hid,
+                     const float* hmask, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
+                     const float* W1, const float* W2, float* dx,
+                     float* dW1, float* db1, float* dW2, float* db2,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* LightpathGNN (lightpath_training/models.py:7-45)                           */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+  const float* lin_w;      /* conv1.lin.weight [128,5]        */
+  const float* att_src;    /* conv1.att_src    [4,32]         */
+  const float* att_dst;    /* conv1.att_dst    [4,32]         */
+  const float* conv_bias;  /* conv1.bias       [128]          */
+  const float* bn_w;       /* norm1.module.weight [128]       */
+  const float* bn_b;       /* norm1.module.bias   [128]       */
+  const float* bn_mean;    /* running_mean [128]              */
+  const float* bn_var;     /* running_var  [128]              */
+  const float* mlp_w1;     /* mlp.0.weight [32,128]           */
+  const float* mlp_b1;     /* mlp.0.bias   [32]               */
+  const float* mlp_w2;     /* mlp.3.weight [3,32]             */
+  const float* mlp_b2;     /* mlp.3.bias   [3]                */
+  float bn_eps;            /* 1e-5                            */
+  int32_t is_lut_index;    /* column of x holding the LUT flag */
+} qot_lightpath_params_t;
+
+/* Fused eval-mode forward: GATConv -> BatchNorm(running stats) -> ReLU -> LUT
+ * readout -> MLP (lightpath_training/models.py:26-45 under model.eval()).
+ * Graph-parallel: graph g owns nodes [gptr[g],gptr[g+1]) and edges
+ * [eptr[g],eptr[g+1]) of edge_index (as every collate produces them).  Only the
+ * rows the readout keeps (LUT nodes) are evaluated -- same values as computing
+ * all rows and selecting.  Outputs are written in ascending node order:
+ *   out [L,3], lut_batch [L] int64 (graph id), lut_node [L] int32, and
+ *   n_lut[0] = L (int32, device).  Capacity of out/lut_batch/lut_node = N rows.
+ * ws: qot_lightpath_infer_workspace_bytes(N,B). */
+size_t qot_lightpath_infer_workspace_bytes(int64_t N, int64_t B);
+/* Folds the parameters once per weight update (attention vectors through lin_w,
+ * conv bias + BatchNorm running stats into one scale/shift, transposed MLP) into
+ * `prepared` (qot_lightpath_prepared_floats() floats). */
+size_t qot_lightpath_prepared_floats(void);
+int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream);
+int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
+                        const int64_t* gptr, const int64_t* eptr, int64_t N, int64_t B,
+                        const float* prepared, int32_t is_lut_index, float* out,
+                        int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* General GATConv forward over a destination-sorted CSR built with flags=3
+ * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.
+ * Optional saves for the backward: z [N,4,5] = sum_j alpha_ij x_j per head, and the
+ * softmax statistics smax [N,4], sden [N,4] (denominator incl. the 1e-16). */
+int qot_gat_fwd(const float* x, const int32_t* rowptr, const int32_t* src, int64_t N,
+                const float* lin_w, const float* att_src, const float* att_dst,
+                const float* conv_bias, float* h, float* z, float* smax, float* sden,
+                void* stream);
+
+/* Backward of qot_gat_fwd w.r.t. its parameters (x carries no gradient: it is the
+ * dataset input, lightpath_training/models.py:27): d_lin_w [128,5], d_att_src
+ * [4,32], d_att_dst [4,32], d_bias [128]. */
+size_t qot_gat_bwd_workspace_bytes(int64_t N);
+int qot_gat_bwd(const float* x, const int32_t* rowptr, const int32_t* src, int64_t N,
+                const float* lin_w, const float* att_src, const float* att_dst,
+                const float* z, const float* smax, const float* sden, const float* dh,
+                float* d_lin_w, float* d_att_src, float* d_att_dst, float* d_bias,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* BatchNorm1d training statistics over the node dimension: mean [C], var [C]
+ * (biased); per-chunk (mean, M2) combined in a fixed order.  When running_mean /
+ * running_var are given they are updated in place with `momentum` (unbiased
+ * variance), as torch.nn.BatchNorm1d does in train(). */
+size_t qot_bn_stats_workspace_bytes(int64_t N, int64_t C);
+int qot_bn_stats(const float* h, int64_t N, int64_t C, float* mean, float* var,
+                 float* running_mean, float* running_var, float momentum,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* Ordered LUT compaction: lut_node [L] int32 ascending, lut_batch [L] int64
+ * (optional), n_lut[0] = L  (lightpath_training/models.py:35-40). */
+size_t qot_lut_select_workspace_bytes(int64_t N);
+int qot_lut_select(const float* x, int64_t N, int64_t F, int32_t is_lut_index,
+                   const int64_t* batch, int32_t* lut_node, int64_t* lut_batch,
+                   int32_t* n_lut, void* ws, size_t ws_bytes, void* stream);
+
+/* LUT rows: y = relu(bn(h[lut_node])) with the given statistics; hid = W1 y + b1;
+ * out = W2 (leaky_relu(hid) * hmask) + b2.  hmask (optional [L,32]) is the dropout
+ * keep-mask already divided by (1-p).  Saves y [L,128], hid [L,32] when non-NULL. */
+int qot_lut_head_fwd(const float* h, const int32_t* lut_node, int64_t L,
+                     const float* bn_mean, const float* bn_var, float bn_eps,
+                     const float* bn_w, const float* bn_b, const float* W1, const float* b1,
+                     const float* W2, const float* b2, const float* hmask, float* y,
+                     float* hid, float* out, void* stream);
+
+/* Backward of the head: dy [L,128] (gradient w.r.t. the BN output, ReLU mask
+ * applied), dW1 [32,128], db1 [32], dW2 [3,32], db2 [3]. */
+size_t qot_lut_head_bwd_workspace_bytes(int64_t L);
+int qot_lut_head_bwd(const float* dout, const float* y, const float* hid, const float* hmask,
+                     int64_t L, const float* W1, const float* W2, float* dy, float* dW1,
+                     float* db1, float* dW2, float* db2, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* BatchNorm backward with a row-sparse upstream gradient (only LUT rows carry dy).
+ * batch_stats=1 (train): dh [N,C] = g*invstd*(dy_n - mean(dy) - xhat_n*mean(dy*xhat));
+ * batch_stats=0 (running stats): dh = g*invstd*dy_n.  Also d_bn_w [C], d_bn_b [C]. */
+size_t qot_bn_bwd_workspace_bytes(int64_t N, int64_t L, int64_t C);
+int qot_bn_bwd_sparse(const float* h, const float* mean, const float* var, float eps,
+                      const float* bn_w, const float* dy, const int32_t* lut_node,
+                      int64_t L, int64_t N, int64_t C, int batch_stats, float* dh,
+                      float* d_bn_w, float* d_bn_b, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOT_B200_H_ */

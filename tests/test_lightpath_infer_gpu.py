@@ -1,0 +1,163 @@
+"""GPU parity: fused LightpathGNN eval forward (csrc/lightpath_infer.cu) through the
+drop-in module vs the oracle and the committed golden vectors.
+Tolerance: 1e-5 relative (BASELINE.json north_star), written below."""
+import pytest
+import torch
+
+from conftest import batch_from_dict, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _model(dev, sd=None):
+    from gnn_qot_estimation_b200 import LightpathGNN
+    m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m.to(dev).eval()
+
+
+def _oracle(sd, dtype=torch.float32):
+    from oracle import LightpathGNNOracle
+    m = LightpathGNNOracle(5, 32, 3, is_lut_index=1, dropout_p=0.0).to(dtype)
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def test_golden_vectors(cuda):
+    g = load_golden("lightpath_eval.pt")
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    b = batch_from_dict(g["batch"]).to(cuda)
+    with torch.no_grad():
+        out, lut_batch = m(b)
+    exp = g["expected"]["torch.float32"]
+    exp64 = g["expected"]["torch.float64"]
+    assert torch.equal(lut_batch.cpu(), exp["lut_batch"])                 # bit-exact indexing
+    assert out.shape == exp["out"].shape
+    assert rel_err(out, exp64["out"]) <= RTOL
+    assert rel_err(out, exp["out"]) <= RTOL
+    torch.testing.assert_close(out.cpu(), exp["out"], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("ckpt", ["ckpt_lightpath_model_0.pt", "ckpt_lightpath_model_1.pt", None])
+@pytest.mark.parametrize("num_graphs,lut_per_graph", [(1, 1), (33, 1), (512, 1), (257, 2)])
+def test_vs_oracle(cuda, ckpt, num_graphs, lut_per_graph):
+    from gnn_qot_estimation_b200 import synthetic
+    torch.manual_seed(3)
+    sd = load_golden(ckpt)["model_state_dict"] if ckpt else None
+    m = _model(cuda, sd)
+    if sd is None:   # random init incl. non-trivial BN stats
+        with torch.no_grad():
+            m.norm1.module.running_mean.normal_()
+            m.norm1.module.running_var.uniform_(0.5, 2.0)
+            m.conv1.bias.normal_()
+        sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    store = synthetic.lightpath_store(num_graphs, seed=11 + num_graphs, device="cpu", lut_per_graph=lut_per_graph)
+    hb = store.host_batch(0, num_graphs)
+    with torch.no_grad():
+        out, lut_batch = m(hb.to(cuda))
+        eo, el = _oracle(sd)(hb)
+        eo64, _ = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(lut_batch.cpu(), el)
+    assert rel_err(out, eo64) <= RTOL
+    torch.testing.assert_close(out.cpu(), eo, rtol=RTOL, atol=1e-6)
+
+
+def _to64(b):
+    bb = b.to("cpu")
+    bb.x = bb.x.double()
+    return bb
+
+
+def test_device_collate_path_equals_host_path(cuda):
+    """Batch built by the device-side collate == host-built batch, and the module gives
+    identical (bitwise) outputs on both; a batch WITHOUT edge_ptr/ptr (foreign collate)
+    goes through qot_graph_ptr/qot_edge_ptr and must agree too."""
+    from gnn_qot_estimation_b200 import Batch, synthetic
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    store = synthetic.lightpath_store(300, seed=5, device="cpu")
+    hb = store.host_batch(10, 290)
+    db = store.to(cuda).collate(range(10, 290))
+    for k in ("x", "edge_index", "batch", "y", "ptr", "edge_ptr"):
+        assert torch.equal(getattr(db, k).cpu(), getattr(hb, k)), k
+    with torch.no_grad():
+        o1, l1 = m(db)
+        o2, l2 = m(hb.to(cuda))
+        foreign = Batch(x=db.x, edge_index=db.edge_index, batch=db.batch)   # no ptr, no num_graphs
+        o3, l3 = m(foreign)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    assert torch.equal(o1, o3) and torch.equal(l1, l3)
+
+
+def test_no_lut_raises_value_error(cuda):
+    from gnn_qot_estimation_b200 import synthetic
+    m = _model(cuda)
+    store = synthetic.lightpath_store(8, seed=2, device="cpu")
+    b = store.host_batch(0, 8)
+    b.x[:, 1] = 0.0
+    with pytest.raises(ValueError, match="No LUT node found in the batch."):
+        with torch.no_grad():
+            m(b.to(cuda))
+
+
+def test_edge_cases(cuda):
+    """self loops in the input (GAT removes them), duplicate edges, isolated LUT node,
+    graphs with zero edges, graphs larger than one warp chunk."""
+    from gnn_qot_estimation_b200 import Batch
+    sd = load_golden("ckpt_lightpath_model_0.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    g = torch.Generator().manual_seed(0)
+    sizes = [1, 3, 70, 40, 2]
+    xs, eis, bts = [], [], []
+    off = 0
+    for gi, n in enumerate(sizes):
+        x = torch.rand(n, 5, generator=g)
+        x[:, 1] = 0.0
+        x[n // 2, 1] = 1.0
+        if gi == 2:
+            x[5, 1] = 1.0           # two LUT nodes in one graph, in different 32-chunks
+            x[66, 1] = 1.0
+        E = 0 if gi in (0, 4) else 6 * n
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = torch.randint(0, n, (E,), generator=g)   # includes self loops and duplicates
+        eis.append(torch.stack([src, dst]) + off)
+        xs.append(x)
+        bts.append(torch.full((n,), gi, dtype=torch.int64))
+        off += n
+    hb = Batch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=len(sizes))
+    with torch.no_grad():
+        out, lb = m(hb.to(cuda))
+        eo, el = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(lb.cpu(), el)
+    assert rel_err(out, eo) <= RTOL
+
+
+def test_ungrouped_edges_fall_back_to_csr_path(cuda):
+    """A batch whose edges are NOT grouped by graph is detected on device and routed
+    through the general CSR kernels; same answer."""
+    from gnn_qot_estimation_b200 import Batch, synthetic
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    store = synthetic.lightpath_store(40, seed=9, device="cpu")
+    hb = store.host_batch(0, 40)
+    perm = torch.randperm(hb.edge_index.shape[1], generator=torch.Generator().manual_seed(1))
+    shuffled = Batch(x=hb.x, edge_index=hb.edge_index[:, perm].contiguous(), batch=hb.batch, num_graphs=40)
+    with torch.no_grad():
+        out, lb = m(shuffled.to(cuda))
+        eo, el = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(lb.cpu(), el)
+    assert rel_err(out, eo) <= RTOL
+
+
+def test_deterministic(cuda):
+    from gnn_qot_estimation_b200 import synthetic
+    m = _model(cuda, load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"])
+    b = synthetic.lightpath_store(2000, seed=4, device="cpu").host_batch(0, 2000).to(cuda)
+    with torch.no_grad():
+        o1, _ = m(b)
+        o1 = o1.clone()
+        o2, _ = m(b)
+    assert torch.equal(o1, o2)
