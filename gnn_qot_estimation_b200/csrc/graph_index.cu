@@ -282,7 +282,8 @@ extern "C" int qot_build_csr(const int64_t* edge_index, int64_t E, int64_t N, in
   QOT_REQUIRE(N >= 0 && E >= 0, "qot_build_csr: negative size");
   QOT_REQUIRE(E + N < (1ll << 31) - 1, "qot_build_csr: E+N exceeds int32 CSR range");
   QOT_REQUIRE(by == 0 || by == 1, "qot_build_csr: by must be 0 (source) or 1 (destination)");
-  QOT_REQUIRE(rowptr && (E + N == 0 || (nbr && eid)), "qot_build_csr: null output");
+  const int64_t max_entries = E + ((flags & 2) ? N : 0);
+  QOT_REQUIRE(rowptr && (max_entries == 0 || (nbr && eid)), "qot_build_csr: null output");
   QOT_REQUIRE(E == 0 || edge_index, "qot_build_csr: null edge_index");
   QOT_REQUIRE(ws && ws_bytes >= qot_csr_workspace_bytes(N, E), "qot_build_csr: workspace too small");
   const int drop_self = flags & 1, add_self = (flags >> 1) & 1;

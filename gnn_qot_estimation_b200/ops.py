@@ -31,6 +31,12 @@ def _f32(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
 
 
+def _edge_attr(t):
+    """fp32 contiguous edge_attr; a zero-edge batch gets one dummy row so the pointer is not NULL."""
+    t = _f32(t)
+    return t if t.shape[0] else t.new_zeros(1, t.shape[1])
+
+
 def _i64(t):
     return t if (t.dtype == torch.int64 and t.is_contiguous()) else t.to(torch.int64).contiguous()
 
@@ -54,8 +60,8 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, by: int = 1, flags: int 
     dev = edge_index.device
     Ep = E + (N if flags & CSR_ADD_SELF else 0)
     rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    nbr = torch.empty(Ep, dtype=torch.int32, device=dev)
-    eid = torch.empty(Ep, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(Ep, 1), dtype=torch.int32, device=dev)[:Ep]    # never a NULL pointer
+    eid = torch.empty(max(Ep, 1), dtype=torch.int32, device=dev)[:Ep]
     status = torch.empty(1, dtype=torch.int32, device=dev)
     L = _lib.lib()
     nb = L.qot_csr_workspace_bytes(N, E)
@@ -451,7 +457,7 @@ class _TConvEdgeFn(torch.autograd.Function):
         H = H4 // 4
         dev = qkvs.device
         csr = graph.csr
-        edge_attr = _f32(edge_attr)
+        edge_attr = _edge_attr(edge_attr)
         We_ = _f32(We.detach())
         need = qkvs.requires_grad or We.requires_grad
         out = torch.empty(N, H, dtype=torch.float32, device=dev)
@@ -504,7 +510,7 @@ class _NNConvEdgeFn(torch.autograd.Function):
         H = yr.shape[1] // (EDGE_HID + 2)
         dev = yr.device
         csr = graph.csr
-        edge_attr = _f32(edge_attr)
+        edge_attr = _edge_attr(edge_attr)
         W1_, b1_, bias_ = _f32(W1.detach()), _f32(b1.detach()), _f32(bias.detach())
         out = torch.empty(N, H, dtype=torch.float32, device=dev)
         check(L.qot_nnconv_fwd(ptr(yr), ptr(csr.rowptr), ptr(csr.nbr), ptr(csr.eid), ptr(edge_attr), ptr(W1_),

