@@ -58,7 +58,7 @@ SIGNATURES = {
     "qot_pool_mlp_fwd": (C.c_int, [P, P, i64, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_pool_mlp_bwd_workspace_bytes": (sz, [i64, i64]),
     "qot_pool_mlp_bwd": (C.c_int, [P, P, P, P, P, i64, i64, i64, P, P, P, P, P, P, P, P, sz, vp]),
-    "qot_lightpath_infer_workspace_bytes": (sz, [i64, i64]),
+    "qot_lightpath_infer_state_bytes": (sz, [i64]),
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, i64, i64, P, i32, P, P, P, P, P, sz, vp]),
@@ -117,6 +117,21 @@ def stream() -> int:
 
 
 _ws_cache = {}
+
+
+_state_cache = {}
+
+
+def infer_state(nbytes: int, device) -> torch.Tensor:
+    """Per-(device, stream) look-back state of qot_lightpath_infer: zeroed when allocated, left
+    zeroed by every launch (see include/qot_b200.h)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _state_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _state_cache[key] = buf
+    return buf
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

@@ -1,0 +1,116 @@
+"""Data parallelism over the GPUs of one box -- NEW capability, the reference
+has none (no torch.distributed anywhere).
+
+Graphs are independent units, so the path shards by graph index with nothing exchanged on the
+data path:
+
+* inference: rank r owns the contiguous graph range ``shard_range(G, r, W)``; every rank writes
+  its own outputs; no collective.
+* training: per-rank disjoint batches, replicated parameters (5,291 floats = 21 KB for
+  TopologicalGNN), and ONE all-reduce per step over a flat fp32 gradient buffer that the backward
+  kernels' results accumulate into directly (``p.grad`` are views of it).  With equal per-rank
+  batch sizes and a mean-reduction loss, the averaged gradient equals the gradient of the
+  concatenated batch -- checked in tests/test_distributed_cpu.py (gloo, world 2) and
+  tests/test_ddp_gpu.py (nccl).
+
+The collective itself is ``torch.distributed.all_reduce`` (NCCL over NVLink/NVSwitch on the GPU
+box, gloo in the CPU tests): 21 KB is latency-bound, there is no compute to overlap it with once
+the last backward kernel has run, so a custom fused kernel has nothing to win here.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_items: int, rank: int, world: int) -> range:
+    """Contiguous, balanced shard: the first ``num_items % world`` ranks get one extra item."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(int(num_items), int(world))
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class FlatGradBuffer:
+    """One flat buffer (fp32 for the product modules) holding every parameter gradient; ``p.grad`` are views into it, so
+    autograd accumulates straight into the buffer NCCL reduces."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        dtype = self.params[0].dtype
+        if any(p.device != dev or p.dtype != dtype for p in self.params):
+            raise ValueError("FlatGradBuffer needs parameters of one dtype on one device")
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        self.attach()
+
+    def view_of(self, i: int) -> torch.Tensor:
+        p = self.params[i]
+        return self.flat[self.offsets[i]: self.offsets[i] + p.numel()].view_as(p)
+
+    def attach(self) -> None:
+        """(Re-)points every ``p.grad`` at its slice; a gradient that was set elsewhere (e.g. after
+        ``optimizer.zero_grad(set_to_none=True)`` + backward) is copied in first."""
+        for i, p in enumerate(self.params):
+            v = self.view_of(i)
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        self.attach()
+
+    def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.attach()
+        rank, world = world_info()
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / world)
+
+
+class GraphDataParallel(torch.nn.Module):
+    """Wraps a module for graph-sharded data-parallel training.
+
+        ddp = GraphDataParallel(model)           # broadcasts rank 0's parameters and buffers
+        for data in loader_of_this_rank:
+            ddp.zero_grad()
+            loss = criterion(ddp(data), y); loss.backward()
+            ddp.sync_gradients()                 # one flat all-reduce, averaged
+            optimizer.step()
+    BatchNorm statistics stay per rank (the reference has no SyncBN)."""
+
+    def __init__(self, module: torch.nn.Module, broadcast: bool = True):
+        super().__init__()
+        self.module = module
+        _, world = world_info()
+        if broadcast and world > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, src=0)
+        self.grads = FlatGradBuffer(module.parameters())
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:   # views must survive: never set to None
+        self.grads.zero()
+
+    def sync_gradients(self) -> None:
+        self.grads.all_reduce_mean()

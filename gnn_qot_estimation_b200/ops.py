@@ -150,8 +150,10 @@ class LightpathInferOut(NamedTuple):
 
 
 def lightpath_infer(x, edge_index, gptr, eptr, prepared, is_lut_index: int,
-                    out: Optional[LightpathInferOut] = None) -> LightpathInferOut:
-    """Launches the fused eval forward; returns device buffers without any host sync."""
+                    out: Optional[LightpathInferOut] = None, state: Optional[torch.Tensor] = None) -> LightpathInferOut:
+    """Launches the fused eval forward (one kernel); returns device buffers without any host sync.
+    ``state``: zero-initialised look-back scratch private to the launching stream (default: a
+    cached per-stream buffer)."""
     _require_cuda(x, edge_index, gptr, eptr, prepared)
     x, edge_index = _f32(x), _i64(edge_index)
     N, E, B = int(x.shape[0]), int(edge_index.shape[1]), int(gptr.numel() - 1)
@@ -162,10 +164,11 @@ def lightpath_infer(x, edge_index, gptr, eptr, prepared, is_lut_index: int,
                                 torch.empty(max(N, 1), dtype=torch.int32, device=dev),
                                 torch.empty(1, dtype=torch.int32, device=dev))
     L = _lib.lib()
-    ws = _lib.workspace(L.qot_lightpath_infer_workspace_bytes(N, B), dev)
+    if state is None:
+        state = _lib.infer_state(L.qot_lightpath_infer_state_bytes(B), dev)
     check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), N, B, ptr(prepared),
                                 int(is_lut_index), ptr(out.out), ptr(out.lut_batch), ptr(out.lut_node),
-                                ptr(out.n_lut), ptr(ws), ws.numel(), stream()), "qot_lightpath_infer")
+                                ptr(out.n_lut), ptr(state), state.numel(), stream()), "qot_lightpath_infer")
     return out
 
 

@@ -80,7 +80,7 @@ int qot_collate(const qot_store_t* store, const int64_t* graph_ids, int64_t B,
                 float* x, int64_t* edge_index, float* edge_attr, int64_t* batch,
                 int64_t* node_ids, float* y, void* stream);
 
-/* Workspace for qot_build_csr / qot_lightpath_infer etc. */
+/* Workspace for qot_build_csr. */
 size_t qot_csr_workspace_bytes(int64_t N, int64_t E);
 
 /* Group the E edges of edge_index [2,E] (int64) by row `by` (1 = by destination,
@@ -229,24 +229,27 @@ typedef struct {
 
 /* Fused eval-mode forward: GATConv -> BatchNorm(running stats) -> ReLU -> LUT
  * readout -> MLP (lightpath_training/models.py:26-45 under model.eval()).
- * Graph-parallel: graph g owns nodes [gptr[g],gptr[g+1]) and edges
- * [eptr[g],eptr[g+1]) of edge_index (as every collate produces them).  Only the
- * rows the readout keeps (LUT nodes) are evaluated -- same values as computing
- * all rows and selecting.  Outputs are written in ascending node order:
+ * Graph-parallel, ONE launch: graph g owns nodes [gptr[g],gptr[g+1]) and edges
+ * [eptr[g],eptr[g+1]) of edge_index (as every collate produces them; both endpoints of an
+ * edge lie in the graph that owns it).  Only the rows the readout keeps (LUT nodes) are
+ * evaluated -- same values as computing all rows and selecting.  Outputs are written in
+ * ascending node order:
  *   out [L,3], lut_batch [L] int64 (graph id), lut_node [L] int32, and
  *   n_lut[0] = L (int32, device).  Capacity of out/lut_batch/lut_node = N rows.
- * ws: qot_lightpath_infer_workspace_bytes(N,B). */
-size_t qot_lightpath_infer_workspace_bytes(int64_t N, int64_t B);
+ * state: qot_lightpath_infer_state_bytes(B) bytes the caller ZEROES ONCE before its first
+ * use; every call leaves it zeroed again (the cross-block look-back cleans up after itself).
+ * One state buffer per stream: launches that may overlap must not share it. */
+size_t qot_lightpath_infer_state_bytes(int64_t B);
 /* Folds the parameters once per weight update (attention vectors through lin_w,
  * conv bias + BatchNorm running stats into one scale/shift, transposed MLP) into
- * `prepared` (qot_lightpath_prepared_floats() floats). */
+ * `prepared` (qot_lightpath_prepared_floats() floats, 16-byte aligned). */
 size_t qot_lightpath_prepared_floats(void);
 int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream);
 int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         const int64_t* gptr, const int64_t* eptr, int64_t N, int64_t B,
                         const float* prepared, int32_t is_lut_index, float* out,
                         int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                        void* ws, size_t ws_bytes, void* stream);
+                        void* state, size_t state_bytes, void* stream);
 
 /* General GATConv forward over a destination-sorted CSR built with flags=3
  * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.

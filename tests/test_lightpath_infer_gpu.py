@@ -161,3 +161,62 @@ def test_deterministic(cuda):
         o1 = o1.clone()
         o2, _ = m(b)
     assert torch.equal(o1, o2)
+
+
+def test_many_tiles_mixed_lut_counts(cuda):
+    """> 256 blocks (several look-back windows), graphs with 0..3 LUT nodes, a few graphs beyond
+    the fast-path caps (n > 64 nodes / > 256 edges) in the middle; repeated launches reuse the
+    self-cleaning look-back state."""
+    from gnn_qot_estimation_b200 import Batch, synthetic
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    G = 9000
+    store = synthetic.lightpath_store(G, seed=21, device="cpu")
+    hb = store.host_batch(0, G)
+    g = torch.Generator().manual_seed(2)
+    hb.x[:, 1] = 0.0
+    counts = torch.randint(0, 4, (G,), generator=g)
+    counts[:300] = 0                                    # whole leading tiles without any LUT row
+    n = hb.ptr[1:] - hb.ptr[:-1]
+    for r in range(3):
+        pos = torch.minimum((torch.rand(G, generator=g) * n).long(), n - 1)
+        sel = counts > r
+        hb.x[hb.ptr[:-1][sel] + pos[sel], 1] = 1.0
+    # append two big graphs (slow path) and re-collate by hand
+    big_n, big_e = 150, 700
+    xs = [hb.x]; eis = [hb.edge_index]; bts = [hb.batch]
+    off = hb.num_nodes
+    for k in range(2):
+        xb = torch.rand(big_n, 5, generator=g); xb[:, 1] = 0.0; xb[[3, 77, 149], 1] = 1.0
+        src = torch.randint(0, big_n, (big_e,), generator=g); dst = torch.randint(0, big_n, (big_e,), generator=g)
+        dst[:40] = 77
+        xs.append(xb); eis.append(torch.stack([src, dst]) + off); bts.append(torch.full((big_n,), G + k))
+        off += big_n
+    full = Batch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=G + 2)
+    with torch.no_grad():
+        db = full.to(cuda)
+        o1, l1 = m(db)
+        o1, l1 = o1.clone(), l1.clone()
+        o2, l2 = m(db)
+        eo, el = _oracle(sd, torch.float64)(_to64(full))
+    assert torch.equal(l1.cpu(), el) and torch.equal(l1, l2) and torch.equal(o1, o2)
+    assert rel_err(o1, eo) <= RTOL
+
+
+def test_pipeline_matches_module(cuda):
+    """Host-facing streaming pipeline (pinned host batches -> results on host) == module path."""
+    from gnn_qot_estimation_b200 import synthetic
+    from gnn_qot_estimation_b200.pipeline import LightpathInferencePipeline
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    store = synthetic.lightpath_store(7 * 128, seed=13, device="cpu", lut_per_graph=2)
+    hbs = [store.host_batch(i * 128, (i + 1) * 128, pin=True) for i in range(7)]
+    pipe = LightpathInferencePipeline(m, max_nodes=max(b.num_nodes for b in hbs),
+                                      max_edges=max(b.num_edges for b in hbs), max_graphs=128, depth=3)
+    res = pipe.run(hbs)
+    assert len(res) == 7
+    with torch.no_grad():
+        for hb, (o, l) in zip(hbs, res):
+            eo, el = m(hb.to(cuda))
+            assert torch.equal(o, eo.cpu()) and torch.equal(l, el.cpu())
+    assert pipe.steps == 7 and pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0

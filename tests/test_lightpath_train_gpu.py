@@ -48,6 +48,31 @@ def _b64(b):
     return bb
 
 
+def _kink_margin(o64, hb):
+    """Smallest |pre-activation| feeding a ReLU / LeakyReLU that the loss depends on (LUT rows).
+    The derivative of those jumps at 0, so a value within fp32 round-off of 0 makes the GRADIENT of
+    any fp32 implementation differ from fp64 by a discrete amount -- such inputs cannot carry a
+    1e-5 gradient comparison (observed: the fp32 oracle itself lands on either side depending on
+    the host CPU)."""
+    import copy
+    o = copy.deepcopy(o64)
+    b = _b64(hb)
+    with torch.no_grad():
+        h = o.norm1(o.conv1(b.x, b.edge_index))
+        pre1 = h[b.x[:, 1] == 1.0]
+        pre2 = o.mlp[0](torch.relu(pre1))
+    return min(float(pre1.abs().min()), float(pre2.abs().min()))
+
+
+def _kink_free_batch(o64, num_graphs, luts, seed):
+    from gnn_qot_estimation_b200 import synthetic
+    for attempt in range(20):
+        hb = synthetic.lightpath_store(num_graphs, seed=seed + 1000 * attempt, lut_per_graph=luts).host_batch(0, num_graphs)
+        if _kink_margin(o64, hb) > 2e-6:          # ~10x the fp32 round-off of O(1) pre-activations
+            return hb
+    raise AssertionError("no kink-free batch found")
+
+
 @pytest.mark.parametrize("ckpt", ["ckpt_lightpath_model_1.pt", None])
 @pytest.mark.parametrize("num_graphs,luts", [(4, 1), (96, 1), (300, 2)])
 def test_train_step_vs_oracle(cuda, ckpt, num_graphs, luts):
@@ -55,15 +80,14 @@ def test_train_step_vs_oracle(cuda, ckpt, num_graphs, luts):
     sd = load_golden(ckpt)["model_state_dict"] if ckpt else None
     m, o, o32 = _pair(cuda, sd, seed=num_graphs)
     m.train(); o.train(); o32.train()
-    hb = synthetic.lightpath_store(num_graphs, seed=2 + num_graphs, lut_per_graph=luts).host_batch(0, num_graphs)
+    hb = _kink_free_batch(o, num_graphs, luts, seed=2 + num_graphs)
     out, lb, loss, grads = _step(m, hb.to(cuda))
     eo, el, eloss, eg = _step(o, _b64(hb), torch.float64)
     _, _, _, eg32 = _step(o32, hb.to("cpu"))
     assert torch.equal(lb.cpu(), el)
     assert rel_err(out, eo) <= RTOL and rel_err(loss, eloss) <= RTOL
     # conv1.bias feeds a batch-statistics BatchNorm: its exact gradient is 0
-    for k, e in grad_parity(grads, eg, eg32, exact_zero=("conv1.bias",)).items():
-        assert e <= RTOL, (k, e)
+    grad_parity(grads, eg, eg32, RTOL, exact_zero=("conv1.bias",))
     # running statistics (momentum 0.1, unbiased variance) and the batch counter
     bn, obn = m.norm1.module, o.norm1.module
     assert rel_err(bn.running_mean, obn.running_mean) <= RTOL
@@ -77,13 +101,12 @@ def test_eval_with_grad_uses_running_stats(cuda):
     sd = load_golden("ckpt_lightpath_model_0.pt")["model_state_dict"]
     m, o, o32 = _pair(cuda, sd)
     m.eval(); o.eval(); o32.eval()
-    hb = synthetic.lightpath_store(50, seed=3).host_batch(0, 50)
+    hb = _kink_free_batch(o, 50, 1, seed=3)
     out, lb, loss, grads = _step(m, hb.to(cuda))
     eo, el, eloss, eg = _step(o, _b64(hb), torch.float64)
     _, _, _, eg32 = _step(o32, hb.to("cpu"))
     assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
-    for k, e in grad_parity(grads, eg, eg32).items():
-        assert e <= RTOL, (k, e)
+    grad_parity(grads, eg, eg32, RTOL)
 
 
 def test_general_path_equals_fused_eval_path(cuda):
