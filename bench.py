@@ -112,10 +112,11 @@ def load_state():
 
 def algorithmic_bytes(batch) -> int:
     """Compulsory traffic of the fused eval kernel for one batch ('lp_infer'):
-    x (20 B/node) + destination row of edge_index (8 B/edge) + gptr/eptr (16 B/graph) +
-    out/lut_batch/lut_node rows (24 B/LUT row, L ~= B)."""
+    x (20 B/node) + destination row of edge_index (8 B/edge) + gptr/eptr/lut_ptr (24 B/graph) +
+    out/lut_batch/lut_node rows (24 B/LUT row, L = lut_ptr[B])."""
     N, E, B = batch.num_nodes, batch.num_edges, batch.num_graphs
-    return 20 * N + 8 * E + 16 * (B + 1) + 24 * B + 4
+    L = B if batch.lut_ptr is None else int(batch.lut_ptr[-1])
+    return 20 * N + 8 * E + 24 * (B + 1) + 24 * L + 4
 
 
 def peaks():
@@ -216,7 +217,7 @@ def run_b200(args):
     batches = [store.collate(range(i * Bsz, min((i + 1) * Bsz, G))) for i in range(nb)]
     outs = [model.forward_device(b) for b in batches]            # eager pass: allocates outputs, warms up
     torch.cuda.synchronize()
-    input_bytes = sum(b.nbytes(("x", "edge_index", "ptr", "edge_ptr")) for b in batches)
+    input_bytes = sum(b.nbytes(("x", "edge_index", "ptr", "edge_ptr", "lut_ptr")) for b in batches)
     launches_per_step = model.launches_per_step
 
     K, W = args.steps, max(args.warmup, 3)

@@ -11,7 +11,10 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libqot_b200.so"
+import os as _os
+
+# QOT_B200_LIB: developer override pointing at an instrumented build of the same sources
+LIB_PATH = Path(_os.environ["QOT_B200_LIB"]) if _os.environ.get("QOT_B200_LIB") else _PKG / "libqot_b200.so"
 
 _lib = None
 
@@ -58,10 +61,11 @@ SIGNATURES = {
     "qot_pool_mlp_fwd": (C.c_int, [P, P, i64, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_pool_mlp_bwd_workspace_bytes": (sz, [i64, i64]),
     "qot_pool_mlp_bwd": (C.c_int, [P, P, P, P, P, i64, i64, i64, P, P, P, P, P, P, P, P, sz, vp]),
-    "qot_lightpath_infer_state_bytes": (sz, [i64]),
+    "qot_lightpath_lut_ptr_workspace_bytes": (sz, [i64]),
+    "qot_lightpath_lut_ptr": (C.c_int, [P, P, i64, i64, i32, P, P, sz, vp]),
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
-    "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, i64, i64, P, i32, P, P, P, P, P, sz, vp]),
+    "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, vp]),
     "qot_gat_fwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_gat_bwd_workspace_bytes": (sz, [i64]),
     "qot_gat_bwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, P, P, P, P, sz, vp]),
@@ -117,21 +121,6 @@ def stream() -> int:
 
 
 _ws_cache = {}
-
-
-_state_cache = {}
-
-
-def infer_state(nbytes: int, device) -> torch.Tensor:
-    """Per-(device, stream) look-back state of qot_lightpath_infer: zeroed when allocated, left
-    zeroed by every launch (see include/qot_b200.h)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
-    buf = _state_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-        _state_cache[key] = buf
-    return buf
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

@@ -19,17 +19,21 @@ import torch
 
 from . import _lib
 
-_FIELDS = ("x", "edge_index", "edge_attr", "batch", "node_ids", "y", "ptr", "edge_ptr")
+_FIELDS = ("x", "edge_index", "edge_attr", "batch", "node_ids", "y", "ptr", "edge_ptr", "lut_ptr")
 
 
 class Batch:
     """Minimal stand-in for ``torch_geometric.data.Batch``."""
 
     def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, node_ids=None,
-                 y=None, ptr=None, edge_ptr=None, num_graphs: Optional[int] = None):
+                 y=None, ptr=None, edge_ptr=None, lut_ptr=None, num_graphs: Optional[int] = None,
+                 lut_col: Optional[int] = None):
         self.x, self.edge_index, self.edge_attr = x, edge_index, edge_attr
         self.batch, self.node_ids, self.y = batch, node_ids, y
         self.ptr, self.edge_ptr = ptr, edge_ptr
+        # lut_ptr [B+1]: exclusive prefix of the per-graph count of nodes with x[:, lut_col] == 1.0
+        # (where each graph's readout rows go); built by the collate like ptr / edge_ptr
+        self.lut_ptr, self.lut_col = lut_ptr, lut_col
         self.num_graphs = num_graphs
         self._cache = {}          # per-batch CSR etc. built lazily by the ops layer
 
@@ -49,12 +53,12 @@ class Batch:
     def to(self, device, non_blocking: bool = False) -> "Batch":
         kw = {k: (getattr(self, k).to(device, non_blocking=non_blocking)
                   if getattr(self, k) is not None else None) for k in _FIELDS}
-        return Batch(num_graphs=self.num_graphs, **kw)
+        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, **kw)
 
     def pin_memory(self) -> "Batch":
         kw = {k: (getattr(self, k).pin_memory() if getattr(self, k) is not None else None)
               for k in _FIELDS}
-        return Batch(num_graphs=self.num_graphs, **kw)
+        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, **kw)
 
     def cpu(self) -> "Batch":
         return self.to("cpu")
@@ -77,7 +81,9 @@ class PackedGraphStore:
     edge_feat [E_tot,D] or None; y [G,3].
     """
 
-    def __init__(self, node_ptr, edge_ptr, edge_src, edge_dst, node_feat=None, edge_feat=None, y=None):
+    def __init__(self, node_ptr, edge_ptr, edge_src, edge_dst, node_feat=None, edge_feat=None, y=None,
+                 lut_col: Optional[int] = None):
+        self.lut_col = lut_col       # column of node_feat holding the LUT flag (lightpath graphs) or None
         self.node_ptr, self.edge_ptr = node_ptr.to(torch.int64), edge_ptr.to(torch.int64)
         self.edge_src, self.edge_dst = edge_src.to(torch.int32), edge_dst.to(torch.int32)
         self.node_feat, self.edge_feat, self.y = node_feat, edge_feat, y
@@ -96,7 +102,7 @@ class PackedGraphStore:
     def to(self, device) -> "PackedGraphStore":
         mv = lambda t: None if t is None else t.to(device)
         return PackedGraphStore(mv(self.node_ptr), mv(self.edge_ptr), mv(self.edge_src), mv(self.edge_dst),
-                                mv(self.node_feat), mv(self.edge_feat), mv(self.y))
+                                mv(self.node_feat), mv(self.edge_feat), mv(self.y), self.lut_col)
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
@@ -150,8 +156,12 @@ class PackedGraphStore:
         _lib.check(lib.qot_collate(C.byref(st), _lib.ptr(gids.contiguous()), B, _lib.ptr(optr), _lib.ptr(oeptr),
                                    N, E, _lib.ptr(x), _lib.ptr(ei), _lib.ptr(ea), _lib.ptr(bt),
                                    _lib.ptr(nid), _lib.ptr(y), _lib.stream()), "qot_collate")
+        lut_ptr = None
+        if self.lut_col is not None and x is not None:
+            from . import ops
+            lut_ptr = ops.lightpath_lut_ptr(x, optr, self.lut_col)
         return Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
-                     ptr=optr, edge_ptr=oeptr, num_graphs=B)
+                     ptr=optr, edge_ptr=oeptr, lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
 
     # -- host-side view of a contiguous range (what a host DataLoader would hand over)
     def host_batch(self, g0: int, g1: int, pin: bool = False) -> Batch:
@@ -176,6 +186,11 @@ class PackedGraphStore:
             nid = torch.arange(n1 - n0, dtype=torch.int64) - torch.repeat_interleave(ptr[:-1], counts_n)
         ea = self.edge_feat[e0:e1].clone() if self.edge_feat is not None else None
         y = self.y[g0:g1].clone() if self.y is not None else None
+        lut_ptr = None
+        if self.lut_col is not None and x is not None:
+            lut_ptr = torch.zeros(B + 1, dtype=torch.int64)
+            flags = (x[:, self.lut_col] == 1.0).to(torch.int64)
+            torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, flags), 0, out=lut_ptr[1:])
         b = Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
-                  ptr=ptr.clone(), edge_ptr=eptr.clone(), num_graphs=B)
+                  ptr=ptr.clone(), edge_ptr=eptr.clone(), lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
         return b.pin_memory() if pin else b

@@ -69,61 +69,120 @@ lp_prepare_kernel(qot_lightpath_params_t p, float* __restrict__ out) {
   if (t < QOT_OUT) out[kOffB2 + t] = p.mlp_b2[t];
 }
 
+#ifdef QOT_LP_TRACE
+// debug build only (scripts/trace_lp_infer.py): per-block phase timestamps, 8 slots per block
+__device__ unsigned long long* g_lp_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LP_TRACE(slot)                                                                         \
+  do {                                                                                         \
+    if (g_lp_trace && threadIdx.x == 0) g_lp_trace[blockIdx.x * 8 + (slot)] = gtimer();        \
+  } while (0)
+#else
+#define LP_TRACE(slot) do {} while (0)
+#endif
+
 constexpr int kIW = 8;                    // warps (= graphs) per block
+constexpr int kThreads = kIW * 32;
 constexpr int kMaxN = 64;                 // fast path: nodes staged in shared memory
 constexpr int kXF = kMaxN * kF;           // 320 floats per graph
 constexpr int kXR = kXF / 32;             // 10 slab loads per lane
 constexpr int kEC = 8;                    // fast path: 8 x 32 = 256 edges held in registers
-constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagInc = 2ull << 32;
+constexpr int kMsgCap = 64;               // message list per warp (sources of one row + its self loop)
+constexpr int kWeightFloats = kPreparedFloats - kOffWf;   // projection + head weights staged per block
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// online-softmax update of one message (logit a, feature value xv of this lane's slot)
-__device__ __forceinline__ void attn_update(float a, float xv, float& m, float& ssum, float& acc) {
-  a = a > 0.f ? a : 0.2f * a;
-  const float mn = fmaxf(m, a);
-  const float sc = expf(m - mn);          // exp(-inf) = 0 on the first message
-  const float pe = expf(a - mn);
-  ssum = fmaf(ssum, sc, pe);
-  acc = fmaf(acc, sc, pe * xv);
-  m = mn;
-}
 __device__ __forceinline__ float pick5(const float (&v)[kF], int f) {
   return (f == 0) ? v[0] : (f == 1) ? v[1] : (f == 2) ? v[2] : (f == 3) ? v[3] : v[4];
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// z (slot h*8+f of s_z) -> folded projection + BatchNorm + ReLU -> MLP head; lanes 0..2 return out[k]
-__device__ __forceinline__ float lut_row_head(const float* __restrict__ prep, const float* s_z, float* s_y,
+// Attention over a list of message sources, 8 messages per round: lane = (slot m = lane>>2,
+// head h = lane&3).  Online softmax across rounds; within a round the 8 slots are combined by
+// a fixed xor-shuffle tree, so the result depends only on the (edge-ordered) list.
+struct AttnState {
+  float m = -INFINITY, ssum = 0.f, acc[kF] = {0.f, 0.f, 0.f, 0.f, 0.f};
+};
+template <typename XF>
+__device__ __forceinline__ void attn_consume(AttnState& st, const int* msg, int M, XF xf,
+                                             const float (&As)[kF], float d_i, int lane) {
+  const int slot = lane >> 2;
+  for (int r0 = 0; r0 < M; r0 += 8) {
+    const bool valid = r0 + slot < M;
+    const int j = msg[valid ? r0 + slot : r0];
+    float xj[kF];
+#pragma unroll
+    for (int k = 0; k < kF; ++k) xj[k] = xf(j, k);
+    float a = d_i;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) a = fmaf(xj[k], As[k], a);
+    a = a > 0.f ? a : 0.2f * a;                     // leaky_relu(., 0.2)
+    if (!valid) a = -INFINITY;
+    float mr = a;
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) mr = fmaxf(mr, __shfl_xor_sync(kFull, mr, o));
+    const float mn = fmaxf(st.m, mr);               // finite: slot 0 of every round is valid
+    const float sc = expf(st.m - mn);               // exp(-inf) = 0 in the first round
+    const float p = valid ? expf(a - mn) : 0.f;
+    float v[kF + 1];
+    v[kF] = p;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) v[k] = p * xj[k];
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k <= kF; ++k) v[k] += __shfl_xor_sync(kFull, v[k], o);
+    }
+    st.ssum = fmaf(st.ssum, sc, v[kF]);
+#pragma unroll
+    for (int k = 0; k < kF; ++k) st.acc[k] = fmaf(st.acc[k], sc, v[k]);
+    st.m = mn;
+  }
+}
+// z[h][f] = acc / (sum + 1e-16) into slot h*8+f of s_z (lane (m,h) stores feature m)
+__device__ __forceinline__ void attn_finish(const AttnState& st, float* s_z, int lane) {
+  const int slot = lane >> 2, h = lane & 3;
+  const float den = st.ssum + 1e-16f;
+  if (slot < kF) s_z[h * 8 + slot] = pick5(st.acc, slot) / den;
+}
+
+// z (slot h*8+f of s_z) -> folded projection + BatchNorm + ReLU -> MLP head; lanes 0..2 return out[k].
+// `w` = the prepared block from kOffWf on (shared memory in the kernel).
+__device__ __forceinline__ float lut_row_head(const float* __restrict__ w, const float* s_z, float* s_y,
                                               int lane) {
+  constexpr int oShift = kOffShift - kOffWf, oW1 = kOffW1t - kOffWf, oB1 = kOffB1 - kOffWf,
+                oW2 = kOffW2 - kOffWf, oB2 = kOffB2 - kOffWf;
   // y[c], c = h2*32 + lane
 #pragma unroll
   for (int h2 = 0; h2 < kHeads; ++h2) {
-    float v = __ldg(prep + kOffShift + h2 * kC + lane);
+    float v = w[oShift + h2 * kC + lane];
 #pragma unroll
-    for (int k = 0; k < kF; ++k) v = fmaf(__ldg(prep + kOffWf + (h2 * kF + k) * kC + lane), s_z[h2 * 8 + k], v);
+    for (int k = 0; k < kF; ++k) v = fmaf(w[(h2 * kF + k) * kC + lane], s_z[h2 * 8 + k], v);
     s_y[h2 * kC + lane] = fmaxf(v, 0.f);
   }
   __syncwarp();
   // hidden layer: lane = (cg, og) owns outputs 4og..4og+3 over channels [32cg, 32cg+32)
   const int cg = lane >> 3, og = lane & 7;
+  const float4* __restrict__ w1 = reinterpret_cast<const float4*>(w + oW1) + cg * 32 * (kHid / 4) + og;
+  const float4* __restrict__ yq = reinterpret_cast<const float4*>(s_y + cg * 32);
   float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* __restrict__ w1 = reinterpret_cast<const float4*>(prep + kOffW1t) + og;
-#pragma unroll 8
-  for (int cc = 0; cc < 32; ++cc) {
-    const int c = cg * 32 + cc;
-    const float4 w = __ldg(w1 + c * (kHid / 4));
-    const float yv = s_y[c];
-    h4.x = fmaf(w.x, yv, h4.x);
-    h4.y = fmaf(w.y, yv, h4.y);
-    h4.z = fmaf(w.z, yv, h4.z);
-    h4.w = fmaf(w.w, yv, h4.w);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 yv = yq[c4];
+    const float4 wa = w1[(4 * c4 + 0) * (kHid / 4)];
+    const float4 wb = w1[(4 * c4 + 1) * (kHid / 4)];
+    const float4 wc = w1[(4 * c4 + 2) * (kHid / 4)];
+    const float4 wd = w1[(4 * c4 + 3) * (kHid / 4)];
+    h4.x = fmaf(wa.x, yv.x, h4.x); h4.y = fmaf(wa.y, yv.x, h4.y); h4.z = fmaf(wa.z, yv.x, h4.z); h4.w = fmaf(wa.w, yv.x, h4.w);
+    h4.x = fmaf(wb.x, yv.y, h4.x); h4.y = fmaf(wb.y, yv.y, h4.y); h4.z = fmaf(wb.z, yv.y, h4.z); h4.w = fmaf(wb.w, yv.y, h4.w);
+    h4.x = fmaf(wc.x, yv.z, h4.x); h4.y = fmaf(wc.y, yv.z, h4.y); h4.z = fmaf(wc.z, yv.z, h4.z); h4.w = fmaf(wc.w, yv.z, h4.w);
+    h4.x = fmaf(wd.x, yv.w, h4.x); h4.y = fmaf(wd.y, yv.w, h4.y); h4.z = fmaf(wd.z, yv.w, h4.z); h4.w = fmaf(wd.w, yv.w, h4.w);
   }
 #pragma unroll
   for (int o = 8; o <= 16; o <<= 1) {
@@ -132,7 +191,7 @@ __device__ __forceinline__ float lut_row_head(const float* __restrict__ prep, co
     h4.z += __shfl_xor_sync(kFull, h4.z, o);
     h4.w += __shfl_xor_sync(kFull, h4.w, o);
   }
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(prep + kOffB1) + og);
+  const float4 b1 = reinterpret_cast<const float4*>(w + oB1)[og];
   float4 act = make_float4(h4.x + b1.x, h4.y + b1.y, h4.z + b1.z, h4.w + b1.w);
   act.x = act.x > 0.f ? act.x : 0.01f * act.x;
   act.y = act.y > 0.f ? act.y : 0.01f * act.y;
@@ -141,319 +200,257 @@ __device__ __forceinline__ float lut_row_head(const float* __restrict__ prep, co
   float o3[QOT_OUT];
 #pragma unroll
   for (int k = 0; k < QOT_OUT; ++k) {
-    const float4 w = __ldg(reinterpret_cast<const float4*>(prep + kOffW2 + k * kHid) + og);
-    float p = w.x * act.x + w.y * act.y + w.z * act.z + w.w * act.w;
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) p += __shfl_xor_sync(kFull, p, o);
-    o3[k] = p;
+    const float4 wk = reinterpret_cast<const float4*>(w + oW2 + k * kHid)[og];
+    o3[k] = wk.x * act.x + wk.y * act.y + wk.z * act.z + wk.w * act.w;
   }
-  const float b2 = lane < QOT_OUT ? __ldg(prep + kOffB2 + lane) : 0.f;
+#pragma unroll
+  for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
+  }
+  const float b2 = lane < QOT_OUT ? w[oB2 + lane] : 0.f;
   return (lane == 0 ? o3[0] : lane == 1 ? o3[1] : o3[2]) + b2;
 }
 
-// Generic row evaluation straight from global memory (graphs beyond the fast-path caps).
-__device__ float lut_row_global(const float* __restrict__ x, const int64_t* __restrict__ esrc,
-                                const int64_t* __restrict__ edst, int64_t e0, int64_t e1, int64_t N,
-                                int64_t i, const float (&As)[kF], const float (&Ad)[kF], int f,
-                                const float* __restrict__ prep, float* s_z, float* s_y, int lane) {
-  float xi[kF];
-#pragma unroll
-  for (int k = 0; k < kF; ++k) xi[k] = x[i * kF + k];
-  float d_i = 0.f, s_i = 0.f;
+// Generic row evaluation straight from global memory: graphs beyond the fast-path caps, further
+// LUT rows of a graph, rows with more than kMsgCap-1 in-edges or a source outside their slab.
+__device__ __noinline__ float lut_row_global(const float* __restrict__ x, const int64_t* __restrict__ esrc,
+                                             const int64_t* __restrict__ edst, int64_t e0, int64_t e1,
+                                             int64_t N, int64_t i, const float* __restrict__ prep,
+                                             const float* __restrict__ w, int* s_msg, float* s_z,
+                                             float* s_y, int lane) {
+  const int h = lane & 3;
+  float As[kF], d_i = 0.f;
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
-    d_i = fmaf(xi[k], Ad[k], d_i);
-    s_i = fmaf(xi[k], As[k], s_i);
+    As[k] = __ldg(prep + kOffAsrc + k * kHeads + h);
+    d_i = fmaf(x[i * kF + k], __ldg(prep + kOffAdst + k * kHeads + h), d_i);
   }
-  float m = -INFINITY, ssum = 0.f, acc = 0.f;
+  auto xf = [&](int j, int k) { return x[static_cast<int64_t>(j) * kF + k]; };
+  AttnState st;
+  int cnt = 0;
   for (int64_t eb = e0; eb < e1; eb += 32) {
     const int64_t e = eb + lane;
     const int64_t dd = (e < e1) ? edst[e] : -1;
     int64_t sj = i;
     if (dd == i) sj = esrc[e];
     const bool hit = (dd == i) && (sj != i) && (static_cast<uint64_t>(sj) < static_cast<uint64_t>(N));
-    unsigned hm = __ballot_sync(kFull, hit);
-    while (hm) {
-      const int l = __ffs(hm) - 1;
-      hm &= hm - 1;
-      const int64_t j = __shfl_sync(kFull, sj, l);
-      float xj[kF];
-#pragma unroll
-      for (int k = 0; k < kF; ++k) xj[k] = x[j * kF + k];
-      float a = d_i;
-#pragma unroll
-      for (int k = 0; k < kF; ++k) a = fmaf(xj[k], As[k], a);
-      attn_update(a, pick5(xj, f), m, ssum, acc);
+    const unsigned hm = __ballot_sync(kFull, hit);
+    if (hit) s_msg[cnt + __popc(hm & ((1u << lane) - 1u))] = static_cast<int>(sj);
+    cnt += __popc(hm);
+    if (cnt >= kMsgCap - 32) {                                   // warp-uniform: keep room for 32 more
+      __syncwarp();
+      attn_consume(st, s_msg, cnt, xf, As, d_i, lane);
+      __syncwarp();
+      cnt = 0;
     }
   }
-  attn_update(s_i + d_i, pick5(xi, f), m, ssum, acc);   // the appended self loop comes last
+  if (lane == 0) s_msg[cnt] = static_cast<int>(i);               // the appended self loop comes last
+  ++cnt;
   __syncwarp();
-  s_z[lane] = acc / (ssum + 1e-16f);
+  attn_consume(st, s_msg, cnt, xf, As, d_i, lane);
+  attn_finish(st, s_z, lane);
   __syncwarp();
-  return lut_row_head(prep, s_z, s_y, lane);
+  const float ov = lut_row_head(w, s_z, s_y, lane);
+  __syncwarp();
+  return ov;
 }
 
-__global__ void __launch_bounds__(kIW * 32, 4)
+// lut_cnt[g] = number of nodes of graph g whose LUT flag is 1.0 (feeds the lut_ptr scan)
+__global__ void __launch_bounds__(256)
+lp_count_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int64_t B,
+                int lut_col, int32_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t g = warp0; g < B; g += nwarps) {
+    const int64_t n0 = gptr[g], n1 = gptr[g + 1];
+    int c = 0;
+    for (int64_t nb = n0; nb < n1; nb += 32) {
+      const int64_t node = nb + lane;
+      const bool f = node < n1 && x[node * kF + lut_col] == 1.0f;
+      c += __popc(__ballot_sync(kFull, f));
+    }
+    if (lane == 0) cnt[g] = c;
+  }
+}
+__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
 lp_infer_kernel(const float* __restrict__ x, const int64_t* __restrict__ edge_index, int64_t E,
-                const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t N,
-                int64_t B, const float* __restrict__ prep, int lut_col,
-                unsigned long long* __restrict__ st, float* __restrict__ out,
+                const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr,
+                const int64_t* __restrict__ lptr, int64_t N, int64_t B,
+                const float* __restrict__ prep, int lut_col, float* __restrict__ out,
                 int64_t* __restrict__ lut_batch, int32_t* __restrict__ lut_node,
-                int32_t* __restrict__ n_lut) {
-  __shared__ float s_x[kIW][kXF];
-  __shared__ float s_y[kIW][kHC];
+                int32_t* __restrict__ n_lut, int32_t* __restrict__ status) {
+  __shared__ __align__(16) float s_w[kWeightFloats];            // projection + head weights (19.5 KB)
+  __shared__ __align__(16) float s_x[kIW][kXF];
+  __shared__ __align__(16) float s_y[kIW][kHC];
   __shared__ float s_z[kIW][32];
-  __shared__ int s_cnt[kIW];
-  __shared__ int s_red[kIW][3];
-  __shared__ int s_base, s_flag;
+  __shared__ int s_msg[kIW][kMsgCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t tile = blockIdx.x, ntiles = gridDim.x;
-  const int64_t g = tile * kIW + warp;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * kIW + warp;
   const bool active = g < B;
   const int64_t* __restrict__ esrc = edge_index;
   const int64_t* __restrict__ edst = edge_index + E;
 
-  // ---- (1) graph extents: 4 lanes fetch gptr[g], gptr[g+1], eptr[g], eptr[g+1]
+  LP_TRACE(0);
+  // ---- (0) weights -> shared memory, asynchronously (lands while the graph data is in flight)
+  for (int i = threadIdx.x * 4; i < kWeightFloats; i += kThreads * 4) cp_async16(s_w + i, prep + kOffWf + i);
+
+  // ---- (1) graph extents: 6 lanes fetch gptr[g..g+1], eptr[g..g+1], lut_ptr[g..g+1]
   long long pv = 0;
-  if (active && lane < 4) pv = (lane < 2) ? gptr[g + lane] : eptr[g + lane - 2];
+  if (active && lane < 6) pv = (lane < 2) ? gptr[g + lane] : (lane < 4) ? eptr[g + lane - 2] : lptr[g + lane - 4];
   const int64_t n0 = __shfl_sync(kFull, pv, 0), n1 = __shfl_sync(kFull, pv, 1);
   const int64_t e0 = __shfl_sync(kFull, pv, 2), e1 = __shfl_sync(kFull, pv, 3);
-  const bool fast = active && (n1 - n0) <= kMaxN && (e1 - e0) <= 32 * kEC && n1 >= n0 && e1 >= e0;
+  const int64_t l0 = __shfl_sync(kFull, pv, 4), l1 = __shfl_sync(kFull, pv, 5);
+  const bool fast = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= 32 * kEC;
   const int n = fast ? static_cast<int>(n1 - n0) : 0;
   const int ne = fast ? static_cast<int>(e1 - e0) : 0;
+  const int n0i = static_cast<int>(n0);          // N < 2^31 (checked on the host)
+  if (g == B - 1 && lane == 0) n_lut[0] = static_cast<int32_t>(l1);
 
+  LP_TRACE(1);
   // ---- (2) every compulsory byte of the graph requested at once
-  int dl[kEC];                                   // destination, graph-local (-1: not in this graph)
+  unsigned dlp[kEC / 4] = {0xffffffffu, 0xffffffffu};   // graph-local destination per held edge, one byte
+                                                        // each (0xff: none / outside the slab)
   if (fast) {
-    const float* __restrict__ xg = x + n0 * kF;
+    const float* __restrict__ xg = x + n0 * kF + lane;
+    const int64_t* __restrict__ dg = edst + e0 + lane;
     const int nf = n * kF;
     float xr[kXR];
+    long long dv[kEC];
 #pragma unroll
-    for (int k = 0; k < kXR; ++k) {
-      const int idx = lane + 32 * k;
-      xr[k] = idx < nf ? __ldg(xg + idx) : 0.f;
-    }
-    long long dq[kEC];
+    for (int k = 0; k < kXR; ++k) xr[k] = (lane + 32 * k < nf) ? __ldg(xg + 32 * k) : 0.f;
 #pragma unroll
-    for (int k = 0; k < kEC; ++k) {
-      const int e = lane + 32 * k;
-      dq[k] = e < ne ? edst[e0 + e] : -1;
-    }
+    for (int k = 0; k < kEC; ++k) dv[k] = (lane + 32 * k < ne) ? dg[32 * k] : -1ll;
 #pragma unroll
-    for (int k = 0; k < kXR; ++k) s_x[warp][lane + 32 * k] = xr[k];
+    for (int k = 0; k < kXR; ++k)
+      if (32 * k < nf) s_x[warp][lane + 32 * k] = xr[k];
 #pragma unroll
     for (int k = 0; k < kEC; ++k) {
-      const long long dd = dq[k] - n0;
-      dl[k] = (dq[k] >= 0 && dd >= 0 && dd < n) ? static_cast<int>(dd) : -1;
+      const unsigned lo = static_cast<unsigned>(dv[k]);
+      const unsigned hi = static_cast<unsigned>(static_cast<unsigned long long>(dv[k]) >> 32);
+      const unsigned loc = lo - static_cast<unsigned>(n0i);
+      const unsigned byte = (hi == 0u && loc < static_cast<unsigned>(n)) ? loc : 0xffu;
+      dlp[k >> 2] = (dlp[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (byte << (8 * (k & 3)));
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < kEC; ++k) dl[k] = -1;
   }
-  __syncwarp();
+  cp_async_wait_all();
+  __syncthreads();                                               // s_w (all threads) and s_x are in place
+  LP_TRACE(2);
 
-  // ---- (3) LUT flags of this graph, block aggregate published for the look-back
-  unsigned m0 = 0, m1 = 0;
-  int cnt = 0;
+  // ---- (3) LUT rows of this graph, in ascending node order, at the offset lut_ptr gives
+  int64_t orow = l0;
+  int found = 0;
   if (fast) {
-    m0 = __ballot_sync(kFull, lane < n && s_x[warp][lane * kF + lut_col] == 1.0f);
-    m1 = __ballot_sync(kFull, lane + 32 < n && s_x[warp][(lane + 32) * kF + lut_col] == 1.0f);
-    cnt = __popc(m0) + __popc(m1);
-  } else if (active) {
-    for (int64_t nb = n0; nb < n1; nb += 32) {
-      const int64_t node = nb + lane;
-      cnt += __popc(__ballot_sync(kFull, node < n1 && x[node * kF + lut_col] == 1.0f));
-    }
-  }
-  if (lane == 0) s_cnt[warp] = cnt;
-  __syncthreads();
-  int tot = 0, wexcl = 0;
-#pragma unroll
-  for (int w = 0; w < kIW; ++w) {
-    const int c = s_cnt[w];
-    if (w < warp) wexcl += c;
-    tot += c;
-  }
-  if (threadIdx.x == 0)
-    st_relaxed_u64(st + 1 + tile, (tile == 0 ? kFlagInc : kFlagAgg) | static_cast<unsigned int>(tot));
-
-  // lane role in the aggregation: head h, feature slot f (slots 5..7 idle)
-  const int h = lane >> 3, f = lane & 7;
-  float As[kF], Ad[kF];
-#pragma unroll
-  for (int k = 0; k < kF; ++k) {
-    As[k] = __ldg(prep + kOffAsrc + k * kHeads + h);
-    Ad[k] = __ldg(prep + kOffAdst + k * kHeads + h);
-  }
-
-  // fast-path row: attention over the in-edges of local node il, from registers + shared memory
-  auto fast_row = [&](int il) -> float {
     const float* sx = s_x[warp];
-    float xi[kF];
+    int* msg = s_msg[warp];
+    unsigned a0 = __ballot_sync(kFull, lane < n && sx[lane * kF + lut_col] == 1.0f);
+    unsigned a1 = __ballot_sync(kFull, lane + 32 < n && sx[(lane + 32) * kF + lut_col] == 1.0f);
+    found = __popc(a0) + __popc(a1);
+    if (found == l1 - l0) {
+      const int h = lane & 3;
+      float As[kF], Ad[kF];
 #pragma unroll
-    for (int k = 0; k < kF; ++k) xi[k] = sx[il * kF + k];
-    float d_i = 0.f, s_i = 0.f;
+      for (int k = 0; k < kF; ++k) {
+        As[k] = __ldg(prep + kOffAsrc + k * kHeads + h);
+        Ad[k] = __ldg(prep + kOffAdst + k * kHeads + h);
+      }
+      while (a0 | a1) {
+        int il;
+        if (a0) { il = __ffs(a0) - 1; a0 &= a0 - 1; } else { il = 32 + __ffs(a1) - 1; a1 &= a1 - 1; }
+        // pass 1: local ids of the edges that point at the LUT node, in edge order
+        int mc = 0;
 #pragma unroll
-    for (int k = 0; k < kF; ++k) {
-      d_i = fmaf(xi[k], Ad[k], d_i);
-      s_i = fmaf(xi[k], As[k], s_i);
-    }
-    // sources of the matching edges, all requests in flight together
-    long long sq[kEC];
-#pragma unroll
-    for (int k = 0; k < kEC; ++k) sq[k] = (dl[k] == il) ? esrc[e0 + lane + 32 * k] : -1;
-    float m = -INFINITY, ssum = 0.f, acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < kEC; ++k) {
-      if (32 * k >= ne) break;                                   // warp-uniform
-      const long long sj = sq[k];
-      const bool hit = (dl[k] == il) && (sj != n0 + il) &&
-                       (static_cast<uint64_t>(sj) < static_cast<uint64_t>(N));
-      unsigned hm = __ballot_sync(kFull, hit);
-      const long long sloc = sj - n0;
-      const int jl_mine = (sloc >= 0 && sloc < n) ? static_cast<int>(sloc) : -1;   // -1: outside the slab
-      while (hm) {
-        const int l = __ffs(hm) - 1;
-        hm &= hm - 1;
-        const int jl = __shfl_sync(kFull, jl_mine, l);
-        float xj[kF];
-        if (jl >= 0) {
-#pragma unroll
-          for (int k2 = 0; k2 < kF; ++k2) xj[k2] = sx[jl * kF + k2];
-        } else {                                                 // cross-graph source: read it from global
-          const long long j = __shfl_sync(kFull, sj, l);
-#pragma unroll
-          for (int k2 = 0; k2 < kF; ++k2) xj[k2] = x[j * kF + k2];
+        for (int k = 0; k < kEC; ++k) {
+          if (32 * k < ne) {                                     // warp-uniform
+            const bool hit = ((dlp[k >> 2] >> (8 * (k & 3))) & 0xffu) == static_cast<unsigned>(il);
+            const unsigned hm = __ballot_sync(kFull, hit);
+            if (hit && mc < kMsgCap - 32) msg[mc + __popc(hm & ((1u << lane) - 1u))] = lane + 32 * k;
+            mc += __popc(hm);
+          }
         }
-        float a = d_i;
+        __syncwarp();
+        float ov;
+        bool done = false;
+        if (mc <= 32) {                                          // warp-uniform; hubs take the generic path
+          // pass 2: their sources (one gather); self loops and out-of-range ids dropped, order kept
+          long long sj = -1;
+          if (lane < mc) sj = esrc[e0 + msg[lane]];
+          const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
+          const long long sloc = sj - n0;
+          const bool inslab = sloc >= 0 && sloc < n;
+          const bool ok = inslab && sloc != il;
+          const unsigned outside = __ballot_sync(kFull, inN && !inslab);
+          const unsigned hm = __ballot_sync(kFull, ok);
+          __syncwarp();
+          if (ok) msg[__popc(hm & ((1u << lane) - 1u))] = static_cast<int>(sloc);
+          mc = __popc(hm);
+          if (outside == 0) {
+            if (lane == 0) msg[mc] = il;                         // the appended self loop comes last
+            ++mc;
+            __syncwarp();
+            float d_i = 0.f;
 #pragma unroll
-        for (int k2 = 0; k2 < kF; ++k2) a = fmaf(xj[k2], As[k2], a);
-        attn_update(a, pick5(xj, f), m, ssum, acc);
+            for (int k = 0; k < kF; ++k) d_i = fmaf(sx[il * kF + k], Ad[k], d_i);
+            AttnState as;
+            attn_consume(as, msg, mc, [&](int j, int k) { return sx[j * kF + k]; }, As, d_i, lane);
+            attn_finish(as, s_z[warp], lane);
+            __syncwarp();
+            ov = lut_row_head(s_w, s_z[warp], s_y[warp], lane);
+            __syncwarp();
+            done = true;
+          }
+        }
+        if (!done)
+          ov = lut_row_global(x, esrc, edst, e0, e1, N, n0 + il, prep, s_w, msg, s_z[warp], s_y[warp], lane);
+        if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
+        if (lane == 0) {
+          lut_batch[orow] = g;
+          lut_node[orow] = static_cast<int32_t>(n0 + il);
+        }
+        ++orow;
       }
     }
-    attn_update(s_i + d_i, pick5(xi, f), m, ssum, acc);          // appended self loop, last
-    __syncwarp();
-    s_z[warp][lane] = acc / (ssum + 1e-16f);
-    __syncwarp();
-    return lut_row_head(prep, s_z[warp], s_y[warp], lane);
-  };
-  auto nth_lut = [&](int r) -> int {                             // r-th LUT node of a fast graph
-    unsigned a = m0;
-    int base = 0;
-    const int c0 = __popc(m0);
-    if (r >= c0) { a = m1; r -= c0; base = 32; }
-    for (int t = 0; t < r; ++t) a &= a - 1;
-    return base + __ffs(a) - 1;
-  };
-
-  // ---- (4) first row of every fast graph before the output offset is known
-  float ov0 = 0.f;
-  int il0 = -1;
-  if (fast && cnt > 0) {
-    il0 = nth_lut(0);
-    ov0 = fast_row(il0);
-  }
-
-  // ---- (5) exclusive prefix of the LUT counts of all preceding tiles (decoupled look-back,
-  //          block-wide window of kIW*32 predecessors per round)
-  if (tile == 0) {
-    if (threadIdx.x == 0) s_base = 0;
-  } else {
-    int excl = 0;
-    int64_t hi = tile - 1;
-    while (true) {
-      const int64_t idx = hi - threadIdx.x;
-      unsigned long long wv = kFlagInc;                          // virtual tiles < 0: inclusive 0
-      if (idx >= 0) wv = ld_relaxed_u64(st + 1 + idx);
-      const unsigned flag = static_cast<unsigned>(wv >> 32);
-      const int val = static_cast<int>(static_cast<unsigned>(wv));
-      // per-warp: lanes are predecessors hi-32w-lane; closest inclusive = lowest lane with flag 2
-      const unsigned inc_m = __ballot_sync(kFull, flag == 2);
-      const unsigned emp_m = __ballot_sync(kFull, flag == 0);
-      const int first_inc = inc_m ? __ffs(inc_m) - 1 : 32;
-      const int first_emp = emp_m ? __ffs(emp_m) - 1 : 32;
-      int part = (lane <= first_inc) ? val : 0;                  // tiles up to and incl. the inclusive one
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-      if (lane == 0) {
-        s_red[warp][0] = part;
-        s_red[warp][1] = first_inc;
-        s_red[warp][2] = first_emp;
-      }
-      __syncthreads();
-      // combine the warps in predecessor order (warp 0 = closest tiles)
-      int sum = 0;
-      bool ready = true, found = false;
-#pragma unroll
-      for (int w = 0; w < kIW; ++w) {
-        if (found || !ready) break;
-        const int fi = s_red[w][1], fe = s_red[w][2];
-        if (fe < fi) { ready = false; break; }                   // an unpublished tile before any inclusive one
-        sum += s_red[w][0];
-        if (fi < 32) found = true;
-      }
-      __syncthreads();
-      if (!ready) continue;                                      // spin: re-read the window
-      excl += sum;
-      if (found) break;
-      hi -= kIW * 32;
-    }
-    if (threadIdx.x == 0) s_base = excl;
-  }
-  __syncthreads();
-  const int base = s_base;
-  if (threadIdx.x == 0) {
-    if (tile != 0) st_relaxed_u64(st + 1 + tile, kFlagInc | static_cast<unsigned int>(base + tot));
-    if (tile == ntiles - 1) n_lut[0] = base + tot;
-  }
-
-  // ---- (6) outputs in ascending node order
-  int64_t orow = static_cast<int64_t>(base) + wexcl;
-  if (fast) {
-    for (int r = 0; r < cnt; ++r) {
-      const int il = (r == 0) ? il0 : nth_lut(r);
-      const float ov = (r == 0) ? ov0 : fast_row(il);
-      if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
-      if (lane == 0) {
-        lut_batch[orow] = g;
-        lut_node[orow] = static_cast<int32_t>(n0 + il);
-      }
-      ++orow;
-    }
-  } else if (active && cnt > 0) {
+  } else if (active) {
     for (int64_t nb = n0; nb < n1; nb += 32) {
       const int64_t node = nb + lane;
       unsigned mask = __ballot_sync(kFull, node < n1 && x[node * kF + lut_col] == 1.0f);
       while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int64_t i = nb + bit;
-        const float ov = lut_row_global(x, esrc, edst, e0, e1, N, i, As, Ad, f, prep, s_z[warp], s_y[warp], lane);
-        if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
-        if (lane == 0) {
-          lut_batch[orow] = g;
-          lut_node[orow] = static_cast<int32_t>(i);
+        ++found;
+        if (orow < l1) {                                         // never write past this graph's rows
+          const int64_t i = nb + bit;
+          const float ov = lut_row_global(x, esrc, edst, e0, e1, N, i, prep, s_w, s_msg[warp], s_z[warp], s_y[warp], lane);
+          if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
+          if (lane == 0) {
+            lut_batch[orow] = g;
+            lut_node[orow] = static_cast<int32_t>(i);
+          }
+          ++orow;
         }
-        ++orow;
       }
     }
   }
-
-  // ---- (7) the last block through its look-back wipes the state for the next launch
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long prev = atomicAdd(st, 1ull);
-    s_flag = (prev == static_cast<unsigned long long>(ntiles - 1));
-  }
-  __syncthreads();
-  if (s_flag) {
-    for (int64_t t = threadIdx.x; t <= ntiles; t += blockDim.x) st[t] = 0ull;
-  }
+  // lut_ptr must describe THIS x: a stale / foreign lut_ptr is reported, never trusted silently
+  if (active && lane == 0 && found != l1 - l0) atomicOr(status, 1);
+  LP_TRACE(7);
 }
 
 }  // namespace qot
 
 using namespace qot;
+
+#ifdef QOT_LP_TRACE
+extern "C" int qot_debug_set_lp_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_lp_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" size_t qot_lightpath_prepared_floats(void) { return kPreparedFloats; }
 
@@ -468,36 +465,56 @@ extern "C" int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* pre
   return QOT_OK;
 }
 
-extern "C" size_t qot_lightpath_infer_state_bytes(int64_t B) {
+extern "C" size_t qot_lightpath_lut_ptr_workspace_bytes(int64_t B) {
   if (B < 0) return 0;
-  return align_up(static_cast<size_t>(cdiv(std::max<int64_t>(B, 1), kIW) + 1) * sizeof(unsigned long long));
+  return 2 * align_up(static_cast<size_t>(B + 1) * 4) + scan_workspace_bytes(B) + 256;
+}
+
+extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_t N, int64_t B,
+                                     int32_t is_lut_index, int64_t* lut_ptr, void* ws, size_t ws_bytes,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(N >= 0 && B >= 0 && lut_ptr && gptr, "qot_lightpath_lut_ptr: bad argument");
+  QOT_REQUIRE(N == 0 || x, "qot_lightpath_lut_ptr: null x");
+  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_lut_ptr: is_lut_index out of range");
+  QOT_REQUIRE(ws && ws_bytes >= qot_lightpath_lut_ptr_workspace_bytes(B), "qot_lightpath_lut_ptr: workspace too small");
+  Carver c(ws);
+  int32_t* cnt = c.take<int32_t>(B + 1);
+  int32_t* off = c.take<int32_t>(B + 1);
+  void* scan_ws = c.take<char>(scan_workspace_bytes(B));
+  if (B > 0) {
+    const int64_t blocks = std::min<int64_t>(cdiv(B, 8), static_cast<int64_t>(kNumSMs) * 8);
+    lp_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, gptr, B, is_lut_index, cnt);
+    QOT_LAUNCH_CHECK();
+  }
+  int rc = exclusive_scan_i32(cnt, 0, off, B, scan_ws, stream);
+  if (rc) return rc;
+  widen_i32_kernel<<<static_cast<unsigned>(cdiv(B + 1, 256)), 256, 0, stream>>>(off, B + 1, lut_ptr);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
 }
 
 extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
-                                   const int64_t* gptr, const int64_t* eptr, int64_t N, int64_t B,
-                                   const float* prepared, int32_t is_lut_index, float* out,
-                                   int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                                   void* state, size_t state_bytes, void* stream_) {
+                                   const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
+                                   int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
+                                   float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
+                                   int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   QOT_REQUIRE(N >= 0 && B >= 0 && E >= 0, "qot_lightpath_infer: negative size");
   QOT_REQUIRE(N < (1ll << 31) - 1, "qot_lightpath_infer: N exceeds int32 range");
   QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer: is_lut_index out of range");
-  QOT_REQUIRE(gptr && eptr && prepared && n_lut, "qot_lightpath_infer: null argument");
+  QOT_REQUIRE(gptr && eptr && lut_ptr && prepared && n_lut && status, "qot_lightpath_infer: null argument");
   QOT_REQUIRE(N == 0 || (x && out && lut_batch && lut_node), "qot_lightpath_infer: null buffer");
   QOT_REQUIRE(E == 0 || edge_index, "qot_lightpath_infer: null edge_index");
   QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer: prepared must be 16-byte aligned");
-  QOT_REQUIRE(state && state_bytes >= qot_lightpath_infer_state_bytes(B) &&
-                  (reinterpret_cast<uintptr_t>(state) & 7) == 0,
-              "qot_lightpath_infer: state buffer too small or misaligned");
   if (B == 0) {
     QOT_CUDA(cudaMemsetAsync(n_lut, 0, 4, stream));
     return QOT_OK;
   }
   const int64_t blocks = cdiv(B, kIW);
   QOT_REQUIRE(blocks < (1ll << 31) - 1, "qot_lightpath_infer: too many graphs for one launch");
-  lp_infer_kernel<<<static_cast<unsigned>(blocks), kIW * 32, 0, stream>>>(
-      x, edge_index, E, gptr, eptr, N, B, prepared, is_lut_index,
-      static_cast<unsigned long long*>(state), out, lut_batch, lut_node, n_lut);
+  lp_infer_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(
+      x, edge_index, E, gptr, eptr, lut_ptr, N, B, prepared, is_lut_index, out, lut_batch, lut_node, n_lut, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

@@ -59,28 +59,38 @@ class LightpathGNN(torch.nn.Module):
         return self._prepared
 
     def forward_device(self, data, out=None) -> ops.LightpathInferOut:
-        """Eval forward without any host synchronisation: returns capacity-sized device
-        buffers plus the device-side row count (CUDA-graph capturable)."""
+        """Eval forward without any host synchronisation: ONE kernel launch when the batch carries
+        ``ptr`` / ``edge_ptr`` / ``lut_ptr`` (every collate of this package provides them); returns
+        capacity-sized device buffers plus the device-side row count (CUDA-graph capturable)."""
         gptr = ops.batch_graph_ptr(data)
+        cache = ops.batch_cache(data)
         eptr = getattr(data, "edge_ptr", None)
         if eptr is None:
-            cache = ops.batch_cache(data)
             if "eptr" not in cache:
                 cache["eptr"] = ops.edge_ptr(data.edge_index, data.batch, gptr.numel() - 1)
             eptr = cache["eptr"][0]
-        return ops.lightpath_infer(data.x, data.edge_index, gptr, eptr, self.prepared(),
+        lut_ptr = getattr(data, "lut_ptr", None)
+        if lut_ptr is None or getattr(data, "lut_col", None) != self.is_lut_index:
+            key = ("lut_ptr", self.is_lut_index)
+            if key not in cache:
+                cache[key] = ops.lightpath_lut_ptr(data.x, gptr, self.is_lut_index)
+            lut_ptr = cache[key]
+        return ops.lightpath_infer(data.x, data.edge_index, gptr, eptr, lut_ptr, self.prepared(),
                                    self.is_lut_index, out)
 
     def _forward_eval(self, data):
         self._check_supported()
         res = self.forward_device(data)
-        if getattr(data, "edge_ptr", None) is not None:
-            n_lut = int(res.n_lut.item())
-        else:
-            # one D2H for both the row count and the "edges grouped by graph" check
-            n_lut, ungrouped = torch.cat([res.n_lut, ops.batch_cache(data)["eptr"][1]]).tolist()
-            if ungrouped:
-                return self._forward_general(data)   # CSR path handles any edge order
+        flags = [res.n_lut, res.status]
+        if getattr(data, "edge_ptr", None) is None:
+            flags.append(ops.batch_cache(data)["eptr"][1])      # "edges grouped by graph" check
+        vals = torch.cat(flags).tolist()                          # the one D2H of this forward
+        n_lut, stale = vals[0], vals[1]
+        if len(vals) > 2 and vals[2]:
+            return self._forward_general(data)                    # CSR path handles any edge order
+        if stale:
+            raise RuntimeError("LightpathGNN: the batch's lut_ptr does not match x[:, is_lut_index] "
+                               "(stale or foreign index array)")
         if n_lut == 0:
             raise ValueError("No LUT node found in the batch.")
         return res.out[:n_lut], res.lut_batch[:n_lut]

@@ -146,29 +146,45 @@ class LightpathInferOut(NamedTuple):
     out: torch.Tensor         # [cap,3]; rows [0,L) valid
     lut_batch: torch.Tensor   # [cap] int64
     lut_node: torch.Tensor    # [cap] int32
-    n_lut: torch.Tensor       # [1] int32 on device
+    n_lut: torch.Tensor       # [1] int32 on device (= lut_ptr[B])
+    status: torch.Tensor      # [1] int32 on device; non-zero: lut_ptr did not match x
 
 
-def lightpath_infer(x, edge_index, gptr, eptr, prepared, is_lut_index: int,
-                    out: Optional[LightpathInferOut] = None, state: Optional[torch.Tensor] = None) -> LightpathInferOut:
-    """Launches the fused eval forward (one kernel); returns device buffers without any host sync.
-    ``state``: zero-initialised look-back scratch private to the launching stream (default: a
-    cached per-stream buffer)."""
-    _require_cuda(x, edge_index, gptr, eptr, prepared)
+def new_infer_out(capacity: int, device) -> LightpathInferOut:
+    cap = max(int(capacity), 1)
+    return LightpathInferOut(torch.empty(cap, 3, dtype=torch.float32, device=device),
+                             torch.empty(cap, dtype=torch.int64, device=device),
+                             torch.empty(cap, dtype=torch.int32, device=device),
+                             torch.empty(1, dtype=torch.int32, device=device),
+                             torch.zeros(1, dtype=torch.int32, device=device))
+
+
+def lightpath_lut_ptr(x, gptr, is_lut_index: int) -> torch.Tensor:
+    """lut_ptr [B+1] int64: exclusive prefix of the per-graph LUT-node counts (device, no sync)."""
+    _require_cuda(x, gptr)
+    x = _f32(x)
+    N, B = int(x.shape[0]), int(gptr.numel() - 1)
+    out = torch.empty(B + 1, dtype=torch.int64, device=x.device)
+    L = _lib.lib()
+    ws = _lib.workspace(L.qot_lightpath_lut_ptr_workspace_bytes(B), x.device)
+    check(L.qot_lightpath_lut_ptr(ptr(x), ptr(gptr), N, B, int(is_lut_index), ptr(out), ptr(ws), ws.numel(),
+                                  stream()), "qot_lightpath_lut_ptr")
+    return out
+
+
+def lightpath_infer(x, edge_index, gptr, eptr, lut_ptr, prepared, is_lut_index: int,
+                    out: Optional[LightpathInferOut] = None) -> LightpathInferOut:
+    """Launches the fused eval forward (ONE kernel); returns device buffers without any host sync."""
+    _require_cuda(x, edge_index, gptr, eptr, lut_ptr, prepared)
     x, edge_index = _f32(x), _i64(edge_index)
     N, E, B = int(x.shape[0]), int(edge_index.shape[1]), int(gptr.numel() - 1)
-    dev = x.device
     if out is None:
-        out = LightpathInferOut(torch.empty(max(N, 1), 3, dtype=torch.float32, device=dev),
-                                torch.empty(max(N, 1), dtype=torch.int64, device=dev),
-                                torch.empty(max(N, 1), dtype=torch.int32, device=dev),
-                                torch.empty(1, dtype=torch.int32, device=dev))
+        out = new_infer_out(N, x.device)
     L = _lib.lib()
-    if state is None:
-        state = _lib.infer_state(L.qot_lightpath_infer_state_bytes(B), dev)
-    check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), N, B, ptr(prepared),
-                                int(is_lut_index), ptr(out.out), ptr(out.lut_batch), ptr(out.lut_node),
-                                ptr(out.n_lut), ptr(state), state.numel(), stream()), "qot_lightpath_infer")
+    check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), ptr(lut_ptr), N, B,
+                                ptr(prepared), int(is_lut_index), ptr(out.out), ptr(out.lut_batch),
+                                ptr(out.lut_node), ptr(out.n_lut), ptr(out.status), stream()),
+          "qot_lightpath_infer")
     return out
 
 

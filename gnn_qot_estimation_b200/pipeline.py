@@ -22,16 +22,13 @@ class _Slot:
         self.ei = torch.empty(2 * max_edges, dtype=torch.int64, device=dev)
         self.gptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
         self.eptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
-        self.res = ops.LightpathInferOut(
-            torch.empty(max_nodes, 3, dtype=torch.float32, device=dev),
-            torch.empty(max_nodes, dtype=torch.int64, device=dev),
-            torch.empty(max_nodes, dtype=torch.int32, device=dev),
-            torch.empty(1, dtype=torch.int32, device=dev))
+        self.lptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
+        self.res = ops.new_infer_out(max_nodes, dev)
         self.out_h = torch.empty(max_nodes, 3, dtype=torch.float32).pin_memory()
         self.lb_h = torch.empty(max_nodes, dtype=torch.int64).pin_memory()
-        self.n_h = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.st_h = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.done = torch.cuda.Event()
-        self.prefetched = 0
+        self.rows = 0
         self.busy = False
 
 
@@ -54,41 +51,38 @@ class LightpathInferencePipeline:
         N, E, B = hb.num_nodes, hb.num_edges, hb.num_graphs
         if N > self.caps[0] or E > self.caps[1] or B > self.caps[2]:
             raise RuntimeError(f"batch (N={N}, E={E}, B={B}) exceeds the pipeline capacity {self.caps}")
-        if hb.ptr is None or hb.edge_ptr is None:
-            raise RuntimeError("LightpathInferencePipeline needs batches carrying ptr and edge_ptr "
+        if hb.ptr is None or hb.edge_ptr is None or hb.lut_ptr is None or hb.lut_col != self.model.is_lut_index:
+            raise RuntimeError("LightpathInferencePipeline needs batches carrying ptr, edge_ptr and lut_ptr "
                                "(PackedGraphStore.host_batch / collate provide them)")
+        L = int(hb.lut_ptr[-1])                     # known on the host: no D2H of the row count
+        if L == 0:
+            raise ValueError("No LUT node found in the batch.")
         with torch.cuda.stream(slot.stream):
             x = slot.x[:N]
             ei = slot.ei[: 2 * E].view(2, E)
-            gptr, eptr = slot.gptr[: B + 1], slot.eptr[: B + 1]
+            gptr, eptr, lptr = slot.gptr[: B + 1], slot.eptr[: B + 1], slot.lptr[: B + 1]
             x.copy_(hb.x, non_blocking=True)
             ei.copy_(hb.edge_index, non_blocking=True)
             gptr.copy_(hb.ptr, non_blocking=True)
             eptr.copy_(hb.edge_ptr, non_blocking=True)
-            self.h2d_bytes += 20 * N + 16 * E + 16 * (B + 1)
-            ops.lightpath_infer(x, ei, gptr, eptr, self.model.prepared(), self.model.is_lut_index, slot.res)
-            pre = min(N, B)                       # L == B when every graph has one LUT node
-            slot.n_h.copy_(slot.res.n_lut, non_blocking=True)
-            slot.out_h[:pre].copy_(slot.res.out[:pre], non_blocking=True)
-            slot.lb_h[:pre].copy_(slot.res.lut_batch[:pre], non_blocking=True)
-            self.d2h_bytes += 4 + 20 * pre
-            slot.prefetched = pre
+            lptr.copy_(hb.lut_ptr, non_blocking=True)
+            self.h2d_bytes += 20 * N + 16 * E + 24 * (B + 1)
+            ops.lightpath_infer(x, ei, gptr, eptr, lptr, self.model.prepared(), self.model.is_lut_index, slot.res)
+            slot.st_h.copy_(slot.res.status, non_blocking=True)
+            slot.out_h[:L].copy_(slot.res.out[:L], non_blocking=True)
+            slot.lb_h[:L].copy_(slot.res.lut_batch[:L], non_blocking=True)
+            self.d2h_bytes += 4 + 20 * L
+            slot.rows = L
             slot.done.record(slot.stream)
         slot.busy = True
         self.steps += 1
 
     def _collect(self, slot: _Slot) -> Tuple[torch.Tensor, torch.Tensor]:
         slot.done.synchronize()
-        n = int(slot.n_h[0])
-        if n == 0:
-            raise ValueError("No LUT node found in the batch.")
-        if n > slot.prefetched:                   # rare: more LUT rows than graphs
-            with torch.cuda.stream(slot.stream):
-                slot.out_h[slot.prefetched:n].copy_(slot.res.out[slot.prefetched:n], non_blocking=True)
-                slot.lb_h[slot.prefetched:n].copy_(slot.res.lut_batch[slot.prefetched:n], non_blocking=True)
-                self.d2h_bytes += 20 * (n - slot.prefetched)
-            slot.stream.synchronize()
         slot.busy = False
+        if int(slot.st_h[0]) != 0:
+            raise RuntimeError("LightpathInferencePipeline: a batch's lut_ptr does not match its x")
+        n = slot.rows
         return slot.out_h[:n].clone(), slot.lb_h[:n].clone()
 
     def run(self, host_batches: Iterable) -> List[Tuple[torch.Tensor, torch.Tensor]]:

@@ -103,7 +103,7 @@ def lightpath_store(num_graphs: int, seed: int = 1, device="cpu", n_min: int = 8
         pos = torch.minimum((torch.rand(G, generator=gen, device=dev) * n).long(), n - 1)
         x[node_ptr[:-1] + pos, 1] = 1.0
     y = torch.rand(G, 3, generator=gen, device=dev)
-    return PackedGraphStore(node_ptr, edge_ptr, dsrc.to(torch.int32), ddst.to(torch.int32), x, None, y)
+    return PackedGraphStore(node_ptr, edge_ptr, dsrc.to(torch.int32), ddst.to(torch.int32), x, None, y, lut_col=1)
 
 
 def random_topology_store(num_nodes: int = 10000, num_links: int = 40000, seed: int = 2,

@@ -229,27 +229,31 @@ typedef struct {
 
 /* Fused eval-mode forward: GATConv -> BatchNorm(running stats) -> ReLU -> LUT
  * readout -> MLP (lightpath_training/models.py:26-45 under model.eval()).
- * Graph-parallel, ONE launch: graph g owns nodes [gptr[g],gptr[g+1]) and edges
- * [eptr[g],eptr[g+1]) of edge_index (as every collate produces them; both endpoints of an
- * edge lie in the graph that owns it).  Only the rows the readout keeps (LUT nodes) are
- * evaluated -- same values as computing all rows and selecting.  Outputs are written in
+ * Graph-parallel, ONE launch, no cross-block dependency: graph g owns nodes
+ * [gptr[g],gptr[g+1]) and edges [eptr[g],eptr[g+1]) of edge_index (as every collate produces
+ * them; both endpoints of an edge lie in the graph that owns it), and its readout rows go to
+ * [lut_ptr[g],lut_ptr[g+1]) -- lut_ptr [B+1] int64 is the exclusive prefix of the per-graph
+ * count of LUT nodes (x[:,is_lut_index] == 1.0), an index array like gptr that the collate
+ * builds once per batch (qot_lightpath_lut_ptr, or on the host).  Only the rows the readout
+ * keeps are evaluated -- same values as computing all rows and selecting.  Outputs, in
  * ascending node order:
- *   out [L,3], lut_batch [L] int64 (graph id), lut_node [L] int32, and
- *   n_lut[0] = L (int32, device).  Capacity of out/lut_batch/lut_node = N rows.
- * state: qot_lightpath_infer_state_bytes(B) bytes the caller ZEROES ONCE before its first
- * use; every call leaves it zeroed again (the cross-block look-back cleans up after itself).
- * One state buffer per stream: launches that may overlap must not share it. */
-size_t qot_lightpath_infer_state_bytes(int64_t B);
+ *   out [L,3], lut_batch [L] int64 (graph id), lut_node [L] int32, n_lut[0] = L = lut_ptr[B].
+ * status (int32[1], zeroed by the caller): bit 0 is set when lut_ptr does not describe x (a
+ * graph holds a different number of LUT nodes); rows of such a graph are not written. */
+size_t qot_lightpath_lut_ptr_workspace_bytes(int64_t B);
+int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_t N, int64_t B,
+                          int32_t is_lut_index, int64_t* lut_ptr, void* ws, size_t ws_bytes,
+                          void* stream);
 /* Folds the parameters once per weight update (attention vectors through lin_w,
  * conv bias + BatchNorm running stats into one scale/shift, transposed MLP) into
  * `prepared` (qot_lightpath_prepared_floats() floats, 16-byte aligned). */
 size_t qot_lightpath_prepared_floats(void);
 int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream);
 int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
-                        const int64_t* gptr, const int64_t* eptr, int64_t N, int64_t B,
-                        const float* prepared, int32_t is_lut_index, float* out,
-                        int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                        void* state, size_t state_bytes, void* stream);
+                        const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
+                        int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
+                        float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
+                        int32_t* status, void* stream);
 
 /* General GATConv forward over a destination-sorted CSR built with flags=3
  * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.

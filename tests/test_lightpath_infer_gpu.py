@@ -81,7 +81,7 @@ def test_device_collate_path_equals_host_path(cuda):
     store = synthetic.lightpath_store(300, seed=5, device="cpu")
     hb = store.host_batch(10, 290)
     db = store.to(cuda).collate(range(10, 290))
-    for k in ("x", "edge_index", "batch", "y", "ptr", "edge_ptr"):
+    for k in ("x", "edge_index", "batch", "y", "ptr", "edge_ptr", "lut_ptr"):
         assert torch.equal(getattr(db, k).cpu(), getattr(hb, k)), k
     with torch.no_grad():
         o1, l1 = m(db)
@@ -98,6 +98,7 @@ def test_no_lut_raises_value_error(cuda):
     store = synthetic.lightpath_store(8, seed=2, device="cpu")
     b = store.host_batch(0, 8)
     b.x[:, 1] = 0.0
+    b.lut_ptr = None                       # x was edited after the collate: drop the derived index array
     with pytest.raises(ValueError, match="No LUT node found in the batch."):
         with torch.no_grad():
             m(b.to(cuda))
@@ -164,9 +165,9 @@ def test_deterministic(cuda):
 
 
 def test_many_tiles_mixed_lut_counts(cuda):
-    """> 256 blocks (several look-back windows), graphs with 0..3 LUT nodes, a few graphs beyond
-    the fast-path caps (n > 64 nodes / > 256 edges) in the middle; repeated launches reuse the
-    self-cleaning look-back state."""
+    """thousands of blocks, graphs with 0..3 LUT nodes (whole leading blocks without any), two
+    graphs beyond the fast-path caps (n > 64 nodes / > 256 edges, a hub LUT node with 40+ in-edges),
+    batch without ptr / edge_ptr / lut_ptr (all three built by the index kernels)."""
     from gnn_qot_estimation_b200 import Batch, synthetic
     sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
     m = _model(cuda, sd)
@@ -220,3 +221,26 @@ def test_pipeline_matches_module(cuda):
             eo, el = m(hb.to(cuda))
             assert torch.equal(o, eo.cpu()) and torch.equal(l, el.cpu())
     assert pipe.steps == 7 and pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+
+
+def test_stale_lut_ptr_is_reported(cuda):
+    """lut_ptr is an index array like ptr: if it does not describe x the kernel says so instead
+    of writing rows to the wrong place."""
+    from gnn_qot_estimation_b200 import synthetic
+    m = _model(cuda, load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"])
+    hb = synthetic.lightpath_store(64, seed=3, device="cpu").host_batch(0, 64)
+    hb.x[int(hb.ptr[5]) + 1, 1] = 1.0 if hb.x[int(hb.ptr[5]) + 1, 1] == 0.0 else 0.0   # flip a LUT flag
+    with torch.no_grad(), pytest.raises(RuntimeError, match="lut_ptr"):
+        m(hb.to(cuda))
+    hb.lut_ptr = None                                      # without the stale array it is recomputed
+    with torch.no_grad():
+        out, lb = m(hb.to(cuda))
+        eo, el = _oracle(load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"], torch.float64)(_to64(hb))
+    assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
+
+
+def test_lut_ptr_kernel_matches_host(cuda):
+    from gnn_qot_estimation_b200 import ops, synthetic
+    hb = synthetic.lightpath_store(3000, seed=8, device="cpu", lut_per_graph=3).host_batch(0, 3000)
+    got = ops.lightpath_lut_ptr(hb.x.to(cuda), hb.ptr.to(cuda), 1)
+    assert torch.equal(got.cpu(), hb.lut_ptr)

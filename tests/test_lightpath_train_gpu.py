@@ -128,6 +128,7 @@ def test_train_no_lut_raises(cuda):
     m.train()
     hb = synthetic.lightpath_store(4, seed=1).host_batch(0, 4)
     hb.x[:, 1] = 0.5
+    hb.lut_ptr = None
     with pytest.raises(ValueError, match="No LUT node found in the batch."):
         m(hb.to(cuda))
 
