@@ -49,7 +49,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--workload", default="lightpath_infer", choices=["lightpath_infer", "topo_train", "topo_stress"],
+                    help="lightpath_infer = BASELINE configs[1] (the headline line); topo_train = configs[2] "
+                         "(TopologicalGNN DDP training, batch 1024/GPU); topo_stress = configs[4] (10k nodes, hidden 256)")
+    ap.add_argument("--streams", type=int, default=4,
                     help="independent batches in flight in the resident run (graph branches)")
     return ap.parse_args()
 
@@ -357,7 +360,10 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload != "lightpath_infer":
+        import bench_topological
+        bench_topological.run(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -1,0 +1,166 @@
+"""Secondary benchmark lines (not the headline): BASELINE configs[2] and configs[4].
+
+  --workload topo_train   TopologicalGNN(14,16,3) fwd + SmoothL1 + bwd + flat NCCL grad all-reduce +
+                          SGD(lr .1, momentum .9), 1024 NSFNET graphs per GPU per step (cfg 3)
+  --workload topo_stress  TopologicalGNN(10000,256,3) fwd (+bwd) on ONE 10k-node / 80k-directed-edge
+                          graph (cfg 5): per-kernel HBM roofline of the fused aggregation kernels
+Both print one JSON line on rank 0; `--impl reference` times the CPU oracle on the same step.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+
+
+def _ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def run(args):
+    if args.workload == "topo_train":
+        run_train(args)
+    else:
+        run_stress(args)
+
+
+# --------------------------------------------------------------------------- cfg 3
+def run_train(args):
+    import torch.distributed as dist
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    from gnn_qot_estimation_b200.distributed import GraphDataParallel
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B = 1024
+    K, W = min(args.steps, 2000), max(3, min(args.warmup, 50))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import TopologicalGNNOracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        m = TopologicalGNNOracle(14, 16, 3, 4, dropout_p=0.0)
+        opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)
+        hb = synthetic.nsfnet_store(B, seed=0).host_batch(0, B)
+        steps = min(K, 30)
+        for i in range(3 + steps):
+            if i == 3:
+                t0 = time.perf_counter()
+            opt.zero_grad()
+            loss = torch.nn.SmoothL1Loss()(m(hb), hb.y.view(-1, 3))
+            loss.backward()
+            opt.step()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"impl": "reference", "metric": "topo_train_graphs_per_sec", "value": steps * B / dt,
+                          "unit": "graphs/s", "n_gpus": args.gpus, "steps": steps, "ms_per_step": dt / steps * 1e3,
+                          "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "sample": f"{steps} steps of {B} graphs"},
+                          "config": {"workload": "BASELINE cfg3 on CPU oracle"}}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev)
+    ddp = GraphDataParallel(model)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    crit = torch.nn.SmoothL1Loss()
+    nb = 16
+    store = synthetic.nsfnet_store(B * nb, seed=rank).to(dev)
+    batches = [store.collate(range(i * B, (i + 1) * B)) for i in range(nb)]
+
+    def step(i):
+        b = batches[i % nb]
+        ddp.zero_grad()
+        loss = crit(ddp(b), b.y.view(-1, 3))
+        loss.backward()
+        ddp.sync_gradients()
+        opt.step()
+        return loss
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = _ev(), _ev()
+    e0.record()
+    for i in range(K):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "topo_train_graphs_per_sec", "value": world * K * B / (float(ms) * 1e-3),
+                          "unit": "graphs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": float(ms) / K,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                          "final_loss": float(loss),
+                          "config": {"workload": "BASELINE cfg3: TopologicalGNN(14,16,3) train step, NSFNET graphs, "
+                                                 f"batch {B}/GPU, SGD(0.1, 0.9), flat grad all-reduce x{world}"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- cfg 5
+def run_stress(args):
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    N, LINKS, H = 10000, 40000, 256
+    if args.impl == "reference":
+        from oracle import TopologicalGNNOracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        m = TopologicalGNNOracle(N, H, 3, 4, dropout_p=0.0, factorised_nnconv=True).eval()
+        hb = synthetic.random_topology_store(N, LINKS, seed=2).host_batch(0, 1)
+        with torch.no_grad():
+            m(hb)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                m(hb)
+            dt = (time.perf_counter() - t0) / 5
+        print(json.dumps({"impl": "reference", "metric": "topo_stress_fwd_ms", "value": dt * 1e3, "unit": "ms",
+                          "cpu_baseline": {"kind": "port", "cores": os.cpu_count(),
+                                           "sample": "5 forwards, factorised NNConv (direct form needs 21 GB)"}}), flush=True)
+        return
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = TopologicalGNN(N, H, 3, edge_dim=4, dropout_p=0.0).to(dev)
+    b = synthetic.random_topology_store(N, LINKS, seed=2).to(dev).collate(range(0, 1))
+    E = b.num_edges
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def timed(fn, reps=20):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = _ev(), _ev()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    model.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            model(b)
+        fwd_ms = timed(lambda: model(b))
+    model.train()
+
+    def fb():
+        model.zero_grad(set_to_none=True)
+        torch.nn.SmoothL1Loss()(model(b), b.y.view(-1, 3)).backward()
+    for _ in range(3):
+        fb()
+    fb_ms = timed(fb)
+    conv_bytes = 8 * H * N + 4 * (N + 1) + 4 * E + 16 * E
+    print(json.dumps({"metric": "topo_stress_fwd_ms", "value": fwd_ms, "unit": "ms", "n_gpus": 1,
+                      "higher_is_better": False, "fwd_bwd_ms": fb_ms, "dtype": "f32", "data": "synthetic",
+                      "alg_bytes": {"conv_fwd_each": conv_bytes, "fwd_total": 2 * conv_bytes + 4 * H * N + 4 * 2 + 12},
+                      "config": {"workload": f"BASELINE cfg5: TopologicalGNN({N},{H},3), one graph, {N} nodes, {E} directed "
+                                             "edges; L2 flushed between iterations"}}), flush=True)
