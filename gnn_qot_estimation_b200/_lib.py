@@ -58,7 +58,8 @@ SIGNATURES = {
     "qot_nnconv_bwd_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_nnconv_bwd": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, i64, i64, i64, C.c_float,
                                  P, P, P, P, P, sz, vp]),
-    "qot_pool_mlp_fwd": (C.c_int, [P, P, i64, i64, P, P, P, P, P, P, P, P, vp]),
+    "qot_pool_mlp_fwd_workspace_bytes": (sz, [i64, i64, i64]),
+    "qot_pool_mlp_fwd": (C.c_int, [P, P, i64, i64, i64, P, P, P, P, P, P, P, P, P, sz, vp]),
     "qot_pool_mlp_bwd_workspace_bytes": (sz, [i64, i64]),
     "qot_pool_mlp_bwd": (C.c_int, [P, P, P, P, P, i64, i64, i64, P, P, P, P, P, P, P, P, sz, vp]),
     "qot_lightpath_lut_ptr_workspace_bytes": (sz, [i64]),

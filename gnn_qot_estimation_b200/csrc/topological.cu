@@ -448,13 +448,52 @@ nnconv_bwd_src_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
 }
 
 // ===========================================================================
-// global_mean_pool + MLP head: one warp per graph, lane c owns channels c, c+32, ...
+// global_mean_pool + MLP head.
+//   stage 1 (pool_partial_kernel): block (g, s) sums rows of chunk s of graph g -- 256 threads =
+//           H channels x 256/H row lanes, coalesced rows, row lanes combined in a fixed order;
+//           S = ceil(avg graph size / 256) chunks so a 10k-node graph spreads over 40 blocks;
+//   stage 2 (pool_mlp_fwd_kernel): one warp per graph adds the S partials in order, divides by
+//           the node count, and runs Linear - LeakyReLU - (dropout mask) - Linear.
 // ===========================================================================
 constexpr int kPoolWarps = 4;
 constexpr int kMaxH = 256;
+constexpr int kPoolMaxSplit = 64;
+
+static int pool_split(int64_t N, int64_t B) {
+  const int64_t avg = B > 0 ? cdiv(N, B) : 0;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(kPoolMaxSplit, cdiv(avg, 256))));
+}
+
+__device__ __forceinline__ void pool_chunk(const int64_t* __restrict__ gptr, int64_t g, int s, int S,
+                                           int64_t& r0, int64_t& r1) {
+  const int64_t n0 = gptr[g], n1 = gptr[g + 1];
+  const int64_t per = (n1 - n0 + S - 1) / S;
+  r0 = min(n0 + s * per, n1);
+  r1 = min(r0 + per, n1);
+}
+
+__global__ void __launch_bounds__(256)
+pool_partial_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int H, int S,
+                    float* __restrict__ partial) {
+  __shared__ float s_acc[256];
+  const int64_t g = blockIdx.x;
+  const int s = blockIdx.y;
+  const int c = threadIdx.x % H, rl = threadIdx.x / H, RL = 256 / H;
+  int64_t r0, r1;
+  pool_chunk(gptr, g, s, S, r0, r1);
+  float a = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += RL) a += x[r * H + c];
+  s_acc[threadIdx.x] = a;
+  __syncthreads();
+  if (rl == 0) {
+    float t = 0.f;
+    for (int k = 0; k < RL; ++k) t += s_acc[k * H + c];
+    partial[(g * S + s) * H + c] = t;
+  }
+}
 
 __global__ void __launch_bounds__(kPoolWarps * 32)
-pool_mlp_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int64_t B, int H,
+pool_mlp_fwd_kernel(const float* __restrict__ partial, int S, const int64_t* __restrict__ gptr, int64_t B, int H,
                     const float* __restrict__ W1, const float* __restrict__ b1,
                     const float* __restrict__ W2, const float* __restrict__ b2,
                     const float* __restrict__ hmask, float* __restrict__ pooled,
@@ -467,7 +506,7 @@ pool_mlp_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ gpt
   const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
   for (int c = lane; c < H; c += 32) {
     float a = 0.f;
-    for (int64_t n = n0; n < n1; ++n) a += x[n * H + c];
+    for (int s = 0; s < S; ++s) a += partial[(g * S + s) * H + c];
     a *= inv;
     s_p[warp][c] = a;
     if (pooled) pooled[g * H + c] = a;
@@ -488,11 +527,12 @@ pool_mlp_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ gpt
   if (lane < QOT_OUT) out[g * QOT_OUT + lane] = (lane == 0 ? o[0] : lane == 1 ? o[1] : o[2]) + b2[lane];
 }
 
+// backward, per graph: dhid, act (for the weight gradients) and dpool [B,H] = W1^T dhid / n_g
 __global__ void __launch_bounds__(kPoolWarps * 32)
 pool_mlp_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hid,
                     const float* __restrict__ hmask, const int64_t* __restrict__ gptr, int64_t B, int H,
                     const float* __restrict__ W1, const float* __restrict__ W2,
-                    float* __restrict__ dx, float* __restrict__ dhid, float* __restrict__ act) {
+                    float* __restrict__ dpool, float* __restrict__ dhid, float* __restrict__ act) {
   __shared__ float s_d[kPoolWarps][kMaxH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t g = static_cast<int64_t>(blockIdx.x) * kPoolWarps + warp;
@@ -513,9 +553,21 @@ pool_mlp_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hi
   for (int c = lane; c < H; c += 32) {
     float dp = 0.f;
     for (int u = 0; u < H; ++u) dp = fmaf(W1[u * H + c], s_d[warp][u], dp);
-    dp *= inv;
-    for (int64_t n = n0; n < n1; ++n) dx[n * H + c] = dp;
+    dpool[g * H + c] = dp * inv;
   }
+}
+
+// dx[n,:] = dpool[graph(n),:]: block (g, s) broadcasts over its chunk of rows
+__global__ void __launch_bounds__(256)
+pool_bwd_rows_kernel(const float* __restrict__ dpool, const int64_t* __restrict__ gptr, int H, int S,
+                     float* __restrict__ dx) {
+  const int64_t g = blockIdx.x;
+  const int s = blockIdx.y;
+  const int c = threadIdx.x % H, rl = threadIdx.x / H, RL = 256 / H;
+  int64_t r0, r1;
+  pool_chunk(gptr, g, s, S, r0, r1);
+  const float v = dpool[g * H + c];
+  for (int64_t r = r0 + rl; r < r1; r += RL) dx[r * H + c] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -662,16 +714,27 @@ extern "C" int qot_nnconv_bwd(const float* yr, const int32_t* rowptr, const int3
   return qot_colsum(dyr + (K_ + 1) * H, (K_ + 2) * H, N, H, dbias, csws, csb, stream_);
 }
 
-extern "C" int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t B, int64_t H,
+extern "C" size_t qot_pool_mlp_fwd_workspace_bytes(int64_t N, int64_t B, int64_t H) {
+  if (N < 0 || B < 0 || H <= 0) return 0;
+  return align_up(static_cast<size_t>(std::max<int64_t>(B, 1)) * pool_split(N, B) * H * 4) + 256;
+}
+
+extern "C" int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
                                 const float* W1, const float* b1, const float* W2, const float* b2,
                                 const float* hmask, float* pooled, float* hid, float* out,
-                                void* stream_) {
+                                void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(B >= 0 && H > 0 && H <= kMaxH, "qot_pool_mlp_fwd: H must be in [1,256]");
+  QOT_REQUIRE(B >= 0 && N >= 0 && h_ok(H), "qot_pool_mlp_fwd: H must be 16/32/64/128/256 (got %lld)", (long long)H);
   if (B == 0) return QOT_OK;
-  QOT_REQUIRE(x && gptr && W1 && b1 && W2 && b2 && out, "qot_pool_mlp_fwd: null argument");
+  QOT_REQUIRE(gptr && W1 && b1 && W2 && b2 && out && (N == 0 || x), "qot_pool_mlp_fwd: null argument");
+  QOT_REQUIRE(ws && ws_bytes >= qot_pool_mlp_fwd_workspace_bytes(N, B, H), "qot_pool_mlp_fwd: workspace too small");
+  QOT_REQUIRE(B <= 0x7fffffffll, "qot_pool_mlp_fwd: too many graphs for one launch");
+  const int S = pool_split(N, B);
+  float* partial = static_cast<float*>(ws);
+  pool_partial_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(x, gptr, static_cast<int>(H), S, partial);
+  QOT_LAUNCH_CHECK();
   pool_mlp_fwd_kernel<<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
-      x, gptr, B, static_cast<int>(H), W1, b1, W2, b2, hmask, pooled, hid, out);
+      partial, S, gptr, B, static_cast<int>(H), W1, b1, W2, b2, hmask, pooled, hid, out);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -679,7 +742,7 @@ extern "C" int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t B, 
 extern "C" size_t qot_pool_mlp_bwd_workspace_bytes(int64_t B, int64_t H) {
   if (B < 0 || H <= 0) return 0;
   const int64_t b = std::max<int64_t>(B, 1);
-  return 2 * align_up(static_cast<size_t>(b) * H * 4) + qot_wgrad_workspace_bytes(b, H, H) +
+  return 3 * align_up(static_cast<size_t>(b) * H * 4) + qot_wgrad_workspace_bytes(b, H, H) +
          qot_wgrad_workspace_bytes(b, QOT_OUT, H) + qot_colsum_workspace_bytes(b, H) + 256;
 }
 
@@ -689,21 +752,27 @@ extern "C" int qot_pool_mlp_bwd(const float* dout, const float* pooled, const fl
                                 float* dW1, float* db1, float* dW2, float* db2,
                                 void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(B > 0 && N >= 0 && H > 0 && H <= kMaxH, "qot_pool_mlp_bwd: bad shape");
+  QOT_REQUIRE(B > 0 && N >= 0 && h_ok(H), "qot_pool_mlp_bwd: bad shape");
   QOT_REQUIRE(dout && pooled && hid && gptr && W1 && W2 && dW1 && db1 && dW2 && db2 && (N == 0 || dx),
               "qot_pool_mlp_bwd: null argument");
   QOT_REQUIRE(ws && ws_bytes >= qot_pool_mlp_bwd_workspace_bytes(B, H), "qot_pool_mlp_bwd: workspace too small");
   Carver c(ws);
   float* dhid = c.take<float>(B * H);
   float* act = c.take<float>(B * H);
+  float* dpool = c.take<float>(B * H);
   const size_t w1b = qot_wgrad_workspace_bytes(B, H, H), w2b = qot_wgrad_workspace_bytes(B, QOT_OUT, H);
   const size_t csb = qot_colsum_workspace_bytes(B, H);
   void* w1ws = c.take<char>(w1b);
   void* w2ws = c.take<char>(w2b);
   void* csws = c.take<char>(csb);
   pool_mlp_bwd_kernel<<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
-      dout, hid, hmask, gptr, B, static_cast<int>(H), W1, W2, dx, dhid, act);
+      dout, hid, hmask, gptr, B, static_cast<int>(H), W1, W2, dpool, dhid, act);
   QOT_LAUNCH_CHECK();
+  if (N > 0) {
+    const int S = pool_split(N, B);
+    pool_bwd_rows_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(dpool, gptr, static_cast<int>(H), S, dx);
+    QOT_LAUNCH_CHECK();
+  }
   int rc;
   if ((rc = qot_wgrad(dhid, H, pooled, H, B, H, H, dW1, H, w1ws, w1b, stream_))) return rc;
   if ((rc = qot_colsum(dhid, H, B, H, db1, csws, csb, stream_))) return rc;

@@ -585,8 +585,10 @@ class _PoolMlpFn(torch.autograd.Function):
         pooled = torch.empty(B, H, dtype=torch.float32, device=dev)
         hid = torch.empty(B, H, dtype=torch.float32, device=dev)
         out = torch.empty(B, 3, dtype=torch.float32, device=dev)
-        check(L.qot_pool_mlp_fwd(ptr(x), ptr(gptr), B, H, ptr(ts[0]), ptr(ts[1]), ptr(ts[2]), ptr(ts[3]),
-                                 ptr(hmask), ptr(pooled), ptr(hid), ptr(out), stream()), "qot_pool_mlp_fwd")
+        ws = _ws(L.qot_pool_mlp_fwd_workspace_bytes(N, B, H), dev)
+        check(L.qot_pool_mlp_fwd(ptr(x), ptr(gptr), N, B, H, ptr(ts[0]), ptr(ts[1]), ptr(ts[2]), ptr(ts[3]),
+                                 ptr(hmask), ptr(pooled), ptr(hid), ptr(out), ptr(ws), ws.numel(), stream()),
+              "qot_pool_mlp_fwd")
         ctx.save_for_backward(gptr, ts[0], ts[2], pooled, hid, hmask)
         ctx.N = N
         return out

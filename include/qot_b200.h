@@ -193,9 +193,11 @@ int qot_nnconv_bwd(const float* yr, const int32_t* rowptr, const int32_t* src,
 /* ------------------------------------------------------------------------ */
 /* pooled [B,H] (saved for backward), hid [B,H] pre-activation (saved), out [B,3].
  * head: Linear(H,H) - LeakyReLU(0.01) - Linear(H,3). */
-int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t B, int64_t H,
+size_t qot_pool_mlp_fwd_workspace_bytes(int64_t N, int64_t B, int64_t H);
+int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
                      const float* W1, const float* b1, const float* W2, const float* b2,
-                     const float* hmask, float* pooled, float* hid, float* out, void* stream);
+                     const float* hmask, float* pooled, float* hid, float* out,
+                     void* ws, size_t ws_bytes, void* stream);
 
 size_t qot_pool_mlp_bwd_workspace_bytes(int64_t B, int64_t H);
 /* dx [N,H] (every node of graph g gets dpooled_g / n_g), dW1,db1,dW2,db2.
