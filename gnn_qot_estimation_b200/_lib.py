@@ -49,7 +49,8 @@ SIGNATURES = {
     "qot_wgrad": (C.c_int, [P, i64, P, i64, i64, i64, i64, P, i64, P, sz, vp]),
     "qot_colsum_workspace_bytes": (sz, [i64, i64]),
     "qot_colsum": (C.c_int, [P, i64, i64, i64, P, P, sz, vp]),
-    "qot_segment_sum": (C.c_int, [P, P, P, i64, i64, P, vp]),
+    "qot_segment_sum_workspace_bytes": (sz, [i64, i64, i64]),
+    "qot_segment_sum": (C.c_int, [P, P, P, i64, i64, i64, P, P, sz, vp]),
     "qot_tconv_fwd": (C.c_int, [P, P, P, P, P, P, i64, i64, C.c_float, P, P, P, P, vp]),
     "qot_tconv_bwd_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_tconv_bwd": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, i64, i64, i64,

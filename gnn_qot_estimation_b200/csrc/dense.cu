@@ -40,25 +40,39 @@ gemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const int64
   const bool a_k_contig = (a_cs == 1);
   const bool b_n_contig = (b_cs == 1);
 
+  // thread -> element maps of the two tile loaders (4 elements each), fixed over the k loop
+  int a_m[4], a_k[4], b_n[4], b_k[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 256;                   // 0..1023
+    if (a_k_contig) { a_k[it] = idx % BK; a_m[it] = idx / BK; } else { a_m[it] = idx % BM; a_k[it] = idx / BM; }
+    if (b_n_contig) { b_n[it] = idx % BN; b_k[it] = idx / BN; } else { b_k[it] = idx % BK; b_n[it] = idx / BK; }
+  }
+  int64_t a_row[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int64_t gm = m0 + a_m[it];
+    a_row[it] = gm < M ? (gather ? gather[gm] : gm) : -1;
+  }
+  auto fetch = [&](int64_t k0, float (&av)[4], float (&bv)[4]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int64_t gk = k0 + a_k[it];
+      av[it] = (a_row[it] >= 0 && gk < kend) ? A[a_row[it] * a_rs + gk * a_cs] : 0.f;
+      const int64_t gn = n0 + b_n[it], gk2 = k0 + b_k[it];
+      bv[it] = (gn < Nc && gk2 < kend) ? B[gk2 * b_rs + gn * b_cs] : 0.f;
+    }
+  };
+  float av[4], bv[4];
+  if (kbeg < kend) fetch(kbeg, av, bv);
   for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int idx = tid + it * 256;                 // 0..1023
-      int am, ak;
-      if (a_k_contig) { ak = idx % BK; am = idx / BK; } else { am = idx % BM; ak = idx / BM; }
-      const int64_t gm = m0 + am, gk = k0 + ak;
-      float v = 0.f;
-      if (gm < M && gk < kend) {
-        const int64_t r = gather ? gather[gm] : gm;
-        v = A[r * a_rs + gk * a_cs];
-      }
-      As[ak][am] = v;
-      int bn, bk;
-      if (b_n_contig) { bn = idx % BN; bk = idx / BN; } else { bk = idx % BK; bn = idx / BK; }
-      const int64_t gn = n0 + bn, gk2 = k0 + bk;
-      Bs[bk][bn] = (gn < Nc && gk2 < kend) ? B[gk2 * b_rs + gn * b_cs] : 0.f;
+      As[a_k[it]][a_m[it]] = av[it];
+      Bs[b_k[it]][b_n[it]] = bv[it];
     }
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK, av, bv);       // next tile in flight while this one is consumed
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
@@ -106,8 +120,10 @@ colsum_stage1_kernel(const float* __restrict__ A, int64_t lda, int64_t R, int64_
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kColsumRows;
   const int64_t r1 = min(R, r0 + kColsumRows);
   float acc = 0.f;
-  if (c < Nc)
+  if (c < Nc) {
+#pragma unroll 8
     for (int64_t r = r0 + ry; r < r1; r += 8) acc += A[r * lda + c];
+  }
   s[ry][cx] = acc;
   __syncthreads();
   if (ry == 0 && c < Nc) {
@@ -118,29 +134,57 @@ colsum_stage1_kernel(const float* __restrict__ A, int64_t lda, int64_t R, int64_
   }
 }
 
-// out[r,:] = sum_{p in [rowptr[r],rowptr[r+1])} X[idx[p],:]   (H/4 float4 lanes per row)
+// out[r,:] = sum_{p in [rowptr[r],rowptr[r+1])} X[idx[p],:].  Block (r, s) sums chunk s of row r:
+// 256 threads = H/4 float4 lanes x 1024/H entry lanes, combined in a fixed order; S > 1 chunks per
+// row go through `partial` and a second fixed-order pass (few long rows: embedding gradients).
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ X, const int32_t* __restrict__ rowptr,
-                   const int32_t* __restrict__ idx, int64_t R, int H, float* __restrict__ out) {
-  const int vec = H / 4;
-  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t r = t / vec;
-  const int l = static_cast<int>(t % vec);
-  if (r >= R) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                   const int32_t* __restrict__ idx, int H, int S, float* __restrict__ out) {
+  __shared__ float4 s_acc[256];
+  const int vec = H / 4, EL = 256 / vec;
+  const int l = threadIdx.x % vec, el = threadIdx.x / vec;
+  const int64_t r = blockIdx.x;
+  const int s = blockIdx.y;
   const int32_t beg = rowptr[r], end = rowptr[r + 1];
-  for (int32_t p = beg; p < end; ++p) {
+  const int32_t per = (end - beg + S - 1) / S;
+  const int32_t p0 = min(beg + s * per, end), p1 = min(p0 + per, end);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int32_t p = p0 + el; p < p1; p += EL) {
     const float4 v = *reinterpret_cast<const float4*>(X + static_cast<int64_t>(idx[p]) * H + 4 * l);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  *reinterpret_cast<float4*>(out + r * H + 4 * l) = acc;
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  if (el == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < EL; ++k) {
+      const float4 v = s_acc[k * vec + l];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (r * S + s) * H + 4 * l) = t;
+  }
+}
+// out[r, c] = sum_s partial[(r*S+s)*H + c], s ascending
+__global__ void segment_sum_final_kernel(const float* __restrict__ partial, int64_t RH, int H, int S,
+                                         float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= RH) return;
+  const int64_t r = i / H, c = i % H;
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += partial[(r * S + s) * H + c];
+  out[i] = a;
+}
+static int segment_split(int64_t entries, int64_t R) {
+  const int64_t avg = R > 0 ? cdiv(entries, R) : 0;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, cdiv(avg, 512))));
 }
 
 static int pick_splits(int64_t R, int64_t tiles) {
-  // enough K-slices to fill the machine, each at least 256 rows deep; depends on
+  // enough K-slices to fill the machine, each at least 64 rows deep; depends on
   // sizes only, so the reduction order is reproducible.
-  int64_t want = std::max<int64_t>(1, (2 * kNumSMs) / std::max<int64_t>(tiles, 1));
-  int64_t cap = std::max<int64_t>(1, R / 256);
+  int64_t want = std::max<int64_t>(1, (4 * kNumSMs) / std::max<int64_t>(tiles, 1));
+  int64_t cap = std::max<int64_t>(1, R / 64);
   return static_cast<int>(std::min<int64_t>(std::min(want, cap), 1024));
 }
 
@@ -219,14 +263,27 @@ extern "C" int qot_colsum(const float* A, int64_t lda, int64_t R, int64_t Nc, fl
   return QOT_OK;
 }
 
-extern "C" int qot_segment_sum(const float* X, const int32_t* rowptr, const int32_t* idx, int64_t R,
-                               int64_t H, float* out, void* stream_) {
+extern "C" size_t qot_segment_sum_workspace_bytes(int64_t entries, int64_t R, int64_t H) {
+  if (entries < 0 || R < 0 || H <= 0) return 0;
+  return align_up(static_cast<size_t>(std::max<int64_t>(R, 1)) * segment_split(entries, R) * H * 4) + 256;
+}
+
+extern "C" int qot_segment_sum(const float* X, const int32_t* rowptr, const int32_t* idx, int64_t entries,
+                               int64_t R, int64_t H, float* out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(R >= 0 && H > 0 && H % 4 == 0, "qot_segment_sum: H must be a positive multiple of 4");
+  QOT_REQUIRE(R >= 0 && entries >= 0 && (H == 16 || H == 32 || H == 64 || H == 128 || H == 256),
+              "qot_segment_sum: H must be 16/32/64/128/256");
   if (R == 0) return QOT_OK;
-  QOT_REQUIRE(X && rowptr && idx && out, "qot_segment_sum: null operand");
-  const int64_t threads = R * (H / 4);
-  segment_sum_kernel<<<static_cast<unsigned>(cdiv(threads, 256)), 256, 0, stream>>>(X, rowptr, idx, R, static_cast<int>(H), out);
+  QOT_REQUIRE(rowptr && out && (entries == 0 || (X && idx)), "qot_segment_sum: null operand");
+  QOT_REQUIRE(ws && ws_bytes >= qot_segment_sum_workspace_bytes(entries, R, H), "qot_segment_sum: workspace too small");
+  QOT_REQUIRE(R <= 0x7fffffffll, "qot_segment_sum: too many rows for one launch");
+  const int S = segment_split(entries, R);
+  float* dst = S == 1 ? out : static_cast<float*>(ws);
+  segment_sum_kernel<<<dim3(static_cast<unsigned>(R), S), 256, 0, stream>>>(X, rowptr, idx, static_cast<int>(H), S, dst);
   QOT_LAUNCH_CHECK();
+  if (S > 1) {
+    segment_sum_final_kernel<<<static_cast<unsigned>(cdiv(R * H, 256)), 256, 0, stream>>>(dst, R * H, static_cast<int>(H), S, out);
+    QOT_LAUNCH_CHECK();
+  }
   return QOT_OK;
 }

@@ -316,7 +316,7 @@ extern "C" int qot_build_csr(const int64_t* edge_index, int64_t E, int64_t N, in
     csr_sort_rows_kernel<<<static_cast<unsigned>(cdiv(N, threads)), threads, 0, stream>>>(
         other, E, N, add_self, rowptr, eid, nbr, big_count, big_rows);
     QOT_LAUNCH_CHECK();
-    csr_sort_big_rows_kernel<<<kNumSMs, 256, 0, stream>>>(other, add_self, rowptr, eid, nbr, big_count, big_rows);
+    csr_sort_big_rows_kernel<<<32, 256, 0, stream>>>(other, add_self, rowptr, eid, nbr, big_count, big_rows);
     QOT_LAUNCH_CHECK();
   }
   return QOT_OK;

@@ -278,14 +278,17 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, const int32_t* __restrict__
   }
 }
 
-// sum of per-block partials, fixed order
-__global__ void sum_partials_kernel(const float* __restrict__ part, int64_t nblocks, int64_t n,
-                                    float* __restrict__ out) {
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+// sum of per-block partials in a fixed order: one block per 8 outputs, 32 lanes stride over the
+// partial blocks, then a shuffle tree (the order depends on nblocks only)
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int64_t nblocks, int64_t n, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (idx >= n) return;
   float a = 0.f;
-  for (int64_t b = 0; b < nblocks; ++b) a += part[b * n + idx];
-  out[idx] = a;
+  for (int64_t b = lane; b < nblocks; b += 32) a += part[b * n + idx];
+  a = warp_sum(a);
+  if (lane == 0) out[idx] = a;
 }
 
 // ===========================================================================
@@ -649,7 +652,7 @@ extern "C" int qot_tconv_bwd(const float* qkvs, const int32_t* rowptr, const int
   QOT_DISPATCH_H(H, (tconv_bwd_src_kernel<LANES, VEC><<<static_cast<unsigned>(cdiv(N * LANES, 256)), 256, 0, stream>>>(
                         qkvs, t_rowptr, t_dst, t_eid, wa, wda, N, dqkvs)));
   QOT_LAUNCH_CHECK();
-  sum_partials_kernel<<<static_cast<unsigned>(cdiv(H * D_, 256)), 256, 0, stream>>>(part, nb, H * D_, dWe);
+  sum_partials_kernel<<<static_cast<unsigned>(cdiv(H * D_, 8)), 256, 0, stream>>>(part, nb, H * D_, dWe);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -706,7 +709,7 @@ extern "C" int qot_nnconv_bwd(const float* yr, const int32_t* rowptr, const int3
   QOT_DISPATCH_H(H, (nnconv_bwd_src_kernel<LANES, VEC><<<static_cast<unsigned>(cdiv(N * LANES, 256)), 256, 0, stream>>>(
                         rowptr, t_rowptr, t_dst, t_eid, edge_attr, W1, b1, N, dyr)));
   QOT_LAUNCH_CHECK();
-  sum_partials_kernel<<<1, 64, 0, stream>>>(part, nb, 40, w1sum);
+  sum_partials_kernel<<<5, 256, 0, stream>>>(part, nb, 40, w1sum);
   QOT_LAUNCH_CHECK();
   QOT_CUDA(cudaMemcpyAsync(dW1, w1sum, K_ * D_ * 4, cudaMemcpyDeviceToDevice, stream));
   QOT_CUDA(cudaMemcpyAsync(db1, w1sum + K_ * D_, K_ * 4, cudaMemcpyDeviceToDevice, stream));

@@ -7,8 +7,8 @@ data path:
 * inference: rank r owns the contiguous graph range ``shard_range(G, r, W)``; every rank writes
   its own outputs; no collective.
 * training: per-rank disjoint batches, replicated parameters (5,291 floats = 21 KB for
-  TopologicalGNN), and ONE all-reduce per step over a flat fp32 gradient buffer that the backward
-  kernels' results accumulate into directly (``p.grad`` are views of it).  With equal per-rank
+  TopologicalGNN), and ONE all-reduce per step over a flat fp32 gradient buffer (one gather
+  kernel in, ``p.grad`` re-pointed at its slices afterwards -- no copy back).  With equal per-rank
   batch sizes and a mean-reduction loss, the averaged gradient equals the gradient of the
   concatenated batch -- checked in tests/test_distributed_cpu.py (gloo, world 2) and
   tests/test_ddp_gpu.py (nccl).
@@ -41,8 +41,11 @@ def world_info():
 
 
 class FlatGradBuffer:
-    """One flat buffer (fp32 for the product modules) holding every parameter gradient; ``p.grad`` are views into it, so
-    autograd accumulates straight into the buffer NCCL reduces."""
+    """One flat buffer (fp32 for the product modules) for every parameter gradient -- the buffer the
+    collective reduces.  Autograd writes fresh ``p.grad`` tensors (no accumulate-adds, no zero
+    fill); ``all_reduce_mean`` gathers them into the flat buffer with ONE concatenation kernel,
+    reduces it once, and re-points every ``p.grad`` at its slice (views, no copy back) so the
+    optimizer reads the averaged values."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -57,32 +60,34 @@ class FlatGradBuffer:
             self.offsets.append(n)
             n += p.numel()
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
-        self.attach()
 
     def view_of(self, i: int) -> torch.Tensor:
         p = self.params[i]
         return self.flat[self.offsets[i]: self.offsets[i] + p.numel()].view_as(p)
 
-    def attach(self) -> None:
-        """(Re-)points every ``p.grad`` at its slice; a gradient that was set elsewhere (e.g. after
-        ``optimizer.zero_grad(set_to_none=True)`` + backward) is copied in first."""
-        for i, p in enumerate(self.params):
-            v = self.view_of(i)
-            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
-            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                p.grad = v
-
     def zero(self) -> None:
-        self.flat.zero_()
-        self.attach()
+        """Drops the gradients (``set_to_none``): the next backward writes them afresh."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self) -> None:
+        """Copies the current ``p.grad`` tensors into the flat buffer (one kernel) and re-points
+        them at their slices.  Parameters without a gradient contribute zeros."""
+        views = [self.view_of(i) for i in range(len(self.params))]
+        if all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, views)):
+            return                                                 # already views of the flat buffer
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(pieces, out=self.flat)
+        for p, v in zip(self.params, views):
+            p.grad = v
 
     def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None) -> None:
-        self.attach()
         rank, world = world_info()
-        if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / world)
+        if world == 1:
+            return                                                 # nothing to exchange: leave p.grad alone
+        self.gather()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.mul_(1.0 / world)
 
 
 class GraphDataParallel(torch.nn.Module):
@@ -109,7 +114,7 @@ class GraphDataParallel(torch.nn.Module):
     def forward(self, *a, **k):
         return self.module(*a, **k)
 
-    def zero_grad(self, set_to_none: bool = False) -> None:   # views must survive: never set to None
+    def zero_grad(self, set_to_none: bool = True) -> None:
         self.grads.zero()
 
     def sync_gradients(self) -> None:

@@ -47,19 +47,13 @@ class GraphedTrainStep:
 
     def _body(self) -> torch.Tensor:
         self.static._cache = {}                      # the CSR of the batch is rebuilt inside the step
-        if self.ddp is not None:
-            self.ddp.zero_grad()
-        else:
-            self.opt.zero_grad(set_to_none=False) if self._grads_exist() else None
+        (self.ddp or self.opt).zero_grad(set_to_none=True)   # backward writes fresh gradients
         loss = self.crit((self.ddp or self.model)(self.static), self.target_of(self.static))
         loss.backward()
         if self.ddp is not None:
             self.ddp.sync_gradients()
         self.opt.step()
         return loss.detach()
-
-    def _grads_exist(self) -> bool:
-        return all(p.grad is not None for p in self.model.parameters() if p.requires_grad)
 
     def step(self, batch: Batch) -> torch.Tensor:
         """Copies ``batch`` into the static buffers and replays the captured step; returns the

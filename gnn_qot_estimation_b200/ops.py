@@ -432,8 +432,9 @@ class _NodeLinearFn(torch.autograd.Function):
                 V = x.shape[0]
                 csr = _ids_csr(ids, V)
                 dx = torch.empty(V, K, dtype=torch.float32, device=dev)
-                check(L.qot_segment_sum(ptr(dxr), ptr(csr.rowptr), ptr(csr.eid), V, K, ptr(dx), stream()),
-                      "qot_segment_sum")
+                ws = _ws(L.qot_segment_sum_workspace_bytes(M, V, K), dev)
+                check(L.qot_segment_sum(ptr(dxr), ptr(csr.rowptr), ptr(csr.eid), M, V, K, ptr(dx),
+                                        ptr(ws), ws.numel(), stream()), "qot_segment_sum")
         if need_w:
             xr = x if ids is None else _gather_rows(x, ids)
             dW = torch.empty(Nc, K, dtype=torch.float32, device=dev)         # dy^T @ x

@@ -133,11 +133,13 @@ size_t qot_colsum_workspace_bytes(int64_t R, int64_t Nc);
 int qot_colsum(const float* A, int64_t lda, int64_t R, int64_t Nc, float* out,
                void* ws, size_t ws_bytes, void* stream);
 
-/* out[r,:] = sum over p in [rowptr[r],rowptr[r+1]) of X[idx[p],:]  (H % 4 == 0).
+/* out[r,:] = sum over p in [rowptr[r],rowptr[r+1]) of X[idx[p],:]  (H in 16/32/64/128/256;
+ * `entries` = rowptr[R]).  Long rows are split over blocks and combined in a fixed order.
  * With the CSR of node_ids this is the deterministic embedding backward
  * (topological_training/models.py:52): dEmb[v] = sum of dX rows whose id is v. */
-int qot_segment_sum(const float* X, const int32_t* rowptr, const int32_t* idx, int64_t R,
-                    int64_t H, float* out, void* stream);
+size_t qot_segment_sum_workspace_bytes(int64_t entries, int64_t R, int64_t H);
+int qot_segment_sum(const float* X, const int32_t* rowptr, const int32_t* idx, int64_t entries,
+                    int64_t R, int64_t H, float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* (2) TransformerConv edge phase (topological_training/models.py:15-17,53)   */

@@ -44,16 +44,23 @@ def test_flat_grad_buffer_single_process():
     assert fb.flat.numel() == sum(p.numel() for p in m.parameters())
     m(torch.ones(5, 4)).sum().backward()
     ref = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
-    assert torch.equal(fb.flat, ref)                      # autograd accumulated into the views
-    for p, i in zip(m.parameters(), range(4)):
-        assert p.grad.data_ptr() == fb.view_of(i).data_ptr()
-    # a foreign zero_grad(set_to_none=True) drops the views; attach() copies the new grads back in
-    torch.optim.SGD(m.parameters(), lr=0.1).zero_grad(set_to_none=True)
-    m(torch.ones(5, 4)).sum().backward()
-    fb.all_reduce_mean()
+    fb.gather()
     assert torch.equal(fb.flat, ref)
+    for i, p in enumerate(m.parameters()):                  # p.grad now aliases the flat buffer
+        assert p.grad.data_ptr() == fb.view_of(i).data_ptr()
+    fb.flat.mul_(0.5)
+    assert torch.equal(torch.cat([p.grad.reshape(-1) for p in m.parameters()]), ref * 0.5)
     fb.zero()
-    assert float(fb.flat.abs().sum()) == 0.0 and all(float(p.grad.abs().sum()) == 0.0 for p in m.parameters())
+    assert all(p.grad is None for p in m.parameters())
+    m(torch.ones(5, 4)).sum().backward()                    # fresh gradients, not accumulated
+    fb.gather()
+    assert torch.equal(fb.flat, ref)
+    # a parameter that received no gradient contributes zeros
+    fb.zero()
+    m[0](torch.ones(5, 4)).sum().backward()
+    fb.gather()
+    n0 = sum(p.numel() for p in m[0].parameters())
+    assert torch.equal(fb.flat[:n0], ref.new_tensor([5.0] * 12 + [5.0] * 3)) and float(fb.flat[n0:].abs().sum()) == 0.0
 
 
 def _worker(rank, world, port, q):
@@ -83,7 +90,7 @@ def _worker(rank, world, port, q):
         ddp.zero_grad()
         loss_of(ddp, store.host_batch(r.start, r.stop)).backward()
         ddp.sync_gradients()
-        got = ddp.grads.flat.clone()
+        got = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
         # single-process reference: the whole batch on a copy of the same parameters
         ref_model = TopologicalGNNOracle(14, 16, 3, 4, dropout_p=0.0).double()
         ref_model.load_state_dict(model.state_dict())
