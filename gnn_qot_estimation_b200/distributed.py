@@ -85,7 +85,7 @@ class FlatGradBuffer:
         rank, world = world_info()
         if world == 1:
             return                                                 # nothing to exchange: leave p.grad alone
-        self.gather()
+        self.gather()                                              # no-op when p.grad already alias the buffer
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.mul_(1.0 / world)
 

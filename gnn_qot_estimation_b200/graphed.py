@@ -4,8 +4,9 @@ The reference's inner loop (``topological_training/train.py:107-116``: ``zero_gr
 SmoothL1 -> ``backward`` -> ``step``) is ~60 small kernels at batch 512-1024; on a B200 each is a
 few microseconds, so the step is bound by Python / launch latency, not by the GPU.  Every entry
 point of libqot_b200 enqueues on the caller's stream without synchronising, so the whole step --
-CSR build, both conv layers, pooling head, loss, all backward kernels, the flat NCCL gradient
-all-reduce and the SGD update -- is captured once and replayed per batch.
+CSR build, both conv layers, pooling head, loss, all backward kernels (graph A) and the SGD update
+(graph B) -- is captured once and replayed per batch, with the flat NCCL gradient all-reduce issued
+eagerly between the two replays.
 
 Static shapes only (N, E, B fixed, e.g. batches of one topology such as BASELINE cfg 1/3); a batch
 of another shape raises.  Dropout masks drawn with ``torch.rand`` inside the captured region advance
@@ -38,22 +39,34 @@ class GraphedTrainStep:
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             for _ in range(max(warmup, 1)):          # allocates workspaces / optimizer state eagerly
-                self._body()
+                self._front()
+                self._exchange()
+                self.opt.step()
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                self.loss = self._body()
+            # graph A: zero -> forward -> loss -> backward (-> gather into the flat buffer);
+            # graph B: optimizer update.  The gradient all-reduce runs between the two, eagerly on
+            # the same stream: a collective inside a captured region would tie every rank's capture
+            # and replay to NCCL's internal streams for no gain (it is one 21 KB call per step).
+            self.graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_a, stream=self.stream):
+                self.loss = self._front()
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, stream=self.stream):
+                self.opt.step()
         torch.cuda.current_stream().wait_stream(self.stream)
 
-    def _body(self) -> torch.Tensor:
+    def _front(self) -> torch.Tensor:
         self.static._cache = {}                      # the CSR of the batch is rebuilt inside the step
         (self.ddp or self.opt).zero_grad(set_to_none=True)   # backward writes fresh gradients
         loss = self.crit((self.ddp or self.model)(self.static), self.target_of(self.static))
         loss.backward()
         if self.ddp is not None:
-            self.ddp.sync_gradients()
-        self.opt.step()
+            self.ddp.grads.gather()                  # one concatenation kernel; p.grad -> flat views
         return loss.detach()
+
+    def _exchange(self) -> None:
+        if self.ddp is not None:
+            self.ddp.grads.all_reduce_mean()         # eager NCCL all-reduce of the flat buffer
 
     def step(self, batch: Batch) -> torch.Tensor:
         """Copies ``batch`` into the static buffers and replays the captured step; returns the
@@ -67,6 +80,8 @@ class GraphedTrainStep:
         with torch.cuda.stream(self.stream):
             for k in self.shapes:
                 getattr(self.static, k).copy_(getattr(batch, k), non_blocking=True)
-            self.graph.replay()
+            self.graph_a.replay()
+            self._exchange()
+            self.graph_b.replay()
         torch.cuda.current_stream().wait_stream(self.stream)
         return self.loss
