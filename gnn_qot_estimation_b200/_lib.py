@@ -35,6 +35,12 @@ class QotLightpathParams(C.Structure):
                 ("bn_eps", C.c_float), ("is_lut_index", i32)]
 
 
+class QotLpSlot(C.Structure):
+    _fields_ = [("x", P), ("edge_src", P), ("edge_dst", P), ("ptrs", P), ("out", P), ("lut_batch", P),
+                ("lut_node", P), ("n_lut", P), ("status", P),
+                ("cap_nodes", i64), ("cap_edges", i64), ("cap_graphs", i64)]
+
+
 # name -> (restype, argtypes); mirrors include/qot_b200.h one to one
 SIGNATURES = {
     "qot_last_error": (C.c_char_p, []),
@@ -68,6 +74,8 @@ SIGNATURES = {
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, vp]),
+    "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,
+                                           C.POINTER(i64), C.POINTER(i64), vp]),
     "qot_gat_fwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_gat_bwd_workspace_bytes": (sz, [i64]),
     "qot_gat_bwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, P, P, P, P, sz, vp]),

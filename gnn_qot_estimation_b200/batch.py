@@ -191,6 +191,16 @@ class PackedGraphStore:
             lut_ptr = torch.zeros(B + 1, dtype=torch.int64)
             flags = (x[:, self.lut_col] == 1.0).to(torch.int64)
             torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, flags), 0, out=lut_ptr[1:])
-        b = Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
-                  ptr=ptr.clone(), edge_ptr=eptr.clone(), lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
-        return b.pin_memory() if pin else b
+        # the three offset arrays share one [3, B+1] buffer: one H2D copy moves them all
+        if lut_ptr is not None:
+            ptrs = torch.stack([ptr, eptr, lut_ptr])
+            if pin:
+                ptrs = ptrs.pin_memory()
+            ptr_v, eptr_v, lut_v = ptrs[0], ptrs[1], ptrs[2]
+        else:
+            ptr_v, eptr_v, lut_v = ptr.clone(), eptr.clone(), None
+            if pin:
+                ptr_v, eptr_v = ptr_v.pin_memory(), eptr_v.pin_memory()
+        pin_ = (lambda t: None if t is None else t.pin_memory()) if pin else (lambda t: t)
+        return Batch(x=pin_(x), edge_index=pin_(ei), edge_attr=pin_(ea), batch=pin_(bt), node_ids=pin_(nid),
+                     y=pin_(y), ptr=ptr_v, edge_ptr=eptr_v, lut_ptr=lut_v, num_graphs=B, lut_col=self.lut_col)

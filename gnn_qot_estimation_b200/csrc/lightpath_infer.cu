@@ -85,6 +85,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define LP_TRACE(slot) do {} while (0)
 #endif
 
+#ifndef QOT_LP_OCC
+#define QOT_LP_OCC 4                      // resident blocks per SM the register budget is sized for
+#endif
 constexpr int kIW = 8;                    // warps (= graphs) per block
 constexpr int kThreads = kIW * 32;
 constexpr int kMaxN = 64;                 // fast path: nodes staged in shared memory
@@ -279,8 +282,9 @@ __global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t n, int6
   if (i < n) out[i] = in[i];
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
-lp_infer_kernel(const float* __restrict__ x, const int64_t* __restrict__ edge_index, int64_t E,
+__global__ void __launch_bounds__(kThreads, QOT_LP_OCC)
+lp_infer_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
+                const int64_t* __restrict__ edst,
                 const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr,
                 const int64_t* __restrict__ lptr, int64_t N, int64_t B,
                 const float* __restrict__ prep, int lut_col, float* __restrict__ out,
@@ -294,8 +298,6 @@ lp_infer_kernel(const float* __restrict__ x, const int64_t* __restrict__ edge_in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t g = static_cast<int64_t>(blockIdx.x) * kIW + warp;
   const bool active = g < B;
-  const int64_t* __restrict__ esrc = edge_index;
-  const int64_t* __restrict__ edst = edge_index + E;
 
   LP_TRACE(0);
   // ---- (0) weights -> shared memory, asynchronously (lands while the graph data is in flight)
@@ -494,6 +496,19 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
   return QOT_OK;
 }
 
+static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* edst,
+                           const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr, int64_t N,
+                           int64_t B, const float* prepared, int32_t is_lut_index, float* out,
+                           int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut, int32_t* status,
+                           cudaStream_t stream) {
+  const int64_t blocks = cdiv(B, kIW);
+  QOT_REQUIRE(blocks < (1ll << 31) - 1, "qot_lightpath_infer: too many graphs for one launch");
+  lp_infer_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(
+      x, esrc, edst, gptr, eptr, lut_ptr, N, B, prepared, is_lut_index, out, lut_batch, lut_node, n_lut, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
 extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                                    const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
                                    int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
@@ -511,10 +526,78 @@ extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, in
     QOT_CUDA(cudaMemsetAsync(n_lut, 0, 4, stream));
     return QOT_OK;
   }
-  const int64_t blocks = cdiv(B, kIW);
-  QOT_REQUIRE(blocks < (1ll << 31) - 1, "qot_lightpath_infer: too many graphs for one launch");
-  lp_infer_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(
-      x, edge_index, E, gptr, eptr, lut_ptr, N, B, prepared, is_lut_index, out, lut_batch, lut_node, n_lut, status);
-  QOT_LAUNCH_CHECK();
+  return lp_infer_launch(x, edge_index, edge_index + E, gptr, eptr, lut_ptr, N, B, prepared, is_lut_index, out,
+                         lut_batch, lut_node, n_lut, status, stream);
+}
+
+// Host-buffer form of the same call: the batch lives in PINNED HOST memory in the reference layout.
+// Enqueues, on `stream`: H2D of x, of the DESTINATION row of edge_index and of the three offset
+// arrays into the caller's device staging slot; the kernel (the source row is not copied -- the
+// few entries the readout needs, one 32-byte sector per in-edge of a LUT node, are read by the
+// kernel straight from the pinned host buffer over PCIe); D2H of out / lut_batch rows [0, L) and
+// the status word, L = lut_ptr_host[B].  Nothing synchronises: the caller waits on its own event.
+extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,
+                                        const int64_t* gptr_host, const int64_t* eptr_host,
+                                        const int64_t* lut_ptr_host, int64_t N, int64_t B,
+                                        const float* prepared, int32_t is_lut_index,
+                                        const qot_lp_slot_t* slot, float* out_host,
+                                        int64_t* lut_batch_host, int32_t* status_host,
+                                        int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(N > 0 && B > 0 && E >= 0, "qot_lightpath_infer_host: empty batch");
+  QOT_REQUIRE(N < (1ll << 31) - 1, "qot_lightpath_infer_host: N exceeds int32 range");
+  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_host: is_lut_index out of range");
+  QOT_REQUIRE(x_host && gptr_host && eptr_host && lut_ptr_host && prepared && slot && out_host &&
+                  lut_batch_host && status_host && (E == 0 || edge_index_host),
+              "qot_lightpath_infer_host: null argument");
+  QOT_REQUIRE(slot->x && slot->edge_dst && slot->ptrs && slot->out && slot->lut_batch && slot->lut_node &&
+                  slot->n_lut && slot->status, "qot_lightpath_infer_host: incomplete staging slot");
+  QOT_REQUIRE(N <= slot->cap_nodes && E <= slot->cap_edges && B <= slot->cap_graphs,
+              "qot_lightpath_infer_host: batch (N=%lld, E=%lld, B=%lld) exceeds the slot capacity",
+              (long long)N, (long long)E, (long long)B);
+  QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer_host: prepared must be 16-byte aligned");
+  const int64_t L = lut_ptr_host[B];
+  QOT_REQUIRE(L >= 0 && L <= N, "qot_lightpath_infer_host: lut_ptr_host[B] out of range");
+  // device view of the pinned source row (UVA: identical address; asked for explicitly so that
+  // unmapped host memory is refused instead of faulting in the kernel)
+  const int64_t* esrc_dev = nullptr;
+  int64_t copied = 0;
+  if (E > 0) {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<int64_t*>(edge_index_host), 0) == cudaSuccess && dp) {
+      esrc_dev = static_cast<const int64_t*>(dp);
+    } else {
+      (void)cudaGetLastError();
+      QOT_REQUIRE(slot->edge_src, "qot_lightpath_infer_host: edge_index_host is not device-mapped pinned memory "
+                                  "and the slot has no edge_src staging buffer");
+      QOT_CUDA(cudaMemcpyAsync(slot->edge_src, edge_index_host, E * 8, cudaMemcpyHostToDevice, stream));
+      esrc_dev = slot->edge_src;
+      copied += E * 8;
+    }
+    QOT_CUDA(cudaMemcpyAsync(slot->edge_dst, edge_index_host + E, E * 8, cudaMemcpyHostToDevice, stream));
+  }
+  QOT_CUDA(cudaMemcpyAsync(slot->x, x_host, N * kF * 4, cudaMemcpyHostToDevice, stream));
+  int64_t* gptr = slot->ptrs;
+  int64_t* eptr = gptr + (B + 1);
+  int64_t* lptr = eptr + (B + 1);
+  if (eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1)) {
+    // the three offset arrays are adjacent on the host (PackedGraphStore.host_batch): one copy
+    QOT_CUDA(cudaMemcpyAsync(gptr, gptr_host, 3 * (B + 1) * 8, cudaMemcpyHostToDevice, stream));
+  } else {
+    QOT_CUDA(cudaMemcpyAsync(gptr, gptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
+    QOT_CUDA(cudaMemcpyAsync(eptr, eptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
+    QOT_CUDA(cudaMemcpyAsync(lptr, lut_ptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
+  }
+  copied += N * kF * 4 + E * 8 + 3 * (B + 1) * 8;
+  int rc = lp_infer_launch(slot->x, esrc_dev, slot->edge_dst, gptr, eptr, lptr, N, B, prepared, is_lut_index,
+                           slot->out, slot->lut_batch, slot->lut_node, slot->n_lut, slot->status, stream);
+  if (rc) return rc;
+  if (L > 0) {
+    QOT_CUDA(cudaMemcpyAsync(out_host, slot->out, L * QOT_OUT * 4, cudaMemcpyDeviceToHost, stream));
+    QOT_CUDA(cudaMemcpyAsync(lut_batch_host, slot->lut_batch, L * 8, cudaMemcpyDeviceToHost, stream));
+  }
+  QOT_CUDA(cudaMemcpyAsync(status_host, slot->status, 4, cudaMemcpyDeviceToHost, stream));
+  if (h2d_bytes) *h2d_bytes = copied;
+  if (d2h_bytes) *d2h_bytes = L * (QOT_OUT * 4 + 8) + 4;
   return QOT_OK;
 }

@@ -3,33 +3,58 @@
 This is the end-to-end form of ``lightpath_training/test.py:77-94`` (``data.to(device)`` ->
 ``model(data)`` -> ``.cpu()`` per batch) without the per-batch stalls: ``depth`` slots, each with
 its own CUDA stream, device staging buffers and pinned result buffers, so the H2D copy of batch
-k+1 overlaps the kernels of batch k and the D2H of batch k-1.  Nothing here computes: the
-arithmetic is the fused eval kernel behind ``qot_lightpath_infer``.
+k+1 overlaps the kernel of batch k and the D2H of batch k-1.  One native call per batch
+(``qot_lightpath_infer_host``) enqueues the copies, the fused eval kernel and the read-back; the
+source row of ``edge_index`` is never copied -- the kernel reads the handful of entries it needs
+straight from the pinned host buffer.  Nothing here computes on the host.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Iterable, List, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
+
+
+def _host_ptr(t: torch.Tensor, dtype, what: str) -> int:
+    if t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f"LightpathInferencePipeline: {what} must be a contiguous host {dtype} tensor")
+    return t.data_ptr()
+
+
+def _check_pinned(hb) -> None:
+    """Once per batch object: every tensor the native call reads must be pinned host memory."""
+    if getattr(hb, "_pinned_ok", False):
+        return
+    for k in ("x", "edge_index", "ptr", "edge_ptr", "lut_ptr"):
+        t = getattr(hb, k)
+        base = t._base if t._base is not None else t
+        if t.is_cuda or not base.is_pinned():
+            raise RuntimeError(f"LightpathInferencePipeline: {k} must be in pinned host memory "
+                               "(Batch.pin_memory() / PackedGraphStore.host_batch(pin=True))")
+    hb._pinned_ok = True
 
 
 class _Slot:
     def __init__(self, dev, max_nodes, max_edges, max_graphs):
         self.stream = torch.cuda.Stream(device=dev)
         self.x = torch.empty(max_nodes, 5, dtype=torch.float32, device=dev)
-        self.ei = torch.empty(2 * max_edges, dtype=torch.int64, device=dev)
-        self.gptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
-        self.eptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
-        self.lptr = torch.empty(max_graphs + 1, dtype=torch.int64, device=dev)
+        self.edst = torch.empty(max_edges, dtype=torch.int64, device=dev)
+        self.ptrs = torch.empty(3 * (max_graphs + 1), dtype=torch.int64, device=dev)
         self.res = ops.new_infer_out(max_nodes, dev)
+        self.c = _lib.QotLpSlot(self.x.data_ptr(), None, self.edst.data_ptr(), self.ptrs.data_ptr(),
+                                self.res.out.data_ptr(), self.res.lut_batch.data_ptr(),
+                                self.res.lut_node.data_ptr(), self.res.n_lut.data_ptr(),
+                                self.res.status.data_ptr(), max_nodes, max_edges, max_graphs)
         self.out_h = torch.empty(max_nodes, 3, dtype=torch.float32).pin_memory()
         self.lb_h = torch.empty(max_nodes, dtype=torch.int64).pin_memory()
         self.st_h = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.done = torch.cuda.Event()
         self.rows = 0
         self.busy = False
+        self.batch = None                         # keeps the host batch alive while the kernel reads it
 
 
 class LightpathInferencePipeline:
@@ -42,44 +67,39 @@ class LightpathInferencePipeline:
         self.model, self.dev = model, p.device
         self.caps = (int(max_nodes), int(max_edges), int(max_graphs))
         self.slots = [_Slot(self.dev, *self.caps) for _ in range(depth)]
-        self.h2d_bytes = self.d2h_bytes = self.steps = 0
-        model.prepared()                          # fold the parameters once, before any slot stream uses them
+        self.h2d_bytes = self.d2h_bytes = self.zero_copy_bytes = self.steps = 0
+        self._h2d, self._d2h = C.c_int64(0), C.c_int64(0)
+        self.prepared = model.prepared()          # folded parameters, before any slot stream uses them
         torch.cuda.synchronize(self.dev)
 
     # -- one batch in flight -------------------------------------------------------
     def _submit(self, slot: _Slot, hb) -> None:
         N, E, B = hb.num_nodes, hb.num_edges, hb.num_graphs
-        if N > self.caps[0] or E > self.caps[1] or B > self.caps[2]:
-            raise RuntimeError(f"batch (N={N}, E={E}, B={B}) exceeds the pipeline capacity {self.caps}")
         if hb.ptr is None or hb.edge_ptr is None or hb.lut_ptr is None or hb.lut_col != self.model.is_lut_index:
             raise RuntimeError("LightpathInferencePipeline needs batches carrying ptr, edge_ptr and lut_ptr "
                                "(PackedGraphStore.host_batch / collate provide them)")
+        _check_pinned(hb)
         L = int(hb.lut_ptr[-1])                     # known on the host: no D2H of the row count
         if L == 0:
             raise ValueError("No LUT node found in the batch.")
-        with torch.cuda.stream(slot.stream):
-            x = slot.x[:N]
-            ei = slot.ei[: 2 * E].view(2, E)
-            gptr, eptr, lptr = slot.gptr[: B + 1], slot.eptr[: B + 1], slot.lptr[: B + 1]
-            x.copy_(hb.x, non_blocking=True)
-            ei.copy_(hb.edge_index, non_blocking=True)
-            gptr.copy_(hb.ptr, non_blocking=True)
-            eptr.copy_(hb.edge_ptr, non_blocking=True)
-            lptr.copy_(hb.lut_ptr, non_blocking=True)
-            self.h2d_bytes += 20 * N + 16 * E + 24 * (B + 1)
-            ops.lightpath_infer(x, ei, gptr, eptr, lptr, self.model.prepared(), self.model.is_lut_index, slot.res)
-            slot.st_h.copy_(slot.res.status, non_blocking=True)
-            slot.out_h[:L].copy_(slot.res.out[:L], non_blocking=True)
-            slot.lb_h[:L].copy_(slot.res.lut_batch[:L], non_blocking=True)
-            self.d2h_bytes += 4 + 20 * L
-            slot.rows = L
-            slot.done.record(slot.stream)
-        slot.busy = True
+        lib = _lib.lib()
+        _lib.check(lib.qot_lightpath_infer_host(
+            _host_ptr(hb.x, torch.float32, "x"), _host_ptr(hb.edge_index, torch.int64, "edge_index"), E,
+            _host_ptr(hb.ptr, torch.int64, "ptr"), _host_ptr(hb.edge_ptr, torch.int64, "edge_ptr"),
+            _host_ptr(hb.lut_ptr, torch.int64, "lut_ptr"), N, B, self.prepared.data_ptr(),
+            int(self.model.is_lut_index), C.byref(slot.c), slot.out_h.data_ptr(), slot.lb_h.data_ptr(),
+            slot.st_h.data_ptr(), C.byref(self._h2d), C.byref(self._d2h), slot.stream.cuda_stream),
+            "qot_lightpath_infer_host")
+        slot.done.record(slot.stream)
+        self.h2d_bytes += self._h2d.value
+        self.d2h_bytes += self._d2h.value
+        self.zero_copy_bytes += 32 * 4 * L          # ~4 in-edges per LUT row, one 32 B sector each (estimate)
+        slot.rows, slot.busy, slot.batch = L, True, hb
         self.steps += 1
 
     def _collect(self, slot: _Slot) -> Tuple[torch.Tensor, torch.Tensor]:
         slot.done.synchronize()
-        slot.busy = False
+        slot.busy, slot.batch = False, None
         if int(slot.st_h[0]) != 0:
             raise RuntimeError("LightpathInferencePipeline: a batch's lut_ptr does not match its x")
         n = slot.rows

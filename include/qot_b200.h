@@ -259,6 +259,33 @@ int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
                         int32_t* status, void* stream);
 
+/* The same call for a batch in PINNED HOST memory (reference layout), into a caller-owned device
+ * staging slot.  Enqueues on `stream`: H2D of x, of the DESTINATION row of edge_index and of the
+ * three offset arrays; the kernel -- the source row is not copied: the few entries the readout
+ * needs (one 32-byte sector per in-edge of a LUT node) are read by the kernel from the pinned
+ * buffer over PCIe (if the buffer is not device-mapped, slot->edge_src must exist and the row is
+ * copied); D2H of rows [0,L) of out / lut_batch and of the status word, L = lut_ptr_host[B].
+ * No synchronisation: the caller waits on its own event before reading the host outputs.
+ * h2d_bytes / d2h_bytes (optional, host): bytes this call copied in each direction. */
+typedef struct {
+  float* x;             /* [cap_nodes,5]                                   */
+  int64_t* edge_src;    /* [cap_edges] or NULL (only for unmapped host memory) */
+  int64_t* edge_dst;    /* [cap_edges]                                     */
+  int64_t* ptrs;        /* [3*(cap_graphs+1)]: gptr | eptr | lut_ptr       */
+  float* out;           /* [cap_nodes,3]                                   */
+  int64_t* lut_batch;   /* [cap_nodes]                                     */
+  int32_t* lut_node;    /* [cap_nodes]                                     */
+  int32_t* n_lut;       /* [1]                                             */
+  int32_t* status;      /* [1], zeroed by the caller once                  */
+  int64_t cap_nodes, cap_edges, cap_graphs;
+} qot_lp_slot_t;
+int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,
+                             const int64_t* gptr_host, const int64_t* eptr_host,
+                             const int64_t* lut_ptr_host, int64_t N, int64_t B,
+                             const float* prepared, int32_t is_lut_index, const qot_lp_slot_t* slot,
+                             float* out_host, int64_t* lut_batch_host, int32_t* status_host,
+                             int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream);
+
 /* General GATConv forward over a destination-sorted CSR built with flags=3
  * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.
  * Optional saves for the backward: z [N,4,5] = sum_j alpha_ij x_j per head, and the
