@@ -1,0 +1,240 @@
+// Node-wise dense projection on the 5th-generation tensor cores with fp32-level accuracy:
+//   C[M,Nc] = A[rows(M),K] * W[Nc,K]^T (+ bias),   fp32 in, fp32 out,
+// computed as three TF32 tcgen05.mma products per k-step on error-compensated operands
+//   a = a_hi + a_lo,  w = w_hi + w_lo   (hi = round-to-tf32, lo = tf32(a - hi)),
+//   a*w ~= a_hi*w_lo + a_lo*w_hi + a_hi*w_hi      (the dropped a_lo*w_lo term is ~2^-22 relative)
+// accumulated in fp32 in TMEM.  This is the one place on the path where the hidden width makes the
+// projection a real contraction (BASELINE cfg 5: [10000,256] x [256,1024] and x [256,2560], 18 GFLOP);
+// at the reference widths (H = 16 / 32) the FFMA kernel in dense.cu stays in charge.
+//
+// One CTA (128 threads) owns a 128 x 128 output tile: accumulator = 128 TMEM lanes x 128 columns.
+// Per 32-wide k-block the threads fetch A / W rows with coalesced 128-bit loads, split them and store
+// hi / lo tiles in the 128-byte-swizzled K-major layout the UMMA shared-memory descriptor expects
+// (no TMA needed: the split has to touch every element anyway); one elected thread issues the
+// 12 MMAs of the block and commits them to an mbarrier, so the loads of the next block (other
+// stage) overlap the tensor work.  Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) + bias.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qot {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // 32 fp32 = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 64;
+constexpr unsigned TC_SPIN_LIMIT = 1u << 26;                // a wedged barrier ends the kernel, never hangs it
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address,
+// LBO (unused for a 128-byte-wide K extent) = 1, SBO = 1024 B (8 rows x 128 B), version 1, layout 2.
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= static_cast<unsigned long long>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<unsigned long long>(1u) << 16;
+  d |= static_cast<unsigned long long>(1024u >> 4) << 32;
+  d |= static_cast<unsigned long long>(1u) << 46;
+  d |= static_cast<unsigned long long>(2u) << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M
+constexpr unsigned tc_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<unsigned>(N >> 3) << 17) |
+         (static_cast<unsigned>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
+  for (unsigned spin = 0; spin < TC_SPIN_LIMIT; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// rows of `src` (row-major, leading dimension ld, optional gather) [r0, r0+128) x k [k0, k0+32) -> hi / lo
+// tiles in the swizzled layout: row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7)
+__device__ __forceinline__ void load_split_tile(const float* __restrict__ src, int64_t ld,
+                                                const int64_t* __restrict__ gather, int64_t r0, int64_t nrows,
+                                                int64_t k0, char* hi, char* lo, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = tid + it * 128;                 // 1024 chunks of 16 bytes
+    const int r = idx >> 3, c = idx & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t gr = r0 + r;
+    if (gr < nrows) {
+      const int64_t row = gather ? gather[gr] : gr;
+      v = *reinterpret_cast<const float4*>(src + row * ld + k0 + c * 4);
+    }
+    float4 h, l;
+    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+gemm_tf32x3_kernel(const float* __restrict__ A, int64_t lda, const int64_t* __restrict__ gather,
+                   const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias,
+                   float* __restrict__ C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
+                   int32_t* __restrict__ status) {
+  extern __shared__ char tc_smem_raw[];
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + TC_STAGES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * TC_BM, n0 = static_cast<int64_t>(blockIdx.y) * TC_BN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(static_cast<unsigned>(TC_BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_d = *tmem_slot;
+  constexpr unsigned idesc = tc_idesc(TC_BM, TC_BN);
+
+  const int64_t nkb = K / TC_BK;
+  bool ok = true;
+  for (int64_t kb = 0; kb < nkb; ++kb) {
+    const int st = static_cast<int>(kb % TC_STAGES);
+    char* base = smem + st * TC_STAGE_BYTES;
+    if (kb >= TC_STAGES)                                            // the MMAs that read this stage are done
+      ok &= mbar_wait(smem_u32(bars + st), static_cast<unsigned>((kb / TC_STAGES - 1) & 1));
+    load_split_tile(A, lda, gather, m0, M, kb * TC_BK, base, base + TC_TILE_BYTES, tid);
+    load_split_tile(W, ldw, nullptr, n0, Nc, kb * TC_BK, base + 2 * TC_TILE_BYTES, base + 3 * TC_TILE_BYTES, tid);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned a_hi = smem_u32(base), a_lo = a_hi + TC_TILE_BYTES;
+      const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+      for (int s = 0; s < TC_BK / 8; ++s) {                         // UMMA_K = 8 for tf32: 32 bytes per step
+        const unsigned ko = s * 32;
+        umma_tf32(tmem_d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, (kb | s) != 0);
+        umma_tf32(tmem_d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+        umma_tf32(tmem_d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+      }
+      // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(bars + st))
+                   : "memory");
+    }
+  }
+  // the last commit covers all MMAs: wait for it before reading the accumulator
+  if (nkb > 0) {
+    const int64_t last = nkb - 1;
+    ok &= mbar_wait(smem_u32(bars + static_cast<int>(last % TC_STAGES)),
+                    static_cast<unsigned>((last / TC_STAGES) & 1));
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok && status) atomicOr(status, 2);
+
+  // ---- epilogue: warp w reads TMEM lanes [32w, 32w+32) = tile rows, 32 columns at a time
+  const int64_t row = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+    unsigned r[32];
+    const unsigned taddr = tmem_d + (static_cast<unsigned>(warp * 32) << 16) + static_cast<unsigned>(c0);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < M) {
+      float* crow = C + row * ldc + n0 + c0;
+      if (n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + j) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < Nc) crow[j] = __uint_as_float(r[j]) + (bias ? bias[n0 + c0 + j] : 0.f);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                 "r"(static_cast<unsigned>(TC_BN))
+                 : "memory");
+}
+
+}  // namespace qot
+
+using namespace qot;
+
+// C[M,Nc] (ldc) = A[gather? gather[m] : m, :K] (lda) * W[Nc,:K]^T (ldw) (+ bias[Nc]); K % 32 == 0,
+// lda/ldw % 4 == 0 and 16-byte aligned bases (128-bit loads).  status (optional, device int32): bit 1 is
+// set if a pipeline barrier timed out (never observed; the result is then undefined, the kernel still ends).
+extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
+                               const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
+                               int32_t* status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(M >= 0 && Nc >= 0 && K > 0, "qot_gemm_tf32x3: bad size");
+  if (M == 0 || Nc == 0) return QOT_OK;
+  QOT_REQUIRE(A && W && C, "qot_gemm_tf32x3: null operand");
+  QOT_REQUIRE(K % TC_BK == 0, "qot_gemm_tf32x3: K must be a multiple of 32 (got %lld)", (long long)K);
+  QOT_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && ldc >= Nc, "qot_gemm_tf32x3: leading dimensions must be multiples of 4");
+  QOT_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+              "qot_gemm_tf32x3: operands must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
+  QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");
+  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(A, lda, gather, W, ldw, bias, C, ldc, M, Nc, K, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}

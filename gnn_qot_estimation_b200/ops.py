@@ -397,6 +397,32 @@ def _ids_csr(ids: torch.Tensor, num_rows: int) -> CSR:
     return build_csr(pair, max(num_rows, n), by=1, flags=0)
 
 
+TC_MIN_ROWS = 1024        # below this the 128-row tensor-core tiles cannot fill the machine
+
+
+def _tc_ok(M: int, Nc: int, K: int) -> bool:
+    """Tensor-core path (qot_gemm_tf32x3): only where the projection is a real contraction."""
+    return K % 32 == 0 and K >= 64 and M >= TC_MIN_ROWS and Nc >= 64 and Nc % 4 == 0
+
+
+_tc_status = {}
+
+
+def gemm_tf32x3(A, W, bias=None, gather=None):
+    """C = A[gather] @ W^T (+ bias) on tcgen05 tensor cores with split-fp32 (3 x TF32) operands."""
+    L = _lib.lib()
+    M = gather.numel() if gather is not None else A.shape[0]
+    K, Nc = A.shape[1], W.shape[0]
+    dev = A.device
+    st = _tc_status.get(dev)
+    if st is None:
+        st = _tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    C_ = torch.empty(M, Nc, dtype=torch.float32, device=dev)
+    check(L.qot_gemm_tf32x3(ptr(A), K, ptr(gather), ptr(W), K, ptr(bias), ptr(C_), Nc, M, Nc, K, ptr(st), stream()),
+          "qot_gemm_tf32x3")
+    return C_
+
+
 class _NodeLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ids, W, b):
@@ -406,9 +432,12 @@ class _NodeLinearFn(torch.autograd.Function):
         b_ = _f32(b.detach()) if b is not None else None
         M = ids.numel() if ids is not None else x.shape[0]
         K, Nc = x.shape[1], W_.shape[0]
-        y = torch.empty(M, Nc, dtype=torch.float32, device=x.device)
-        check(L.qot_gemm(ptr(x), K, 1, ptr(ids), ptr(W_), 1, K, ptr(b_), ptr(y), Nc, M, Nc, K, stream()),
-              "qot_gemm")
+        if _tc_ok(M, Nc, K):
+            y = gemm_tf32x3(x, W_, b_, ids)
+        else:
+            y = torch.empty(M, Nc, dtype=torch.float32, device=x.device)
+            check(L.qot_gemm(ptr(x), K, 1, ptr(ids), ptr(W_), 1, K, ptr(b_), ptr(y), Nc, M, Nc, K, stream()),
+                  "qot_gemm")
         ctx.save_for_backward(x, ids, W_)
         ctx.has_bias = b is not None
         return y
@@ -424,8 +453,12 @@ class _NodeLinearFn(torch.autograd.Function):
         dx = dW = db = None
         need_x, _, need_w, need_b = ctx.needs_input_grad
         if need_x:
-            dxr = torch.empty(M, K, dtype=torch.float32, device=dev)        # dy @ W
-            check(L.qot_gemm(ptr(dy), Nc, 1, None, ptr(W), K, 1, None, ptr(dxr), K, M, K, Nc, stream()), "qot_gemm")
+            if _tc_ok(M, K, Nc):                                             # dy @ W = dy @ (W^T)^T
+                dxr = gemm_tf32x3(dy, W.t().contiguous())
+            else:
+                dxr = torch.empty(M, K, dtype=torch.float32, device=dev)    # dy @ W
+                check(L.qot_gemm(ptr(dy), Nc, 1, None, ptr(W), K, 1, None, ptr(dxr), K, M, K, Nc, stream()),
+                      "qot_gemm")
             if ids is None:
                 dx = dxr
             else:

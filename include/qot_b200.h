@@ -119,6 +119,16 @@ int qot_gemm(const float* A, int64_t a_rs, int64_t a_cs, const int64_t* gather,
              const float* B, int64_t b_rs, int64_t b_cs, const float* bias,
              float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, void* stream);
 
+/* The same projection on the tensor cores (tcgen05.mma kind::tf32, TMEM accumulator) with
+ * fp32-level accuracy: C[M,Nc] (ldc) = A[gather ? gather[m] : m, :K] (lda) * W[Nc,:K]^T (ldw)
+ * (+ bias[Nc]), three TF32 products per k-step on hi/lo-split operands.  For hidden widths where
+ * the projection is a real contraction (K % 32 == 0; BASELINE cfg 5, H = 256); lda, ldw multiples
+ * of 4, 16-byte aligned bases.  status (optional, device int32[1]): bit 1 = a pipeline barrier
+ * timed out (result undefined). */
+int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
+                    const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
+                    int32_t* status, void* stream);
+
 /* Deterministic weight gradient: C[Mo,No] (ldc) = sum_r A[r,Mo]^T * B[r,No] over
  * R rows (row-major A [R,lda], B [R,ldb]); two-stage fixed-order reduction.
  * gather (optional int64 [R]) scatters by row: C[gather[r], :] += B[r, :] is NOT
