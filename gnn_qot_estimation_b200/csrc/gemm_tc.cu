@@ -7,12 +7,15 @@
 // projection a real contraction (BASELINE cfg 5: [10000,256] x [256,1024] and x [256,2560], 18 GFLOP);
 // at the reference widths (H = 16 / 32) the FFMA kernel in dense.cu stays in charge.
 //
-// One CTA (128 threads) owns a 128 x 128 output tile: accumulator = 128 TMEM lanes x 128 columns.
-// Per 32-wide k-block the threads fetch A / W rows with coalesced 128-bit loads, split them and store
-// hi / lo tiles in the 128-byte-swizzled K-major layout the UMMA shared-memory descriptor expects
-// (no TMA needed: the split has to touch every element anyway); one elected thread issues the
-// 12 MMAs of the block and commits them to an mbarrier, so the loads of the next block (other
-// stage) overlap the tensor work.  Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) + bias.
+// Two kernels.  split_tf32_kernel writes the hi / lo halves of an operand once (and performs the
+// embedding-row gather of topological_training/models.py:52 on the way), so the GEMM does not redo
+// the split in every tile.  gemm_tf32x3_kernel: one CTA (128 threads) owns a 128 x 128 output tile,
+// accumulator = 128 TMEM lanes x 128 columns.  Per 32-wide k-block the four operand tiles
+// (A_hi, A_lo, W_hi, W_lo; 64 KB) are copied global -> shared with cp.async (LDGSTS, zero-filled
+// past the matrix edge) straight into the 128-byte-swizzled K-major layout the UMMA shared-memory
+// descriptor expects, three stages deep; one elected thread issues the 12 MMAs of the block and
+// commits them to the stage's mbarrier, which gates the refill of that stage.  Epilogue:
+// tcgen05.ld (32 lanes x 32 columns per warp) + bias -> global.
 #include <algorithm>
 
 #include "common.cuh"
@@ -20,7 +23,7 @@
 namespace qot {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 64;
@@ -72,35 +75,46 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
   return false;
 }
 
-// rows of `src` (row-major, leading dimension ld, optional gather) [r0, r0+128) x k [k0, k0+32) -> hi / lo
-// tiles in the swizzled layout: row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7)
-__device__ __forceinline__ void load_split_tile(const float* __restrict__ src, int64_t ld,
-                                                const int64_t* __restrict__ gather, int64_t r0, int64_t nrows,
-                                                int64_t k0, char* hi, char* lo, int tid) {
+// hi = tf32(v), lo = tf32(v - hi) of rows [0, rows) of `src` (optional gather), K columns
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ gather,
+                  int64_t rows, int64_t K, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t kv = K / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * kv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / kv, c = i % kv;
+    const int64_t row = gather ? gather[r] : r;
+    const float4 v = *reinterpret_cast<const float4*>(src + row * ld + c * 4);
+    float4 h, l;
+    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+    *reinterpret_cast<float4*>(hi + r * K + c * 4) = h;
+    *reinterpret_cast<float4*>(lo + r * K + c * 4) = l;
+  }
+}
+
+// rows [r0, r0+128) x k [k0, k0+32) of a dense [nrows, K] matrix -> one swizzled shared tile with cp.async:
+// row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7); rows past nrows are zero-filled
+__device__ __forceinline__ void cp_async_tile(const float* __restrict__ src, int64_t K, int64_t r0,
+                                              int64_t nrows, int64_t k0, char* tile, int tid) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int idx = tid + it * 128;                 // 1024 chunks of 16 bytes
     const int r = idx >> 3, c = idx & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t gr = r0 + r;
-    if (gr < nrows) {
-      const int64_t row = gather ? gather[gr] : gr;
-      v = *reinterpret_cast<const float4*>(src + row * ld + k0 + c * 4);
-    }
-    float4 h, l;
-    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    const int off = r * 128 + ((c ^ (r & 7)) << 4);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
+    const bool in = gr < nrows;
+    const float* g = src + (in ? gr : 0) * K + k0 + c * 4;
+    const unsigned dst = smem_u32(tile + r * 128 + ((c ^ (r & 7)) << 4));
+    const unsigned bytes = in ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(bytes) : "memory");
   }
 }
 
 __global__ void __launch_bounds__(128)
-gemm_tf32x3_kernel(const float* __restrict__ A, int64_t lda, const int64_t* __restrict__ gather,
-                   const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias,
-                   float* __restrict__ C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
-                   int32_t* __restrict__ status) {
+gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
+                   const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M,
+                   int64_t Nc, int64_t K, int32_t* __restrict__ status) {
   extern __shared__ char tc_smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -126,20 +140,35 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int64_t lda, const int64_t* __re
   constexpr unsigned idesc = tc_idesc(TC_BM, TC_BN);
 
   const int64_t nkb = K / TC_BK;
+  auto issue_loads = [&](int64_t kb) {
+    char* base = smem + static_cast<int>(kb % TC_STAGES) * TC_STAGE_BYTES;
+    cp_async_tile(Ahi, K, m0, M, kb * TC_BK, base, tid);
+    cp_async_tile(Alo, K, m0, M, kb * TC_BK, base + TC_TILE_BYTES, tid);
+    cp_async_tile(Whi, K, n0, Nc, kb * TC_BK, base + 2 * TC_TILE_BYTES, tid);
+    cp_async_tile(Wlo, K, n0, Nc, kb * TC_BK, base + 3 * TC_TILE_BYTES, tid);
+  };
   bool ok = true;
+  for (int64_t kb = 0; kb < TC_STAGES - 1; ++kb) {                  // prologue: STAGES-1 blocks in flight
+    if (kb < nkb) issue_loads(kb);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int64_t kb = 0; kb < nkb; ++kb) {
     const int st = static_cast<int>(kb % TC_STAGES);
-    char* base = smem + st * TC_STAGE_BYTES;
-    if (kb >= TC_STAGES)                                            // the MMAs that read this stage are done
-      ok &= mbar_wait(smem_u32(bars + st), static_cast<unsigned>((kb / TC_STAGES - 1) & 1));
-    load_split_tile(A, lda, gather, m0, M, kb * TC_BK, base, base + TC_TILE_BYTES, tid);
-    load_split_tile(W, ldw, nullptr, n0, Nc, kb * TC_BK, base + 2 * TC_TILE_BYTES, base + 3 * TC_TILE_BYTES, tid);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> async proxy
+    const int64_t nxt = kb + TC_STAGES - 1;                         // block to prefetch; its stage was read by
+    if (nxt < nkb) {                                                // the MMAs of block kb-1
+      if (kb >= 1)
+        ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
+                        static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
+      issue_loads(nxt);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 1) : "memory");   // this thread's part of block kb landed
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned a_hi = smem_u32(base), a_lo = a_hi + TC_TILE_BYTES;
+      const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
       const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
       for (int s = 0; s < TC_BK / 8; ++s) {                         // UMMA_K = 8 for tf32: 32 bytes per step
@@ -213,11 +242,17 @@ gemm_tf32x3_kernel(const float* __restrict__ A, int64_t lda, const int64_t* __re
 using namespace qot;
 
 // C[M,Nc] (ldc) = A[gather? gather[m] : m, :K] (lda) * W[Nc,:K]^T (ldw) (+ bias[Nc]); K % 32 == 0,
-// lda/ldw % 4 == 0 and 16-byte aligned bases (128-bit loads).  status (optional, device int32): bit 1 is
-// set if a pipeline barrier timed out (never observed; the result is then undefined, the kernel still ends).
+// lda/ldw % 4 == 0 and 16-byte aligned bases (128-bit accesses).  ws: qot_gemm_tf32x3_workspace_bytes(M,Nc,K)
+// bytes for the hi / lo halves of both operands.  status (optional, device int32): bit 1 is set if a
+// pipeline barrier timed out (never observed; the result is then undefined, the kernel still ends).
+extern "C" size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K) {
+  if (M < 0 || Nc < 0 || K < 0) return 0;
+  return 2 * align_up(static_cast<size_t>(M) * K * 4) + 2 * align_up(static_cast<size_t>(Nc) * K * 4) + 256;
+}
+
 extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
                                const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
-                               int32_t* status, void* stream_) {
+                               int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   QOT_REQUIRE(M >= 0 && Nc >= 0 && K > 0, "qot_gemm_tf32x3: bad size");
   if (M == 0 || Nc == 0) return QOT_OK;
@@ -227,14 +262,25 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
               "qot_gemm_tf32x3: operands must be 16-byte aligned");
+  QOT_REQUIRE(ws && ws_bytes >= qot_gemm_tf32x3_workspace_bytes(M, Nc, K), "qot_gemm_tf32x3: workspace too small");
   static bool attr_set = false;
   if (!attr_set) {
     QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
+  Carver c(ws);
+  float* a_hi = c.take<float>(M * K);
+  float* a_lo = c.take<float>(M * K);
+  float* w_hi = c.take<float>(Nc * K);
+  float* w_lo = c.take<float>(Nc * K);
+  auto blocks_for = [](int64_t n) { return static_cast<unsigned>(std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)); };
+  split_tf32_kernel<<<blocks_for(M * K / 4), 256, 0, stream>>>(A, lda, gather, M, K, a_hi, a_lo);
+  QOT_LAUNCH_CHECK();
+  split_tf32_kernel<<<blocks_for(Nc * K / 4), 256, 0, stream>>>(W, ldw, nullptr, Nc, K, w_hi, w_lo);
+  QOT_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
   QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");
-  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(A, lda, gather, W, ldw, bias, C, ldc, M, Nc, K, status);
+  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

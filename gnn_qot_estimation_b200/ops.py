@@ -418,8 +418,9 @@ def gemm_tf32x3(A, W, bias=None, gather=None):
     if st is None:
         st = _tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
     C_ = torch.empty(M, Nc, dtype=torch.float32, device=dev)
-    check(L.qot_gemm_tf32x3(ptr(A), K, ptr(gather), ptr(W), K, ptr(bias), ptr(C_), Nc, M, Nc, K, ptr(st), stream()),
-          "qot_gemm_tf32x3")
+    ws = _lib.workspace(L.qot_gemm_tf32x3_workspace_bytes(M, Nc, K), dev)
+    check(L.qot_gemm_tf32x3(ptr(A), K, ptr(gather), ptr(W), K, ptr(bias), ptr(C_), Nc, M, Nc, K, ptr(st),
+                            ptr(ws), ws.numel(), stream()), "qot_gemm_tf32x3")
     return C_
 
 

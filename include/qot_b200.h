@@ -124,10 +124,12 @@ int qot_gemm(const float* A, int64_t a_rs, int64_t a_cs, const int64_t* gather,
  * (+ bias[Nc]), three TF32 products per k-step on hi/lo-split operands.  For hidden widths where
  * the projection is a real contraction (K % 32 == 0; BASELINE cfg 5, H = 256); lda, ldw multiples
  * of 4, 16-byte aligned bases.  status (optional, device int32[1]): bit 1 = a pipeline barrier
- * timed out (result undefined). */
+ * timed out (result undefined).  ws: room for the hi / lo halves of both operands, which a small
+ * pre-pass writes once (it also performs the row gather). */
+size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K);
 int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
                     const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
-                    int32_t* status, void* stream);
+                    int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
 /* Deterministic weight gradient: C[Mo,No] (ldc) = sum_r A[r,Mo]^T * B[r,No] over
  * R rows (row-major A [R,lda], B [R,ldb]); two-stage fixed-order reduction.
