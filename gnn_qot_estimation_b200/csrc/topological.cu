@@ -77,6 +77,16 @@ __device__ __forceinline__ float4 edge_proj(const float4 (&w)[4], const float4& 
 // ===========================================================================
 // TransformerConv forward
 // ===========================================================================
+template <int LANES>
+__device__ __forceinline__ float4 gshfl4(const float4& v, int srcl, unsigned mask) {
+  return make_float4(__shfl_sync(mask, v.x, srcl, LANES), __shfl_sync(mask, v.y, srcl, LANES),
+                     __shfl_sync(mask, v.z, srcl, LANES), __shfl_sync(mask, v.w, srcl, LANES));
+}
+
+// The in-edges of a row are consumed in chunks of LANES: lane l fetches the (src, eid, edge_attr) of
+// edge c0+l with coalesced loads, the values are handed round by shuffles, and the k_j / v_j rows of
+// edge t+1 are requested before edge t is reduced -- the row's gathers are no longer a chain of
+// dependent round trips (index -> row -> index -> row ...).
 template <int LANES, int VEC>
 __global__ void __launch_bounds__(256)
 tconv_fwd_kernel(const float* __restrict__ qkvs, const int32_t* __restrict__ rowptr,
@@ -101,27 +111,61 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, const int32_t* __restrict__ row
   }
   float m = -INFINITY, den = 0.f;
   const int32_t beg = rowptr[i], end = rowptr[i + 1];
-  for (int32_t p = beg; p < end; ++p) {
-    const int64_t j = src[p];
-    const float4 ea = ld4(edge_attr + static_cast<int64_t>(eid[p]) * D_);
-    float4 ve[VEC];
-    float part = 0.f;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const int c0 = (v * LANES + l) * 4;
-      const float4 e = edge_proj(we[v], ea);
-      const float4 kj = add4(ld4(qkvs + j * 4 * H + H + c0), e);
-      ve[v] = add4(ld4(qkvs + j * 4 * H + 2 * H + c0), e);
-      part += dot4(q[v], kj);
+  for (int32_t c0 = beg; c0 < end; c0 += LANES) {
+    const int cnt = min(LANES, end - c0);
+    int my_src = 0;
+    float4 my_ea = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < cnt) {
+      my_src = src[c0 + l];
+      my_ea = ld4(edge_attr + static_cast<int64_t>(eid[c0 + l]) * D_);
     }
-    const float a = gsum<LANES>(part, mask);
-    if (logit && l == 0) logit[p] = a;
-    const float mn = fmaxf(m, a);
-    const float sc = expf(m - mn), pe = expf(a - mn);
-    den = fmaf(den, sc, pe);
+    float4 kj[VEC], vj[VEC];
+    {
+      const int64_t j = __shfl_sync(mask, my_src, 0, LANES);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = fma4(pe, ve[v], scale4(sc, acc[v]));
-    m = mn;
+      for (int v = 0; v < VEC; ++v) {
+        const int cc = (v * LANES + l) * 4;
+        kj[v] = ld4(qkvs + j * 4 * H + H + cc);
+        vj[v] = ld4(qkvs + j * 4 * H + 2 * H + cc);
+      }
+    }
+    for (int t = 0; t < cnt; ++t) {
+      float4 kn[VEC], vn[VEC];
+      if (t + 1 < cnt) {                                         // group-uniform: next edge's rows in flight
+        const int64_t jn = __shfl_sync(mask, my_src, t + 1, LANES);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int cc = (v * LANES + l) * 4;
+          kn[v] = ld4(qkvs + jn * 4 * H + H + cc);
+          vn[v] = ld4(qkvs + jn * 4 * H + 2 * H + cc);
+        }
+      }
+      const float4 ea = gshfl4<LANES>(my_ea, t, mask);
+      float4 ve[VEC];
+      float part = 0.f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float4 e = edge_proj(we[v], ea);
+        const float4 ke = add4(kj[v], e);
+        ve[v] = add4(vj[v], e);
+        part += dot4(q[v], ke);
+      }
+      const float a = gsum<LANES>(part, mask);
+      if (logit && l == 0) logit[c0 + t] = a;
+      const float mn = fmaxf(m, a);
+      const float sc = expf(m - mn), pe = expf(a - mn);
+      den = fmaf(den, sc, pe);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = fma4(pe, ve[v], scale4(sc, acc[v]));
+      m = mn;
+      if (t + 1 < cnt) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          kj[v] = kn[v];
+          vj[v] = vn[v];
+        }
+      }
+    }
   }
   den += 1e-16f;
   const float inv = 1.0f / den;
