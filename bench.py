@@ -299,8 +299,13 @@ def run_b200(args):
     step_s = ms * 1e-3 / K
     peak, peak_kind = peaks()
     achieved = alg / step_s / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "r1_lp_infer_traffic.json"          # dram__bytes_{read,write}.sum of one ncu --set full capture
+    if tp.exists() and Bsz == 4096:
+        tj = json.loads(tp.read_text())
+        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": model.dominant_kernel, "alg_bytes_per_launch": alg,
+                "traffic": traffic, "kernel": model.dominant_kernel, "alg_bytes_per_launch": alg,
                 "avg_launch_us": step_s * 1e6, "launches_in_flight": S, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"}
 
     # ---- end to end: pinned host batches -> H2D -> kernels -> D2H, through the public pipeline API

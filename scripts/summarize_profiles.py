@@ -15,7 +15,7 @@ for r in rows[1:]:
 ours = {k: v for k, v in d.items() if k.startswith("qot::")}
 tot_all = sum(sum(v) for v in d.values()); tot_ours = sum(sum(v) for v in ours.values())
 out.append(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)\n")
-out.append(f"command: python bench.py --steps 490 --warmup 5 --streams 4 --no-e2e --no-cpu-baseline  ({len(rows)-1} launches captured)\n")
+out.append(f"command: python bench.py --steps 490 --warmup 5 --no-e2e --no-cpu-baseline (default: 4 graph branches)  ({len(rows)-1} launches captured)\n")
 out.append("| kernel | launches | mean us | total us | share of all | share of qot:: kernels |\n|---|---:|---:|---:|---:|---:|")
 for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
     name = k.split("(")[0][:70]
