@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=4, help="batches in flight in the host pipeline")
     ap.add_argument("--no-graph", action="store_true", help="topo_train: eager step instead of the CUDA-graphed step")
-    ap.add_argument("--workload", default="lightpath_infer", choices=["lightpath_infer", "topo_train", "topo_stress"],
+    ap.add_argument("--workload", default="lightpath_infer", choices=["lightpath_infer", "topo_train", "topo_stress", "lightpath_train"],
                     help="lightpath_infer = BASELINE configs[1] (the headline line); topo_train = configs[2] "
                          "(TopologicalGNN DDP training, batch 1024/GPU); topo_stress = configs[4] (10k nodes, hidden 256)")
     ap.add_argument("--streams", type=int, default=4,

@@ -22,8 +22,71 @@ def _ev():
 def run(args):
     if args.workload == "topo_train":
         run_train(args)
+    elif args.workload == "lightpath_train":
+        run_lightpath_train(args)
     else:
         run_stress(args)
+
+
+# --------------------------------------------------------------------------- lightpath training step
+def run_lightpath_train(args):
+    """LightpathGNN train step as lightpath_training/train.py:109-132 drives it (batch 512, SGD(0.1, 0.9),
+    SmoothL1 on out vs y[lut_batch]); GAT fwd -> batch-stat BN -> LUT head, and every backward kernel."""
+    from gnn_qot_estimation_b200 import LightpathGNN, synthetic
+    B = args.batch if args.batch != 4096 else 512
+    K, W = min(args.steps, 300), max(3, min(args.warmup, 20))
+    crit = torch.nn.SmoothL1Loss()
+    if args.impl == "reference":
+        from oracle import LightpathGNNOracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        m = LightpathGNNOracle(5, 32, 3, 1, dropout_p=0.5).train()
+        opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)
+        hb = synthetic.lightpath_store(B, seed=1).host_batch(0, B)
+        steps = min(K, 20)
+        for i in range(3 + steps):
+            if i == 3:
+                t0 = time.perf_counter()
+            opt.zero_grad()
+            out, lb = m(hb)
+            crit(out, hb.y[lb]).backward()
+            opt.step()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"impl": "reference", "metric": "lightpath_train_graphs_per_sec", "value": steps * B / dt,
+                          "unit": "graphs/s", "steps": steps, "ms_per_step": dt / steps * 1e3,
+                          "cpu_baseline": {"kind": "port", "cores": os.cpu_count(), "sample": f"{steps} steps of {B} graphs"}}),
+              flush=True)
+        return
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.5).to(dev).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    nb = 16
+    store = synthetic.lightpath_store(B * nb, seed=1, device=dev)
+    batches = [store.collate(range(i * B, (i + 1) * B)) for i in range(nb)]
+
+    def step(i):
+        b = batches[i % nb]
+        opt.zero_grad()
+        out, lb = model(b)
+        loss = crit(out, b.y[lb])
+        loss.backward()
+        opt.step()
+        return loss
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = _ev(), _ev()
+    e0.record()
+    for i in range(K):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"metric": "lightpath_train_graphs_per_sec", "value": K * B / (ms * 1e-3), "unit": "graphs/s",
+                      "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "final_loss": float(loss),
+                      "config": {"workload": f"LightpathGNN train step, batch {B}, SGD(0.1,0.9), dropout 0.5, eager"}}),
+          flush=True)
 
 
 # --------------------------------------------------------------------------- cfg 3

@@ -53,6 +53,8 @@ SIGNATURES = {
     "qot_gemm": (C.c_int, [P, i64, i64, P, P, i64, i64, P, P, i64, i64, i64, i64, vp]),
     "qot_gemm_tf32x3_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_gemm_tf32x3": (C.c_int, [P, i64, P, P, i64, P, P, i64, i64, i64, i64, P, P, sz, vp]),
+    "qot_wgrad_tf32x3_workspace_bytes": (sz, [i64, i64, i64]),
+    "qot_wgrad_tf32x3": (C.c_int, [P, i64, P, i64, P, i64, i64, i64, P, i64, P, P, sz, vp]),
     "qot_wgrad_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_wgrad": (C.c_int, [P, i64, P, i64, i64, i64, i64, P, i64, P, sz, vp]),
     "qot_colsum_workspace_bytes": (sz, [i64, i64]),

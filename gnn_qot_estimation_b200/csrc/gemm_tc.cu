@@ -93,6 +93,44 @@ split_tf32_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __re
   }
 }
 
+// Transposing variant for weight gradients: src [R, Cc] (optional row gather) -> hi / lo [Cc, Rpad],
+// i.e. the reduction dimension R becomes the contiguous (K-major) one; columns r in [R, Rpad) are zero.
+__global__ void __launch_bounds__(256)
+split_tf32_transpose_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ gather,
+                            int64_t R, int64_t Cc, int64_t Rpad, float* __restrict__ hi,
+                            float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) v = src[(gather ? gather[r] : r) * ld + c];
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < Cc && r < Rpad) {
+      const float v = tile[tx][ty + 8 * i];
+      const float h = to_tf32(v);
+      hi[c * Rpad + r] = h;
+      lo[c * Rpad + r] = to_tf32(v - h);
+    }
+  }
+}
+// out[i] = sum_z part[z*n + i], z ascending (fixed order)
+__global__ void tc_reduce_splits_kernel(const float* __restrict__ part, int64_t n, int splits,
+                                        float* __restrict__ out, int64_t ncols, int64_t ld_out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int z = 0; z < splits; ++z) a += part[static_cast<int64_t>(z) * n + i];
+  out[(i / ncols) * ld_out + (i % ncols)] = a;
+}
+
 // rows [r0, r0+128) x k [k0, k0+32) of a dense [nrows, K] matrix -> one swizzled shared tile with cp.async:
 // row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7); rows past nrows are zero-filled
 __device__ __forceinline__ void cp_async_tile(const float* __restrict__ src, int64_t K, int64_t r0,
@@ -114,7 +152,7 @@ __global__ void __launch_bounds__(128)
 gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    const float* __restrict__ Whi, const float* __restrict__ Wlo,
                    const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M,
-                   int64_t Nc, int64_t K, int32_t* __restrict__ status) {
+                   int64_t Nc, int64_t K, int64_t kb_per_split, int32_t* __restrict__ status) {
   extern __shared__ char tc_smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -139,13 +177,18 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   const unsigned tmem_d = *tmem_slot;
   constexpr unsigned idesc = tc_idesc(TC_BM, TC_BN);
 
-  const int64_t nkb = K / TC_BK;
+  // split-K (weight gradients: few output tiles, long reduction): slice z owns k-blocks
+  // [kb0, kb0 + nkb) and writes its own partial tile set C + z*M*Nc (ldc == Nc), summed afterwards
+  const int64_t kb0 = static_cast<int64_t>(blockIdx.z) * kb_per_split;
+  const int64_t nkb = max(static_cast<int64_t>(0), min(K / TC_BK - kb0, kb_per_split));
+  if (gridDim.z > 1) C += static_cast<int64_t>(blockIdx.z) * M * Nc;
   auto issue_loads = [&](int64_t kb) {
     char* base = smem + static_cast<int>(kb % TC_STAGES) * TC_STAGE_BYTES;
-    cp_async_tile(Ahi, K, m0, M, kb * TC_BK, base, tid);
-    cp_async_tile(Alo, K, m0, M, kb * TC_BK, base + TC_TILE_BYTES, tid);
-    cp_async_tile(Whi, K, n0, Nc, kb * TC_BK, base + 2 * TC_TILE_BYTES, tid);
-    cp_async_tile(Wlo, K, n0, Nc, kb * TC_BK, base + 3 * TC_TILE_BYTES, tid);
+    const int64_t k0 = (kb0 + kb) * TC_BK;
+    cp_async_tile(Ahi, K, m0, M, k0, base, tid);
+    cp_async_tile(Alo, K, m0, M, k0, base + TC_TILE_BYTES, tid);
+    cp_async_tile(Whi, K, n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
+    cp_async_tile(Wlo, K, n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
   };
   bool ok = true;
   for (int64_t kb = 0; kb < TC_STAGES - 1; ++kb) {                  // prologue: STAGES-1 blocks in flight
@@ -209,6 +252,10 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (nkb == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;                       // empty k-slice: the accumulator was never written
+    }
     if (row < M) {
       float* crow = C + row * ldc + n0 + c0;
       if (n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
@@ -280,7 +327,70 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
   QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");
-  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K, status);
+  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K,
+                                                            K / TC_BK, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+// Weight gradient on the tensor cores: C[Mo,No] (ldc) = sum_r A[r,:Mo]^T B[r,:No] over R rows (row-major
+// A [R,lda], B [R,ldb]; optional row gather on B: the embedding lookup of the forward).  Both operands are
+// transposed + hi/lo-split into K-major form (reduction over rows contiguous, padded to 32), the reduction is
+// cut into split-K slices so the few output tiles still fill the machine, and the slices are summed in a fixed
+// order -- deterministic.
+static int tc_wgrad_splits(int64_t tiles, int64_t nkb) {
+  const int64_t want = std::max<int64_t>(1, (2 * kNumSMs) / std::max<int64_t>(tiles, 1));
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, nkb / 4 + 1), 64)));
+}
+static int64_t tc_rpad(int64_t R) { return cdiv(R, TC_BK) * TC_BK; }
+
+extern "C" size_t qot_wgrad_tf32x3_workspace_bytes(int64_t R, int64_t Mo, int64_t No) {
+  if (R < 0 || Mo < 0 || No < 0) return 0;
+  const int64_t rp = tc_rpad(R);
+  const int splits = tc_wgrad_splits(cdiv(Mo, TC_BM) * cdiv(No, TC_BN), rp / TC_BK);
+  return 2 * align_up(static_cast<size_t>(Mo) * rp * 4) + 2 * align_up(static_cast<size_t>(No) * rp * 4) +
+         align_up(static_cast<size_t>(splits) * Mo * No * 4) + 256;
+}
+
+extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb,
+                                const int64_t* gather_b, int64_t R, int64_t Mo, int64_t No, float* C,
+                                int64_t ldc, int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(R > 0 && Mo > 0 && No > 0, "qot_wgrad_tf32x3: bad size");
+  QOT_REQUIRE(A && B && C && ldc >= No, "qot_wgrad_tf32x3: null operand");
+  QOT_REQUIRE(ws && ws_bytes >= qot_wgrad_tf32x3_workspace_bytes(R, Mo, No), "qot_wgrad_tf32x3: workspace too small");
+  static bool attr_set = false;
+  if (!attr_set) {
+    QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t rp = tc_rpad(R), nkb = rp / TC_BK;
+  const int64_t tiles = cdiv(Mo, TC_BM) * cdiv(No, TC_BN);
+  const int splits = tc_wgrad_splits(tiles, nkb);
+  const int64_t kps = cdiv(nkb, splits);
+  Carver c(ws);
+  float* at_hi = c.take<float>(Mo * rp);
+  float* at_lo = c.take<float>(Mo * rp);
+  float* bt_hi = c.take<float>(No * rp);
+  float* bt_lo = c.take<float>(No * rp);
+  float* part = c.take<float>(static_cast<size_t>(splits) * Mo * No);
+  dim3 ga(static_cast<unsigned>(rp / 32), static_cast<unsigned>(cdiv(Mo, 32)));
+  dim3 gb(static_cast<unsigned>(rp / 32), static_cast<unsigned>(cdiv(No, 32)));
+  QOT_REQUIRE(ga.y <= 65535u && gb.y <= 65535u, "qot_wgrad_tf32x3: operand too wide for one launch");
+  split_tf32_transpose_kernel<<<ga, 256, 0, stream>>>(A, lda, nullptr, R, Mo, rp, at_hi, at_lo);
+  QOT_LAUNCH_CHECK();
+  split_tf32_transpose_kernel<<<gb, 256, 0, stream>>>(B, ldb, gather_b, R, No, rp, bt_hi, bt_lo);
+  QOT_LAUNCH_CHECK();
+  dim3 grid(static_cast<unsigned>(cdiv(Mo, TC_BM)), static_cast<unsigned>(cdiv(No, TC_BN)), static_cast<unsigned>(splits));
+  if (splits == 1) {
+    gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, status);
+    QOT_LAUNCH_CHECK();
+    return QOT_OK;
+  }
+  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, status);
+  QOT_LAUNCH_CHECK();
+  const int64_t n = Mo * No;
+  tc_reduce_splits_kernel<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, stream>>>(part, n, splits, C, No, ldc);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

@@ -424,6 +424,22 @@ def gemm_tf32x3(A, W, bias=None, gather=None):
     return C_
 
 
+def wgrad_tf32x3(dy, x, gather=None):
+    """dW [Nc,K] = dy^T @ x[gather] on the tensor cores (split-K, fixed-order sum)."""
+    L = _lib.lib()
+    R, Nc = dy.shape
+    K = x.shape[1]
+    dev = dy.device
+    st = _tc_status.get(dev)
+    if st is None:
+        st = _tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    dW = torch.empty(Nc, K, dtype=torch.float32, device=dev)
+    ws = _lib.workspace(L.qot_wgrad_tf32x3_workspace_bytes(R, Nc, K), dev)
+    check(L.qot_wgrad_tf32x3(ptr(dy), Nc, ptr(x), K, ptr(gather), R, Nc, K, ptr(dW), K, ptr(st),
+                             ptr(ws), ws.numel(), stream()), "qot_wgrad_tf32x3")
+    return dW
+
+
 class _NodeLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ids, W, b):
@@ -469,7 +485,9 @@ class _NodeLinearFn(torch.autograd.Function):
                 ws = _ws(L.qot_segment_sum_workspace_bytes(M, V, K), dev)
                 check(L.qot_segment_sum(ptr(dxr), ptr(csr.rowptr), ptr(csr.eid), M, V, K, ptr(dx),
                                         ptr(ws), ws.numel(), stream()), "qot_segment_sum")
-        if need_w:
+        if need_w and M >= TC_MIN_ROWS and Nc >= 64 and K >= 64:
+            dW = wgrad_tf32x3(dy, x, ids)                                    # dy^T @ x[ids], tensor cores
+        elif need_w:
             xr = x if ids is None else _gather_rows(x, ids)
             dW = torch.empty(Nc, K, dtype=torch.float32, device=dev)         # dy^T @ x
             ws = _ws(L.qot_wgrad_workspace_bytes(M, Nc, K), dev)

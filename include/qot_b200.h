@@ -131,6 +131,14 @@ int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const fl
                     const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
                     int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
+/* Weight gradient on the tensor cores (same 3 x TF32 scheme): C[Mo,No] (ldc) = sum_r A[r,:Mo]^T
+ * B[gather_b ? gather_b[r] : r, :No] over R rows.  Operands are transposed + split into K-major form,
+ * the reduction is cut into split-K slices that are summed in a fixed order (deterministic). */
+size_t qot_wgrad_tf32x3_workspace_bytes(int64_t R, int64_t Mo, int64_t No);
+int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, const int64_t* gather_b,
+                     int64_t R, int64_t Mo, int64_t No, float* C, int64_t ldc, int32_t* status,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* Deterministic weight gradient: C[Mo,No] (ldc) = sum_r A[r,Mo]^T * B[r,No] over
  * R rows (row-major A [R,lda], B [R,ldb]); two-stage fixed-order reduction.
  * gather (optional int64 [R]) scatters by row: C[gather[r], :] += B[r, :] is NOT

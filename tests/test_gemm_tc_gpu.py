@@ -42,3 +42,30 @@ def test_gemm_tf32x3_deterministic(cuda):
     A = torch.randn(2048, 256, device=cuda)
     W = torch.randn(512, 256, device=cuda)
     assert torch.equal(ops.gemm_tf32x3(A, W), ops.gemm_tf32x3(A, W))
+
+
+@pytest.mark.parametrize("R,Mo,No", [(1000, 128, 128), (10000, 2560, 256), (4099, 1024, 256), (2048, 70, 100)])
+def test_wgrad_tf32x3_matches_fp64(cuda, R, Mo, No):
+    """dW = dy^T x on the tensor cores (transposed split operands, split-K slices summed in fixed order)."""
+    from gnn_qot_estimation_b200 import ops
+    g = torch.Generator().manual_seed(R + Mo)
+    dy = torch.randn(R, Mo, generator=g)
+    x = torch.randn(R, No, generator=g)
+    C = ops.wgrad_tf32x3(dy.to(cuda), x.to(cuda))
+    ref = dy.double().t() @ x.double()
+    assert int(ops._tc_status[C.device].item()) == 0
+    assert rel_err(C, ref) <= 1e-5
+    scale = (dy.abs().double().t() @ x.abs().double()).clamp_min(1e-30)
+    assert float(((C.double().cpu() - ref).abs() / scale).max()) <= 2e-6
+    assert torch.equal(C, ops.wgrad_tf32x3(dy.to(cuda), x.to(cuda)))
+
+
+def test_wgrad_tf32x3_gather(cuda):
+    from gnn_qot_estimation_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    table = torch.randn(300, 128, generator=g)
+    ids = torch.randint(0, 300, (5000,), generator=g)
+    dy = torch.randn(5000, 192, generator=g)
+    C = ops.wgrad_tf32x3(dy.to(cuda), table.to(cuda), ids.to(cuda))
+    ref = dy.double().t() @ table[ids].double()
+    assert rel_err(C, ref) <= 1e-5
