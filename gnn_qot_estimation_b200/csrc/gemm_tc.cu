@@ -75,21 +75,33 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
   return false;
 }
 
-// hi = tf32(v), lo = tf32(v - hi) of rows [0, rows) of `src` (optional gather), K columns
+// hi = tf32(v), lo = tf32(v - hi) of rows [0, rows) of `src` (optional gather), K columns.
+// One warp per row per pass, four rows in flight per warp (independent 128-bit loads).
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ gather,
                   int64_t rows, int64_t K, float* __restrict__ hi, float* __restrict__ lo) {
-  const int64_t kv = K / 4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * kv;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / kv, c = i % kv;
-    const int64_t row = gather ? gather[r] : r;
-    const float4 v = *reinterpret_cast<const float4*>(src + row * ld + c * 4);
-    float4 h, l;
-    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    *reinterpret_cast<float4*>(hi + r * K + c * 4) = h;
-    *reinterpret_cast<float4*>(lo + r * K + c * 4) = l;
+  const int lane = threadIdx.x & 31;
+  const int kv = static_cast<int>(K / 4);
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 4;
+  for (int c = lane; c < kv; c += 32) {
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v[i] = *reinterpret_cast<const float4*>(src + (gather ? gather[r] : r) * ld + c * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + i;
+      if (r < rows) {
+        float4 h, l;
+        h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
+        l.x = to_tf32(v[i].x - h.x); l.y = to_tf32(v[i].y - h.y); l.z = to_tf32(v[i].z - h.z); l.w = to_tf32(v[i].w - h.w);
+        *reinterpret_cast<float4*>(hi + r * K + c * 4) = h;
+        *reinterpret_cast<float4*>(lo + r * K + c * 4) = l;
+      }
+    }
   }
 }
 
@@ -197,15 +209,7 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   }
   for (int64_t kb = 0; kb < nkb; ++kb) {
     const int st = static_cast<int>(kb % TC_STAGES);
-    const int64_t nxt = kb + TC_STAGES - 1;                         // block to prefetch; its stage was read by
-    if (nxt < nkb) {                                                // the MMAs of block kb-1
-      if (kb >= 1)
-        ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
-                        static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
-      issue_loads(nxt);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 1) : "memory");   // this thread's part of block kb landed
+    asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block kb landed
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -225,6 +229,16 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                        smem_u32(bars + st))
                    : "memory");
     }
+    // refill the stage block kb-1 used, for block kb+STAGES-1.  Its MMAs are waited for only now, with
+    // the MMAs of block kb already queued behind them, so the tensor pipe never drains.
+    const int64_t nxt = kb + TC_STAGES - 1;
+    if (nxt < nkb) {
+      if (kb >= 1)
+        ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
+                        static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
+      issue_loads(nxt);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // the last commit covers all MMAs: wait for it before reading the accumulator
   if (nkb > 0) {
@@ -320,10 +334,9 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   float* a_lo = c.take<float>(M * K);
   float* w_hi = c.take<float>(Nc * K);
   float* w_lo = c.take<float>(Nc * K);
-  auto blocks_for = [](int64_t n) { return static_cast<unsigned>(std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)); };
-  split_tf32_kernel<<<blocks_for(M * K / 4), 256, 0, stream>>>(A, lda, gather, M, K, a_hi, a_lo);
+  split_tf32_kernel<<<static_cast<unsigned>(cdiv(M, 32)), 256, 0, stream>>>(A, lda, gather, M, K, a_hi, a_lo);
   QOT_LAUNCH_CHECK();
-  split_tf32_kernel<<<blocks_for(Nc * K / 4), 256, 0, stream>>>(W, ldw, nullptr, Nc, K, w_hi, w_lo);
+  split_tf32_kernel<<<static_cast<unsigned>(cdiv(Nc, 32)), 256, 0, stream>>>(W, ldw, nullptr, Nc, K, w_hi, w_lo);
   QOT_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
   QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");

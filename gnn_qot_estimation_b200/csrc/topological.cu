@@ -539,68 +539,108 @@ pool_partial_kernel(const float* __restrict__ x, const int64_t* __restrict__ gpt
   }
 }
 
-__global__ void __launch_bounds__(kPoolWarps * 32)
+// Head, one graph per TPG threads (TPG = 32: a warp per graph for H <= 32; TPG = 256: a block per
+// graph for wide hidden sizes, so the H x H weight is read with coalesced rows and the work of a
+// single big graph is not left to one warp).  pooled = sum of the S partials / n.
+template <int TPG>
+__global__ void __launch_bounds__(kPoolWarps * 32 < TPG ? TPG : kPoolWarps * 32)
 pool_mlp_fwd_kernel(const float* __restrict__ partial, int S, const int64_t* __restrict__ gptr, int64_t B, int H,
                     const float* __restrict__ W1, const float* __restrict__ b1,
                     const float* __restrict__ W2, const float* __restrict__ b2,
                     const float* __restrict__ hmask, float* __restrict__ pooled,
                     float* __restrict__ hid, float* __restrict__ out) {
-  __shared__ float s_p[kPoolWarps][kMaxH];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * kPoolWarps + warp;
-  if (g >= B) return;
-  const int64_t n0 = gptr[g], n1 = gptr[g + 1];
-  const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
-  for (int c = lane; c < H; c += 32) {
-    float a = 0.f;
-    for (int s = 0; s < S; ++s) a += partial[(g * S + s) * H + c];
-    a *= inv;
-    s_p[warp][c] = a;
-    if (pooled) pooled[g * H + c] = a;
+  constexpr int GPB = (kPoolWarps * 32 < TPG ? TPG : kPoolWarps * 32) / TPG;   // graphs per block
+  __shared__ float s_p[GPB][kMaxH];
+  __shared__ float s_a[GPB][kMaxH];
+  const int gl = threadIdx.x / TPG, t = threadIdx.x % TPG;
+  const int lane = threadIdx.x & 31;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * GPB + gl;
+  const bool live = g < B;
+  if (live) {
+    const int64_t n0 = gptr[g], n1 = gptr[g + 1];
+    const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
+    for (int c = t; c < H; c += TPG) {
+      float a = 0.f;
+      for (int s = 0; s < S; ++s) a += partial[(g * S + s) * H + c];
+      a *= inv;
+      s_p[gl][c] = a;
+      if (pooled) pooled[g * H + c] = a;
+    }
   }
-  __syncwarp();
-  float o[QOT_OUT] = {0.f, 0.f, 0.f};
-  for (int u = lane; u < H; u += 32) {
-    float hv = b1[u];
-    for (int c = 0; c < H; ++c) hv = fmaf(W1[u * H + c], s_p[warp][c], hv);
-    if (hid) hid[g * H + u] = hv;
-    float act = leaky(hv, 0.01f);
-    if (hmask) act *= hmask[g * H + u];
-#pragma unroll
-    for (int k = 0; k < QOT_OUT; ++k) o[k] = fmaf(W2[k * H + u], act, o[k]);
+  if (TPG > 32) __syncthreads(); else __syncwarp();
+  if (live) {
+    if (TPG == 32) {                                   // lane u owns hidden unit u (H <= 32 here: tiny weights)
+      for (int u = t; u < H; u += 32) {
+        float hv = b1[u];
+        for (int c = 0; c < H; ++c) hv = fmaf(W1[u * H + c], s_p[gl][c], hv);
+        if (hid) hid[g * H + u] = hv;
+        float act = leaky(hv, 0.01f);
+        if (hmask) act *= hmask[g * H + u];
+        s_a[gl][u] = act;
+      }
+    } else {                                           // warp w owns units w, w+8, ...; lanes stride the row
+      const int w = t >> 5;
+      for (int u = w; u < H; u += TPG / 32) {
+        float part = 0.f;
+        for (int c = lane; c < H; c += 32) part = fmaf(W1[u * H + c], s_p[gl][c], part);
+        part = warp_sum(part);
+        if (lane == 0) {
+          const float hv = part + b1[u];
+          if (hid) hid[g * H + u] = hv;
+          float act = leaky(hv, 0.01f);
+          if (hmask) act *= hmask[g * H + u];
+          s_a[gl][u] = act;
+        }
+      }
+    }
   }
+  if (TPG > 32) __syncthreads(); else __syncwarp();
+  if (live && t < 32) {                                // first warp of the graph: the 3 outputs
+    float o[QOT_OUT] = {0.f, 0.f, 0.f};
+    for (int u = lane; u < H; u += 32) {
+      const float act = s_a[gl][u];
 #pragma unroll
-  for (int k = 0; k < QOT_OUT; ++k) o[k] = warp_sum(o[k]);
-  if (lane < QOT_OUT) out[g * QOT_OUT + lane] = (lane == 0 ? o[0] : lane == 1 ? o[1] : o[2]) + b2[lane];
+      for (int k = 0; k < QOT_OUT; ++k) o[k] = fmaf(W2[k * H + u], act, o[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < QOT_OUT; ++k) o[k] = warp_sum(o[k]);
+    if (lane < QOT_OUT) out[g * QOT_OUT + lane] = (lane == 0 ? o[0] : lane == 1 ? o[1] : o[2]) + b2[lane];
+  }
 }
 
 // backward, per graph: dhid, act (for the weight gradients) and dpool [B,H] = W1^T dhid / n_g
-__global__ void __launch_bounds__(kPoolWarps * 32)
+template <int TPG>
+__global__ void __launch_bounds__(kPoolWarps * 32 < TPG ? TPG : kPoolWarps * 32)
 pool_mlp_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hid,
                     const float* __restrict__ hmask, const int64_t* __restrict__ gptr, int64_t B, int H,
                     const float* __restrict__ W1, const float* __restrict__ W2,
                     float* __restrict__ dpool, float* __restrict__ dhid, float* __restrict__ act) {
-  __shared__ float s_d[kPoolWarps][kMaxH];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * kPoolWarps + warp;
-  if (g >= B) return;
-  const float d0 = dout[g * QOT_OUT + 0], d1 = dout[g * QOT_OUT + 1], d2 = dout[g * QOT_OUT + 2];
-  for (int u = lane; u < H; u += 32) {
-    const float hv = hid[g * H + u];
-    const float mk = hmask ? hmask[g * H + u] : 1.f;
-    const float dact = W2[0 * H + u] * d0 + W2[1 * H + u] * d1 + W2[2 * H + u] * d2;
-    const float dh = dact * mk * (hv > 0.f ? 1.f : 0.01f);
-    s_d[warp][u] = dh;
-    dhid[g * H + u] = dh;
-    act[g * H + u] = leaky(hv, 0.01f) * mk;
+  constexpr int GPB = (kPoolWarps * 32 < TPG ? TPG : kPoolWarps * 32) / TPG;
+  __shared__ float s_d[GPB][kMaxH];
+  const int gl = threadIdx.x / TPG, t = threadIdx.x % TPG;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * GPB + gl;
+  const bool live = g < B;
+  if (live) {
+    const float d0 = dout[g * QOT_OUT + 0], d1 = dout[g * QOT_OUT + 1], d2 = dout[g * QOT_OUT + 2];
+    for (int u = t; u < H; u += TPG) {
+      const float hv = hid[g * H + u];
+      const float mk = hmask ? hmask[g * H + u] : 1.f;
+      const float dact = W2[0 * H + u] * d0 + W2[1 * H + u] * d1 + W2[2 * H + u] * d2;
+      const float dh = dact * mk * (hv > 0.f ? 1.f : 0.01f);
+      s_d[gl][u] = dh;
+      dhid[g * H + u] = dh;
+      act[g * H + u] = leaky(hv, 0.01f) * mk;
+    }
   }
-  __syncwarp();
-  const int64_t n0 = gptr[g], n1 = gptr[g + 1];
-  const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
-  for (int c = lane; c < H; c += 32) {
-    float dp = 0.f;
-    for (int u = 0; u < H; ++u) dp = fmaf(W1[u * H + c], s_d[warp][u], dp);
-    dpool[g * H + c] = dp * inv;
+  if (TPG > 32) __syncthreads(); else __syncwarp();
+  if (live) {
+    const int64_t n0 = gptr[g], n1 = gptr[g + 1];
+    const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
+    for (int c = t; c < H; c += TPG) {                 // W1[u*H + c]: coalesced over c
+      float dp = 0.f;
+      for (int u = 0; u < H; ++u) dp = fmaf(W1[u * H + c], s_d[gl][u], dp);
+      dpool[g * H + c] = dp * inv;
+    }
   }
 }
 
@@ -780,8 +820,12 @@ extern "C" int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t N, 
   float* partial = static_cast<float*>(ws);
   pool_partial_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(x, gptr, static_cast<int>(H), S, partial);
   QOT_LAUNCH_CHECK();
-  pool_mlp_fwd_kernel<<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
-      partial, S, gptr, B, static_cast<int>(H), W1, b1, W2, b2, hmask, pooled, hid, out);
+  if (H <= 32)
+    pool_mlp_fwd_kernel<32><<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
+        partial, S, gptr, B, static_cast<int>(H), W1, b1, W2, b2, hmask, pooled, hid, out);
+  else
+    pool_mlp_fwd_kernel<256><<<static_cast<unsigned>(B), 256, 0, stream>>>(
+        partial, S, gptr, B, static_cast<int>(H), W1, b1, W2, b2, hmask, pooled, hid, out);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -812,8 +856,12 @@ extern "C" int qot_pool_mlp_bwd(const float* dout, const float* pooled, const fl
   void* w1ws = c.take<char>(w1b);
   void* w2ws = c.take<char>(w2b);
   void* csws = c.take<char>(csb);
-  pool_mlp_bwd_kernel<<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
-      dout, hid, hmask, gptr, B, static_cast<int>(H), W1, W2, dpool, dhid, act);
+  if (H <= 32)
+    pool_mlp_bwd_kernel<32><<<static_cast<unsigned>(cdiv(B, kPoolWarps)), kPoolWarps * 32, 0, stream>>>(
+        dout, hid, hmask, gptr, B, static_cast<int>(H), W1, W2, dpool, dhid, act);
+  else
+    pool_mlp_bwd_kernel<256><<<static_cast<unsigned>(B), 256, 0, stream>>>(
+        dout, hid, hmask, gptr, B, static_cast<int>(H), W1, W2, dpool, dhid, act);
   QOT_LAUNCH_CHECK();
   if (N > 0) {
     const int S = pool_split(N, B);
