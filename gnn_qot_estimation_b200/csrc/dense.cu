@@ -98,14 +98,18 @@ gemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const int64
   }
 }
 
-// out[i] = sum_s part[s*n + i], s ascending: the fixed-order second stage.
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int64_t n, int splits,
-                                       float* __restrict__ out, int64_t ld_out, int64_t ncols) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+// out[i] = sum_s part[s*n + i]: the fixed-order second stage.  One warp per output element: lanes
+// stride over the slices, then a shuffle tree (the order depends on `splits` only).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int64_t n, int splits,
+                       float* __restrict__ out, int64_t ld_out, int64_t ncols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (i >= n) return;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += part[static_cast<int64_t>(k) * n + i];
-  out[(i / ncols) * ld_out + (i % ncols)] = s;
+  for (int k = lane; k < splits; k += 32) s += part[static_cast<int64_t>(k) * n + i];
+  s = warp_sum(s);
+  if (lane == 0) out[(i / ncols) * ld_out + (i % ncols)] = s;
 }
 
 constexpr int kColsumRows = 256;   // rows per first-stage block
@@ -234,7 +238,7 @@ extern "C" int qot_wgrad(const float* A, int64_t lda, const float* B, int64_t ld
   gemm_kernel<<<grid, 256, 0, stream>>>(A, 1, lda, nullptr, B, ldb, 1, nullptr, part, No, Mo, No, R, kps);
   QOT_LAUNCH_CHECK();
   const int64_t n = Mo * No;
-  reduce_partials_kernel<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, stream>>>(part, n, splits, C, ldc, No);
+  reduce_partials_kernel<<<static_cast<unsigned>(cdiv(n, 8)), 256, 0, stream>>>(part, n, splits, C, ldc, No);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -257,7 +261,7 @@ extern "C" int qot_colsum(const float* A, int64_t lda, int64_t R, int64_t Nc, fl
   dim3 grid(static_cast<unsigned>(cdiv(Nc, 32)), static_cast<unsigned>(chunks));
   colsum_stage1_kernel<<<grid, 256, 0, stream>>>(A, lda, R, Nc, part);
   QOT_LAUNCH_CHECK();
-  reduce_partials_kernel<<<static_cast<unsigned>(cdiv(Nc, 256)), 256, 0, stream>>>(
+  reduce_partials_kernel<<<static_cast<unsigned>(cdiv(Nc, 8)), 256, 0, stream>>>(
       part, Nc, static_cast<int>(chunks), out, Nc, Nc);
   QOT_LAUNCH_CHECK();
   return QOT_OK;

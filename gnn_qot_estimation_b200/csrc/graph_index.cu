@@ -172,19 +172,52 @@ __global__ void csr_sort_rows_kernel(const int64_t* __restrict__ other, int64_t 
   for (int32_t i = beg; i < end; ++i) nbr[i] = static_cast<int32_t>(other[eid[i]]);
 }
 
-// Hub rows: rank sort (edge ids are unique), using the not-yet-written nbr segment
-// of the row as the temporary copy.
+// Hub rows (more than kSmallRow entries): up to kBitonicMax entries are sorted by a bitonic network in
+// shared memory; longer rows by rank (edge ids are unique), using the not-yet-written nbr segment of
+// the row as the temporary copy.
+constexpr int kBitonicMax = 4096;
+
 __global__ void __launch_bounds__(256)
 csr_sort_big_rows_kernel(const int64_t* __restrict__ other, int add_self,
                          const int32_t* __restrict__ rowptr, int32_t* __restrict__ eid,
                          int32_t* __restrict__ nbr, const int32_t* __restrict__ big_count,
                          const int32_t* __restrict__ big_rows) {
+  __shared__ int32_t s_key[kBitonicMax];
   const int32_t nbig = *big_count;
   for (int32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
     const int32_t r = big_rows[b];
     const int32_t beg = rowptr[r];
     const int32_t end = rowptr[r + 1] - (add_self ? 1 : 0);
     const int32_t n = end - beg;
+    if (n <= kBitonicMax) {
+      int32_t m = 1;
+      while (m < n) m <<= 1;
+      for (int32_t i = threadIdx.x; i < m; i += blockDim.x) s_key[i] = i < n ? eid[beg + i] : 0x7fffffff;
+      __syncthreads();
+      for (int32_t k = 2; k <= m; k <<= 1) {
+        for (int32_t j = k >> 1; j > 0; j >>= 1) {
+          for (int32_t i = threadIdx.x; i < m; i += blockDim.x) {
+            const int32_t p = i ^ j;
+            if (p > i) {
+              const int32_t a = s_key[i], c = s_key[p];
+              const bool up = (i & k) == 0;
+              if ((a > c) == up) {
+                s_key[i] = c;
+                s_key[p] = a;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int32_t e = s_key[i];
+        eid[beg + i] = e;
+        nbr[beg + i] = static_cast<int32_t>(other[e]);
+      }
+      __syncthreads();
+      continue;
+    }
     for (int32_t i = threadIdx.x; i < n; i += blockDim.x) nbr[beg + i] = eid[beg + i];
     __syncthreads();
     for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
