@@ -85,6 +85,12 @@ SIGNATURES = {
     "qot_gat_bwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, P, P, P, P, sz, vp]),
     "qot_bn_stats_workspace_bytes": (sz, [i64, i64]),
     "qot_bn_stats": (C.c_int, [P, i64, i64, P, P, P, P, C.c_float, P, sz, vp]),
+    "qot_bn_apply": (C.c_int, [P, i64, i64, P, P, C.c_float, P, P, P, vp]),
+    "qot_bn_bwd_dense_workspace_bytes": (sz, [i64, i64]),
+    "qot_bn_bwd_dense": (C.c_int, [P, P, P, C.c_float, P, P, i64, i64, C.c_int, P, P, P, P, sz, vp]),
+    "qot_mean_pool_workspace_bytes": (sz, [i64, i64, i64]),
+    "qot_mean_pool_fwd": (C.c_int, [P, P, i64, i64, i64, P, P, sz, vp]),
+    "qot_mean_pool_bwd": (C.c_int, [P, P, i64, i64, i64, P, P, sz, vp]),
     "qot_lut_select_workspace_bytes": (sz, [i64]),
     "qot_lut_select": (C.c_int, [P, i64, i64, i32, P, P, P, P, P, sz, vp]),
     "qot_lut_head_fwd": (C.c_int, [P, P, i64, P, P, C.c_float, P, P, P, P, P, P, P, P, P, P, vp]),

@@ -496,6 +496,87 @@ __global__ void bn_bwd_lut_rows_kernel(const float* __restrict__ var, float eps,
   dh[static_cast<int64_t>(lut_node[l]) * C + c] += bn_w[c] / sqrtf(var[c] + eps) * dy[idx];
 }
 
+// ---------------------------------------------------------------------------
+// Stand-alone BatchNorm over all rows (PyG BatchNorm used as its own layer,
+// lightpath_training/models.py:31 when the reference's models.py is kept and only its layer
+// imports are swapped): apply, and the dense backward.
+// ---------------------------------------------------------------------------
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t total4, int64_t C,
+                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ y) {
+  const int64_t i4 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t c0 = (i4 * 4) % C;
+  const float4 v = *reinterpret_cast<const float4*>(x + i4 * 4);
+  const float in[4] = {v.x, v.y, v.z, v.w};
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t c = c0 + k;
+    o[k] = (in[k] - mean[c]) / sqrtf(var[c] + eps) * w[c] + b[c];
+  }
+  *reinterpret_cast<float4*>(y + i4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// partials of sum(dy * xhat) and sum(dy) per channel over chunks of kBnRows rows
+__global__ void __launch_bounds__(256)
+bn_bwd_dense_stage1_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ var, float eps, const float* __restrict__ dy,
+                           int64_t N, int64_t C, float* __restrict__ part) {
+  __shared__ float s_w[8][33], s_b[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 32 + cx;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kBnRows, r1 = min(N, r0 + kBnRows);
+  float gw = 0.f, gb = 0.f;
+  if (c < C) {
+    const float mu = mean[c], inv = 1.f / sqrtf(var[c] + eps);
+#pragma unroll 4
+    for (int64_t r = r0 + ry; r < r1; r += 8) {
+      const float g = dy[r * C + c];
+      gw = fmaf(g, (x[r * C + c] - mu) * inv, gw);
+      gb += g;
+    }
+  }
+  s_w[ry][cx] = gw;
+  s_b[ry][cx] = gb;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      tw += s_w[k][cx];
+      tb += s_b[k][cx];
+    }
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * C + c] = tw;
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * C + c] = tb;
+  }
+}
+
+__global__ void bn_bwd_dense_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                          const float* __restrict__ var, float eps,
+                                          const float* __restrict__ w, const float* __restrict__ dy,
+                                          const float* __restrict__ d_w, const float* __restrict__ d_b,
+                                          int64_t N, int64_t C, int batch_stats, float* __restrict__ dx) {
+  const int64_t i4 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i4 >= N * C / 4) return;
+  const int64_t c0 = (i4 * 4) % C;
+  const float4 xv = *reinterpret_cast<const float4*>(x + i4 * 4);
+  const float4 gv = *reinterpret_cast<const float4*>(dy + i4 * 4);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+  const float invN = 1.f / static_cast<float>(N);
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t c = c0 + k;
+    const float inv = 1.f / sqrtf(var[c] + eps);
+    float g = gs[k];
+    if (batch_stats) g -= invN * (d_b[c] + (xs[k] - mean[c]) * inv * d_w[c]);
+    o[k] = w[c] * inv * g;
+  }
+  *reinterpret_cast<float4*>(dx + i4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace qot
 
 using namespace qot;
@@ -690,6 +771,44 @@ extern "C" int qot_bn_bwd_sparse(const float* h, const float* mean, const float*
       h, mean, var, eps, bn_w, d_bn_w, d_bn_b, N, C, batch_stats, dh);
   QOT_LAUNCH_CHECK();
   bn_bwd_lut_rows_kernel<<<static_cast<unsigned>(cdiv(L * C, 256)), 256, 0, stream>>>(var, eps, bn_w, dy, lut_node, L, C, dh);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" int qot_bn_apply(const float* x, int64_t N, int64_t C, const float* mean, const float* var,
+                            float eps, const float* w, const float* b, float* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(N >= 0 && C > 0 && C % 4 == 0, "qot_bn_apply: C must be a positive multiple of 4");
+  if (N == 0) return QOT_OK;
+  QOT_REQUIRE(x && mean && var && w && b && y, "qot_bn_apply: null argument");
+  const int64_t total4 = N * C / 4;
+  bn_apply_kernel<<<static_cast<unsigned>(cdiv(total4, 256)), 256, 0, stream>>>(x, total4, C, mean, var, eps, w, b, y);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" size_t qot_bn_bwd_dense_workspace_bytes(int64_t N, int64_t C) {
+  if (N < 0 || C < 0) return 0;
+  return align_up(static_cast<size_t>(cdiv(std::max<int64_t>(N, 1), kBnRows)) * 2 * C * 4) + 256;
+}
+
+extern "C" int qot_bn_bwd_dense(const float* x, const float* mean, const float* var, float eps,
+                                const float* w, const float* dy, int64_t N, int64_t C, int batch_stats,
+                                float* dx, float* d_w, float* d_b, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "qot_bn_bwd_dense: bad shape");
+  QOT_REQUIRE(x && mean && var && w && dy && dx && d_w && d_b, "qot_bn_bwd_dense: null argument");
+  QOT_REQUIRE(ws && ws_bytes >= qot_bn_bwd_dense_workspace_bytes(N, C), "qot_bn_bwd_dense: workspace too small");
+  const int64_t chunks = cdiv(N, kBnRows);
+  QOT_REQUIRE(chunks <= 65535, "qot_bn_bwd_dense: too many rows for one launch");
+  float* part = static_cast<float*>(ws);
+  dim3 g1(static_cast<unsigned>(cdiv(C, 32)), static_cast<unsigned>(chunks));
+  bn_bwd_dense_stage1_kernel<<<g1, 256, 0, stream>>>(x, mean, var, eps, dy, N, C, part);
+  QOT_LAUNCH_CHECK();
+  bn_bwd_param_stage2_kernel<<<static_cast<unsigned>(cdiv(C, 128)), 128, 0, stream>>>(part, chunks, C, d_w, d_b);
+  QOT_LAUNCH_CHECK();
+  bn_bwd_dense_apply_kernel<<<static_cast<unsigned>(cdiv(N * C / 4, 256)), 256, 0, stream>>>(
+      x, mean, var, eps, w, dy, d_w, d_b, N, C, batch_stats, dx);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

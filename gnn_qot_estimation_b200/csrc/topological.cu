@@ -657,6 +657,26 @@ pool_bwd_rows_kernel(const float* __restrict__ dpool, const int64_t* __restrict_
   for (int64_t r = r0 + rl; r < r1; r += RL) dx[r * H + c] = v;
 }
 
+// stand-alone global_mean_pool (PyG layer used on its own, topological_training/models.py:61 when
+// the reference's models.py is kept): partials -> mean; backward broadcasts dpooled / n_g
+__global__ void pool_mean_final_kernel(const float* __restrict__ partial, int S, const int64_t* __restrict__ gptr,
+                                       int64_t B, int H, float* __restrict__ pooled) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= B * H) return;
+  const int64_t g = i / H;
+  const int c = static_cast<int>(i % H);
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += partial[(g * S + s) * H + c];
+  pooled[i] = a / static_cast<float>(max(gptr[g + 1] - gptr[g], static_cast<int64_t>(1)));
+}
+__global__ void pool_scale_kernel(const float* __restrict__ dpooled, const int64_t* __restrict__ gptr, int64_t B,
+                                  int H, float* __restrict__ dscaled) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= B * H) return;
+  const int64_t g = i / H;
+  dscaled[i] = dpooled[i] / static_cast<float>(max(gptr[g + 1] - gptr[g], static_cast<int64_t>(1)));
+}
+
 // ---------------------------------------------------------------------------
 // dispatch on H
 // ---------------------------------------------------------------------------
@@ -873,5 +893,42 @@ extern "C" int qot_pool_mlp_bwd(const float* dout, const float* pooled, const fl
   if ((rc = qot_colsum(dhid, H, B, H, db1, csws, csb, stream_))) return rc;
   if ((rc = qot_wgrad(dout, QOT_OUT, act, H, B, QOT_OUT, H, dW2, H, w2ws, w2b, stream_))) return rc;
   if ((rc = qot_colsum(dout, QOT_OUT, B, QOT_OUT, db2, csws, csb, stream_))) return rc;
+  return QOT_OK;
+}
+
+extern "C" size_t qot_mean_pool_workspace_bytes(int64_t N, int64_t B, int64_t H) {
+  return qot_pool_mlp_fwd_workspace_bytes(N, B, H) + align_up(static_cast<size_t>(std::max<int64_t>(B, 1)) * H * 4);
+}
+
+extern "C" int qot_mean_pool_fwd(const float* x, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
+                                 float* pooled, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(B >= 0 && N >= 0 && h_ok(H), "qot_mean_pool_fwd: H must be 16/32/64/128/256 (got %lld)", (long long)H);
+  if (B == 0) return QOT_OK;
+  QOT_REQUIRE(gptr && pooled && (N == 0 || x), "qot_mean_pool_fwd: null argument");
+  QOT_REQUIRE(ws && ws_bytes >= qot_mean_pool_workspace_bytes(N, B, H), "qot_mean_pool_fwd: workspace too small");
+  QOT_REQUIRE(B <= 0x7fffffffll, "qot_mean_pool_fwd: too many graphs for one launch");
+  const int S = pool_split(N, B);
+  float* partial = static_cast<float*>(ws);
+  pool_partial_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(x, gptr, static_cast<int>(H), S, partial);
+  QOT_LAUNCH_CHECK();
+  pool_mean_final_kernel<<<static_cast<unsigned>(cdiv(B * H, 256)), 256, 0, stream>>>(partial, S, gptr, B, static_cast<int>(H), pooled);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" int qot_mean_pool_bwd(const float* dpooled, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
+                                 float* dx, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(B >= 0 && N >= 0 && h_ok(H), "qot_mean_pool_bwd: H must be 16/32/64/128/256 (got %lld)", (long long)H);
+  if (B == 0 || N == 0) return QOT_OK;
+  QOT_REQUIRE(dpooled && gptr && dx, "qot_mean_pool_bwd: null argument");
+  QOT_REQUIRE(ws && ws_bytes >= qot_mean_pool_workspace_bytes(N, B, H), "qot_mean_pool_bwd: workspace too small");
+  float* dscaled = static_cast<float*>(ws);
+  pool_scale_kernel<<<static_cast<unsigned>(cdiv(B * H, 256)), 256, 0, stream>>>(dpooled, gptr, B, static_cast<int>(H), dscaled);
+  QOT_LAUNCH_CHECK();
+  const int S = pool_split(N, B);
+  pool_bwd_rows_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(dscaled, gptr, static_cast<int>(H), S, dx);
+  QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

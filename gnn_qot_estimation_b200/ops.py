@@ -380,10 +380,77 @@ def lut_bn_head(h, x_feat, batch, is_lut_index, bn: torch.nn.BatchNorm1d, W1, b1
     return out, lut_batch
 
 
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, var, eps, w, b, batch_stats):
+        L = _lib.lib()
+        x = _f32(x)
+        N, C_ = x.shape
+        w_, b_ = _f32(w.detach()), _f32(b.detach())
+        y = torch.empty_like(x)
+        check(L.qot_bn_apply(ptr(x), N, C_, ptr(mean), ptr(var), float(eps), ptr(w_), ptr(b_), ptr(y), stream()),
+              "qot_bn_apply")
+        ctx.save_for_backward(x, mean, var, w_)
+        ctx.eps, ctx.batch_stats = float(eps), bool(batch_stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, mean, var, w = ctx.saved_tensors
+        N, C_ = x.shape
+        dy = _f32(dy)
+        dx = torch.empty_like(x)
+        dw = torch.empty(C_, dtype=torch.float32, device=x.device)
+        db = torch.empty(C_, dtype=torch.float32, device=x.device)
+        ws = _ws(L.qot_bn_bwd_dense_workspace_bytes(N, C_), x.device)
+        check(L.qot_bn_bwd_dense(ptr(x), ptr(mean), ptr(var), ctx.eps, ptr(w), ptr(dy), N, C_, int(ctx.batch_stats),
+                                 ptr(dx), ptr(dw), ptr(db), ptr(ws), ws.numel(), stream()), "qot_bn_bwd_dense")
+        return dx, None, None, None, dw, db, None
+
+
 def batch_norm(x, bn: torch.nn.BatchNorm1d, training: bool):
-    raise NotImplementedError(
-        "stand-alone BatchNorm over all rows is not on the reference hot path: LightpathGNN fuses "
-        "norm1 with the LUT readout (ops.lut_bn_head)")
+    """BatchNorm1d over the node dimension as its own layer (PyG ``BatchNorm.forward``):
+    batch statistics + running-stat update in train(), running statistics in eval()."""
+    _require_cuda(x)
+    if x.shape[0] == 0:
+        return x
+    if training:
+        mean, var = bn_batch_stats(x.detach(), bn.running_mean, bn.running_var,
+                                   bn.momentum if bn.momentum is not None else 0.1)
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+    else:
+        mean, var = bn.running_mean, bn.running_var
+    return _BatchNormFn.apply(x, mean, var, bn.eps, bn.weight, bn.bias, training)
+
+
+class _MeanPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gptr):
+        L = _lib.lib()
+        x = _f32(x)
+        N, H = x.shape
+        B = gptr.numel() - 1
+        pooled = torch.empty(B, H, dtype=torch.float32, device=x.device)
+        ws = _ws(L.qot_mean_pool_workspace_bytes(N, B, H), x.device)
+        check(L.qot_mean_pool_fwd(ptr(x), ptr(gptr), N, B, H, ptr(pooled), ptr(ws), ws.numel(), stream()),
+              "qot_mean_pool_fwd")
+        ctx.save_for_backward(gptr)
+        ctx.N = N
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        L = _lib.lib()
+        (gptr,) = ctx.saved_tensors
+        dpooled = _f32(dpooled)
+        B, H = dpooled.shape
+        dx = torch.empty(ctx.N, H, dtype=torch.float32, device=dpooled.device)
+        ws = _ws(L.qot_mean_pool_workspace_bytes(ctx.N, B, H), dpooled.device)
+        check(L.qot_mean_pool_bwd(ptr(dpooled), ptr(gptr), ctx.N, B, H, ptr(dx), ptr(ws), ws.numel(), stream()),
+              "qot_mean_pool_bwd")
+        return dx, None
 
 
 # --------------------------------------------------------------------------- #
@@ -677,5 +744,6 @@ def pool_mlp(x, gptr, W1, b1, W2, b2, training: bool = False, dropout_p: float =
 
 
 def mean_pool(x, gptr):
-    """global_mean_pool alone: segment mean via the pooling kernel's first phase."""
-    raise NotImplementedError("stand-alone global_mean_pool is fused with the MLP head (ops.pool_mlp)")
+    """global_mean_pool as its own layer (the fused form is ops.pool_mlp)."""
+    _require_cuda(x, gptr)
+    return _MeanPoolFn.apply(x, gptr)

@@ -231,6 +231,15 @@ int qot_pool_mlp_bwd(const float* dout, const float* pooled, const float* hid,
                      float* dW1, float* db1, float* dW2, float* db2,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* global_mean_pool on its own (PyG layer, topological_training/models.py:61 when the reference's
+ * models.py is kept and only its layer imports are swapped): pooled [B,H]; backward
+ * dx[n,:] = dpooled[graph(n),:] / n_graph.  ws: qot_mean_pool_workspace_bytes. */
+size_t qot_mean_pool_workspace_bytes(int64_t N, int64_t B, int64_t H);
+int qot_mean_pool_fwd(const float* x, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
+                      float* pooled, void* ws, size_t ws_bytes, void* stream);
+int qot_mean_pool_bwd(const float* dpooled, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
+                      float* dx, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* LightpathGNN (lightpath_training/models.py:7-45)                           */
 /* ------------------------------------------------------------------------ */
@@ -333,6 +342,18 @@ size_t qot_bn_stats_workspace_bytes(int64_t N, int64_t C);
 int qot_bn_stats(const float* h, int64_t N, int64_t C, float* mean, float* var,
                  float* running_mean, float* running_var, float momentum,
                  void* ws, size_t ws_bytes, void* stream);
+
+/* BatchNorm as a stand-alone layer over all rows (PyG BatchNorm, lightpath_training/models.py:31):
+ * y = (x - mean) / sqrt(var + eps) * w + b with the given statistics (qot_bn_stats in train(),
+ * running stats in eval()), and its dense backward: batch_stats=1 ->
+ * dx = w*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)); batch_stats=0 -> dx = w*invstd*dy;
+ * d_w = sum(dy*xhat), d_b = sum(dy) (fixed-order two-stage sums).  C % 4 == 0. */
+int qot_bn_apply(const float* x, int64_t N, int64_t C, const float* mean, const float* var,
+                 float eps, const float* w, const float* b, float* y, void* stream);
+size_t qot_bn_bwd_dense_workspace_bytes(int64_t N, int64_t C);
+int qot_bn_bwd_dense(const float* x, const float* mean, const float* var, float eps, const float* w,
+                     const float* dy, int64_t N, int64_t C, int batch_stats, float* dx, float* d_w,
+                     float* d_b, void* ws, size_t ws_bytes, void* stream);
 
 /* Ordered LUT compaction: lut_node [L] int32 ascending, lut_batch [L] int64
  * (optional), n_lut[0] = L  (lightpath_training/models.py:35-40). */

@@ -1,0 +1,113 @@
+"""GPU parity of the PyG-named layers in gnn_qot_estimation_b200.nn used ONE BY ONE -- the path a
+reference maintainer takes when keeping the reference's models.py and swapping only its layer imports
+(topological_training/models.py:3, lightpath_training/models.py:3): each layer is
+its own autograd op, the glue (leaky_relu / relu / dropout / boolean LUT mask / torch MLP) stays torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import grad_errs, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def test_topological_composed_from_layers(cuda):
+    from gnn_qot_estimation_b200 import nn as qnn, synthetic
+    from oracle import TopologicalGNNOracle
+    sd = load_golden("ckpt_topological_model_0.pt")["model_state_dict"]
+    o = TopologicalGNNOracle(75, 16, 3, 4, dropout_p=0.0).double()
+    o.load_state_dict(sd, strict=True)
+    emb = torch.nn.Embedding(75, 16)
+    conv1 = qnn.TransformerConv(16, 16, edge_dim=4)
+    edge_nn = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 256))
+    conv2 = qnn.NNConv(16, 16, nn=edge_nn, aggr="mean")
+    mlp = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.LeakyReLU(), torch.nn.Dropout(0.0), torch.nn.Linear(16, 3))
+    mods = {"node_embeddings": emb, "conv1": conv1, "conv2": conv2, "mlp": mlp}
+    for name, m in mods.items():
+        m.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=True)
+        m.to(cuda)
+    hb = synthetic.nsfnet_store(40, seed=2).host_batch(0, 40)
+    b = hb.to(cuda)
+    x = emb(b.node_ids)
+    x = F.leaky_relu(conv1(x, b.edge_index, b.edge_attr))
+    x = F.leaky_relu(conv2(x, b.edge_index, b.edge_attr))
+    out = mlp(qnn.global_mean_pool(x, b.batch))
+    loss = F.smooth_l1_loss(out, b.y.view(-1, 3))
+    loss.backward()
+    hb.edge_attr = hb.edge_attr.double()
+    eo = o(hb)
+    el = F.smooth_l1_loss(eo, hb.y.double().view(-1, 3))
+    el.backward()
+    assert rel_err(out, eo) <= RTOL and rel_err(loss, el) <= RTOL
+    got = {f"{n}.{k}": p.grad for n, m in mods.items() for k, p in m.named_parameters()}
+    ref = {k: p.grad for k, p in o.named_parameters()}
+    for k, e in grad_errs(got, ref, exact_zero=("conv1.lin_key.bias",)).items():
+        assert e <= RTOL, (k, e)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_lightpath_composed_from_layers(cuda, train):
+    from gnn_qot_estimation_b200 import nn as qnn, synthetic
+    from oracle import LightpathGNNOracle
+    from test_lightpath_train_gpu import _kink_free_batch
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    o = LightpathGNNOracle(5, 32, 3, 1, dropout_p=0.0).double()
+    o.load_state_dict(sd, strict=True)
+    conv1 = qnn.GATConv(5, 32, heads=4, concat=True)
+    norm1 = qnn.BatchNorm(128)
+    mlp = torch.nn.Sequential(torch.nn.Linear(128, 32), torch.nn.LeakyReLU(), torch.nn.Dropout(0.0), torch.nn.Linear(32, 3))
+    mods = {"conv1": conv1, "norm1": norm1, "mlp": mlp}
+    for name, m in mods.items():
+        m.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=True)
+        m.to(cuda).train(train)
+    o.train(train)
+    hb = _kink_free_batch(o, 60, 1, seed=17)
+    b = hb.to(cuda)
+    h = F.relu(norm1(conv1(b.x, b.edge_index)))
+    mask = b.x[:, 1] == 1.0
+    out = mlp(h[mask])
+    lut_batch = b.batch[mask]
+    loss = F.smooth_l1_loss(out, b.y[lut_batch])
+    loss.backward()
+    hb.x = hb.x.double()
+    eo, elb = o(hb)
+    el = F.smooth_l1_loss(eo, hb.y.double()[elb])
+    el.backward()
+    assert torch.equal(lut_batch.cpu(), elb)
+    assert rel_err(out, eo) <= RTOL and rel_err(loss, el) <= RTOL
+    got = {f"{n}.{k}": p.grad for n, m in mods.items() for k, p in m.named_parameters()}
+    ref = {k: p.grad for k, p in o.named_parameters()}
+    zero = ("conv1.bias",) if train else ()
+    for k, e in grad_errs(got, ref, exact_zero=zero).items():
+        assert e <= RTOL, (k, e)
+    if train:
+        assert rel_err(norm1.module.running_mean, o.norm1.module.running_mean) <= RTOL
+        assert rel_err(norm1.module.running_var, o.norm1.module.running_var) <= RTOL
+
+
+def test_mean_pool_and_batchnorm_standalone(cuda):
+    from gnn_qot_estimation_b200 import nn as qnn
+    g = torch.Generator().manual_seed(0)
+    sizes = torch.tensor([5, 1, 300, 44])
+    x = torch.randn(int(sizes.sum()), 32, generator=g)
+    batch = torch.repeat_interleave(torch.arange(4), sizes)
+    xd = x.to(cuda).requires_grad_(True)
+    p = qnn.global_mean_pool(xd, batch.to(cuda))
+    p.square().sum().backward()
+    x64 = x.double().requires_grad_(True)
+    ref = torch.stack([x64[batch == i].mean(0) for i in range(4)])
+    ref.square().sum().backward()
+    assert rel_err(p, ref) <= RTOL and rel_err(xd.grad, x64.grad) <= RTOL
+    bn = qnn.BatchNorm(32).to(cuda).train()
+    bn64 = torch.nn.BatchNorm1d(32).double().train()
+    xd2 = x.to(cuda).requires_grad_(True)
+    y = bn(xd2)
+    (y * torch.arange(32, device=cuda)).sum().backward()
+    x642 = x.double().requires_grad_(True)
+    y64 = bn64(x642)
+    (y64 * torch.arange(32, dtype=torch.float64)).sum().backward()
+    assert rel_err(y, y64) <= RTOL
+    scale = float(x642.grad.abs().max())
+    assert float((xd2.grad.double().cpu() - x642.grad).abs().max()) <= RTOL * max(scale, 1.0)
+    assert rel_err(bn.module.running_var, bn64.running_var) <= RTOL
