@@ -111,3 +111,46 @@ def test_mean_pool_and_batchnorm_standalone(cuda):
     scale = float(x642.grad.abs().max())
     assert float((xd2.grad.double().cpu() - x642.grad).abs().max()) <= RTOL * max(scale, 1.0)
     assert rel_err(bn.module.running_var, bn64.running_var) <= RTOL
+
+
+def test_stand_in_batches_feed_the_b200_modules(cuda):
+    """torch_geometric stand-in: networkx graphs -> from_networkx -> DataLoader -> Batch.to(cuda) ->
+    the drop-in modules; same answers as the oracle on the same batch."""
+    import networkx as nx
+    from gnn_qot_estimation_b200 import LightpathGNN, TopologicalGNN
+    from gnn_qot_estimation_b200.pyg_compat import DataLoader, from_networkx
+    from oracle import LightpathGNNOracle, TopologicalGNNOracle
+    g = torch.Generator().manual_seed(0)
+    items_t, items_l = [], []
+    for s in range(6):
+        G = nx.gnm_random_graph(12 + s, 30, seed=s)
+        d = from_networkx(G)
+        d.node_ids = torch.arange(d.num_nodes)
+        d.edge_attr = torch.rand(d.edge_index.shape[1], 4, generator=g)
+        d.x = None
+        d.y = torch.rand(3, generator=g)
+        items_t.append(d)
+        e = from_networkx(G)
+        x = torch.rand(e.num_nodes, 5, generator=g)
+        x[:, 1] = 0.0
+        x[s % e.num_nodes, 1] = 1.0
+        e.x = x
+        e.y = torch.rand(1, 3, generator=g)
+        items_l.append(e)
+    sd = load_golden("ckpt_topological_model_0.pt")["model_state_dict"]
+    bt = next(iter(DataLoader(items_t, batch_size=6)))
+    m = TopologicalGNN(75, 16, 3, edge_dim=4, dropout_p=0.0); m.load_state_dict(sd); m.to(cuda).eval()
+    o = TopologicalGNNOracle(75, 16, 3, 4, dropout_p=0.0).double(); o.load_state_dict(sd); o.eval()
+    with torch.no_grad():
+        out = m(bt.to(cuda))
+        bt.edge_attr = bt.edge_attr.double()
+        assert rel_err(out, o(bt)) <= RTOL
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    bl = next(iter(DataLoader(items_l, batch_size=6)))
+    m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0); m.load_state_dict(sd); m.to(cuda).eval()
+    o = LightpathGNNOracle(5, 32, 3, 1, dropout_p=0.0).double(); o.load_state_dict(sd); o.eval()
+    with torch.no_grad():
+        out, lb = m(bl.to(cuda))
+        bl.x = bl.x.double()
+        eo, el = o(bl)
+    assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
