@@ -91,6 +91,8 @@ SIGNATURES = {
     "qot_mean_pool_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_mean_pool_fwd": (C.c_int, [P, P, i64, i64, i64, P, P, sz, vp]),
     "qot_mean_pool_bwd": (C.c_int, [P, P, i64, i64, i64, P, P, sz, vp]),
+    "qot_smooth_l1_workspace_bytes": (sz, [i64]),
+    "qot_smooth_l1": (C.c_int, [P, P, P, i64, C.c_float, P, P, P, P, sz, vp]),
     "qot_lut_select_workspace_bytes": (sz, [i64]),
     "qot_lut_select": (C.c_int, [P, i64, i64, i32, P, P, P, P, P, sz, vp]),
     "qot_lut_head_fwd": (C.c_int, [P, P, i64, P, P, C.c_float, P, P, P, P, P, P, P, P, P, P, vp]),

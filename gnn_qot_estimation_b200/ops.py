@@ -747,3 +747,59 @@ def mean_pool(x, gptr):
     """global_mean_pool as its own layer (the fused form is ops.pool_mlp)."""
     _require_cuda(x, gptr)
     return _MeanPoolFn.apply(x, gptr)
+
+
+# --------------------------------------------------------------------------- #
+# fused SmoothL1 loss + running regression metrics
+# --------------------------------------------------------------------------- #
+class RegressionMetrics:
+    """Device-side accumulator of the sums behind the reference's per-epoch numbers
+    (topological_training/train.py:117-129): average loss and sklearn ``r2_score`` (uniform average
+    over the three outputs).  Nothing is read on the host until :meth:`result`."""
+
+    def __init__(self, device):
+        self.sums = torch.zeros(3, 5, dtype=torch.float64, device=device)
+
+    def reset(self) -> None:
+        self.sums.zero_()
+
+    def result(self) -> dict:
+        s = self.sums.cpu()
+        n, sy, syy, ssr, sl = (s[:, i] for i in range(5))
+        ss_tot = syy - sy * sy / n.clamp(min=1)
+        r2 = 1.0 - ssr / ss_tot
+        return {"count": int(n[0]), "loss": float(sl.sum() / (n[0] * 3).clamp(min=1)),
+                "mse": (ssr / n.clamp(min=1)).tolist(), "r2": r2.tolist(), "r2_uniform_average": float(r2.mean())}
+
+
+class _SmoothL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, target_rows, beta, metrics):
+        L = _lib.lib()
+        pred, target = _f32(pred), _f32(target)
+        n, dev = pred.shape[0], pred.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        dpred = torch.empty_like(pred)
+        ws = _ws(L.qot_smooth_l1_workspace_bytes(n), dev)
+        check(L.qot_smooth_l1(ptr(pred), ptr(target), ptr(target_rows), n, float(beta), ptr(loss), ptr(dpred),
+                              ptr(metrics), ptr(ws), ws.numel(), stream()), "qot_smooth_l1")
+        ctx.save_for_backward(dpred)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None, None, None, None
+
+
+def smooth_l1_loss(pred, target, target_rows=None, beta: float = 1.0, metrics: Optional[RegressionMetrics] = None):
+    """``torch.nn.SmoothL1Loss()(pred, target[target_rows])`` with the gradient computed in the same
+    kernel and, optionally, the epoch metrics accumulated on the device."""
+    _require_cuda(pred, target)
+    if pred.dim() != 2 or pred.shape[1] != 3:
+        raise RuntimeError("libqot_b200 smooth_l1_loss: predictions must be [n, 3] (osnr, snr, ber)")
+    target = target.reshape(-1, 3)
+    rows = _i64(target_rows) if target_rows is not None else None
+    if rows is None and target.shape[0] != pred.shape[0]:
+        raise RuntimeError("smooth_l1_loss: target rows do not match the predictions")
+    return _SmoothL1Fn.apply(pred, target, rows, beta, metrics.sums if metrics is not None else None)

@@ -240,6 +240,17 @@ int qot_mean_pool_fwd(const float* x, const int64_t* gptr, int64_t N, int64_t B,
 int qot_mean_pool_bwd(const float* dpooled, const int64_t* gptr, int64_t N, int64_t B, int64_t H,
                       float* dx, void* ws, size_t ws_bytes, void* stream);
 
+/* Fused SmoothL1Loss (mean reduction, beta) forward + gradient + running regression metrics:
+ * replaces criterion(out, y) / loss.backward() entry / loss.item() / the per-batch .cpu() copies
+ * for R^2 of topological_training/train.py:114-129 and lightpath_training/train.py:122-136.
+ * pred [n,3]; target rows taken at target_rows[r] (NULL = r; y[lut_batch] without a gather).
+ * loss [1] (optional), dpred [n,3] = d loss / d pred (optional), metrics [3,5] fp64 (optional):
+ * per output column [count, sum y, sum y^2, sum (y-pred)^2, sum loss elements], ACCUMULATED. */
+size_t qot_smooth_l1_workspace_bytes(int64_t n);
+int qot_smooth_l1(const float* pred, const float* target, const int64_t* target_rows, int64_t n,
+                  float beta, float* loss, float* dpred, double* metrics, void* ws, size_t ws_bytes,
+                  void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* LightpathGNN (lightpath_training/models.py:7-45)                           */
 /* ------------------------------------------------------------------------ */

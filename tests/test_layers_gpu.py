@@ -154,3 +154,34 @@ def test_stand_in_batches_feed_the_b200_modules(cuda):
         bl.x = bl.x.double()
         eo, el = o(bl)
     assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
+
+
+def test_fused_smooth_l1_and_metrics(cuda):
+    """qot_smooth_l1 == torch SmoothL1Loss (value and gradient), incl. the y[lut_batch] row gather, and
+    the device-side accumulator reproduces sklearn's r2_score over several batches."""
+    from sklearn.metrics import r2_score
+    from gnn_qot_estimation_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    acc = ops.RegressionMetrics(cuda)
+    ys, ps = [], []
+    for n in (1, 300, 1025):
+        pred = (torch.randn(n, 3, generator=g) * 1.5).to(cuda).requires_grad_(True)
+        y = torch.randn(n + 7, 3, generator=g).to(cuda)
+        rows = torch.randint(0, n + 7, (n,), generator=g).to(cuda)
+        loss = ops.smooth_l1_loss(pred, y, rows, metrics=acc)
+        (loss * 2.0).backward()
+        p64 = pred.detach().double().cpu().requires_grad_(True)
+        ref = torch.nn.SmoothL1Loss()(p64, y.double().cpu()[rows.cpu()])
+        (ref * 2.0).backward()
+        assert rel_err(loss, ref) <= RTOL and rel_err(pred.grad, p64.grad) <= RTOL
+        ys.append(y.cpu()[rows.cpu()]); ps.append(pred.detach().cpu())
+    res = acc.result()
+    Y, P = torch.cat(ys).numpy(), torch.cat(ps).numpy()
+    assert res["count"] == Y.shape[0]
+    r2 = r2_score(Y.astype("float64"), P.astype("float64"), multioutput="uniform_average")   # fp64 like the accumulator
+    assert abs(res["r2_uniform_average"] - r2) <= 1e-9 * max(1.0, abs(r2))
+    # plain form (no row gather) inside a model step
+    pred = torch.randn(64, 3, device=cuda, requires_grad=True)
+    y = torch.randn(64, 3, device=cuda)
+    l1 = ops.smooth_l1_loss(pred, y.view(-1))                 # train.py:112 views y as [-1, 3]
+    assert rel_err(l1, torch.nn.SmoothL1Loss()(pred.detach(), y)) <= RTOL
