@@ -78,6 +78,8 @@ SIGNATURES = {
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, vp]),
+    "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
+    "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,
                                            C.POINTER(i64), C.POINTER(i64), vp]),
     "qot_gat_fwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, vp]),
@@ -117,6 +119,8 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if _os.environ.get("QOT_LP_VARIANT"):
+        handle.qot_lightpath_set_variant(int(_os.environ["QOT_LP_VARIANT"]))
     _lib = handle
     return handle
 

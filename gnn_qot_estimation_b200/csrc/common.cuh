@@ -75,35 +75,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
-  return v;
-}
-// Sum over aligned groups of G lanes (G power of two <= 32); every lane gets the result.
-template <int G>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-// streaming 128-bit loads that do not pollute L1 (read-once operands)
-__device__ __forceinline__ int4 ldg_stream_v4(const void* p) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ longlong2 ldg_stream_l2(const void* p) {
-  longlong2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];"
-               : "=l"(r.x), "=l"(r.y)
-               : "l"(p));
-  return r;
-}
 #endif
 
 }  // namespace qot

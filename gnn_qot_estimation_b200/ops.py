@@ -8,7 +8,7 @@ torch only allocates the tensors.
 from __future__ import annotations
 
 import ctypes as C
-from typing import NamedTuple, Optional, Tuple
+from typing import NamedTuple, Optional
 
 import torch
 

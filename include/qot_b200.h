@@ -299,6 +299,12 @@ int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
                         int32_t* status, void* stream);
 
+/* Kernel variant behind qot_lightpath_infer[_host]: 0 = one warp per graph, 1 = 8 lanes per graph in
+ * the scan / attention phase + block-wide two-row heads.  Same results to fp32 round-off
+ * (the summation trees differ); process-wide, set before launching. */
+int qot_lightpath_set_variant(int variant);
+int qot_lightpath_get_variant(void);
+
 /* The same call for a batch in PINNED HOST memory (reference layout), into a caller-owned device
  * staging slot.  Enqueues on `stream`: H2D of x, of the DESTINATION row of edge_index and of the
  * three offset arrays; the kernel -- the source row is not copied: the few entries the readout
