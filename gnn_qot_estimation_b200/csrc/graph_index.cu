@@ -246,10 +246,13 @@ __global__ void graph_ptr_kernel(const int64_t* __restrict__ batch, const int64_
   auto id_at = [&](int64_t i) -> int64_t {
     if (!via) return batch[i];
     const int64_t node = via[i];
-    if (static_cast<uint64_t>(node) >= static_cast<uint64_t>(n_nodes)) {
-      if (status) *status = 1;
+    const int64_t peer = via[n_items + i];          // destination row of edge_index [2, E]
+    if (static_cast<uint64_t>(node) >= static_cast<uint64_t>(n_nodes) ||
+        static_cast<uint64_t>(peer) >= static_cast<uint64_t>(n_nodes)) {
+      if (status) *status = 1;                      // an endpoint outside [0, N): not a valid batch
       return 0;
     }
+    if (batch[peer] != batch[node] && status) *status = 1;   // an edge must stay inside one graph
     return batch[node];
   };
   const int64_t prev = (n == 0) ? -1 : id_at(n - 1);

@@ -586,36 +586,36 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  // ---- destination row: lane sl holds edges sl + 8j, j = 0..31, one graph-local byte each
+  // ---- destination row: lane sl holds edges sl + 8j, j = 0..31, one graph-local byte each.  Only the
+  // low words are fetched (ids are < N < 2^31 for every batch a collate or qot_edge_ptr vouches for;
+  // the value is only ever compared, never used as an address), 16 loads in flight per lane.
   unsigned pk[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) pk[q] = 0xffffffffu;
   {
-    const int64_t* __restrict__ dg = edst + e0;
+    const unsigned* __restrict__ dg = reinterpret_cast<const unsigned*>(edst + e0);
     const unsigned n0u = static_cast<unsigned>(n0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (__any_sync(kFull, 32 * q < ne)) {
-        long long d[4];
+    for (int half = 0; half < 2; ++half) {
+      if (__any_sync(kFull, 128 * half < ne)) {
+        unsigned d[16];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int e = sl + 8 * (4 * q + t);
-          d[t] = e < ne ? dg[e] : -1ll;
+        for (int t = 0; t < 16; ++t) {
+          const int e = sl + 8 * (16 * half + t);
+          d[t] = e < ne ? __ldg(dg + 2 * e) : 0xffffffffu;
         }
-        unsigned wv = 0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const unsigned lo = static_cast<unsigned>(d[t]);
-          const unsigned hi = static_cast<unsigned>(static_cast<unsigned long long>(d[t]) >> 32);
-          const unsigned loc = lo - n0u;
-          wv |= ((hi == 0u && loc < static_cast<unsigned>(n)) ? loc : 0xffu) << (8 * t);
+        for (int t = 0; t < 16; ++t) {
+          const unsigned loc = d[t] - n0u;
+          const unsigned byte = (e0 >= 0 && loc < static_cast<unsigned>(n) && sl + 8 * (16 * half + t) < ne) ? loc : 0xffu;
+          const int q = 4 * half + (t >> 2);
+          pk[q] = (pk[q] & ~(0xffu << (8 * (t & 3)))) | (byte << (8 * (t & 3)));
         }
-        pk[q] = wv;
       }
     }
   }
   cp_async_wait_all();
-  __syncthreads();                                   // weights (all threads) and slabs are in place
+  __syncwarp();                                      // this sub-group's slab is in place
 
   // ---- LUT node(s) of the graph
   int cnt = 0, il = -1;
@@ -694,8 +694,8 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
       const float xi = sx[ils * kF + k];
 #pragma unroll
       for (int h = 0; h < kHeads; ++h) {
-        As[k][h] = sm.w[kOffAsrc + k * kHeads + h];
-        d[h] = fmaf(xi, sm.w[kOffAdst + k * kHeads + h], d[h]);
+        As[k][h] = __ldg(prep + kOffAsrc + k * kHeads + h);
+        d[h] = fmaf(xi, __ldg(prep + kOffAdst + k * kHeads + h), d[h]);
       }
     }
     float mx[kHeads], ssum[kHeads], acc[kHeads][kF];
@@ -871,7 +871,7 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
 }
 
 // 0: one warp per graph (lp_infer_kernel); 1: 8 lanes per graph (lp_infer_sub_kernel)
-static int g_lp_variant = 0;
+static int g_lp_variant = 1;
 extern "C" int qot_lightpath_set_variant(int v) {
   if (v != 0 && v != 1) return QOT_E_BADARG;
   g_lp_variant = v;

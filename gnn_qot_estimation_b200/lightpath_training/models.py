@@ -21,8 +21,8 @@ from ..nn import BatchNorm, GATConv
 
 class LightpathGNN(torch.nn.Module):
     # kernels launched by one eval forward_device() call (bench.py counts launches with these)
-    launches_per_step = 1                  # lp_infer_kernel
-    dominant_kernel = "lp_infer_kernel"
+    launches_per_step = 1                  # one fused kernel per batch
+    dominant_kernel = "lp_infer_sub_kernel"   # qot_lightpath_set_variant(0) selects lp_infer_kernel instead
 
     def __init__(self, in_channels, hidden_channels, output_dim, is_lut_index, dropout_p=0.5):
         super().__init__()

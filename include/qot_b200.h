@@ -102,7 +102,9 @@ int qot_graph_ptr(const int64_t* batch, int64_t N, int64_t B, int64_t* gptr, voi
 
 /* eptr [B+1] int64: first edge whose source node lies in a graph >= g.  Valid when
  * the edges of edge_index [2,E] are grouped by graph in ascending order (every
- * collate emits them so); status[0] (int32) is set non-zero otherwise. */
+ * collate emits them so); status[0] (int32) is set non-zero otherwise, and also when an
+ * endpoint lies outside [0,N) or an edge joins two different graphs -- the fused
+ * inference kernel relies on this check for batches that do not come from a collate. */
 int qot_edge_ptr(const int64_t* edge_index, int64_t E, const int64_t* batch, int64_t N,
                  int64_t B, int64_t* eptr, int32_t* status, void* stream);
 

@@ -244,3 +244,30 @@ def test_lut_ptr_kernel_matches_host(cuda):
     hb = synthetic.lightpath_store(3000, seed=8, device="cpu", lut_per_graph=3).host_batch(0, 3000)
     got = ops.lightpath_lut_ptr(hb.x.to(cuda), hb.ptr.to(cuda), 1)
     assert torch.equal(got.cpu(), hb.lut_ptr)
+
+
+def test_kernel_variants_agree(cuda):
+    """Both kernels behind qot_lightpath_infer (one warp per graph / 8 lanes per graph) give the same
+    rows (same order, same indices) and values within round-off of each other and of the oracle."""
+    from gnn_qot_estimation_b200 import _lib, synthetic
+    sd = load_golden("ckpt_lightpath_model_0.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    hb = synthetic.lightpath_store(1500, seed=23, device="cpu", lut_per_graph=2).host_batch(0, 1500)
+    b = hb.to(cuda)
+    L = _lib.lib()
+    prev = L.qot_lightpath_get_variant()
+    try:
+        res = {}
+        for v in (0, 1):
+            assert L.qot_lightpath_set_variant(v) == 0 and L.qot_lightpath_get_variant() == v
+            with torch.no_grad():
+                o, l = m(b)
+            res[v] = (o.clone(), l.clone())
+        assert L.qot_lightpath_set_variant(7) != 0
+    finally:
+        L.qot_lightpath_set_variant(prev)
+    assert torch.equal(res[0][1], res[1][1])
+    assert rel_err(res[0][0], res[1][0]) <= RTOL
+    with torch.no_grad():
+        eo, el = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(res[1][1].cpu(), el) and rel_err(res[1][0], eo) <= RTOL and rel_err(res[0][0], eo) <= RTOL
