@@ -454,6 +454,9 @@ lp_infer_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
 // exactly one LUT node, more than 15 in-edges on it, a source outside the slab) are handed to
 // the generic per-warp path at the end of the same launch.
 // =====================================================================================
+#ifndef QOT_LP_SUB_OCC
+#define QOT_LP_SUB_OCC 4
+#endif
 constexpr int kGPB = 32;                  // graphs per block
 constexpr int kSubMsg = 16;               // sources of the LUT row + its self loop
 
@@ -461,9 +464,10 @@ struct SubMeta {
   int64_t n0, n1, e0, e1, l0, l1;
   int il, state;                          // state: 0 nothing to do, 1 fast row ready (z staged), 2 generic path
 };
+constexpr int kSlabNodes = 1216;          // nodes of one block's 32 graphs staged together (mean 1024 at
+                                          // n ~ U{8..56}; graphs that do not fit take the generic path)
 struct SubSmem {
-  float w[kPreparedFloats];               // the whole prepared block, 20.1 KB
-  float x[kGPB][kXF];                     // node slabs, 40 KB
+  float x[kSlabNodes * kF];               // the block's node slabs, packed as in global memory, 23.8 KB
   float z[kGPB][kHeads * kF];             // attention outputs, z[h*5+f]
   float y[8][2][kHC];                     // per warp: two activation rows (generic path scratch too)
   int msg[kGPB][kSubMsg];
@@ -548,7 +552,7 @@ __device__ __forceinline__ void lut_head2(const float* __restrict__ w, const flo
   ob = (lane == 0 ? pb[0] : lane == 1 ? pb[1] : pb[2]) + b2;
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, QOT_LP_SUB_OCC)
 lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
                     const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
                     const int64_t* __restrict__ eptr, const int64_t* __restrict__ lptr, int64_t N,
@@ -563,22 +567,21 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
   const int64_t g = static_cast<int64_t>(blockIdx.x) * kGPB + gl;
   const bool active = g < B;
 
-  // ---- weights -> shared memory, asynchronously
-  for (int i = tid * 4; i < kPreparedFloats; i += 256 * 4) cp_async16(sm.w + i, prep + i);
-
-  // ---- extents of the sub-group's graph
+  // ---- extents of the sub-group's graph (+ the block's first node: slabs are packed from there)
+  const int64_t nb0 = gptr[min(static_cast<int64_t>(blockIdx.x) * kGPB, B)];
   long long pv = 0;
   if (active && sl < 6) pv = (sl < 2) ? gptr[g + sl] : (sl < 4) ? eptr[g + sl - 2] : lptr[g + sl - 4];
   const int64_t n0 = __shfl_sync(kFull, pv, base + 0), n1 = __shfl_sync(kFull, pv, base + 1);
   const int64_t e0 = __shfl_sync(kFull, pv, base + 2), e1 = __shfl_sync(kFull, pv, base + 3);
   const int64_t l0 = __shfl_sync(kFull, pv, base + 4), l1 = __shfl_sync(kFull, pv, base + 5);
-  const bool fits = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= 32 * kEC;
+  const bool fits = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= 32 * kEC &&
+                    n0 >= nb0 && (n1 - nb0) <= kSlabNodes;
   const int n = fits ? static_cast<int>(n1 - n0) : 0;
   const int ne = fits ? static_cast<int>(e1 - e0) : 0;
   if (g == B - 1 && sl == 0) n_lut[0] = static_cast<int32_t>(l1);
 
   // ---- node slab -> shared memory (4-byte cp.async: slabs are only 4-byte aligned)
-  float* sx = sm.x[gl];
+  float* sx = sm.x + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
   {
     const float* __restrict__ xg = x + n0 * kF;
     const int nf = n * kF;
@@ -757,8 +760,8 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
   }
   __syncthreads();
 
-  // ---- readout heads, two rows per warp at a time
-  const float* wh = sm.w + kOffWf;
+  // ---- readout heads, two rows per warp at a time; the 19.5 KB of weights are read through L1
+  const float* __restrict__ wh = prep + kOffWf;
 #pragma unroll 1
   for (int p = 0; p < 2; ++p) {
     const int ga = warp + 16 * p, gb = ga + 8;
