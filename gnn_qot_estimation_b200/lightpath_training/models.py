@@ -22,7 +22,13 @@ from ..nn import BatchNorm, GATConv
 class LightpathGNN(torch.nn.Module):
     # kernels launched by one eval forward_device() call (bench.py counts launches with these)
     launches_per_step = 1                  # one fused kernel per batch
-    dominant_kernel = "lp_infer_sub_kernel"   # qot_lightpath_set_variant(0) selects lp_infer_kernel instead
+    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_infer_bulk_kernel")
+
+    @property
+    def dominant_kernel(self):
+        """Name of the kernel behind qot_lightpath_infer for the active qot_lightpath_set_variant()."""
+        from .. import _lib
+        return self._variant_kernels[_lib.lib().qot_lightpath_get_variant()]
 
     def __init__(self, in_channels, hidden_channels, output_dim, is_lut_index, dropout_p=0.5):
         super().__init__()

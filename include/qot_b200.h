@@ -302,8 +302,10 @@ int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         int32_t* status, void* stream);
 
 /* Kernel variant behind qot_lightpath_infer[_host]: 0 = one warp per graph, 1 = 8 lanes per graph in
- * the scan / attention phase + block-wide two-row heads.  Same results to fp32 round-off
- * (the summation trees differ); process-wide, set before launching. */
+ * the scan / attention phase + block-wide two-row heads, 2 (default) = 8 lanes per graph with the
+ * block's node / destination slabs moved by bulk async copies and the readout head on the tensor
+ * cores (error-compensated TF32).  Same rows, values equal to fp32 round-off (the summation trees
+ * differ); process-wide, set before launching. */
 int qot_lightpath_set_variant(int variant);
 int qot_lightpath_get_variant(void);
 

@@ -247,8 +247,9 @@ def test_lut_ptr_kernel_matches_host(cuda):
 
 
 def test_kernel_variants_agree(cuda):
-    """Both kernels behind qot_lightpath_infer (one warp per graph / 8 lanes per graph) give the same
-    rows (same order, same indices) and values within round-off of each other and of the oracle."""
+    """The three kernels behind qot_lightpath_infer (one warp per graph / 8 lanes per graph / 8 lanes per
+    graph with bulk-copied slabs and the tensor-core head) give the same rows (same order, same indices)
+    and values within round-off of each other and of the oracle."""
     from gnn_qot_estimation_b200 import _lib, synthetic
     sd = load_golden("ckpt_lightpath_model_0.pt")["model_state_dict"]
     m = _model(cuda, sd)
@@ -258,7 +259,7 @@ def test_kernel_variants_agree(cuda):
     prev = L.qot_lightpath_get_variant()
     try:
         res = {}
-        for v in (0, 1):
+        for v in (0, 1, 2):
             assert L.qot_lightpath_set_variant(v) == 0 and L.qot_lightpath_get_variant() == v
             with torch.no_grad():
                 o, l = m(b)
@@ -266,8 +267,34 @@ def test_kernel_variants_agree(cuda):
         assert L.qot_lightpath_set_variant(7) != 0
     finally:
         L.qot_lightpath_set_variant(prev)
-    assert torch.equal(res[0][1], res[1][1])
-    assert rel_err(res[0][0], res[1][0]) <= RTOL
     with torch.no_grad():
         eo, el = _oracle(sd, torch.float64)(_to64(hb))
-    assert torch.equal(res[1][1].cpu(), el) and rel_err(res[1][0], eo) <= RTOL and rel_err(res[0][0], eo) <= RTOL
+    for v in (0, 1, 2):
+        assert torch.equal(res[v][1], res[2][1])
+        assert rel_err(res[v][0], res[2][0]) <= RTOL
+        assert torch.equal(res[v][1].cpu(), el) and rel_err(res[v][0], eo) <= RTOL
+
+
+@pytest.mark.parametrize("shift_floats,num_graphs", [(1, 70), (2, 33), (3, 257)])
+def test_unaligned_buffers(cuda, shift_floats, num_graphs):
+    """x / edge_index views that start 4, 8 or 12 bytes off a 16-byte boundary and end flush with their
+    allocation: the bulk-copy windows are aligned in absolute addresses and must neither miss nor
+    over-read a byte (lp_infer_bulk_kernel), same rows as the oracle."""
+    from gnn_qot_estimation_b200 import Batch, synthetic
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    hb = synthetic.lightpath_store(num_graphs, seed=40 + shift_floats, device="cpu").host_batch(0, num_graphs)
+    N, E = hb.x.shape[0], hb.edge_index.shape[1]
+    xbuf = torch.empty(shift_floats + N * 5, device=cuda)
+    xv = xbuf[shift_floats:].view(N, 5)
+    xv.copy_(hb.x)
+    ebuf = torch.empty(1 + 2 * E, dtype=torch.int64, device=cuda)
+    ev = ebuf[1:].view(2, E)
+    ev.copy_(hb.edge_index)
+    assert xv.data_ptr() % 16 == 4 * shift_floats and ev.data_ptr() % 16 == 8
+    b = Batch(x=xv, edge_index=ev, batch=hb.batch.to(cuda), ptr=hb.ptr.to(cuda), edge_ptr=hb.edge_ptr.to(cuda),
+              lut_ptr=hb.lut_ptr.to(cuda), num_graphs=num_graphs)
+    with torch.no_grad():
+        out, lb = m(b)
+        eo, el = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
