@@ -37,7 +37,7 @@ class QotLightpathParams(C.Structure):
 
 class QotLpSlot(C.Structure):
     _fields_ = [("x", P), ("edge_src", P), ("edge_dst", P), ("ptrs", P), ("out", P), ("lut_batch", P),
-                ("lut_node", P), ("n_lut", P), ("status", P),
+                ("lut_node", P), ("n_lut", P), ("status", P), ("z", P),
                 ("cap_nodes", i64), ("cap_edges", i64), ("cap_graphs", i64)]
 
 
@@ -77,7 +77,8 @@ SIGNATURES = {
     "qot_lightpath_lut_ptr": (C.c_int, [P, P, i64, i64, i32, P, P, sz, vp]),
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
-    "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, vp]),
+    "qot_lightpath_infer_workspace_bytes": (sz, [i64]),
+    "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, P, sz, vp]),
     "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
     "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,

@@ -17,6 +17,7 @@
 // Deterministic: edges of a row are consumed in edge order, reductions use fixed shuffle
 // trees, no atomics on floats.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,7 +43,10 @@ constexpr int kPreparedBase = ((kOffB2 + QOT_OUT + 3) / 4) * 4;
 // of the residual (error-compensated 3-product scheme, as in gemm_tc.cu)
 constexpr int kOffB1f = kPreparedBase;                  // [ntile 16][lane 32][4]: folded GAT projection + shift row
 constexpr int kOffB2f = kOffB1f + 16 * 32 * 4;          // [ktile 16][ntile 4][lane 32][4]: mlp.0 weight
-constexpr int kPreparedFloats = kOffB2f + 16 * 4 * 32 * 4;
+// attention vectors in the per-lane slot order of lp_attn_kernel (see there)
+constexpr int kOffAsP = kOffB2f + 16 * 4 * 32 * 4;      // [sl 8][slot 6][head slot 4]
+constexpr int kOffAdP = kOffAsP + 8 * 6 * 4;            // [sl>>1 4][f 5][head slot 4]
+constexpr int kPreparedFloats = kOffAdP + 4 * kF * 4;
 
 __device__ __forceinline__ unsigned tf32_rna(float v) {
   unsigned r;
@@ -83,6 +87,16 @@ lp_prepare_kernel(qot_lightpath_params_t p, float* __restrict__ out) {
   if (t < kHid) out[kOffB1 + t] = p.mlp_b1[t];
   if (t < QOT_OUT * kHid) out[kOffW2 + t] = p.mlp_w2[t];
   if (t < QOT_OUT) out[kOffB2 + t] = p.mlp_b2[t];
+  __syncthreads();                                     // A_src / A_dst above are read back below
+  for (int i = t; i < 8 * 6 * 4; i += blockDim.x) {
+    const int sl = i / 24, m = (i / 4) % 6, hs = i % 4;
+    const int fm = (sl & 1) ? (m + 3) % 6 : m;          // feature of slot m; 5 = the constant one
+    out[kOffAsP + i] = fm == 5 ? 0.f : out[kOffAsrc + fm * kHeads + (hs ^ (sl >> 1))];
+  }
+  for (int i = t; i < 4 * kF * 4; i += blockDim.x) {
+    const int hx = i / (kF * 4), f = (i / 4) % kF, hs = i % 4;
+    out[kOffAdP + i] = out[kOffAdst + f * kHeads + (hs ^ hx)];
+  }
   // B fragments (mma.m16n8k8 .col): lane holds B[k = t4][n = g8] and B[k = t4 + 4][n = g8]
   for (int i = t; i < 16 * 32; i += blockDim.x) {
     const int j = i >> 5, ln = i & 31, g8 = ln >> 2, t4 = ln & 3;
@@ -251,6 +265,7 @@ __device__ __forceinline__ float lut_row_head(const float* __restrict__ w, const
 
 // Generic row evaluation straight from global memory: graphs beyond the fast-path caps, further
 // LUT rows of a graph, rows with more than kMsgCap-1 in-edges or a source outside their slab.
+template <bool kHead = true>
 __device__ __noinline__ float lut_row_global(const float* __restrict__ x, const int64_t* __restrict__ esrc,
                                              const int64_t* __restrict__ edst, int64_t e0, int64_t e1,
                                              int64_t N, int64_t i, const float* __restrict__ prep,
@@ -288,6 +303,7 @@ __device__ __noinline__ float lut_row_global(const float* __restrict__ x, const 
   attn_consume(st, s_msg, cnt, xf, As, d_i, lane);
   attn_finish(st, s_z, lane);
   __syncwarp();
+  if (!kHead) return 0.f;                                        // z only (lp_attn_kernel)
   const float ov = lut_row_head(w, s_z, s_y, lane);
   __syncwarp();
   return ov;
@@ -874,6 +890,19 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
 //  The attention keeps one message per lane; the 24 per-graph sums (4 heads x (5 + 1)) are combined
 //  with a reduce-scatter (21 shuffles instead of 72).
 // =====================================================================================
+#ifdef QOT_LP_TRACE
+#define LPB_TRACE_DECL long long lpb_tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define LPB_TRACE(slot) do { if (threadIdx.x == 0) lpb_tr[slot] = clock64(); } while (0)
+#define LPB_TRACE_FLUSH()                                                                        \
+  do {                                                                                           \
+    if (g_lp_trace && threadIdx.x == 0)                                                          \
+      for (int i_ = 0; i_ < 8; ++i_) g_lp_trace[blockIdx.x * 8 + i_] = lpb_tr[i_];               \
+  } while (0)
+#else
+#define LPB_TRACE_DECL do {} while (0)
+#define LPB_TRACE(slot) do {} while (0)
+#define LPB_TRACE_FLUSH() do {} while (0)
+#endif
 #ifndef QOT_LP_BULK_OCC
 #define QOT_LP_BULK_OCC 3
 #endif
@@ -919,6 +948,8 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
                      int32_t* __restrict__ status) {
   extern __shared__ __align__(128) char bulk_smem_raw[];
   BulkSmem& sm = *reinterpret_cast<BulkSmem*>(bulk_smem_raw);
+  LPB_TRACE_DECL;
+  LPB_TRACE(0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
   const int gl = warp * 4 + sg;
@@ -956,6 +987,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
   if (en > 0 && tid == 32 && dspan > dbytes)
     *reinterpret_cast<long long*>(sm.slab + kBDOff + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
   __syncthreads();                                   // barrier initialised, hand-copied tails in place
+  LPB_TRACE(1);
   if (tid == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes + dbytes) : "memory");
     if (xbytes)
@@ -987,6 +1019,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
     Ad[k][0] = b.x; Ad[k][1] = b.y; Ad[k][2] = b.z; Ad[k][3] = b.w;
   }
   while (!mbar_try_wait(bar, 0u)) {}
+  LPB_TRACE(2);
 
   // ---- LUT node(s) of the graph
   int cnt = 0, il = -1;
@@ -1068,6 +1101,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
   if (ok && sl == 0) msg[mc] = il;                    // the appended self loop comes last
   ++mc;
   __syncwarp();
+  LPB_TRACE(3);
 
   // ---- attention: lane = message slot, all 4 heads per lane; the 24 sums are reduce-scattered so that
   // lane sl ends with sums 3*sl .. 3*sl+2 of [h][x0..x4, p] -- its own head is sl >> 1
@@ -1166,6 +1200,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
     }
   }
   int my_state = 0;
+  LPB_TRACE(4);
   if (sl == 0) {
     SubMeta& mt = sm.meta[gl];
     mt.n0 = n0; mt.n1 = n1; mt.e0 = e0; mt.e1 = e1; mt.l0 = l0; mt.l1 = l1;
@@ -1175,6 +1210,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
     mt.state = my_state;
   }
   const int any_generic = __syncthreads_or(my_state == 2);   // z rows staged; the slab is dead from here
+  LPB_TRACE(5);
 
   // ---- readout head on the tensor cores; warp w owns channels 16w .. 16w+15 (head w >> 1)
   float* red = reinterpret_cast<float*>(sm.slab);
@@ -1238,6 +1274,7 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
         for (int i = 0; i < 4; ++i) red[(warp * 32 + (m * 4 + q) * 4 + i) * 32 + lane] = H[m][q][i];
   }
   __syncthreads();
+  LPB_TRACE(6);
   // ---- warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp = (m-tile, row half)
   if (warp < 4) {
     const int g8 = lane >> 2, t4 = lane & 3, m = warp >> 1, upper = warp & 1;
@@ -1316,6 +1353,463 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
       if (lane == 0 && found != mt.l1 - mt.l0) atomicOr(status, 1);
     }
   }
+  LPB_TRACE(7);
+  LPB_TRACE_FLUSH();
+}
+
+// =====================================================================================
+// variant 3 (default): two kernels per batch, the decomposition BASELINE.json's north_star names --
+//   lp_attn_kernel : collate arrays -> gather -> attention softmax -> z rows [L,20] (+ lut_batch / lut_node)
+//   lp_head_kernel : z rows -> folded projection + BN + ReLU -> mlp.0 -> LeakyReLU -> mlp.3 on tensor cores
+// Splitting the readout head off means a block of lp_attn_kernel gives its 64 KB of shared memory
+// back as soon as its attention rows are written: no block-wide barrier, no tensor-pipe phase and no
+// straggler wait while the slabs sit idle (per-block phase trace: 5 000 of 18 400 cycles in variant 2).
+// z is 80 bytes per LUT row (0.33 MB per 4096-graph batch, L2-resident between the two launches).
+// lp_attn_kernel differs from variant 2's first phase in three more ways: the edge scan is fully
+// unrolled with one compare per slot; the message sums use per-lane PERMUTED head / feature slots so
+// the reduce-scatter needs no selects (tables built once by lp_prepare_kernel); graphs the fast path
+// declines are evaluated by their own warp without any block-level bookkeeping.
+// =====================================================================================
+constexpr int kZRow = kHeads * kF;        // floats per z row in the workspace
+
+template <bool kXG>
+struct AttnSmem {
+  alignas(128) unsigned char slab[(kXG ? 0 : kBXBytes + 16) + kBDBytes + 16];   // [x window,] destination window
+  int msg[kGPB][kSubMsg];
+  float gen[8][128];                       // generic path scratch per warp: z (32 floats) + message list (64)
+  alignas(8) unsigned long long mbar;
+};
+
+// kXG: the node features are NOT staged -- flags and the handful of rows a graph needs are read from
+// global memory (L1 / L2), which leaves 39 KB of shared memory per block: 4 resident blocks per SM
+#ifndef QOT_LP_ATTN_OCC
+#define QOT_LP_ATTN_OCC 4                 // register budget: 64 per thread, so that lp_head_kernel blocks fit beside 3 resident blocks
+#endif
+template <bool kXG>
+__global__ void __launch_bounds__(256, QOT_LP_ATTN_OCC)
+lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
+               const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
+               const int64_t* __restrict__ eptr, const int64_t* __restrict__ lptr, int64_t N,
+               int64_t E, int64_t B, const float* __restrict__ prep, int lut_col,
+               float* __restrict__ zbuf, int64_t* __restrict__ lut_batch,
+               int32_t* __restrict__ lut_node, int32_t* __restrict__ n_lut,
+               int32_t* __restrict__ status) {
+  extern __shared__ __align__(128) char attn_smem_raw[];
+  AttnSmem<kXG>& sm = *reinterpret_cast<AttnSmem<kXG>*>(attn_smem_raw);
+  constexpr int kDOff = kXG ? 0 : kBDOff;
+  LPB_TRACE_DECL;
+  LPB_TRACE(0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
+  const int gl = warp * 4 + sg;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kGPB;
+  const int64_t g = g0 + gl;
+  const bool active = g < B;
+  const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&sm.mbar));
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                                   // barrier word initialised before anyone polls it
+
+  // ---- extents of the block's tile (every thread: broadcast loads) and of the sub-group's graph
+  const int64_t gE = min(g0 + kGPB, B);
+  const int64_t nb0 = gptr[g0], nb1 = gptr[gE], eb0 = eptr[g0], eb1 = eptr[gE];
+  long long pv = 0;
+  if (active && sl < 6) pv = (sl < 2) ? gptr[g + sl] : (sl < 4) ? eptr[g + sl - 2] : lptr[g + sl - 4];
+  // windows staged: nodes [nb0, nb0 + xn), edges [eb0, eb0 + en), 16-byte aligned in global memory
+  int xn = 0, en = 0;
+  if (!kXG && nb0 >= 0 && nb1 >= nb0 && nb0 <= N) xn = static_cast<int>(min(min(nb1, N) - nb0, static_cast<int64_t>(kBNodes)));
+  if (eb0 >= 0 && eb1 >= eb0 && eb0 <= E) en = static_cast<int>(min(min(eb1, E) - eb0, static_cast<int64_t>(kBEdges)));
+  const uintptr_t xa = reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(xn > 0 ? nb0 : 0) * (kF * 4);
+  const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? eb0 : 0) * 8;
+  const unsigned xlead = static_cast<unsigned>(xa & 15), dlead = static_cast<unsigned>(da & 15);
+  if (tid == 0) {
+    // one thread sizes the two windows, copies by hand the few bytes a rounded-up window would read
+    // past the end of its tensor, and issues the bulk copies
+    const uintptr_t xs0 = xa - xlead, ds0 = da - dlead;
+    const unsigned xspan = xlead + static_cast<unsigned>(xn) * (kF * 4), dspan = dlead + static_cast<unsigned>(en) * 8;
+    unsigned xbytes = (xspan + 15u) & ~15u, dbytes = (dspan + 15u) & ~15u;
+    if (xs0 + xbytes > reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(N) * (kF * 4)) xbytes = xspan & ~15u;
+    if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(E) * 8) dbytes = dspan & ~15u;
+    if (xn == 0) xbytes = 0;
+    if (en == 0) dbytes = 0;
+    if (xn > 0)
+      for (unsigned o = xbytes; o < xspan; o += 4)
+        *reinterpret_cast<float*>(sm.slab + o) = *reinterpret_cast<const float*>(xs0 + o);
+    if (en > 0 && dspan > dbytes)
+      *reinterpret_cast<long long*>(sm.slab + kDOff + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes + dbytes) : "memory");
+    if (xbytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab))), "l"(xs0), "r"(xbytes), "r"(bar) : "memory");
+    if (dbytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab + kDOff))), "l"(ds0), "r"(dbytes), "r"(bar) : "memory");
+  }
+  LPB_TRACE(1);
+
+  const int64_t n0 = __shfl_sync(kFull, pv, base + 0), n1 = __shfl_sync(kFull, pv, base + 1);
+  const int64_t e0 = __shfl_sync(kFull, pv, base + 2), e1 = __shfl_sync(kFull, pv, base + 3);
+  const int64_t l0 = __shfl_sync(kFull, pv, base + 4), l1 = __shfl_sync(kFull, pv, base + 5);
+  const bool fits = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kBMaxE &&
+                    (kXG ? (n0 >= 0 && n1 <= N) : (n0 >= nb0 && (n1 - nb0) <= xn)) && e0 >= eb0 && (e1 - eb0) <= en;
+  const int n = fits ? static_cast<int>(n1 - n0) : 0;
+  const int ne = fits ? static_cast<int>(e1 - e0) : 0;
+  if (g == B - 1 && sl == 0) n_lut[0] = static_cast<int32_t>(l1);
+  const float* sx = kXG ? x + (fits ? n0 : 0) * kF
+                        : reinterpret_cast<const float*>(sm.slab + xlead) + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
+  const long long* sd = reinterpret_cast<const long long*>(sm.slab + kDOff + dlead) + (fits ? static_cast<int>(e0 - eb0) : 0);
+  // kXG: the LUT flags of the graph, all requested before anything waits (8 nodes per load round)
+  float flag[kMaxN / 8];
+  if (kXG) {
+#pragma unroll
+    for (int r = 0; r < kMaxN / 8; ++r) {
+      const int node = sl + 8 * r;
+      flag[r] = node < n ? __ldg(sx + node * kF + lut_col) : 0.f;
+    }
+  }
+
+  // attention vectors in this lane's slot order while the copies fly: local head slot i is head
+  // i ^ (sl >> 1); local feature slot m is (x0 x1 x2 x3 x4 ONE) on even lanes, (x3 x4 ONE x0 x1 x2) on odd
+  const int hx = sl >> 1;
+  const bool odd = (sl & 1) != 0;
+  float AsP[6][kHeads];
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + sl * 6 + m);
+    AsP[m][0] = a.x; AsP[m][1] = a.y; AsP[m][2] = a.z; AsP[m][3] = a.w;
+  }
+  while (!mbar_try_wait(bar, 0u)) {}
+  LPB_TRACE(2);
+
+  // ---- LUT node(s) of the graph
+  int cnt = 0, il = -1;
+#pragma unroll
+  for (int r = 0; r < kMaxN / 8; ++r) {
+    if (__any_sync(kFull, 8 * r < n)) {
+      const int node = sl + 8 * r;
+      const unsigned bal = __ballot_sync(kFull, node < n && (kXG ? flag[r] : sx[node * kF + lut_col]) == 1.0f);
+      const unsigned sub = (bal >> (8 * sg)) & 0xffu;
+      if (sub) {
+        if (il < 0) il = 8 * r + __ffs(sub) - 1;
+        cnt += __popc(sub);
+      }
+    }
+  }
+  bool ok = fits && cnt == 1 && (l1 - l0) == 1;      // fast row: exactly one LUT node, as lut_ptr says
+  if (fits && sl == 0 && cnt != l1 - l0) atomicOr(status, 1);   // lut_ptr does not describe this x
+
+  // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph (c odd: the
+  // 8-byte reads of the 8 lanes fall into distinct banks); one predicate per slot
+  int* msg = sm.msg[gl];
+  int mc = 0;
+  {
+    const int c = ((ne + 7) >> 3) | 1;
+    const int eb = sl * c;
+    const int tmax = ok ? min(c, ne - eb) : 0;
+    const int cmax = __reduce_max_sync(kFull, tmax);
+    const long long target = ok ? n0 + il : -2;
+    const long long* sde = sd + eb;
+    unsigned hm = 0u;
+#pragma unroll
+    for (int t4 = 0; t4 < 32; t4 += 4) {
+      if (t4 < cmax) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = t4 + i;
+          if (t < 31) {
+            long long d = -1;
+            if (t < tmax) d = sde[t];
+            if (d == target) hm |= 1u << t;
+          }
+        }
+      }
+    }
+    const int h = __popc(hm);
+    int incl = h;
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      const int up = __shfl_up_sync(kFull, incl, o, 8);
+      if (sl >= o) incl += up;
+    }
+    mc = __shfl_sync(kFull, incl, base + 7);
+    int pos = incl - h;
+    while (hm) {
+      const int t = __ffs(hm) - 1;
+      hm &= hm - 1u;
+      if (pos < kSubMsg - 1) msg[pos] = eb + t;
+      ++pos;
+    }
+  }
+  if (mc > kSubMsg - 1) ok = false;                  // hub row: generic path
+  __syncwarp();
+  // sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
+  {
+    int kept = 0;
+    bool outside = false;
+#pragma unroll
+    for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
+      if (__any_sync(kFull, ok && t0 < mc)) {
+        const int t = t0 + sl;
+        long long sj = -1;
+        if (ok && t < mc) sj = esrc[e0 + msg[t]];
+        const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
+        const long long sloc = sj - n0;
+        const bool inslab = sloc >= 0 && sloc < n;
+        const bool keep = inslab && sloc != il;
+        outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
+        const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
+        __syncwarp();
+        if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
+        kept += __popc(sub);
+        __syncwarp();
+      }
+    }
+    if (outside) ok = false;                          // a source outside the slab: generic path
+    mc = kept;
+  }
+  if (ok && sl == 0) msg[mc] = il;                    // the appended self loop comes last
+  ++mc;
+  __syncwarp();
+  LPB_TRACE(3);
+
+  // ---- attention: lane = message slot, all 4 heads per lane.  The 24 sums per graph (4 heads x
+  // (x0..x4, 1)) are reduce-scattered: three exchange steps, each lane sends the half it does not
+  // keep -- statically the upper half of its registers thanks to the slot permutation
+  {
+    float d[kHeads];
+    const int ils = ok ? il : 0;
+#pragma unroll
+    for (int i = 0; i < kHeads; ++i) d[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+      const float xi = sx[ils * kF + k];
+      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + hx * kF + k);
+      d[0] = fmaf(xi, b.x, d[0]); d[1] = fmaf(xi, b.y, d[1]);
+      d[2] = fmaf(xi, b.z, d[2]); d[3] = fmaf(xi, b.w, d[3]);
+    }
+    float mx[kHeads], acc3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < kHeads; ++i) mx[i] = -INFINITY;
+    const int o0 = odd ? 3 : 0;
+#pragma unroll
+    for (int r0 = 0; r0 < kSubMsg; r0 += 8) {
+      if (__any_sync(kFull, ok && r0 < mc)) {
+        const bool valid = ok && r0 + sl < mc;
+        const float* xr = sx + (valid ? msg[r0 + sl] : 0) * kF;
+        float q[6];
+        const float x2 = xr[2];
+        q[0] = xr[o0]; q[1] = xr[o0 + 1]; q[3] = xr[3 - o0]; q[4] = xr[4 - o0];
+        q[2] = odd ? 1.0f : x2;
+        q[5] = odd ? x2 : 1.0f;
+        float a[kHeads], mr[kHeads], m2[kHeads];
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) {
+          float t = d[i];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) t = fmaf(q[m], AsP[m][i], t);    // the ONE slot carries weight 0
+          t = t > 0.f ? t : 0.2f * t;
+          a[i] = valid ? t : -INFINITY;
+        }
+        // per-head maximum over the 8 lanes: the partner's slot for MY head i is i (xor 1: same
+        // permutation), i ^ 1 (xor 2) and i ^ 2 (xor 4) -- register renaming, no selects
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(a[i], __shfl_xor_sync(kFull, a[i], 1));
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) m2[i] = fmaxf(mr[i], __shfl_xor_sync(kFull, mr[i ^ 1], 2));
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(m2[i], __shfl_xor_sync(kFull, m2[i ^ 2], 4));
+        float v[24];
+        float scarg = 0.f;
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) {
+          const float mn = fmaxf(fmaxf(mx[i], mr[i]), -1e30f);   // idle sub-groups stay finite
+          const float p = valid ? expf(a[i] - mn) : 0.f;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) v[i * 6 + m] = p * q[m];
+          if (i == 0) scarg = mx[0] - mn;                     // -inf in the first round: exp -> 0
+          mx[i] = mn;
+        }
+        float u[12], s6[6], w3[3];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) u[t] = v[t] + __shfl_xor_sync(kFull, v[t + 12], 4);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) s6[t] = u[t] + __shfl_xor_sync(kFull, u[t + 6], 2);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) w3[t] = s6[t] + __shfl_xor_sync(kFull, s6[t + 3], 1);
+        const float sc = expf(scarg);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) acc3[t] = fmaf(acc3[t], sc, w3[t]);
+      }
+    }
+    // even lane: sums x0..x2 of head sl>>1; odd lane: x3, x4 and the softmax denominator
+    const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
+    const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
+    if (ok) {
+      float* zr = zbuf + l0 * kZRow + hx * kF + o0;
+      zr[0] = acc3[0] * inv;
+      zr[1] = acc3[1] * inv;
+      if (!odd) zr[2] = acc3[2] * inv;
+      if (sl == 0) {
+        lut_batch[l0] = g;
+        lut_node[l0] = static_cast<int32_t>(n0 + il);
+      }
+    }
+  }
+  LPB_TRACE(4);
+
+  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
+  const int my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
+  if (__any_sync(kFull, my_state == 2)) {
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      if (__shfl_sync(kFull, my_state, 8 * s) != 2) continue;
+      const int64_t gn0 = __shfl_sync(kFull, n0, 8 * s), gn1 = __shfl_sync(kFull, n1, 8 * s);
+      const int64_t ge0 = __shfl_sync(kFull, e0, 8 * s), ge1 = __shfl_sync(kFull, e1, 8 * s);
+      const int64_t gl0 = __shfl_sync(kFull, l0, 8 * s), gl1 = __shfl_sync(kFull, l1, 8 * s);
+      float* s_z = sm.gen[warp];
+      int* s_m = reinterpret_cast<int*>(sm.gen[warp] + 32);
+      int64_t orow = gl0;
+      int found = 0;
+      for (int64_t nb = gn0; nb < gn1; nb += 32) {
+        const int64_t node = nb + lane;
+        unsigned mask = __ballot_sync(kFull, node < gn1 && x[node * kF + lut_col] == 1.0f);
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ++found;
+          if (orow < gl1) {                                      // never write past this graph's rows
+            const int64_t i = nb + bit;
+            lut_row_global<false>(x, esrc, edst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
+            if (lane < kZRow) zbuf[orow * kZRow + lane] = s_z[(lane / kF) * 8 + lane % kF];
+            if (lane == 0) {
+              lut_batch[orow] = g0 + warp * 4 + s;
+              lut_node[orow] = static_cast<int32_t>(i);
+            }
+            __syncwarp();
+            ++orow;
+          }
+        }
+      }
+      if (lane == 0 && found != gl1 - gl0) atomicOr(status, 1);
+    }
+  }
+  LPB_TRACE(7);
+  LPB_TRACE_FLUSH();
+}
+
+// Readout head over the L = lut_ptr[B] rows of z: a block stages the 40 KB of pre-split B fragments in
+// shared memory once and each of its 4 warps takes 16 rows (64 rows per block: 64 blocks for a 4096-row
+// batch, so the fragments cross L2 -> SM 64 times per batch, not once per 16 rows); everything else
+// stays in registers, no block barrier after the staging.
+//   y = relu(z_h Wf_h + shift)  (16 n-tiles, K = 8 per head: x0..x4, the constant 1 against the shift row)
+//   h = y W1^T                  (each y tile is at once the next product's A fragment)
+//   out = leaky(h + b1) W2^T + b2
+// Accuracy: the tensor cores truncate when they add into a running accumulator, so the large
+// (hi x hi) terms are produced by stand-alone MMAs and added in fp32 on the CUDA cores; only the small
+// compensation terms (lo x hi + hi x lo) chain inside an accumulator.
+__global__ void lp_debug_empty_kernel(int32_t* p) { if (p == nullptr) printf("x"); }
+constexpr int kHeadFrag4 = (kOffAsP - kOffB1f) / 4;   // float4 entries of B1f | B2f (contiguous in `prepared`)
+__global__ void __launch_bounds__(128)
+lp_head_kernel(const float* __restrict__ zbuf, const int64_t* __restrict__ lptr, int64_t B,
+               const float* __restrict__ prep, float* __restrict__ out) {
+  __shared__ float4 frag[kHeadFrag4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+  const int64_t L = lptr[B];
+  if (static_cast<int64_t>(blockIdx.x) * 64 >= L) return;
+  for (int i = tid; i < kHeadFrag4; i += 128) frag[i] = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + i);
+  __syncthreads();
+  const float4* __restrict__ f1 = frag;
+  const float4* __restrict__ f2 = frag + 16 * 32;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + warp; tile * 16 < L;
+       tile += static_cast<int64_t>(gridDim.x) * 4) {
+    const int64_t ra = tile * 16 + g8, rb = ra + 8;
+    const bool va = ra < L, vb = rb < L;
+    const float* za = zbuf + ra * kZRow;
+    const float* zb = zbuf + rb * kZRow;
+    float H[4][4], Hc[4][4];                           // fp32 sums of the hi x hi tiles; compensation chains
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) H[q][i] = Hc[q][i] = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < kHeads; ++h) {
+      // A fragment of head h: rows (g8, g8+8), k slots (t4, t4+4): x_t4 | x4, 1, 0, 0
+      unsigned ahi[4], alo[4];
+      {
+        float a[4];
+        a[0] = va ? za[h * kF + t4] : 0.f;
+        a[1] = vb ? zb[h * kF + t4] : 0.f;
+        a[2] = t4 == 0 ? (va ? za[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
+        a[3] = t4 == 0 ? (vb ? zb[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ahi[i] = tf32_rna(a[i]);
+          alo[i] = tf32_rna(a[i] - __uint_as_float(ahi[i]));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * h + jj;
+        const float4 b = f1[j * 32 + lane];
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_tf32(c, alo, b.x, b.y);
+        mma_tf32(c, ahi, b.z, b.w);
+        mma_tf32(c, ahi, b.x, b.y);
+        // ReLU, split, and C -> A fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3)
+        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
+        unsigned yhi[4], ylo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          yhi[i] = tf32_rna(y[i]);
+          ylo[i] = tf32_rna(y[i] - __uint_as_float(yhi[i]));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b2 = f2[(j * 4 + q) * 32 + lane];
+          mma_tf32(Hc[q], ylo, b2.x, b2.y);
+          mma_tf32(Hc[q], yhi, b2.z, b2.w);
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_tf32(t, yhi, b2.x, b2.y);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) H[q][i] += t[i];
+        }
+      }
+    }
+    // H[q]: rows (g8: regs 0,1 | g8+8: regs 2,3), hidden units 8q + 2*t4 + (0,1)
+    float oa[QOT_OUT] = {0.f, 0.f, 0.f}, ob[QOT_OUT] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = 8 * q + 2 * t4;
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
+      float hv[4] = {H[q][0] + Hc[q][0] + b1.x, H[q][1] + Hc[q][1] + b1.y, H[q][2] + Hc[q][2] + b1.x,
+                     H[q][3] + Hc[q][3] + b1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hv[i] = hv[i] > 0.f ? hv[i] : 0.01f * hv[i];
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
+        oa[k] = fmaf(hv[0], w2.x, oa[k]);
+        oa[k] = fmaf(hv[1], w2.y, oa[k]);
+        ob[k] = fmaf(hv[2], w2.x, ob[k]);
+        ob[k] = fmaf(hv[3], w2.y, ob[k]);
+      }
+    }
+#pragma unroll
+    for (int s = 1; s <= 2; s <<= 1) {
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        oa[k] += __shfl_xor_sync(kFull, oa[k], s);
+        ob[k] += __shfl_xor_sync(kFull, ob[k], s);
+      }
+    }
+    if (t4 < QOT_OUT) {
+      const float b2 = __ldg(prep + kOffB2 + t4);
+      if (va) out[ra * QOT_OUT + t4] = (t4 == 0 ? oa[0] : t4 == 1 ? oa[1] : oa[2]) + b2;
+      if (vb) out[rb * QOT_OUT + t4] = (t4 == 0 ? ob[0] : t4 == 1 ? ob[1] : ob[2]) + b2;
+    }
+  }
 }
 
 }  // namespace qot
@@ -1371,20 +1865,59 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
 }
 
 // 0: one warp per graph (lp_infer_kernel); 1: 8 lanes per graph (lp_infer_sub_kernel);
-// 2: 8 lanes per graph, bulk-copied slabs, tensor-core readout head (lp_infer_bulk_kernel)
-static int g_lp_variant = 2;
+// 2: 8 lanes per graph, bulk-copied slabs, tensor-core readout head (lp_infer_bulk_kernel);
+// 3: lp_attn_kernel (z rows into the workspace) + lp_head_kernel (tensor-core readout head)
+static int g_lp_variant = 3;
 extern "C" int qot_lightpath_set_variant(int v) {
-  if (v < 0 || v > 2) return QOT_E_BADARG;
+  if (v < 0 || v > 3) return QOT_E_BADARG;
   g_lp_variant = v;
   return QOT_OK;
 }
 extern "C" int qot_lightpath_get_variant(void) { return g_lp_variant; }
 
+static int g_dbg_flags = 0;   // TEMP
+extern "C" int qot_debug_lp_flags(int f) { g_dbg_flags = f; return 0; }   // TEMP
 static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* edst,
                            const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr, int64_t N,
                            int64_t E, int64_t B, const float* prepared, int32_t is_lut_index, float* out,
                            int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut, int32_t* status,
-                           cudaStream_t stream) {
+                           float* zbuf, cudaStream_t stream) {
+  if (g_lp_variant == 3) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sizeof(AttnSmem<false>))));
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      // the head kernel uses no shared memory, but it runs between attention kernels that need the
+      // largest carve-out: asking for the same split keeps the SMs from reconfiguring (and draining)
+      if (!getenv("QOT_LP_NO_CARVEOUT"))
+        QOT_CUDA(cudaFuncSetAttribute(lp_head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+      attr_set = true;
+    }
+    const int64_t blocks = cdiv(B, kGPB);
+    const bool skip_attn = getenv("QOT_LP_DEBUG_SKIP_ATTN") != nullptr || (g_dbg_flags & 1);   // TEMP experiment switch
+    static const bool xg = getenv("QOT_LP_DEBUG_XG") != nullptr;   // TEMP experiment switch
+    if (skip_attn) {
+    } else if (xg) {
+      static const size_t xg_smem = getenv("QOT_LP_DEBUG_XG_SMEM") ? static_cast<size_t>(atoi(getenv("QOT_LP_DEBUG_XG_SMEM"))) : sizeof(AttnSmem<true>);   // TEMP
+      lp_attn_kernel<true><<<static_cast<unsigned>(blocks), 256, xg_smem, stream>>>(
+          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, lut_batch, lut_node, n_lut, status);
+    } else {
+      lp_attn_kernel<false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false>), stream>>>(
+          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, lut_batch, lut_node, n_lut, status);
+    }
+    QOT_LAUNCH_CHECK();
+    // one block per 64 rows; L is only known on the device: the grid covers the common case (about one
+    // LUT row per graph) and the blocks stride over any further tiles
+    const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(std::min(N, B), 64), 4 * kNumSMs));
+    const bool skip_head = getenv("QOT_LP_DEBUG_SKIP_HEAD") != nullptr || (g_dbg_flags & 2);   // TEMP experiment switch
+    static const bool empty_head = getenv("QOT_LP_DEBUG_EMPTY_HEAD") != nullptr;   // TEMP experiment switch
+    if (empty_head) lp_debug_empty_kernel<<<1, 32, 0, stream>>>(n_lut);
+    else if (!skip_head) lp_head_kernel<<<static_cast<unsigned>(hb), 128, 0, stream>>>(zbuf, lut_ptr, B, prepared, out);
+    QOT_LAUNCH_CHECK();
+    return QOT_OK;
+  }
   if (g_lp_variant == 2) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -1419,11 +1952,15 @@ static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* e
   return QOT_OK;
 }
 
+extern "C" size_t qot_lightpath_infer_workspace_bytes(int64_t N) {
+  return N > 0 ? align_up(static_cast<size_t>(N) * kZRow * 4) : 256;
+}
+
 extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                                    const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
                                    int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
                                    float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                                   int32_t* status, void* stream_) {
+                                   int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   QOT_REQUIRE(N >= 0 && B >= 0 && E >= 0, "qot_lightpath_infer: negative size");
   QOT_REQUIRE(N < (1ll << 31) - 1, "qot_lightpath_infer: N exceeds int32 range");
@@ -1432,12 +1969,14 @@ extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, in
   QOT_REQUIRE(N == 0 || (x && out && lut_batch && lut_node), "qot_lightpath_infer: null buffer");
   QOT_REQUIRE(E == 0 || edge_index, "qot_lightpath_infer: null edge_index");
   QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer: prepared must be 16-byte aligned");
+  QOT_REQUIRE(ws && ws_bytes >= qot_lightpath_infer_workspace_bytes(N) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+              "qot_lightpath_infer: workspace missing, misaligned or smaller than qot_lightpath_infer_workspace_bytes(N)");
   if (B == 0) {
     QOT_CUDA(cudaMemsetAsync(n_lut, 0, 4, stream));
     return QOT_OK;
   }
   return lp_infer_launch(x, edge_index, edge_index + E, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, out,
-                         lut_batch, lut_node, n_lut, status, stream);
+                         lut_batch, lut_node, n_lut, status, static_cast<float*>(ws), stream);
 }
 
 // Host-buffer form of the same call: the batch lives in PINNED HOST memory in the reference layout.
@@ -1461,7 +2000,7 @@ extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge
                   lut_batch_host && status_host && (E == 0 || edge_index_host),
               "qot_lightpath_infer_host: null argument");
   QOT_REQUIRE(slot->x && slot->edge_dst && slot->ptrs && slot->out && slot->lut_batch && slot->lut_node &&
-                  slot->n_lut && slot->status, "qot_lightpath_infer_host: incomplete staging slot");
+                  slot->n_lut && slot->status && slot->z, "qot_lightpath_infer_host: incomplete staging slot");
   QOT_REQUIRE(N <= slot->cap_nodes && E <= slot->cap_edges && B <= slot->cap_graphs,
               "qot_lightpath_infer_host: batch (N=%lld, E=%lld, B=%lld) exceeds the slot capacity",
               (long long)N, (long long)E, (long long)B);
@@ -1500,7 +2039,7 @@ extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge
   }
   copied += N * kF * 4 + E * 8 + 3 * (B + 1) * 8;
   int rc = lp_infer_launch(slot->x, esrc_dev, slot->edge_dst, gptr, eptr, lptr, N, E, B, prepared, is_lut_index,
-                           slot->out, slot->lut_batch, slot->lut_node, slot->n_lut, slot->status, stream);
+                           slot->out, slot->lut_batch, slot->lut_node, slot->n_lut, slot->status, slot->z, stream);
   if (rc) return rc;
   if (L > 0) {
     QOT_CUDA(cudaMemcpyAsync(out_host, slot->out, L * QOT_OUT * 4, cudaMemcpyDeviceToHost, stream));

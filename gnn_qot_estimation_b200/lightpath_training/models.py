@@ -20,9 +20,15 @@ from ..nn import BatchNorm, GATConv
 
 
 class LightpathGNN(torch.nn.Module):
-    # kernels launched by one eval forward_device() call (bench.py counts launches with these)
-    launches_per_step = 1                  # one fused kernel per batch
-    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_infer_bulk_kernel")
+    # kernels behind qot_lightpath_infer per qot_lightpath_set_variant() value (bench.py counts
+    # launches and names the dominant kernel with these)
+    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_infer_bulk_kernel", "lp_attn_kernel")
+    _variant_launches = (1, 1, 1, 2)       # variant 3: lp_attn_kernel + lp_head_kernel
+
+    @property
+    def launches_per_step(self):
+        from .. import _lib
+        return self._variant_launches[_lib.lib().qot_lightpath_get_variant()]
 
     @property
     def dominant_kernel(self):

@@ -174,16 +174,19 @@ def lightpath_lut_ptr(x, gptr, is_lut_index: int) -> torch.Tensor:
 
 def lightpath_infer(x, edge_index, gptr, eptr, lut_ptr, prepared, is_lut_index: int,
                     out: Optional[LightpathInferOut] = None) -> LightpathInferOut:
-    """Launches the fused eval forward (ONE kernel); returns device buffers without any host sync."""
+    """Launches the fused eval forward (attention kernel + readout-head kernel; ONE kernel for the
+    older variants); returns device buffers without any host sync."""
     _require_cuda(x, edge_index, gptr, eptr, lut_ptr, prepared)
     x, edge_index = _f32(x), _i64(edge_index)
     N, E, B = int(x.shape[0]), int(edge_index.shape[1]), int(gptr.numel() - 1)
     if out is None:
         out = new_infer_out(N, x.device)
     L = _lib.lib()
+    ws = _lib.workspace(L.qot_lightpath_infer_workspace_bytes(N), x.device)
     check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), ptr(lut_ptr), N, B,
                                 ptr(prepared), int(is_lut_index), ptr(out.out), ptr(out.lut_batch),
-                                ptr(out.lut_node), ptr(out.n_lut), ptr(out.status), stream()),
+                                ptr(out.lut_node), ptr(out.n_lut), ptr(out.status), ptr(ws), ws.numel(),
+                                stream()),
           "qot_lightpath_infer")
     return out
 

@@ -295,17 +295,22 @@ int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_t N, int64_
  * `prepared` (qot_lightpath_prepared_floats() floats, 16-byte aligned). */
 size_t qot_lightpath_prepared_floats(void);
 int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream);
+/* `ws`: caller-provided scratch of qot_lightpath_infer_workspace_bytes(N) bytes, 16-byte aligned
+ * (the attention rows z [L,20] handed from lp_attn_kernel to lp_head_kernel); the library keeps no
+ * reference to it after the call's work has run on `stream`. */
+size_t qot_lightpath_infer_workspace_bytes(int64_t N);
 int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
                         int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
                         float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                        int32_t* status, void* stream);
+                        int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
 /* Kernel variant behind qot_lightpath_infer[_host]: 0 = one warp per graph, 1 = 8 lanes per graph in
  * the scan / attention phase + block-wide two-row heads, 2 (default) = 8 lanes per graph with the
  * block's node / destination slabs moved by bulk async copies and the readout head on the tensor
- * cores (error-compensated TF32).  Same rows, values equal to fp32 round-off (the summation trees
- * differ); process-wide, set before launching. */
+ * cores (error-compensated TF32), 3 (default) = the same split into two launches (lp_attn_kernel
+ * writes the attention rows into `ws`, lp_head_kernel runs the readout head over them).  Same rows,
+ * values equal to fp32 round-off (the summation trees differ); process-wide, set before launching. */
 int qot_lightpath_set_variant(int variant);
 int qot_lightpath_get_variant(void);
 
@@ -327,6 +332,7 @@ typedef struct {
   int32_t* lut_node;    /* [cap_nodes]                                     */
   int32_t* n_lut;       /* [1]                                             */
   int32_t* status;      /* [1], zeroed by the caller once                  */
+  float* z;             /* qot_lightpath_infer_workspace_bytes(cap_nodes) bytes, 16-byte aligned */
   int64_t cap_nodes, cap_edges, cap_graphs;
 } qot_lp_slot_t;
 int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,

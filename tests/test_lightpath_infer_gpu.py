@@ -247,8 +247,8 @@ def test_lut_ptr_kernel_matches_host(cuda):
 
 
 def test_kernel_variants_agree(cuda):
-    """The three kernels behind qot_lightpath_infer (one warp per graph / 8 lanes per graph / 8 lanes per
-    graph with bulk-copied slabs and the tensor-core head) give the same rows (same order, same indices)
+    """The four variants behind qot_lightpath_infer (one warp per graph / 8 lanes per graph / 8 lanes per
+    graph with bulk-copied slabs and the tensor-core head / the same as attention + head launches) give the same rows (same order, same indices)
     and values within round-off of each other and of the oracle."""
     from gnn_qot_estimation_b200 import _lib, synthetic
     sd = load_golden("ckpt_lightpath_model_0.pt")["model_state_dict"]
@@ -259,7 +259,7 @@ def test_kernel_variants_agree(cuda):
     prev = L.qot_lightpath_get_variant()
     try:
         res = {}
-        for v in (0, 1, 2):
+        for v in (0, 1, 2, 3):
             assert L.qot_lightpath_set_variant(v) == 0 and L.qot_lightpath_get_variant() == v
             with torch.no_grad():
                 o, l = m(b)
@@ -269,9 +269,9 @@ def test_kernel_variants_agree(cuda):
         L.qot_lightpath_set_variant(prev)
     with torch.no_grad():
         eo, el = _oracle(sd, torch.float64)(_to64(hb))
-    for v in (0, 1, 2):
-        assert torch.equal(res[v][1], res[2][1])
-        assert rel_err(res[v][0], res[2][0]) <= RTOL
+    for v in (0, 1, 2, 3):
+        assert torch.equal(res[v][1], res[3][1])
+        assert rel_err(res[v][0], res[3][0]) <= RTOL
         assert torch.equal(res[v][1].cpu(), el) and rel_err(res[v][0], eo) <= RTOL
 
 
