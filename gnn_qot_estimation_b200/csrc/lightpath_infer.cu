@@ -872,23 +872,7 @@ lp_infer_sub_kernel(const float* __restrict__ x, const int64_t* __restrict__ esr
 }
 
 // =====================================================================================
-// variant 2 (default): lp_infer_bulk_kernel.  Same 8-lanes-per-graph decomposition as variant 1,
-// with the two instruction-heavy parts of that kernel removed:
-//  * loads: the block's 32 graphs are contiguous in x and in the destination row of edge_index, so
-//    ONE elected thread moves both ranges into shared memory with two bulk async copies
-//    (cp.async.bulk, 16-byte aligned windows, completion on an mbarrier) -- ~24 KB + ~31 KB per block
-//    for two instructions instead of ~50 per lane.  With the destination ids in shared memory each lane
-//    scans a CONTIGUOUS run of its graph's edges (odd run length: bank-conflict-free 8-byte reads), so
-//    the in-edges of the LUT node come out in edge order from one 8-lane prefix sum.
-//  * readout head: relu(Z Wf + shift) [32 x 128] and its product with mlp.0 [128 x 32] run on the
-//    tensor cores (mma.sync m16n8k8 TF32, error-compensated hi/lo operands: 3 products, fp32
-//    accumulate -- entrywise error ~2^-21 of |A||W|, inside the 1e-5 bar).  Each warp owns 16 of the
-//    128 channels: its C fragments of the first product ARE the A fragments of the second (the
-//    k-order of the pre-built B fragments is permuted to make that so); the eight partial [32 x 32]
-//    products are summed in a fixed order through shared memory (the dead slab) by the warps that
-//    finish LeakyReLU + mlp.3.
-//  The attention keeps one message per lane; the 24 per-graph sums (4 heads x (5 + 1)) are combined
-//  with a reduce-scatter (21 shuffles instead of 72).
+// Shared pieces of variants 2 and 3 (lp_attn_kernel, lp_head_kernel): bulk-copied slabs, tensor-core head.
 // =====================================================================================
 #ifdef QOT_LP_TRACE
 #define LPB_TRACE_DECL long long lpb_tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}
@@ -914,16 +898,6 @@ constexpr int kBDBytes = kBEdges * 8;
 constexpr int kBDOff = kBXBytes + 16;     // destination slab offset inside BulkSmem::slab
 constexpr int kZStride = 36;              // floats per graph row of z (4 heads x 8, padded: conflict-free fragments)
 
-struct BulkSmem {
-  alignas(128) unsigned char slab[kBXBytes + 16 + kBDBytes + 16];   // x window, destination window; later H partials
-  float zhi[kGPB * kZStride];
-  float zlo[kGPB * kZStride];
-  int msg[kGPB][kSubMsg];
-  SubMeta meta[kGPB];
-  alignas(8) unsigned long long mbar;
-};
-static_assert(sizeof(BulkSmem::slab) >= 8 * 32 * 32 * 4, "slab is reused for the 8 partial [32x32] products");
-
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], float b0, float b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -936,425 +910,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
       "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0u;
-}
-
-__global__ void __launch_bounds__(256, QOT_LP_BULK_OCC)
-lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
-                     const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
-                     const int64_t* __restrict__ eptr, const int64_t* __restrict__ lptr, int64_t N,
-                     int64_t E, int64_t B, const float* __restrict__ prep, int lut_col,
-                     float* __restrict__ out, int64_t* __restrict__ lut_batch,
-                     int32_t* __restrict__ lut_node, int32_t* __restrict__ n_lut,
-                     int32_t* __restrict__ status) {
-  extern __shared__ __align__(128) char bulk_smem_raw[];
-  BulkSmem& sm = *reinterpret_cast<BulkSmem*>(bulk_smem_raw);
-  LPB_TRACE_DECL;
-  LPB_TRACE(0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
-  const int gl = warp * 4 + sg;
-  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kGPB;
-  const int64_t g = g0 + gl;
-  const bool active = g < B;
-  const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&sm.mbar));
-
-  // ---- extents: of the block's tile (every thread, broadcast loads) and of the sub-group's graph
-  const int64_t gE = min(g0 + kGPB, B);
-  const int64_t nb0 = gptr[g0], nb1 = gptr[gE], eb0 = eptr[g0], eb1 = eptr[gE];
-  long long pv = 0;
-  if (active && sl < 6) pv = (sl < 2) ? gptr[g + sl] : (sl < 4) ? eptr[g + sl - 2] : lptr[g + sl - 4];
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // windows actually staged: nodes [nb0, nb0 + xn), edges [eb0, eb0 + en); 16-byte aligned in global
-  // memory, the few bytes a rounded-up window would read past the end of the tensor are copied by hand
-  int xn = 0, en = 0;
-  if (nb0 >= 0 && nb1 >= nb0 && nb0 <= N) xn = static_cast<int>(min(min(nb1, N) - nb0, static_cast<int64_t>(kBNodes)));
-  if (eb0 >= 0 && eb1 >= eb0 && eb0 <= E) en = static_cast<int>(min(min(eb1, E) - eb0, static_cast<int64_t>(kBEdges)));
-  const uintptr_t xa = reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(xn > 0 ? nb0 : 0) * (kF * 4);
-  const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? eb0 : 0) * 8;
-  const uintptr_t xs0 = xa & ~static_cast<uintptr_t>(15), ds0 = da & ~static_cast<uintptr_t>(15);
-  const unsigned xlead = static_cast<unsigned>(xa - xs0), dlead = static_cast<unsigned>(da - ds0);
-  const unsigned xspan = xlead + static_cast<unsigned>(xn) * (kF * 4), dspan = dlead + static_cast<unsigned>(en) * 8;
-  unsigned xbytes = (xspan + 15u) & ~15u, dbytes = (dspan + 15u) & ~15u;
-  if (xs0 + xbytes > reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(N) * (kF * 4)) xbytes = xspan & ~15u;
-  if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(E) * 8) dbytes = dspan & ~15u;
-  if (xn == 0) xbytes = 0;
-  if (en == 0) dbytes = 0;
-  if (xn > 0 && tid < static_cast<int>((xspan - min(xspan, xbytes)) >> 2))
-    reinterpret_cast<float*>(sm.slab + xbytes)[tid] = reinterpret_cast<const float*>(xs0 + xbytes)[tid];
-  if (en > 0 && tid == 32 && dspan > dbytes)
-    *reinterpret_cast<long long*>(sm.slab + kBDOff + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
-  __syncthreads();                                   // barrier initialised, hand-copied tails in place
-  LPB_TRACE(1);
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes + dbytes) : "memory");
-    if (xbytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab))), "l"(xs0), "r"(xbytes), "r"(bar) : "memory");
-    if (dbytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab + kBDOff))), "l"(ds0), "r"(dbytes), "r"(bar) : "memory");
-  }
-
-  const int64_t n0 = __shfl_sync(kFull, pv, base + 0), n1 = __shfl_sync(kFull, pv, base + 1);
-  const int64_t e0 = __shfl_sync(kFull, pv, base + 2), e1 = __shfl_sync(kFull, pv, base + 3);
-  const int64_t l0 = __shfl_sync(kFull, pv, base + 4), l1 = __shfl_sync(kFull, pv, base + 5);
-  const bool fits = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kBMaxE &&
-                    n0 >= nb0 && (n1 - nb0) <= xn && e0 >= eb0 && (e1 - eb0) <= en;
-  const int n = fits ? static_cast<int>(n1 - n0) : 0;
-  const int ne = fits ? static_cast<int>(e1 - e0) : 0;
-  if (g == B - 1 && sl == 0) n_lut[0] = static_cast<int32_t>(l1);
-  const float* sx = reinterpret_cast<const float*>(sm.slab + xlead) + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
-  const long long* sd = reinterpret_cast<const long long*>(sm.slab + kBDOff + dlead) + (fits ? static_cast<int>(e0 - eb0) : 0);
-
-  // attention vectors while the copies fly: A_src[k][0..3], and the LUT row's A_dst dot later
-  float As[kF][kHeads], Ad[kF][kHeads];
-#pragma unroll
-  for (int k = 0; k < kF; ++k) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(prep + kOffAsrc) + k);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdst) + k);
-    As[k][0] = a.x; As[k][1] = a.y; As[k][2] = a.z; As[k][3] = a.w;
-    Ad[k][0] = b.x; Ad[k][1] = b.y; Ad[k][2] = b.z; Ad[k][3] = b.w;
-  }
-  while (!mbar_try_wait(bar, 0u)) {}
-  LPB_TRACE(2);
-
-  // ---- LUT node(s) of the graph
-  int cnt = 0, il = -1;
-#pragma unroll
-  for (int r = 0; r < kMaxN / 8; ++r) {
-    if (__any_sync(kFull, 8 * r < n)) {
-      const int node = sl + 8 * r;
-      const unsigned bal = __ballot_sync(kFull, node < n && sx[node * kF + lut_col] == 1.0f);
-      const unsigned sub = (bal >> (8 * sg)) & 0xffu;
-      if (sub) {
-        if (il < 0) il = 8 * r + __ffs(sub) - 1;
-        cnt += __popc(sub);
-      }
-    }
-  }
-  bool ok = fits && cnt == 1 && (l1 - l0) == 1;      // fast row: exactly one LUT node, as lut_ptr says
-  if (fits && sl == 0 && cnt != l1 - l0) atomicOr(status, 1);   // lut_ptr does not describe this x
-
-  // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph
-  int* msg = sm.msg[gl];
-  int mc = 0;
-  {
-    const int c = ((ne + 7) >> 3) | 1;
-    const int cmax = __reduce_max_sync(kFull, ok ? c : 0);
-    const long long target = n0 + il;
-    const int eb = sl * c;
-    unsigned hm = 0u;
-#pragma unroll 4
-    for (int t = 0; t < cmax; ++t) {
-      const int e = eb + t;
-      const bool v = ok && t < c && e < ne;
-      long long d = 0;
-      if (v) d = sd[e];
-      hm |= ((v && d == target) ? 1u : 0u) << t;
-    }
-    const int h = __popc(hm);
-    int incl = h;
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-      const int up = __shfl_up_sync(kFull, incl, o, 8);
-      if (sl >= o) incl += up;
-    }
-    mc = __shfl_sync(kFull, incl, base + 7);
-    int pos = incl - h;
-    while (hm) {
-      const int t = __ffs(hm) - 1;
-      hm &= hm - 1u;
-      if (pos < kSubMsg - 1) msg[pos] = eb + t;
-      ++pos;
-    }
-  }
-  if (mc > kSubMsg - 1) ok = false;                  // hub row: generic path
-  __syncwarp();
-  // sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
-  {
-    int kept = 0;
-    bool outside = false;
-#pragma unroll
-    for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
-      if (__any_sync(kFull, ok && t0 < mc)) {
-        const int t = t0 + sl;
-        long long sj = -1;
-        if (ok && t < mc) sj = esrc[e0 + msg[t]];
-        const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
-        const long long sloc = sj - n0;
-        const bool inslab = sloc >= 0 && sloc < n;
-        const bool keep = inslab && sloc != il;
-        outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
-        const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
-        __syncwarp();
-        if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
-        kept += __popc(sub);
-        __syncwarp();
-      }
-    }
-    if (outside) ok = false;                          // a source outside the slab: generic path
-    mc = kept;
-  }
-  if (ok && sl == 0) msg[mc] = il;                    // the appended self loop comes last
-  ++mc;
-  __syncwarp();
-  LPB_TRACE(3);
-
-  // ---- attention: lane = message slot, all 4 heads per lane; the 24 sums are reduce-scattered so that
-  // lane sl ends with sums 3*sl .. 3*sl+2 of [h][x0..x4, p] -- its own head is sl >> 1
-  {
-    float d[kHeads];
-    const int ils = ok ? il : 0;
-#pragma unroll
-    for (int h = 0; h < kHeads; ++h) d[h] = 0.f;
-#pragma unroll
-    for (int k = 0; k < kF; ++k) {
-      const float xi = sx[ils * kF + k];
-#pragma unroll
-      for (int h = 0; h < kHeads; ++h) d[h] = fmaf(xi, Ad[k][h], d[h]);
-    }
-    float mx[kHeads], acc3[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int h = 0; h < kHeads; ++h) mx[h] = -INFINITY;
-    const int hown = sl >> 1;
-#pragma unroll
-    for (int r0 = 0; r0 < kSubMsg; r0 += 8) {
-      if (__any_sync(kFull, ok && r0 < mc)) {
-        const bool valid = ok && r0 + sl < mc;
-        const int j = valid ? msg[r0 + sl] : 0;
-        float xj[kF];
-#pragma unroll
-        for (int k = 0; k < kF; ++k) xj[k] = sx[j * kF + k];
-        float v[24];
-        float scarg = 0.f;
-#pragma unroll
-        for (int h = 0; h < kHeads; ++h) {
-          float a = d[h];
-#pragma unroll
-          for (int k = 0; k < kF; ++k) a = fmaf(xj[k], As[k][h], a);
-          a = a > 0.f ? a : 0.2f * a;
-          if (!valid) a = -INFINITY;
-          float mr = a;
-#pragma unroll
-          for (int o = 1; o <= 4; o <<= 1) mr = fmaxf(mr, __shfl_xor_sync(kFull, mr, o));
-          const float mn = fmaxf(fmaxf(mx[h], mr), -1e30f);   // idle sub-groups stay finite
-          const float p = valid ? expf(a - mn) : 0.f;
-#pragma unroll
-          for (int k = 0; k < kF; ++k) v[h * 6 + k] = p * xj[k];
-          v[h * 6 + kF] = p;
-          if (h == hown) scarg = mx[h] - mn;                  // -inf in the first round: exp -> 0
-          mx[h] = mn;
-        }
-        float u[12], s6[6], w3[3];
-        {
-          const bool up = (sl & 4) != 0;
-#pragma unroll
-          for (int i = 0; i < 12; ++i) {
-            const float send = up ? v[i] : v[i + 12], keep = up ? v[i + 12] : v[i];
-            u[i] = keep + __shfl_xor_sync(kFull, send, 4);
-          }
-        }
-        {
-          const bool up = (sl & 2) != 0;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const float send = up ? u[i] : u[i + 6], keep = up ? u[i + 6] : u[i];
-            s6[i] = keep + __shfl_xor_sync(kFull, send, 2);
-          }
-        }
-        {
-          const bool up = (sl & 1) != 0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float send = up ? s6[i] : s6[i + 3], keep = up ? s6[i + 3] : s6[i];
-            w3[i] = keep + __shfl_xor_sync(kFull, send, 1);
-          }
-        }
-        const float sc = expf(scarg);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) acc3[i] = fmaf(acc3[i], sc, w3[i]);
-      }
-    }
-    // even lane: sums x0..x2 of head sl>>1; odd lane: x3, x4 and the softmax denominator
-    const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
-    const float inv = 1.0f / (((sl & 1) ? acc3[2] : den_other) + 1e-16f);
-    if (ok) {
-      float zv[3];
-      zv[0] = acc3[0] * inv;
-      zv[1] = acc3[1] * inv;
-      zv[2] = (sl & 1) ? 1.0f : acc3[2] * inv;        // slot 5 of the head row multiplies the shift row
-      const int zo = gl * kZStride + hown * 8 + ((sl & 1) ? 3 : 0);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float hi = __uint_as_float(tf32_rna(zv[i]));
-        sm.zhi[zo + i] = hi;
-        sm.zlo[zo + i] = __uint_as_float(tf32_rna(zv[i] - hi));
-      }
-      if (sl & 1) {
-        sm.zhi[zo + 3] = 0.f; sm.zhi[zo + 4] = 0.f;
-        sm.zlo[zo + 3] = 0.f; sm.zlo[zo + 4] = 0.f;
-      }
-    }
-  }
-  int my_state = 0;
-  LPB_TRACE(4);
-  if (sl == 0) {
-    SubMeta& mt = sm.meta[gl];
-    mt.n0 = n0; mt.n1 = n1; mt.e0 = e0; mt.e1 = e1; mt.l0 = l0; mt.l1 = l1;
-    mt.il = il;
-    // generic path: anything active that is not a finished fast row and may own LUT rows
-    my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
-    mt.state = my_state;
-  }
-  const int any_generic = __syncthreads_or(my_state == 2);   // z rows staged; the slab is dead from here
-  LPB_TRACE(5);
-
-  // ---- readout head on the tensor cores; warp w owns channels 16w .. 16w+15 (head w >> 1)
-  float* red = reinterpret_cast<float*>(sm.slab);
-  {
-    const int g8 = lane >> 2, t4 = lane & 3;
-    unsigned ahi[2][4], alo[2][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const int o = (16 * m + g8) * kZStride + (warp >> 1) * 8 + t4;
-      ahi[m][0] = __float_as_uint(sm.zhi[o]);
-      ahi[m][1] = __float_as_uint(sm.zhi[o + 8 * kZStride]);
-      ahi[m][2] = __float_as_uint(sm.zhi[o + 4]);
-      ahi[m][3] = __float_as_uint(sm.zhi[o + 8 * kZStride + 4]);
-      alo[m][0] = __float_as_uint(sm.zlo[o]);
-      alo[m][1] = __float_as_uint(sm.zlo[o + 8 * kZStride]);
-      alo[m][2] = __float_as_uint(sm.zlo[o + 4]);
-      alo[m][3] = __float_as_uint(sm.zlo[o + 8 * kZStride + 4]);
-    }
-    float H[2][4][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) H[m][q][i] = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = 2 * warp + jj;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + j * 32 + lane);
-      unsigned yhi[2][4], ylo[2][4];
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(c, alo[m], b.x, b.y);
-        mma_tf32(c, ahi[m], b.z, b.w);
-        mma_tf32(c, ahi[m], b.x, b.y);
-        // ReLU, split, and C -> A fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3)
-        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          yhi[m][i] = tf32_rna(y[i]);
-          ylo[m][i] = tf32_rna(y[i] - __uint_as_float(yhi[m][i]));
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(prep + kOffB2f) + (j * 4 + q) * 32 + lane);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_tf32(H[m][q], ylo[m], b2.x, b2.y);
-          mma_tf32(H[m][q], yhi[m], b2.z, b2.w);
-          mma_tf32(H[m][q], yhi[m], b2.x, b2.y);
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) red[(warp * 32 + (m * 4 + q) * 4 + i) * 32 + lane] = H[m][q][i];
-  }
-  __syncthreads();
-  LPB_TRACE(6);
-  // ---- warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp = (m-tile, row half)
-  if (warp < 4) {
-    const int g8 = lane >> 2, t4 = lane & 3, m = warp >> 1, upper = warp & 1;
-    float o3[QOT_OUT] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int o = 8 * q + 2 * t4;
-      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
-      float hv[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int reg = (m * 4 + q) * 4 + upper * 2 + p;
-        float h = 0.f;
-#pragma unroll
-        for (int pw = 0; pw < 8; ++pw) h += red[(pw * 32 + reg) * 32 + lane];
-        h += p ? b1.y : b1.x;
-        hv[p] = h > 0.f ? h : 0.01f * h;
-      }
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) {
-        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
-        o3[k] = fmaf(hv[0], w2.x, o3[k]);
-        o3[k] = fmaf(hv[1], w2.y, o3[k]);
-      }
-    }
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
-    }
-    const int r = 16 * m + 8 * upper + g8;            // graph slot of this row
-    const SubMeta& mt = sm.meta[r];
-    if (mt.state == 1) {
-      if (t4 < QOT_OUT) {
-        const float ov = (t4 == 0 ? o3[0] : t4 == 1 ? o3[1] : o3[2]) + __ldg(prep + kOffB2 + t4);
-        out[mt.l0 * QOT_OUT + t4] = ov;
-      } else {
-        lut_batch[mt.l0] = g0 + r;
-        lut_node[mt.l0] = static_cast<int32_t>(mt.n0 + mt.il);
-      }
-    }
-  }
-
-  // ---- generic path for the graphs the fast path declined (one warp per graph)
-  if (any_generic) {
-    __syncthreads();                                  // the partial products have been consumed
-    const float* __restrict__ wh = prep + kOffWf;
-    for (int gs = warp; gs < kGPB; gs += 8) {
-      if (sm.meta[gs].state != 2) continue;
-      const SubMeta mt = sm.meta[gs];
-      const int64_t gg = g0 + gs;
-      float* s_y = red + warp * 256;
-      float* s_z = s_y + kHC;
-      int* s_m = reinterpret_cast<int*>(s_y + kHC + 32);
-      int64_t orow = mt.l0;
-      int found = 0;
-      for (int64_t nb = mt.n0; nb < mt.n1; nb += 32) {
-        const int64_t node = nb + lane;
-        unsigned mask = __ballot_sync(kFull, node < mt.n1 && x[node * kF + lut_col] == 1.0f);
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          ++found;
-          if (orow < mt.l1) {                                      // never write past this graph's rows
-            const int64_t i = nb + bit;
-            const float ov = lut_row_global(x, esrc, edst, mt.e0, mt.e1, N, i, prep, wh, s_m, s_z, s_y, lane);
-            if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
-            if (lane == 0) {
-              lut_batch[orow] = gg;
-              lut_node[orow] = static_cast<int32_t>(i);
-            }
-            ++orow;
-          }
-        }
-      }
-      if (lane == 0 && found != mt.l1 - mt.l0) atomicOr(status, 1);
-    }
-  }
-  LPB_TRACE(7);
-  LPB_TRACE_FLUSH();
 }
 
 // =====================================================================================
@@ -1372,11 +927,14 @@ lp_infer_bulk_kernel(const float* __restrict__ x, const int64_t* __restrict__ es
 // =====================================================================================
 constexpr int kZRow = kHeads * kF;        // floats per z row in the workspace
 
-template <bool kXG>
+template <bool kXG, bool kFused>
 struct AttnSmem {
-  alignas(128) unsigned char slab[(kXG ? 0 : kBXBytes + 16) + kBDBytes + 16];   // [x window,] destination window
+  alignas(128) unsigned char slab[(kXG ? 0 : kBXBytes + 16) + kBDBytes + 16];   // [x window,] destination window; kFused: later the H partials
+  float zhi[kFused ? kGPB * kZStride : 4];   // kFused: attention rows stay on chip, already split for the tensor cores
+  float zlo[kFused ? kGPB * kZStride : 4];
+  SubMeta meta[kFused ? kGPB : 1];
   int msg[kGPB][kSubMsg];
-  float gen[8][128];                       // generic path scratch per warp: z (32 floats) + message list (64)
+  float gen[kFused ? 1 : 8][128];          // split form: generic path scratch per warp, z (32 floats) + message list (64)
   alignas(8) unsigned long long mbar;
 };
 
@@ -1385,17 +943,17 @@ struct AttnSmem {
 #ifndef QOT_LP_ATTN_OCC
 #define QOT_LP_ATTN_OCC 4                 // register budget: 64 per thread, so that lp_head_kernel blocks fit beside 3 resident blocks
 #endif
-template <bool kXG>
-__global__ void __launch_bounds__(256, QOT_LP_ATTN_OCC)
-lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
+template <bool kXG, bool kFused>
+__global__ void __launch_bounds__(256, kFused ? QOT_LP_BULK_OCC : QOT_LP_ATTN_OCC)
+lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   // static_assert below: 3 fused blocks per SM
                const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
                const int64_t* __restrict__ eptr, const int64_t* __restrict__ lptr, int64_t N,
                int64_t E, int64_t B, const float* __restrict__ prep, int lut_col,
-               float* __restrict__ zbuf, int64_t* __restrict__ lut_batch,
+               float* __restrict__ zbuf, float* __restrict__ out, int64_t* __restrict__ lut_batch,
                int32_t* __restrict__ lut_node, int32_t* __restrict__ n_lut,
                int32_t* __restrict__ status) {
   extern __shared__ __align__(128) char attn_smem_raw[];
-  AttnSmem<kXG>& sm = *reinterpret_cast<AttnSmem<kXG>*>(attn_smem_raw);
+  AttnSmem<kXG, kFused>& sm = *reinterpret_cast<AttnSmem<kXG, kFused>*>(attn_smem_raw);
   constexpr int kDOff = kXG ? 0 : kBDOff;
   LPB_TRACE_DECL;
   LPB_TRACE(0);
@@ -1647,10 +1205,28 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
     const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
     const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
     if (ok) {
-      float* zr = zbuf + l0 * kZRow + hx * kF + o0;
-      zr[0] = acc3[0] * inv;
-      zr[1] = acc3[1] * inv;
-      if (!odd) zr[2] = acc3[2] * inv;
+      if (kFused) {
+        float zv[3];
+        zv[0] = acc3[0] * inv;
+        zv[1] = acc3[1] * inv;
+        zv[2] = odd ? 1.0f : acc3[2] * inv;            // slot 5 of the head row multiplies the shift row
+        const int zo = gl * kZStride + hx * 8 + o0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float hi = __uint_as_float(tf32_rna(zv[i]));
+          sm.zhi[zo + i] = hi;
+          sm.zlo[zo + i] = __uint_as_float(tf32_rna(zv[i] - hi));
+        }
+        if (odd) {
+          sm.zhi[zo + 3] = 0.f; sm.zhi[zo + 4] = 0.f;
+          sm.zlo[zo + 3] = 0.f; sm.zlo[zo + 4] = 0.f;
+        }
+      } else {
+        float* zr = zbuf + l0 * kZRow + hx * kF + o0;
+        zr[0] = acc3[0] * inv;
+        zr[1] = acc3[1] * inv;
+        if (!odd) zr[2] = acc3[2] * inv;
+      }
       if (sl == 0) {
         lut_batch[l0] = g;
         lut_node[l0] = static_cast<int32_t>(n0 + il);
@@ -1659,8 +1235,160 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
   }
   LPB_TRACE(4);
 
-  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
   const int my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
+  if constexpr (kFused) {
+  if (sl == 0) {
+    SubMeta& mt = sm.meta[gl];
+    mt.n0 = n0; mt.n1 = n1; mt.e0 = e0; mt.e1 = e1; mt.l0 = l0; mt.l1 = l1;
+    mt.il = il;
+    mt.state = my_state;
+  }
+  const int any_generic = __syncthreads_or(sl == 0 && my_state == 2);   // z rows staged; the slab is dead from here
+  LPB_TRACE(5);
+
+  // ---- readout head on the tensor cores; warp w owns channels 16w .. 16w+15 (head w >> 1)
+  float* red = reinterpret_cast<float*>(sm.slab);
+  {
+    const int g8 = lane >> 2, t4 = lane & 3;
+    unsigned ahi[2][4], alo[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int o = (16 * m + g8) * kZStride + (warp >> 1) * 8 + t4;
+      ahi[m][0] = __float_as_uint(sm.zhi[o]);
+      ahi[m][1] = __float_as_uint(sm.zhi[o + 8 * kZStride]);
+      ahi[m][2] = __float_as_uint(sm.zhi[o + 4]);
+      ahi[m][3] = __float_as_uint(sm.zhi[o + 8 * kZStride + 4]);
+      alo[m][0] = __float_as_uint(sm.zlo[o]);
+      alo[m][1] = __float_as_uint(sm.zlo[o + 8 * kZStride]);
+      alo[m][2] = __float_as_uint(sm.zlo[o + 4]);
+      alo[m][3] = __float_as_uint(sm.zlo[o + 8 * kZStride + 4]);
+    }
+    float H[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) H[m][q][i] = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = 2 * warp + jj;
+      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + j * 32 + lane);
+      unsigned yhi[2][4], ylo[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_tf32(c, alo[m], b.x, b.y);
+        mma_tf32(c, ahi[m], b.z, b.w);
+        mma_tf32(c, ahi[m], b.x, b.y);
+        // ReLU, split, and C -> A fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3)
+        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          yhi[m][i] = tf32_rna(y[i]);
+          ylo[m][i] = tf32_rna(y[i] - __uint_as_float(yhi[m][i]));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b2 = __ldg(reinterpret_cast<const float4*>(prep + kOffB2f) + (j * 4 + q) * 32 + lane);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_tf32(H[m][q], ylo[m], b2.x, b2.y);
+          mma_tf32(H[m][q], yhi[m], b2.z, b2.w);
+          mma_tf32(H[m][q], yhi[m], b2.x, b2.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[(warp * 32 + (m * 4 + q) * 4 + i) * 32 + lane] = H[m][q][i];
+  }
+  __syncthreads();
+  LPB_TRACE(6);
+  // ---- warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp = (m-tile, row half)
+  if (warp < 4) {
+    const int g8 = lane >> 2, t4 = lane & 3, m = warp >> 1, upper = warp & 1;
+    float o3[QOT_OUT] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = 8 * q + 2 * t4;
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
+      float hv[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int reg = (m * 4 + q) * 4 + upper * 2 + p;
+        float h = 0.f;
+#pragma unroll
+        for (int pw = 0; pw < 8; ++pw) h += red[(pw * 32 + reg) * 32 + lane];
+        h += p ? b1.y : b1.x;
+        hv[p] = h > 0.f ? h : 0.01f * h;
+      }
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
+        o3[k] = fmaf(hv[0], w2.x, o3[k]);
+        o3[k] = fmaf(hv[1], w2.y, o3[k]);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
+    }
+    const int r = 16 * m + 8 * upper + g8;            // graph slot of this row
+    const SubMeta& mt = sm.meta[r];
+    if (mt.state == 1) {
+      if (t4 < QOT_OUT) {
+        const float ov = (t4 == 0 ? o3[0] : t4 == 1 ? o3[1] : o3[2]) + __ldg(prep + kOffB2 + t4);
+        out[mt.l0 * QOT_OUT + t4] = ov;
+      }
+    }
+  }
+
+  // ---- generic path for the graphs the fast path declined (one warp per graph)
+  if (any_generic) {
+    __syncthreads();                                  // the partial products have been consumed
+    const float* __restrict__ wh = prep + kOffWf;
+    for (int gs = warp; gs < kGPB; gs += 8) {
+      if (sm.meta[gs].state != 2) continue;
+      const SubMeta mt = sm.meta[gs];
+      const int64_t gg = g0 + gs;
+      float* s_y = red + warp * 256;
+      float* s_z = s_y + kHC;
+      int* s_m = reinterpret_cast<int*>(s_y + kHC + 32);
+      int64_t orow = mt.l0;
+      int found = 0;
+      for (int64_t nb = mt.n0; nb < mt.n1; nb += 32) {
+        const int64_t node = nb + lane;
+        unsigned mask = __ballot_sync(kFull, node < mt.n1 && x[node * kF + lut_col] == 1.0f);
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ++found;
+          if (orow < mt.l1) {                                      // never write past this graph's rows
+            const int64_t i = nb + bit;
+            const float ov = lut_row_global(x, esrc, edst, mt.e0, mt.e1, N, i, prep, wh, s_m, s_z, s_y, lane);
+            if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
+            if (lane == 0) {
+              lut_batch[orow] = gg;
+              lut_node[orow] = static_cast<int32_t>(i);
+            }
+            ++orow;
+          }
+        }
+      }
+      if (lane == 0 && found != mt.l1 - mt.l0) atomicOr(status, 1);
+    }
+  }
+  LPB_TRACE(7);
+  LPB_TRACE_FLUSH();
+  return;
+  }
+  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
   if (__any_sync(kFull, my_state == 2)) {
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
@@ -1709,7 +1437,6 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,
 // Accuracy: the tensor cores truncate when they add into a running accumulator, so the large
 // (hi x hi) terms are produced by stand-alone MMAs and added in fp32 on the CUDA cores; only the small
 // compensation terms (lo x hi + hi x lo) chain inside an accumulator.
-__global__ void lp_debug_empty_kernel(int32_t* p) { if (p == nullptr) printf("x"); }
 constexpr int kHeadFrag4 = (kOffAsP - kOffB1f) / 4;   // float4 entries of B1f | B2f (contiguous in `prepared`)
 __global__ void __launch_bounds__(128)
 lp_head_kernel(const float* __restrict__ zbuf, const int64_t* __restrict__ lptr, int64_t B,
@@ -1865,9 +1592,9 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
 }
 
 // 0: one warp per graph (lp_infer_kernel); 1: 8 lanes per graph (lp_infer_sub_kernel);
-// 2: 8 lanes per graph, bulk-copied slabs, tensor-core readout head (lp_infer_bulk_kernel);
-// 3: lp_attn_kernel (z rows into the workspace) + lp_head_kernel (tensor-core readout head)
-static int g_lp_variant = 3;
+// 2 (default): lp_attn_kernel<.., kFused = true>: 8 lanes per graph, bulk-copied slabs, tensor-core readout
+// head in the same launch; 3: lp_attn_kernel<.., false> (z rows into the workspace) + lp_head_kernel
+static int g_lp_variant = 2;
 extern "C" int qot_lightpath_set_variant(int v) {
   if (v < 0 || v > 3) return QOT_E_BADARG;
   g_lp_variant = v;
@@ -1875,8 +1602,13 @@ extern "C" int qot_lightpath_set_variant(int v) {
 }
 extern "C" int qot_lightpath_get_variant(void) { return g_lp_variant; }
 
-static int g_dbg_flags = 0;   // TEMP
-extern "C" int qot_debug_lp_flags(int f) { g_dbg_flags = f; return 0; }   // TEMP
+static_assert(3 * (sizeof(AttnSmem<false, true>) + 1024) <= 228 * 1024, "the fused kernel must keep 3 blocks per SM");
+static_assert(3 * (sizeof(AttnSmem<false, false>) + 1024) <= 228 * 1024, "the attention kernel must keep 3 blocks per SM");
+static_assert(sizeof(AttnSmem<true, true>::slab) >= 8 * 32 * 32 * 4, "slab is reused for the 8 partial [32x32] products");
+#ifndef QOT_LP_FUSED_XG
+#define QOT_LP_FUSED_XG 0                 // 1: the fused kernel reads node features from global memory (4 blocks per SM)
+#endif
+constexpr bool kFusedXG = QOT_LP_FUSED_XG != 0;
 static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* edst,
                            const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr, int64_t N,
                            int64_t E, int64_t B, const float* prepared, int32_t is_lut_index, float* out,
@@ -1885,49 +1617,35 @@ static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* e
   if (g_lp_variant == 3) {
     static bool attr_set = false;
     if (!attr_set) {
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(AttnSmem<false>))));
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sizeof(AttnSmem<false, false>))));
       // the head kernel uses no shared memory, but it runs between attention kernels that need the
       // largest carve-out: asking for the same split keeps the SMs from reconfiguring (and draining)
-      if (!getenv("QOT_LP_NO_CARVEOUT"))
-        QOT_CUDA(cudaFuncSetAttribute(lp_head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
+      QOT_CUDA(cudaFuncSetAttribute(lp_head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
       attr_set = true;
     }
     const int64_t blocks = cdiv(B, kGPB);
-    const bool skip_attn = getenv("QOT_LP_DEBUG_SKIP_ATTN") != nullptr || (g_dbg_flags & 1);   // TEMP experiment switch
-    static const bool xg = getenv("QOT_LP_DEBUG_XG") != nullptr;   // TEMP experiment switch
-    if (skip_attn) {
-    } else if (xg) {
-      static const size_t xg_smem = getenv("QOT_LP_DEBUG_XG_SMEM") ? static_cast<size_t>(atoi(getenv("QOT_LP_DEBUG_XG_SMEM"))) : sizeof(AttnSmem<true>);   // TEMP
-      lp_attn_kernel<true><<<static_cast<unsigned>(blocks), 256, xg_smem, stream>>>(
-          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, lut_batch, lut_node, n_lut, status);
-    } else {
-      lp_attn_kernel<false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false>), stream>>>(
-          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, lut_batch, lut_node, n_lut, status);
-    }
+    lp_attn_kernel<false, false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false, false>), stream>>>(
+        x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, out, lut_batch, lut_node, n_lut, status);
     QOT_LAUNCH_CHECK();
     // one block per 64 rows; L is only known on the device: the grid covers the common case (about one
     // LUT row per graph) and the blocks stride over any further tiles
     const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(std::min(N, B), 64), 4 * kNumSMs));
-    const bool skip_head = getenv("QOT_LP_DEBUG_SKIP_HEAD") != nullptr || (g_dbg_flags & 2);   // TEMP experiment switch
-    static const bool empty_head = getenv("QOT_LP_DEBUG_EMPTY_HEAD") != nullptr;   // TEMP experiment switch
-    if (empty_head) lp_debug_empty_kernel<<<1, 32, 0, stream>>>(n_lut);
-    else if (!skip_head) lp_head_kernel<<<static_cast<unsigned>(hb), 128, 0, stream>>>(zbuf, lut_ptr, B, prepared, out);
+    lp_head_kernel<<<static_cast<unsigned>(hb), 128, 0, stream>>>(zbuf, lut_ptr, B, prepared, out);
     QOT_LAUNCH_CHECK();
     return QOT_OK;
   }
   if (g_lp_variant == 2) {
     static bool attr_set = false;
     if (!attr_set) {
-      QOT_CUDA(cudaFuncSetAttribute(lp_infer_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(BulkSmem))));
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<kFusedXG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sizeof(AttnSmem<kFusedXG, true>))));
       attr_set = true;
     }
     const int64_t blocks = cdiv(B, kGPB);
-    lp_infer_bulk_kernel<<<static_cast<unsigned>(blocks), 256, sizeof(BulkSmem), stream>>>(
-        x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, out, lut_batch, lut_node, n_lut, status);
+    lp_attn_kernel<kFusedXG, true><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<kFusedXG, true>), stream>>>(
+        x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, nullptr, out, lut_batch, lut_node, n_lut, status);
     QOT_LAUNCH_CHECK();
     return QOT_OK;
   }
