@@ -943,7 +943,7 @@ struct AttnSmem {
 #ifndef QOT_LP_ATTN_OCC
 #define QOT_LP_ATTN_OCC 4                 // register budget: 64 per thread, so that lp_head_kernel blocks fit beside 3 resident blocks
 #endif
-template <bool kXG, bool kFused>
+template <bool kXG, bool kFused, bool kTC = true>
 __global__ void __launch_bounds__(256, kFused ? QOT_LP_BULK_OCC : QOT_LP_ATTN_OCC)
 lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   // static_assert below: 3 fused blocks per SM
                const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
@@ -1213,11 +1213,11 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
         const int zo = gl * kZStride + hx * 8 + o0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const float hi = __uint_as_float(tf32_rna(zv[i]));
+          const float hi = kTC ? __uint_as_float(tf32_rna(zv[i])) : zv[i];
           sm.zhi[zo + i] = hi;
-          sm.zlo[zo + i] = __uint_as_float(tf32_rna(zv[i] - hi));
+          if (kTC) sm.zlo[zo + i] = __uint_as_float(tf32_rna(zv[i] - hi));
         }
-        if (odd) {
+        if (kTC && odd) {
           sm.zhi[zo + 3] = 0.f; sm.zhi[zo + 4] = 0.f;
           sm.zlo[zo + 3] = 0.f; sm.zlo[zo + 4] = 0.f;
         }
@@ -1246,8 +1246,83 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
   const int any_generic = __syncthreads_or(sl == 0 && my_state == 2);   // z rows staged; the slab is dead from here
   LPB_TRACE(5);
 
-  // ---- readout head on the tensor cores; warp w owns channels 16w .. 16w+15 (head w >> 1)
-  float* red = reinterpret_cast<float*>(sm.slab);
+  // ---- readout head.  kTC: on the tensor cores (mma.sync TF32 x3), warp w owns channels 16w .. 16w+15.
+  // !kTC: the same decomposition on the FP32 pipe -- exact fp32 arithmetic, and on this part (the
+  // legacy mma.sync path of sm_100 issues one m16n8k8 TF32 MMA per ~20 cycles per scheduler and holds
+  // the issue port meanwhile) also the faster of the two: measured in profiles/r1_summary.md
+  float* red = reinterpret_cast<float*>(sm.slab) + (kTC ? 0 : kHC * kZStride);
+  if constexpr (!kTC) {
+    float* ybuf = reinterpret_cast<float*>(sm.slab);          // y[c][row], row stride kZStride (16-byte aligned quads)
+    {
+      // y = relu(z_h Wf_h + shift): lane = (channel 16w + (lane & 15), 16 of the 32 rows)
+      const int c = 16 * warp + (lane & 15), hh = warp >> 1, rh = lane >> 4;
+      const float* __restrict__ wf = prep + kOffWf + hh * kF * kC + (c & 31);
+      const float w0 = __ldg(wf), w1 = __ldg(wf + kC), w2 = __ldg(wf + 2 * kC), w3 = __ldg(wf + 3 * kC),
+                  w4 = __ldg(wf + 4 * kC), sh = __ldg(prep + kOffShift + c);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = 16 * rh + i;
+        const float4 z4 = *reinterpret_cast<const float4*>(sm.zhi + r * kZStride + hh * 8);
+        const float z5 = sm.zhi[r * kZStride + hh * 8 + 4];
+        float y = sh;
+        y = fmaf(z4.x, w0, y); y = fmaf(z4.y, w1, y); y = fmaf(z4.z, w2, y); y = fmaf(z4.w, w3, y);
+        y = fmaf(z5, w4, y);
+        ybuf[c * kZStride + r] = fmaxf(y, 0.f);
+      }
+    }
+    __syncwarp();                                       // a warp consumes exactly the channels it produced
+    {
+      // partial h = y W1^T over the warp's 16 channels: lane tile = rows 4rq..4rq+3 x units 8uq..8uq+7
+      const int rq = lane & 7, uq = lane >> 3;
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+      for (int kk = 0; kk < 16; ++kk) {
+        const int c = 16 * warp + kk;
+        const float4 y4 = *reinterpret_cast<const float4*>(ybuf + c * kZStride + 4 * rq);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(prep + kOffW1t + c * kHid + 8 * uq));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(prep + kOffW1t + c * kHid + 8 * uq + 4));
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(yv[i], wv[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(warp * 32 + i * 8 + j) * 32 + lane] = acc[i][j];
+    }
+    __syncthreads();
+    LPB_TRACE(6);
+    // warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp w finishes rows 4rq + w
+    if (warp < 4) {
+      const int rq = lane & 7, uq = lane >> 3;
+      float o3[QOT_OUT] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float h = 0.f;
+#pragma unroll
+        for (int pw = 0; pw < 8; ++pw) h += red[(pw * 32 + warp * 8 + j) * 32 + lane];
+        h += __ldg(prep + kOffB1 + 8 * uq + j);
+        h = h > 0.f ? h : 0.01f * h;
+#pragma unroll
+        for (int k = 0; k < QOT_OUT; ++k) o3[k] = fmaf(h, __ldg(prep + kOffW2 + k * kHid + 8 * uq + j), o3[k]);
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
+      }
+      const SubMeta& mt = sm.meta[4 * rq + warp];
+      if (mt.state == 1 && uq < QOT_OUT)
+        out[mt.l0 * QOT_OUT + uq] = (uq == 0 ? o3[0] : uq == 1 ? o3[1] : o3[2]) + __ldg(prep + kOffB2 + uq);
+    }
+  } else {
   {
     const int g8 = lane >> 2, t4 = lane & 3;
     unsigned ahi[2][4], alo[2][4];
@@ -1347,6 +1422,8 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
         out[mt.l0 * QOT_OUT + t4] = ov;
       }
     }
+  }
+
   }
 
   // ---- generic path for the graphs the fast path declined (one warp per graph)
@@ -1596,7 +1673,7 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
 // head in the same launch; 3: lp_attn_kernel<.., false> (z rows into the workspace) + lp_head_kernel
 static int g_lp_variant = 2;
 extern "C" int qot_lightpath_set_variant(int v) {
-  if (v < 0 || v > 3) return QOT_E_BADARG;
+  if (v < 0 || v > 4) return QOT_E_BADARG;
   g_lp_variant = v;
   return QOT_OK;
 }
@@ -1605,6 +1682,7 @@ extern "C" int qot_lightpath_get_variant(void) { return g_lp_variant; }
 static_assert(3 * (sizeof(AttnSmem<false, true>) + 1024) <= 228 * 1024, "the fused kernel must keep 3 blocks per SM");
 static_assert(3 * (sizeof(AttnSmem<false, false>) + 1024) <= 228 * 1024, "the attention kernel must keep 3 blocks per SM");
 static_assert(sizeof(AttnSmem<true, true>::slab) >= 8 * 32 * 32 * 4, "slab is reused for the 8 partial [32x32] products");
+static_assert(sizeof(AttnSmem<false, true>::slab) >= (kHC * kZStride + 8 * 32 * 32) * 4, "slab is reused for y and the partial products");
 #ifndef QOT_LP_FUSED_XG
 #define QOT_LP_FUSED_XG 0                 // 1: the fused kernel reads node features from global memory (4 blocks per SM)
 #endif
@@ -1636,15 +1714,21 @@ static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* e
     QOT_LAUNCH_CHECK();
     return QOT_OK;
   }
-  if (g_lp_variant == 2) {
+  if (g_lp_variant == 2 || g_lp_variant == 4) {
     static bool attr_set = false;
     if (!attr_set) {
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<kFusedXG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<kFusedXG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(sizeof(AttnSmem<kFusedXG, true>))));
+      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sizeof(AttnSmem<false, true>))));
       attr_set = true;
     }
     const int64_t blocks = cdiv(B, kGPB);
-    lp_attn_kernel<kFusedXG, true><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<kFusedXG, true>), stream>>>(
+    if (g_lp_variant == 4)
+      lp_attn_kernel<false, true, false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false, true>), stream>>>(
+          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, nullptr, out, lut_batch, lut_node, n_lut, status);
+    else
+    lp_attn_kernel<kFusedXG, true, true><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<kFusedXG, true>), stream>>>(
         x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, nullptr, out, lut_batch, lut_node, n_lut, status);
     QOT_LAUNCH_CHECK();
     return QOT_OK;

@@ -22,8 +22,9 @@ from ..nn import BatchNorm, GATConv
 class LightpathGNN(torch.nn.Module):
     # kernels behind qot_lightpath_infer per qot_lightpath_set_variant() value (bench.py counts
     # launches and names the dominant kernel with these)
-    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_attn_kernel<fused head>", "lp_attn_kernel + lp_head_kernel")
-    _variant_launches = (1, 1, 1, 2)       # variant 3: lp_attn_kernel + lp_head_kernel
+    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_attn_kernel<fused, tensor-core head>",
+                        "lp_attn_kernel + lp_head_kernel", "lp_attn_kernel<fused, fp32 head>")
+    _variant_launches = (1, 1, 1, 2, 1)    # variant 3: lp_attn_kernel + lp_head_kernel
 
     @property
     def launches_per_step(self):

@@ -259,19 +259,19 @@ def test_kernel_variants_agree(cuda):
     prev = L.qot_lightpath_get_variant()
     try:
         res = {}
-        for v in (0, 1, 2, 3):
+        for v in (0, 1, 2, 3, 4):
             assert L.qot_lightpath_set_variant(v) == 0 and L.qot_lightpath_get_variant() == v
             with torch.no_grad():
                 o, l = m(b)
             res[v] = (o.clone(), l.clone())
-        assert L.qot_lightpath_set_variant(7) != 0
+        assert L.qot_lightpath_set_variant(7) != 0 and L.qot_lightpath_set_variant(-1) != 0
     finally:
         L.qot_lightpath_set_variant(prev)
     with torch.no_grad():
         eo, el = _oracle(sd, torch.float64)(_to64(hb))
-    for v in (0, 1, 2, 3):
-        assert torch.equal(res[v][1], res[3][1])
-        assert rel_err(res[v][0], res[3][0]) <= RTOL
+    for v in (0, 1, 2, 3, 4):
+        assert torch.equal(res[v][1], res[4][1])
+        assert rel_err(res[v][0], res[4][0]) <= RTOL
         assert torch.equal(res[v][1].cpu(), el) and rel_err(res[v][0], eo) <= RTOL
 
 
