@@ -12,10 +12,10 @@ for r in rows[1:]:
         d[r[ki]].append(float(r[vi].replace(",", "")))
     except ValueError:
         pass
-ours = {k: v for k, v in d.items() if k.startswith("qot::")}
+ours = {k: v for k, v in d.items() if "qot::" in k}
 tot_all = sum(sum(v) for v in d.values()); tot_ours = sum(sum(v) for v in ours.values())
 out.append(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)\n")
-out.append(f"command: python bench.py --steps 490 --warmup 5 --no-e2e --no-cpu-baseline (default: 4 graph branches)  ({len(rows)-1} launches captured)\n")
+out.append(f"command: python bench.py --steps 490 --warmup 5 --no-e2e --no-cpu-baseline (default: 8 graph branches)  ({len(rows)-1} launches captured)\n")
 out.append("| kernel | launches | mean us | total us | share of all | share of qot:: kernels |\n|---|---:|---:|---:|---:|---:|")
 for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
     name = k.split("(")[0][:70]
@@ -23,7 +23,7 @@ for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
     out.append(f"| `{name}` | {len(v)} | {sum(v)/len(v)/1e3:.2f} | {sum(v)/1e3:.1f} | {sum(v)/tot_all*100:.1f}% | {so} |")
 out.append("\nThe setup kernels (torch generators / sort / index ops that build the synthetic shard, `collate_kernel`, "
            "`lp_count_kernel`+`scan_kernel`+`widen_i32_kernel` that build lut_ptr at collate time) run before the timed region; "
-           "inside the timed region a step is exactly one `lp_infer_sub_kernel` launch, so its share of the step is 100%.\n")
+           "inside the timed region a step is exactly one `lp_attn_kernel<false, true, true>` launch (the fused kernel), so its share of the step is 100%.\n")
 # ---- full capture of the dominant kernel
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(raw))); h, u = r[0], r[1]
@@ -33,7 +33,7 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__block_size", "launch__grid_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
         "sm__inst_executed.avg.per_cycle_elapsed", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-out.append(f"# {tag}: ncu --set full of the dominant kernel (lp_infer_sub_kernel) ({len(r)-2} launches)\n\n| metric | unit | per launch |\n|---|---|---|")
+out.append(f"# {tag}: ncu --set full of the dominant kernel (lp_attn_kernel<false, true, true>: attention + tensor-core head in one launch) ({len(r)-2} launches)\n\n| metric | unit | per launch |\n|---|---|---|")
 for k in keys:
     if k in h:
         i = h.index(k)
