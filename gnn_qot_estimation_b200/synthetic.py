@@ -124,3 +124,61 @@ def random_topology_store(num_nodes: int = 10000, num_links: int = 40000, seed: 
     edge_ptr = torch.tensor([0, src.numel()], dtype=torch.int64)
     y = torch.rand(1, 3, generator=gen)
     return PackedGraphStore(node_ptr, edge_ptr, src.to(torch.int32), dst.to(torch.int32), None, ea, y).to(device)
+
+
+# --------------------------------------------------------------------------------------------- #
+# raw "network status" samples: the input of to_graph.py (the HHI .nc dataset is not shipped)
+# --------------------------------------------------------------------------------------------- #
+LP_FEAT = ["conn_id", "src_id", "dst_id", "mod_order", "path_len", "num_spans", "freq", "osnr", "snr", "ber"]
+METRICS = ["osnr", "snr", "ber", "class"]
+
+
+def network_status_samples(num_samples: int, num_links: int = 40, num_freqs: int = 64, seed: int = 0,
+                           spacing: float = 0.0375, max_lightpaths: int = 48, super_channel_p: float = 0.1):
+    """Seeded stand-in for ``dataset["data"]`` of to_graph.py:124-129: a float32 array
+    ``[sample, lp_feat, link, freq]`` that is zero on free channels and carries the lightpath's
+    feature vector on every (link, frequency) channel it occupies, plus ``target [sample, 4]``,
+    the frequency grid ``freqs [num_freqs]`` (float64, 192.2 + k*spacing) and the name lists.
+    Every sample holds 8..max_lightpaths lightpaths routed over 1..6 random links with one
+    frequency slot each (a few take two adjacent slots: super-channels, which to_graph.py turns
+    into self loops); the last lightpath placed is the LUT (osnr = snr = ber = -1)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    F = len(LP_FEAT)
+    fi = {k: i for i, k in enumerate(LP_FEAT)}
+    freqs = 192.2 + spacing * np.arange(num_freqs, dtype=np.float64)
+    data = np.zeros((num_samples, F, num_links, num_freqs), dtype=np.float32)
+    target = np.zeros((num_samples, len(METRICS)), dtype=np.float64)
+    for s in range(num_samples):
+        n_lp = int(rng.integers(8, max_lightpaths + 1))
+        free = np.ones((num_links, num_freqs), dtype=bool)
+        conn_ids = rng.permutation(np.arange(1, 4 * max_lightpaths))[:n_lp]
+        placed = 0
+        for k in range(n_lp):
+            width = 2 if rng.random() < super_channel_p else 1
+            links = rng.choice(num_links, size=int(rng.integers(1, 7)), replace=False)
+            ok_q = [q for q in range(num_freqs - width + 1) if all(free[l, q:q + width].all() for l in links)]
+            if not ok_q:
+                continue
+            q0 = int(rng.choice(ok_q))
+            vec = np.zeros(F, dtype=np.float32)
+            vec[fi["conn_id"]] = conn_ids[k]
+            vec[fi["src_id"]], vec[fi["dst_id"]] = rng.choice(np.arange(1, 76), 2, replace=False)
+            vec[fi["mod_order"]] = rng.choice([4, 8, 16, 32, 64])
+            vec[fi["path_len"]] = int(rng.integers(24214, 7834746))
+            vec[fi["num_spans"]] = int(rng.integers(1, 107))
+            vec[fi["osnr"]], vec[fi["snr"]], vec[fi["ber"]] = rng.uniform(13, 33), rng.uniform(9, 29), rng.uniform(1e-11, 1e-2)
+            for l in links:
+                for q in range(q0, q0 + width):
+                    v = vec.copy()
+                    v[fi["freq"]] = freqs[q]
+                    data[s, :, l, q] = v
+                    free[l, q] = False
+            placed += 1
+            last = (links, q0, width)
+        links, q0, width = last                       # the LUT: metrics unknown (-1), to be predicted
+        for l in links:
+            for q in range(q0, q0 + width):
+                data[s, fi["osnr"], l, q] = data[s, fi["snr"], l, q] = data[s, fi["ber"], l, q] = -1.0
+        target[s] = [rng.uniform(12.47, 33.49), rng.uniform(8.96, 29.98), rng.uniform(1.7e-12, 1.98e-2), rng.integers(0, 3)]
+    return {"data": data, "target": target, "freqs": freqs, "lp_feat": list(LP_FEAT), "metric": list(METRICS)}

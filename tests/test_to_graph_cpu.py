@@ -1,0 +1,58 @@
+"""SURVEY 8(f)4 -- graph construction (to_graph.py::create_lightpath_graph + LightpathDataset tensorisation).
+CPU side: the numpy restatement under oracle/ against golden vectors produced by the REFERENCE's own code
+(tests/golden/make_to_graph_golden.py); in the build container also against the reference itself on fresh seeds."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+REF = Path(os.environ.get("QOT_REFERENCE", "/root/reference"))
+
+
+def _oracle_all(samples):
+    from oracle import lightpath_data_ref
+    return [lightpath_data_ref(samples["data"][i], samples["target"][i], samples["freqs"], samples["lp_feat"], samples["metric"])
+            for i in range(samples["data"].shape[0])]
+
+
+def test_oracle_matches_reference_golden_vectors():
+    from gnn_qot_estimation_b200 import synthetic
+    gold = load_golden("to_graph_lightpath.pt")
+    total_edges = loops = 0
+    for (S, L, Q, seed, spacing), res in zip(gold["cases"], gold["results"]):
+        samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing)
+        assert float(np.abs(samples["data"]).sum(dtype=np.float64)) == res["input_checksum"]   # same inputs as the generator saw
+        for (conn, x, y, ei), g in zip(_oracle_all(samples), res["graphs"]):
+            assert np.array_equal(conn, g["conn_ids"].numpy())                 # node order
+            assert np.array_equal(x, g["x"].numpy())                           # bit-exact features
+            assert np.array_equal(y, g["y"].numpy())
+            assert np.array_equal(ei, g["edge_index_sorted"].numpy())          # edge set
+            assert int((x[:, 1] == 1.0).sum()) == 1                            # one LUT lightpath
+            total_edges += ei.shape[1]
+            loops += int((ei[0] == ei[1]).sum())
+    assert total_edges > 200 and loops > 10                                     # the fixtures do exercise the join
+
+
+@pytest.mark.skipif(not (REF / "to_graph.py").exists(), reason="reference checkout not present")
+@pytest.mark.parametrize("seed,spacing", [(11, 0.0375), (12, 0.05), (13, 0.025)])
+def test_oracle_matches_reference_code_on_fresh_seeds(seed, spacing):
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    try:
+        import make_to_graph_golden as mk
+    finally:
+        sys.path.pop(0)
+    from gnn_qot_estimation_b200 import synthetic
+    samples = synthetic.network_status_samples(3, 9, 40, seed=seed, spacing=spacing)
+    graphs = mk.reference_graphs(samples)
+    datas, _ = mk.reference_data_objects(graphs)
+    for (conn, x, y, ei), g, d in zip(_oracle_all(samples), graphs, datas):
+        c = mk.canonical(g, d)
+        assert np.array_equal(conn, c["conn_ids"].numpy()) and np.array_equal(x, c["x"].numpy())
+        assert np.array_equal(y, c["y"].numpy()) and np.array_equal(ei, c["edge_index_sorted"].numpy())
+    for k in [k for k in sys.modules if k.split(".")[0] == "torch_geometric"]:
+        del sys.modules[k]
