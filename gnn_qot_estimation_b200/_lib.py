@@ -28,6 +28,14 @@ class QotStore(C.Structure):
                 ("node_dim", i32), ("edge_dim", i32), ("y_dim", i32)]
 
 
+class QotLpGraphCfg(C.Structure):
+    _fields_ = [("F", i32), ("L", i32), ("Q", i32), ("T", i32),
+                ("i_conn", i32), ("i_osnr", i32), ("i_snr", i32), ("i_ber", i32),
+                ("i_feat", i32 * 4), ("feat_lo", C.c_double * 4), ("feat_hi", C.c_double * 4),
+                ("i_tgt", i32 * 3), ("tgt_lo", C.c_double * 3), ("tgt_hi", C.c_double * 3),
+                ("freq_threshold", C.c_double)]
+
+
 class QotLightpathParams(C.Structure):
     _fields_ = [("lin_w", P), ("att_src", P), ("att_dst", P), ("conv_bias", P),
                 ("bn_w", P), ("bn_b", P), ("bn_mean", P), ("bn_var", P),
@@ -79,6 +87,8 @@ SIGNATURES = {
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer_workspace_bytes": (sz, [i64]),
     "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, P, sz, vp]),
+    "qot_lightpath_graph_count": (C.c_int, [P, P, i64, C.POINTER(QotLpGraphCfg), P, P, vp]),
+    "qot_lightpath_graph_fill": (C.c_int, [P, P, P, i64, C.POINTER(QotLpGraphCfg), P, P, P, P, P, P, P, P, vp]),
     "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
     "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,

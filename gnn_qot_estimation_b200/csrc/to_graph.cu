@@ -1,0 +1,282 @@
+// Lightpath graph construction on the device: to_graph.py::create_lightpath_graph (:187-312) fused
+// with the tensorisation of lightpath_training/dataset.py:53-123.  One 256-thread block per sample;
+// everything between the raw [lp_feat, link, freq] tensor and the packed graph store stays in shared
+// memory:
+//   1. row-major scan of the (link, freq) channels, occupied ones compacted IN ORDER (block scan);
+//   2. conn_id -> first occupied channel through a shared-memory hash table (atomicCAS claims a slot,
+//      atomicMin keeps the earliest channel), so node order = order of first appearance;
+//   3. node rows from the first channel (fp64 min-max scaling, then fp32 -- bit-exact with the
+//      Python floats of dataset.py:77-80);
+//   4. the 0 < |df| < threshold join per link over the link's contiguous run of entries, fp64 like
+//      numpy (to_graph.py:296-299), links used by one lightpath skipped (:285), edges as bits of an
+//      n x n adjacency matrix (set semantics of nx.Graph.add_edge for free);
+//   5. directed edges written sorted by (source, target) from the bit rows.
+// Integer / index work throughout: HBM-bound on the one read of the sample tensor (F*L*Q*4 bytes).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qot {
+
+constexpr int kTgThreads = 256;
+constexpr int kTgHash = 1024;                 // slots (>= 4 x QOT_TG_MAX_NODES), open addressing
+constexpr int kTgAdjWords = QOT_TG_MAX_NODES / 32;
+
+struct TgSmem {
+  int conn[QOT_TG_MAX_CHANNELS];              // conn_id of the k-th occupied channel (row-major order)
+  unsigned short link[QOT_TG_MAX_CHANNELS], freq[QOT_TG_MAX_CHANNELS], node[QOT_TG_MAX_CHANNELS];
+  int hkey[kTgHash], hmin[kTgHash], hnode[kTgHash];
+  int seg[QOT_TG_MAX_LINKS + 1];              // first entry of every link's run
+  unsigned adj[QOT_TG_MAX_NODES][kTgAdjWords];
+  int first[QOT_TG_MAX_NODES];                // entry index of each node's first channel
+  int scan[kTgThreads / 32];
+  int total, bad;
+};
+
+// exclusive prefix of `v` over the block (256 threads); *total = block sum.  Two barriers.
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += up;
+  }
+  __syncthreads();                              // previous use of warp_sums is over
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kTgThreads / 32; ++w) {
+    const int s = warp_sums[w];
+    if (w < warp) base += s;
+    tot += s;
+  }
+  *total = tot;
+  return base + incl - v;
+}
+__device__ __forceinline__ unsigned tg_hash(int c) { return (static_cast<unsigned>(c) * 2654435761u) >> 22; }
+
+template <bool kFill>
+__global__ void __launch_bounds__(kTgThreads)
+lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ freqs,
+                      const double* __restrict__ target, qot_lp_graph_cfg_t cfg, int32_t* __restrict__ counts,
+                      const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr,
+                      float* __restrict__ node_feat, int64_t* __restrict__ conn_ids,
+                      int32_t* __restrict__ edge_src, int32_t* __restrict__ edge_dst,
+                      float* __restrict__ y, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) char tg_smem_raw[];
+  TgSmem& sm = *reinterpret_cast<TgSmem*>(tg_smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  const int L = cfg.L, Q = cfg.Q, LQ = L * Q;
+  const float* __restrict__ d = data + s * static_cast<int64_t>(cfg.F) * LQ;
+  for (int i = tid; i < kTgHash; i += kTgThreads) { sm.hkey[i] = INT_MIN; sm.hmin[i] = INT_MAX; sm.hnode[i] = -1; }
+  for (int i = tid; i < QOT_TG_MAX_NODES * kTgAdjWords; i += kTgThreads) (&sm.adj[0][0])[i] = 0u;
+  for (int i = tid; i <= min(L, QOT_TG_MAX_LINKS); i += kTgThreads) sm.seg[i] = -1;
+  if (tid == 0) sm.bad = 0;
+  __syncthreads();
+
+  // ---- 1. occupied channels, compacted in row-major order (to_graph.py:229-232)
+  int K = 0;
+  for (int c0 = 0; c0 < LQ; c0 += kTgThreads) {
+    const int ch = c0 + tid;
+    bool occ = false;
+    if (ch < LQ)
+      for (int f = 0; f < cfg.F; ++f) occ |= d[static_cast<int64_t>(f) * LQ + ch] != 0.f;
+    int tot;
+    const int pos = K + block_excl_scan(occ ? 1 : 0, sm.scan, &tot);
+    if (occ) {
+      if (pos < QOT_TG_MAX_CHANNELS) {
+        sm.conn[pos] = static_cast<int>(d[static_cast<int64_t>(cfg.i_conn) * LQ + ch]);   // int(): toward zero (:243)
+        sm.link[pos] = static_cast<unsigned short>(ch / Q);
+        sm.freq[pos] = static_cast<unsigned short>(ch % Q);
+      } else {
+        sm.bad = 1;
+      }
+    }
+    K += tot;
+  }
+  __syncthreads();
+  bool bad = sm.bad != 0 || L > QOT_TG_MAX_LINKS || K > QOT_TG_MAX_CHANNELS;
+  if (bad) K = 0;
+
+  // ---- 2. conn_id -> earliest entry (dict insertion order of to_graph.py:245-268)
+  for (int k = tid; k < K; k += kTgThreads) {
+    const int c = sm.conn[k];
+    unsigned h = tg_hash(c);
+    bool placed = false;
+    for (int probe = 0; probe < kTgHash && !placed; ++probe, h = (h + 1) & (kTgHash - 1)) {
+      const int prev = atomicCAS(&sm.hkey[h], INT_MIN, c);
+      if (prev == INT_MIN || prev == c) {
+        atomicMin(&sm.hmin[h], k);
+        placed = true;
+      }
+    }
+    if (!placed || c == INT_MIN) sm.bad = 1;           // more distinct conn_ids than slots: over capacity
+  }
+  __syncthreads();
+  if (sm.bad) { bad = true; K = 0; }                   // (also keeps every lookup below finite)
+  // nodes in order of first appearance: rank of the "first" entries
+  int n = 0;
+  for (int k0 = 0; k0 < K; k0 += kTgThreads) {
+    const int k = k0 + tid;
+    bool is_first = false;
+    unsigned h = 0;
+    if (k < K) {
+      const int c = sm.conn[k];
+      h = tg_hash(c);
+      while (sm.hkey[h] != c) h = (h + 1) & (kTgHash - 1);
+      is_first = sm.hmin[h] == k;
+    }
+    int tot;
+    const int r = n + block_excl_scan(is_first ? 1 : 0, sm.scan, &tot);
+    if (is_first) {
+      if (r < QOT_TG_MAX_NODES) {
+        sm.hnode[h] = r;
+        sm.first[r] = k;
+      } else {
+        sm.bad = 1;
+      }
+    }
+    n += tot;
+  }
+  __syncthreads();
+  if (sm.bad || n > QOT_TG_MAX_NODES) { bad = true; n = 0; K = 0; }
+  for (int k = tid; k < K; k += kTgThreads) {
+    const int c = sm.conn[k];
+    unsigned h = tg_hash(c);
+    while (sm.hkey[h] != c) h = (h + 1) & (kTgHash - 1);
+    sm.node[k] = static_cast<unsigned short>(sm.hnode[h]);
+    if (k == 0 || sm.link[k - 1] != sm.link[k]) sm.seg[sm.link[k]] = k;       // start of the link's run
+  }
+  __syncthreads();
+
+  // ---- 4. interactions per link: entries of a link are contiguous and ordered by frequency index
+  for (int i = tid; i < K; i += kTgThreads) {
+    const int l = sm.link[i];
+    const int a = sm.seg[l];
+    int b = a;
+    while (b < K && sm.link[b] == l) ++b;                                   // runs are short (<= Q)
+    // links used by a single lightpath are skipped (to_graph.py:285-286)
+    bool two = false;
+    for (int j = a; j < b; ++j) two |= sm.node[j] != sm.node[a];
+    if (!two) continue;
+    const double fi = freqs[sm.freq[i]];
+    const int ni = sm.node[i];
+    for (int j = a; j < b; ++j) {
+      const double df = fabs(fi - freqs[sm.freq[j]]);                        // :296, float64 like numpy
+      if (df < cfg.freq_threshold && df > 0.0) atomicOr(&sm.adj[ni][sm.node[j] >> 5], 1u << (sm.node[j] & 31));
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. directed edges, sorted by (source, target): one adjacency row per thread
+  int deg = 0;
+  if (tid < n)
+    for (int w = 0; w < kTgAdjWords; ++w) deg += __popc(sm.adj[tid][w]);
+  int E;
+  const int e_off = block_excl_scan(deg, sm.scan, &E);
+  if (!kFill) {
+    if (tid == 0) {
+      counts[2 * s] = n;
+      counts[2 * s + 1] = E;
+      if (bad) atomicOr(status, 1);
+    }
+    return;
+  }
+  const int64_t n0 = node_ptr[s], e0 = edge_ptr[s];
+  if (node_ptr[s + 1] - n0 != n || edge_ptr[s + 1] - e0 != E) {            // offsets from another pass / another tensor
+    if (tid == 0) atomicOr(status, 2);
+    return;
+  }
+  if (tid < n) {
+    int64_t o = e0 + e_off;
+    for (int w = 0; w < kTgAdjWords; ++w) {
+      unsigned m = sm.adj[tid][w];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        edge_src[o] = tid;
+        edge_dst[o] = 32 * w + bit;
+        ++o;
+      }
+    }
+    // ---- 3. node row from the node's first channel (dataset.py:74-80; sorted-name column order)
+    const int k = sm.first[tid];
+    const int ch = sm.link[k] * Q + sm.freq[k];
+    const float osnr = d[static_cast<int64_t>(cfg.i_osnr) * LQ + ch], snr = d[static_cast<int64_t>(cfg.i_snr) * LQ + ch],
+                ber = d[static_cast<int64_t>(cfg.i_ber) * LQ + ch];
+    float* xr = node_feat + (n0 + tid) * 5;
+    constexpr int col[4] = {0, 2, 3, 4};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double v = static_cast<double>(d[static_cast<int64_t>(cfg.i_feat[q]) * LQ + ch]);
+      xr[col[q]] = static_cast<float>((v - cfg.feat_lo[q]) / (cfg.feat_hi[q] - cfg.feat_lo[q]));
+    }
+    xr[1] = (osnr == -1.f && snr == -1.f && ber == -1.f) ? 1.0f : 0.0f;   // to_graph.py:247-251
+    conn_ids[n0 + tid] = sm.conn[k];
+  }
+  if (tid < 3) {
+    const double v = target[s * cfg.T + cfg.i_tgt[tid]];
+    y[s * 3 + tid] = static_cast<float>((v - cfg.tgt_lo[tid]) / (cfg.tgt_hi[tid] - cfg.tgt_lo[tid]));   // dataset.py:111-121
+  }
+}
+
+static int tg_check(const float* data, const double* freqs, int64_t S, const qot_lp_graph_cfg_t* cfg, const char* who) {
+  QOT_REQUIRE(cfg && S >= 0, "%s: bad argument", who);
+  QOT_REQUIRE(S == 0 || (data && freqs), "%s: null input", who);
+  QOT_REQUIRE(cfg->F > 0 && cfg->L > 0 && cfg->Q > 0 && cfg->Q <= 65535 && cfg->L <= 65535 &&
+                  static_cast<int64_t>(cfg->L) * cfg->Q < (1ll << 30), "%s: bad tensor extents", who);
+  const int rows[8] = {cfg->i_conn, cfg->i_osnr, cfg->i_snr, cfg->i_ber, cfg->i_feat[0], cfg->i_feat[1], cfg->i_feat[2], cfg->i_feat[3]};
+  for (int r : rows) QOT_REQUIRE(r >= 0 && r < cfg->F, "%s: lp_feat row index out of range", who);
+  return QOT_OK;
+}
+static int tg_attr() {
+  static bool done = false;
+  if (!done) {
+    QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
+    QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
+    done = true;
+  }
+  return QOT_OK;
+}
+
+}  // namespace qot
+
+using namespace qot;
+
+extern "C" int qot_lightpath_graph_count(const float* data, const double* freqs, int64_t S,
+                                         const qot_lp_graph_cfg_t* cfg, int32_t* counts, int32_t* status,
+                                         void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tg_check(data, freqs, S, cfg, "qot_lightpath_graph_count");
+  if (rc) return rc;
+  QOT_REQUIRE(status && (S == 0 || counts), "qot_lightpath_graph_count: null output");
+  if (S == 0) return QOT_OK;
+  if ((rc = tg_attr())) return rc;
+  lp_graph_build_kernel<false><<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
+      data, freqs, nullptr, *cfg, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" int qot_lightpath_graph_fill(const float* data, const double* freqs, const double* target, int64_t S,
+                                        const qot_lp_graph_cfg_t* cfg, const int64_t* node_ptr,
+                                        const int64_t* edge_ptr, float* node_feat, int64_t* conn_ids,
+                                        int32_t* edge_src, int32_t* edge_dst, float* y, int32_t* status,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tg_check(data, freqs, S, cfg, "qot_lightpath_graph_fill");
+  if (rc) return rc;
+  QOT_REQUIRE(status && (S == 0 || (target && node_ptr && edge_ptr && node_feat && conn_ids && edge_src && edge_dst && y)),
+              "qot_lightpath_graph_fill: null argument");
+  QOT_REQUIRE(cfg->T > 0, "qot_lightpath_graph_fill: bad target extent");
+  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_lightpath_graph_fill: target column out of range");
+  if (S == 0) return QOT_OK;
+  if ((rc = tg_attr())) return rc;
+  lp_graph_build_kernel<true><<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
+      data, freqs, target, *cfg, nullptr, node_ptr, edge_ptr, node_feat, conn_ids, edge_src, edge_dst, y, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}

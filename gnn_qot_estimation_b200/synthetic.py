@@ -156,7 +156,7 @@ def network_status_samples(num_samples: int, num_links: int = 40, num_freqs: int
         placed = 0
         for k in range(n_lp):
             width = 2 if rng.random() < super_channel_p else 1
-            links = rng.choice(num_links, size=int(rng.integers(1, 7)), replace=False)
+            links = rng.choice(num_links, size=min(int(rng.integers(1, 7)), num_links), replace=False)
             ok_q = [q for q in range(num_freqs - width + 1) if all(free[l, q:q + width].all() for l in links)]
             if not ok_q:
                 continue

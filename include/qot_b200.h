@@ -415,6 +415,45 @@ int qot_bn_bwd_sparse(const float* h, const float* mean, const float* var, float
                       int64_t L, int64_t N, int64_t C, int batch_stats, float* dh,
                       float* d_bn_w, float* d_bn_b, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- graph construction on the device -----------------------------------------
+ * Replaces to_graph.py::create_lightpath_graph (to_graph.py:187-312: occupied-channel scan, one node
+ * per conn_id in order of first appearance, node features from that first channel, is_lut = osnr ==
+ * snr == ber == -1, interaction edges between lightpaths that share a link at 0 < |df| < threshold,
+ * links used by a single lightpath skipped) fused with the tensorisation of
+ * lightpath_training/dataset.py:53-123 (min-max scaling in fp64 then fp32, x columns in sorted-name
+ * order [freq, is_lut, mod_order, num_spans, path_len], y = scaled [osnr, snr, ber]).
+ * One thread block per sample; output is the packed graph store qot_collate consumes.
+ *   data    [S, F, L, Q] float32, 0 = free channel          freqs [Q] float64 (the dataset's grid)
+ *   target  [S, T] float64
+ * Two passes with the same arguments: qot_lightpath_graph_count fills counts [S,2] int32 = (nodes,
+ * directed edges) per sample; the caller scans them into node_ptr / edge_ptr [S+1] int64 and calls
+ * qot_lightpath_graph_fill, which writes node_feat [N_tot,5], conn_ids [N_tot] int64, edge_src /
+ * edge_dst [E_tot] int32 (graph-local, both directions of every interaction, a self loop once, sorted
+ * by (source, target) -- the reference's own edge ORDER follows CPython set iteration and is not part
+ * of the contract) and y [S,3].  status (int32[1], zeroed by the caller): bit 0 = a sample exceeds the
+ * per-block capacities (QOT_TG_MAX_CHANNELS occupied channels, QOT_TG_MAX_NODES lightpaths, L <=
+ * QOT_TG_MAX_LINKS); such a sample is reported with zero nodes. */
+#define QOT_TG_MAX_CHANNELS 6144
+#define QOT_TG_MAX_NODES 256
+#define QOT_TG_MAX_LINKS 1024
+typedef struct {
+  int32_t F, L, Q, T;              /* lp_feat, link, freq extents of `data`; columns of `target`          */
+  int32_t i_conn, i_osnr, i_snr, i_ber;   /* rows of the lp_feat axis                                    */
+  int32_t i_feat[4];               /* lp_feat rows of freq, mod_order, num_spans, path_len (x cols 0,2,3,4) */
+  double feat_lo[4], feat_hi[4];   /* constants.py FEATURE_RANGES in the same order                       */
+  int32_t i_tgt[3];                /* columns of `target` holding osnr, snr, ber                           */
+  double tgt_lo[3], tgt_hi[3];     /* constants.py TARGET_RANGES                                           */
+  double freq_threshold;           /* to_graph.py:188 (0.05)                                               */
+} qot_lp_graph_cfg_t;
+int qot_lightpath_graph_count(const float* data, const double* freqs, int64_t S,
+                              const qot_lp_graph_cfg_t* cfg, int32_t* counts, int32_t* status,
+                              void* stream);
+int qot_lightpath_graph_fill(const float* data, const double* freqs, const double* target, int64_t S,
+                             const qot_lp_graph_cfg_t* cfg, const int64_t* node_ptr,
+                             const int64_t* edge_ptr, float* node_feat, int64_t* conn_ids,
+                             int32_t* edge_src, int32_t* edge_dst, float* y, int32_t* status,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,90 @@
+"""GPU parity, SURVEY 8(f)4: csrc/to_graph.cu through gnn_qot_estimation_b200.to_graph.create_lightpath_graphs
+against (a) golden vectors made by the REFERENCE's own to_graph.py + LightpathDataset and (b) the numpy
+oracle on fresh seeds.  Bit-exact: node order, x, y, edge set."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(samples, dev):
+    from gnn_qot_estimation_b200.to_graph import create_lightpath_graphs
+    return create_lightpath_graphs(torch.from_numpy(samples["data"]).to(dev), torch.from_numpy(samples["target"]),
+                                   torch.from_numpy(samples["freqs"]), samples["lp_feat"], samples["metric"],
+                                   return_conn_ids=True)
+
+
+def _graph(store, conn, i):
+    n0, n1 = int(store.node_ptr[i]), int(store.node_ptr[i + 1])
+    e0, e1 = int(store.edge_ptr[i]), int(store.edge_ptr[i + 1])
+    ei = torch.stack([store.edge_src[e0:e1], store.edge_dst[e0:e1]]).to(torch.int64).cpu()
+    return conn[n0:n1].cpu(), store.node_feat[n0:n1].cpu(), store.y[i:i + 1].cpu(), ei
+
+
+def test_matches_reference_golden_vectors(cuda):
+    from gnn_qot_estimation_b200 import synthetic
+    gold = load_golden("to_graph_lightpath.pt")
+    for (S, L, Q, seed, spacing), res in zip(gold["cases"], gold["results"]):
+        samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing)
+        store, conn = _build(samples, cuda)
+        assert store.num_graphs == S
+        for i, g in enumerate(res["graphs"]):
+            c, x, y, ei = _graph(store, conn, i)
+            assert torch.equal(c, g["conn_ids"])                           # node order = first appearance
+            assert torch.equal(x, g["x"]) and torch.equal(y, g["y"])       # bit-exact (fp64 scaling, then fp32)
+            assert torch.equal(ei, g["edge_index_sorted"])                 # edge set, incl. self loops and the 0.05 boundary
+
+
+@pytest.mark.parametrize("S,L,Q,seed,spacing", [(64, 16, 80, 5, 0.0375), (7, 3, 17, 6, 0.05), (5, 120, 96, 7, 0.01)])
+def test_matches_oracle_on_fresh_seeds(cuda, S, L, Q, seed, spacing):
+    from gnn_qot_estimation_b200 import synthetic
+    from oracle import lightpath_data_ref
+    samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing)
+    samples["data"][S // 2] = 0.0                                          # an empty sample: zero nodes, zero edges
+    store, conn = _build(samples, cuda)
+    for i in range(S):
+        ec, ex, ey, eei = lightpath_data_ref(samples["data"][i], samples["target"][i], samples["freqs"],
+                                             samples["lp_feat"], samples["metric"])
+        c, x, y, ei = _graph(store, conn, i)
+        assert np.array_equal(c.numpy(), ec) and np.array_equal(x.numpy(), ex) and np.array_equal(y.numpy(), ey)
+        assert np.array_equal(ei.numpy(), eei)
+
+
+def test_built_store_feeds_the_model(cuda):
+    """raw samples -> device graph construction -> device collate -> fused eval kernel == oracle model on the
+    oracle-built graphs."""
+    from gnn_qot_estimation_b200 import Batch, LightpathGNN, synthetic
+    from oracle import LightpathGNNOracle, lightpath_data_ref
+    samples = synthetic.network_status_samples(40, 12, 64, seed=9)
+    store, _ = _build(samples, cuda)
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).eval()
+    with torch.no_grad():
+        out, lb = m(store.collate(range(40)))
+    xs, eis, bts, off = [], [], [], 0
+    for i in range(40):
+        _, x, _, ei = lightpath_data_ref(samples["data"][i], samples["target"][i], samples["freqs"], samples["lp_feat"], samples["metric"])
+        xs.append(torch.from_numpy(x)); eis.append(torch.from_numpy(ei) + off); bts.append(torch.full((x.shape[0],), i)); off += x.shape[0]
+    ob = Batch(x=torch.cat(xs).double(), edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=40)
+    om = LightpathGNNOracle(5, 32, 3, is_lut_index=1, dropout_p=0.0).double()
+    om.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        eo, el = om.eval()(ob)
+    assert torch.equal(lb.cpu(), el)
+    assert float((out.cpu().double() - eo).abs().max() / eo.abs().max()) <= 1e-5
+
+
+def test_capacity_overflow_is_reported(cuda):
+    from gnn_qot_estimation_b200.to_graph import create_lightpath_graphs
+    from gnn_qot_estimation_b200 import synthetic
+    F = len(synthetic.LP_FEAT)
+    data = torch.zeros(1, F, 100, 80)
+    data[0, 0] = torch.arange(8000, dtype=torch.float32).view(100, 80) + 1     # 8000 occupied channels, all distinct ids
+    with pytest.raises(RuntimeError, match="capacity"):
+        create_lightpath_graphs(data.to(cuda), torch.zeros(1, 4, dtype=torch.float64), torch.linspace(192.2, 195.8, 80, dtype=torch.float64),
+                                synthetic.LP_FEAT, synthetic.METRICS)
