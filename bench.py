@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--workload", default="lightpath_infer", choices=["lightpath_infer", "topo_train", "topo_stress", "lightpath_train"],
                     help="lightpath_infer = BASELINE configs[1] (the headline line); topo_train = configs[2] "
                          "(TopologicalGNN DDP training, batch 1024/GPU); topo_stress = configs[4] (10k nodes, hidden 256)")
-    ap.add_argument("--streams", type=int, default=8,
+    ap.add_argument("--streams", type=int, default=16,
                     help="independent batches in flight in the resident run (graph branches)")
     return ap.parse_args()
 
