@@ -57,20 +57,12 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
 }
 __device__ __forceinline__ unsigned tg_hash(int c) { return (static_cast<unsigned>(c) * 2654435761u) >> 22; }
 
-template <bool kFill>
-__global__ void __launch_bounds__(kTgThreads)
-lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ freqs,
-                      const double* __restrict__ target, qot_lp_graph_cfg_t cfg, int32_t* __restrict__ counts,
-                      const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr,
-                      float* __restrict__ node_feat, int64_t* __restrict__ conn_ids,
-                      int32_t* __restrict__ edge_src, int32_t* __restrict__ edge_dst,
-                      float* __restrict__ y, int32_t* __restrict__ status) {
-  extern __shared__ __align__(16) char tg_smem_raw[];
-  TgSmem& sm = *reinterpret_cast<TgSmem*>(tg_smem_raw);
+// Steps 1-2, shared by both representations: occupied channels compacted in row-major order, conn_id ->
+// earliest entry, nodes ranked by first appearance.  Returns K (entries), n (distinct conn_ids), bad.
+__device__ __forceinline__ void tg_scan_and_rank(TgSmem& sm, const float* __restrict__ d, const qot_lp_graph_cfg_t& cfg,
+                                                 int& K_out, int& n_out, bool& bad_out) {
   const int tid = threadIdx.x;
-  const int64_t s = blockIdx.x;
   const int L = cfg.L, Q = cfg.Q, LQ = L * Q;
-  const float* __restrict__ d = data + s * static_cast<int64_t>(cfg.F) * LQ;
   for (int i = tid; i < kTgHash; i += kTgThreads) { sm.hkey[i] = INT_MIN; sm.hmin[i] = INT_MAX; sm.hnode[i] = -1; }
   for (int i = tid; i < QOT_TG_MAX_NODES * kTgAdjWords; i += kTgThreads) (&sm.adj[0][0])[i] = 0u;
   for (int i = tid; i <= min(L, QOT_TG_MAX_LINKS); i += kTgThreads) sm.seg[i] = -1;
@@ -152,6 +144,30 @@ lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__
   }
   __syncthreads();
 
+  K_out = K;
+  n_out = n;
+  bad_out = bad;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(kTgThreads)
+lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ freqs,
+                      const double* __restrict__ target, qot_lp_graph_cfg_t cfg, int32_t* __restrict__ counts,
+                      const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr,
+                      float* __restrict__ node_feat, int64_t* __restrict__ conn_ids,
+                      int32_t* __restrict__ edge_src, int32_t* __restrict__ edge_dst,
+                      float* __restrict__ y, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) char tg_smem_raw[];
+  TgSmem& sm = *reinterpret_cast<TgSmem*>(tg_smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  const int L = cfg.L, Q = cfg.Q, LQ = L * Q;
+  const float* __restrict__ d = data + s * static_cast<int64_t>(cfg.F) * LQ;
+  int K, n;
+  bool bad;
+  tg_scan_and_rank(sm, d, cfg, K, n, bad);
+  (void)L;
+
   // ---- 4. interactions per link: entries of a link are contiguous and ordered by frequency index
   for (int i = tid; i < K; i += kTgThreads) {
     const int l = sm.link[i];
@@ -223,6 +239,132 @@ lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__
   }
 }
 
+
+// Topological representation: to_graph.py::create_topological_graph (:62-184) + TopologicalDataset.__getitem__
+// (topological_training/dataset.py:46-123).  Lightpaths are added to an nx.Graph in ascending conn_id
+// (np.unique); one edge per node pair survives -- its adjacency position dates from the FIRST lightpath
+// of the pair, its attributes from the LAST; dataset.py:57 relabels through a copy that re-orders every
+// adjacency list (smaller neighbours first, ascending; then the rest in first-seen order); from_networkx
+// lists each node's neighbours in that order.  All of it is ranking over <= 256 lightpaths: counting
+// sorts in shared memory, bit-exact edge ORDER.
+struct TpSmem {
+  TgSmem base;
+  int tord[QOT_TG_MAX_NODES];                 // time (ascending conn_id rank) -> node rank r
+  short ea[QOT_TG_MAX_NODES], eb[QOT_TG_MAX_NODES];   // endpoints (0-based) of the lightpath added at time t
+  short tfirst[QOT_TG_MAX_NODES], tlast[QOT_TG_MAX_NODES];
+  int dkey[2 * QOT_TG_MAX_NODES];             // sort key of every directed edge candidate (-1: none)
+};
+
+template <bool kFill>
+__global__ void __launch_bounds__(kTgThreads)
+tp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ target, qot_lp_graph_cfg_t cfg,
+                      int num_nodes, int i_src, int i_dst, int32_t* __restrict__ counts,
+                      const int64_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_src,
+                      int32_t* __restrict__ edge_dst, float* __restrict__ edge_feat, float* __restrict__ y,
+                      int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) char tg_smem_raw[];
+  TpSmem& tp = *reinterpret_cast<TpSmem*>(tg_smem_raw);
+  TgSmem& sm = tp.base;
+  const int tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  const int Q = cfg.Q, LQ = cfg.L * Q;
+  const float* __restrict__ d = data + s * static_cast<int64_t>(cfg.F) * LQ;
+  int K, n;
+  bool bad;
+  tg_scan_and_rank(sm, d, cfg, K, n, bad);
+  (void)K;
+  // time order = ascending conn_id (np.unique, to_graph.py:156): counting sort over the n distinct ids
+  if (tid < n) {
+    const int c = sm.conn[sm.first[tid]];
+    int t = 0;
+    for (int r = 0; r < n; ++r) t += sm.conn[sm.first[r]] < c;
+    tp.tord[t] = tid;
+  }
+  __syncthreads();
+  if (tid < n) {
+    const int k = sm.first[tp.tord[tid]];
+    const int ch = sm.link[k] * Q + sm.freq[k];
+    const int a = static_cast<int>(d[static_cast<int64_t>(i_src) * LQ + ch]) - 1;     // nodes 1..75 -> 0..74
+    const int b = static_cast<int>(d[static_cast<int64_t>(i_dst) * LQ + ch]) - 1;
+    if (a < 0 || b < 0 || a >= num_nodes || b >= num_nodes) sm.bad = 1;
+    tp.ea[tid] = static_cast<short>(a);
+    tp.eb[tid] = static_cast<short>(b);
+  }
+  __syncthreads();
+  if (sm.bad) { bad = true; n = 0; }
+  // first / last lightpath of every unordered node pair
+  if (tid < n) {
+    const int lo = min(tp.ea[tid], tp.eb[tid]), hi = max(tp.ea[tid], tp.eb[tid]);
+    int tf = tid, tl = tid;
+    for (int t = 0; t < n; ++t) {
+      if (min(tp.ea[t], tp.eb[t]) == lo && max(tp.ea[t], tp.eb[t]) == hi) {
+        tf = min(tf, t);
+        tl = max(tl, t);
+      }
+    }
+    tp.tfirst[tid] = static_cast<short>(tf);
+    tp.tlast[tid] = static_cast<short>(tl);
+  }
+  __syncthreads();
+  // directed candidates: slot 2t = (a -> b), slot 2t+1 = (b -> a) of the pair's first lightpath.
+  // key = (source, smaller-neighbour-first, then first-seen time): see the header comment
+  for (int q = tid; q < 2 * QOT_TG_MAX_NODES; q += kTgThreads) {
+    const int t = q >> 1;
+    int key = -1;
+    if (t < n && tp.tfirst[t] == t) {
+      const int a = tp.ea[t], b = tp.eb[t];
+      const int w = (q & 1) ? b : a, x = (q & 1) ? a : b;
+      if (!((q & 1) && a == b)) key = (w << 12) | (x < w ? x : (1 << 11) | t);    // a self loop is listed once
+    }
+    tp.dkey[q] = key;
+  }
+  __syncthreads();
+  int mine[2], pos[2] = {0, 0};
+#pragma unroll
+  for (int u = 0; u < 2; ++u) mine[u] = tp.dkey[tid + u * kTgThreads];
+  int E = 0;
+  for (int q = 0; q < 2 * n; ++q) {
+    const int kq = tp.dkey[q];
+    if (kq < 0) continue;
+    ++E;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) pos[u] += kq < mine[u];
+  }
+  if (!kFill) {
+    if (tid == 0) {
+      counts[s] = E;
+      if (bad) atomicOr(status, 1);
+    }
+    return;
+  }
+  const int64_t e0 = edge_ptr[s];
+  if (edge_ptr[s + 1] - e0 != E) {
+    if (tid == 0) atomicOr(status, 2);
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (mine[u] < 0) continue;
+    const int q = tid + u * kTgThreads, t = q >> 1;
+    const int a = tp.ea[t], b = tp.eb[t];
+    const int64_t o = e0 + pos[u];
+    edge_src[o] = (q & 1) ? b : a;
+    edge_dst[o] = (q & 1) ? a : b;
+    // attributes of the LAST lightpath of the pair, sorted-name order [freq, mod_order, num_spans, path_len]
+    const int k = sm.first[tp.tord[tp.tlast[t]]];
+    const int ch = sm.link[k] * Q + sm.freq[k];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const double v = static_cast<double>(d[static_cast<int64_t>(cfg.i_feat[f]) * LQ + ch]);
+      edge_feat[o * 4 + f] = static_cast<float>((v - cfg.feat_lo[f]) / (cfg.feat_hi[f] - cfg.feat_lo[f]));
+    }
+  }
+  if (tid < 3) {
+    const double v = target[s * cfg.T + cfg.i_tgt[tid]];
+    y[s * 3 + tid] = static_cast<float>((v - cfg.tgt_lo[tid]) / (cfg.tgt_hi[tid] - cfg.tgt_lo[tid]));
+  }
+}
+
 static int tg_check(const float* data, const double* freqs, int64_t S, const qot_lp_graph_cfg_t* cfg, const char* who) {
   QOT_REQUIRE(cfg && S >= 0, "%s: bad argument", who);
   QOT_REQUIRE(S == 0 || (data && freqs), "%s: null input", who);
@@ -237,6 +379,8 @@ static int tg_attr() {
   if (!done) {
     QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
     QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
+    QOT_CUDA(cudaFuncSetAttribute(tp_graph_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
+    QOT_CUDA(cudaFuncSetAttribute(tp_graph_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
     done = true;
   }
   return QOT_OK;
@@ -277,6 +421,45 @@ extern "C" int qot_lightpath_graph_fill(const float* data, const double* freqs, 
   if ((rc = tg_attr())) return rc;
   lp_graph_build_kernel<true><<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
       data, freqs, target, *cfg, nullptr, node_ptr, edge_ptr, node_feat, conn_ids, edge_src, edge_dst, y, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" int qot_topological_graph_count(const float* data, int64_t S, const qot_lp_graph_cfg_t* cfg,
+                                           int32_t num_nodes, int32_t i_src, int32_t i_dst, int32_t* counts,
+                                           int32_t* status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tg_check(data, reinterpret_cast<const double*>(data), S, cfg, "qot_topological_graph_count");
+  if (rc) return rc;
+  QOT_REQUIRE(status && (S == 0 || counts), "qot_topological_graph_count: null output");
+  QOT_REQUIRE(num_nodes > 0 && num_nodes < 2048 && i_src >= 0 && i_src < cfg->F && i_dst >= 0 && i_dst < cfg->F,
+              "qot_topological_graph_count: bad node count or endpoint rows");
+  if (S == 0) return QOT_OK;
+  if ((rc = tg_attr())) return rc;
+  tp_graph_build_kernel<false><<<static_cast<unsigned>(S), kTgThreads, sizeof(TpSmem), stream>>>(
+      data, nullptr, *cfg, num_nodes, i_src, i_dst, counts, nullptr, nullptr, nullptr, nullptr, nullptr, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" int qot_topological_graph_fill(const float* data, const double* target, int64_t S,
+                                          const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
+                                          int32_t i_dst, const int64_t* edge_ptr, int32_t* edge_src,
+                                          int32_t* edge_dst, float* edge_feat, float* y, int32_t* status,
+                                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tg_check(data, reinterpret_cast<const double*>(data), S, cfg, "qot_topological_graph_fill");
+  if (rc) return rc;
+  QOT_REQUIRE(status && (S == 0 || (target && edge_ptr && edge_src && edge_dst && edge_feat && y)),
+              "qot_topological_graph_fill: null argument");
+  QOT_REQUIRE(num_nodes > 0 && num_nodes < 2048 && i_src >= 0 && i_src < cfg->F && i_dst >= 0 && i_dst < cfg->F,
+              "qot_topological_graph_fill: bad node count or endpoint rows");
+  QOT_REQUIRE(cfg->T > 0, "qot_topological_graph_fill: bad target extent");
+  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_topological_graph_fill: target column out of range");
+  if (S == 0) return QOT_OK;
+  if ((rc = tg_attr())) return rc;
+  tp_graph_build_kernel<true><<<static_cast<unsigned>(S), kTgThreads, sizeof(TpSmem), stream>>>(
+      data, target, *cfg, num_nodes, i_src, i_dst, nullptr, edge_ptr, edge_src, edge_dst, edge_feat, y, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

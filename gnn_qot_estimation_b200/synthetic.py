@@ -134,14 +134,17 @@ METRICS = ["osnr", "snr", "ber", "class"]
 
 
 def network_status_samples(num_samples: int, num_links: int = 40, num_freqs: int = 64, seed: int = 0,
-                           spacing: float = 0.0375, max_lightpaths: int = 48, super_channel_p: float = 0.1):
+                           spacing: float = 0.0375, max_lightpaths: int = 48, super_channel_p: float = 0.1,
+                           num_nodes: int = 75):
     """Seeded stand-in for ``dataset["data"]`` of to_graph.py:124-129: a float32 array
     ``[sample, lp_feat, link, freq]`` that is zero on free channels and carries the lightpath's
     feature vector on every (link, frequency) channel it occupies, plus ``target [sample, 4]``,
     the frequency grid ``freqs [num_freqs]`` (float64, 192.2 + k*spacing) and the name lists.
     Every sample holds 8..max_lightpaths lightpaths routed over 1..6 random links with one
     frequency slot each (a few take two adjacent slots: super-channels, which to_graph.py turns
-    into self loops); the last lightpath placed is the LUT (osnr = snr = ber = -1)."""
+    into self loops); the last lightpath placed is the LUT (osnr = snr = ber = -1).  Endpoints are drawn
+    from 1..num_nodes (small values give many lightpaths per node pair: nx.Graph keeps one edge, last
+    attributes win, to_graph.py:175-178)."""
     import numpy as np
     rng = np.random.default_rng(seed)
     F = len(LP_FEAT)
@@ -163,7 +166,7 @@ def network_status_samples(num_samples: int, num_links: int = 40, num_freqs: int
             q0 = int(rng.choice(ok_q))
             vec = np.zeros(F, dtype=np.float32)
             vec[fi["conn_id"]] = conn_ids[k]
-            vec[fi["src_id"]], vec[fi["dst_id"]] = rng.choice(np.arange(1, 76), 2, replace=False)
+            vec[fi["src_id"]], vec[fi["dst_id"]] = rng.choice(np.arange(1, num_nodes + 1), 2, replace=False)
             vec[fi["mod_order"]] = rng.choice([4, 8, 16, 32, 64])
             vec[fi["path_len"]] = int(rng.integers(24214, 7834746))
             vec[fi["num_spans"]] = int(rng.integers(1, 107))

@@ -86,3 +86,45 @@ def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: tor
                                        stream()), "qot_lightpath_graph_fill")
     store = PackedGraphStore(node_ptr, edge_ptr, edge_src, edge_dst, node_feat, None, y, lut_col=1)
     return (store, conn_ids) if return_conn_ids else store
+
+
+def create_topological_graphs(data: torch.Tensor, target: torch.Tensor, lp_feat: Sequence[str], metric: Sequence[str],
+                              num_nodes: int = 75) -> PackedGraphStore:
+    """The topological representation for all samples at once: ``to_graph.create_topological_graph``
+    (to_graph.py:62-184) -> pickle -> ``TopologicalDataset.__getitem__`` (topological_training/dataset.py:46-123).
+    data [S, F, L, Q] float32 (CUDA), target [S, T] float64 -> PackedGraphStore with ``num_nodes`` nodes per
+    graph (no node features: the model embeds ``node_ids``), edges in the reference's order, edge_feat [E,4] in
+    sorted-name order [freq, mod_order, num_spans, path_len] (min-max scaled), y [S,3]."""
+    if not data.is_cuda:
+        raise RuntimeError("create_topological_graphs needs CUDA tensors (gnn_qot_estimation_b200 has no CPU path)")
+    dev = data.device
+    data = data.to(torch.float32).contiguous()
+    target = target.to(dev, torch.float64).contiguous()
+    S, F, L, Q = (int(v) for v in data.shape)
+    if target.shape[0] != S:
+        raise ValueError("target must have data.shape[0] rows")
+    fi = {k: i for i, k in enumerate(lp_feat)}
+    for k in ("src_id", "dst_id"):
+        if k not in fi:
+            raise KeyError(f"lp_feat has no '{k}' entry (to_graph.py:152-153 needs it)")
+    cfg = _cfg(lp_feat, metric, F, L, Q, int(target.shape[1]), 0.05)
+    lib = _lib.lib()
+    counts = torch.zeros(S, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.qot_topological_graph_count(ptr(data), S, C.byref(cfg), int(num_nodes), fi["src_id"], fi["dst_id"],
+                                          ptr(counts), ptr(status), stream()), "qot_topological_graph_count")
+    edge_ptr = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    edge_ptr[1:] = torch.cumsum(counts.to(torch.int64), dim=0)
+    e_tot, st = (int(v) for v in torch.stack([edge_ptr[-1], status[0].to(torch.int64)]).tolist())
+    if st & 1:
+        raise RuntimeError("create_topological_graphs: a sample exceeds the per-block capacity or names a network "
+                           f"node outside 1..{num_nodes}")
+    edge_src = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
+    edge_dst = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
+    edge_feat = torch.empty(max(e_tot, 1), 4, dtype=torch.float32, device=dev)[:e_tot]
+    y = torch.empty(S, 3, dtype=torch.float32, device=dev)
+    check(lib.qot_topological_graph_fill(ptr(data), ptr(target), S, C.byref(cfg), int(num_nodes), fi["src_id"],
+                                         fi["dst_id"], ptr(edge_ptr), ptr(edge_src), ptr(edge_dst), ptr(edge_feat),
+                                         ptr(y), ptr(status), stream()), "qot_topological_graph_fill")
+    node_ptr = torch.arange(S + 1, dtype=torch.int64, device=dev) * int(num_nodes)
+    return PackedGraphStore(node_ptr, edge_ptr, edge_src, edge_dst, None, edge_feat, y)

@@ -454,6 +454,24 @@ int qot_lightpath_graph_fill(const float* data, const double* freqs, const doubl
                              int32_t* edge_src, int32_t* edge_dst, float* y, int32_t* status,
                              void* stream);
 
+/* The topological representation: to_graph.py::create_topological_graph (:62-184: one edge per
+ * lightpath between its source and destination network node, lightpaths added in ascending conn_id,
+ * nx.Graph keeps one edge per node pair -- position from the first, attributes from the last) fused
+ * with topological_training/dataset.py:46-123 (relabelling copy, from_networkx edge order, min-max
+ * scaled edge_attr in sorted-name order [freq, mod_order, num_spans, path_len], y).  Every sample has
+ * num_nodes nodes (75, to_graph.py:134; node_ptr = num_nodes * s, no node features).  Same two-pass
+ * protocol: counts [S] int32 = directed edges per sample; then edge_src / edge_dst [E_tot] int32 in
+ * the REFERENCE'S edge order, edge_feat [E_tot,4], y [S,3].  i_src / i_dst: lp_feat rows of src_id /
+ * dst_id (1-based node ids).  status bit 0: capacity exceeded or an endpoint outside 1..num_nodes. */
+int qot_topological_graph_count(const float* data, int64_t S, const qot_lp_graph_cfg_t* cfg,
+                                int32_t num_nodes, int32_t i_src, int32_t i_dst, int32_t* counts,
+                                int32_t* status, void* stream);
+int qot_topological_graph_fill(const float* data, const double* target, int64_t S,
+                               const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
+                               int32_t i_dst, const int64_t* edge_ptr, int32_t* edge_src,
+                               int32_t* edge_dst, float* edge_feat, float* y, int32_t* status,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,4 +18,4 @@ known-answer fixtures for this path.  The oracle therefore restates PyG's
   * fp64 gradcheck and direct-vs-factorised NNConv identities.
 """
 from .qot_oracle import *  # noqa: F401,F403
-from .to_graph_oracle import lightpath_graph_ref, lightpath_data_ref  # noqa: F401
+from .to_graph_oracle import lightpath_graph_ref, lightpath_data_ref, topological_data_ref  # noqa: F401

@@ -81,3 +81,48 @@ def lightpath_data_ref(sample, target, freqs, lp_feat, metric, freq_threshold=0.
     d = sorted(d)
     ei = np.array(d, dtype=np.int64).reshape(-1, 2).T if d else np.zeros((2, 0), dtype=np.int64)
     return conn, x, y, np.ascontiguousarray(ei)
+
+
+TOPO_FEATURES = ["freq", "mod_order", "num_spans", "path_len"]     # sorted names, topological dataset.py:38-41
+
+
+def topological_data_ref(sample, target, lp_feat, metric, num_nodes=75):
+    """to_graph.py::create_topological_graph (:62-184) + TopologicalDataset.__getitem__
+    (topological_training/dataset.py:46-123) for one sample -> (edge_index [2,E] int64 in the reference's
+    ORDER, edge_attr [E,4] float32, y [3] float32).  Order: lightpaths are added in ascending conn_id
+    (np.unique, :147), nx.Graph keeps one edge per node pair -- adjacency position from the FIRST add,
+    attributes from the LAST (:175-178); the relabelling copy of dataset.py:57 re-orders the adjacency
+    lists (below) and from_networkx lists, for every node ascending, its neighbours in adjacency order."""
+    fi = {k: i for i, k in enumerate(lp_feat)}
+    occupied = np.any(sample != 0, axis=0)                              # :140
+    vecs = sample[:, occupied]                                          # :144, row-major channel order
+    conn = vecs[fi["conn_id"]].astype(int)                              # :151
+    _, uidx = np.unique(conn, return_index=True)                        # :156: ascending conn_id, first occurrence
+    adj = [dict() for _ in range(num_nodes)]                            # adjacency dicts: insertion order
+    for k in uidx:
+        u, v = int(vecs[fi["src_id"], k]) - 1, int(vecs[fi["dst_id"], k]) - 1     # nodes 1..75 -> 0..74 (dataset.py:57)
+        attr = [(float(vecs[fi[name], k]) - FEATURE_RANGES[name][0]) / (FEATURE_RANGES[name][1] - FEATURE_RANGES[name][0])
+                for name in TOPO_FEATURES]                              # dataset.py:65-72
+        adj[u][v] = attr                                                # nx.Graph.add_edge: both directions share
+        adj[v][u] = attr                                                # the (last) attribute dict
+    # dataset.py:57 nx.convert_node_labels_to_integers copies the graph by re-adding G.edges() (every node
+    # ascending, its not-yet-visited neighbours in adjacency order), which re-orders the adjacency lists:
+    # neighbours with a smaller id come first, ascending; then the others in the order G first saw them
+    H = [dict() for _ in range(num_nodes)]
+    seen = set()
+    for u in range(num_nodes):
+        for v, attr in adj[u].items():
+            if v not in seen:
+                H[u][v] = attr
+                H[v][u] = attr
+        seen.add(u)
+    src, dst, ea = [], [], []
+    for u in range(num_nodes):                                          # from_networkx: node ascending, adjacency order
+        for v, attr in H[u].items():
+            src.append(u); dst.append(v); ea.append(attr)
+    ei = np.array([src, dst], dtype=np.int64).reshape(2, -1)
+    ea = np.array(ea, dtype=np.float32).reshape(-1, len(TOPO_FEATURES))
+    mi = {k: i for i, k in enumerate(metric)}
+    y = np.array([(float(target[mi[k]]) - TARGET_RANGES[k][0]) / (TARGET_RANGES[k][1] - TARGET_RANGES[k][0])
+                  for k in ("osnr", "snr", "ber")], dtype=np.float32)   # dataset.py:109-121
+    return ei, ea, y

@@ -49,8 +49,8 @@ def install_fake_xarray(samples):
     sys.modules["xarray"] = mod
 
 
-def reference_graphs(samples, freq_threshold=0.05):
-    """[networkx.Graph] from the reference's create_lightpath_graph, one per sample."""
+def reference_graphs(samples, freq_threshold=0.05, representation="lightpath"):
+    """[networkx.Graph] from the reference's create_lightpath_graph / create_topological_graph, one per sample."""
     install_fake_xarray(samples)
     sys.path.insert(0, str(REF))
     sys.modules.pop("to_graph", None)
@@ -59,7 +59,10 @@ def reference_graphs(samples, freq_threshold=0.05):
     out = []
     with contextlib.redirect_stdout(io.StringIO()):
         for i in range(samples["data"].shape[0]):
-            out.append(to_graph.create_lightpath_graph(i, FEATURES, "unused.nc", freq_threshold=freq_threshold))
+            if representation == "lightpath":
+                out.append(to_graph.create_lightpath_graph(i, FEATURES, "unused.nc", freq_threshold=freq_threshold))
+            else:
+                out.append(to_graph.create_topological_graph(i, FEATURES, "unused.nc"))
     sys.path.remove(str(REF))
     sys.modules.pop("to_graph", None)
     sys.modules.pop("xarray", None)
@@ -82,6 +85,26 @@ def reference_data_objects(graphs):
     finally:
         sys.path.remove(str(REF))
         for k in [k for k in sys.modules if k.split(".")[0] in ("lightpath_training", "constants")]:
+            del sys.modules[k]
+
+
+def reference_topological_data_objects(graphs):
+    """The reference's TopologicalDataset over pickles of those graphs -> [Data] (edge ORDER included:
+    edges are added in ascending conn_id order, to_graph.py:147-178, so it is well defined)."""
+    from gnn_qot_estimation_b200 import pyg_compat
+    pyg_compat.install()
+    sys.path.insert(0, str(REF))
+    try:
+        from topological_training.dataset import TopologicalDataset      # the reference's file
+        with tempfile.TemporaryDirectory() as d:
+            for i, g in enumerate(graphs):
+                with open(os.path.join(d, f"graph_{i:04d}.gpickle"), "wb") as f:
+                    pickle.dump(g, f)
+            ds = TopologicalDataset(directory=d)
+            return [ds[i] for i in range(len(ds))], list(ds.FEATURES)
+    finally:
+        sys.path.remove(str(REF))
+        for k in [k for k in sys.modules if k.split(".")[0] in ("topological_training", "constants")]:
             del sys.modules[k]
 
 
@@ -109,6 +132,18 @@ def main():
         print(f"case {(S, L, Q, seed, spacing)}: nodes {[len(g) for g in graphs]}, "
               f"edges {[g.number_of_edges() for g in graphs]}, self loops {[len(list(__import__('networkx').selfloop_edges(g))) for g in graphs]}")
     torch.save(gold, Path(__file__).parent / "to_graph_lightpath.pt")
+    # topological representation: the reference's edge order is part of the contract here
+    tcases = [c + (75,) for c in CASES] + [(5, 10, 48, 4, 0.0375, 6)]     # last: 6 endpoints -> duplicate node pairs
+    tgold = {"cases": tcases, "features": FEATURES, "results": []}
+    for (S, L, Q, seed, spacing, nn) in tcases:
+        samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing, num_nodes=nn)
+        graphs = reference_graphs(samples, representation="topological")
+        datas, names = reference_topological_data_objects(graphs)
+        assert names == ["freq", "mod_order", "num_spans", "path_len"], names
+        tgold["results"].append({"graphs": [{"edge_index": d.edge_index.clone(), "edge_attr": d.edge_attr.clone(),
+                                             "y": d.y.clone(), "num_nodes": int(d.num_nodes)} for d in datas]})
+        print(f"topological case {(S, L, Q, seed, spacing, nn)}: directed edges {[int(d.edge_index.shape[1]) for d in datas]}")
+    torch.save(tgold, Path(__file__).parent / "to_graph_topological.pt")
 
 
 if __name__ == "__main__":

@@ -56,3 +56,22 @@ def test_oracle_matches_reference_code_on_fresh_seeds(seed, spacing):
         assert np.array_equal(y, c["y"].numpy()) and np.array_equal(ei, c["edge_index_sorted"].numpy())
     for k in [k for k in sys.modules if k.split(".")[0] == "torch_geometric"]:
         del sys.modules[k]
+
+
+def test_topological_oracle_matches_reference_golden_vectors():
+    """create_topological_graph + TopologicalDataset: edge ORDER, attributes (last lightpath of a node pair
+    wins) and labels, bit for bit."""
+    from gnn_qot_estimation_b200 import synthetic
+    from oracle import topological_data_ref
+    gold = load_golden("to_graph_topological.pt")
+    dup = 0
+    for (S, L, Q, seed, spacing, nn), res in zip(gold["cases"], gold["results"]):
+        samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing, num_nodes=nn)
+        for i, g in enumerate(res["graphs"]):
+            ei, ea, y = topological_data_ref(samples["data"][i], samples["target"][i], samples["lp_feat"], samples["metric"])
+            assert g["num_nodes"] == 75
+            assert np.array_equal(ei, g["edge_index"].numpy())
+            assert np.array_equal(ea, g["edge_attr"].numpy()) and np.array_equal(y, g["y"].numpy())
+            n_lp = len(np.unique(samples["data"][i][0][np.any(samples["data"][i] != 0, axis=0)]))
+            dup += int(ei.shape[1] < 2 * n_lp)
+    assert dup >= 4                                                     # node pairs shared by several lightpaths occur

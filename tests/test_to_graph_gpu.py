@@ -88,3 +88,51 @@ def test_capacity_overflow_is_reported(cuda):
     with pytest.raises(RuntimeError, match="capacity"):
         create_lightpath_graphs(data.to(cuda), torch.zeros(1, 4, dtype=torch.float64), torch.linspace(192.2, 195.8, 80, dtype=torch.float64),
                                 synthetic.LP_FEAT, synthetic.METRICS)
+
+
+def test_topological_matches_reference_golden_vectors(cuda):
+    """create_topological_graph + TopologicalDataset: edge ORDER, attributes (last lightpath of a node pair
+    wins), labels -- bit for bit against the reference's own outputs."""
+    from gnn_qot_estimation_b200 import synthetic
+    from gnn_qot_estimation_b200.to_graph import create_topological_graphs
+    gold = load_golden("to_graph_topological.pt")
+    for (S, L, Q, seed, spacing, nn), res in zip(gold["cases"], gold["results"]):
+        samples = synthetic.network_status_samples(S, L, Q, seed=seed, spacing=spacing, num_nodes=nn)
+        store = create_topological_graphs(torch.from_numpy(samples["data"]).to(cuda), torch.from_numpy(samples["target"]),
+                                          samples["lp_feat"], samples["metric"])
+        assert store.num_graphs == S and int(store.node_ptr[-1]) == 75 * S
+        for i, g in enumerate(res["graphs"]):
+            e0, e1 = int(store.edge_ptr[i]), int(store.edge_ptr[i + 1])
+            ei = torch.stack([store.edge_src[e0:e1], store.edge_dst[e0:e1]]).to(torch.int64).cpu()
+            assert torch.equal(ei, g["edge_index"])
+            assert torch.equal(store.edge_feat[e0:e1].cpu(), g["edge_attr"]) and torch.equal(store.y[i].cpu(), g["y"])
+
+
+@pytest.mark.parametrize("S,L,Q,seed,nn", [(48, 14, 64, 21, 75), (9, 6, 40, 22, 4), (6, 50, 80, 23, 12)])
+def test_topological_matches_oracle_on_fresh_seeds(cuda, S, L, Q, seed, nn):
+    from gnn_qot_estimation_b200 import synthetic
+    from gnn_qot_estimation_b200.to_graph import create_topological_graphs
+    from oracle import topological_data_ref
+    samples = synthetic.network_status_samples(S, L, Q, seed=seed, num_nodes=nn)
+    samples["data"][S // 3] = 0.0
+    store = create_topological_graphs(torch.from_numpy(samples["data"]).to(cuda), torch.from_numpy(samples["target"]),
+                                      samples["lp_feat"], samples["metric"])
+    for i in range(S):
+        eei, eea, ey = topological_data_ref(samples["data"][i], samples["target"][i], samples["lp_feat"], samples["metric"])
+        e0, e1 = int(store.edge_ptr[i]), int(store.edge_ptr[i + 1])
+        ei = torch.stack([store.edge_src[e0:e1], store.edge_dst[e0:e1]]).to(torch.int64).cpu().numpy()
+        assert np.array_equal(ei, eei) and np.array_equal(store.edge_feat[e0:e1].cpu().numpy(), eea)
+        assert np.array_equal(store.y[i].cpu().numpy(), ey)
+
+
+def test_topological_store_feeds_the_model(cuda):
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    from gnn_qot_estimation_b200.to_graph import create_topological_graphs
+    samples = synthetic.network_status_samples(16, 12, 64, seed=31)
+    store = create_topological_graphs(torch.from_numpy(samples["data"]).to(cuda), torch.from_numpy(samples["target"]),
+                                      samples["lp_feat"], samples["metric"])
+    sd = load_golden("ckpt_topological_model_0.pt")["model_state_dict"]
+    m = TopologicalGNN(75, 16, 3, edge_dim=4, dropout_p=0.0)
+    m.load_state_dict(sd, strict=True)
+    out = m.to(cuda).eval()(store.collate(range(16)))
+    assert out.shape == (16, 3) and bool(torch.isfinite(out).all())
