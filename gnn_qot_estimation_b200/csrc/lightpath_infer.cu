@@ -53,6 +53,8 @@ __device__ __forceinline__ unsigned tf32_rna(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
 }
+// the same rounding for finite inputs (cvt.rna.tf32 is add-half-ulp + mask plus an Inf/NaN guard on sm_100)
+__device__ __forceinline__ unsigned tf32_rna_finite(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float4 tf32_split2(float b0, float b1) {
   const float h0 = __uint_as_float(tf32_rna(b0)), h1 = __uint_as_float(tf32_rna(b1));
   return make_float4(h0, h1, __uint_as_float(tf32_rna(b0 - h0)), __uint_as_float(tf32_rna(b1 - h1)));
@@ -1041,19 +1043,23 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
   while (!mbar_try_wait(bar, 0u)) {}
   LPB_TRACE(2);
 
-  // ---- LUT node(s) of the graph
+  // ---- LUT node(s) of the graph: a per-lane bit per node, then one count and one minimum over the 8 lanes
   int cnt = 0, il = -1;
+  {
+    unsigned m = 0u;
 #pragma unroll
-  for (int r = 0; r < kMaxN / 8; ++r) {
-    if (__any_sync(kFull, 8 * r < n)) {
+    for (int r = 0; r < kMaxN / 8; ++r) {
       const int node = sl + 8 * r;
-      const unsigned bal = __ballot_sync(kFull, node < n && (kXG ? flag[r] : sx[node * kF + lut_col]) == 1.0f);
-      const unsigned sub = (bal >> (8 * sg)) & 0xffu;
-      if (sub) {
-        if (il < 0) il = 8 * r + __ffs(sub) - 1;
-        cnt += __popc(sub);
-      }
+      if (node < n && (kXG ? flag[r] : sx[node * kF + lut_col]) == 1.0f) m |= 1u << r;
     }
+    cnt = __popc(m);
+    int first = m ? 8 * (__ffs(m) - 1) + sl : 0x7fff;
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      cnt += __shfl_xor_sync(kFull, cnt, o);
+      first = min(first, __shfl_xor_sync(kFull, first, o));
+    }
+    if (cnt) il = first;
   }
   bool ok = fits && cnt == 1 && (l1 - l0) == 1;      // fast row: exactly one LUT node, as lut_ptr says
   if (fits && sl == 0 && cnt != l1 - l0) atomicOr(status, 1);   // lut_ptr does not describe this x
@@ -1067,8 +1073,11 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
     const int eb = sl * c;
     const int tmax = ok ? min(c, ne - eb) : 0;
     const int cmax = __reduce_max_sync(kFull, tmax);
-    const long long target = ok ? n0 + il : -2;
-    const long long* sde = sd + eb;
+    const long long target = n0 + il;
+    const int tlo = static_cast<int>(target), thi = static_cast<int>(target >> 32);
+    // unconditional 8-byte reads: slots past the lane's run stay inside the block's shared memory (the
+    // window is followed by the z rows) and are masked by t < tmax
+    const int2* sde = reinterpret_cast<const int2*>(sd + eb);
     unsigned hm = 0u;
 #pragma unroll
     for (int t4 = 0; t4 < 32; t4 += 4) {
@@ -1077,13 +1086,19 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
         for (int i = 0; i < 4; ++i) {
           const int t = t4 + i;
           if (t < 31) {
-            long long d = -1;
-            if (t < tmax) d = sde[t];
-            if (d == target) hm |= 1u << t;
+            const int2 d = sde[t];
+            // two chained predicates and one predicated OR per slot (the compiler's own select chain
+            // costs twice that); slots past the run are masked once, below
+            asm("{ .reg .pred p;\n\t"
+                "setp.eq.s32 p, %1, %3;\n\t"
+                "setp.eq.and.s32 p, %2, %4, p;\n\t"
+                "@p or.b32 %0, %0, %5; }"
+                : "+r"(hm) : "r"(d.x), "r"(d.y), "r"(tlo), "r"(thi), "r"(1u << t));
           }
         }
       }
     }
+    hm &= (1u << max(tmax, 0)) - 1u;                   // tmax <= 31
     const int h = __popc(hm);
     int incl = h;
 #pragma unroll
@@ -1360,8 +1375,8 @@ lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   
         const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          yhi[m][i] = tf32_rna(y[i]);
-          ylo[m][i] = tf32_rna(y[i] - __uint_as_float(yhi[m][i]));
+          yhi[m][i] = tf32_rna_finite(y[i]);               // y >= 0; an Inf keeps hi = Inf, lo = NaN
+          ylo[m][i] = tf32_rna_finite(y[i] - __uint_as_float(yhi[m][i]));
         }
       }
 #pragma unroll
@@ -1566,8 +1581,8 @@ lp_head_kernel(const float* __restrict__ zbuf, const int64_t* __restrict__ lptr,
         unsigned yhi[4], ylo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          yhi[i] = tf32_rna(y[i]);
-          ylo[i] = tf32_rna(y[i] - __uint_as_float(yhi[i]));
+          yhi[i] = tf32_rna_finite(y[i]);
+          ylo[i] = tf32_rna_finite(y[i] - __uint_as_float(yhi[i]));
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
