@@ -69,22 +69,44 @@ __device__ __forceinline__ void tg_scan_and_rank(TgSmem& sm, const float* __rest
   if (tid == 0) sm.bad = 0;
   __syncthreads();
 
-  // ---- 1. occupied channels, compacted in row-major order (to_graph.py:229-232)
+  // ---- 1. occupied channels, compacted in row-major order (to_graph.py:229-232).  A thread takes 4
+  // consecutive channels per round (one 16-byte load per lp_feat row, all rows in flight at once), the
+  // block one prefix sum per 1024 channels
   int K = 0;
-  for (int c0 = 0; c0 < LQ; c0 += kTgThreads) {
-    const int ch = c0 + tid;
-    bool occ = false;
-    if (ch < LQ)
-      for (int f = 0; f < cfg.F; ++f) occ |= d[static_cast<int64_t>(f) * LQ + ch] != 0.f;
+  const bool vec = (LQ & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
+  for (int c0 = 0; c0 < LQ; c0 += 4 * kTgThreads) {
+    const int ch0 = c0 + 4 * tid;
+    unsigned occ4 = 0u;
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && ch0 < LQ) {                              // LQ % 4 == 0: the quad is entirely inside
+#pragma unroll 5
+      for (int f = 0; f < cfg.F; ++f) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(d + static_cast<int64_t>(f) * LQ + ch0));
+        occ4 |= (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
+        if (f == cfg.i_conn) { cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w; }
+      }
+    } else if (!vec) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ch0 + u < LQ) {
+          for (int f = 0; f < cfg.F; ++f) occ4 |= (d[static_cast<int64_t>(f) * LQ + ch0 + u] != 0.f ? 1u : 0u) << u;
+          cv[u] = d[static_cast<int64_t>(cfg.i_conn) * LQ + ch0 + u];
+        }
+      }
+    }
     int tot;
-    const int pos = K + block_excl_scan(occ ? 1 : 0, sm.scan, &tot);
-    if (occ) {
-      if (pos < QOT_TG_MAX_CHANNELS) {
-        sm.conn[pos] = static_cast<int>(d[static_cast<int64_t>(cfg.i_conn) * LQ + ch]);   // int(): toward zero (:243)
-        sm.link[pos] = static_cast<unsigned short>(ch / Q);
-        sm.freq[pos] = static_cast<unsigned short>(ch % Q);
-      } else {
-        sm.bad = 1;
+    int pos = K + block_excl_scan(__popc(occ4), sm.scan, &tot);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if ((occ4 >> u) & 1u) {
+        if (pos < QOT_TG_MAX_CHANNELS) {
+          sm.conn[pos] = static_cast<int>(cv[u]);                            // int(): toward zero (:243)
+          sm.link[pos] = static_cast<unsigned short>((ch0 + u) / Q);
+          sm.freq[pos] = static_cast<unsigned short>((ch0 + u) % Q);
+        } else {
+          sm.bad = 1;
+        }
+        ++pos;
       }
     }
     K += tot;
