@@ -298,3 +298,29 @@ def test_unaligned_buffers(cuda, shift_floats, num_graphs):
         out, lb = m(b)
         eo, el = _oracle(sd, torch.float64)(_to64(hb))
     assert torch.equal(lb.cpu(), el) and rel_err(out, eo) <= RTOL
+
+
+def test_tiles_larger_than_the_staged_windows(cuda):
+    """Tiles whose 32 graphs exceed the shared-memory windows of the fused kernel (1216 nodes / 4608 edges):
+    the graphs past the window take the generic path inside the same launch, rows stay in order."""
+    from gnn_qot_estimation_b200 import Batch
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    g = torch.Generator().manual_seed(5)
+    xs, eis, bts, off = [], [], [], 0
+    sizes = [56] * 40 + [60, 12, 64, 9] * 8 + [30] * 11          # 83 graphs: 2-3 tiles, the first two far over the caps
+    for gi, n in enumerate(sizes):
+        x = torch.rand(n, 5, generator=g)
+        x[:, 1] = 0.0
+        x[int(torch.randint(0, n, (1,), generator=g)), 1] = 1.0
+        E = min(240, 5 * n)
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = torch.randint(0, n, (E,), generator=g)
+        xs.append(x); eis.append(torch.stack([src, dst]) + off); bts.append(torch.full((n,), gi, dtype=torch.int64))
+        off += n
+    hb = Batch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=len(sizes))
+    with torch.no_grad():
+        out, lb = m(hb.to(cuda))
+        eo, el = _oracle(sd, torch.float64)(_to64(hb))
+    assert torch.equal(lb.cpu(), el) and out.shape == (len(sizes), 3)
+    assert rel_err(out, eo) <= RTOL
