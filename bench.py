@@ -203,6 +203,9 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from gnn_qot_estimation_b200.distributed import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa_node(local)          # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -341,6 +344,8 @@ def run_b200(args):
                            f"(~{pipe.zero_copy_bytes / max(pipe.steps, 1):.0f} B/step, estimated, included)"}
 
     cpu_base = None
+    if all_cpus is not None:
+        os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core back
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cs = synthetic.lightpath_store(4 * Bsz, seed=1, device="cpu")
@@ -359,7 +364,7 @@ def run_b200(args):
                                    f"{G} synthetic lightpath graphs per GPU, n~U{{8..56}}, batch {Bsz}",
                        "batch": Bsz, "graphs_per_gpu": G, "weights": "lightpath_training/models/model_1.pth",
                        "l2": f"inputs cycle through {input_bytes / 1e9:.2f} GB of distinct batches (> 126 MB L2)",
-                       "parallelism": f"graph-sharded x{world}, no collective"},
+                       "parallelism": f"graph-sharded x{world}, no collective", "host": numa},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
             "gpu_launches": launches_per_step * K, "clocks": clk.summary(),
         }

@@ -119,3 +119,40 @@ class GraphDataParallel(torch.nn.Module):
 
     def sync_gradients(self) -> None:
         self.grads.all_reduce_mean()
+
+
+def bind_to_gpu_numa_node(device_index: int) -> str:
+    """Pins the calling process to the CPU cores NVML reports as local to GPU `device_index`, so that
+    the pinned host buffers it allocates afterwards (first-touch) and its copy-submitting threads sit on
+    the GPU's own NUMA node.  With one process per GPU this keeps every rank's host->device traffic off
+    the inter-socket link.  Returns a short description; never raises (no NVML / no affinity API: no-op).
+    Disabled by QOT_NO_NUMA_BIND=1."""
+    import os
+    if os.environ.get("QOT_NO_NUMA_BIND") or not hasattr(os, "sched_setaffinity"):
+        return "numa binding off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES re-numbering: resolve through the PCI bus id of the torch device
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        h = None
+        if bus is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                    h = hi
+                    break
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "numa binding: empty affinity mask, unchanged"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} cores local to GPU {device_index}"
+    except Exception as e:                                  # noqa: BLE001 -- best effort by design
+        return f"numa binding unavailable ({type(e).__name__})"
