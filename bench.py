@@ -339,7 +339,8 @@ def run_b200(args):
         e2e = {"value": world * ge / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": (pipe.h2d_bytes + pipe.zero_copy_bytes) / max(pipe.steps, 1),
                "d2h_bytes_per_step": pipe.d2h_bytes / max(pipe.steps, 1), "steps": Ke,
-               "h2d_note": "copied: x, destination row of edge_index, ptr/edge_ptr/lut_ptr; the source row stays in "
+               "h2d_note": "copied in ONE transfer per step (the host batch keeps them contiguous): destination row of "
+                           "edge_index, ptr/edge_ptr/lut_ptr, x; the source row stays in "
                            "pinned host memory and the kernel reads ~4 sectors (32 B) per LUT row from it over PCIe "
                            f"(~{pipe.zero_copy_bytes / max(pipe.steps, 1):.0f} B/step, estimated, included)"}
 

@@ -45,7 +45,7 @@ class QotLightpathParams(C.Structure):
 
 class QotLpSlot(C.Structure):
     _fields_ = [("x", P), ("edge_src", P), ("edge_dst", P), ("ptrs", P), ("out", P), ("lut_batch", P),
-                ("lut_node", P), ("n_lut", P), ("status", P), ("z", P),
+                ("lut_node", P), ("n_lut", P), ("status", P), ("z", P), ("arena", P),
                 ("cap_nodes", i64), ("cap_edges", i64), ("cap_graphs", i64)]
 
 

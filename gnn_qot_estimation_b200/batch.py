@@ -191,6 +191,22 @@ class PackedGraphStore:
             lut_ptr = torch.zeros(B + 1, dtype=torch.int64)
             flags = (x[:, self.lut_col] == 1.0).to(torch.int64)
             torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, flags), 0, out=lut_ptr[1:])
+        if pin and lut_ptr is not None and x is not None:
+            # one pinned arena per batch: [edge_index (src row | dst row) | ptr | edge_ptr | lut_ptr | x].  Everything
+            # the fused eval kernel needs on the device -- the destination row, the three offset arrays and x --
+            # is then ONE contiguous range: qot_lightpath_infer_host moves it with a single copy
+            E_, N_ = int(ei.shape[1]), int(x.shape[0])
+            nbytes = 16 * E_ + 24 * (B + 1) + 20 * N_
+            arena = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
+            ei_v = arena[:16 * E_].view(torch.int64).view(2, E_)
+            ptrs = arena[16 * E_:16 * E_ + 24 * (B + 1)].view(torch.int64).view(3, B + 1)
+            x_v = arena[16 * E_ + 24 * (B + 1):nbytes].view(torch.float32).view(N_, x.shape[1])
+            ei_v.copy_(ei); ptrs[0].copy_(ptr); ptrs[1].copy_(eptr); ptrs[2].copy_(lut_ptr); x_v.copy_(x)
+            pin_ = lambda t: None if t is None else t.pin_memory()
+            b = Batch(x=x_v, edge_index=ei_v, edge_attr=pin_(ea), batch=pin_(bt), node_ids=pin_(nid), y=pin_(y),
+                      ptr=ptrs[0], edge_ptr=ptrs[1], lut_ptr=ptrs[2], num_graphs=B, lut_col=self.lut_col)
+            b._arena = arena                              # keeps the pinned allocation alive
+            return b
         # the three offset arrays share one [3, B+1] buffer: one H2D copy moves them all
         if lut_ptr is not None:
             ptrs = torch.stack([ptr, eptr, lut_ptr])

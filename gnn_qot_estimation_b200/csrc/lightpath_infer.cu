@@ -1824,6 +1824,10 @@ extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge
   QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer_host: prepared must be 16-byte aligned");
   const int64_t L = lut_ptr_host[B];
   QOT_REQUIRE(L >= 0 && L <= N, "qot_lightpath_infer_host: lut_ptr_host[B] out of range");
+  // contiguous host batch [dst row | gptr | eptr | lut_ptr | x] and an arena in the slot: one copy
+  const bool merged = slot->arena && E > 0 && gptr_host == edge_index_host + 2 * E &&
+                      eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1) &&
+                      reinterpret_cast<const char*>(x_host) == reinterpret_cast<const char*>(lut_ptr_host + (B + 1));
   // device view of the pinned source row (UVA: identical address; asked for explicitly so that
   // unmapped host memory is refused instead of faulting in the kernel)
   const int64_t* esrc_dev = nullptr;
@@ -1840,13 +1844,24 @@ extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge
       esrc_dev = slot->edge_src;
       copied += E * 8;
     }
-    QOT_CUDA(cudaMemcpyAsync(slot->edge_dst, edge_index_host + E, E * 8, cudaMemcpyHostToDevice, stream));
+    if (!merged) QOT_CUDA(cudaMemcpyAsync(slot->edge_dst, edge_index_host + E, E * 8, cudaMemcpyHostToDevice, stream));
   }
-  QOT_CUDA(cudaMemcpyAsync(slot->x, x_host, N * kF * 4, cudaMemcpyHostToDevice, stream));
+  const float* x_dev = slot->x;
+  const int64_t* edst_dev = slot->edge_dst;
   int64_t* gptr = slot->ptrs;
+  if (merged) {
+    char* a = static_cast<char*>(slot->arena);
+    QOT_CUDA(cudaMemcpyAsync(a, edge_index_host + E, E * 8 + 3 * (B + 1) * 8 + N * kF * 4, cudaMemcpyHostToDevice, stream));
+    edst_dev = reinterpret_cast<const int64_t*>(a);
+    gptr = reinterpret_cast<int64_t*>(a + E * 8);
+    x_dev = reinterpret_cast<const float*>(a + E * 8 + 3 * (B + 1) * 8);
+  } else {
+    QOT_CUDA(cudaMemcpyAsync(slot->x, x_host, N * kF * 4, cudaMemcpyHostToDevice, stream));
+  }
   int64_t* eptr = gptr + (B + 1);
   int64_t* lptr = eptr + (B + 1);
-  if (eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1)) {
+  if (merged) {
+  } else if (eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1)) {
     // the three offset arrays are adjacent on the host (PackedGraphStore.host_batch): one copy
     QOT_CUDA(cudaMemcpyAsync(gptr, gptr_host, 3 * (B + 1) * 8, cudaMemcpyHostToDevice, stream));
   } else {
@@ -1855,7 +1870,7 @@ extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge
     QOT_CUDA(cudaMemcpyAsync(lptr, lut_ptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
   }
   copied += N * kF * 4 + E * 8 + 3 * (B + 1) * 8;
-  int rc = lp_infer_launch(slot->x, esrc_dev, slot->edge_dst, gptr, eptr, lptr, N, E, B, prepared, is_lut_index,
+  int rc = lp_infer_launch(x_dev, esrc_dev, edst_dev, gptr, eptr, lptr, N, E, B, prepared, is_lut_index,
                            slot->out, slot->lut_batch, slot->lut_node, slot->n_lut, slot->status, slot->z, stream);
   if (rc) return rc;
   if (L > 0) {

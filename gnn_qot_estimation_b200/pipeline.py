@@ -45,10 +45,11 @@ class _Slot:
         self.ptrs = torch.empty(3 * (max_graphs + 1), dtype=torch.int64, device=dev)
         self.res = ops.new_infer_out(max_nodes, dev)
         self.z = torch.empty(_lib.lib().qot_lightpath_infer_workspace_bytes(max_nodes), dtype=torch.uint8, device=dev)
+        self.arena = torch.empty(8 * max_edges + 24 * (max_graphs + 1) + 20 * max_nodes + 16, dtype=torch.uint8, device=dev)
         self.c = _lib.QotLpSlot(self.x.data_ptr(), None, self.edst.data_ptr(), self.ptrs.data_ptr(),
                                 self.res.out.data_ptr(), self.res.lut_batch.data_ptr(),
                                 self.res.lut_node.data_ptr(), self.res.n_lut.data_ptr(),
-                                self.res.status.data_ptr(), self.z.data_ptr(), max_nodes, max_edges, max_graphs)
+                                self.res.status.data_ptr(), self.z.data_ptr(), self.arena.data_ptr(), max_nodes, max_edges, max_graphs)
         self.out_h = torch.empty(max_nodes, 3, dtype=torch.float32).pin_memory()
         self.lb_h = torch.empty(max_nodes, dtype=torch.int64).pin_memory()
         self.st_h = torch.zeros(1, dtype=torch.int32).pin_memory()

@@ -333,6 +333,9 @@ typedef struct {
   int32_t* n_lut;       /* [1]                                             */
   int32_t* status;      /* [1], zeroed by the caller once                  */
   float* z;             /* qot_lightpath_infer_workspace_bytes(cap_nodes) bytes, 16-byte aligned */
+  void* arena;          /* optional: 8*cap_edges + 24*(cap_graphs+1) + 20*cap_nodes bytes.  When the host batch
+                           keeps [dst row | gptr | eptr | lut_ptr | x] contiguous (PackedGraphStore.host_batch(pin=True)
+                           does) the call moves that range with ONE copy into the arena instead of three */
   int64_t cap_nodes, cap_edges, cap_graphs;
 } qot_lp_slot_t;
 int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,
