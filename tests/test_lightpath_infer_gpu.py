@@ -324,3 +324,52 @@ def test_tiles_larger_than_the_staged_windows(cuda):
         eo, el = _oracle(sd, torch.float64)(_to64(hb))
     assert torch.equal(lb.cpu(), el) and out.shape == (len(sizes), 3)
     assert rel_err(out, eo) <= RTOL
+
+
+def test_full_size_batches_size_independent_properties(cuda):
+    """BASELINE cfg 2 batch size (4096 graphs, ~131 k nodes, ~490 k edges per batch), several batches:
+    properties that hold at any size, checked bit for bit --
+      * batch-split invariance: a 4096-graph batch == its two 2048-graph halves, concatenated;
+      * graph-order equivariance: permuting the graphs of a batch permutes the output rows -- bitwise for
+        graphs evaluated by the same code path (a row does not depend on the graph's tile, lane group or
+        neighbours), to round-off for the few that change between the fast and the generic path;
+      * run-to-run determinism;
+    plus the oracle (fp64) on a 256-graph subsample of every batch."""
+    from gnn_qot_estimation_b200 import synthetic
+    sd = load_golden("ckpt_lightpath_model_1.pt")["model_state_dict"]
+    m = _model(cuda, sd)
+    B, nb = 4096, 4
+    store = synthetic.lightpath_store(B * nb, seed=77, device="cpu")
+    dstore = store.to(cuda)
+    o64 = _oracle(sd, torch.float64)
+    gen = torch.Generator().manual_seed(3)
+    for k in range(nb):
+        ids = torch.arange(k * B, (k + 1) * B)
+        with torch.no_grad():
+            full, lb = m(dstore.collate(range(k * B, (k + 1) * B)))
+            full = full.clone()
+            again, _ = m(dstore.collate(range(k * B, (k + 1) * B)))
+            assert torch.equal(full, again)                                         # deterministic
+            h0, _ = m(dstore.collate(range(k * B, k * B + B // 2)))
+            h0 = h0.clone()
+            h1, _ = m(dstore.collate(range(k * B + B // 2, (k + 1) * B)))
+            assert torch.equal(full, torch.cat([h0, h1]))                           # split invariance
+            perm = torch.randperm(B, generator=gen)
+            pout, plb = m(dstore.collate(ids[perm]))
+            assert torch.equal(plb.cpu(), torch.arange(B))
+            ref = full[perm.to(cuda)]
+            same = (pout == ref).all(dim=1).float().mean().item()
+            # equivariance: bit for bit for every graph evaluated by the same code path; the few graphs whose
+            # tile overflows the staged windows in one arrangement and not in the other (generic path, FP32
+            # head, other summation tree) agree to round-off
+            assert same >= 0.97 and rel_err(pout, ref) <= 2e-6
+            sub = ids[torch.randperm(B, generator=gen)[:256]].sort().values
+            so, _ = m(dstore.collate(sub))
+            xs, eis, bts, off = [], [], [], 0
+            for j, gid in enumerate(sub.tolist()):
+                g1 = store.host_batch(gid, gid + 1)
+                xs.append(g1.x); eis.append(g1.edge_index + off); bts.append(torch.full((g1.x.shape[0],), j)); off += g1.x.shape[0]
+            from gnn_qot_estimation_b200 import Batch
+            ob = Batch(x=torch.cat(xs).double(), edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=256)
+            eo, _ = o64(ob)
+            assert rel_err(so, eo) <= RTOL
