@@ -136,3 +136,38 @@ def test_topological_store_feeds_the_model(cuda):
     m.load_state_dict(sd, strict=True)
     out = m.to(cuda).eval()(store.collate(range(16)))
     assert out.shape == (16, 3) and bool(torch.isfinite(out).all())
+
+
+def test_sample_order_equivariance_and_batch_invariance(cuda):
+    """512 samples [10, 60, 80]: permuting the sample axis permutes the graphs (bit for bit, both
+    representations); one call on all samples == one call per chunk, concatenated."""
+    from gnn_qot_estimation_b200 import synthetic
+    from gnn_qot_estimation_b200.to_graph import create_lightpath_graphs, create_topological_graphs
+    s = synthetic.network_status_samples(64, 60, 80, seed=41)
+    data = torch.from_numpy(s["data"]).to(cuda).repeat(8, 1, 1, 1)
+    data[64:] += 0.0
+    # make the repeats differ: shift conn ids per copy (keeps structure, changes labels)
+    ci = s["lp_feat"].index("conn_id")
+    for r in range(1, 8):
+        blk = data[64 * r:64 * (r + 1), ci]
+        blk[blk != 0] += 1000.0 * r
+    tgt = torch.from_numpy(s["target"]).repeat(8, 1)
+    fr = torch.from_numpy(s["freqs"])
+    S = data.shape[0]
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(1))
+
+    def graphs(store, with_x):
+        out = []
+        for i in range(store.num_graphs):
+            n0, n1, e0, e1 = int(store.node_ptr[i]), int(store.node_ptr[i + 1]), int(store.edge_ptr[i]), int(store.edge_ptr[i + 1])
+            out.append((store.node_feat[n0:n1] if with_x else store.edge_feat[e0:e1], store.edge_src[e0:e1], store.edge_dst[e0:e1], store.y[i]))
+        return out
+
+    for build, with_x in ((lambda d, t: create_lightpath_graphs(d, t, fr, s["lp_feat"], s["metric"]), True),
+                          (lambda d, t: create_topological_graphs(d, t, s["lp_feat"], s["metric"]), False)):
+        base = graphs(build(data, tgt), with_x)
+        pg = graphs(build(data[perm.to(cuda)].contiguous(), tgt[perm]), with_x)
+        for j, i in enumerate(perm.tolist()):
+            assert all(torch.equal(a, b) for a, b in zip(pg[j], base[i]))
+        parts = graphs(build(data[:200].contiguous(), tgt[:200]), with_x) + graphs(build(data[200:].contiguous(), tgt[200:]), with_x)
+        assert len(parts) == S and all(torch.equal(a, b) for g, h in zip(parts, base) for a, b in zip(g, h))
