@@ -87,10 +87,12 @@ SIGNATURES = {
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer_workspace_bytes": (sz, [i64]),
     "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, P, sz, vp]),
-    "qot_lightpath_graph_count": (C.c_int, [P, P, i64, C.POINTER(QotLpGraphCfg), P, P, vp]),
-    "qot_lightpath_graph_fill": (C.c_int, [P, P, P, i64, C.POINTER(QotLpGraphCfg), P, P, P, P, P, P, P, P, vp]),
-    "qot_topological_graph_count": (C.c_int, [P, i64, C.POINTER(QotLpGraphCfg), i32, i32, i32, P, P, vp]),
-    "qot_topological_graph_fill": (C.c_int, [P, P, i64, C.POINTER(QotLpGraphCfg), i32, i32, i32, P, P, P, P, P, P, vp]),
+    "qot_lightpath_graph_scratch_bytes": (sz, [i64]),
+    "qot_lightpath_graph_count": (C.c_int, [P, P, P, i64, C.POINTER(QotLpGraphCfg), P, P, P, sz, P, vp]),
+    "qot_lightpath_graph_fill": (C.c_int, [P, i64, P, P, P, P, P, P, P, vp]),
+    "qot_topological_graph_scratch_bytes": (sz, [i64]),
+    "qot_topological_graph_count": (C.c_int, [P, P, i64, C.POINTER(QotLpGraphCfg), i32, i32, i32, P, P, P, sz, P, vp]),
+    "qot_topological_graph_fill": (C.c_int, [P, i64, P, P, P, P, P, vp]),
     "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
     "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,

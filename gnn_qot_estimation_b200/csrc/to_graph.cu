@@ -171,14 +171,19 @@ __device__ __forceinline__ void tg_scan_and_rank(TgSmem& sm, const float* __rest
   bad_out = bad;
 }
 
-template <bool kFill>
+// per-sample record of the scan pass (qot_lightpath_graph_count): everything the pack pass needs, so the
+// sample tensor is read ONCE
+struct LpRecord {
+  int n, E, pad0, pad1;
+  int conn[QOT_TG_MAX_NODES];
+  float x[QOT_TG_MAX_NODES][5];
+  unsigned adj[QOT_TG_MAX_NODES][kTgAdjWords];
+};
+
 __global__ void __launch_bounds__(kTgThreads)
-lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ freqs,
-                      const double* __restrict__ target, qot_lp_graph_cfg_t cfg, int32_t* __restrict__ counts,
-                      const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr,
-                      float* __restrict__ node_feat, int64_t* __restrict__ conn_ids,
-                      int32_t* __restrict__ edge_src, int32_t* __restrict__ edge_dst,
-                      float* __restrict__ y, int32_t* __restrict__ status) {
+lp_graph_scan_kernel(const float* __restrict__ data, const double* __restrict__ freqs,
+                     const double* __restrict__ target, qot_lp_graph_cfg_t cfg, int32_t* __restrict__ counts,
+                     LpRecord* __restrict__ records, float* __restrict__ y, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tg_smem_raw[];
   TgSmem& sm = *reinterpret_cast<TgSmem*>(tg_smem_raw);
   const int tid = threadIdx.x;
@@ -215,23 +220,70 @@ lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__
     for (int w = 0; w < kTgAdjWords; ++w) deg += __popc(sm.adj[tid][w]);
   int E;
   const int e_off = block_excl_scan(deg, sm.scan, &E);
-  if (!kFill) {
-    if (tid == 0) {
-      counts[2 * s] = n;
-      counts[2 * s + 1] = E;
-      if (bad) atomicOr(status, 1);
-    }
-    return;
+  (void)e_off;
+  LpRecord& rec = records[s];
+  if (tid == 0) {
+    counts[2 * s] = n;
+    counts[2 * s + 1] = E;
+    rec.n = n;
+    rec.E = E;
+    if (bad) atomicOr(status, 1);
   }
+  if (tid < n) {
+#pragma unroll
+    for (int w = 0; w < kTgAdjWords; ++w) rec.adj[tid][w] = sm.adj[tid][w];
+    // ---- 3. node row from the node's first channel (dataset.py:74-80; sorted-name column order)
+    const int k = sm.first[tid];
+    const int ch = sm.link[k] * Q + sm.freq[k];
+    const float osnr = d[static_cast<int64_t>(cfg.i_osnr) * LQ + ch], snr = d[static_cast<int64_t>(cfg.i_snr) * LQ + ch],
+                ber = d[static_cast<int64_t>(cfg.i_ber) * LQ + ch];
+    float* xr = rec.x[tid];
+    constexpr int col[4] = {0, 2, 3, 4};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double v = static_cast<double>(d[static_cast<int64_t>(cfg.i_feat[q]) * LQ + ch]);
+      xr[col[q]] = static_cast<float>((v - cfg.feat_lo[q]) / (cfg.feat_hi[q] - cfg.feat_lo[q]));
+    }
+    xr[1] = (osnr == -1.f && snr == -1.f && ber == -1.f) ? 1.0f : 0.0f;   // to_graph.py:247-251
+    rec.conn[tid] = sm.conn[k];
+  }
+  if (tid < 3) {
+    const double v = target[s * cfg.T + cfg.i_tgt[tid]];
+    y[s * 3 + tid] = static_cast<float>((v - cfg.tgt_lo[tid]) / (cfg.tgt_hi[tid] - cfg.tgt_lo[tid]));   // dataset.py:111-121
+  }
+}
+
+// pack pass: per-sample records -> the packed store (directed edges sorted by (source, target): one
+// adjacency row per thread)
+__global__ void __launch_bounds__(kTgThreads)
+lp_graph_pack_kernel(const LpRecord* __restrict__ records, const int64_t* __restrict__ node_ptr,
+                     const int64_t* __restrict__ edge_ptr, float* __restrict__ node_feat,
+                     int64_t* __restrict__ conn_ids, int32_t* __restrict__ edge_src,
+                     int32_t* __restrict__ edge_dst, int32_t* __restrict__ status) {
+  __shared__ int warp_sums[kTgThreads / 32];
+  const int tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  const LpRecord& rec = records[s];
+  const int n = rec.n;
   const int64_t n0 = node_ptr[s], e0 = edge_ptr[s];
-  if (node_ptr[s + 1] - n0 != n || edge_ptr[s + 1] - e0 != E) {            // offsets from another pass / another tensor
+  unsigned row[kTgAdjWords];
+  int deg = 0;
+#pragma unroll
+  for (int w = 0; w < kTgAdjWords; ++w) {
+    row[w] = tid < n ? rec.adj[tid][w] : 0u;
+    deg += __popc(row[w]);
+  }
+  int E;
+  const int e_off = block_excl_scan(deg, warp_sums, &E);
+  if (node_ptr[s + 1] - n0 != n || edge_ptr[s + 1] - e0 != E || E != rec.E) {   // offsets from another pass / another tensor
     if (tid == 0) atomicOr(status, 2);
     return;
   }
   if (tid < n) {
     int64_t o = e0 + e_off;
+#pragma unroll
     for (int w = 0; w < kTgAdjWords; ++w) {
-      unsigned m = sm.adj[tid][w];
+      unsigned m = row[w];
       while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1;
@@ -240,24 +292,9 @@ lp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__
         ++o;
       }
     }
-    // ---- 3. node row from the node's first channel (dataset.py:74-80; sorted-name column order)
-    const int k = sm.first[tid];
-    const int ch = sm.link[k] * Q + sm.freq[k];
-    const float osnr = d[static_cast<int64_t>(cfg.i_osnr) * LQ + ch], snr = d[static_cast<int64_t>(cfg.i_snr) * LQ + ch],
-                ber = d[static_cast<int64_t>(cfg.i_ber) * LQ + ch];
-    float* xr = node_feat + (n0 + tid) * 5;
-    constexpr int col[4] = {0, 2, 3, 4};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const double v = static_cast<double>(d[static_cast<int64_t>(cfg.i_feat[q]) * LQ + ch]);
-      xr[col[q]] = static_cast<float>((v - cfg.feat_lo[q]) / (cfg.feat_hi[q] - cfg.feat_lo[q]));
-    }
-    xr[1] = (osnr == -1.f && snr == -1.f && ber == -1.f) ? 1.0f : 0.0f;   // to_graph.py:247-251
-    conn_ids[n0 + tid] = sm.conn[k];
-  }
-  if (tid < 3) {
-    const double v = target[s * cfg.T + cfg.i_tgt[tid]];
-    y[s * 3 + tid] = static_cast<float>((v - cfg.tgt_lo[tid]) / (cfg.tgt_hi[tid] - cfg.tgt_lo[tid]));   // dataset.py:111-121
+    for (int q = 0; q < 5; ++q) node_feat[(n0 + tid) * 5 + q] = rec.x[tid][q];
+    conn_ids[n0 + tid] = rec.conn[tid];
   }
 }
 
@@ -277,13 +314,16 @@ struct TpSmem {
   int dkey[2 * QOT_TG_MAX_NODES];             // sort key of every directed edge candidate (-1: none)
 };
 
-template <bool kFill>
+struct TpRecord {
+  int E, pad0, pad1, pad2;
+  short src[2 * QOT_TG_MAX_NODES], dst[2 * QOT_TG_MAX_NODES];
+  float feat[2 * QOT_TG_MAX_NODES][4];
+};
+
 __global__ void __launch_bounds__(kTgThreads)
-tp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__ target, qot_lp_graph_cfg_t cfg,
-                      int num_nodes, int i_src, int i_dst, int32_t* __restrict__ counts,
-                      const int64_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_src,
-                      int32_t* __restrict__ edge_dst, float* __restrict__ edge_feat, float* __restrict__ y,
-                      int32_t* __restrict__ status) {
+tp_graph_scan_kernel(const float* __restrict__ data, const double* __restrict__ target, qot_lp_graph_cfg_t cfg,
+                     int num_nodes, int i_src, int i_dst, int32_t* __restrict__ counts,
+                     TpRecord* __restrict__ records, float* __restrict__ y, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tg_smem_raw[];
   TpSmem& tp = *reinterpret_cast<TpSmem*>(tg_smem_raw);
   TgSmem& sm = tp.base;
@@ -352,38 +392,51 @@ tp_graph_build_kernel(const float* __restrict__ data, const double* __restrict__
 #pragma unroll
     for (int u = 0; u < 2; ++u) pos[u] += kq < mine[u];
   }
-  if (!kFill) {
-    if (tid == 0) {
-      counts[s] = E;
-      if (bad) atomicOr(status, 1);
-    }
-    return;
-  }
-  const int64_t e0 = edge_ptr[s];
-  if (edge_ptr[s + 1] - e0 != E) {
-    if (tid == 0) atomicOr(status, 2);
-    return;
+  TpRecord& rec = records[s];
+  if (tid == 0) {
+    counts[s] = E;
+    rec.E = E;
+    if (bad) atomicOr(status, 1);
   }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     if (mine[u] < 0) continue;
     const int q = tid + u * kTgThreads, t = q >> 1;
     const int a = tp.ea[t], b = tp.eb[t];
-    const int64_t o = e0 + pos[u];
-    edge_src[o] = (q & 1) ? b : a;
-    edge_dst[o] = (q & 1) ? a : b;
+    const int o = pos[u];
+    rec.src[o] = static_cast<short>((q & 1) ? b : a);
+    rec.dst[o] = static_cast<short>((q & 1) ? a : b);
     // attributes of the LAST lightpath of the pair, sorted-name order [freq, mod_order, num_spans, path_len]
     const int k = sm.first[tp.tord[tp.tlast[t]]];
     const int ch = sm.link[k] * Q + sm.freq[k];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       const double v = static_cast<double>(d[static_cast<int64_t>(cfg.i_feat[f]) * LQ + ch]);
-      edge_feat[o * 4 + f] = static_cast<float>((v - cfg.feat_lo[f]) / (cfg.feat_hi[f] - cfg.feat_lo[f]));
+      rec.feat[o][f] = static_cast<float>((v - cfg.feat_lo[f]) / (cfg.feat_hi[f] - cfg.feat_lo[f]));
     }
   }
   if (tid < 3) {
     const double v = target[s * cfg.T + cfg.i_tgt[tid]];
     y[s * 3 + tid] = static_cast<float>((v - cfg.tgt_lo[tid]) / (cfg.tgt_hi[tid] - cfg.tgt_lo[tid]));
+  }
+}
+
+__global__ void __launch_bounds__(kTgThreads)
+tp_graph_pack_kernel(const TpRecord* __restrict__ records, const int64_t* __restrict__ edge_ptr,
+                     int32_t* __restrict__ edge_src, int32_t* __restrict__ edge_dst,
+                     float* __restrict__ edge_feat, int32_t* __restrict__ status) {
+  const int64_t s = blockIdx.x;
+  const TpRecord& rec = records[s];
+  const int64_t e0 = edge_ptr[s];
+  const int E = rec.E;
+  if (edge_ptr[s + 1] - e0 != E) {
+    if (threadIdx.x == 0) atomicOr(status, 2);
+    return;
+  }
+  for (int o = threadIdx.x; o < E; o += kTgThreads) {
+    edge_src[e0 + o] = rec.src[o];
+    edge_dst[e0 + o] = rec.dst[o];
+    reinterpret_cast<float4*>(edge_feat)[e0 + o] = *reinterpret_cast<const float4*>(rec.feat[o]);
   }
 }
 
@@ -399,10 +452,8 @@ static int tg_check(const float* data, const double* freqs, int64_t S, const qot
 static int tg_attr() {
   static bool done = false;
   if (!done) {
-    QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
-    QOT_CUDA(cudaFuncSetAttribute(lp_graph_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
-    QOT_CUDA(cudaFuncSetAttribute(tp_graph_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
-    QOT_CUDA(cudaFuncSetAttribute(tp_graph_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
+    QOT_CUDA(cudaFuncSetAttribute(lp_graph_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
+    QOT_CUDA(cudaFuncSetAttribute(tp_graph_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
     done = true;
   }
   return QOT_OK;
@@ -412,76 +463,73 @@ static int tg_attr() {
 
 using namespace qot;
 
-extern "C" int qot_lightpath_graph_count(const float* data, const double* freqs, int64_t S,
-                                         const qot_lp_graph_cfg_t* cfg, int32_t* counts, int32_t* status,
-                                         void* stream_) {
+extern "C" size_t qot_lightpath_graph_scratch_bytes(int64_t S) { return S > 0 ? static_cast<size_t>(S) * sizeof(LpRecord) : 256; }
+extern "C" size_t qot_topological_graph_scratch_bytes(int64_t S) { return S > 0 ? static_cast<size_t>(S) * sizeof(TpRecord) : 256; }
+
+extern "C" int qot_lightpath_graph_count(const float* data, const double* freqs, const double* target, int64_t S,
+                                         const qot_lp_graph_cfg_t* cfg, int32_t* counts, float* y, void* scratch,
+                                         size_t scratch_bytes, int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tg_check(data, freqs, S, cfg, "qot_lightpath_graph_count");
   if (rc) return rc;
-  QOT_REQUIRE(status && (S == 0 || counts), "qot_lightpath_graph_count: null output");
+  QOT_REQUIRE(status && (S == 0 || (counts && target && y)), "qot_lightpath_graph_count: null argument");
+  QOT_REQUIRE(cfg->T > 0, "qot_lightpath_graph_count: bad target extent");
+  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_lightpath_graph_count: target column out of range");
+  QOT_REQUIRE(scratch && scratch_bytes >= qot_lightpath_graph_scratch_bytes(S) && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0,
+              "qot_lightpath_graph_count: scratch missing, misaligned or smaller than qot_lightpath_graph_scratch_bytes(S)");
   if (S == 0) return QOT_OK;
   if ((rc = tg_attr())) return rc;
-  lp_graph_build_kernel<false><<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
-      data, freqs, nullptr, *cfg, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, status);
+  lp_graph_scan_kernel<<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
+      data, freqs, target, *cfg, counts, static_cast<LpRecord*>(scratch), y, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
 
-extern "C" int qot_lightpath_graph_fill(const float* data, const double* freqs, const double* target, int64_t S,
-                                        const qot_lp_graph_cfg_t* cfg, const int64_t* node_ptr,
+extern "C" int qot_lightpath_graph_fill(const void* scratch, int64_t S, const int64_t* node_ptr,
                                         const int64_t* edge_ptr, float* node_feat, int64_t* conn_ids,
-                                        int32_t* edge_src, int32_t* edge_dst, float* y, int32_t* status,
-                                        void* stream_) {
+                                        int32_t* edge_src, int32_t* edge_dst, int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = tg_check(data, freqs, S, cfg, "qot_lightpath_graph_fill");
-  if (rc) return rc;
-  QOT_REQUIRE(status && (S == 0 || (target && node_ptr && edge_ptr && node_feat && conn_ids && edge_src && edge_dst && y)),
+  QOT_REQUIRE(S >= 0 && status && (S == 0 || (scratch && node_ptr && edge_ptr && node_feat && conn_ids && edge_src && edge_dst)),
               "qot_lightpath_graph_fill: null argument");
-  QOT_REQUIRE(cfg->T > 0, "qot_lightpath_graph_fill: bad target extent");
-  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_lightpath_graph_fill: target column out of range");
   if (S == 0) return QOT_OK;
-  if ((rc = tg_attr())) return rc;
-  lp_graph_build_kernel<true><<<static_cast<unsigned>(S), kTgThreads, sizeof(TgSmem), stream>>>(
-      data, freqs, target, *cfg, nullptr, node_ptr, edge_ptr, node_feat, conn_ids, edge_src, edge_dst, y, status);
+  lp_graph_pack_kernel<<<static_cast<unsigned>(S), kTgThreads, 0, stream>>>(
+      static_cast<const LpRecord*>(scratch), node_ptr, edge_ptr, node_feat, conn_ids, edge_src, edge_dst, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
 
-extern "C" int qot_topological_graph_count(const float* data, int64_t S, const qot_lp_graph_cfg_t* cfg,
-                                           int32_t num_nodes, int32_t i_src, int32_t i_dst, int32_t* counts,
-                                           int32_t* status, void* stream_) {
+extern "C" int qot_topological_graph_count(const float* data, const double* target, int64_t S,
+                                           const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
+                                           int32_t i_dst, int32_t* counts, float* y, void* scratch,
+                                           size_t scratch_bytes, int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tg_check(data, reinterpret_cast<const double*>(data), S, cfg, "qot_topological_graph_count");
   if (rc) return rc;
-  QOT_REQUIRE(status && (S == 0 || counts), "qot_topological_graph_count: null output");
+  QOT_REQUIRE(status && (S == 0 || (counts && target && y)), "qot_topological_graph_count: null argument");
   QOT_REQUIRE(num_nodes > 0 && num_nodes < 2048 && i_src >= 0 && i_src < cfg->F && i_dst >= 0 && i_dst < cfg->F,
               "qot_topological_graph_count: bad node count or endpoint rows");
+  QOT_REQUIRE(cfg->T > 0, "qot_topological_graph_count: bad target extent");
+  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_topological_graph_count: target column out of range");
+  QOT_REQUIRE(scratch && scratch_bytes >= qot_topological_graph_scratch_bytes(S) && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0,
+              "qot_topological_graph_count: scratch missing, misaligned or smaller than qot_topological_graph_scratch_bytes(S)");
   if (S == 0) return QOT_OK;
   if ((rc = tg_attr())) return rc;
-  tp_graph_build_kernel<false><<<static_cast<unsigned>(S), kTgThreads, sizeof(TpSmem), stream>>>(
-      data, nullptr, *cfg, num_nodes, i_src, i_dst, counts, nullptr, nullptr, nullptr, nullptr, nullptr, status);
+  tp_graph_scan_kernel<<<static_cast<unsigned>(S), kTgThreads, sizeof(TpSmem), stream>>>(
+      data, target, *cfg, num_nodes, i_src, i_dst, counts, static_cast<TpRecord*>(scratch), y, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
 
-extern "C" int qot_topological_graph_fill(const float* data, const double* target, int64_t S,
-                                          const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
-                                          int32_t i_dst, const int64_t* edge_ptr, int32_t* edge_src,
-                                          int32_t* edge_dst, float* edge_feat, float* y, int32_t* status,
-                                          void* stream_) {
+extern "C" int qot_topological_graph_fill(const void* scratch, int64_t S, const int64_t* edge_ptr,
+                                          int32_t* edge_src, int32_t* edge_dst, float* edge_feat,
+                                          int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = tg_check(data, reinterpret_cast<const double*>(data), S, cfg, "qot_topological_graph_fill");
-  if (rc) return rc;
-  QOT_REQUIRE(status && (S == 0 || (target && edge_ptr && edge_src && edge_dst && edge_feat && y)),
+  QOT_REQUIRE(S >= 0 && status && (S == 0 || (scratch && edge_ptr && edge_src && edge_dst && edge_feat)),
               "qot_topological_graph_fill: null argument");
-  QOT_REQUIRE(num_nodes > 0 && num_nodes < 2048 && i_src >= 0 && i_src < cfg->F && i_dst >= 0 && i_dst < cfg->F,
-              "qot_topological_graph_fill: bad node count or endpoint rows");
-  QOT_REQUIRE(cfg->T > 0, "qot_topological_graph_fill: bad target extent");
-  for (int k = 0; k < 3; ++k) QOT_REQUIRE(cfg->i_tgt[k] >= 0 && cfg->i_tgt[k] < cfg->T, "qot_topological_graph_fill: target column out of range");
+  QOT_REQUIRE((reinterpret_cast<uintptr_t>(edge_feat) & 15) == 0, "qot_topological_graph_fill: edge_feat must be 16-byte aligned");
   if (S == 0) return QOT_OK;
-  if ((rc = tg_attr())) return rc;
-  tp_graph_build_kernel<true><<<static_cast<unsigned>(S), kTgThreads, sizeof(TpSmem), stream>>>(
-      data, target, *cfg, num_nodes, i_src, i_dst, nullptr, edge_ptr, edge_src, edge_dst, edge_feat, y, status);
+  tp_graph_pack_kernel<<<static_cast<unsigned>(S), kTgThreads, 0, stream>>>(
+      static_cast<const TpRecord*>(scratch), edge_ptr, edge_src, edge_dst, edge_feat, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

@@ -52,8 +52,9 @@ def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: tor
                             metric: Sequence[str], freq_threshold: float = 0.05,
                             return_conn_ids: bool = False):
     """data [S, F, L, Q] float32 (CUDA), target [S, T] float64, freqs [Q] float64 -> PackedGraphStore with
-    node_feat [N,5] (``NODE_FEATURES`` order, min-max scaled), y [S,3], lut_col = 1.  One host sync (the
-    per-sample counts are scanned on the device, their totals size the output)."""
+    node_feat [N,5] (``NODE_FEATURES`` order, min-max scaled), y [S,3], lut_col = 1.  The sample tensor is read
+    once (scan launch -> per-sample records), then packed; one host sync (the per-sample counts are scanned on
+    the device, their totals size the output)."""
     if not data.is_cuda:
         raise RuntimeError("create_lightpath_graphs needs CUDA tensors (gnn_qot_estimation_b200 has no CPU path)")
     dev = data.device
@@ -67,7 +68,10 @@ def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: tor
     lib = _lib.lib()
     counts = torch.zeros(S, 2, dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    check(lib.qot_lightpath_graph_count(ptr(data), ptr(freqs), S, C.byref(cfg), ptr(counts), ptr(status), stream()),
+    y = torch.empty(S, 3, dtype=torch.float32, device=dev)
+    scratch = torch.empty(lib.qot_lightpath_graph_scratch_bytes(S), dtype=torch.uint8, device=dev)
+    check(lib.qot_lightpath_graph_count(ptr(data), ptr(freqs), ptr(target), S, C.byref(cfg), ptr(counts), ptr(y),
+                                        ptr(scratch), scratch.numel(), ptr(status), stream()),
           "qot_lightpath_graph_count")
     ptrs = torch.zeros(2, S + 1, dtype=torch.int64, device=dev)
     ptrs[:, 1:] = torch.cumsum(counts.to(torch.int64).t(), dim=1)
@@ -79,11 +83,9 @@ def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: tor
     conn_ids = torch.empty(max(n_tot, 1), dtype=torch.int64, device=dev)[:n_tot]
     edge_src = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
     edge_dst = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
-    y = torch.empty(S, 3, dtype=torch.float32, device=dev)
     node_ptr, edge_ptr = ptrs[0].contiguous(), ptrs[1].contiguous()
-    check(lib.qot_lightpath_graph_fill(ptr(data), ptr(freqs), ptr(target), S, C.byref(cfg), ptr(node_ptr), ptr(edge_ptr),
-                                       ptr(node_feat), ptr(conn_ids), ptr(edge_src), ptr(edge_dst), ptr(y), ptr(status),
-                                       stream()), "qot_lightpath_graph_fill")
+    check(lib.qot_lightpath_graph_fill(ptr(scratch), S, ptr(node_ptr), ptr(edge_ptr), ptr(node_feat), ptr(conn_ids),
+                                       ptr(edge_src), ptr(edge_dst), ptr(status), stream()), "qot_lightpath_graph_fill")
     store = PackedGraphStore(node_ptr, edge_ptr, edge_src, edge_dst, node_feat, None, y, lut_col=1)
     return (store, conn_ids) if return_conn_ids else store
 
@@ -111,8 +113,11 @@ def create_topological_graphs(data: torch.Tensor, target: torch.Tensor, lp_feat:
     lib = _lib.lib()
     counts = torch.zeros(S, dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    check(lib.qot_topological_graph_count(ptr(data), S, C.byref(cfg), int(num_nodes), fi["src_id"], fi["dst_id"],
-                                          ptr(counts), ptr(status), stream()), "qot_topological_graph_count")
+    y = torch.empty(S, 3, dtype=torch.float32, device=dev)
+    scratch = torch.empty(lib.qot_topological_graph_scratch_bytes(S), dtype=torch.uint8, device=dev)
+    check(lib.qot_topological_graph_count(ptr(data), ptr(target), S, C.byref(cfg), int(num_nodes), fi["src_id"],
+                                          fi["dst_id"], ptr(counts), ptr(y), ptr(scratch), scratch.numel(),
+                                          ptr(status), stream()), "qot_topological_graph_count")
     edge_ptr = torch.zeros(S + 1, dtype=torch.int64, device=dev)
     edge_ptr[1:] = torch.cumsum(counts.to(torch.int64), dim=0)
     e_tot, st = (int(v) for v in torch.stack([edge_ptr[-1], status[0].to(torch.int64)]).tolist())
@@ -122,9 +127,7 @@ def create_topological_graphs(data: torch.Tensor, target: torch.Tensor, lp_feat:
     edge_src = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
     edge_dst = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
     edge_feat = torch.empty(max(e_tot, 1), 4, dtype=torch.float32, device=dev)[:e_tot]
-    y = torch.empty(S, 3, dtype=torch.float32, device=dev)
-    check(lib.qot_topological_graph_fill(ptr(data), ptr(target), S, C.byref(cfg), int(num_nodes), fi["src_id"],
-                                         fi["dst_id"], ptr(edge_ptr), ptr(edge_src), ptr(edge_dst), ptr(edge_feat),
-                                         ptr(y), ptr(status), stream()), "qot_topological_graph_fill")
+    check(lib.qot_topological_graph_fill(ptr(scratch), S, ptr(edge_ptr), ptr(edge_src), ptr(edge_dst), ptr(edge_feat),
+                                         ptr(status), stream()), "qot_topological_graph_fill")
     node_ptr = torch.arange(S + 1, dtype=torch.int64, device=dev) * int(num_nodes)
     return PackedGraphStore(node_ptr, edge_ptr, edge_src, edge_dst, None, edge_feat, y)

@@ -428,14 +428,17 @@ int qot_bn_bwd_sparse(const float* h, const float* mean, const float* var, float
  * One thread block per sample; output is the packed graph store qot_collate consumes.
  *   data    [S, F, L, Q] float32, 0 = free channel          freqs [Q] float64 (the dataset's grid)
  *   target  [S, T] float64
- * Two passes with the same arguments: qot_lightpath_graph_count fills counts [S,2] int32 = (nodes,
- * directed edges) per sample; the caller scans them into node_ptr / edge_ptr [S+1] int64 and calls
- * qot_lightpath_graph_fill, which writes node_feat [N_tot,5], conn_ids [N_tot] int64, edge_src /
- * edge_dst [E_tot] int32 (graph-local, both directions of every interaction, a self loop once, sorted
- * by (source, target) -- the reference's own edge ORDER follows CPython set iteration and is not part
- * of the contract) and y [S,3].  status (int32[1], zeroed by the caller): bit 0 = a sample exceeds the
+ * Two launches, the sample tensor is read once: qot_lightpath_graph_count scans every sample, fills
+ * counts [S,2] int32 = (nodes, directed edges), y [S,3] and a per-sample record in `scratch`
+ * (qot_lightpath_graph_scratch_bytes(S) bytes, 16-byte aligned: node rows, conn ids, adjacency bits);
+ * the caller scans the counts into node_ptr / edge_ptr [S+1] int64 and calls
+ * qot_lightpath_graph_fill, which packs the records into node_feat [N_tot,5], conn_ids [N_tot] int64,
+ * edge_src / edge_dst [E_tot] int32 (graph-local, both directions of every interaction, a self loop
+ * once, sorted by (source, target) -- the reference's own edge ORDER follows CPython set iteration and
+ * is not part of the contract).  status (int32[1], zeroed by the caller): bit 0 = a sample exceeds the
  * per-block capacities (QOT_TG_MAX_CHANNELS occupied channels, QOT_TG_MAX_NODES lightpaths, L <=
- * QOT_TG_MAX_LINKS); such a sample is reported with zero nodes. */
+ * QOT_TG_MAX_LINKS); such a sample is reported with zero nodes; bit 1 = node_ptr / edge_ptr do not
+ * match the records. */
 #define QOT_TG_MAX_CHANNELS 6144
 #define QOT_TG_MAX_NODES 256
 #define QOT_TG_MAX_LINKS 1024
@@ -448,32 +451,32 @@ typedef struct {
   double tgt_lo[3], tgt_hi[3];     /* constants.py TARGET_RANGES                                           */
   double freq_threshold;           /* to_graph.py:188 (0.05)                                               */
 } qot_lp_graph_cfg_t;
-int qot_lightpath_graph_count(const float* data, const double* freqs, int64_t S,
-                              const qot_lp_graph_cfg_t* cfg, int32_t* counts, int32_t* status,
-                              void* stream);
-int qot_lightpath_graph_fill(const float* data, const double* freqs, const double* target, int64_t S,
-                             const qot_lp_graph_cfg_t* cfg, const int64_t* node_ptr,
+size_t qot_lightpath_graph_scratch_bytes(int64_t S);
+int qot_lightpath_graph_count(const float* data, const double* freqs, const double* target, int64_t S,
+                              const qot_lp_graph_cfg_t* cfg, int32_t* counts, float* y, void* scratch,
+                              size_t scratch_bytes, int32_t* status, void* stream);
+int qot_lightpath_graph_fill(const void* scratch, int64_t S, const int64_t* node_ptr,
                              const int64_t* edge_ptr, float* node_feat, int64_t* conn_ids,
-                             int32_t* edge_src, int32_t* edge_dst, float* y, int32_t* status,
-                             void* stream);
+                             int32_t* edge_src, int32_t* edge_dst, int32_t* status, void* stream);
 
 /* The topological representation: to_graph.py::create_topological_graph (:62-184: one edge per
  * lightpath between its source and destination network node, lightpaths added in ascending conn_id,
  * nx.Graph keeps one edge per node pair -- position from the first, attributes from the last) fused
  * with topological_training/dataset.py:46-123 (relabelling copy, from_networkx edge order, min-max
  * scaled edge_attr in sorted-name order [freq, mod_order, num_spans, path_len], y).  Every sample has
- * num_nodes nodes (75, to_graph.py:134; node_ptr = num_nodes * s, no node features).  Same two-pass
- * protocol: counts [S] int32 = directed edges per sample; then edge_src / edge_dst [E_tot] int32 in
+ * num_nodes nodes (75, to_graph.py:134; node_ptr = num_nodes * s, no node features).  Same two-launch
+ * protocol (scan into `scratch` + counts [S] int32 = directed edges per sample and y; then pack):
+ * edge_src / edge_dst [E_tot] int32 in
  * the REFERENCE'S edge order, edge_feat [E_tot,4], y [S,3].  i_src / i_dst: lp_feat rows of src_id /
  * dst_id (1-based node ids).  status bit 0: capacity exceeded or an endpoint outside 1..num_nodes. */
-int qot_topological_graph_count(const float* data, int64_t S, const qot_lp_graph_cfg_t* cfg,
-                                int32_t num_nodes, int32_t i_src, int32_t i_dst, int32_t* counts,
-                                int32_t* status, void* stream);
-int qot_topological_graph_fill(const float* data, const double* target, int64_t S,
-                               const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
-                               int32_t i_dst, const int64_t* edge_ptr, int32_t* edge_src,
-                               int32_t* edge_dst, float* edge_feat, float* y, int32_t* status,
-                               void* stream);
+size_t qot_topological_graph_scratch_bytes(int64_t S);
+int qot_topological_graph_count(const float* data, const double* target, int64_t S,
+                                const qot_lp_graph_cfg_t* cfg, int32_t num_nodes, int32_t i_src,
+                                int32_t i_dst, int32_t* counts, float* y, void* scratch,
+                                size_t scratch_bytes, int32_t* status, void* stream);
+int qot_topological_graph_fill(const void* scratch, int64_t S, const int64_t* edge_ptr,
+                               int32_t* edge_src, int32_t* edge_dst, float* edge_feat,
+                               int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

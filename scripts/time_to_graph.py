@@ -1,5 +1,5 @@
 """Developer tool: device graph construction throughput (both representations), kernels timed with CUDA
-events around the whole call (two launches + the offset scan + one host sync)."""
+events around the whole call (scan launch + offset scan + one host sync + pack launch)."""
 import sys, time, torch
 sys.path.insert(0, ".")
 from gnn_qot_estimation_b200 import synthetic
@@ -20,6 +20,6 @@ for (L, Q) in ((60, 80), (37, 50)):
             st = fn()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        gb = data.numel() * 4 * 2 / 1e9                                   # two passes over the sample tensor
+        gb = data.numel() * 4 / 1e9                                       # the sample tensor is read once
         print(f"{name:12s} [F=10,L={L},Q={Q}] x {data.shape[0]} samples: {ms:.3f} ms = {data.shape[0]/ms*1e3:.3g} samples/s, "
-              f"{gb/ms*1e3:.0f} GB/s of input traffic (2 passes), nodes {int(st.node_ptr[-1])}, edges {int(st.edge_ptr[-1])}")
+              f"{gb/ms*1e3:.0f} GB/s of input (read once), nodes {int(st.node_ptr[-1])}, edges {int(st.edge_ptr[-1])}")
