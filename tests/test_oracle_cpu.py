@@ -308,3 +308,43 @@ def test_gat_edges_ref():
     ei = torch.tensor([[0, 1, 1, 2], [0, 2, 1, 0]])
     out = oracle.gat_edges_ref(ei, 3)
     assert out.tolist() == [[1, 2, 0, 1, 2], [2, 0, 0, 1, 2]]
+
+
+def test_hand_written_backward_matches_autograd():
+    """oracle/topo_fused_math.py (the per-graph forward + SmoothL1 + backward a fused training kernel evaluates,
+    written out without autograd) == autograd of TopologicalGNNOracle, fp64, ragged graphs incl. isolated
+    nodes and duplicate edges."""
+    import torch
+    from oracle import TopologicalGNNOracle
+    from oracle.topo_fused_math import graph_fwd_bwd
+    from gnn_qot_estimation_b200 import Batch
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(6)
+    m = TopologicalGNNOracle(20, 16, 3, 4, dropout_p=0.0).double()
+    sizes = [14, 3, 20, 1, 9]
+    ids, eis, eas, bts, off = [], [], [], [], 0
+    per_graph = []
+    for gi, n in enumerate(sizes):
+        E = 0 if n == 1 else 3 * n
+        src, dst = torch.randint(0, n, (E,), generator=g), torch.randint(0, n, (E,), generator=g)
+        ea = torch.rand(E, 4, generator=g, dtype=torch.float64)
+        nid = torch.randperm(20, generator=g)[:n]
+        per_graph.append((nid, src, dst, ea))
+        ids.append(nid); eis.append(torch.stack([src, dst]) + off); eas.append(ea); bts.append(torch.full((n,), gi)); off += n
+    y = torch.rand(len(sizes), 3, generator=g, dtype=torch.float64) * 3 - 1      # some |diff| > 1: both SmoothL1 branches
+    b = Batch(x=None, edge_index=torch.cat(eis, 1), edge_attr=torch.cat(eas), batch=torch.cat(bts),
+              node_ids=torch.cat(ids), num_graphs=len(sizes))
+    out = m(b)
+    loss = torch.nn.SmoothL1Loss()(out, y)
+    loss.backward()
+    p = {k: v.detach() for k, v in m.state_dict().items()}
+    tot, grads = 0.0, {k: torch.zeros_like(v) for k, v in p.items()}
+    for gi, (nid, src, dst, ea) in enumerate(per_graph):
+        o, l, gg = graph_fwd_bwd(p, nid, src, dst, ea, y[gi], 3 * len(sizes))
+        assert torch.allclose(o, out[gi].detach(), rtol=1e-12, atol=1e-12)
+        tot = tot + l
+        for k, v in gg.items():
+            grads[k] += v
+    assert abs(float(tot) - float(loss)) < 1e-12
+    for k, prm in m.named_parameters():
+        assert torch.allclose(grads[k], prm.grad, rtol=1e-9, atol=1e-12), k
