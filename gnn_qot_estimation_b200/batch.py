@@ -160,8 +160,16 @@ class PackedGraphStore:
         if self.lut_col is not None and x is not None:
             from . import ops
             lut_ptr = ops.lightpath_lut_ptr(x, optr, self.lut_col)
-        return Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
-                     ptr=optr, edge_ptr=oeptr, lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
+        b = Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
+                  ptr=optr, edge_ptr=oeptr, lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
+        # largest graph of the batch (host arrays, no sync): sizes the per-graph kernels' shared memory
+        if isinstance(ids, range) and ids.step == 1:
+            dn, de = np.diff(nph[g0:g1 + 1]), np.diff(eph[g0:g1 + 1])
+        else:
+            dn, de = nph[ids_np + 1] - nph[ids_np], eph[ids_np + 1] - eph[ids_np]
+        b.max_nodes = int(dn.max()) if B else 0
+        b.max_edges = int(de.max()) if B else 0
+        return b
 
     # -- host-side view of a contiguous range (what a host DataLoader would hand over)
     def host_batch(self, g0: int, g1: int, pin: bool = False) -> Batch:

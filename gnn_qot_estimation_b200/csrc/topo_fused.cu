@@ -1,0 +1,592 @@
+// TopologicalGNN, one thread block per graph: the whole forward (Embedding -> TransformerConv -> LeakyReLU
+// -> NNConv(mean) -> LeakyReLU -> global_mean_pool -> MLP; topological_training/models.py:43-64) in one
+// launch, and the whole backward (forward recomputed from the inputs, then every parameter gradient) in
+// another.  Nothing couples the graphs of a batch in this model, so all activations of a graph live in
+// shared memory (n <= 96 nodes: ~1.3 KB per node, 60 B per edge); the 4 092 parameters sit beside them
+// (with transposed copies so that every inner loop reads consecutive banks) and, in the backward, so does
+// a gradient accumulator of the same size plus the embedding-table gradient.  Blocks are persistent over
+// graphs; every gradient element is owned by one thread and summed over nodes / edges / graphs in a fixed
+// order; per-block partials go to global memory and are summed in block order by a second kernel:
+// bit-reproducible for a given grid.  NNConv in factorised form (T_j = h1_j [P_0..P_7 | P_b]),
+// the per-destination softmax in edge order.  The math, line by line, is oracle/topo_fused_math.py.
+// Reference shape only: hidden 16, edge_dim 4, edge MLP 4 -> 8 -> 256, out 3; dropout must be inactive.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qot {
+
+constexpr int TF_H = 16, TF_K = 8, TF_D = 4, TF_KP = 9, TF_T = TF_KP * TF_H;   // T row: 144 floats
+// flat parameter / gradient layout (floats); W2 | b2 are held as P[c][k*16+o] in shared memory
+constexpr int oWq = 0, obq = 256, oWk = 272, obk = 528, oWv = 544, obv = 800, oWs = 816, obs = 1072, oWe = 1088,
+              oW1 = 1152, ob1 = 1184, oW2 = 1192, ob2 = 3240, oWroot = 3496, obias2 = 3752, oWm1 = 3768,
+              obm1 = 4024, oWm2 = 4040, obm2 = 4088, kTfParams = 4092;
+constexpr int kTfThreads = 128;
+constexpr float kTfSlope = 0.01f;
+
+struct TfPtrs {                  // carved out of dynamic shared memory
+  float *par, *WqT, *WkT, *WvT, *WsT, *WrootT, *Wm1T;    // par: flat layout, with P at oW2 (oW2..ob2+256)
+  float *grad, *gemb;                                      // backward only
+  float *X, *Q, *K, *V, *H1, *B1, *B2, *G1, *G2, *G3, *T;  // node arrays (G*: backward only)
+  float *attr, *hid, *alpha, *dlogit, *dhid;               // edge arrays (dlogit, dhid: backward only)
+  int *rowd, *rows;                                        // CSR by destination / by source: [nmax + 1]
+  unsigned short *src, *dst, *permd, *perms;               // [emax]
+  float *small;                                            // pool[16] pre1[16] z1[16] out[4] dpool[16] dpre1[16] dout[4]
+};
+
+__host__ __device__ inline size_t tf_smem_bytes(int nmax, int emax, int num_nodes, bool bwd) {
+  size_t f = kTfParams + 6 * 256;
+  if (bwd) f += kTfParams + static_cast<size_t>(num_nodes) * TF_H;
+  f += static_cast<size_t>(nmax) * (TF_H * (bwd ? 10 : 7) + TF_T);
+  f += static_cast<size_t>(emax) * (TF_D + TF_K + (bwd ? 2 + TF_K : 1));
+  f += 96;
+  size_t b = f * 4 + 2 * static_cast<size_t>(nmax + 1) * 4 + 4 * static_cast<size_t>(emax) * 2;
+  return (b + 15) & ~static_cast<size_t>(15);
+}
+
+__device__ inline TfPtrs tf_carve(char* base, int nmax, int emax, int num_nodes, bool bwd) {
+  TfPtrs p;
+  float* f = reinterpret_cast<float*>(base);
+  auto take = [&](size_t n) { float* r = f; f += n; return r; };
+  p.par = take(kTfParams);
+  p.WqT = take(256); p.WkT = take(256); p.WvT = take(256); p.WsT = take(256); p.WrootT = take(256); p.Wm1T = take(256);
+  p.grad = bwd ? take(kTfParams) : nullptr;
+  p.gemb = bwd ? take(static_cast<size_t>(num_nodes) * TF_H) : nullptr;
+  p.X = take(nmax * TF_H); p.Q = take(nmax * TF_H); p.K = take(nmax * TF_H); p.V = take(nmax * TF_H);
+  p.H1 = take(nmax * TF_H); p.B1 = take(nmax * TF_H); p.B2 = take(nmax * TF_H);
+  p.G1 = bwd ? take(nmax * TF_H) : nullptr; p.G2 = bwd ? take(nmax * TF_H) : nullptr; p.G3 = bwd ? take(nmax * TF_H) : nullptr;
+  p.T = take(static_cast<size_t>(nmax) * TF_T);
+  p.attr = take(static_cast<size_t>(emax) * TF_D); p.hid = take(static_cast<size_t>(emax) * TF_K); p.alpha = take(emax);
+  p.dlogit = bwd ? take(emax) : nullptr;
+  p.dhid = bwd ? take(static_cast<size_t>(emax) * TF_K) : nullptr;
+  p.small = take(96);
+  int* ip = reinterpret_cast<int*>(f);
+  p.rowd = ip; ip += nmax + 1;
+  p.rows = ip; ip += nmax + 1;
+  unsigned short* sp = reinterpret_cast<unsigned short*>(ip);
+  p.src = sp; sp += emax; p.dst = sp; sp += emax; p.permd = sp; sp += emax; p.perms = sp;
+  return p;
+}
+
+__device__ __forceinline__ float tf_lk(float v) { return v > 0.f ? v : kTfSlope * v; }
+__device__ __forceinline__ float tf_dlk_from_act(float act) { return act > 0.f ? 1.f : kTfSlope; }   // act = leaky(pre): same sign
+__device__ __forceinline__ float tf_sum16(float v) {                       // over an aligned 16-lane group
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o, 16);
+  return v;
+}
+
+// parameters -> shared memory (flat copy, P rearrangement of W2 | b2, transposed 16x16 matrices)
+__device__ void tf_load_params(const TfPtrs& p, const float* __restrict__ flat) {
+  for (int i = threadIdx.x; i < kTfParams; i += kTfThreads)
+    if (i < oW2 || i >= oWroot) p.par[i] = flat[i];
+  // P[c][k*16+o] = W2[(c*16+o)*8 + k] (k < 8), P[c][8*16+o] = b2[c*16+o]; stored at par + oW2, row stride 144
+  for (int i = threadIdx.x; i < TF_H * TF_T; i += kTfThreads) {
+    const int c = i / TF_T, r = i % TF_T, k = r / TF_H, o = r % TF_H;
+    p.par[oW2 + i] = k < TF_K ? flat[oW2 + (c * TF_H + o) * TF_K + k] : flat[ob2 + c * TF_H + o];
+  }
+  for (int i = threadIdx.x; i < 256; i += kTfThreads) {
+    const int a = i >> 4, b = i & 15;                  // T[b][a] = W[a][b]
+    p.WqT[b * 16 + a] = flat[oWq + i]; p.WkT[b * 16 + a] = flat[oWk + i]; p.WvT[b * 16 + a] = flat[oWv + i];
+    p.WsT[b * 16 + a] = flat[oWs + i]; p.WrootT[b * 16 + a] = flat[oWroot + i]; p.Wm1T[b * 16 + a] = flat[oWm1 + i];
+  }
+}
+
+// One graph, forward.  Leaves in shared memory everything the backward needs: X Q K V H1 (leaky(O1)),
+// B1 = H2 (leaky(O2)), T, attr, hid, alpha, both CSRs, small[] = pool | pre1 | z1 | out.
+__device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
+                                 const int64_t* __restrict__ esrc, const int64_t* __restrict__ edst,
+                                 const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes) {
+  const int tid = threadIdx.x;
+  const float* par = p.par;
+  // ---- inputs
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int i = idx >> 4, c = idx & 15;
+    long long id = node_ids[n0 + i];
+    id = id < 0 ? 0 : (id >= num_nodes ? num_nodes - 1 : id);
+    p.X[idx] = emb[id * TF_H + c];
+  }
+  for (int e = tid; e < E; e += kTfThreads) {
+    p.src[e] = static_cast<unsigned short>(esrc[e0 + e] - n0);
+    p.dst[e] = static_cast<unsigned short>(edst[e0 + e] - n0);
+  }
+  for (int idx = tid; idx < E * TF_D; idx += kTfThreads) p.attr[idx] = eattr[e0 * TF_D + idx];
+  __syncthreads();
+  // ---- both CSRs (stable: edge order inside a row), one node per thread
+  for (int i = tid; i < n; i += kTfThreads) {
+    int cd = 0, cs = 0;
+    for (int e = 0; e < E; ++e) { cd += p.dst[e] == i; cs += p.src[e] == i; }
+    p.rowd[i + 1] = cd; p.rows[i + 1] = cs;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.rowd[0] = 0; p.rows[0] = 0;
+    for (int i = 0; i < n; ++i) { p.rowd[i + 1] += p.rowd[i]; p.rows[i + 1] += p.rows[i]; }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kTfThreads) {
+    int pd = p.rowd[i], ps = p.rows[i];
+    for (int e = 0; e < E; ++e) {
+      if (p.dst[e] == i) p.permd[pd++] = static_cast<unsigned short>(e);
+      if (p.src[e] == i) p.perms[ps++] = static_cast<unsigned short>(e);
+    }
+  }
+  // ---- node projections q k v (skip goes straight into O1, held in B2 for now)
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int i = idx >> 4, c = idx & 15;
+    float q = par[obq + c], k = par[obk + c], v = par[obv + c], s = par[obs + c];
+#pragma unroll
+    for (int d = 0; d < TF_H; ++d) {
+      const float x = p.X[i * TF_H + d];
+      q = fmaf(x, p.WqT[d * 16 + c], q); k = fmaf(x, p.WkT[d * 16 + c], k);
+      v = fmaf(x, p.WvT[d * 16 + c], v); s = fmaf(x, p.WsT[d * 16 + c], s);
+    }
+    p.Q[idx] = q; p.K[idx] = k; p.V[idx] = v; p.B2[idx] = s;
+  }
+  // ---- edge MLP hidden layer
+  for (int idx = tid; idx < E * TF_K; idx += kTfThreads) {
+    const int e = idx >> 3, k = idx & 7;
+    float h = par[ob1 + k];
+#pragma unroll
+    for (int d = 0; d < TF_D; ++d) h = fmaf(p.attr[e * TF_D + d], par[oW1 + k * TF_D + d], h);
+    p.hid[idx] = fmaxf(h, 0.f);
+  }
+  __syncthreads();
+  // ---- TransformerConv attention: 16 lanes (channels) per destination node, in-edges in edge order
+  for (int base = 0; base < n * TF_H; base += kTfThreads) {
+    const int idx = base + tid, i = idx >> 4, c = idx & 15;
+    const bool valid = idx < n * TF_H;
+    const int r0 = valid ? p.rowd[i] : 0, r1 = valid ? p.rowd[i + 1] : 0;
+    int rmax = r1 - r0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = max(rmax, __shfl_xor_sync(kFull, rmax, o));
+    const float qi = valid ? p.Q[idx] : 0.f;
+    float mx = -INFINITY;
+    for (int r = 0; r < rmax; ++r) {                    // pass 1: logits (kept in alpha[]) and their maximum
+      const bool on = r0 + r < r1;
+      const int e = on ? p.permd[r0 + r] : 0;
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float lg = tf_sum16(on ? qi * (p.K[p.src[e] * TF_H + c] + ee) : 0.f) * 0.25f;
+      if (on) {
+        mx = fmaxf(mx, lg);
+        if (c == 0) p.alpha[e] = lg;
+      }
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int r = r0; r < r1; ++r) den += expf(p.alpha[p.permd[r]] - mx);          // every lane, same order
+    float acc = valid ? p.B2[idx] : 0.f;                // skip term
+    for (int r = r0; r < r1; ++r) {
+      const int e = p.permd[r];
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float a = expf(p.alpha[e] - mx) / (den + 1e-16f);
+      acc = fmaf(a, p.V[p.src[e] * TF_H + c] + ee, acc);
+    }
+    __syncwarp();
+    for (int r = r0; r < r1; ++r) {                     // logits -> weights (lane 0 of the group)
+      const int e = p.permd[r];
+      if (c == 0) p.alpha[e] = expf(p.alpha[e] - mx) / (den + 1e-16f);
+    }
+    if (valid) p.H1[idx] = tf_lk(acc);
+  }
+  __syncthreads();
+  // ---- factorised NNConv: T_j = h1_j P
+  for (int idx = tid; idx < n * TF_T; idx += kTfThreads) {
+    const int j = idx / TF_T, r = idx % TF_T;
+    float t = 0.f;
+#pragma unroll
+    for (int c = 0; c < TF_H; ++c) t = fmaf(p.H1[j * TF_H + c], par[oW2 + c * TF_T + r], t);
+    p.T[idx] = t;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int i = idx >> 4, o = idx & 15;
+    const int r0 = p.rowd[i], r1 = p.rowd[i + 1];
+    float m = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const int e = p.permd[r];
+      const float* t = p.T + p.src[e] * TF_T + o;
+      float me = t[TF_K * TF_H];                        // the bias slab (hid' = 1)
+#pragma unroll
+      for (int k = 0; k < TF_K; ++k) me = fmaf(p.hid[e * TF_K + k], t[k * TF_H], me);
+      m += me;
+    }
+    float v = m / static_cast<float>(max(r1 - r0, 1)) + par[obias2 + o];
+#pragma unroll
+    for (int c = 0; c < TF_H; ++c) v = fmaf(p.H1[i * TF_H + c], p.WrootT[c * 16 + o], v);
+    p.B1[idx] = tf_lk(v);
+  }
+  __syncthreads();
+  // ---- global mean pool + MLP head (one warp)
+  float* pool = p.small; float* pre1 = p.small + 16; float* z1 = p.small + 32; float* outv = p.small + 48;
+  if (tid < TF_H) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += p.B1[i * TF_H + tid];
+    pool[tid] = s / static_cast<float>(max(n, 1));
+  }
+  __syncthreads();
+  if (tid < TF_H) {
+    float h = par[obm1 + tid];
+#pragma unroll
+    for (int o = 0; o < TF_H; ++o) h = fmaf(pool[o], p.Wm1T[o * 16 + tid], h);
+    pre1[tid] = h;
+    z1[tid] = tf_lk(h);
+  }
+  __syncthreads();
+  if (tid < QOT_OUT) {
+    float o3 = par[obm2 + tid];
+#pragma unroll
+    for (int o = 0; o < TF_H; ++o) o3 = fmaf(z1[o], par[oWm2 + tid * TF_H + o], o3);
+    outv[tid] = o3;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTfThreads)
+topo_fused_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
+                      const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
+                      const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
+                      int num_nodes, float* __restrict__ out, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) char tf_smem[];
+  const TfPtrs p = tf_carve(tf_smem, nmax, emax, num_nodes, false);
+  tf_load_params(p, flat);
+  __syncthreads();
+  for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
+    const int64_t n0 = gptr[g], e0 = eptr[g];
+    const int64_t n = gptr[g + 1] - n0, E = eptr[g + 1] - e0;
+    if (n < 0 || E < 0 || n > nmax || E > emax) {       // caps come from the same arrays on the host: never expected
+      if (threadIdx.x == 0) atomicOr(status, 1);
+      continue;
+    }
+    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes);
+    if (threadIdx.x < QOT_OUT) out[g * QOT_OUT + threadIdx.x] = p.small[48 + threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// forward recomputed, then the backward of one graph given d loss / d out; gradients accumulate in p.grad
+// (flat layout, P layout for W2 | b2) and p.gemb
+__device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ node_ids, int64_t n0, int n, int E,
+                                  int num_nodes) {
+  const int tid = threadIdx.x;
+  const float* par = p.par;
+  float* g = p.grad;
+  float* pool = p.small; float* pre1 = p.small + 16; float* z1 = p.small + 32;
+  float* dpool = p.small + 64; float* dpre1 = p.small + 80; const float* dout = p.small + 52;
+  // ---- MLP head
+  if (tid < TF_H) {
+    float dz = 0.f;
+#pragma unroll
+    for (int k = 0; k < QOT_OUT; ++k) dz = fmaf(par[oWm2 + k * TF_H + tid], dout[k], dz);
+    dpre1[tid] = dz * (pre1[tid] > 0.f ? 1.f : kTfSlope);
+#pragma unroll
+    for (int k = 0; k < QOT_OUT; ++k) g[oWm2 + k * TF_H + tid] += dout[k] * z1[tid];
+    if (tid < QOT_OUT) g[obm2 + tid] += dout[tid];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 256; idx += kTfThreads) g[oWm1 + idx] += dpre1[idx >> 4] * pool[idx & 15];
+  if (tid < TF_H) {
+    g[obm1 + tid] += dpre1[tid];
+    float d = 0.f;
+#pragma unroll
+    for (int o = 0; o < TF_H; ++o) d = fmaf(par[oWm1 + o * TF_H + tid], dpre1[o], d);
+    dpool[tid] = d / static_cast<float>(max(n, 1));
+  }
+  __syncthreads();
+  // ---- dO2 (in place of H2 in B1); dH1 starts in B2
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) p.B1[idx] = dpool[idx & 15] * tf_dlk_from_act(p.B1[idx]);
+  __syncthreads();
+  if (tid < TF_H) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += p.B1[i * TF_H + tid];
+    g[obias2 + tid] += s;
+  }
+  for (int idx = tid; idx < 256; idx += kTfThreads) {   // dWroot[o][c] += sum_i dO2[i][o] h1[i][c]
+    const int o = idx >> 4, c = idx & 15;
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = fmaf(p.B1[i * TF_H + o], p.H1[i * TF_H + c], s);
+    g[oWroot + idx] += s;
+  }
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int i = idx >> 4, c = idx & 15;
+    float d = 0.f;
+#pragma unroll
+    for (int o = 0; o < TF_H; ++o) d = fmaf(par[oWroot + o * TF_H + c], p.B1[i * TF_H + o], d);
+    p.B2[idx] = d;
+  }
+  // ---- d hid' per edge (needs T of the source), edge-MLP layer-1 gradients
+  for (int idx = tid; idx < E * TF_K; idx += kTfThreads) {
+    const int e = idx >> 3, k = idx & 7, i = p.dst[e];
+    const float inv = 1.f / static_cast<float>(max(p.rowd[i + 1] - p.rowd[i], 1));
+    const float* t = p.T + p.src[e] * TF_T + k * TF_H;
+    float d = 0.f;
+#pragma unroll
+    for (int o = 0; o < TF_H; ++o) d = fmaf(t[o], p.B1[i * TF_H + o], d);
+    p.dhid[idx] = p.hid[idx] > 0.f ? d * inv : 0.f;
+  }
+  __syncthreads();
+  if (tid < TF_K * TF_D) {                              // dW1[k][d] += sum_e dhidpre[e][k] attr[e][d]
+    const int k = tid >> 2, d = tid & 3;
+    float s = 0.f;
+    for (int e = 0; e < E; ++e) s = fmaf(p.dhid[e * TF_K + k], p.attr[e * TF_D + d], s);
+    g[oW1 + tid] += s;
+  } else if (tid < TF_K * TF_D + TF_K) {
+    const int k = tid - TF_K * TF_D;
+    float s = 0.f;
+    for (int e = 0; e < E; ++e) s += p.dhid[e * TF_K + k];
+    g[ob1 + k] += s;
+  }
+  __syncthreads();
+  // ---- dT_j (over the out-edges of j, edge order) overwrites T_j
+  for (int idx = tid; idx < n * TF_T; idx += kTfThreads) {
+    const int j = idx / TF_T, r = idx % TF_T, k = r >> 4, o = r & 15;
+    float s = 0.f;
+    for (int q = p.rows[j]; q < p.rows[j + 1]; ++q) {
+      const int e = p.perms[q], i = p.dst[e];
+      const float inv = 1.f / static_cast<float>(max(p.rowd[i + 1] - p.rowd[i], 1));
+      const float hk = k < TF_K ? p.hid[e * TF_K + k] : 1.f;
+      s = fmaf(hk, p.B1[i * TF_H + o] * inv, s);
+    }
+    p.T[idx] = s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TF_H * TF_T; idx += kTfThreads) {   // dP[c][r] += sum_j h1[j][c] dT_j[r]
+    const int c = idx / TF_T, r = idx % TF_T;
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) s = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s);
+    g[oW2 + idx] += s;
+  }
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dH1[j][c] += sum_r P[c][r] dT_j[r]; then dO1
+    const int j = idx >> 4, c = idx & 15;
+    float d = p.B2[idx];
+    const float* pr = par + oW2 + c * TF_T;
+    const float* t = p.T + j * TF_T;
+    for (int r = 0; r < TF_T; ++r) d = fmaf(pr[r], t[r], d);
+    p.B2[idx] = d * tf_dlk_from_act(p.H1[idx]);
+  }
+  __syncthreads();
+  // ---- skip projection
+  if (tid < TF_H) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += p.B2[i * TF_H + tid];
+    g[obs + tid] += s;
+  }
+  for (int idx = tid; idx < 256; idx += kTfThreads) {
+    const int c = idx >> 4, k = idx & 15;
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = fmaf(p.B2[i * TF_H + c], p.X[i * TF_H + k], s);
+    g[oWs + idx] += s;
+  }
+  // ---- attention backward, destination side: dalpha, dlogit (per edge), dQ (G1)
+  __syncthreads();
+  for (int base = 0; base < n * TF_H; base += kTfThreads) {
+    const int idx = base + tid, i = idx >> 4, c = idx & 15;
+    const bool valid = idx < n * TF_H;
+    const int r0 = valid ? p.rowd[i] : 0, r1 = valid ? p.rowd[i + 1] : 0;
+    int rmax = r1 - r0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = max(rmax, __shfl_xor_sync(kFull, rmax, o));
+    const float gi = valid ? p.B2[idx] : 0.f, qi = valid ? p.Q[idx] : 0.f;
+    float tsum = 0.f;
+    for (int r = 0; r < rmax; ++r) {                    // pass 1: dalpha_e (kept in dlogit[]), t = sum alpha dalpha
+      const bool on = r0 + r < r1;
+      const int e = on ? p.permd[r0 + r] : 0;
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float da = tf_sum16(on ? gi * (p.V[p.src[e] * TF_H + c] + ee) : 0.f);
+      if (on) {
+        tsum = fmaf(p.alpha[e], da, tsum);
+        if (c == 0) p.dlogit[e] = da;
+      }
+    }
+    __syncwarp();
+    float dq = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const int e = p.permd[r];
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float dl = p.alpha[e] * (p.dlogit[e] - tsum);
+      dq = fmaf(dl, (p.K[p.src[e] * TF_H + c] + ee) * 0.25f, dq);
+    }
+    __syncwarp();
+    for (int r = r0; r < r1; ++r) {
+      const int e = p.permd[r];
+      if (c == 0) p.dlogit[e] = p.alpha[e] * (p.dlogit[e] - tsum);
+    }
+    if (valid) p.G1[idx] = dq;
+    (void)qi;
+  }
+  __syncthreads();
+  // ---- source side: dV (G3), dK (G2) over the out-edges of j, edge order
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int j = idx >> 4, c = idx & 15;
+    float dv = 0.f, dk = 0.f;
+    for (int q = p.rows[j]; q < p.rows[j + 1]; ++q) {
+      const int e = p.perms[q], i = p.dst[e];
+      dv = fmaf(p.alpha[e], p.B2[i * TF_H + c], dv);
+      dk = fmaf(p.dlogit[e], p.Q[i * TF_H + c] * 0.25f, dk);
+    }
+    p.G3[idx] = dv; p.G2[idx] = dk;
+  }
+  if (tid < TF_H * TF_D) {                                // dWe[c][d] += sum_e (dmsg_e[c] + dkey_e[c]) attr[e][d]
+    const int c = tid >> 2, d = tid & 3;
+    float s = 0.f;
+    for (int e = 0; e < E; ++e) {
+      const int i = p.dst[e];
+      s = fmaf(fmaf(p.alpha[e], p.B2[i * TF_H + c], p.dlogit[e] * p.Q[i * TF_H + c] * 0.25f), p.attr[e * TF_D + d], s);
+    }
+    g[oWe + tid] += s;
+  }
+  __syncthreads();
+  // ---- q / k / v weight gradients, dX, embedding rows
+  if (tid < 3 * TF_H) {
+    const int w = tid >> 4, c = tid & 15;
+    const float* G = w == 0 ? p.G1 : (w == 1 ? p.G2 : p.G3);
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += G[i * TF_H + c];
+    g[(w == 0 ? obq : (w == 1 ? obk : obv)) + c] += s;
+  }
+  for (int idx = tid; idx < 3 * 256; idx += kTfThreads) {
+    const int w = idx >> 8, c = (idx >> 4) & 15, k = idx & 15;
+    const float* G = w == 0 ? p.G1 : (w == 1 ? p.G2 : p.G3);
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = fmaf(G[i * TF_H + c], p.X[i * TF_H + k], s);
+    g[(w == 0 ? oWq : (w == 1 ? oWk : oWv)) + (idx & 255)] += s;
+  }
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dX[i][k] into B1 (dO2 is dead)
+    const int i = idx >> 4, k = idx & 15;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < TF_H; ++c) {
+      d = fmaf(p.B2[i * TF_H + c], par[oWs + c * TF_H + k], d);
+      d = fmaf(p.G1[i * TF_H + c], par[oWq + c * TF_H + k], d);
+      d = fmaf(p.G2[i * TF_H + c], par[oWk + c * TF_H + k], d);
+      d = fmaf(p.G3[i * TF_H + c], par[oWv + c * TF_H + k], d);
+    }
+    p.T[idx] = d;                                         // T is dead: dX lives there
+  }
+  __syncthreads();
+  if (tid < TF_H) {                                       // one thread per column, nodes in order: duplicates of an id are summed deterministically
+    for (int i = 0; i < n; ++i) {
+      long long id = node_ids[n0 + i];
+      id = id < 0 ? 0 : (id >= num_nodes ? num_nodes - 1 : id);
+      p.gemb[id * TF_H + tid] += p.T[i * TF_H + tid];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTfThreads)
+topo_fused_bwd_kernel(const float* __restrict__ flat, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
+                      const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
+                      const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
+                      int num_nodes, const float* __restrict__ dout, float* __restrict__ partial,
+                      int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) char tf_smem[];
+  const TfPtrs p = tf_carve(tf_smem, nmax, emax, num_nodes, true);
+  tf_load_params(p, flat);
+  const int gsz = kTfParams + num_nodes * TF_H;
+  for (int i = threadIdx.x; i < gsz; i += kTfThreads) p.grad[i] = 0.f;       // grad | gemb are contiguous
+  __syncthreads();
+  for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
+    const int64_t n0 = gptr[g], e0 = eptr[g];
+    const int64_t n = gptr[g + 1] - n0, E = eptr[g + 1] - e0;
+    if (n < 0 || E < 0 || n > nmax || E > emax) {
+      if (threadIdx.x == 0) atomicOr(status, 1);
+      continue;
+    }
+    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes);
+    if (threadIdx.x < QOT_OUT) p.small[52 + threadIdx.x] = dout[g * QOT_OUT + threadIdx.x];
+    __syncthreads();
+    tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes);
+  }
+  float* dst = partial + static_cast<size_t>(blockIdx.x) * gsz;
+  for (int i = threadIdx.x; i < gsz; i += kTfThreads) dst[i] = p.grad[i];
+}
+
+// per-block partials -> flat gradient (block order: fixed summation order); W2 | b2 back from the P layout
+__global__ void topo_fused_reduce_kernel(const float* __restrict__ partial, int blocks, int num_nodes,
+                                         float* __restrict__ gflat, float* __restrict__ gemb) {
+  const int gsz = kTfParams + num_nodes * TF_H;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= gsz) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partial[static_cast<size_t>(b) * gsz + i];
+  if (i >= kTfParams) { gemb[i - kTfParams] = s; return; }
+  if (i >= oW2 && i < oWroot) {
+    const int q = i - oW2, c = q / TF_T, r = q % TF_T, k = r / TF_H, o = r % TF_H;
+    if (k < TF_K) gflat[oW2 + (c * TF_H + o) * TF_K + k] = s; else gflat[ob2 + c * TF_H + o] = s;
+    return;
+  }
+  gflat[i] = s;
+}
+
+}  // namespace qot
+
+using namespace qot;
+
+extern "C" int qot_topo_fused_params(void) { return kTfParams; }
+
+static int tf_check(int64_t B, int nmax, int emax, int num_nodes, const char* who) {
+  QOT_REQUIRE(B >= 0 && nmax >= 0 && emax >= 0 && num_nodes > 0, "%s: bad sizes", who);
+  QOT_REQUIRE(nmax <= 4096 && emax <= 60000, "%s: graph too large for one block", who);
+  return QOT_OK;
+}
+
+extern "C" int qot_topo_fused_fwd(const float* flat, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
+                                  int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
+                                  int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, float* out,
+                                  int32_t* status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_fwd");
+  if (rc) return rc;
+  QOT_REQUIRE(flat && emb && gptr && eptr && status && (B == 0 || out), "qot_topo_fused_fwd: null argument");
+  if (B == 0) return QOT_OK;
+  const size_t smem = tf_smem_bytes(nmax, emax, num_nodes, false);
+  QOT_REQUIRE(smem <= 227 * 1024, "qot_topo_fused_fwd: graphs of %d nodes / %d edges need %zu bytes of shared memory", nmax, emax, smem);
+  QOT_CUDA(cudaFuncSetAttribute(topo_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (228 * 1024) / (smem + 1024))));
+  const int blocks = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(per_sm) * kNumSMs));
+  topo_fused_fwd_kernel<<<blocks, kTfThreads, smem, stream>>>(flat, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
+                                                             nmax, emax, num_nodes, out, status);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+extern "C" size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes) {
+  return static_cast<size_t>(4 * kNumSMs) * (kTfParams + static_cast<size_t>(std::max(num_nodes, 0)) * TF_H) * 4 + 256;
+}
+
+extern "C" int qot_topo_fused_bwd(const float* flat, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
+                                  int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
+                                  int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, const float* dout,
+                                  float* gflat, float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_bwd");
+  if (rc) return rc;
+  QOT_REQUIRE(flat && emb && gptr && eptr && status && gflat && gemb && (B == 0 || dout), "qot_topo_fused_bwd: null argument");
+  QOT_REQUIRE(ws && ws_bytes >= qot_topo_fused_bwd_workspace_bytes(num_nodes), "qot_topo_fused_bwd: workspace too small");
+  const int gsz = kTfParams + num_nodes * TF_H;
+  if (B == 0) {
+    QOT_CUDA(cudaMemsetAsync(gflat, 0, kTfParams * 4, stream));
+    QOT_CUDA(cudaMemsetAsync(gemb, 0, static_cast<size_t>(num_nodes) * TF_H * 4, stream));
+    return QOT_OK;
+  }
+  const size_t smem = tf_smem_bytes(nmax, emax, num_nodes, true);
+  QOT_REQUIRE(smem <= 227 * 1024, "qot_topo_fused_bwd: graphs of %d nodes / %d edges need %zu bytes of shared memory", nmax, emax, smem);
+  QOT_CUDA(cudaFuncSetAttribute(topo_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (228 * 1024) / (smem + 1024))));
+  const int blocks = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(per_sm) * kNumSMs));
+  topo_fused_bwd_kernel<<<blocks, kTfThreads, smem, stream>>>(flat, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
+                                                             nmax, emax, num_nodes, dout, static_cast<float*>(ws), status);
+  QOT_LAUNCH_CHECK();
+  topo_fused_reduce_kernel<<<(gsz + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(ws), blocks, num_nodes, gflat, gemb);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}

@@ -8,7 +8,7 @@ torch only allocates the tensors.
 from __future__ import annotations
 
 import ctypes as C
-from typing import NamedTuple, Optional
+from typing import Sequence, NamedTuple, Optional
 
 import torch
 
@@ -692,6 +692,83 @@ def nnconv_mean(x, graph: GraphIndex, edge_attr, W1, b1, W2, b2, Wroot, bias, sl
     Pcat = torch.cat([W2.view(H, H, K).permute(0, 2, 1).reshape(H, K * H), b2.view(H, H), Wroot.t()], dim=1)
     yr = node_linear(x, Pcat.t().contiguous(), None)      # W argument is [out,in]
     return _NNConvEdgeFn.apply(yr, edge_attr, W1, b1, bias, graph, slope)
+
+
+# --------------------------------------------------------------------------- #
+# TopologicalGNN, one block per graph (csrc/topo_fused.cu)
+# --------------------------------------------------------------------------- #
+def batch_max_sizes(data):
+    """(largest node count, largest edge count) of a graph in the batch.  Collates of this package record
+    them from host arrays; a foreign batch costs one device->host read, cached on the batch."""
+    if getattr(data, "max_nodes", None) is not None and getattr(data, "max_edges", None) is not None:
+        return int(data.max_nodes), int(data.max_edges)
+    cache = batch_cache(data)
+    if "max_sizes" not in cache:
+        gptr = batch_graph_ptr(data)
+        eptr = getattr(data, "edge_ptr", None)
+        if eptr is None:
+            if "eptr" not in cache:
+                cache["eptr"] = edge_ptr(data.edge_index, data.batch, gptr.numel() - 1)
+            eptr = cache["eptr"][0]
+        if gptr.numel() < 2:
+            cache["max_sizes"] = (0, 0)
+        else:
+            v = torch.stack([(gptr[1:] - gptr[:-1]).max(), (eptr[1:] - eptr[:-1]).max()]).tolist()
+            cache["max_sizes"] = (int(v[0]), int(v[1]))
+    return cache["max_sizes"]
+
+
+class _TopoFusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax: int, emax: int):
+        L = _lib.lib()
+        B = int(gptr.numel() - 1)
+        dev = flat.device
+        flat_, emb_ = _f32(flat.detach()), _f32(emb.detach())
+        node_ids, edge_index, edge_attr = _i64(node_ids), _i64(edge_index), _edge_attr(edge_attr)
+        out = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(L.qot_topo_fused_fwd(ptr(flat_), ptr(emb_), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
+                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, int(nmax), int(emax), int(emb_.shape[0]),
+                                   ptr(out), ptr(status), stream()), "qot_topo_fused_fwd")
+        ctx.save_for_backward(flat_, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status)
+        ctx.sizes = (int(nmax), int(emax))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, status = ctx.saved_tensors
+        nmax, emax = ctx.sizes
+        B = int(gptr.numel() - 1)
+        dev = flat.device
+        gflat = torch.empty_like(flat)
+        gemb = torch.empty_like(emb)
+        ws = _ws(L.qot_topo_fused_bwd_workspace_bytes(int(emb.shape[0])), dev)
+        check(L.qot_topo_fused_bwd(ptr(flat), ptr(emb), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
+                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, nmax, emax, int(emb.shape[0]),
+                                   ptr(_f32(dout)), ptr(gflat), ptr(gemb), ptr(ws), ws.numel(), ptr(status), stream()),
+              "qot_topo_fused_bwd")
+        return gflat, gemb, None, None, None, None, None, None, None
+
+
+TOPO_FUSED_SMEM_LIMIT = 227 * 1024
+
+
+def topo_fused_fits(nmax: int, emax: int, num_nodes: int) -> bool:
+    """Whether one graph of the batch fits one block's shared memory in the BACKWARD kernel (the larger one)."""
+    P = _lib.lib().qot_topo_fused_params()
+    floats = P + 6 * 256 + P + num_nodes * 16 + nmax * (16 * 10 + 144) + emax * (4 + 8 + 2 + 8) + 96
+    nbytes = floats * 4 + 2 * (nmax + 1) * 4 + 4 * emax * 2 + 16
+    return nmax <= 4096 and emax <= 60000 and nbytes <= TOPO_FUSED_SMEM_LIMIT
+
+
+def topological_fused(params: Sequence[torch.Tensor], emb, node_ids, edge_index, edge_attr, gptr, eptr,
+                      nmax: int, emax: int):
+    """out [B,3] of TopologicalGNN (reference shape) with one launch forward / two backward.  `params` in the
+    order of include/qot_b200.h (qot_topo_fused_fwd)."""
+    flat = torch.cat([p.reshape(-1) for p in params] + [params[0].new_zeros(1)])
+    return _TopoFusedFn.apply(flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax, emax)
 
 
 # --------------------------------------------------------------------------- #

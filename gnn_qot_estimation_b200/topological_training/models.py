@@ -12,6 +12,8 @@ projection -> NNConv edge kernel (+leaky_relu) -> pool + MLP head.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.nn import Dropout, LeakyReLU, Linear, ReLU
@@ -42,6 +44,33 @@ class TopologicalGNN(torch.nn.Module):
         )
         self.dropout = torch.nn.Dropout(p=dropout_p)
 
+    # one block per graph (csrc/topo_fused.cu): the reference shape, embedding branch, dropout inactive, every
+    # graph of the batch small enough for one block's shared memory.  QOT_TOPO_FUSED=0 switches it off.
+    use_fused = os.environ.get("QOT_TOPO_FUSED", "1") != "0"
+
+    def _fused_path(self, data, node_ids, edge_index, edge_attr):
+        c1, c2 = self.conv1, self.conv2
+        if not self.use_fused or node_ids is None or edge_attr is None:
+            return None
+        if (self.training and (self.dropout.p > 0 or self.mlp[2].p > 0)):
+            return None
+        if (c1.in_channels, c1.out_channels, c1.lin_edge.in_features) != (16, 16, 4) or self.mlp[3].out_features != 3 \
+                or c2.nn[0].out_features != 8 or self.mlp[0].out_features != 16:
+            return None
+        gptr = ops.batch_graph_ptr(data)
+        eptr = getattr(data, "edge_ptr", None)
+        if eptr is None:
+            return None                                 # foreign batch: edges may not be grouped by graph
+        nmax, emax = ops.batch_max_sizes(data)
+        if not ops.topo_fused_fits(nmax, emax, self.node_embeddings.num_embeddings):
+            return None
+        params = [c1.lin_query.weight, c1.lin_query.bias, c1.lin_key.weight, c1.lin_key.bias, c1.lin_value.weight,
+                  c1.lin_value.bias, c1.lin_skip.weight, c1.lin_skip.bias, c1.lin_edge.weight,
+                  c2.nn[0].weight, c2.nn[0].bias, c2.nn[2].weight, c2.nn[2].bias, c2.lin.weight, c2.bias,
+                  self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias]
+        return ops.topological_fused(params, self.node_embeddings.weight, node_ids, edge_index, edge_attr, gptr, eptr,
+                                     nmax, emax)
+
     def forward(self, data):
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if not edge_index.is_cuda:
@@ -52,6 +81,9 @@ class TopologicalGNN(torch.nn.Module):
             n = int(node_ids.shape[0])
         else:
             n = int(x.shape[0])
+        fused = self._fused_path(data, node_ids, edge_index, edge_attr)
+        if fused is not None:
+            return fused
         graph = ops.batch_graph(data, n)
         x = self.conv1(x, edge_index, edge_attr, graph=graph, node_ids=node_ids, slope=LEAKY)
         x = self.dropout(x)

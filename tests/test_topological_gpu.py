@@ -191,3 +191,62 @@ def test_cpu_batch_is_refused():
     hb = synthetic.nsfnet_store(2, seed=0).host_batch(0, 2)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(hb)
+
+
+def _ragged_topo_batch(cuda, sizes, num_nodes, seed):
+    from gnn_qot_estimation_b200 import Batch
+    g = torch.Generator().manual_seed(seed)
+    ids, eis, eas, bts, ptr, eptr, off = [], [], [], [], [0], [0], 0
+    for gi, n in enumerate(sizes):
+        E = 0 if n == 1 else int(torch.randint(n, 4 * n, (1,), generator=g))
+        src, dst = torch.randint(0, n, (E,), generator=g), torch.randint(0, n, (E,), generator=g)
+        ids.append(torch.randperm(num_nodes, generator=g)[:n]); eis.append(torch.stack([src, dst]) + off)
+        eas.append(torch.rand(E, 4, generator=g)); bts.append(torch.full((n,), gi)); off += n
+        ptr.append(off); eptr.append(eptr[-1] + E)
+    b = Batch(x=None, edge_index=torch.cat(eis, 1), edge_attr=torch.cat(eas), batch=torch.cat(bts), node_ids=torch.cat(ids),
+              ptr=torch.tensor(ptr), edge_ptr=torch.tensor(eptr), num_graphs=len(sizes))
+    y = torch.rand(len(sizes), 3, generator=g) * 3 - 1
+    return b, y
+
+
+@pytest.mark.parametrize("sizes,num_nodes", [([14] * 64, 14), ([14, 3, 20, 1, 9, 75, 40, 2] * 9, 75), ([75] * 5, 75)])
+def test_fused_block_per_graph_path_matches_oracle_and_layer_path(cuda, sizes, num_nodes):
+    """csrc/topo_fused.cu (one block per graph, forward + recomputing backward) against the fp64 oracle
+    (out, loss, every gradient: 1e-5 relative) and against the layer-by-layer kernels; bit-reproducible."""
+    from gnn_qot_estimation_b200 import TopologicalGNN
+    from oracle import TopologicalGNNOracle
+    torch.manual_seed(1)
+    m = TopologicalGNN(num_nodes, 16, 3, edge_dim=4, dropout_p=0.0)
+    o = TopologicalGNNOracle(num_nodes, 16, 3, 4, dropout_p=0.0).double()
+    o.load_state_dict(m.state_dict(), strict=True)
+    m = m.to(cuda)
+    hb, y = _ragged_topo_batch(cuda, sizes, num_nodes, seed=len(sizes))
+    b = hb.to(cuda)
+    b.max_nodes, b.max_edges = None, None                      # foreign batch: sizes read back once, cached
+
+    def run(fused):
+        m.use_fused = fused
+        m.zero_grad(set_to_none=True)
+        out = m(b)
+        loss = torch.nn.SmoothL1Loss()(out, y.to(cuda))
+        loss.backward()
+        return out.detach().clone(), loss.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+    of, lf, gf = run(True)
+    of2, _, gf2 = run(True)
+    ol, ll, gl = run(False)
+    m.use_fused = True
+    assert torch.equal(of, of2) and all(torch.equal(gf[k], gf2[k]) for k in gf)        # deterministic
+    hb64 = hb.to("cpu"); hb64.edge_attr = hb64.edge_attr.double()
+    eo = o(hb64)
+    el = torch.nn.SmoothL1Loss()(eo, y.double())
+    el.backward()
+    ref = {k: p.grad for k, p in o.named_parameters()}
+    floor = 1e-3 * max(float(v.abs().max()) for v in ref.values())
+    assert rel_err(of, eo.detach()) <= RTOL and rel_err(lf, el.detach()) <= RTOL
+    assert rel_err(of, ol) <= RTOL
+    for k in gf:
+        err = float((gf[k].double().cpu() - ref[k]).abs().max()) / max(float(ref[k].abs().max()), floor)
+        assert err <= RTOL, (k, err)
+        errl = float((gf[k] - gl[k]).abs().max()) / max(float(gl[k].abs().max()), floor)
+        assert errl <= RTOL, (k, errl)
