@@ -35,6 +35,10 @@ class GraphedTrainStep:
                             **{k: (getattr(example, k).clone() if getattr(example, k) is not None else None)
                                for k in _FIELDS})
         self.shapes = {k: tuple(getattr(example, k).shape) for k in _FIELDS if getattr(example, k) is not None}
+        # largest graph of the batch: sizes the shared memory of the block-per-graph kernels; read once here
+        # (one host sync for a foreign batch), a constant of the captured step afterwards
+        from . import ops
+        self.static.max_nodes, self.static.max_edges = ops.batch_max_sizes(example)
         self.stream = torch.cuda.Stream()
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
@@ -76,6 +80,10 @@ class GraphedTrainStep:
             if t is None or tuple(t.shape) != shape:
                 raise RuntimeError(f"GraphedTrainStep was captured for {k}{shape}; got "
                                    f"{None if t is None else tuple(t.shape)} (static shapes only)")
+        mn, me = getattr(batch, "max_nodes", None), getattr(batch, "max_edges", None)
+        if (mn is not None and mn > self.static.max_nodes) or (me is not None and me > self.static.max_edges):
+            raise RuntimeError(f"GraphedTrainStep was captured for graphs of <= {self.static.max_nodes} nodes / "
+                               f"{self.static.max_edges} edges; got {mn} / {me}")
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             for k in self.shapes:
