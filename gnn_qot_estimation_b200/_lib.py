@@ -94,6 +94,8 @@ SIGNATURES = {
     "qot_topological_graph_count": (C.c_int, [P, P, i64, C.POINTER(QotLpGraphCfg), i32, i32, i32, P, P, P, sz, P, vp]),
     "qot_topological_graph_fill": (C.c_int, [P, i64, P, P, P, P, P, vp]),
     "qot_topo_fused_params": (C.c_int, []),
+    "qot_topo_fused_prepared_floats": (C.c_int, []),
+    "qot_topo_fused_prepare": (C.c_int, [P, P, vp]),
     "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i32, i32, i32, P, P, vp]),
     "qot_topo_fused_bwd_workspace_bytes": (sz, [i32]),
     "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i32, i32, i32, P, P, P, P, sz, P, vp]),

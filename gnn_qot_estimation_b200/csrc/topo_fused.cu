@@ -24,8 +24,9 @@ constexpr int oWq = 0, obq = 256, oWk = 272, obk = 528, oWv = 544, obv = 800, oW
 constexpr int kTfThreads = 128;
 constexpr float kTfSlope = 0.01f;
 
-struct TfPtrs {                  // carved out of dynamic shared memory
-  float *par, *WqT, *WkT, *WvT, *WsT, *WrootT, *Wm1T;    // par: flat layout, with P at oW2 (oW2..ob2+256)
+constexpr int kTfPrepared = kTfParams + 6 * 256;          // flat (P layout at oW2) | WqT WkT WvT WsT WrootT Wm1T
+struct TfPtrs {                  // par..Wm1T: the prepared GLOBAL buffer (16 KB, L1-resident); the rest is shared memory
+  const float *par, *WqT, *WkT, *WvT, *WsT, *WrootT, *Wm1T;    // par: flat layout, with P at oW2 (oW2..ob2+256)
   float *grad, *gemb;                                      // backward only
   float *X, *Q, *K, *V, *H1, *B1, *B2, *G1, *G2, *G3, *T;  // node arrays (G*: backward only)
   float *attr, *hid, *alpha, *dlogit, *dhid;               // edge arrays (dlogit, dhid: backward only)
@@ -35,7 +36,7 @@ struct TfPtrs {                  // carved out of dynamic shared memory
 };
 
 __host__ __device__ inline size_t tf_smem_bytes(int nmax, int emax, int num_nodes, bool bwd) {
-  size_t f = kTfParams + 6 * 256;
+  size_t f = 0;
   if (bwd) f += kTfParams + static_cast<size_t>(num_nodes) * TF_H;
   f += static_cast<size_t>(nmax) * (TF_H * (bwd ? 10 : 7) + TF_T);
   f += static_cast<size_t>(emax) * (TF_D + TF_K + (bwd ? 2 + TF_K : 1));
@@ -44,12 +45,13 @@ __host__ __device__ inline size_t tf_smem_bytes(int nmax, int emax, int num_node
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
-__device__ inline TfPtrs tf_carve(char* base, int nmax, int emax, int num_nodes, bool bwd) {
+__device__ inline TfPtrs tf_carve(char* base, const float* __restrict__ prep, int nmax, int emax, int num_nodes, bool bwd) {
   TfPtrs p;
   float* f = reinterpret_cast<float*>(base);
   auto take = [&](size_t n) { float* r = f; f += n; return r; };
-  p.par = take(kTfParams);
-  p.WqT = take(256); p.WkT = take(256); p.WvT = take(256); p.WsT = take(256); p.WrootT = take(256); p.Wm1T = take(256);
+  p.par = prep;
+  p.WqT = prep + kTfParams; p.WkT = p.WqT + 256; p.WvT = p.WkT + 256; p.WsT = p.WvT + 256; p.WrootT = p.WsT + 256;
+  p.Wm1T = p.WrootT + 256;
   p.grad = bwd ? take(kTfParams) : nullptr;
   p.gemb = bwd ? take(static_cast<size_t>(num_nodes) * TF_H) : nullptr;
   p.X = take(nmax * TF_H); p.Q = take(nmax * TF_H); p.K = take(nmax * TF_H); p.V = take(nmax * TF_H);
@@ -76,19 +78,21 @@ __device__ __forceinline__ float tf_sum16(float v) {                       // ov
   return v;
 }
 
-// parameters -> shared memory (flat copy, P rearrangement of W2 | b2, transposed 16x16 matrices)
-__device__ void tf_load_params(const TfPtrs& p, const float* __restrict__ flat) {
-  for (int i = threadIdx.x; i < kTfParams; i += kTfThreads)
-    if (i < oW2 || i >= oWroot) p.par[i] = flat[i];
-  // P[c][k*16+o] = W2[(c*16+o)*8 + k] (k < 8), P[c][8*16+o] = b2[c*16+o]; stored at par + oW2, row stride 144
-  for (int i = threadIdx.x; i < TF_H * TF_T; i += kTfThreads) {
+// parameters -> the prepared buffer (flat copy, P rearrangement of W2 | b2, transposed 16x16 matrices); one block
+__global__ void __launch_bounds__(256)
+topo_fused_prepare_kernel(const float* __restrict__ flat, float* __restrict__ prep) {
+  for (int i = threadIdx.x; i < kTfParams; i += blockDim.x)
+    if (i < oW2 || i >= oWroot) prep[i] = flat[i];
+  // P[c][k*16+o] = W2[(c*16+o)*8 + k] (k < 8), P[c][8*16+o] = b2[c*16+o]; stored at oW2, row stride 144
+  for (int i = threadIdx.x; i < TF_H * TF_T; i += blockDim.x) {
     const int c = i / TF_T, r = i % TF_T, k = r / TF_H, o = r % TF_H;
-    p.par[oW2 + i] = k < TF_K ? flat[oW2 + (c * TF_H + o) * TF_K + k] : flat[ob2 + c * TF_H + o];
+    prep[oW2 + i] = k < TF_K ? flat[oW2 + (c * TF_H + o) * TF_K + k] : flat[ob2 + c * TF_H + o];
   }
-  for (int i = threadIdx.x; i < 256; i += kTfThreads) {
+  float* t = prep + kTfParams;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const int a = i >> 4, b = i & 15;                  // T[b][a] = W[a][b]
-    p.WqT[b * 16 + a] = flat[oWq + i]; p.WkT[b * 16 + a] = flat[oWk + i]; p.WvT[b * 16 + a] = flat[oWv + i];
-    p.WsT[b * 16 + a] = flat[oWs + i]; p.WrootT[b * 16 + a] = flat[oWroot + i]; p.Wm1T[b * 16 + a] = flat[oWm1 + i];
+    t[b * 16 + a] = flat[oWq + i]; t[256 + b * 16 + a] = flat[oWk + i]; t[512 + b * 16 + a] = flat[oWv + i];
+    t[768 + b * 16 + a] = flat[oWs + i]; t[1024 + b * 16 + a] = flat[oWroot + i]; t[1280 + b * 16 + a] = flat[oWm1 + i];
   }
 }
 
@@ -98,7 +102,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
                                  const int64_t* __restrict__ esrc, const int64_t* __restrict__ edst,
                                  const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes) {
   const int tid = threadIdx.x;
-  const float* par = p.par;
+  const float* __restrict__ par = p.par;
   // ---- inputs
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int i = idx >> 4, c = idx & 15;
@@ -246,15 +250,13 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTfThreads)
-topo_fused_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
+__global__ void __launch_bounds__(kTfThreads, 7)
+topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
                       int num_nodes, float* __restrict__ out, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tf_smem[];
-  const TfPtrs p = tf_carve(tf_smem, nmax, emax, num_nodes, false);
-  tf_load_params(p, flat);
-  __syncthreads();
+  const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, false);
   for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
     const int64_t n0 = gptr[g], e0 = eptr[g];
     const int64_t n = gptr[g + 1] - n0, E = eptr[g + 1] - e0;
@@ -482,15 +484,14 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTfThreads)
-topo_fused_bwd_kernel(const float* __restrict__ flat, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
+__global__ void __launch_bounds__(kTfThreads, 7)
+topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
                       int num_nodes, const float* __restrict__ dout, float* __restrict__ partial,
                       int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tf_smem[];
-  const TfPtrs p = tf_carve(tf_smem, nmax, emax, num_nodes, true);
-  tf_load_params(p, flat);
+  const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, true);
   const int gsz = kTfParams + num_nodes * TF_H;
   for (int i = threadIdx.x; i < gsz; i += kTfThreads) p.grad[i] = 0.f;       // grad | gemb are contiguous
   __syncthreads();
@@ -510,14 +511,23 @@ topo_fused_bwd_kernel(const float* __restrict__ flat, const float* __restrict__ 
   for (int i = threadIdx.x; i < gsz; i += kTfThreads) dst[i] = p.grad[i];
 }
 
-// per-block partials -> flat gradient (block order: fixed summation order); W2 | b2 back from the P layout
-__global__ void topo_fused_reduce_kernel(const float* __restrict__ partial, int blocks, int num_nodes,
-                                         float* __restrict__ gflat, float* __restrict__ gemb) {
+// per-block partials -> flat gradient; W2 | b2 back from the P layout.  256 threads = 8 slices of the block
+// range x 32 gradient elements; slice sums are combined in slice order: a fixed summation tree
+__global__ void __launch_bounds__(256)
+topo_fused_reduce_kernel(const float* __restrict__ partial, int blocks, int num_nodes,
+                         float* __restrict__ gflat, float* __restrict__ gemb) {
+  __shared__ float part[8][32];
   const int gsz = kTfParams + num_nodes * TF_H;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= gsz) return;
+  const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[static_cast<size_t>(b) * gsz + i];
+  if (i < gsz)
+    for (int b = sl; b < blocks; b += 8) s += partial[static_cast<size_t>(b) * gsz + i];
+  part[sl][col] = s;
+  __syncthreads();
+  if (sl != 0 || i >= gsz) return;
+#pragma unroll
+  for (int r = 1; r < 8; ++r) s += part[r][col];
   if (i >= kTfParams) { gemb[i - kTfParams] = s; return; }
   if (i >= oW2 && i < oWroot) {
     const int q = i - oW2, c = q / TF_T, r = q % TF_T, k = r / TF_H, o = r % TF_H;
@@ -532,6 +542,21 @@ __global__ void topo_fused_reduce_kernel(const float* __restrict__ partial, int 
 using namespace qot;
 
 extern "C" int qot_topo_fused_params(void) { return kTfParams; }
+extern "C" int qot_topo_fused_prepared_floats(void) { return kTfPrepared; }
+
+extern "C" int qot_topo_fused_prepare(const float* flat, float* prepared, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(flat && prepared, "qot_topo_fused_prepare: null argument");
+  topo_fused_prepare_kernel<<<1, 256, 0, stream>>>(flat, prepared);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+static int tf_blocks(int64_t B, size_t smem) {
+  // resident blocks per SM: shared memory, 64 registers x 128 threads, at most 8
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(7, (228 * 1024) / (smem + 1024))));
+  return static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(per_sm) * kNumSMs));
+}
 
 static int tf_check(int64_t B, int nmax, int emax, int num_nodes, const char* who) {
   QOT_REQUIRE(B >= 0 && nmax >= 0 && emax >= 0 && num_nodes > 0, "%s: bad sizes", who);
@@ -539,38 +564,37 @@ static int tf_check(int64_t B, int nmax, int emax, int num_nodes, const char* wh
   return QOT_OK;
 }
 
-extern "C" int qot_topo_fused_fwd(const float* flat, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
+extern "C" int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
                                   int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, float* out,
                                   int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_fwd");
   if (rc) return rc;
-  QOT_REQUIRE(flat && emb && gptr && eptr && status && (B == 0 || out), "qot_topo_fused_fwd: null argument");
+  QOT_REQUIRE(prepared && emb && gptr && eptr && status && (B == 0 || out), "qot_topo_fused_fwd: null argument");
   if (B == 0) return QOT_OK;
   const size_t smem = tf_smem_bytes(nmax, emax, num_nodes, false);
   QOT_REQUIRE(smem <= 227 * 1024, "qot_topo_fused_fwd: graphs of %d nodes / %d edges need %zu bytes of shared memory", nmax, emax, smem);
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (228 * 1024) / (smem + 1024))));
-  const int blocks = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(per_sm) * kNumSMs));
-  topo_fused_fwd_kernel<<<blocks, kTfThreads, smem, stream>>>(flat, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
+  const int blocks = tf_blocks(B, smem);
+  topo_fused_fwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
                                                              nmax, emax, num_nodes, out, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
 
 extern "C" size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes) {
-  return static_cast<size_t>(4 * kNumSMs) * (kTfParams + static_cast<size_t>(std::max(num_nodes, 0)) * TF_H) * 4 + 256;
+  return static_cast<size_t>(8 * kNumSMs) * (kTfParams + static_cast<size_t>(std::max(num_nodes, 0)) * TF_H) * 4 + 256;
 }
 
-extern "C" int qot_topo_fused_bwd(const float* flat, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
+extern "C" int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
                                   int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, const float* dout,
                                   float* gflat, float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_bwd");
   if (rc) return rc;
-  QOT_REQUIRE(flat && emb && gptr && eptr && status && gflat && gemb && (B == 0 || dout), "qot_topo_fused_bwd: null argument");
+  QOT_REQUIRE(prepared && emb && gptr && eptr && status && gflat && gemb && (B == 0 || dout), "qot_topo_fused_bwd: null argument");
   QOT_REQUIRE(ws && ws_bytes >= qot_topo_fused_bwd_workspace_bytes(num_nodes), "qot_topo_fused_bwd: workspace too small");
   const int gsz = kTfParams + num_nodes * TF_H;
   if (B == 0) {
@@ -581,12 +605,11 @@ extern "C" int qot_topo_fused_bwd(const float* flat, const float* emb, const int
   const size_t smem = tf_smem_bytes(nmax, emax, num_nodes, true);
   QOT_REQUIRE(smem <= 227 * 1024, "qot_topo_fused_bwd: graphs of %d nodes / %d edges need %zu bytes of shared memory", nmax, emax, smem);
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (228 * 1024) / (smem + 1024))));
-  const int blocks = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(per_sm) * kNumSMs));
-  topo_fused_bwd_kernel<<<blocks, kTfThreads, smem, stream>>>(flat, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
+  const int blocks = tf_blocks(B, smem);
+  topo_fused_bwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
                                                              nmax, emax, num_nodes, dout, static_cast<float*>(ws), status);
   QOT_LAUNCH_CHECK();
-  topo_fused_reduce_kernel<<<(gsz + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(ws), blocks, num_nodes, gflat, gemb);
+  topo_fused_reduce_kernel<<<(gsz + 31) / 32, 256, 0, stream>>>(static_cast<const float*>(ws), blocks, num_nodes, gflat, gemb);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

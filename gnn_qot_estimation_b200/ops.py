@@ -728,24 +728,26 @@ class _TopoFusedFn(torch.autograd.Function):
         node_ids, edge_index, edge_attr = _i64(node_ids), _i64(edge_index), _edge_attr(edge_attr)
         out = torch.empty(B, 3, dtype=torch.float32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(L.qot_topo_fused_fwd(ptr(flat_), ptr(emb_), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
+        prep = torch.empty(L.qot_topo_fused_prepared_floats(), dtype=torch.float32, device=dev)
+        check(L.qot_topo_fused_prepare(ptr(flat_), ptr(prep), stream()), "qot_topo_fused_prepare")
+        check(L.qot_topo_fused_fwd(ptr(prep), ptr(emb_), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
                                    ptr(edge_attr), ptr(gptr), ptr(eptr), B, int(nmax), int(emax), int(emb_.shape[0]),
                                    ptr(out), ptr(status), stream()), "qot_topo_fused_fwd")
-        ctx.save_for_backward(flat_, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status)
+        ctx.save_for_backward(prep, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status)
         ctx.sizes = (int(nmax), int(emax))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, status = ctx.saved_tensors
+        prep, emb, node_ids, edge_index, edge_attr, gptr, eptr, status = ctx.saved_tensors
         nmax, emax = ctx.sizes
         B = int(gptr.numel() - 1)
-        dev = flat.device
-        gflat = torch.empty_like(flat)
+        dev = prep.device
+        gflat = torch.empty(L.qot_topo_fused_params(), dtype=torch.float32, device=dev)
         gemb = torch.empty_like(emb)
         ws = _ws(L.qot_topo_fused_bwd_workspace_bytes(int(emb.shape[0])), dev)
-        check(L.qot_topo_fused_bwd(ptr(flat), ptr(emb), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
+        check(L.qot_topo_fused_bwd(ptr(prep), ptr(emb), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
                                    ptr(edge_attr), ptr(gptr), ptr(eptr), B, nmax, emax, int(emb.shape[0]),
                                    ptr(_f32(dout)), ptr(gflat), ptr(gemb), ptr(ws), ws.numel(), ptr(status), stream()),
               "qot_topo_fused_bwd")
@@ -758,7 +760,7 @@ TOPO_FUSED_SMEM_LIMIT = 227 * 1024
 def topo_fused_fits(nmax: int, emax: int, num_nodes: int) -> bool:
     """Whether one graph of the batch fits one block's shared memory in the BACKWARD kernel (the larger one)."""
     P = _lib.lib().qot_topo_fused_params()
-    floats = P + 6 * 256 + P + num_nodes * 16 + nmax * (16 * 10 + 144) + emax * (4 + 8 + 2 + 8) + 96
+    floats = P + num_nodes * 16 + nmax * (16 * 10 + 144) + emax * (4 + 8 + 2 + 8) + 96
     nbytes = floats * 4 + 2 * (nmax + 1) * 4 + 4 * emax * 2 + 16
     return nmax <= 4096 and emax <= 60000 and nbytes <= TOPO_FUSED_SMEM_LIMIT
 

@@ -484,18 +484,22 @@ int qot_topological_graph_fill(const void* scratch, int64_t S, const int64_t* ed
  * edge_dim 4, edge MLP 4 -> 8 -> 256, 3 outputs, embedding branch, dropout inactive) and graphs small
  * enough for one block's shared memory.  `flat` [qot_topo_fused_params()] fp32: Wq bq Wk bk Wv bv Ws bs
  * We | nn.0.weight nn.0.bias nn.2.weight nn.2.bias | conv2.lin.weight conv2.bias | mlp.0.weight
- * mlp.0.bias mlp.3.weight mlp.3.bias, each row-major as in the state_dict; emb [num_nodes,16].
+ * mlp.0.bias mlp.3.weight mlp.3.bias, each row-major as in the state_dict; qot_topo_fused_prepare
+ * turns it into `prepared` [qot_topo_fused_prepared_floats()] (transposed copies, factorised NNConv
+ * layout) once per weight update -- the kernels read that 22 KB buffer through L1; emb [num_nodes,16].
  * nmax / emax: largest node / edge count of a graph in the batch (host-known from the collate).
  * Forward: out [B,3].  Backward: dout [B,3] -> gflat (same layout as flat), gemb [num_nodes,16];
  * ws: qot_topo_fused_bwd_workspace_bytes(num_nodes).  Deterministic (fixed summation orders).
  * status bit 0: a graph exceeds nmax / emax (skipped). */
 int qot_topo_fused_params(void);
-int qot_topo_fused_fwd(const float* flat, const float* emb, const int64_t* node_ids,
+int qot_topo_fused_prepared_floats(void);
+int qot_topo_fused_prepare(const float* flat, float* prepared, void* stream);
+int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* node_ids,
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
                        const int64_t* gptr, const int64_t* eptr, int64_t B, int32_t nmax, int32_t emax,
                        int32_t num_nodes, float* out, int32_t* status, void* stream);
 size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes);
-int qot_topo_fused_bwd(const float* flat, const float* emb, const int64_t* node_ids,
+int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* node_ids,
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
                        const int64_t* gptr, const int64_t* eptr, int64_t B, int32_t nmax, int32_t emax,
                        int32_t num_nodes, const float* dout, float* gflat, float* gemb, void* ws,
