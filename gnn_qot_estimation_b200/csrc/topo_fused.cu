@@ -22,6 +22,12 @@ constexpr int oWq = 0, obq = 256, oWk = 272, obk = 528, oWv = 544, obv = 800, oW
               oW1 = 1152, ob1 = 1184, oW2 = 1192, ob2 = 3240, oWroot = 3496, obias2 = 3752, oWm1 = 3768,
               obm1 = 4024, oWm2 = 4040, obm2 = 4088, kTfParams = 4092;
 constexpr int kTfThreads = 128;
+#ifdef QOT_LP_TRACE
+__device__ long long* g_tf_trace = nullptr;               // debug build: 24 clock stamps per block (scripts/trace_topo_fused.py)
+#define TF_STAMP(k) do { if (threadIdx.x == 0 && g_tf_trace) g_tf_trace[blockIdx.x * 24 + (k)] = clock64(); } while (0)
+#else
+#define TF_STAMP(k) do {} while (0)
+#endif
 constexpr float kTfSlope = 0.01f;
 
 constexpr int kTfPrepared = kTfParams + 6 * 256;          // flat (P layout at oW2) | WqT WkT WvT WsT WrootT Wm1T
@@ -116,25 +122,51 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
   }
   for (int idx = tid; idx < E * TF_D; idx += kTfThreads) p.attr[idx] = eattr[e0 * TF_D + idx];
   __syncthreads();
-  // ---- both CSRs (stable: edge order inside a row), one node per thread
-  for (int i = tid; i < n; i += kTfThreads) {
-    int cd = 0, cs = 0;
-    for (int e = 0; e < E; ++e) { cd += p.dst[e] == i; cs += p.src[e] == i; }
-    p.rowd[i + 1] = cd; p.rows[i + 1] = cs;
-  }
+  TF_STAMP(1);
+  // ---- both CSRs, stable (edge order inside a row): one edge per thread -- its rank among the earlier
+  // edges of the same row; row sizes by integer atomics (order-free); offsets by a warp scan
+  for (int i = tid; i <= n; i += kTfThreads) { p.rowd[i] = 0; p.rows[i] = 0; }
   __syncthreads();
-  if (tid == 0) {
-    p.rowd[0] = 0; p.rows[0] = 0;
-    for (int i = 0; i < n; ++i) { p.rowd[i + 1] += p.rowd[i]; p.rows[i + 1] += p.rows[i]; }
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += kTfThreads) {
-    int pd = p.rowd[i], ps = p.rows[i];
-    for (int e = 0; e < E; ++e) {
-      if (p.dst[e] == i) p.permd[pd++] = static_cast<unsigned short>(e);
-      if (p.src[e] == i) p.perms[ps++] = static_cast<unsigned short>(e);
+  int rank_d[4], rank_s[4];                             // edges tid, tid+128, ... (emax <= 512 on this path: checked on the host)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = tid + u * kTfThreads;
+    rank_d[u] = rank_s[u] = 0;
+    if (e < E) {
+      const int d = p.dst[e], sr = p.src[e];
+      int rd = 0, rs = 0;
+      for (int q = 0; q < e; ++q) { rd += p.dst[q] == d; rs += p.src[q] == sr; }
+      rank_d[u] = rd; rank_s[u] = rs;
+      atomicAdd(&p.rowd[d + 1], 1);
+      atomicAdd(&p.rows[sr + 1], 1);
     }
   }
+  __syncthreads();
+  if (tid < 64) {                                       // warp 0: rowd, warp 1: rows; inclusive scan in chunks of 32
+    int* row = tid < 32 ? p.rowd : p.rows;
+    const int ln = tid & 31;
+    int carry = 0;
+    for (int b0 = 0; b0 <= n; b0 += 32) {
+      int v = b0 + ln <= n ? row[b0 + ln] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, v, o);
+        if (ln >= o) v += up;
+      }
+      if (b0 + ln <= n) row[b0 + ln] = v + carry;
+      carry += __shfl_sync(kFull, v, 31);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = tid + u * kTfThreads;
+    if (e < E) {
+      p.permd[p.rowd[p.dst[e]] + rank_d[u]] = static_cast<unsigned short>(e);
+      p.perms[p.rows[p.src[e]] + rank_s[u]] = static_cast<unsigned short>(e);
+    }
+  }
+  TF_STAMP(2);
   // ---- node projections q k v (skip goes straight into O1, held in B2 for now)
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int i = idx >> 4, c = idx & 15;
@@ -156,9 +188,13 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     p.hid[idx] = fmaxf(h, 0.f);
   }
   __syncthreads();
+  TF_STAMP(3);
   // ---- TransformerConv attention: 16 lanes (channels) per destination node, in-edges in edge order
+  const int cl = tid & 15;                              // this thread's channel in every (node, channel) loop
+  const float we0 = par[oWe + cl * TF_D], we1 = par[oWe + cl * TF_D + 1], we2 = par[oWe + cl * TF_D + 2],
+              we3 = par[oWe + cl * TF_D + 3];
   for (int base = 0; base < n * TF_H; base += kTfThreads) {
-    const int idx = base + tid, i = idx >> 4, c = idx & 15;
+    const int idx = base + tid, i = idx >> 4, c = cl;
     const bool valid = idx < n * TF_H;
     const int r0 = valid ? p.rowd[i] : 0, r1 = valid ? p.rowd[i + 1] : 0;
     int rmax = r1 - r0;
@@ -169,9 +205,8 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     for (int r = 0; r < rmax; ++r) {                    // pass 1: logits (kept in alpha[]) and their maximum
       const bool on = r0 + r < r1;
       const int e = on ? p.permd[r0 + r] : 0;
-      float ee = 0.f;
-#pragma unroll
-      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float* at = p.attr + e * TF_D;
+      const float ee = fmaf(at[3], we3, fmaf(at[2], we2, fmaf(at[1], we1, at[0] * we0)));
       const float lg = tf_sum16(on ? qi * (p.K[p.src[e] * TF_H + c] + ee) : 0.f) * 0.25f;
       if (on) {
         mx = fmaxf(mx, lg);
@@ -179,32 +214,34 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
       }
     }
     __syncwarp();
-    float den = 0.f;
-    for (int r = r0; r < r1; ++r) den += expf(p.alpha[p.permd[r]] - mx);          // every lane, same order
-    float acc = valid ? p.B2[idx] : 0.f;                // skip term
-    for (int r = r0; r < r1; ++r) {
+    float den = 0.f, acc = 0.f;
+    for (int r = r0; r < r1; ++r) {                     // pass 2: one exp per edge; unnormalised weights back into alpha[]
       const int e = p.permd[r];
-      float ee = 0.f;
-#pragma unroll
-      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
-      const float a = expf(p.alpha[e] - mx) / (den + 1e-16f);
-      acc = fmaf(a, p.V[p.src[e] * TF_H + c] + ee, acc);
+      const float* at = p.attr + e * TF_D;
+      const float ee = fmaf(at[3], we3, fmaf(at[2], we2, fmaf(at[1], we1, at[0] * we0)));
+      const float w = expf(p.alpha[e] - mx);
+      den += w;
+      acc = fmaf(w, p.V[p.src[e] * TF_H + c] + ee, acc);
     }
+    const float inv = 1.f / (den + 1e-16f);
     __syncwarp();
-    for (int r = r0; r < r1; ++r) {                     // logits -> weights (lane 0 of the group)
-      const int e = p.permd[r];
-      if (c == 0) p.alpha[e] = expf(p.alpha[e] - mx) / (den + 1e-16f);
-    }
-    if (valid) p.H1[idx] = tf_lk(acc);
+    if (c == 0)
+      for (int r = r0; r < r1; ++r) { const int e = p.permd[r]; p.alpha[e] = expf(p.alpha[e] - mx) * inv; }
+    if (valid) p.H1[idx] = tf_lk(fmaf(acc, inv, p.B2[idx]));
   }
   __syncthreads();
+  TF_STAMP(4);
   // ---- factorised NNConv: T_j = h1_j P
-  for (int idx = tid; idx < n * TF_T; idx += kTfThreads) {
-    const int j = idx / TF_T, r = idx % TF_T;
-    float t = 0.f;
+  for (int idx = tid; idx < n * (TF_T / 4); idx += kTfThreads) {
+    const int j = idx / (TF_T / 4), r = 4 * (idx % (TF_T / 4));
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < TF_H; ++c) t = fmaf(p.H1[j * TF_H + c], par[oW2 + c * TF_T + r], t);
-    p.T[idx] = t;
+    for (int c = 0; c < TF_H; ++c) {
+      const float h = p.H1[j * TF_H + c];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(par + oW2 + c * TF_T + r));
+      t.x = fmaf(h, w.x, t.x); t.y = fmaf(h, w.y, t.y); t.z = fmaf(h, w.z, t.z); t.w = fmaf(h, w.w, t.w);
+    }
+    *reinterpret_cast<float4*>(p.T + j * TF_T + r) = t;
   }
   __syncthreads();
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
@@ -225,6 +262,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     p.B1[idx] = tf_lk(v);
   }
   __syncthreads();
+  TF_STAMP(5);
   // ---- global mean pool + MLP head (one warp)
   float* pool = p.small; float* pre1 = p.small + 16; float* z1 = p.small + 32; float* outv = p.small + 48;
   if (tid < TF_H) {
@@ -279,6 +317,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
   float* g = p.grad;
   float* pool = p.small; float* pre1 = p.small + 16; float* z1 = p.small + 32;
   float* dpool = p.small + 64; float* dpre1 = p.small + 80; const float* dout = p.small + 52;
+  TF_STAMP(6);
   // ---- MLP head
   if (tid < TF_H) {
     float dz = 0.f;
@@ -299,6 +338,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     dpool[tid] = d / static_cast<float>(max(n, 1));
   }
   __syncthreads();
+  TF_STAMP(7);
   // ---- dO2 (in place of H2 in B1); dH1 starts in B2
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) p.B1[idx] = dpool[idx & 15] * tf_dlk_from_act(p.B1[idx]);
   __syncthreads();
@@ -320,15 +360,24 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int o = 0; o < TF_H; ++o) d = fmaf(par[oWroot + o * TF_H + c], p.B1[i * TF_H + o], d);
     p.B2[idx] = d;
   }
+  TF_STAMP(8);
+  // ---- dm_i = dO2_i / deg_i (G3: free until the attention backward)
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
+    const int i = idx >> 4;
+    p.G3[idx] = p.B1[idx] / static_cast<float>(max(p.rowd[i + 1] - p.rowd[i], 1));
+  }
+  __syncthreads();
   // ---- d hid' per edge (needs T of the source), edge-MLP layer-1 gradients
   for (int idx = tid; idx < E * TF_K; idx += kTfThreads) {
     const int e = idx >> 3, k = idx & 7, i = p.dst[e];
-    const float inv = 1.f / static_cast<float>(max(p.rowd[i + 1] - p.rowd[i], 1));
     const float* t = p.T + p.src[e] * TF_T + k * TF_H;
-    float d = 0.f;
+    float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int o = 0; o < TF_H; ++o) d = fmaf(t[o], p.B1[i * TF_H + o], d);
-    p.dhid[idx] = p.hid[idx] > 0.f ? d * inv : 0.f;
+    for (int o = 0; o < TF_H; o += 2) {
+      d0 = fmaf(t[o], p.G3[i * TF_H + o], d0);
+      d1 = fmaf(t[o + 1], p.G3[i * TF_H + o + 1], d1);
+    }
+    p.dhid[idx] = p.hid[idx] > 0.f ? d0 + d1 : 0.f;
   }
   __syncthreads();
   if (tid < TF_K * TF_D) {                              // dW1[k][d] += sum_e dhidpre[e][k] attr[e][d]
@@ -343,34 +392,45 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     g[ob1 + k] += s;
   }
   __syncthreads();
+  TF_STAMP(9);
   // ---- dT_j (over the out-edges of j, edge order) overwrites T_j
   for (int idx = tid; idx < n * TF_T; idx += kTfThreads) {
     const int j = idx / TF_T, r = idx % TF_T, k = r >> 4, o = r & 15;
     float s = 0.f;
     for (int q = p.rows[j]; q < p.rows[j + 1]; ++q) {
       const int e = p.perms[q], i = p.dst[e];
-      const float inv = 1.f / static_cast<float>(max(p.rowd[i + 1] - p.rowd[i], 1));
       const float hk = k < TF_K ? p.hid[e * TF_K + k] : 1.f;
-      s = fmaf(hk, p.B1[i * TF_H + o] * inv, s);
+      s = fmaf(hk, p.G3[i * TF_H + o], s);
     }
     p.T[idx] = s;
   }
   __syncthreads();
+  TF_STAMP(10);
   for (int idx = tid; idx < TF_H * TF_T; idx += kTfThreads) {   // dP[c][r] += sum_j h1[j][c] dT_j[r]
     const int c = idx / TF_T, r = idx % TF_T;
-    float s = 0.f;
-    for (int j = 0; j < n; ++j) s = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s);
-    g[oW2 + idx] += s;
+    float s0 = 0.f, s1 = 0.f;
+    int j = 0;
+    for (; j + 1 < n; j += 2) {
+      s0 = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s0);
+      s1 = fmaf(p.H1[(j + 1) * TF_H + c], p.T[(j + 1) * TF_T + r], s1);
+    }
+    if (j < n) s0 = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s0);
+    g[oW2 + idx] += s0 + s1;
   }
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dH1[j][c] += sum_r P[c][r] dT_j[r]; then dO1
     const int j = idx >> 4, c = idx & 15;
-    float d = p.B2[idx];
-    const float* pr = par + oW2 + c * TF_T;
-    const float* t = p.T + j * TF_T;
-    for (int r = 0; r < TF_T; ++r) d = fmaf(pr[r], t[r], d);
-    p.B2[idx] = d * tf_dlk_from_act(p.H1[idx]);
+    const float4* pr = reinterpret_cast<const float4*>(par + oW2 + c * TF_T);
+    const float4* t = reinterpret_cast<const float4*>(p.T + j * TF_T);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < TF_T / 4; ++r) {
+      const float4 w = __ldg(pr + r), v = t[r];
+      d0 = fmaf(w.x, v.x, d0); d1 = fmaf(w.y, v.y, d1); d2 = fmaf(w.z, v.z, d2); d3 = fmaf(w.w, v.w, d3);
+    }
+    p.B2[idx] = (p.B2[idx] + ((d0 + d1) + (d2 + d3))) * tf_dlk_from_act(p.H1[idx]);
   }
   __syncthreads();
+  TF_STAMP(11);
   // ---- skip projection
   if (tid < TF_H) {
     float s = 0.f;
@@ -383,8 +443,12 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int i = 0; i < n; ++i) s = fmaf(p.B2[i * TF_H + c], p.X[i * TF_H + k], s);
     g[oWs + idx] += s;
   }
+  TF_STAMP(12);
   // ---- attention backward, destination side: dalpha, dlogit (per edge), dQ (G1)
   __syncthreads();
+  const int cb = tid & 15;
+  const float we0 = par[oWe + cb * TF_D], we1 = par[oWe + cb * TF_D + 1], we2 = par[oWe + cb * TF_D + 2],
+              we3 = par[oWe + cb * TF_D + 3];
   for (int base = 0; base < n * TF_H; base += kTfThreads) {
     const int idx = base + tid, i = idx >> 4, c = idx & 15;
     const bool valid = idx < n * TF_H;
@@ -397,9 +461,8 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int r = 0; r < rmax; ++r) {                    // pass 1: dalpha_e (kept in dlogit[]), t = sum alpha dalpha
       const bool on = r0 + r < r1;
       const int e = on ? p.permd[r0 + r] : 0;
-      float ee = 0.f;
-#pragma unroll
-      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float* at = p.attr + e * TF_D;
+      const float ee = fmaf(at[3], we3, fmaf(at[2], we2, fmaf(at[1], we1, at[0] * we0)));
       const float da = tf_sum16(on ? gi * (p.V[p.src[e] * TF_H + c] + ee) : 0.f);
       if (on) {
         tsum = fmaf(p.alpha[e], da, tsum);
@@ -410,9 +473,8 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     float dq = 0.f;
     for (int r = r0; r < r1; ++r) {
       const int e = p.permd[r];
-      float ee = 0.f;
-#pragma unroll
-      for (int d = 0; d < TF_D; ++d) ee = fmaf(p.attr[e * TF_D + d], par[oWe + c * TF_D + d], ee);
+      const float* at = p.attr + e * TF_D;
+      const float ee = fmaf(at[3], we3, fmaf(at[2], we2, fmaf(at[1], we1, at[0] * we0)));
       const float dl = p.alpha[e] * (p.dlogit[e] - tsum);
       dq = fmaf(dl, (p.K[p.src[e] * TF_H + c] + ee) * 0.25f, dq);
     }
@@ -425,6 +487,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     (void)qi;
   }
   __syncthreads();
+  TF_STAMP(13);
   // ---- source side: dV (G3), dK (G2) over the out-edges of j, edge order
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int j = idx >> 4, c = idx & 15;
@@ -446,6 +509,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     g[oWe + tid] += s;
   }
   __syncthreads();
+  TF_STAMP(14);
   // ---- q / k / v weight gradients, dX, embedding rows
   if (tid < 3 * TF_H) {
     const int w = tid >> 4, c = tid & 15;
@@ -463,17 +527,18 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
   }
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dX[i][k] into B1 (dO2 is dead)
     const int i = idx >> 4, k = idx & 15;
-    float d = 0.f;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
     for (int c = 0; c < TF_H; ++c) {
-      d = fmaf(p.B2[i * TF_H + c], par[oWs + c * TF_H + k], d);
-      d = fmaf(p.G1[i * TF_H + c], par[oWq + c * TF_H + k], d);
-      d = fmaf(p.G2[i * TF_H + c], par[oWk + c * TF_H + k], d);
-      d = fmaf(p.G3[i * TF_H + c], par[oWv + c * TF_H + k], d);
+      d0 = fmaf(p.B2[i * TF_H + c], par[oWs + c * TF_H + k], d0);
+      d1 = fmaf(p.G1[i * TF_H + c], par[oWq + c * TF_H + k], d1);
+      d2 = fmaf(p.G2[i * TF_H + c], par[oWk + c * TF_H + k], d2);
+      d3 = fmaf(p.G3[i * TF_H + c], par[oWv + c * TF_H + k], d3);
     }
-    p.T[idx] = d;                                         // T is dead: dX lives there
+    p.T[idx] = (d0 + d1) + (d2 + d3);                     // T is dead: dX lives there
   }
   __syncthreads();
+  TF_STAMP(15);
   if (tid < TF_H) {                                       // one thread per column, nodes in order: duplicates of an id are summed deterministically
     for (int i = 0; i < n; ++i) {
       long long id = node_ids[n0 + i];
@@ -502,10 +567,12 @@ topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
       if (threadIdx.x == 0) atomicOr(status, 1);
       continue;
     }
+    TF_STAMP(0);
     tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes);
     if (threadIdx.x < QOT_OUT) p.small[52 + threadIdx.x] = dout[g * QOT_OUT + threadIdx.x];
     __syncthreads();
     tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes);
+    TF_STAMP(16);
   }
   float* dst = partial + static_cast<size_t>(blockIdx.x) * gsz;
   for (int i = threadIdx.x; i < gsz; i += kTfThreads) dst[i] = p.grad[i];
@@ -541,6 +608,9 @@ topo_fused_reduce_kernel(const float* __restrict__ partial, int blocks, int num_
 
 using namespace qot;
 
+#ifdef QOT_LP_TRACE
+extern "C" int qot_debug_set_tf_trace(long long* buf) { return cudaMemcpyToSymbol(g_tf_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3; }
+#endif
 extern "C" int qot_topo_fused_params(void) { return kTfParams; }
 extern "C" int qot_topo_fused_prepared_floats(void) { return kTfPrepared; }
 
@@ -560,7 +630,7 @@ static int tf_blocks(int64_t B, size_t smem) {
 
 static int tf_check(int64_t B, int nmax, int emax, int num_nodes, const char* who) {
   QOT_REQUIRE(B >= 0 && nmax >= 0 && emax >= 0 && num_nodes > 0, "%s: bad sizes", who);
-  QOT_REQUIRE(nmax <= 4096 && emax <= 60000, "%s: graph too large for one block", who);
+  QOT_REQUIRE(nmax <= 4096 && emax <= 4 * kTfThreads, "%s: graph too large for one block (at most %d edges)", who, 4 * kTfThreads);
   return QOT_OK;
 }
 

@@ -762,7 +762,7 @@ def topo_fused_fits(nmax: int, emax: int, num_nodes: int) -> bool:
     P = _lib.lib().qot_topo_fused_params()
     floats = P + num_nodes * 16 + nmax * (16 * 10 + 144) + emax * (4 + 8 + 2 + 8) + 96
     nbytes = floats * 4 + 2 * (nmax + 1) * 4 + 4 * emax * 2 + 16
-    return nmax <= 4096 and emax <= 60000 and nbytes <= TOPO_FUSED_SMEM_LIMIT
+    return nmax <= 4096 and emax <= 512 and nbytes <= TOPO_FUSED_SMEM_LIMIT
 
 
 def topological_fused(params: Sequence[torch.Tensor], emb, node_ids, edge_index, edge_attr, gptr, eptr,
