@@ -394,28 +394,31 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
   __syncthreads();
   TF_STAMP(9);
   // ---- dT_j (over the out-edges of j, edge order) overwrites T_j
-  for (int idx = tid; idx < n * TF_T; idx += kTfThreads) {
-    const int j = idx / TF_T, r = idx % TF_T, k = r >> 4, o = r & 15;
-    float s = 0.f;
+  for (int idx = tid; idx < n * (TF_T / 4); idx += kTfThreads) {
+    const int j = idx / (TF_T / 4), r = 4 * (idx % (TF_T / 4)), k = r >> 4, o = r & 15;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = p.rows[j]; q < p.rows[j + 1]; ++q) {
       const int e = p.perms[q], i = p.dst[e];
       const float hk = k < TF_K ? p.hid[e * TF_K + k] : 1.f;
-      s = fmaf(hk, p.G3[i * TF_H + o], s);
+      const float4 dm = *reinterpret_cast<const float4*>(p.G3 + i * TF_H + o);
+      acc.x = fmaf(hk, dm.x, acc.x); acc.y = fmaf(hk, dm.y, acc.y); acc.z = fmaf(hk, dm.z, acc.z); acc.w = fmaf(hk, dm.w, acc.w);
     }
-    p.T[idx] = s;
+    *reinterpret_cast<float4*>(p.T + j * TF_T + r) = acc;
   }
   __syncthreads();
   TF_STAMP(10);
-  for (int idx = tid; idx < TF_H * TF_T; idx += kTfThreads) {   // dP[c][r] += sum_j h1[j][c] dT_j[r]
-    const int c = idx / TF_T, r = idx % TF_T;
-    float s0 = 0.f, s1 = 0.f;
-    int j = 0;
-    for (; j + 1 < n; j += 2) {
-      s0 = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s0);
-      s1 = fmaf(p.H1[(j + 1) * TF_H + c], p.T[(j + 1) * TF_T + r], s1);
+  for (int idx = tid; idx < TF_H * (TF_T / 4); idx += kTfThreads) {   // dP[c][r..r+3] += sum_j h1[j][c] dT_j[r..r+3]
+    const int c = idx / (TF_T / 4), r = 4 * (idx % (TF_T / 4));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      const float h = p.H1[j * TF_H + c];
+      const float4 t = *reinterpret_cast<const float4*>(p.T + j * TF_T + r);
+      acc.x = fmaf(h, t.x, acc.x); acc.y = fmaf(h, t.y, acc.y); acc.z = fmaf(h, t.z, acc.z); acc.w = fmaf(h, t.w, acc.w);
     }
-    if (j < n) s0 = fmaf(p.H1[j * TF_H + c], p.T[j * TF_T + r], s0);
-    g[oW2 + idx] += s0 + s1;
+    float4* gp = reinterpret_cast<float4*>(g + oW2 + c * TF_T + r);
+    float4 cur = *gp;
+    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+    *gp = cur;
   }
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dH1[j][c] += sum_r P[c][r] dT_j[r]; then dO1
     const int j = idx >> 4, c = idx & 15;
