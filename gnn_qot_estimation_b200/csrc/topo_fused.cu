@@ -347,11 +347,16 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int i = 0; i < n; ++i) s += p.B1[i * TF_H + tid];
     g[obias2 + tid] += s;
   }
-  for (int idx = tid; idx < 256; idx += kTfThreads) {   // dWroot[o][c] += sum_i dO2[i][o] h1[i][c]
-    const int o = idx >> 4, c = idx & 15;
-    float s = 0.f;
-    for (int i = 0; i < n; ++i) s = fmaf(p.B1[i * TF_H + o], p.H1[i * TF_H + c], s);
-    g[oWroot + idx] += s;
+  for (int idx = tid; idx < 64; idx += kTfThreads) {    // dWroot[o][c..c+3] += sum_i dO2[i][o] h1[i][c..c+3]
+    const int o = idx >> 2, c = 4 * (idx & 3);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n; ++i) {
+      const float d = p.B1[i * TF_H + o];
+      const float4 h = *reinterpret_cast<const float4*>(p.H1 + i * TF_H + c);
+      acc.x = fmaf(d, h.x, acc.x); acc.y = fmaf(d, h.y, acc.y); acc.z = fmaf(d, h.z, acc.z); acc.w = fmaf(d, h.w, acc.w);
+    }
+    float* gp = g + oWroot + o * TF_H + c;
+    gp[0] += acc.x; gp[1] += acc.y; gp[2] += acc.z; gp[3] += acc.w;
   }
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int i = idx >> 4, c = idx & 15;
@@ -440,11 +445,16 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int i = 0; i < n; ++i) s += p.B2[i * TF_H + tid];
     g[obs + tid] += s;
   }
-  for (int idx = tid; idx < 256; idx += kTfThreads) {
-    const int c = idx >> 4, k = idx & 15;
-    float s = 0.f;
-    for (int i = 0; i < n; ++i) s = fmaf(p.B2[i * TF_H + c], p.X[i * TF_H + k], s);
-    g[oWs + idx] += s;
+  for (int idx = tid; idx < 64; idx += kTfThreads) {
+    const int c = idx >> 2, k = 4 * (idx & 3);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n; ++i) {
+      const float d = p.B2[i * TF_H + c];
+      const float4 xv = *reinterpret_cast<const float4*>(p.X + i * TF_H + k);
+      acc.x = fmaf(d, xv.x, acc.x); acc.y = fmaf(d, xv.y, acc.y); acc.z = fmaf(d, xv.z, acc.z); acc.w = fmaf(d, xv.w, acc.w);
+    }
+    float* gp = g + oWs + c * TF_H + k;
+    gp[0] += acc.x; gp[1] += acc.y; gp[2] += acc.z; gp[3] += acc.w;
   }
   TF_STAMP(12);
   // ---- attention backward, destination side: dalpha, dlogit (per edge), dQ (G1)
@@ -521,12 +531,17 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     for (int i = 0; i < n; ++i) s += G[i * TF_H + c];
     g[(w == 0 ? obq : (w == 1 ? obk : obv)) + c] += s;
   }
-  for (int idx = tid; idx < 3 * 256; idx += kTfThreads) {
-    const int w = idx >> 8, c = (idx >> 4) & 15, k = idx & 15;
+  for (int idx = tid; idx < 3 * 64; idx += kTfThreads) {
+    const int w = idx >> 6, c = (idx >> 2) & 15, k = 4 * (idx & 3);
     const float* G = w == 0 ? p.G1 : (w == 1 ? p.G2 : p.G3);
-    float s = 0.f;
-    for (int i = 0; i < n; ++i) s = fmaf(G[i * TF_H + c], p.X[i * TF_H + k], s);
-    g[(w == 0 ? oWq : (w == 1 ? oWk : oWv)) + (idx & 255)] += s;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n; ++i) {
+      const float d = G[i * TF_H + c];
+      const float4 xv = *reinterpret_cast<const float4*>(p.X + i * TF_H + k);
+      acc.x = fmaf(d, xv.x, acc.x); acc.y = fmaf(d, xv.y, acc.y); acc.z = fmaf(d, xv.z, acc.z); acc.w = fmaf(d, xv.w, acc.w);
+    }
+    float* gp = g + (w == 0 ? oWq : (w == 1 ? oWk : oWv)) + c * TF_H + k;
+    gp[0] += acc.x; gp[1] += acc.y; gp[2] += acc.z; gp[3] += acc.w;
   }
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {      // dX[i][k] into B1 (dO2 is dead)
     const int i = idx >> 4, k = idx & 15;
