@@ -96,9 +96,10 @@ SIGNATURES = {
     "qot_topo_fused_params": (C.c_int, []),
     "qot_topo_fused_prepared_floats": (C.c_int, []),
     "qot_topo_fused_prepare": (C.c_int, [P, P, vp]),
-    "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i32, i32, i32, P, P, vp]),
+    "qot_topo_fused_saved_floats": (sz, [i64, i64, i64]),
+    "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, vp]),
     "qot_topo_fused_bwd_workspace_bytes": (sz, [i32]),
-    "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i32, i32, i32, P, P, P, P, sz, P, vp]),
+    "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, vp]),
     "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
     "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,

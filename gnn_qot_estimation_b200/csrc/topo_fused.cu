@@ -104,9 +104,18 @@ topo_fused_prepare_kernel(const float* __restrict__ flat, float* __restrict__ pr
 
 // One graph, forward.  Leaves in shared memory everything the backward needs: X Q K V H1 (leaky(O1)),
 // B1 = H2 (leaky(O2)), T, attr, hid, alpha, both CSRs, small[] = pool | pre1 | z1 | out.
+// Saved forward state of one graph (training): [Q | K | V | H1 | H2 | T] per node range, [hid | alpha] per edge
+// range, pool | pre1 | z1 | out per graph.  kTfSaveNode floats per node, kTfSaveEdge per edge, kTfSaveGraph per graph.
+constexpr int kTfSaveNode = 5 * TF_H + TF_T, kTfSaveEdge = TF_K + 1, kTfSaveGraph = 64;
+
+// `save` (nullable): the forward state is also written there; `restore` (nullable): the state is READ from there
+// instead of being computed (the backward kernel, when the forward kernel of the same step saved it)
 __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
                                  const int64_t* __restrict__ esrc, const int64_t* __restrict__ edst,
-                                 const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes) {
+                                 const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes,
+                                 float* __restrict__ save_n, float* __restrict__ save_e, float* __restrict__ save_g,
+                                 const float* __restrict__ rest_n, const float* __restrict__ rest_e,
+                                 const float* __restrict__ rest_g) {
   const int tid = threadIdx.x;
   const float* __restrict__ par = p.par;
   // ---- inputs
@@ -167,6 +176,19 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     }
   }
   TF_STAMP(2);
+  if (rest_n) {                                          // restore instead of recomputing
+    const int nh = n * TF_H;
+    for (int idx = tid; idx < nh; idx += kTfThreads) {
+      p.Q[idx] = rest_n[idx]; p.K[idx] = rest_n[nh + idx]; p.V[idx] = rest_n[2 * nh + idx];
+      p.H1[idx] = rest_n[3 * nh + idx]; p.B1[idx] = rest_n[4 * nh + idx];
+    }
+    for (int idx = tid; idx < n * TF_T; idx += kTfThreads) p.T[idx] = rest_n[5 * nh + idx];
+    for (int idx = tid; idx < E * TF_K; idx += kTfThreads) p.hid[idx] = rest_e[idx];
+    for (int idx = tid; idx < E; idx += kTfThreads) p.alpha[idx] = rest_e[E * TF_K + idx];
+    if (tid < 52) p.small[tid] = rest_g[tid];
+    __syncthreads();
+    return;
+  }
   // ---- node projections q k v (skip goes straight into O1, held in B2 for now)
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int i = idx >> 4, c = idx & 15;
@@ -286,15 +308,29 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     outv[tid] = o3;
   }
   __syncthreads();
+  if (save_n) {
+    const int nh = n * TF_H;
+    for (int idx = tid; idx < nh; idx += kTfThreads) {
+      save_n[idx] = p.Q[idx]; save_n[nh + idx] = p.K[idx]; save_n[2 * nh + idx] = p.V[idx];
+      save_n[3 * nh + idx] = p.H1[idx]; save_n[4 * nh + idx] = p.B1[idx];
+    }
+    for (int idx = tid; idx < n * TF_T; idx += kTfThreads) save_n[5 * nh + idx] = p.T[idx];
+    for (int idx = tid; idx < E * TF_K; idx += kTfThreads) save_e[idx] = p.hid[idx];
+    for (int idx = tid; idx < E; idx += kTfThreads) save_e[E * TF_K + idx] = p.alpha[idx];
+    if (tid < 52) save_g[tid] = p.small[tid];
+  }
 }
 
 __global__ void __launch_bounds__(kTfThreads, 7)
 topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
-                      int num_nodes, float* __restrict__ out, int32_t* __restrict__ status) {
+                      int num_nodes, float* __restrict__ out, float* __restrict__ saved, int64_t Ntot,
+                      int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tf_smem[];
   const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, false);
+  float* sv_e = saved ? saved + Ntot * kTfSaveNode : nullptr;
+  float* sv_g = saved ? sv_e + Etot * kTfSaveEdge : nullptr;
   for (int64_t g = blockIdx.x; g < B; g += gridDim.x) {
     const int64_t n0 = gptr[g], e0 = eptr[g];
     const int64_t n = gptr[g + 1] - n0, E = eptr[g + 1] - e0;
@@ -302,7 +338,9 @@ topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
       if (threadIdx.x == 0) atomicOr(status, 1);
       continue;
     }
-    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes);
+    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
+                     saved ? saved + n0 * kTfSaveNode : nullptr, saved ? sv_e + e0 * kTfSaveEdge : nullptr,
+                     saved ? sv_g + g * kTfSaveGraph : nullptr, nullptr, nullptr, nullptr);
     if (threadIdx.x < QOT_OUT) out[g * QOT_OUT + threadIdx.x] = p.small[48 + threadIdx.x];
     __syncthreads();
   }
@@ -571,10 +609,12 @@ __global__ void __launch_bounds__(kTfThreads, 7)
 topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ emb, const int64_t* __restrict__ node_ids,
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
-                      int num_nodes, const float* __restrict__ dout, float* __restrict__ partial,
-                      int32_t* __restrict__ status) {
+                      int num_nodes, const float* __restrict__ dout, const float* __restrict__ saved, int64_t Ntot,
+                      float* __restrict__ partial, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) char tf_smem[];
   const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, true);
+  const float* sv_e = saved ? saved + Ntot * kTfSaveNode : nullptr;
+  const float* sv_g = saved ? sv_e + Etot * kTfSaveEdge : nullptr;
   const int gsz = kTfParams + num_nodes * TF_H;
   for (int i = threadIdx.x; i < gsz; i += kTfThreads) p.grad[i] = 0.f;       // grad | gemb are contiguous
   __syncthreads();
@@ -586,7 +626,9 @@ topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
       continue;
     }
     TF_STAMP(0);
-    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes);
+    tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
+                     nullptr, nullptr, nullptr, saved ? saved + n0 * kTfSaveNode : nullptr,
+                     saved ? sv_e + e0 * kTfSaveEdge : nullptr, saved ? sv_g + g * kTfSaveGraph : nullptr);
     if (threadIdx.x < QOT_OUT) p.small[52 + threadIdx.x] = dout[g * QOT_OUT + threadIdx.x];
     __syncthreads();
     tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes);
@@ -652,10 +694,15 @@ static int tf_check(int64_t B, int nmax, int emax, int num_nodes, const char* wh
   return QOT_OK;
 }
 
+extern "C" size_t qot_topo_fused_saved_floats(int64_t N, int64_t E, int64_t B) {
+  return static_cast<size_t>(std::max<int64_t>(N, 0)) * kTfSaveNode + static_cast<size_t>(std::max<int64_t>(E, 0)) * kTfSaveEdge +
+         static_cast<size_t>(std::max<int64_t>(B, 0)) * kTfSaveGraph + 4;
+}
+
 extern "C" int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
-                                  int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, float* out,
-                                  int32_t* status, void* stream_) {
+                                  int64_t B, int64_t N, int32_t nmax, int32_t emax, int32_t num_nodes, float* out,
+                                  float* saved, int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_fwd");
   if (rc) return rc;
@@ -666,7 +713,7 @@ extern "C" int qot_topo_fused_fwd(const float* prepared, const float* emb, const
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = tf_blocks(B, smem);
   topo_fused_fwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
-                                                             nmax, emax, num_nodes, out, status);
+                                                             nmax, emax, num_nodes, out, saved, N, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -677,8 +724,9 @@ extern "C" size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes) {
 
 extern "C" int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
-                                  int64_t B, int32_t nmax, int32_t emax, int32_t num_nodes, const float* dout,
-                                  float* gflat, float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream_) {
+                                  int64_t B, int64_t N, int32_t nmax, int32_t emax, int32_t num_nodes, const float* dout,
+                                  const float* saved, float* gflat, float* gemb, void* ws, size_t ws_bytes,
+                                  int32_t* status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_bwd");
   if (rc) return rc;
@@ -695,7 +743,7 @@ extern "C" int qot_topo_fused_bwd(const float* prepared, const float* emb, const
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = tf_blocks(B, smem);
   topo_fused_bwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
-                                                             nmax, emax, num_nodes, dout, static_cast<float*>(ws), status);
+                                                             nmax, emax, num_nodes, dout, saved, N, static_cast<float*>(ws), status);
   QOT_LAUNCH_CHECK();
   topo_fused_reduce_kernel<<<(gsz + 31) / 32, 256, 0, stream>>>(static_cast<const float*>(ws), blocks, num_nodes, gflat, gemb);
   QOT_LAUNCH_CHECK();

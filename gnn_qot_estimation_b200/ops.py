@@ -730,17 +730,21 @@ class _TopoFusedFn(torch.autograd.Function):
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         prep = torch.empty(L.qot_topo_fused_prepared_floats(), dtype=torch.float32, device=dev)
         check(L.qot_topo_fused_prepare(ptr(flat_), ptr(prep), stream()), "qot_topo_fused_prepare")
-        check(L.qot_topo_fused_fwd(ptr(prep), ptr(emb_), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
-                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, int(nmax), int(emax), int(emb_.shape[0]),
-                                   ptr(out), ptr(status), stream()), "qot_topo_fused_fwd")
-        ctx.save_for_backward(prep, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status)
+        N, E = int(node_ids.shape[0]), int(edge_index.shape[1])
+        saved = None                                     # forward state for the backward (training only)
+        if any(ctx.needs_input_grad[:2]):
+            saved = torch.empty(L.qot_topo_fused_saved_floats(N, E, B), dtype=torch.float32, device=dev)
+        check(L.qot_topo_fused_fwd(ptr(prep), ptr(emb_), ptr(node_ids), ptr(edge_index), E,
+                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, N, int(nmax), int(emax), int(emb_.shape[0]),
+                                   ptr(out), ptr(saved), ptr(status), stream()), "qot_topo_fused_fwd")
+        ctx.save_for_backward(prep, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status, saved)
         ctx.sizes = (int(nmax), int(emax))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        prep, emb, node_ids, edge_index, edge_attr, gptr, eptr, status = ctx.saved_tensors
+        prep, emb, node_ids, edge_index, edge_attr, gptr, eptr, status, saved = ctx.saved_tensors
         nmax, emax = ctx.sizes
         B = int(gptr.numel() - 1)
         dev = prep.device
@@ -748,8 +752,9 @@ class _TopoFusedFn(torch.autograd.Function):
         gemb = torch.empty_like(emb)
         ws = _ws(L.qot_topo_fused_bwd_workspace_bytes(int(emb.shape[0])), dev)
         check(L.qot_topo_fused_bwd(ptr(prep), ptr(emb), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
-                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, nmax, emax, int(emb.shape[0]),
-                                   ptr(_f32(dout)), ptr(gflat), ptr(gemb), ptr(ws), ws.numel(), ptr(status), stream()),
+                                   ptr(edge_attr), ptr(gptr), ptr(eptr), B, int(node_ids.shape[0]), nmax, emax,
+                                   int(emb.shape[0]), ptr(_f32(dout)), ptr(saved), ptr(gflat), ptr(gemb), ptr(ws),
+                                   ws.numel(), ptr(status), stream()),
               "qot_topo_fused_bwd")
         return gflat, gemb, None, None, None, None, None, None, None
 

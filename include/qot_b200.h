@@ -488,22 +488,27 @@ int qot_topological_graph_fill(const void* scratch, int64_t S, const int64_t* ed
  * turns it into `prepared` [qot_topo_fused_prepared_floats()] (transposed copies, factorised NNConv
  * layout) once per weight update -- the kernels read that 22 KB buffer through L1; emb [num_nodes,16].
  * nmax / emax: largest node / edge count of a graph in the batch (host-known from the collate).
- * Forward: out [B,3].  Backward: dout [B,3] -> gflat (same layout as flat), gemb [num_nodes,16];
- * ws: qot_topo_fused_bwd_workspace_bytes(num_nodes).  Deterministic (fixed summation orders).
+ * Forward: out [B,3]; `saved` (optional, qot_topo_fused_saved_floats(N, E, B) floats): the forward
+ * state the backward would otherwise recompute (q k v h1 h2 T per node, edge-MLP hidden + softmax
+ * weights per edge).  Backward: dout [B,3] (+ the same `saved`, or NULL to recompute) -> gflat (same
+ * layout as flat), gemb [num_nodes,16]; ws: qot_topo_fused_bwd_workspace_bytes(num_nodes).
+ * N = total nodes of the batch.  Deterministic (fixed summation orders).
  * status bit 0: a graph exceeds nmax / emax (skipped). */
 int qot_topo_fused_params(void);
 int qot_topo_fused_prepared_floats(void);
 int qot_topo_fused_prepare(const float* flat, float* prepared, void* stream);
+size_t qot_topo_fused_saved_floats(int64_t N, int64_t E, int64_t B);
 int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* node_ids,
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
-                       const int64_t* gptr, const int64_t* eptr, int64_t B, int32_t nmax, int32_t emax,
-                       int32_t num_nodes, float* out, int32_t* status, void* stream);
+                       const int64_t* gptr, const int64_t* eptr, int64_t B, int64_t N, int32_t nmax,
+                       int32_t emax, int32_t num_nodes, float* out, float* saved, int32_t* status,
+                       void* stream);
 size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes);
 int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* node_ids,
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
-                       const int64_t* gptr, const int64_t* eptr, int64_t B, int32_t nmax, int32_t emax,
-                       int32_t num_nodes, const float* dout, float* gflat, float* gemb, void* ws,
-                       size_t ws_bytes, int32_t* status, void* stream);
+                       const int64_t* gptr, const int64_t* eptr, int64_t B, int64_t N, int32_t nmax,
+                       int32_t emax, int32_t num_nodes, const float* dout, const float* saved, float* gflat,
+                       float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }
