@@ -84,18 +84,19 @@ __device__ __forceinline__ float tf_sum16(float v) {                       // ov
   return v;
 }
 
-// parameters -> the prepared buffer (flat copy, P rearrangement of W2 | b2, transposed 16x16 matrices); one block
+// parameters -> the prepared buffer (flat copy, P rearrangement of W2 | b2, transposed 16x16 matrices)
 __global__ void __launch_bounds__(256)
 topo_fused_prepare_kernel(const float* __restrict__ flat, float* __restrict__ prep) {
-  for (int i = threadIdx.x; i < kTfParams; i += blockDim.x)
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = t0; i < kTfParams; i += nt)
     if (i < oW2 || i >= oWroot) prep[i] = flat[i];
   // P[c][k*16+o] = W2[(c*16+o)*8 + k] (k < 8), P[c][8*16+o] = b2[c*16+o]; stored at oW2, row stride 144
-  for (int i = threadIdx.x; i < TF_H * TF_T; i += blockDim.x) {
+  for (int i = t0; i < TF_H * TF_T; i += nt) {
     const int c = i / TF_T, r = i % TF_T, k = r / TF_H, o = r % TF_H;
     prep[oW2 + i] = k < TF_K ? flat[oW2 + (c * TF_H + o) * TF_K + k] : flat[ob2 + c * TF_H + o];
   }
   float* t = prep + kTfParams;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+  for (int i = t0; i < 256; i += nt) {
     const int a = i >> 4, b = i & 15;                  // T[b][a] = W[a][b]
     t[b * 16 + a] = flat[oWq + i]; t[256 + b * 16 + a] = flat[oWk + i]; t[512 + b * 16 + a] = flat[oWv + i];
     t[768 + b * 16 + a] = flat[oWs + i]; t[1024 + b * 16 + a] = flat[oWroot + i]; t[1280 + b * 16 + a] = flat[oWm1 + i];
@@ -677,7 +678,7 @@ extern "C" int qot_topo_fused_prepared_floats(void) { return kTfPrepared; }
 extern "C" int qot_topo_fused_prepare(const float* flat, float* prepared, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   QOT_REQUIRE(flat && prepared, "qot_topo_fused_prepare: null argument");
-  topo_fused_prepare_kernel<<<1, 256, 0, stream>>>(flat, prepared);
+  topo_fused_prepare_kernel<<<16, 256, 0, stream>>>(flat, prepared);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
