@@ -126,9 +126,10 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     id = id < 0 ? 0 : (id >= num_nodes ? num_nodes - 1 : id);
     p.X[idx] = emb[id * TF_H + c];
   }
-  for (int e = tid; e < E; e += kTfThreads) {
-    p.src[e] = static_cast<unsigned short>(esrc[e0 + e] - n0);
-    p.dst[e] = static_cast<unsigned short>(edst[e0 + e] - n0);
+  for (int e = tid; e < E; e += kTfThreads) {            // endpoints outside the graph's node range (an edge_ptr that
+    const long long a = esrc[e0 + e] - n0, b = edst[e0 + e] - n0;   // does not describe edge_index) are pinned to node 0
+    p.src[e] = static_cast<unsigned short>(a >= 0 && a < n ? a : 0);
+    p.dst[e] = static_cast<unsigned short>(b >= 0 && b < n ? b : 0);
   }
   for (int idx = tid; idx < E * TF_D; idx += kTfThreads) p.attr[idx] = eattr[e0 * TF_D + idx];
   __syncthreads();
