@@ -123,3 +123,30 @@ def test_store_refuses_cpu_collate():
     st = synthetic.nsfnet_store(2, seed=0)
     with pytest.raises(RuntimeError, match="GPU"):
         st.collate(range(0, 2))
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa_node never raises: without NVML / a GPU it reports why and leaves the affinity alone."""
+    import os
+    from gnn_qot_estimation_b200.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    msg = bind_to_gpu_numa_node(0)
+    assert isinstance(msg, str) and msg
+    os.environ["QOT_NO_NUMA_BIND"] = "1"
+    try:
+        assert bind_to_gpu_numa_node(0) == "numa binding off"
+    finally:
+        del os.environ["QOT_NO_NUMA_BIND"]
+    if before is not None and "bound to" not in msg:
+        assert os.sched_getaffinity(0) == before
+
+
+def test_fused_topological_path_admission():
+    """The block-per-graph kernels take a batch only if its largest graph fits one block's shared memory
+    (and <= 512 edges: four edges per thread in the CSR build); everything else goes layer by layer."""
+    from gnn_qot_estimation_b200 import ops
+    assert ops.topo_fused_fits(14, 42, 14)            # NSFNET (cfg 1 / cfg 3)
+    assert ops.topo_fused_fits(75, 400, 75)           # the real 75-node topology
+    assert not ops.topo_fused_fits(75, 513, 75)       # too many edges for the in-block CSR build
+    assert not ops.topo_fused_fits(400, 100, 75)      # node arrays beyond 227 KB
+    assert not ops.topo_fused_fits(10000, 80000, 10000)   # cfg 5 stays on the layer-by-layer / tensor-core path
