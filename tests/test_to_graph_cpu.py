@@ -75,3 +75,40 @@ def test_topological_oracle_matches_reference_golden_vectors():
             n_lp = len(np.unique(samples["data"][i][0][np.any(samples["data"][i] != 0, axis=0)]))
             dup += int(ei.shape[1] < 2 * n_lp)
     assert dup >= 4                                                     # node pairs shared by several lightpaths occur
+
+
+@pytest.mark.skipif(not (REF / "to_graph.py").exists(), reason="reference checkout not present")
+def test_oracle_matches_reference_code_on_corner_cases():
+    """Hand-built samples through the reference's own code and through the restatement: a single lightpath, two
+    lightpaths that never share a link, two that share a link at distance exactly / just under / just over the
+    threshold, a link carrying one lightpath on two adjacent channels only (skipped by to_graph.py:285), float
+    conn ids (int() truncation), an empty sample."""
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    try:
+        import make_to_graph_golden as mk
+    finally:
+        sys.path.pop(0)
+    from oracle import lightpath_data_ref, topological_data_ref
+    from tg_cases import corner_case_samples
+    samples = corner_case_samples()
+    freqs = samples["freqs"]
+    graphs = mk.reference_graphs(samples)
+    keep = [i for i, g in enumerate(graphs) if len(g) > 0]                 # the reference's dataset class cannot tensorise an empty graph
+    datas, _ = mk.reference_data_objects([graphs[i] for i in keep])
+    for i, d in zip(keep, datas):
+        cn, x, y, ei = lightpath_data_ref(samples["data"][i], samples["target"][i], freqs, samples["lp_feat"], samples["metric"])
+        ref = mk.canonical(graphs[i], d)
+        assert np.array_equal(cn, ref["conn_ids"].numpy()) and np.array_equal(x, ref["x"].numpy()), i
+        assert np.array_equal(y, ref["y"].numpy()) and np.array_equal(ei, ref["edge_index_sorted"].numpy()), i
+    cn, x, y, ei = lightpath_data_ref(samples["data"][-1], samples["target"][-1], freqs, samples["lp_feat"], samples["metric"])
+    assert cn.shape == (0,) and x.shape == (0, 5) and ei.shape == (2, 0)
+    assert [len(g) for g in graphs] == [1, 2, 2, 2, 2, 2, 3, 0]
+    assert [g.number_of_edges() for g in graphs] == [0, 0, 1, 0, 0, 0, 3, 0]
+    tg = mk.reference_graphs(samples, representation="topological")
+    tdatas, _ = mk.reference_topological_data_objects(tg)
+    for i, d in enumerate(tdatas):
+        ei, ea, yy = topological_data_ref(samples["data"][i], samples["target"][i], samples["lp_feat"], samples["metric"])
+        assert np.array_equal(ei, d.edge_index.numpy()) and np.array_equal(ea, d.edge_attr.numpy().reshape(-1, 4)), i
+        assert np.array_equal(yy, d.y.numpy())
+    for k in [k for k in sys.modules if k.split(".")[0] == "torch_geometric"]:
+        del sys.modules[k]

@@ -171,3 +171,24 @@ def test_sample_order_equivariance_and_batch_invariance(cuda):
             assert all(torch.equal(a, b) for a, b in zip(pg[j], base[i]))
         parts = graphs(build(data[:200].contiguous(), tgt[:200]), with_x) + graphs(build(data[200:].contiguous(), tgt[200:]), with_x)
         assert len(parts) == S and all(torch.equal(a, b) for g, h in zip(parts, base) for a, b in zip(g, h))
+
+
+def test_corner_cases_match_oracle(cuda):
+    """The hand-built samples of tests/tg_cases.py (checked on the CPU against the reference's own code): single
+    lightpath, the strict 0.05 boundary, a skipped single-lightpath link, a self loop, float conn ids, an empty
+    sample -- both representations, bit for bit."""
+    from tg_cases import corner_case_samples
+    from gnn_qot_estimation_b200.to_graph import create_topological_graphs
+    from oracle import lightpath_data_ref, topological_data_ref
+    s = corner_case_samples()
+    store, conn = _build(s, cuda)
+    tstore = create_topological_graphs(torch.from_numpy(s["data"]).to(cuda), torch.from_numpy(s["target"]), s["lp_feat"], s["metric"])
+    for i in range(s["data"].shape[0]):
+        ec, ex, ey, eei = lightpath_data_ref(s["data"][i], s["target"][i], s["freqs"], s["lp_feat"], s["metric"])
+        c, x, y, ei = _graph(store, conn, i)
+        assert np.array_equal(c.numpy(), ec) and np.array_equal(x.numpy(), ex) and np.array_equal(ei.numpy(), eei), i
+        assert np.array_equal(y.numpy(), ey)
+        tei, tea, ty = topological_data_ref(s["data"][i], s["target"][i], s["lp_feat"], s["metric"])
+        e0, e1 = int(tstore.edge_ptr[i]), int(tstore.edge_ptr[i + 1])
+        gei = torch.stack([tstore.edge_src[e0:e1], tstore.edge_dst[e0:e1]]).to(torch.int64).cpu().numpy()
+        assert np.array_equal(gei, tei) and np.array_equal(tstore.edge_feat[e0:e1].cpu().numpy(), tea.reshape(-1, 4)), i
