@@ -150,3 +150,33 @@ def test_fused_topological_path_admission():
     assert not ops.topo_fused_fits(75, 513, 75)       # too many edges for the in-block CSR build
     assert not ops.topo_fused_fits(400, 100, 75)      # node arrays beyond 227 KB
     assert not ops.topo_fused_fits(10000, 80000, 10000)   # cfg 5 stays on the layer-by-layer / tensor-core path
+
+
+def test_sources_follow_from_the_destination_histogram_on_from_networkx_layouts():
+    """for the layout from_networkx emits (both directions of every link, grouped by
+    source ascending; a self loop once) the source row is redundant -- src[p] is the node u with
+    outptr[u] <= p < outptr[u+1], and outdeg == indeg == a histogram of the destination row."""
+    import networkx as nx
+    from gnn_qot_estimation_b200 import pyg_compat, synthetic
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        n = int(rng.integers(2, 40))
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        for _ in range(int(rng.integers(0, 3 * n))):
+            u, v = rng.integers(0, n, 2)
+            g.add_edge(int(u), int(v))                      # includes self loops and repeated pairs
+        ei = pyg_compat.utils.from_networkx(g).edge_index.numpy()
+        src, dst = ei[0], ei[1]
+        indeg = np.bincount(dst, minlength=n)
+        outptr = np.concatenate([[0], np.cumsum(indeg)])
+        inferred = np.searchsorted(outptr, np.arange(src.shape[0]), side="right") - 1
+        assert np.array_equal(inferred, src), trial
+    # the synthetic lightpath shards of the benchmark have the same layout
+    st = synthetic.lightpath_store(200, seed=5)
+    for gi in range(200):
+        e0, e1 = int(st.edge_ptr[gi]), int(st.edge_ptr[gi + 1])
+        n = int(st.node_ptr[gi + 1] - st.node_ptr[gi])
+        src, dst = st.edge_src[e0:e1].numpy(), st.edge_dst[e0:e1].numpy()
+        outptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=n))])
+        assert np.array_equal(np.searchsorted(outptr, np.arange(e1 - e0), side="right") - 1, src)
