@@ -56,7 +56,22 @@ def parse_args():
                          "(TopologicalGNN DDP training, batch 1024/GPU); topo_stress = configs[4] (10k nodes, hidden 256)")
     ap.add_argument("--streams", type=int, default=16,
                     help="independent batches in flight in the resident run (graph branches)")
+    ap.add_argument("--min-timed-ms", type=float, default=100.0,
+                    help="the K-step unit is repeated until the timed region is at least this long")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the time-boxed cfg 3 (DDP training) and cfg 5 (stress graph) blocks of the default line")
     return ap.parse_args()
+
+
+def workload_config(args, world: int) -> dict:
+    """`config` of the JSON line: a function of the command line only, so both arms print the same dict."""
+    nb = (args.graphs + args.batch - 1) // args.batch
+    return {"workload": "BASELINE cfg2: LightpathGNN eval (GAT->BN->ReLU->LUT->MLP), "
+                        f"{args.graphs} synthetic lightpath graphs per GPU, n~U{{8..56}}, batch {args.batch}",
+            "batch": args.batch, "graphs_per_gpu": args.graphs, "weights": "lightpath_training/models/model_1.pth",
+            "l2": f"no flush: every repeat of the K-step unit starts at a different batch of the shard's {nb} "
+                  "distinct batches (~1.7 KB/graph; the bytes actually cycled are reported as l2_cycled_bytes)",
+            "parallelism": f"graph-sharded x{world}, no collective"}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -166,8 +181,10 @@ def run_reference(args):
     m = LightpathGNNOracle(5, 32, 3, is_lut_index=1, dropout_p=0.0)
     m.load_state_dict(load_state(), strict=True)
     m.eval()
-    steps = max(1, min(args.steps, 200))                      # bounded: each step = one 4096-graph batch
-    warm = max(1, min(args.warmup, 3))
+    # bounded sample: a step (one 4096-graph batch) is ~0.1 s of CPU work; the caps only bite on the
+    # long default run (24 500 steps) and are stated in `steps` / `warmup` / `cpu_baseline.sample`
+    steps = max(1, min(args.steps, 200))
+    warm = max(1, min(args.warmup, 50))
     with torch.no_grad():
         for i in range(warm):
             m(hbs[i % n_b])
@@ -182,8 +199,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE cfg2: LightpathGNN eval, synthetic lightpath graphs n~U{8..56}, batch 4096",
-                   "batch": args.batch, "weights": "lightpath_training/models/model_1.pth"},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} batches of {args.batch} graphs, pure-PyTorch oracle (PyG absent)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -192,6 +208,83 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- B200 arm
+class ResidentRunner:
+    """The K timed steps as CUDA graphs over batches resident in HBM.
+
+    A *unit* is a captured graph of `unit_steps` consecutive steps (a multiple of K, at least
+    `min_unit` steps so that a replay is long against the CPU's graph-launch cost) with `S`
+    independent batches in flight as graph branches.  Successive units start at successive
+    batches of the shard (wrapping), so consecutive replays read different bytes.  Every
+    distinct unit graph is replayed once before the timed region: no cold replay is ever timed."""
+
+    def __init__(self, model, batches, outs, K: int, S: int, min_unit: int = 256, max_variants: int = 16):
+        self.model, self.batches, self.outs = model, batches, outs
+        self.nb, self.K, self.S = len(batches), K, max(1, S)
+        self.side = torch.cuda.Stream()
+        self.branches = [torch.cuda.Stream() for _ in range(self.S)] if self.S > 1 else [self.side]
+        if K >= self.nb:                                          # a unit = one pass over the shard
+            self.unit_steps, self.n_var = self.nb, 1
+        else:
+            self.unit_steps = K * max(1, -(-min_unit // K))       # a multiple of K, >= min_unit steps
+            self.n_var = 1 if self.unit_steps >= self.nb else min(-(-self.nb // self.unit_steps), max_variants)
+        self.graphs = []
+
+    def run_steps(self, first: int, count: int):
+        cur = torch.cuda.current_stream()
+        S = self.S
+        if S > 1:
+            for b in self.branches:
+                b.wait_stream(cur)
+        for s in range(first, first + count):
+            i = s % self.nb
+            if S > 1:
+                with torch.cuda.stream(self.branches[s % S]):
+                    self.model.forward_device(self.batches[i], self.outs[i])
+            else:
+                self.model.forward_device(self.batches[i], self.outs[i])
+        if S > 1:
+            for b in self.branches:
+                cur.wait_stream(b)
+
+    def capture(self, warmup_steps: int):
+        with torch.cuda.stream(self.side):
+            self.run_steps(0, max(warmup_steps, 3))                # eager warm-up on the streams captured below
+            torch.cuda.synchronize()
+            for v in range(self.n_var):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.side):
+                    self.run_steps(v * self.unit_steps, self.unit_steps)
+                self.graphs.append(g)
+            for g in self.graphs:                                  # upload + first replay outside the timed region
+                g.replay()
+            torch.cuda.synchronize()
+
+    def replay(self, n_units: int):
+        """Enqueues `n_units` unit replays on the side stream (cycling through the variants)."""
+        for r in range(n_units):
+            self.graphs[r % self.n_var].replay()
+
+    def timed(self, n_units: int, ev0, ev1):
+        with torch.cuda.stream(self.side):
+            ev0.record(self.side)
+            self.replay(n_units)
+            ev1.record(self.side)
+
+    def graphs_in(self, n_units: int) -> int:
+        tot = 0
+        for r in range(n_units):
+            f = (r % self.n_var) * self.unit_steps
+            tot += sum(self.batches[s % self.nb].num_graphs for s in range(f, f + self.unit_steps))
+        return tot
+
+    def distinct_batches(self, n_units: int):
+        seen = set()
+        for r in range(min(n_units, self.n_var)):
+            f = r * self.unit_steps
+            seen.update(s % self.nb for s in range(f, f + self.unit_steps))
+        return sorted(seen)
+
+
 def run_b200(args):
     import torch.distributed as dist
     from gnn_qot_estimation_b200 import LightpathGNN, synthetic
@@ -214,6 +307,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_ranks(v: float):
+        """[v of rank 0, ..., v of rank world-1] on every rank."""
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = v
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(a) for a in t.tolist()]
+
     model = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0)
     model.load_state_dict(load_state(), strict=True)
     model.to(dev).eval()
@@ -225,70 +326,36 @@ def run_b200(args):
     batches = [store.collate(range(i * Bsz, min((i + 1) * Bsz, G))) for i in range(nb)]
     outs = [model.forward_device(b) for b in batches]            # eager pass: allocates outputs, warms up
     torch.cuda.synchronize()
-    input_bytes = sum(b.nbytes(("x", "edge_index", "ptr", "edge_ptr", "lut_ptr")) for b in batches)
     launches_per_step = model.launches_per_step
 
-    K, W = args.steps, max(args.warmup, 3)
-    S = max(1, args.streams)
-    side = torch.cuda.Stream()
-    branches = [torch.cuda.Stream() for _ in range(S)] if S > 1 else [side]
-
-    def run_steps(first, count, fork=False):
-        """`count` steps starting at batch `first`; with S > 1 consecutive steps go round-robin onto S
-        streams forked from / joined back into the current one (independent batches overlap)."""
-        cur = torch.cuda.current_stream()
-        if fork and S > 1:
-            for b in branches:
-                b.wait_stream(cur)
-        for s in range(first, first + count):
-            i = s % nb
-            if fork and S > 1:
-                with torch.cuda.stream(branches[s % S]):
-                    model.forward_device(batches[i], outs[i])
-            else:
-                model.forward_device(batches[i], outs[i])
-        if fork and S > 1:
-            for b in branches:
-                cur.wait_stream(b)
-
-    # warm-up (eager, on the streams that will be captured so their scratch exists), then capture
-    # the K timed steps as CUDA graphs: whole passes over the shard + a remainder
-    passes, rem = divmod(K, nb)
-    g_pass = g_rem = None
-    with torch.cuda.stream(side):
-        run_steps(0, W, fork=True)
+    K, W = max(1, args.steps), max(args.warmup, 3)
+    runner = ResidentRunner(model, batches, outs, K, args.streams)
+    runner.capture(W)
+    # ---- calibrate: how many unit replays make the timed region >= --min-timed-ms (same count on every rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n_cal = max(runner.n_var, 2)
+    runner.timed(n_cal, ev0, ev1)
+    torch.cuda.synchronize()
+    unit_ms = max(all_ranks(ev0.elapsed_time(ev1) / n_cal))
+    n_units = max(1, int(-(-args.min_timed_ms // max(unit_ms, 1e-6))), -(-K // runner.unit_steps))
+    n_units = min(n_units, 1_000_000)
+    timed_steps = n_units * runner.unit_steps
+    graphs_done = runner.graphs_in(n_units)
+    barrier()
+    with ClockSampler(local) as clk:
+        runner.timed(n_units, ev0, ev1)
         torch.cuda.synchronize()
-        if passes:
-            g_pass = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_pass, stream=side):
-                run_steps(0, nb, fork=True)
-        if rem:
-            g_rem = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_rem, stream=side):
-                run_steps(0, rem, fork=True)
-        if g_pass is not None:
-            g_pass.replay()
-        torch.cuda.synchronize()
-        graphs_done = passes * G + sum(batches[i].num_graphs for i in range(rem))
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with ClockSampler(local) as clk:
-            ev0.record(side)
-            for _ in range(passes):
-                g_pass.replay()
-            if g_rem is not None:
-                g_rem.replay()
-            ev1.record(side)
-            torch.cuda.synchronize()
-        barrier()
+    barrier()
     ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * graphs_done / (ms_max * 1e-3)
+    per_rank_ms = all_ranks(ms)
+    ms_max = max(per_rank_ms)
+    graphs_all = sum(all_ranks(float(graphs_done)))
+    value = graphs_all / (ms_max * 1e-3)
+    cycled = runner.distinct_batches(n_units)
+    l2_cycled_bytes = sum(batches[i].nbytes(("x", "ptr", "edge_ptr", "lut_ptr")) + batches[i].num_edges * 8 for i in cycled)
 
-    # ---- checksum of the last pass against an eager run through the oracle-checked module path
+    # ---- checksum of the replays against an eager run through the oracle-checked module path
     n_chk = min(nb, 3)
     for i in range(n_chk):
         with torch.no_grad():
@@ -296,20 +363,22 @@ def run_b200(args):
         n = int(outs[i].n_lut.item())
         assert n == ref.shape[0] and torch.equal(outs[i].out[:n], ref), "graph replay diverged from eager path"
 
-    # ---- roofline of the dominant kernel: duration measured live (steps are back to back on one
-    # stream; the step is the kernel chain of qot_lightpath_infer)
-    alg = sum(algorithmic_bytes(b) for b in batches) / nb
-    step_s = ms * 1e-3 / K
+    # ---- roofline of the dominant kernel: its average duration over the timed region, measured live
+    # (CUDA events on the launching stream; the region is nothing but launches of that kernel)
+    alg = sum(algorithmic_bytes(batches[i]) for i in cycled) / len(cycled)
+    step_s = ms * 1e-3 / timed_steps
     peak, peak_kind = peaks()
     achieved = alg / step_s / 1e9
     traffic = None
-    tp = ROOT / "profiles" / "r1_lp_infer_traffic.json"          # dram__bytes_{read,write}.sum of one ncu --set full capture
+    tp = ROOT / "profiles" / "lp_infer_traffic.json"             # dram__bytes_{read,write}.sum of one ncu --set full capture
     if tp.exists() and Bsz == 4096:
         tj = json.loads(tp.read_text())
-        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+        if tj.get("kernel") == model.dominant_kernel:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": model.dominant_kernel, "alg_bytes_per_launch": alg,
-                "avg_launch_us": step_s * 1e6, "launches_in_flight": S, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"}
+                "traffic": traffic, "kernel": model.dominant_kernel, "alg_bytes_per_launch": alg * model.batches_per_launch,
+                "avg_launch_us": step_s * 1e6 * model.batches_per_launch, "launches_in_flight": runner.S,
+                "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"}
 
     # ---- end to end: pinned host batches -> H2D -> kernels -> D2H, through the public pipeline API
     e2e = None
@@ -320,29 +389,28 @@ def run_b200(args):
         hbs = [cpu_store.host_batch(i * Bsz, (i + 1) * Bsz, pin=True) for i in range(n_host)]
         pipe = LightpathInferencePipeline(model, max_nodes=max(b.num_nodes for b in hbs),
                                           max_edges=max(b.num_edges for b in hbs), max_graphs=Bsz, depth=args.e2e_depth)
+        # the K-step sequence repeated until the region is long enough to time (>= ~0.15 s of copies)
         Ke = max(1, min(args.e2e_steps, K))
+        Ke = Ke * max(1, -(-1500 // Ke))
         seq = [hbs[i % n_host] for i in range(Ke)]
         pipe.run(seq[: max(3, min(W, 16))])                    # warm-up
+        h2d0, zc0, d2h0, st0 = pipe.h2d_bytes, pipe.zero_copy_bytes, pipe.d2h_bytes, pipe.steps
         barrier()
         t0 = time.perf_counter()
         res = pipe.run(seq)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ge = sum(b.num_graphs for b in seq)
+        dt_max = max(all_ranks(dt))
+        ge = sum(all_ranks(float(sum(b.num_graphs for b in seq))))
         # parity of the pipeline against the module path on one batch
         with torch.no_grad():
             o_ref, l_ref = model(hbs[0].to(dev))
         assert torch.equal(res[0][0], o_ref.cpu()) and torch.equal(res[0][1], l_ref.cpu())
-        e2e = {"value": world * ge / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": (pipe.h2d_bytes + pipe.zero_copy_bytes) / max(pipe.steps, 1),
-               "d2h_bytes_per_step": pipe.d2h_bytes / max(pipe.steps, 1), "steps": Ke,
-               "h2d_note": "copied in ONE transfer per step (the host batch keeps them contiguous): destination row of "
-                           "edge_index, ptr/edge_ptr/lut_ptr, x; the source row stays in "
-                           "pinned host memory and the kernel reads ~4 sectors (32 B) per LUT row from it over PCIe "
-                           f"(~{pipe.zero_copy_bytes / max(pipe.steps, 1):.0f} B/step, estimated, included)"}
+        n_st = max(pipe.steps - st0, 1)
+        e2e = {"value": ge / dt_max, "unit": UNIT,
+               "h2d_bytes_per_step": (pipe.h2d_bytes - h2d0 + pipe.zero_copy_bytes - zc0) / n_st,
+               "d2h_bytes_per_step": (pipe.d2h_bytes - d2h0) / n_st, "steps": Ke, "ms_per_step": dt_max / Ke * 1e3,
+               "h2d_note": pipe.wire_note}
 
     cpu_base = None
     if all_cpus is not None:
@@ -356,18 +424,34 @@ def run_b200(args):
                     "sample": f"{n_it} batches of {Bsz} graphs ({n_g} graphs), pure-PyTorch oracle of the "
                               f"PyG path (torch_geometric absent), fp32, {threads} threads"}
 
+    # ---- secondary, time-boxed: BASELINE cfg 3 (DDP training step, exercises the gradient exchange at N > 1)
+    # and cfg 5 (stress graph, rank 0 only: replicas).  Not part of `value`.
+    secondary = None
+    if not args.no_secondary:
+        del runner, outs, batches, store
+        torch.cuda.empty_cache()
+        import bench_topological
+        secondary = {}
+        try:
+            secondary["cfg3_topo_train"] = bench_topological.measure_train(world, rank, dev, steps=300, warmup=20)
+        except Exception as e:                                    # noqa: BLE001 -- a secondary block never kills the headline
+            secondary["cfg3_topo_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0:
+            try:
+                secondary["cfg5_topo_stress"] = bench_topological.measure_stress(dev, reps=10)
+            except Exception as e:                                # noqa: BLE001
+                secondary["cfg5_topo_stress"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        barrier()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE cfg2: LightpathGNN eval (GAT->BN->ReLU->LUT->MLP), "
-                                   f"{G} synthetic lightpath graphs per GPU, n~U{{8..56}}, batch {Bsz}",
-                       "batch": Bsz, "graphs_per_gpu": G, "weights": "lightpath_training/models/model_1.pth",
-                       "l2": f"inputs cycle through {input_bytes / 1e9:.2f} GB of distinct batches (> 126 MB L2)",
-                       "parallelism": f"graph-sharded x{world}, no collective", "host": numa},
+            "ms_per_step": ms_max / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "repeats": timed_steps / K, "timed_steps": timed_steps, "timed_region_ms": ms_max,
+            "per_rank_ms": per_rank_ms, "l2_cycled_bytes": l2_cycled_bytes, "host": numa,
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
-            "gpu_launches": launches_per_step * K, "clocks": clk.summary(),
+            "gpu_launches": launches_per_step * timed_steps, "clocks": clk.summary(), "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

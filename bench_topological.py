@@ -125,6 +125,24 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    res = measure_train(world, rank, dev, steps=K, warmup=W, graph=not getattr(args, "no_graph", False))
+    if rank == 0:
+        print(json.dumps({"metric": "topo_train_graphs_per_sec", "unit": "graphs/s", "n_gpus": world,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic", **res}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20, graph: bool = True,
+                  min_timed_ms: float = 60.0) -> dict:
+    """BASELINE cfg 3: TopologicalGNN(14,16,3) train step (zero_grad -> forward -> SmoothL1 -> backward ->
+    gradient all-reduce -> SGD(0.1, 0.9)) on 1024 NSFNET graphs per GPU, the process group (if any) already
+    initialised.  Returns the JSON fields; every rank must call it (the step holds a collective at N > 1)."""
+    import torch.distributed as dist
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    from gnn_qot_estimation_b200.distributed import GraphDataParallel
+    B = 1024
     torch.manual_seed(0)
     model = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev)
     ddp = GraphDataParallel(model)
@@ -135,7 +153,7 @@ def run_train(args):
     batches = [store.collate(range(i * B, (i + 1) * B)) for i in range(nb)]
 
     graphed = None
-    if not getattr(args, "no_graph", False):
+    if graph:
         from gnn_qot_estimation_b200.graphed import GraphedTrainStep
         graphed = GraphedTrainStep(model, opt, crit, batches[0], ddp=ddp)
 
@@ -150,32 +168,54 @@ def run_train(args):
         opt.step()
         return loss
 
-    for i in range(W):
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n):
+        e0, e1 = _ev(), _ev()
+        sync()
+        e0.record()
+        for i in range(n):
+            loss = step(i)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), loss
+
+    for i in range(max(warmup, 3)):
         step(i)
-    torch.cuda.synchronize()
+    ms, loss = timed(steps)
+    n = steps
+    if ms < min_timed_ms:                                    # every rank sees the same (max-reduced) time
+        n = int(steps * min(50.0, min_timed_ms / max(ms, 1e-3))) + 1
+        ms, loss = timed(n)
+    out = {"value": world * n * B / (ms * 1e-3), "steps": n, "warmup": max(warmup, 3), "ms_per_step": ms / n,
+           "final_loss": float(loss),
+           "config": {"workload": "BASELINE cfg3: TopologicalGNN(14,16,3) train step, NSFNET graphs, "
+                                  f"batch {B}/GPU, SGD(0.1, 0.9), flat grad all-reduce x{world}",
+                      "cuda_graph": graphed is not None,
+                      "exchange": (graphed.exchange if graphed is not None else ("eager" if world > 1 else "none"))}}
+    # the collective alone: the flat gradient all-reduce as the step issues it, back to back
     if world > 1:
-        dist.barrier()
-    e0, e1 = _ev(), _ev()
-    e0.record()
-    for i in range(K):
-        loss = step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(json.dumps({"metric": "topo_train_graphs_per_sec", "value": world * K * B / (float(ms) * 1e-3),
-                          "unit": "graphs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": float(ms) / K,
-                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
-                          "final_loss": float(loss),
-                          "config": {"workload": "BASELINE cfg3: TopologicalGNN(14,16,3) train step, NSFNET graphs, "
-                                                 f"batch {B}/GPU, SGD(0.1, 0.9), flat grad all-reduce x{world}",
-                                     "cuda_graph": graphed is not None}}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        e0, e1 = _ev(), _ev()
+        for _ in range(10):
+            ddp.grads.all_reduce_mean()
+        sync()
+        e0.record()
+        for _ in range(100):
+            ddp.grads.all_reduce_mean()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["allreduce_us"] = float(t) * 10.0                # ms / 100 calls -> us
+        out["allreduce_bytes"] = int(ddp.grads.flat.numel() * 4)
+    return out
 
 
 # --------------------------------------------------------------------------- cfg 5
@@ -199,13 +239,24 @@ def run_stress(args):
                                            "sample": "5 forwards, factorised NNConv (direct form needs 21 GB)"}}), flush=True)
         return
     dev = torch.device("cuda", 0)
+    res = measure_stress(dev)
+    print(json.dumps({"metric": "topo_stress_fwd_ms", "unit": "ms", "n_gpus": 1, "higher_is_better": False,
+                      "dtype": "f32", "data": "synthetic", **res}), flush=True)
+
+
+def measure_stress(dev, reps: int = 20) -> dict:
+    """BASELINE cfg 5: TopologicalGNN(10000,256,3) forward (and forward + backward) on ONE 10k-node /
+    80k-directed-edge graph, L2 flushed between iterations; per-kernel roofline of the two aggregation kernels
+    (algorithmic bytes of SURVEY 8d / BASELINE.md section 4 over their CUDA-event time)."""
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    N, LINKS, H = 10000, 40000, 256
     torch.manual_seed(0)
     model = TopologicalGNN(N, H, 3, edge_dim=4, dropout_p=0.0).to(dev)
     b = synthetic.random_topology_store(N, LINKS, seed=2).to(dev).collate(range(0, 1))
     E = b.num_edges
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def timed(fn, reps=20):
+    def timed(fn, reps=reps):
         ts = []
         for _ in range(reps):
             flush.zero_()
@@ -230,8 +281,7 @@ def run_stress(args):
         fb()
     fb_ms = timed(fb)
     conv_bytes = 8 * H * N + 4 * (N + 1) + 4 * E + 16 * E
-    print(json.dumps({"metric": "topo_stress_fwd_ms", "value": fwd_ms, "unit": "ms", "n_gpus": 1,
-                      "higher_is_better": False, "fwd_bwd_ms": fb_ms, "dtype": "f32", "data": "synthetic",
-                      "alg_bytes": {"conv_fwd_each": conv_bytes, "fwd_total": 2 * conv_bytes + 4 * H * N + 4 * 2 + 12},
-                      "config": {"workload": f"BASELINE cfg5: TopologicalGNN({N},{H},3), one graph, {N} nodes, {E} directed "
-                                             "edges; L2 flushed between iterations"}}), flush=True)
+    return {"value": fwd_ms, "fwd_bwd_ms": fb_ms,
+            "alg_bytes": {"conv_fwd_each": conv_bytes, "fwd_total": 2 * conv_bytes + 4 * H * N + 4 * 2 + 12},
+            "config": {"workload": f"BASELINE cfg5: TopologicalGNN({N},{H},3), one graph, {N} nodes, {E} directed "
+                                   "edges; L2 flushed between iterations"}}

@@ -6,6 +6,7 @@ any compute op raises, and every op refuses non-CUDA tensors.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from pathlib import Path
 
 import torch
@@ -166,6 +167,35 @@ def ptr(t):
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.device
+        elif not isinstance(a, torch.nn.Module):
+            t = getattr(a, "edge_index", None)
+            if torch.is_tensor(t) and t.is_cuda:
+                return t.device
+            d = getattr(a, "device", None)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                return d
+    return None
+
+
+def on_tensor_device(fn):
+    """Runs `fn` with the device of its first CUDA tensor (or batch / store) argument current, so that
+    `stream()`, workspaces and every `cudaFuncSetAttribute` inside the library refer to the GPU the data
+    lives on -- a process may drive several GPUs (one process per GPU is the normal deployment)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 _ws_cache = {}

@@ -110,6 +110,7 @@ class PackedGraphStore:
                     self.edge_feat, self.y) if t is not None)
 
     # -- device-side collate ---------------------------------------------------
+    @_lib.on_tensor_device
     def collate(self, ids: Union[range, slice, torch.Tensor, Sequence[int]]) -> Batch:
         """Collates graphs ``ids`` into one :class:`Batch` on the store's CUDA device
         with one launch of ``qot_collate``; no device->host synchronisation."""

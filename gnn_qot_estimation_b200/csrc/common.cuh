@@ -1,6 +1,7 @@
 // Shared host/device helpers for libqot_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -48,6 +49,19 @@ constexpr unsigned kFull = 0xffffffffu;
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// cudaFuncSetAttribute is a per-DEVICE setting: `done` keeps one bit per device ordinal, so a process
+// driving several GPUs opts every one of them in (and two threads racing only repeat an idempotent call).
+template <typename F>
+static inline int once_per_device(std::atomic<unsigned long long>& done, F&& set) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return QOT_E_CUDA;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return QOT_OK;
+  const int rc = set();
+  if (rc == QOT_OK) done.fetch_or(bit, std::memory_order_release);
+  return rc;
+}
 
 // Carves aligned sub-buffers out of the caller's workspace.
 struct Carver {

@@ -306,6 +306,14 @@ using namespace qot;
 // lda/ldw % 4 == 0 and 16-byte aligned bases (128-bit accesses).  ws: qot_gemm_tf32x3_workspace_bytes(M,Nc,K)
 // bytes for the hi / lo halves of both operands.  status (optional, device int32): bit 1 is set if a
 // pipeline barrier timed out (never observed; the result is then undefined, the kernel still ends).
+static int tc_attr() {
+  static std::atomic<unsigned long long> done{0};
+  return once_per_device(done, [] {
+    QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    return static_cast<int>(QOT_OK);
+  });
+}
+
 extern "C" size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K) {
   if (M < 0 || Nc < 0 || K < 0) return 0;
   return 2 * align_up(static_cast<size_t>(M) * K * 4) + 2 * align_up(static_cast<size_t>(Nc) * K * 4) + 256;
@@ -324,11 +332,7 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
                   (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
               "qot_gemm_tf32x3: operands must be 16-byte aligned");
   QOT_REQUIRE(ws && ws_bytes >= qot_gemm_tf32x3_workspace_bytes(M, Nc, K), "qot_gemm_tf32x3: workspace too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = tc_attr()) return rc;
   Carver c(ws);
   float* a_hi = c.take<float>(M * K);
   float* a_lo = c.take<float>(M * K);
@@ -372,11 +376,7 @@ extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int
   QOT_REQUIRE(R > 0 && Mo > 0 && No > 0, "qot_wgrad_tf32x3: bad size");
   QOT_REQUIRE(A && B && C && ldc >= No, "qot_wgrad_tf32x3: null operand");
   QOT_REQUIRE(ws && ws_bytes >= qot_wgrad_tf32x3_workspace_bytes(R, Mo, No), "qot_wgrad_tf32x3: workspace too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = tc_attr()) return rc;
   const int64_t rp = tc_rpad(R), nkb = rp / TC_BK;
   const int64_t tiles = cdiv(Mo, TC_BM) * cdiv(No, TC_BN);
   const int splits = tc_wgrad_splits(tiles, nkb);

@@ -450,13 +450,12 @@ static int tg_check(const float* data, const double* freqs, int64_t S, const qot
   return QOT_OK;
 }
 static int tg_attr() {
-  static bool done = false;
-  if (!done) {
+  static std::atomic<unsigned long long> done{0};
+  return once_per_device(done, [] {
     QOT_CUDA(cudaFuncSetAttribute(lp_graph_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TgSmem))));
     QOT_CUDA(cudaFuncSetAttribute(tp_graph_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TpSmem))));
-    done = true;
-  }
-  return QOT_OK;
+    return static_cast<int>(QOT_OK);
+  });
 }
 
 }  // namespace qot

@@ -116,18 +116,24 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
                                  const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes,
                                  float* __restrict__ save_n, float* __restrict__ save_e, float* __restrict__ save_g,
                                  const float* __restrict__ rest_n, const float* __restrict__ rest_e,
-                                 const float* __restrict__ rest_g) {
+                                 const float* __restrict__ rest_g, int32_t* __restrict__ status) {
   const int tid = threadIdx.x;
   const float* __restrict__ par = p.par;
-  // ---- inputs
+  // ---- inputs.  Out-of-range ids / endpoints are clamped for memory safety AND reported (status bit 2: the
+  // reference's embedding lookup / scatter would raise on them); ops.check_status() turns the bit into an error
   for (int idx = tid; idx < n * TF_H; idx += kTfThreads) {
     const int i = idx >> 4, c = idx & 15;
     long long id = node_ids[n0 + i];
-    id = id < 0 ? 0 : (id >= num_nodes ? num_nodes - 1 : id);
+    if (id < 0 || id >= num_nodes) {
+      if (c == 0) atomicOr(status, 2);
+      id = id < 0 ? 0 : num_nodes - 1;
+    }
     p.X[idx] = emb[id * TF_H + c];
   }
-  for (int e = tid; e < E; e += kTfThreads) {            // endpoints outside the graph's node range (an edge_ptr that
-    const long long a = esrc[e0 + e] - n0, b = edst[e0 + e] - n0;   // does not describe edge_index) are pinned to node 0
+  for (int e = tid; e < E; e += kTfThreads) {            // endpoints outside the graph's node range: an edge_ptr that
+    const long long a = esrc[e0 + e] - n0, b = edst[e0 + e] - n0;   // does not describe edge_index
+    const bool ok = a >= 0 && a < n && b >= 0 && b < n;
+    if (!ok) atomicOr(status, 2);
     p.src[e] = static_cast<unsigned short>(a >= 0 && a < n ? a : 0);
     p.dst[e] = static_cast<unsigned short>(b >= 0 && b < n ? b : 0);
   }
@@ -338,11 +344,12 @@ topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
     const int64_t n = gptr[g + 1] - n0, E = eptr[g + 1] - e0;
     if (n < 0 || E < 0 || n > nmax || E > emax) {       // caps come from the same arrays on the host: never expected
       if (threadIdx.x == 0) atomicOr(status, 1);
+      if (threadIdx.x < QOT_OUT) out[g * QOT_OUT + threadIdx.x] = __int_as_float(0x7fc00000);   // NaN, never stale memory
       continue;
     }
     tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
                      saved ? saved + n0 * kTfSaveNode : nullptr, saved ? sv_e + e0 * kTfSaveEdge : nullptr,
-                     saved ? sv_g + g * kTfSaveGraph : nullptr, nullptr, nullptr, nullptr);
+                     saved ? sv_g + g * kTfSaveGraph : nullptr, nullptr, nullptr, nullptr, status);
     if (threadIdx.x < QOT_OUT) out[g * QOT_OUT + threadIdx.x] = p.small[48 + threadIdx.x];
     __syncthreads();
   }
@@ -630,7 +637,7 @@ topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
     TF_STAMP(0);
     tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
                      nullptr, nullptr, nullptr, saved ? saved + n0 * kTfSaveNode : nullptr,
-                     saved ? sv_e + e0 * kTfSaveEdge : nullptr, saved ? sv_g + g * kTfSaveGraph : nullptr);
+                     saved ? sv_e + e0 * kTfSaveEdge : nullptr, saved ? sv_g + g * kTfSaveGraph : nullptr, status);
     if (threadIdx.x < QOT_OUT) p.small[52 + threadIdx.x] = dout[g * QOT_OUT + threadIdx.x];
     __syncthreads();
     tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes);

@@ -4,9 +4,21 @@ The reference's inner loop (``topological_training/train.py:107-116``: ``zero_gr
 SmoothL1 -> ``backward`` -> ``step``) is ~60 small kernels at batch 512-1024; on a B200 each is a
 few microseconds, so the step is bound by Python / launch latency, not by the GPU.  Every entry
 point of libqot_b200 enqueues on the caller's stream without synchronising, so the whole step --
-CSR build, both conv layers, pooling head, loss, all backward kernels (graph A) and the SGD update
-(graph B) -- is captured once and replayed per batch, with the flat NCCL gradient all-reduce issued
-eagerly between the two replays.
+CSR build, both conv layers, pooling head, loss, all backward kernels, the gradient exchange and the
+optimizer update -- is captured once and replayed per batch.
+
+Gradient exchange under data parallelism (``ddp=GraphDataParallel(model)``), ``exchange=``:
+
+* ``"graph"`` (default): the flat NCCL all-reduce is captured INSIDE the step graph -- one replay per
+  step, no eager launch between kernels;
+* ``"eager"``: graph A (zero -> forward -> loss -> backward -> gather) / eager all-reduce / graph B
+  (optimizer), the round-1 arrangement, kept for NCCL builds that refuse capture.
+
+Constructing the object does NOT move the model: parameters, buffers and optimizer state are
+snapshotted before the warm-up steps that capture needs and restored in place afterwards.  The
+optimizer's hyper-parameters (lr after ``StepLR.step()``, momentum, weight decay ...) are baked into
+a captured update as host scalars, so ``step()`` compares them with the values captured and
+re-captures the update when a scheduler changed them.
 
 Static shapes only (N, E, B fixed, e.g. batches of one topology such as BASELINE cfg 1/3); a batch
 of another shape raises.  Dropout masks drawn with ``torch.rand`` inside the captured region advance
@@ -14,23 +26,38 @@ correctly on replay (torch's CUDA generator registers with the graph).
 """
 from __future__ import annotations
 
+import copy
+import os
 from typing import Callable, Optional
 
 import torch
 
 from .batch import Batch, _FIELDS
 
+_HYPER_KEYS = ("lr", "momentum", "dampening", "weight_decay", "nesterov", "maximize", "betas", "eps", "amsgrad")
+
+
+def _hyper(opt: torch.optim.Optimizer):
+    return tuple(tuple((k, float(g[k]) if isinstance(g[k], (int, float)) else repr(g[k]))
+                       for k in _HYPER_KEYS if k in g) for g in opt.param_groups)
+
 
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, criterion: Callable,
-                 example: Batch, target_of: Optional[Callable] = None, ddp=None, warmup: int = 3):
+                 example: Batch, target_of: Optional[Callable] = None, ddp=None, warmup: int = 3,
+                 exchange: Optional[str] = None):
         """``model(batch)`` -> prediction; ``criterion(pred, target_of(batch))`` -> scalar loss.
-        ``ddp``: a :class:`~.distributed.GraphDataParallel` wrapping ``model`` (its zero / flat
-        all-reduce are captured too); ``None`` for single-GPU training."""
+        ``ddp``: a :class:`~.distributed.GraphDataParallel` wrapping ``model``; ``None`` for
+        single-GPU training."""
         if not example.edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs a CUDA batch (no CPU path)")
         self.model, self.opt, self.crit, self.ddp = model, optimizer, criterion, ddp
         self.target_of = target_of or (lambda b: b.y.view(-1, 3))
+        exchange = exchange or os.environ.get("QOT_DDP_EXCHANGE", "graph")
+        if exchange not in ("graph", "eager"):
+            raise ValueError(f"exchange must be 'graph' or 'eager', got {exchange!r}")
+        from .distributed import world_info
+        self.exchange = exchange if (ddp is not None and world_info()[1] > 1) else "none"
         self.static = Batch(num_graphs=example.num_graphs, lut_col=example.lut_col,
                             **{k: (getattr(example, k).clone() if getattr(example, k) is not None else None)
                                for k in _FIELDS})
@@ -41,23 +68,62 @@ class GraphedTrainStep:
         self.static.max_nodes, self.static.max_edges = ops.batch_max_sizes(example)
         self.stream = torch.cuda.Stream()
         self.stream.wait_stream(torch.cuda.current_stream())
+        # ---- snapshot: the warm-up below takes real optimizer steps
+        model_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        opt_sd = copy.deepcopy(optimizer.state_dict())
+        had_state = len(optimizer.state) > 0
         with torch.cuda.stream(self.stream):
             for _ in range(max(warmup, 1)):          # allocates workspaces / optimizer state eagerly
                 self._front()
                 self._exchange()
                 self.opt.step()
             torch.cuda.synchronize()
-            # graph A: zero -> forward -> loss -> backward (-> gather into the flat buffer);
-            # graph B: optimizer update.  The gradient all-reduce runs between the two, eagerly on
-            # the same stream: a collective inside a captured region would tie every rank's capture
-            # and replay to NCCL's internal streams for no gain (it is one 21 KB call per step).
+            self._capture()
+            torch.cuda.synchronize()
+            # ---- restore in place (the graphs hold the addresses of these tensors)
+            with torch.no_grad():
+                for k, v in model.state_dict().items():
+                    v.copy_(model_sd[k])
+                if had_state:
+                    cur = optimizer.state_dict()["state"]
+                    for idx, st in opt_sd["state"].items():
+                        for name, val in st.items():
+                            if torch.is_tensor(val):
+                                cur[idx][name].copy_(val)
+                else:
+                    # fresh optimizer: zeroed buffers reproduce the first-step rule of SGD / Adam exactly
+                    # (buf = 0 * momentum + grad), except for SGD with dampening != 0
+                    for group in optimizer.param_groups:
+                        if group.get("dampening", 0) != 0:
+                            raise NotImplementedError("GraphedTrainStep: SGD dampening != 0 with a fresh optimizer")
+                    for st in optimizer.state.values():
+                        for name, val in st.items():
+                            if torch.is_tensor(val):
+                                val.zero_()
+            torch.cuda.synchronize()
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    # ------------------------------------------------------------------ capture
+    def _capture(self) -> None:
+        self.hyper = _hyper(self.opt)
+        self.graph_b = None
+        if self.exchange == "eager":
             self.graph_a = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_a, stream=self.stream):
                 self.loss = self._front()
-            self.graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_b, stream=self.stream):
+            self._capture_update()
+        else:
+            # one graph: zero -> forward -> loss -> backward (-> gather -> all-reduce) -> optimizer
+            self.graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_a, stream=self.stream):
+                self.loss = self._front()
+                self._exchange()
                 self.opt.step()
-        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def _capture_update(self) -> None:
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, stream=self.stream):
+            self.opt.step()
 
     def _front(self) -> torch.Tensor:
         self.static._cache = {}                      # the CSR of the batch is rebuilt inside the step
@@ -70,7 +136,26 @@ class GraphedTrainStep:
 
     def _exchange(self) -> None:
         if self.ddp is not None:
-            self.ddp.grads.all_reduce_mean()         # eager NCCL all-reduce of the flat buffer
+            self.ddp.grads.all_reduce_mean()         # flat NCCL all-reduce (captured or eager)
+
+    def _check_hyper(self) -> None:
+        """A scheduler (``StepLR.step()``) changes ``param_groups``; the captured update holds the old
+        values as host scalars: re-capture it (the whole step when it is one graph)."""
+        if _hyper(self.opt) == self.hyper:
+            return
+        with torch.cuda.stream(self.stream):
+            torch.cuda.synchronize()
+            self.hyper = _hyper(self.opt)
+            if self.graph_b is not None:
+                self._capture_update()
+            else:
+                # re-capturing runs nothing: parameters and optimizer state are untouched
+                self.graph_a = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_a, stream=self.stream):
+                    self.loss_new = self._front()
+                    self._exchange()
+                    self.opt.step()
+                self.loss = self.loss_new
 
     def step(self, batch: Batch) -> torch.Tensor:
         """Copies ``batch`` into the static buffers and replays the captured step; returns the
@@ -81,15 +166,20 @@ class GraphedTrainStep:
                 raise RuntimeError(f"GraphedTrainStep was captured for {k}{shape}; got "
                                    f"{None if t is None else tuple(t.shape)} (static shapes only)")
         mn, me = getattr(batch, "max_nodes", None), getattr(batch, "max_edges", None)
-        if (mn is not None and mn > self.static.max_nodes) or (me is not None and me > self.static.max_edges):
+        if mn is None or me is None:
+            from . import ops
+            mn, me = ops.batch_max_sizes(batch)      # foreign batch: one device->host read, cached on the batch
+        if mn > self.static.max_nodes or me > self.static.max_edges:
             raise RuntimeError(f"GraphedTrainStep was captured for graphs of <= {self.static.max_nodes} nodes / "
                                f"{self.static.max_edges} edges; got {mn} / {me}")
+        self._check_hyper()
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             for k in self.shapes:
                 getattr(self.static, k).copy_(getattr(batch, k), non_blocking=True)
             self.graph_a.replay()
-            self._exchange()
-            self.graph_b.replay()
+            if self.graph_b is not None:
+                self._exchange()
+                self.graph_b.replay()
         torch.cuda.current_stream().wait_stream(self.stream)
         return self.loss

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 from torch.nn import Dropout, LeakyReLU, Linear
 
-from .. import ops
+from .. import _lib, ops
 from ..nn import BatchNorm, GATConv
 
 
@@ -30,6 +30,8 @@ class LightpathGNN(torch.nn.Module):
     def launches_per_step(self):
         from .. import _lib
         return self._variant_launches[_lib.lib().qot_lightpath_get_variant()]
+
+    batches_per_launch = 1                 # qot_lightpath_infer: one launch per batch
 
     @property
     def dominant_kernel(self):
@@ -71,6 +73,7 @@ class LightpathGNN(torch.nn.Module):
             self._prepared_key = key
         return self._prepared
 
+    @_lib.on_tensor_device
     def forward_device(self, data, out=None) -> ops.LightpathInferOut:
         """Eval forward without any host synchronisation: ONE kernel launch when the batch carries
         ``ptr`` / ``edge_ptr`` / ``lut_ptr`` (every collate of this package provides them); returns
@@ -125,6 +128,7 @@ class LightpathGNN(torch.nn.Module):
             self.training, self.mlp[2].p if self.training else 0.0)
         return out, lut_batch
 
+    @_lib.on_tensor_device
     def forward(self, data):
         if not data.x.is_cuda:
             raise RuntimeError("LightpathGNN (B200) needs the batch on a CUDA device; there is no CPU path")

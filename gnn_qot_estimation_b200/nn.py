@@ -13,7 +13,7 @@ import math
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 
 
 class TransformerConv(nn.Module):
@@ -36,6 +36,7 @@ class TransformerConv(nn.Module):
         self.lin_edge = nn.Linear(edge_dim, out_channels, bias=False)
         self.lin_skip = nn.Linear(in_channels, out_channels)
 
+    @_lib.on_tensor_device
     def forward(self, x, edge_index, edge_attr=None, *, graph=None, node_ids=None, slope: float = 1.0):
         """``graph`` (ops.GraphIndex) lets callers share one CSR between layers;
         ``node_ids`` fuses the embedding lookup (x is then the embedding table);
@@ -72,6 +73,7 @@ class NNConv(nn.Module):
         bound = 1.0 / math.sqrt(in_channels)            # PyG Linear(weight_initializer='uniform')
         torch.nn.init.uniform_(self.lin.weight, -bound, bound)
 
+    @_lib.on_tensor_device
     def forward(self, x, edge_index, edge_attr=None, *, graph=None, slope: float = 1.0):
         if graph is None:
             graph = ops.GraphIndex(edge_index, x.shape[0])
@@ -99,6 +101,7 @@ class GATConv(nn.Module):
         nn.init.xavier_uniform_(self.att_src)
         nn.init.xavier_uniform_(self.att_dst)
 
+    @_lib.on_tensor_device
     def forward(self, x, edge_index, *, graph=None):
         if (self.in_channels, self.out_channels, self.heads) != (5, 32, 4):
             raise NotImplementedError("libqot_b200 GATConv kernels: in=5, out=32, heads=4 only")
@@ -117,10 +120,12 @@ class BatchNorm(nn.Module):
             raise NotImplementedError("libqot_b200 BatchNorm: affine=True, track_running_stats=True only")
         self.module = nn.BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
 
+    @_lib.on_tensor_device
     def forward(self, x):
         return ops.batch_norm(x, self.module, self.training)
 
 
+@_lib.on_tensor_device
 def global_mean_pool(x, batch, size=None):
     """Per-graph mean of node rows."""
     B = int(size) if size is not None else (int(batch.max().item()) + 1 if batch.numel() else 0)

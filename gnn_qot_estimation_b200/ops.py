@@ -42,6 +42,48 @@ def _i64(t):
 
 
 # --------------------------------------------------------------------------- #
+# device status words
+# --------------------------------------------------------------------------- #
+# Kernels never synchronise; when an input violates a contract the reference would raise on (an edge
+# endpoint or node id out of range, edges not grouped by graph, a graph larger than the sizes a fused
+# launch was made for, a tensor-core barrier timeout) they set a bit in a one-word device buffer, write
+# NaN (never stale memory) where a result is missing, and carry on.  check_status() is the explicit sync
+# point: ONE device->host read of every word produced since the last call; raises naming the ops.
+_status_words = {}          # data_ptr -> (what, tensor): a long-lived word (e.g. one per device) is tracked once
+_STATUS_CAP = 4096
+
+
+def _track_status(what: str, t: torch.Tensor) -> torch.Tensor:
+    if len(_status_words) >= _STATUS_CAP:
+        for k in list(_status_words)[:_STATUS_CAP // 2]:
+            del _status_words[k]
+    _status_words[t.data_ptr()] = (what, t)
+    return t
+
+
+def check_status(clear: bool = True) -> None:
+    """Raises RuntimeError if any kernel launched through this module since the last call flagged its
+    input (see above).  Costs one small device->host copy (a synchronisation): call it where the loop
+    already reads the loss, or once per epoch."""
+    if not _status_words:
+        return
+    words = list(_status_words.values())
+    if clear:
+        _status_words.clear()
+    by_dev = {}
+    for what, t in words:
+        by_dev.setdefault(t.device, []).append((what, t))
+    bad = []
+    for dev, items in by_dev.items():
+        vals = torch.cat([t.reshape(1) for _, t in items]).tolist()
+        bad += [f"{what} (status {v})" for (what, _), v in zip(items, vals) if v]
+    if bad:
+        raise RuntimeError("libqot_b200: input contract violated in: " + "; ".join(sorted(set(bad))[:8]) +
+                           " -- out-of-range node ids / edge endpoints, edges not grouped by graph, or a graph "
+                           "larger than the captured launch was sized for")
+
+
+# --------------------------------------------------------------------------- #
 # integer side
 # --------------------------------------------------------------------------- #
 class CSR(NamedTuple):
@@ -68,7 +110,7 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, by: int = 1, flags: int 
     ws = _lib.workspace(nb, dev)
     check(L.qot_build_csr(ptr(edge_index), E, N, by, flags, ptr(rowptr), ptr(nbr), ptr(eid), ptr(status),
                           ptr(ws), ws.numel(), stream()), "qot_build_csr")
-    return CSR(rowptr, nbr, eid, status)
+    return CSR(rowptr, nbr, eid, _track_status("qot_build_csr (edge_index entry outside [0, num_nodes))", status))
 
 
 def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
@@ -88,7 +130,7 @@ def edge_ptr(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: int):
     status = torch.empty(1, dtype=torch.int32, device=batch.device)
     check(_lib.lib().qot_edge_ptr(ptr(edge_index), edge_index.shape[1], ptr(batch), batch.numel(),
                                   num_graphs, ptr(out), ptr(status), stream()), "qot_edge_ptr")
-    return out, status
+    return out, status          # read by the caller (LightpathGNN._forward_eval): chooses the general path
 
 
 def batch_num_graphs(data) -> int:
@@ -487,6 +529,7 @@ def gemm_tf32x3(A, W, bias=None, gather=None):
     st = _tc_status.get(dev)
     if st is None:
         st = _tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    _track_status("qot_gemm_tf32x3 (tcgen05 barrier timeout)", st)
     C_ = torch.empty(M, Nc, dtype=torch.float32, device=dev)
     ws = _lib.workspace(L.qot_gemm_tf32x3_workspace_bytes(M, Nc, K), dev)
     check(L.qot_gemm_tf32x3(ptr(A), K, ptr(gather), ptr(W), K, ptr(bias), ptr(C_), Nc, M, Nc, K, ptr(st),
@@ -503,6 +546,7 @@ def wgrad_tf32x3(dy, x, gather=None):
     st = _tc_status.get(dev)
     if st is None:
         st = _tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    _track_status("qot_wgrad_tf32x3 (tcgen05 barrier timeout)", st)
     dW = torch.empty(Nc, K, dtype=torch.float32, device=dev)
     ws = _lib.workspace(L.qot_wgrad_tf32x3_workspace_bytes(R, Nc, K), dev)
     check(L.qot_wgrad_tf32x3(ptr(dy), Nc, ptr(x), K, ptr(gather), R, Nc, K, ptr(dW), K, ptr(st),
@@ -727,7 +771,8 @@ class _TopoFusedFn(torch.autograd.Function):
         flat_, emb_ = _f32(flat.detach()), _f32(emb.detach())
         node_ids, edge_index, edge_attr = _i64(node_ids), _i64(edge_index), _edge_attr(edge_attr)
         out = torch.empty(B, 3, dtype=torch.float32, device=dev)
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = _track_status("qot_topo_fused (graph over the launch's node/edge caps, or ids out of range)",
+                               torch.zeros(1, dtype=torch.int32, device=dev))
         prep = torch.empty(L.qot_topo_fused_prepared_floats(), dtype=torch.float32, device=dev)
         check(L.qot_topo_fused_prepare(ptr(flat_), ptr(prep), stream()), "qot_topo_fused_prepare")
         N, E = int(node_ids.shape[0]), int(edge_index.shape[1])

@@ -60,6 +60,10 @@ class _Slot:
 
 
 class LightpathInferencePipeline:
+    wire_note = ("copied in ONE transfer per step (the host batch keeps them contiguous): destination row of "
+                 "edge_index, ptr/edge_ptr/lut_ptr, x; the source row stays in pinned host memory and the kernel "
+                 "reads ~4 sectors (32 B) per LUT row from it over PCIe (estimated, included in h2d_bytes_per_step)")
+
     def __init__(self, model, max_nodes: int, max_edges: int, max_graphs: int, depth: int = 3):
         p = next(model.parameters())
         if not p.is_cuda:

@@ -48,6 +48,7 @@ def _cfg(lp_feat: Sequence[str], metric: Sequence[str], F: int, L: int, Q: int, 
     return cfg
 
 
+@_lib.on_tensor_device
 def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: torch.Tensor, lp_feat: Sequence[str],
                             metric: Sequence[str], freq_threshold: float = 0.05,
                             return_conn_ids: bool = False):
@@ -90,6 +91,7 @@ def create_lightpath_graphs(data: torch.Tensor, target: torch.Tensor, freqs: tor
     return (store, conn_ids) if return_conn_ids else store
 
 
+@_lib.on_tensor_device
 def create_topological_graphs(data: torch.Tensor, target: torch.Tensor, lp_feat: Sequence[str], metric: Sequence[str],
                               num_nodes: int = 75) -> PackedGraphStore:
     """The topological representation for all samples at once: ``to_graph.create_topological_graph``

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch.nn import Dropout, LeakyReLU, Linear, ReLU
 from torch.nn import Sequential as Seq
 
-from .. import ops
+from .. import _lib, ops
 from ..nn import NNConv, TransformerConv
 
 LEAKY = 0.01   # F.leaky_relu default slope (models.py:54,58)
@@ -71,6 +71,7 @@ class TopologicalGNN(torch.nn.Module):
         return ops.topological_fused(params, self.node_embeddings.weight, node_ids, edge_index, edge_attr, gptr, eptr,
                                      nmax, emax)
 
+    @_lib.on_tensor_device
     def forward(self, data):
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if not edge_index.is_cuda:

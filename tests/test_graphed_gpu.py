@@ -21,11 +21,10 @@ def test_graphed_step_equals_eager(cuda):
     o2 = torch.optim.SGD(m2.parameters(), lr=0.1, momentum=0.9)
     store = synthetic.nsfnet_store(64 * 6, seed=3).to(cuda)
     batches = [store.collate(range(i * 64, (i + 1) * 64)) for i in range(6)]
-    sd0 = copy.deepcopy(m2.state_dict())
     g = GraphedTrainStep(m2, o2, crit, batches[0], warmup=2)
-    m2.load_state_dict(sd0)                               # the warm-up steps moved the weights: rewind
-    for st in o2.state.values():
-        st["momentum_buffer"].zero_()
+    # constructing the step must not move the model or the optimizer state (snapshot / restore inside)
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1, p2), k
     for b in batches:
         o1.zero_grad()
         l1 = crit(m1(b), b.y.view(-1, 3))
@@ -37,6 +36,37 @@ def test_graphed_step_equals_eager(cuda):
         assert torch.equal(p1, p2), k
     with pytest.raises(RuntimeError, match="static shapes"):
         g.step(store.collate(range(0, 32)))
+
+
+def test_graphed_step_follows_lr_schedule(cuda):
+    """StepLR changes param_groups['lr'] between steps (topological_training/train.py:67,152): the captured
+    update must follow it, and a resumed optimizer (existing momentum) must keep its state."""
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    from gnn_qot_estimation_b200.graphed import GraphedTrainStep
+    torch.manual_seed(1)
+    m1 = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(cuda)
+    crit = torch.nn.SmoothL1Loss()
+    o1 = torch.optim.SGD(m1.parameters(), lr=0.1, momentum=0.9)
+    store = synthetic.nsfnet_store(32 * 6, seed=4).to(cuda)
+    batches = [store.collate(range(i * 32, (i + 1) * 32)) for i in range(6)]
+    # one eager step first: the graphed optimizer starts from existing momentum buffers
+    o1.zero_grad(); crit(m1(batches[0]), batches[0].y.view(-1, 3)).backward(); o1.step()
+    m2 = copy.deepcopy(m1)
+    o2 = torch.optim.SGD(m2.parameters(), lr=0.1, momentum=0.9)
+    o2.load_state_dict(copy.deepcopy(o1.state_dict()))
+    s1 = torch.optim.lr_scheduler.StepLR(o1, step_size=2, gamma=0.5)
+    s2 = torch.optim.lr_scheduler.StepLR(o2, step_size=2, gamma=0.5)
+    g = GraphedTrainStep(m2, o2, crit, batches[0], warmup=2)
+    for b in batches:
+        o1.zero_grad()
+        l1 = crit(m1(b), b.y.view(-1, 3))
+        l1.backward()
+        o1.step(); s1.step()
+        l2 = g.step(b); s2.step()
+        assert torch.equal(l1.detach(), l2), (float(l1), float(l2))
+    assert o1.param_groups[0]["lr"] == o2.param_groups[0]["lr"] == 0.1 * 0.5 ** 3
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1, p2), k
 
 
 @pytest.mark.parametrize("sizes", [[3000], [700, 1, 1300, 40], [260] * 7])
