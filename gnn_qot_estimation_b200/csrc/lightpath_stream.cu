@@ -1,0 +1,670 @@
+// LightpathGNN eval-mode forward as ONE persistent, warp-specialised, multi-stage kernel over MANY
+// batches (lightpath_training/models.py:26-45 under model.eval(), as driven by
+// lightpath_training/test.py:77-94; PyG semantics per SURVEY.md Appendix A.3 / A.5):
+//
+//   work item = a TILE of 16 consecutive graphs of one batch; a launch covers every tile of an array
+//   of batch descriptors (reference layout: fp32 x, int64 edge_index, ptr / edge_ptr / lut_ptr);
+//   one CTA per SM loops over tiles  bid, bid + grid, bid + 2*grid, ...
+//
+//   warp 0            PRODUCER.  Its 32 lanes look 32 tiles ahead (tile extents = 4 index loads each, all in
+//                     flight at once), then per tile: wait for a free stage, 51 x 8-byte cp.async for the
+//                     tile's ptr / edge_ptr / lut_ptr rows, and ONE elected lane issues two cp.async.bulk
+//                     copies -- the x window (20 B/node) and the window of the DESTINATION row of
+//                     edge_index (8 B/edge) -- completing on the stage's `full` mbarrier.
+//   warps 1..12       three CONSUMER groups of four warps.  Group q takes the CTA's tiles k = q (mod 3):
+//                     8 lanes per graph -- LUT flag scan, destination scan (contiguous runs, one compare
+//                     per slot), the few sources of the LUT row fetched from the source row in global
+//                     memory, 4-head attention softmax over 5-float messages (z = sum_j alpha_ij x_j),
+//                     then the z row (20 floats) goes to the readout head.  The stage is released on its
+//                     `empty` mbarrier as soon as the slabs are dead.
+//   (head)            see lp_head_kernel below / the tcgen05 head warps.
+//
+// Nothing is re-read: the parameter block, the attention vectors and the barrier setup are loaded once
+// per CTA, tile extents once per 32 tiles, and every compulsory byte of a graph is requested by one
+// asynchronous copy several tiles before it is needed, so the three dependent DRAM round trips of the
+// one-launch-per-batch kernel (extents -> slabs -> sources) overlap across tiles instead of
+// serialising inside a CTA.  Deterministic: edges of a row are consumed in edge order, fixed trees.
+#include <algorithm>
+
+#include "lightpath_common.cuh"
+
+namespace qot {
+
+constexpr int kTG = 16;                    // graphs per tile
+constexpr int kTNodes = 704;               // x window: mean 512 nodes + 3.4 sigma (sigma = 4 * 14.1)
+constexpr int kTEdges = 2688;              // destination window: mean 1984 edges + 3.1 sigma
+constexpr int kTMaxE = 248;                // per graph: 8 lanes x 31 contiguous edges (bit mask per lane)
+constexpr int kStStages = 4;
+constexpr int kStGroups = 3;               // consumer groups
+constexpr int kStGroupWarps = 4;           // 4 warps x 4 graphs = one tile
+constexpr int kStConsumerWarps = kStGroups * kStGroupWarps;
+constexpr int kStThreads = 32 * (1 + kStConsumerWarps);
+constexpr int kStXBytes = kTNodes * kF * 4;
+constexpr int kStDBytes = kTEdges * 8;
+constexpr unsigned kStSpin = 1u << 28;     // a wedged barrier ends the kernel (status bit 4), never hangs it
+
+struct alignas(16) StTileInfo {
+  const float* x;                          // batch tensors (generic path + source gather)
+  const int64_t* esrc;
+  const int64_t* edst;
+  float* z;
+  float* out;
+  int64_t* lut_batch;
+  int32_t* lut_node;
+  int32_t* n_lut;
+  int32_t* status;
+  int64_t N, E, B;
+  int64_t g0;                              // first graph of the tile (index inside its batch)
+  int64_t nb0, eb0;                        // first node / edge staged
+  int xn, en;                              // nodes / edges staged (0: window unusable, graphs take the generic path)
+  unsigned xlead, dlead;                   // bytes between the 16-byte aligned copy start and the first element
+  int ng;                                  // graphs in the tile
+  int pad;
+};
+
+struct alignas(128) StStage {
+  alignas(128) unsigned char xs[kStXBytes + 16];
+  alignas(16) unsigned char ds[kStDBytes + 16];
+  alignas(16) long long ptrs[3][kTG + 2];  // ptr / edge_ptr / lut_ptr rows of the tile (kTG + 1 entries each)
+  StTileInfo info;
+};
+
+struct StGroupScratch {
+  int msg[kTG][kSubMsg];
+  float gen[kStGroupWarps][128];           // generic path: z (32 floats) + message list (64 ints) per warp
+};
+
+struct StSmem {
+  StStage stage[kStStages];
+  StGroupScratch grp[kStGroups];
+  alignas(8) unsigned long long full[kStStages];
+  alignas(8) unsigned long long empty[kStStages];
+};
+static_assert(sizeof(StSmem) + 1024 <= 227 * 1024, "lp_stream_kernel: shared memory over the 227 KB block limit");
+
+__device__ __forceinline__ unsigned st_smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ bool st_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ bool st_wait(unsigned bar, unsigned parity) {
+  for (unsigned spin = 0; spin < kStSpin; ++spin)
+    if (st_try_wait(bar, parity)) return true;
+  return false;
+}
+__device__ __forceinline__ void st_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// descriptor of the batch tile T of the launch belongs to (uniform tile count per batch, or prefix search)
+__device__ __forceinline__ int st_batch_of(const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb, int64_t T) {
+  if (tpb > 0) return static_cast<int>(min(T / tpb, static_cast<int64_t>(nb - 1)));
+  int lo = 0, hi = nb - 1;                 // last b with tile0[b] <= T
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bt[mid].tile0 <= T) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// producer: one warp
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb,
+                                            int64_t total_tiles, int lane) {
+  const int64_t G = gridDim.x;
+  const int64_t my_tiles = (total_tiles - blockIdx.x + G - 1) / G;
+  for (int64_t kb = 0; kb < my_tiles; kb += 32) {
+    // ---- look-ahead: lane j owns tile kb + j of this CTA
+    int b = 0;
+    long long g0 = 0, nb0 = 0, nb1 = 0, eb0 = 0, eb1 = 0;
+    if (kb + lane < my_tiles) {
+      const int64_t T = blockIdx.x + (kb + lane) * G;
+      b = st_batch_of(bt, nb, tpb, T);
+      const qot_lp_batch_t& d = bt[b];
+      g0 = (T - d.tile0) * kTG;
+      const int64_t gE = min(g0 + kTG, d.B);
+      nb0 = d.ptr[g0]; nb1 = d.ptr[gE];
+      eb0 = d.edge_ptr[g0]; eb1 = d.edge_ptr[gE];
+    }
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(32), my_tiles - kb));
+    for (int j = 0; j < cnt; ++j) {
+      const int64_t k = kb + j;
+      const int s = static_cast<int>(k % kStStages);
+      const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
+      StStage& st = sm.stage[s];
+      const unsigned fbar = st_smem_u32(&sm.full[s]);
+      st_wait(st_smem_u32(&sm.empty[s]), ph ^ 1u);       // consumers released the stage's previous tile
+      const int tb = __shfl_sync(kFull, b, j);
+      const long long tg0 = __shfl_sync(kFull, g0, j);
+      const long long tn0 = __shfl_sync(kFull, nb0, j), tn1 = __shfl_sync(kFull, nb1, j);
+      const long long te0 = __shfl_sync(kFull, eb0, j), te1 = __shfl_sync(kFull, eb1, j);
+      const qot_lp_batch_t d = bt[tb];                   // every lane: the same 128 bytes (broadcast, L1)
+      // ---- the tile's index rows: 3 x (kTG + 1) entries, 8-byte asynchronous copies
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int idx = lane + 32 * r;
+        if (idx < 3 * (kTG + 1)) {
+          const int which = idx / (kTG + 1), i = idx % (kTG + 1);
+          const int64_t gi = min(static_cast<int64_t>(tg0 + i), d.B);
+          const int64_t* src = (which == 0 ? d.ptr : which == 1 ? d.edge_ptr : d.lut_ptr) + gi;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st_smem_u32(&st.ptrs[which][i])), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fbar) : "memory");
+      if (lane == 0) {
+        // ---- windows: nodes [nb0, nb0 + xn), edges [eb0, eb0 + en), copied from 16-byte aligned addresses;
+        // a window that does not fit (or nonsense offsets) is not staged: its graphs take the generic path
+        int xn = 0, en = 0;
+        if (tn0 >= 0 && tn1 >= tn0 && tn1 <= d.N && tn1 - tn0 <= kTNodes) xn = static_cast<int>(tn1 - tn0);
+        if (te0 >= 0 && te1 >= te0 && te1 <= d.E && te1 - te0 <= kTEdges) en = static_cast<int>(te1 - te0);
+        if (xn == 0 || (en == 0 && te1 != te0)) { xn = 0; en = 0; }
+        const int64_t* edst = d.edge_index + d.E;
+        const uintptr_t xa = reinterpret_cast<uintptr_t>(d.x) + static_cast<uintptr_t>(xn > 0 ? tn0 : 0) * (kF * 4);
+        const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? te0 : 0) * 8;
+        const unsigned xlead = static_cast<unsigned>(xa & 15), dlead = static_cast<unsigned>(da & 15);
+        const uintptr_t xs0 = xa - xlead, ds0 = da - dlead;
+        const unsigned xspan = xlead + static_cast<unsigned>(xn) * (kF * 4), dspan = dlead + static_cast<unsigned>(en) * 8;
+        unsigned xbytes = (xspan + 15u) & ~15u, dbytes = (dspan + 15u) & ~15u;
+        // never read past the end of a tensor: the few bytes a rounded-up window would add are copied by hand
+        if (xs0 + xbytes > reinterpret_cast<uintptr_t>(d.x) + static_cast<uintptr_t>(d.N) * (kF * 4)) xbytes = xspan & ~15u;
+        if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(d.E) * 8) dbytes = dspan & ~15u;
+        if (xn == 0) xbytes = 0;
+        if (en == 0) dbytes = 0;
+        if (xn > 0)
+          for (unsigned o = xbytes; o < xspan; o += 4)
+            *reinterpret_cast<float*>(st.xs + o) = *reinterpret_cast<const float*>(xs0 + o);
+        if (en > 0 && dspan > dbytes)
+          *reinterpret_cast<long long*>(st.ds + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
+        StTileInfo& ti = st.info;
+        ti.x = d.x; ti.esrc = d.edge_index; ti.edst = edst; ti.z = d.z; ti.out = d.out;
+        ti.lut_batch = d.lut_batch; ti.lut_node = d.lut_node; ti.n_lut = d.n_lut; ti.status = d.status;
+        ti.N = d.N; ti.E = d.E; ti.B = d.B; ti.g0 = tg0; ti.nb0 = tn0; ti.eb0 = te0;
+        ti.xn = xn; ti.en = en; ti.xlead = xlead; ti.dlead = dlead;
+        ti.ng = static_cast<int>(min(static_cast<int64_t>(kTG), d.B - tg0));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fbar), "r"(xbytes + dbytes) : "memory");
+        if (xbytes)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(st_smem_u32(st.xs)), "l"(xs0), "r"(xbytes), "r"(fbar) : "memory");
+        if (dbytes)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(st_smem_u32(st.ds)), "l"(ds0), "r"(dbytes), "r"(fbar) : "memory");
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumer: one tile (16 graphs) per group of 4 warps; 8 lanes per graph
+// ------------------------------------------------------------------------------------------------
+struct StLaneConst {
+  float AsP[6][kHeads];                    // attention source vectors in this lane's slot order
+  float AdP[kF][kHeads];                   // attention destination vectors, head slots of this lane
+};
+
+// z row (kZRow floats) of graph `g` -> the readout head (this build: the caller's z workspace, row l0)
+template <bool kHeadInKernel>
+__device__ __forceinline__ void st_emit_z(const StTileInfo& ti, int64_t l0, int hx, int o0, bool odd, const float (&acc3)[3],
+                                          float inv) {
+  float* zr = ti.z + l0 * (kHeads * kF) + hx * kF + o0;
+  zr[0] = acc3[0] * inv;
+  zr[1] = acc3[1] * inv;
+  if (!odd) zr[2] = acc3[2] * inv;
+}
+
+template <bool kHeadInKernel>
+__device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs, const StLaneConst& lc,
+                                                const float* __restrict__ prep, int lut_col, int gw, int lane,
+                                                unsigned ebar) {
+  const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
+  const int gl = gw * 4 + sg;                          // graph slot inside the tile
+  const StTileInfo& ti = st.info;
+  const bool active = gl < ti.ng;
+  const int64_t g = ti.g0 + gl;
+  const int64_t N = ti.N;
+  const int64_t n0 = st.ptrs[0][gl], n1 = st.ptrs[0][gl + 1];
+  const int64_t e0 = st.ptrs[1][gl], e1 = st.ptrs[1][gl + 1];
+  const int64_t l0 = st.ptrs[2][gl], l1 = st.ptrs[2][gl + 1];
+  const int64_t nb0 = ti.nb0, eb0 = ti.eb0;
+  const int xn = ti.xn, en = ti.en;
+  const bool fits = active && xn > 0 && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kTMaxE &&
+                    n0 >= nb0 && (n1 - nb0) <= xn && e0 >= eb0 && (e1 - eb0) <= en;
+  const int n = fits ? static_cast<int>(n1 - n0) : 0;
+  const int ne = fits ? static_cast<int>(e1 - e0) : 0;
+  if (active && g == ti.B - 1 && sl == 0) ti.n_lut[0] = static_cast<int32_t>(l1);
+  const float* sx = reinterpret_cast<const float*>(st.xs + ti.xlead) + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
+  const long long* sd = reinterpret_cast<const long long*>(st.ds + ti.dlead) + (fits ? static_cast<int>(e0 - eb0) : 0);
+  const int hx = sl >> 1;
+  const bool odd = (sl & 1) != 0;
+
+  // ---- LUT node(s) of the graph: a per-lane bit per node, then one count and one minimum over the 8 lanes
+  int cnt = 0, il = -1;
+  {
+    unsigned m = 0u;
+#pragma unroll
+    for (int r = 0; r < kMaxN / 8; ++r) {
+      const int node = sl + 8 * r;
+      if (node < n && sx[node * kF + lut_col] == 1.0f) m |= 1u << r;
+    }
+    cnt = __popc(m);
+    int first = m ? 8 * (__ffs(m) - 1) + sl : 0x7fff;
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      cnt += __shfl_xor_sync(kFull, cnt, o);
+      first = min(first, __shfl_xor_sync(kFull, first, o));
+    }
+    if (cnt) il = first;
+  }
+  bool ok = fits && cnt == 1 && (l1 - l0) == 1;        // fast row: exactly one LUT node, as lut_ptr says
+  if (fits && sl == 0 && cnt != l1 - l0) atomicOr(ti.status, 1);   // lut_ptr does not describe this x
+
+  // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph (c odd: the 8-byte reads of
+  // the 8 lanes fall into distinct banks); one predicate per slot
+  int* msg = gs.msg[gl];
+  int mc = 0;
+  {
+    const int c = ((ne + 7) >> 3) | 1;
+    const int eb = sl * c;
+    const int tmax = ok ? min(c, ne - eb) : 0;
+    const int cmax = __reduce_max_sync(kFull, tmax);
+    const long long target = n0 + il;
+    const int tlo = static_cast<int>(target), thi = static_cast<int>(target >> 32);
+    // unconditional 8-byte reads: slots past the lane's run stay inside the stage (the window is followed by the
+    // index rows and the tile record) and are masked by t < tmax
+    const int2* sde = reinterpret_cast<const int2*>(sd + eb);
+    unsigned hm = 0u;
+#pragma unroll
+    for (int t4 = 0; t4 < 32; t4 += 4) {
+      if (t4 < cmax) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = t4 + i;
+          if (t < 31) {
+            const int2 d = sde[t];
+            asm("{ .reg .pred p;\n\t"
+                "setp.eq.s32 p, %1, %3;\n\t"
+                "setp.eq.and.s32 p, %2, %4, p;\n\t"
+                "@p or.b32 %0, %0, %5; }"
+                : "+r"(hm) : "r"(d.x), "r"(d.y), "r"(tlo), "r"(thi), "r"(1u << t));
+          }
+        }
+      }
+    }
+    hm &= (1u << max(tmax, 0)) - 1u;                   // tmax <= 31
+    const int h = __popc(hm);
+    int incl = h;
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      const int up = __shfl_up_sync(kFull, incl, o, 8);
+      if (sl >= o) incl += up;
+    }
+    mc = __shfl_sync(kFull, incl, base + 7);
+    int pos = incl - h;
+    while (hm) {
+      const int t = __ffs(hm) - 1;
+      hm &= hm - 1u;
+      if (pos < kSubMsg - 1) msg[pos] = eb + t;
+      ++pos;
+    }
+  }
+  if (mc > kSubMsg - 1) ok = false;                    // hub row: generic path
+  __syncwarp();
+  // ---- sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
+  {
+    int kept = 0;
+    bool outside = false;
+    const int64_t* __restrict__ esrc = ti.esrc;
+#pragma unroll
+    for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
+      if (__any_sync(kFull, ok && t0 < mc)) {
+        const int t = t0 + sl;
+        long long sj = -1;
+        if (ok && t < mc) sj = esrc[e0 + msg[t]];
+        const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
+        const long long sloc = sj - n0;
+        const bool inslab = sloc >= 0 && sloc < n;
+        const bool keep = inslab && sloc != il;
+        outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
+        const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
+        __syncwarp();
+        if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
+        kept += __popc(sub);
+        __syncwarp();
+      }
+    }
+    if (outside) ok = false;                           // a source outside the graph's node range: generic path
+    mc = kept;
+  }
+  if (ok && sl == 0) msg[mc] = il;                     // the appended self loop comes last
+  ++mc;
+  __syncwarp();
+
+  // ---- attention: lane = message slot, all 4 heads per lane.  The 24 sums per graph (4 heads x (x0..x4, 1)) are
+  // reduce-scattered: three exchange steps, each lane sends the half it does not keep -- statically the upper
+  // half of its registers thanks to the slot permutation (tables built once by lp_prepare_kernel)
+  {
+    float d[kHeads];
+    const int ils = ok ? il : 0;
+#pragma unroll
+    for (int i = 0; i < kHeads; ++i) d[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+      const float xi = sx[ils * kF + k];
+#pragma unroll
+      for (int i = 0; i < kHeads; ++i) d[i] = fmaf(xi, lc.AdP[k][i], d[i]);
+    }
+    float mx[kHeads], acc3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < kHeads; ++i) mx[i] = -INFINITY;
+    const int o0 = odd ? 3 : 0;
+#pragma unroll
+    for (int r0 = 0; r0 < kSubMsg; r0 += 8) {
+      if (__any_sync(kFull, ok && r0 < mc)) {
+        const bool valid = ok && r0 + sl < mc;
+        const float* xr = sx + (valid ? msg[r0 + sl] : 0) * kF;
+        float q[6];
+        const float x2 = xr[2];
+        q[0] = xr[o0]; q[1] = xr[o0 + 1]; q[3] = xr[3 - o0]; q[4] = xr[4 - o0];
+        q[2] = odd ? 1.0f : x2;
+        q[5] = odd ? x2 : 1.0f;
+        float a[kHeads], mr[kHeads], m2[kHeads];
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) {
+          float t = d[i];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) t = fmaf(q[m], lc.AsP[m][i], t);    // the ONE slot carries weight 0
+          t = t > 0.f ? t : 0.2f * t;
+          a[i] = valid ? t : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(a[i], __shfl_xor_sync(kFull, a[i], 1));
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) m2[i] = fmaxf(mr[i], __shfl_xor_sync(kFull, mr[i ^ 1], 2));
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(m2[i], __shfl_xor_sync(kFull, m2[i ^ 2], 4));
+        float v[24];
+        float scarg = 0.f;
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) {
+          const float mn = fmaxf(fmaxf(mx[i], mr[i]), -1e30f);   // idle sub-groups stay finite
+          const float p = valid ? expf(a[i] - mn) : 0.f;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) v[i * 6 + m] = p * q[m];
+          if (i == 0) scarg = mx[0] - mn;                     // -inf in the first round: exp -> 0
+          mx[i] = mn;
+        }
+        float u[12], s6[6], w3[3];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) u[t] = v[t] + __shfl_xor_sync(kFull, v[t + 12], 4);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) s6[t] = u[t] + __shfl_xor_sync(kFull, u[t + 6], 2);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) w3[t] = s6[t] + __shfl_xor_sync(kFull, s6[t + 3], 1);
+        const float sc = expf(scarg);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) acc3[t] = fmaf(acc3[t], sc, w3[t]);
+      }
+    }
+    // even lane: sums x0..x2 of head sl>>1; odd lane: x3, x4 and the softmax denominator
+    const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
+    const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
+    if (ok) {
+      st_emit_z<kHeadInKernel>(ti, l0, hx, o0, odd, acc3, inv);
+      if (sl == 0) {
+        ti.lut_batch[l0] = g;
+        ti.lut_node[l0] = static_cast<int32_t>(n0 + il);
+      }
+    }
+  }
+  const int my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
+  // pointers the generic path needs, read before the stage is handed back
+  const float* gx = ti.x;
+  const int64_t* gesrc = ti.esrc;
+  const int64_t* gedst = ti.edst;
+  float* gz = ti.z;
+  int64_t* glb = ti.lut_batch;
+  int32_t* gln = ti.lut_node;
+  int32_t* gstatus = ti.status;
+  const int64_t tg0 = ti.g0;
+  const bool any_generic = __any_sync(kFull, my_state == 2);
+  __syncwarp();
+  if (lane == 0) st_arrive(ebar);                      // the slabs are dead: the producer may refill the stage
+
+  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
+  if (any_generic) {
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      if (__shfl_sync(kFull, my_state, 8 * s) != 2) continue;
+      const int64_t gn0 = __shfl_sync(kFull, n0, 8 * s), gn1 = __shfl_sync(kFull, n1, 8 * s);
+      const int64_t ge0 = __shfl_sync(kFull, e0, 8 * s), ge1 = __shfl_sync(kFull, e1, 8 * s);
+      const int64_t gl0 = __shfl_sync(kFull, l0, 8 * s), gl1 = __shfl_sync(kFull, l1, 8 * s);
+      float* s_z = gs.gen[gw];
+      int* s_m = reinterpret_cast<int*>(gs.gen[gw] + 32);
+      int64_t orow = gl0;
+      int found = 0;
+      if (gn0 >= 0 && gn1 <= N && ge0 >= 0 && ge1 <= ti.E) {
+        for (int64_t nbq = gn0; nbq < gn1; nbq += 32) {
+          const int64_t node = nbq + lane;
+          unsigned mask = __ballot_sync(kFull, node < gn1 && gx[node * kF + lut_col] == 1.0f);
+          while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            ++found;
+            if (orow < gl1) {                                      // never write past this graph's rows
+              const int64_t i = nbq + bit;
+              lut_row_global<false>(gx, gesrc, gedst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
+              if (lane < kHeads * kF) gz[orow * (kHeads * kF) + lane] = s_z[(lane / kF) * 8 + lane % kF];
+              if (lane == 0) {
+                glb[orow] = tg0 + gw * 4 + s;
+                gln[orow] = static_cast<int32_t>(i);
+              }
+              __syncwarp();
+              ++orow;
+            }
+          }
+        }
+      }
+      if (lane == 0 && found != gl1 - gl0) atomicOr(gstatus, 1);
+    }
+  }
+}
+
+template <bool kHeadInKernel>
+__global__ void __launch_bounds__(kStThreads, 1)
+lp_stream_kernel(const qot_lp_batch_t* __restrict__ batches, int n_batches, int64_t tiles_per_batch,
+                 int64_t total_tiles, const float* __restrict__ prep, int lut_col) {
+  extern __shared__ __align__(128) char st_smem_raw[];
+  StSmem& sm = *reinterpret_cast<StSmem*>((reinterpret_cast<uintptr_t>(st_smem_raw) + 127) & ~uintptr_t(127));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kStStages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.full[s])), "r"(33) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.empty[s])), "r"(kStGroupWarps) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    st_producer(sm, batches, n_batches, tiles_per_batch, total_tiles, lane);
+    return;
+  }
+  // ---- consumers
+  const int cw = warp - 1, q = cw / kStGroupWarps, gw = cw % kStGroupWarps;
+  const int sl = lane & 7;
+  StLaneConst lc;
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + sl * 6 + m);
+    lc.AsP[m][0] = a.x; lc.AsP[m][1] = a.y; lc.AsP[m][2] = a.z; lc.AsP[m][3] = a.w;
+  }
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + (sl >> 1) * kF + k);
+    lc.AdP[k][0] = b.x; lc.AdP[k][1] = b.y; lc.AdP[k][2] = b.z; lc.AdP[k][3] = b.w;
+  }
+  const int64_t G = gridDim.x;
+  const int64_t my_tiles = (total_tiles - blockIdx.x + G - 1) / G;
+  for (int64_t k = q; k < my_tiles; k += kStGroups) {
+    const int s = static_cast<int>(k % kStStages);
+    const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
+    if (!st_wait(st_smem_u32(&sm.full[s]), ph)) {
+      if (lane == 0) atomicOr(batches[0].status, 4);
+      return;
+    }
+    st_consume_tile<kHeadInKernel>(sm.stage[s], sm.grp[q], lc, prep, lut_col, gw, lane, st_smem_u32(&sm.empty[s]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// readout head over the z rows of every batch of the launch (grid.y = batch): folded projection + BN + ReLU
+// -> mlp.0 -> LeakyReLU -> mlp.3 on the tensor cores (mma.sync TF32 x3), 64 rows per block
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_mma_tf32(float (&c)[4], const unsigned (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+constexpr int kStHeadFrag4 = (kOffAsP - kOffB1f) / 4;   // float4 entries of B1f | B2f (contiguous in `prepared`)
+
+__global__ void __launch_bounds__(128)
+lp_stream_head_kernel(const qot_lp_batch_t* __restrict__ batches, const float* __restrict__ prep) {
+  __shared__ float4 frag[kStHeadFrag4];
+  const qot_lp_batch_t& d = batches[blockIdx.y];
+  const float* __restrict__ zbuf = d.z;
+  float* __restrict__ out = d.out;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+  const int64_t L = d.lut_ptr[d.B];
+  if (static_cast<int64_t>(blockIdx.x) * 64 >= L) return;
+  for (int i = tid; i < kStHeadFrag4; i += 128) frag[i] = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + i);
+  __syncthreads();
+  const float4* __restrict__ f1 = frag;
+  const float4* __restrict__ f2 = frag + 16 * 32;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + warp; tile * 16 < L;
+       tile += static_cast<int64_t>(gridDim.x) * 4) {
+    const int64_t ra = tile * 16 + g8, rb = ra + 8;
+    const bool va = ra < L, vb = rb < L;
+    const float* za = zbuf + ra * (kHeads * kF);
+    const float* zb = zbuf + rb * (kHeads * kF);
+    float H[4][4], Hc[4][4];                           // fp32 sums of the hi x hi tiles; compensation chains
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) H[q][i] = Hc[q][i] = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < kHeads; ++h) {
+      unsigned ahi[4], alo[4];
+      {
+        float a[4];
+        a[0] = va ? za[h * kF + t4] : 0.f;
+        a[1] = vb ? zb[h * kF + t4] : 0.f;
+        a[2] = t4 == 0 ? (va ? za[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
+        a[3] = t4 == 0 ? (vb ? zb[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ahi[i] = tf32_rna(a[i]);
+          alo[i] = tf32_rna(a[i] - __uint_as_float(ahi[i]));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * h + jj;
+        const float4 b = f1[j * 32 + lane];
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        st_mma_tf32(c, alo, b.x, b.y);
+        st_mma_tf32(c, ahi, b.z, b.w);
+        st_mma_tf32(c, ahi, b.x, b.y);
+        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
+        unsigned yhi[4], ylo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          yhi[i] = tf32_rna_finite(y[i]);
+          ylo[i] = tf32_rna_finite(y[i] - __uint_as_float(yhi[i]));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b2 = f2[(j * 4 + q) * 32 + lane];
+          st_mma_tf32(Hc[q], ylo, b2.x, b2.y);
+          st_mma_tf32(Hc[q], yhi, b2.z, b2.w);
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          st_mma_tf32(t, yhi, b2.x, b2.y);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) H[q][i] += t[i];
+        }
+      }
+    }
+    float oa[QOT_OUT] = {0.f, 0.f, 0.f}, ob[QOT_OUT] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = 8 * q + 2 * t4;
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
+      float hv[4] = {H[q][0] + Hc[q][0] + b1.x, H[q][1] + Hc[q][1] + b1.y, H[q][2] + Hc[q][2] + b1.x,
+                     H[q][3] + Hc[q][3] + b1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hv[i] = hv[i] > 0.f ? hv[i] : 0.01f * hv[i];
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
+        oa[k] = fmaf(hv[0], w2.x, oa[k]);
+        oa[k] = fmaf(hv[1], w2.y, oa[k]);
+        ob[k] = fmaf(hv[2], w2.x, ob[k]);
+        ob[k] = fmaf(hv[3], w2.y, ob[k]);
+      }
+    }
+#pragma unroll
+    for (int s = 1; s <= 2; s <<= 1) {
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        oa[k] += __shfl_xor_sync(kFull, oa[k], s);
+        ob[k] += __shfl_xor_sync(kFull, ob[k], s);
+      }
+    }
+    if (t4 < QOT_OUT) {
+      const float b2 = __ldg(prep + kOffB2 + t4);
+      if (va) out[ra * QOT_OUT + t4] = (t4 == 0 ? oa[0] : t4 == 1 ? oa[1] : oa[2]) + b2;
+      if (vb) out[rb * QOT_OUT + t4] = (t4 == 0 ? ob[0] : t4 == 1 ? ob[1] : ob[2]) + b2;
+    }
+  }
+}
+
+}  // namespace qot
+
+using namespace qot;
+
+extern "C" int64_t qot_lightpath_stream_tiles(int64_t B) { return B > 0 ? cdiv(B, kTG) : 0; }
+
+// `batches`: DEVICE array of n_batches descriptors with tile0 filled (tile0[0] = 0, tile0[b+1] = tile0[b] +
+// qot_lightpath_stream_tiles(B_b)); total_tiles = their sum; uniform_tiles = tiles per batch when every batch
+// but the last has the same count (0: the kernel searches tile0).  max_rows = the largest lut_ptr[B] over
+// the batches (an upper bound such as max N is fine): sizes the head grid.  The status words of the batches
+// must be zero on entry (one cudaMemsetAsync over a pooled array does it).
+extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches, int64_t total_tiles,
+                                          int64_t uniform_tiles, int64_t max_rows, const float* prepared,
+                                          int32_t is_lut_index, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(batches && n_batches > 0 && total_tiles >= 0 && uniform_tiles >= 0 && max_rows >= 0,
+              "qot_lightpath_infer_stream: bad argument");
+  QOT_REQUIRE(prepared && (reinterpret_cast<uintptr_t>(prepared) & 15) == 0,
+              "qot_lightpath_infer_stream: prepared must be 16-byte aligned");
+  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_stream: is_lut_index out of range");
+  if (total_tiles == 0) return QOT_OK;
+  static std::atomic<unsigned long long> done{0};
+  const int smem = static_cast<int>(sizeof(StSmem) + 128);
+  if (int rc = once_per_device(done, [smem] {
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        return static_cast<int>(QOT_OK);
+      }))
+    return rc;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(kNumSMs, total_tiles));
+  lp_stream_kernel<false><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles, prepared,
+                                                            is_lut_index);
+  QOT_LAUNCH_CHECK();
+  const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(max_rows, 64), 4 * kNumSMs));
+  lp_stream_head_kernel<<<dim3(static_cast<unsigned>(hb), static_cast<unsigned>(n_batches)), 128, 0, stream>>>(batches, prepared);
+  QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
