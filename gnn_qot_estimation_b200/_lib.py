@@ -44,6 +44,13 @@ class QotLightpathParams(C.Structure):
                 ("bn_eps", C.c_float), ("is_lut_index", i32)]
 
 
+class QotLpBatch(C.Structure):
+    _fields_ = [("x", P), ("edge_index", P), ("ptr", P), ("edge_ptr", P), ("lut_ptr", P),
+                ("N", i64), ("E", i64), ("B", i64),
+                ("out", P), ("lut_batch", P), ("lut_node", P), ("n_lut", P), ("status", P), ("z", P),
+                ("tile0", i64), ("reserved", i64)]
+
+
 class QotLpSlot(C.Structure):
     _fields_ = [("x", P), ("edge_src", P), ("edge_dst", P), ("ptrs", P), ("out", P), ("lut_batch", P),
                 ("lut_node", P), ("n_lut", P), ("status", P), ("z", P), ("arena", P),
@@ -101,6 +108,8 @@ SIGNATURES = {
     "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, vp]),
     "qot_topo_fused_bwd_workspace_bytes": (sz, [i32]),
     "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, vp]),
+    "qot_lightpath_stream_tiles": (i64, [i64]),
+    "qot_lightpath_infer_stream": (C.c_int, [P, i32, i64, i64, i64, P, i32, i32, vp]),
     "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
     "qot_lightpath_get_variant": (C.c_int, []),
     "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,

@@ -27,7 +27,7 @@ class Batch:
 
     def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, node_ids=None,
                  y=None, ptr=None, edge_ptr=None, lut_ptr=None, num_graphs: Optional[int] = None,
-                 lut_col: Optional[int] = None):
+                 lut_col: Optional[int] = None, sym_by_src: bool = False):
         self.x, self.edge_index, self.edge_attr = x, edge_index, edge_attr
         self.batch, self.node_ids, self.y = batch, node_ids, y
         self.ptr, self.edge_ptr = ptr, edge_ptr
@@ -35,6 +35,10 @@ class Batch:
         # (where each graph's readout rows go); built by the collate like ptr / edge_ptr
         self.lut_ptr, self.lut_col = lut_ptr, lut_col
         self.num_graphs = num_graphs
+        # True only when the producer of the batch VERIFIED the from_networkx layout of undirected graphs for every
+        # graph (edges grouped by source ascending, both directions present, no duplicate pair):
+        # PackedGraphStore.verify_layout().  Lets the eval kernels skip the source row of edge_index.
+        self.sym_by_src = bool(sym_by_src)
         self._cache = {}          # per-batch CSR etc. built lazily by the ops layer
 
     # -- PyG-like conveniences ------------------------------------------------
@@ -53,12 +57,12 @@ class Batch:
     def to(self, device, non_blocking: bool = False) -> "Batch":
         kw = {k: (getattr(self, k).to(device, non_blocking=non_blocking)
                   if getattr(self, k) is not None else None) for k in _FIELDS}
-        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, **kw)
+        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, sym_by_src=self.sym_by_src, **kw)
 
     def pin_memory(self) -> "Batch":
         kw = {k: (getattr(self, k).pin_memory() if getattr(self, k) is not None else None)
               for k in _FIELDS}
-        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, **kw)
+        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, sym_by_src=self.sym_by_src, **kw)
 
     def cpu(self) -> "Batch":
         return self.to("cpu")
@@ -90,6 +94,7 @@ class PackedGraphStore:
         self._node_ptr_host = self.node_ptr.cpu().numpy()
         self._edge_ptr_host = self.edge_ptr.cpu().numpy()
         self._arange = None
+        self.sym_by_src = False      # set by verify_layout()
 
     @property
     def num_graphs(self) -> int:
@@ -101,8 +106,39 @@ class PackedGraphStore:
 
     def to(self, device) -> "PackedGraphStore":
         mv = lambda t: None if t is None else t.to(device)
-        return PackedGraphStore(mv(self.node_ptr), mv(self.edge_ptr), mv(self.edge_src), mv(self.edge_dst),
-                                mv(self.node_feat), mv(self.edge_feat), mv(self.y), self.lut_col)
+        st = PackedGraphStore(mv(self.node_ptr), mv(self.edge_ptr), mv(self.edge_src), mv(self.edge_dst),
+                              mv(self.node_feat), mv(self.edge_feat), mv(self.y), self.lut_col)
+        st.sym_by_src = self.sym_by_src
+        return st
+
+    def verify_layout(self) -> bool:
+        """One-time check (on the store's device, a few sorts over the edge arrays -- not on the hot path) of the
+        layout ``torch_geometric.utils.from_networkx`` gives an undirected ``nx.Graph`` (SURVEY.md A.6;
+        lightpath_training/dataset.py:86): inside every graph the edges are grouped by source node ascending,
+        every edge is present in both directions, no (source, destination) pair repeats, endpoints lie inside
+        the graph.  Sets and returns ``sym_by_src``; batches collated from the store inherit it, and the
+        LightpathGNN eval kernels then never read the source row of ``edge_index``."""
+        E = int(self.edge_src.numel())
+        ok = True
+        if E:
+            n = (self.node_ptr[1:] - self.node_ptr[:-1])
+            cnt = (self.edge_ptr[1:] - self.edge_ptr[:-1])
+            g = torch.repeat_interleave(torch.arange(self.num_graphs, device=self.device), cnt)
+            src, dst = self.edge_src.to(torch.int64), self.edge_dst.to(torch.int64)
+            ng = n[g]
+            K = int(n.max().item()) + 1
+            ok = bool(((src >= 0) & (src < ng) & (dst >= 0) & (dst < ng)).all().item())
+            if ok:
+                same = g[1:] == g[:-1]
+                ok = bool((~same | (src[1:] >= src[:-1])).all().item())
+            if ok:
+                kf = (g * K + src) * K + dst
+                kr = (g * K + dst) * K + src
+                kf_sorted = torch.sort(kf).values
+                ok = bool((kf_sorted[1:] != kf_sorted[:-1]).all().item()) and \
+                    bool(torch.equal(kf_sorted, torch.sort(kr).values))
+        self.sym_by_src = ok
+        return ok
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
@@ -162,7 +198,8 @@ class PackedGraphStore:
             from . import ops
             lut_ptr = ops.lightpath_lut_ptr(x, optr, self.lut_col)
         b = Batch(x=x, edge_index=ei, edge_attr=ea, batch=bt, node_ids=nid, y=y,
-                  ptr=optr, edge_ptr=oeptr, lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col)
+                  ptr=optr, edge_ptr=oeptr, lut_ptr=lut_ptr, num_graphs=B, lut_col=self.lut_col,
+                  sym_by_src=self.sym_by_src)
         # largest graph of the batch (host arrays, no sync): sizes the per-graph kernels' shared memory
         if isinstance(ids, range) and ids.step == 1:
             dn, de = np.diff(nph[g0:g1 + 1]), np.diff(eph[g0:g1 + 1])
@@ -213,7 +250,8 @@ class PackedGraphStore:
             ei_v.copy_(ei); ptrs[0].copy_(ptr); ptrs[1].copy_(eptr); ptrs[2].copy_(lut_ptr); x_v.copy_(x)
             pin_ = lambda t: None if t is None else t.pin_memory()
             b = Batch(x=x_v, edge_index=ei_v, edge_attr=pin_(ea), batch=pin_(bt), node_ids=pin_(nid), y=pin_(y),
-                      ptr=ptrs[0], edge_ptr=ptrs[1], lut_ptr=ptrs[2], num_graphs=B, lut_col=self.lut_col)
+                      ptr=ptrs[0], edge_ptr=ptrs[1], lut_ptr=ptrs[2], num_graphs=B, lut_col=self.lut_col,
+                      sym_by_src=self.sym_by_src)
             b._arena = arena                              # keeps the pinned allocation alive
             return b
         # the three offset arrays share one [3, B+1] buffer: one H2D copy moves them all
@@ -228,4 +266,5 @@ class PackedGraphStore:
                 ptr_v, eptr_v = ptr_v.pin_memory(), eptr_v.pin_memory()
         pin_ = (lambda t: None if t is None else t.pin_memory()) if pin else (lambda t: t)
         return Batch(x=pin_(x), edge_index=pin_(ei), edge_attr=pin_(ea), batch=pin_(bt), node_ids=pin_(nid),
-                     y=pin_(y), ptr=ptr_v, edge_ptr=eptr_v, lut_ptr=lut_v, num_graphs=B, lut_col=self.lut_col)
+                     y=pin_(y), ptr=ptr_v, edge_ptr=eptr_v, lut_ptr=lut_v, num_graphs=B, lut_col=self.lut_col,
+                     sym_by_src=self.sym_by_src)

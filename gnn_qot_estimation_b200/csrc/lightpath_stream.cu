@@ -34,26 +34,27 @@ constexpr int kTG = 16;                    // graphs per tile
 constexpr int kTNodes = 704;               // x window: mean 512 nodes + 3.4 sigma (sigma = 4 * 14.1)
 constexpr int kTEdges = 2688;              // destination window: mean 1984 edges + 3.1 sigma
 constexpr int kTMaxE = 248;                // per graph: 8 lanes x 31 contiguous edges (bit mask per lane)
-constexpr int kStStages = 4;
-constexpr int kStGroups = 3;               // consumer groups
-constexpr int kStGroupWarps = 4;           // 4 warps x 4 graphs = one tile
-constexpr int kStConsumerWarps = kStGroups * kStGroupWarps;
+#ifndef QOT_ST_WARPS
+#define QOT_ST_WARPS 15
+#endif
+#ifndef QOT_ST_XSTAGES
+#define QOT_ST_XSTAGES 7
+#endif
+#ifndef QOT_ST_DSTAGES
+#define QOT_ST_DSTAGES 4
+#endif
+constexpr int kStStages = QOT_ST_XSTAGES;  // x ring: a stage lives until its tile's attention rows are out
+constexpr int kStDStages = QOT_ST_DSTAGES; // destination ring: a stage is dead as soon as the tile has been scanned
+constexpr int kStGroupWarps = 4;           // a tile = 4 quarter-tiles of 4 graphs; a consumer warp takes one at a time
+constexpr int kStConsumerWarps = QOT_ST_WARPS;
 constexpr int kStThreads = 32 * (1 + kStConsumerWarps);
 constexpr int kStXBytes = kTNodes * kF * 4;
 constexpr int kStDBytes = kTEdges * 8;
-constexpr unsigned kStSpin = 1u << 28;     // a wedged barrier ends the kernel (status bit 4), never hangs it
+constexpr unsigned kStSpin = 1u << 22;     // polls (each may sleep up to the suspend hint): a wedged barrier ends the kernel
+                                           // (status bit 4), never hangs it
 
 struct alignas(16) StTileInfo {
-  const float* x;                          // batch tensors (generic path + source gather)
-  const int64_t* esrc;
-  const int64_t* edst;
-  float* z;
-  float* out;
-  int64_t* lut_batch;
-  int32_t* lut_node;
-  int32_t* n_lut;
-  int32_t* status;
-  int64_t N, E, B;
+  qot_lp_batch_t d;                        // the batch descriptor, copied asynchronously with the index rows
   int64_t g0;                              // first graph of the tile (index inside its batch)
   int64_t nb0, eb0;                        // first node / edge staged
   int xn, en;                              // nodes / edges staged (0: window unusable, graphs take the generic path)
@@ -61,33 +62,74 @@ struct alignas(16) StTileInfo {
   int ng;                                  // graphs in the tile
   int pad;
 };
+static_assert(sizeof(qot_lp_batch_t) == 128, "the descriptor is copied as eight 16-byte pieces");
 
 struct alignas(128) StStage {
   alignas(128) unsigned char xs[kStXBytes + 16];
-  alignas(16) unsigned char ds[kStDBytes + 16];
   alignas(16) long long ptrs[3][kTG + 2];  // ptr / edge_ptr / lut_ptr rows of the tile (kTG + 1 entries each)
   StTileInfo info;
 };
+struct alignas(128) StDStage {
+  alignas(128) unsigned char ds[kStDBytes + 16];
+};
 
-struct StGroupScratch {
-  int msg[kTG][kSubMsg];
-  float gen[kStGroupWarps][128];           // generic path: z (32 floats) + message list (64 ints) per warp
+struct StGenericArgs {                     // tile fields the generic path needs after the stage is handed back
+  const float* x;
+  const int64_t* esrc;
+  const int64_t* edst;
+  float* z;
+  int64_t* lut_batch;
+  int32_t* lut_node;
+  int32_t* status;
+  int64_t N, E, g0;
+  int64_t p[4][6];                         // per graph of the warp: n0 n1 e0 e1 l0 l1
+};
+
+struct StWarpScratch {                     // per consumer warp
+  StGenericArgs gargs;
+  int msg[4][kSubMsg];
+  int raw[4][kSubMsg];                     // kSym: the LUT node's out-run before ranking
+  float gen[128];                          // generic path: z (32 floats) + message list (64 ints)
 };
 
 struct StSmem {
+  StDStage dstage[kStDStages];             // first: the scan's masked over-reads past a window stay inside the block
   StStage stage[kStStages];
-  StGroupScratch grp[kStGroups];
-  alignas(8) unsigned long long full[kStStages];
-  alignas(8) unsigned long long empty[kStStages];
+  float4 asp[8][6];                        // attention source vectors per lane slot (lp_prepare_kernel's kOffAsP table)
+  StWarpScratch wsc[kStConsumerWarps];
+  alignas(8) unsigned long long full[kStStages];    // x window + destination window + index rows of a tile landed
+  alignas(8) unsigned long long empty[kStStages];   // x stage released (4 consumer warps)
+  alignas(8) unsigned long long dempty[kStDStages]; // destination stage released (4 consumer warps)
+  int next_unit;                                    // quarter-tiles handed out so far (consumer warps claim them in order)
 };
 static_assert(sizeof(StSmem) + 1024 <= 227 * 1024, "lp_stream_kernel: shared memory over the 227 KB block limit");
 
+#ifdef QOT_ST_TRACE
+// debug build only (scripts/build_variant.sh ... -DQOT_ST_TRACE): per-CTA cycle sums, 8 slots per CTA:
+// 0 producer wait-empty, 1 producer issue, 2 consumer wait-full (all warps), 3 consumer work, 4 tiles, 5 total
+__device__ unsigned long long* g_st_trace = nullptr;
+#define ST_DECL() long long st_acc_[4] = {0, 0, 0, 0}
+#define ST_T0() const long long st_t0_ = clock64()
+#define ST_ACC(slot) do { st_acc_[slot] += clock64() - st_t0_; } while (0)
+#define ST_FLUSH() do { if (g_st_trace && lane == 0) for (int i_ = 0; i_ < 4; ++i_) if (st_acc_[i_]) atomicAdd(g_st_trace + blockIdx.x * 8 + i_, static_cast<unsigned long long>(st_acc_[i_])); } while (0)
+#else
+#define ST_DECL() do {} while (0)
+#define ST_T0() do {} while (0)
+#define ST_ACC(slot) do {} while (0)
+#define ST_FLUSH() do {} while (0)
+#endif
 __device__ __forceinline__ unsigned st_smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+// try_wait with an explicit suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of re-issuing the poll -- 57 % of all issued instructions were polls without it, and they
+// compete with the producer warp for issue slots
+#ifndef QOT_ST_SUSPEND_NS
+#define QOT_ST_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool st_try_wait(unsigned bar, unsigned parity) {
   unsigned ok;
   asm volatile(
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(QOT_ST_SUSPEND_NS) : "memory");
   return ok != 0u;
 }
 __device__ __forceinline__ bool st_wait(unsigned bar, unsigned parity) {
@@ -100,8 +142,9 @@ __device__ __forceinline__ void st_arrive(unsigned bar) {
 }
 
 // descriptor of the batch tile T of the launch belongs to (uniform tile count per batch, or prefix search)
-__device__ __forceinline__ int st_batch_of(const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb, int64_t T) {
-  if (tpb > 0) return static_cast<int>(min(T / tpb, static_cast<int64_t>(nb - 1)));
+// T is absolute (tile0 units); the launch covers tiles [base, base + total)
+__device__ __forceinline__ int st_batch_of(const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb, int64_t base, int64_t T) {
+  if (tpb > 0) return static_cast<int>(min((T - base) / tpb, static_cast<int64_t>(nb - 1)));
   int lo = 0, hi = nb - 1;                 // last b with tile0[b] <= T
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -113,22 +156,29 @@ __device__ __forceinline__ int st_batch_of(const qot_lp_batch_t* __restrict__ bt
 // ------------------------------------------------------------------------------------------------
 // producer: one warp
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb,
-                                            int64_t total_tiles, int lane) {
+__device__ __noinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb,
+                                         int64_t tile_base, int64_t total_tiles, int lane) {
   const int64_t G = gridDim.x;
   const int64_t my_tiles = (total_tiles - blockIdx.x + G - 1) / G;
+  ST_DECL();
   for (int64_t kb = 0; kb < my_tiles; kb += 32) {
-    // ---- look-ahead: lane j owns tile kb + j of this CTA
+    // ---- look-ahead: lane j owns tile kb + j of this CTA and fetches EVERYTHING its issue needs from global memory
+    // (descriptor fields, tile extents) -- 32 tiles' worth of dependent loads in flight at once, so the per-tile
+    // issue path below touches registers and shared memory only
     int b = 0;
-    long long g0 = 0, nb0 = 0, nb1 = 0, eb0 = 0, eb1 = 0;
+    long long g0 = 0, nb0 = 0, nb1 = 0, eb0 = 0, eb1 = 0, dN = 0, dE = 0, dB = 0;
+    const float* dx = nullptr;
+    const int64_t *dei = nullptr, *dptr = nullptr, *deptr = nullptr, *dlptr = nullptr;
     if (kb + lane < my_tiles) {
-      const int64_t T = blockIdx.x + (kb + lane) * G;
-      b = st_batch_of(bt, nb, tpb, T);
+      const int64_t T = tile_base + blockIdx.x + (kb + lane) * G;
+      b = st_batch_of(bt, nb, tpb, tile_base, T);
       const qot_lp_batch_t& d = bt[b];
+      dx = d.x; dei = d.edge_index; dptr = d.ptr; deptr = d.edge_ptr; dlptr = d.lut_ptr;
+      dN = d.N; dE = d.E; dB = d.B;
       g0 = (T - d.tile0) * kTG;
-      const int64_t gE = min(g0 + kTG, d.B);
-      nb0 = d.ptr[g0]; nb1 = d.ptr[gE];
-      eb0 = d.edge_ptr[g0]; eb1 = d.edge_ptr[gE];
+      const int64_t gE = min(static_cast<int64_t>(g0 + kTG), static_cast<int64_t>(dB));
+      nb0 = dptr[g0]; nb1 = dptr[gE];
+      eb0 = deptr[g0]; eb1 = deptr[gE];
     }
     const int cnt = static_cast<int>(min(static_cast<int64_t>(32), my_tiles - kb));
     for (int j = 0; j < cnt; ++j) {
@@ -136,108 +186,151 @@ __device__ __forceinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __
       const int s = static_cast<int>(k % kStStages);
       const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
       StStage& st = sm.stage[s];
+      const int sd_ = static_cast<int>(k % kStDStages);
+      StDStage& dst_stage = sm.dstage[sd_];
       const unsigned fbar = st_smem_u32(&sm.full[s]);
-      st_wait(st_smem_u32(&sm.empty[s]), ph ^ 1u);       // consumers released the stage's previous tile
+      {
+        ST_T0();
+        st_wait(st_smem_u32(&sm.empty[s]), ph ^ 1u);     // consumers released the stages' previous tiles
+        st_wait(st_smem_u32(&sm.dempty[sd_]), static_cast<unsigned>((k / kStDStages) & 1) ^ 1u);
+        ST_ACC(0);
+      }
+      ST_T0();
       const int tb = __shfl_sync(kFull, b, j);
-      const long long tg0 = __shfl_sync(kFull, g0, j);
-      const long long tn0 = __shfl_sync(kFull, nb0, j), tn1 = __shfl_sync(kFull, nb1, j);
-      const long long te0 = __shfl_sync(kFull, eb0, j), te1 = __shfl_sync(kFull, eb1, j);
-      const qot_lp_batch_t d = bt[tb];                   // every lane: the same 128 bytes (broadcast, L1)
-      // ---- the tile's index rows: 3 x (kTG + 1) entries, 8-byte asynchronous copies
+      const long long tg0 = __shfl_sync(kFull, g0, j), tB = __shfl_sync(kFull, dB, j);
+      const int64_t* tptr = reinterpret_cast<const int64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(dptr), j));
+      const int64_t* teptr = reinterpret_cast<const int64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(deptr), j));
+      const int64_t* tlptr = reinterpret_cast<const int64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(dlptr), j));
+      // ---- the tile's index rows (3 x (kTG + 1) entries, 8-byte pieces) and its batch descriptor (8 x 16 bytes),
+      // all asynchronous: they arrive on the stage's `full` barrier like the two windows
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int idx = lane + 32 * r;
         if (idx < 3 * (kTG + 1)) {
           const int which = idx / (kTG + 1), i = idx % (kTG + 1);
-          const int64_t gi = min(static_cast<int64_t>(tg0 + i), d.B);
-          const int64_t* src = (which == 0 ? d.ptr : which == 1 ? d.edge_ptr : d.lut_ptr) + gi;
+          const int64_t gi = min(static_cast<int64_t>(tg0 + i), static_cast<int64_t>(tB));
+          const int64_t* src = (which == 0 ? tptr : which == 1 ? teptr : tlptr) + gi;
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st_smem_u32(&st.ptrs[which][i])), "l"(src) : "memory");
         }
       }
+      if (lane >= 24)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"(st_smem_u32(reinterpret_cast<char*>(&st.info.d) + 16 * (lane - 24))),
+                       "l"(reinterpret_cast<const char*>(bt + tb) + 16 * (lane - 24)) : "memory");
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fbar) : "memory");
-      if (lane == 0) {
+      // lane j still holds the tile's remaining values: it sizes the windows and issues the bulk copies itself
+      if (lane == j) {
         // ---- windows: nodes [nb0, nb0 + xn), edges [eb0, eb0 + en), copied from 16-byte aligned addresses;
         // a window that does not fit (or nonsense offsets) is not staged: its graphs take the generic path
         int xn = 0, en = 0;
-        if (tn0 >= 0 && tn1 >= tn0 && tn1 <= d.N && tn1 - tn0 <= kTNodes) xn = static_cast<int>(tn1 - tn0);
-        if (te0 >= 0 && te1 >= te0 && te1 <= d.E && te1 - te0 <= kTEdges) en = static_cast<int>(te1 - te0);
-        if (xn == 0 || (en == 0 && te1 != te0)) { xn = 0; en = 0; }
-        const int64_t* edst = d.edge_index + d.E;
-        const uintptr_t xa = reinterpret_cast<uintptr_t>(d.x) + static_cast<uintptr_t>(xn > 0 ? tn0 : 0) * (kF * 4);
-        const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? te0 : 0) * 8;
+        if (nb0 >= 0 && nb1 >= nb0 && nb1 <= dN && nb1 - nb0 <= kTNodes) xn = static_cast<int>(nb1 - nb0);
+        if (eb0 >= 0 && eb1 >= eb0 && eb1 <= dE && eb1 - eb0 <= kTEdges) en = static_cast<int>(eb1 - eb0);
+        if (xn == 0 || (en == 0 && eb1 != eb0)) { xn = 0; en = 0; }
+        const int64_t* edst = dei + dE;
+        const uintptr_t xa = reinterpret_cast<uintptr_t>(dx) + static_cast<uintptr_t>(xn > 0 ? nb0 : 0) * (kF * 4);
+        const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? eb0 : 0) * 8;
         const unsigned xlead = static_cast<unsigned>(xa & 15), dlead = static_cast<unsigned>(da & 15);
         const uintptr_t xs0 = xa - xlead, ds0 = da - dlead;
         const unsigned xspan = xlead + static_cast<unsigned>(xn) * (kF * 4), dspan = dlead + static_cast<unsigned>(en) * 8;
         unsigned xbytes = (xspan + 15u) & ~15u, dbytes = (dspan + 15u) & ~15u;
         // never read past the end of a tensor: the few bytes a rounded-up window would add are copied by hand
-        if (xs0 + xbytes > reinterpret_cast<uintptr_t>(d.x) + static_cast<uintptr_t>(d.N) * (kF * 4)) xbytes = xspan & ~15u;
-        if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(d.E) * 8) dbytes = dspan & ~15u;
+        if (xs0 + xbytes > reinterpret_cast<uintptr_t>(dx) + static_cast<uintptr_t>(dN) * (kF * 4)) xbytes = xspan & ~15u;
+        if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(dE) * 8) dbytes = dspan & ~15u;
         if (xn == 0) xbytes = 0;
         if (en == 0) dbytes = 0;
         if (xn > 0)
           for (unsigned o = xbytes; o < xspan; o += 4)
             *reinterpret_cast<float*>(st.xs + o) = *reinterpret_cast<const float*>(xs0 + o);
         if (en > 0 && dspan > dbytes)
-          *reinterpret_cast<long long*>(st.ds + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
+          *reinterpret_cast<long long*>(dst_stage.ds + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
         StTileInfo& ti = st.info;
-        ti.x = d.x; ti.esrc = d.edge_index; ti.edst = edst; ti.z = d.z; ti.out = d.out;
-        ti.lut_batch = d.lut_batch; ti.lut_node = d.lut_node; ti.n_lut = d.n_lut; ti.status = d.status;
-        ti.N = d.N; ti.E = d.E; ti.B = d.B; ti.g0 = tg0; ti.nb0 = tn0; ti.eb0 = te0;
+        ti.g0 = g0; ti.nb0 = nb0; ti.eb0 = eb0;
         ti.xn = xn; ti.en = en; ti.xlead = xlead; ti.dlead = dlead;
-        ti.ng = static_cast<int>(min(static_cast<int64_t>(kTG), d.B - tg0));
+        ti.ng = static_cast<int>(min(static_cast<int64_t>(kTG), static_cast<int64_t>(dB - g0)));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fbar), "r"(xbytes + dbytes) : "memory");
         if (xbytes)
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(st_smem_u32(st.xs)), "l"(xs0), "r"(xbytes), "r"(fbar) : "memory");
         if (dbytes)
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(st_smem_u32(st.ds)), "l"(ds0), "r"(dbytes), "r"(fbar) : "memory");
+                       ::"r"(st_smem_u32(dst_stage.ds)), "l"(ds0), "r"(dbytes), "r"(fbar) : "memory");
       }
       __syncwarp();
+      ST_ACC(1);
     }
+  }
+  ST_FLUSH();
+}
+
+// generic path: graphs of this warp the fast path declined (over the caps, several / no LUT rows, hub rows,
+// foreign ids): one warp per graph, straight from global memory, z rows into the batch's workspace
+__device__ __noinline__ void st_generic(const StGenericArgs& ga, float* scratch, unsigned todo,
+                                        const float* __restrict__ prep, int lut_col, int lane) {
+  const float* gx = ga.x;
+  const int64_t N = ga.N;
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    if (!((todo >> s) & 1u)) continue;
+    const int64_t gn0 = ga.p[s][0], gn1 = ga.p[s][1], ge0 = ga.p[s][2], ge1 = ga.p[s][3], gl0 = ga.p[s][4], gl1 = ga.p[s][5];
+    float* s_z = scratch;
+    int* s_m = reinterpret_cast<int*>(scratch + 32);
+    int64_t orow = gl0;
+    int found = 0;
+    if (gn0 >= 0 && gn1 <= N && ge0 >= 0 && ge1 <= ga.E) {
+      for (int64_t nbq = gn0; nbq < gn1; nbq += 32) {
+        const int64_t node = nbq + lane;
+        unsigned mask = __ballot_sync(kFull, node < gn1 && gx[node * kF + lut_col] == 1.0f);
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ++found;
+          if (orow < gl1) {                                      // never write past this graph's rows
+            const int64_t i = nbq + bit;
+            lut_row_global<false>(gx, ga.esrc, ga.edst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
+            if (lane < kHeads * kF) ga.z[orow * (kHeads * kF) + lane] = s_z[(lane / kF) * 8 + lane % kF];
+            if (lane == 0) {
+              ga.lut_batch[orow] = ga.g0 + s;
+              ga.lut_node[orow] = static_cast<int32_t>(i);
+            }
+            __syncwarp();
+            ++orow;
+          }
+        }
+      }
+    }
+    if (lane == 0 && found != gl1 - gl0) atomicOr(ga.status, 1);
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// consumer: one tile (16 graphs) per group of 4 warps; 8 lanes per graph
-// ------------------------------------------------------------------------------------------------
-struct StLaneConst {
-  float AsP[6][kHeads];                    // attention source vectors in this lane's slot order
-  float AdP[kF][kHeads];                   // attention destination vectors, head slots of this lane
-};
-
-// z row (kZRow floats) of graph `g` -> the readout head (this build: the caller's z workspace, row l0)
-template <bool kHeadInKernel>
-__device__ __forceinline__ void st_emit_z(const StTileInfo& ti, int64_t l0, int hx, int o0, bool odd, const float (&acc3)[3],
-                                          float inv) {
-  float* zr = ti.z + l0 * (kHeads * kF) + hx * kF + o0;
-  zr[0] = acc3[0] * inv;
-  zr[1] = acc3[1] * inv;
-  if (!odd) zr[2] = acc3[2] * inv;
-}
-
-template <bool kHeadInKernel>
-__device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs, const StLaneConst& lc,
-                                                const float* __restrict__ prep, int lut_col, int gw, int lane,
-                                                unsigned ebar) {
-  const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
+// One tile.  Everything per graph is kept as 32-bit offsets inside the tile's windows (the 64-bit index rows stay in
+// the stage and are re-read where a global index is needed): registers are what bounds the consumer-warp count.
+template <bool kHeadInKernel, bool kSym>
+__device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dstg, StWarpScratch& gs,
+                                                const float4 (*__restrict__ asp)[6], const float* __restrict__ prep,
+                                                int lut_col, int gw, int lane, unsigned ebar, unsigned dbar) {
+  const int sg = lane >> 3, sl = lane & 7;
   const int gl = gw * 4 + sg;                          // graph slot inside the tile
   const StTileInfo& ti = st.info;
-  const bool active = gl < ti.ng;
-  const int64_t g = ti.g0 + gl;
-  const int64_t N = ti.N;
-  const int64_t n0 = st.ptrs[0][gl], n1 = st.ptrs[0][gl + 1];
-  const int64_t e0 = st.ptrs[1][gl], e1 = st.ptrs[1][gl + 1];
-  const int64_t l0 = st.ptrs[2][gl], l1 = st.ptrs[2][gl + 1];
-  const int64_t nb0 = ti.nb0, eb0 = ti.eb0;
-  const int xn = ti.xn, en = ti.en;
-  const bool fits = active && xn > 0 && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kTMaxE &&
-                    n0 >= nb0 && (n1 - nb0) <= xn && e0 >= eb0 && (e1 - eb0) <= en;
-  const int n = fits ? static_cast<int>(n1 - n0) : 0;
-  const int ne = fits ? static_cast<int>(e1 - e0) : 0;
-  if (active && g == ti.B - 1 && sl == 0) ti.n_lut[0] = static_cast<int32_t>(l1);
-  const float* sx = reinterpret_cast<const float*>(st.xs + ti.xlead) + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
-  const long long* sd = reinterpret_cast<const long long*>(st.ds + ti.dlead) + (fits ? static_cast<int>(e0 - eb0) : 0);
+  int n = 0, ne = 0, xoff = 0, eoff = 0, lrows = 0;
+  bool active, fits;
+  {
+    const int64_t n0 = st.ptrs[0][gl], n1 = st.ptrs[0][gl + 1];
+    const int64_t e0 = st.ptrs[1][gl], e1 = st.ptrs[1][gl + 1];
+    const int64_t l0 = st.ptrs[2][gl], l1 = st.ptrs[2][gl + 1];
+    const int64_t nb0 = ti.nb0, eb0 = ti.eb0;
+    const int xn = ti.xn, en = ti.en;
+    active = gl < ti.ng;
+    fits = active && xn > 0 && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kTMaxE &&
+           n0 >= nb0 && (n1 - nb0) <= xn && e0 >= eb0 && (e1 - eb0) <= en && l1 >= l0 && (l1 - l0) <= kMaxN;
+    if (fits) {
+      n = static_cast<int>(n1 - n0); ne = static_cast<int>(e1 - e0);
+      xoff = static_cast<int>(n0 - nb0); eoff = static_cast<int>(e0 - eb0);
+      lrows = static_cast<int>(l1 - l0);
+    }
+    if (active && ti.g0 + gl == ti.d.B - 1 && sl == 0) ti.d.n_lut[0] = static_cast<int32_t>(l1);
+  }
+  const float* sx = reinterpret_cast<const float*>(st.xs + ti.xlead) + xoff * kF;
+  const long long* sd = reinterpret_cast<const long long*>(dstg.ds + ti.dlead) + eoff;
   const int hx = sl >> 1;
   const bool odd = (sl & 1) != 0;
 
@@ -245,10 +338,13 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
   int cnt = 0, il = -1;
   {
     unsigned m = 0u;
+    const int rmax = (__reduce_max_sync(kFull, n) + 7) >> 3;
 #pragma unroll
     for (int r = 0; r < kMaxN / 8; ++r) {
-      const int node = sl + 8 * r;
-      if (node < n && sx[node * kF + lut_col] == 1.0f) m |= 1u << r;
+      if (r < rmax) {
+        const int node = sl + 8 * r;
+        if (node < n && sx[node * kF + lut_col] == 1.0f) m |= 1u << r;
+      }
     }
     cnt = __popc(m);
     int first = m ? 8 * (__ffs(m) - 1) + sl : 0x7fff;
@@ -259,24 +355,26 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
     }
     if (cnt) il = first;
   }
-  bool ok = fits && cnt == 1 && (l1 - l0) == 1;        // fast row: exactly one LUT node, as lut_ptr says
-  if (fits && sl == 0 && cnt != l1 - l0) atomicOr(ti.status, 1);   // lut_ptr does not describe this x
+  bool ok = fits && cnt == 1 && lrows == 1;            // fast row: exactly one LUT node, as lut_ptr says
+  if (fits && sl == 0 && cnt != lrows) atomicOr(ti.d.status, 1);   // lut_ptr does not describe this x
 
-  // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph (c odd: the 8-byte reads of
-  // the 8 lanes fall into distinct banks); one predicate per slot
-  int* msg = gs.msg[gl];
+  int* msg = gs.msg[sg];
   int mc = 0;
-  {
-    const int c = ((ne + 7) >> 3) | 1;
+  if constexpr (kSym) {
+    // ---- layout invariant verified by the store (PackedGraphStore.verify_layout): every graph is symmetric, without
+    // duplicate edges, its edges grouped by source ascending, every endpoint inside the graph (what from_networkx
+    // emits for an undirected graph).  Then indeg(u) = outdeg(u) for every node, the out-run of the
+    // LUT node il starts at #{edges with dst < il}, is #{dst == il} long, and its destinations ARE the sources of
+    // il's in-edges; in edge order those sources ascend.  So the scan only counts -- on the low words: verified ids
+    // are < N < 2^31 -- and nothing is read from the source row.
+    const int c = ((ne + 7) >> 3) | 1;                 // odd run length: the 8 lanes' reads hit distinct banks
     const int eb = sl * c;
     const int tmax = ok ? min(c, ne - eb) : 0;
     const int cmax = __reduce_max_sync(kFull, tmax);
-    const long long target = n0 + il;
-    const int tlo = static_cast<int>(target), thi = static_cast<int>(target >> 32);
-    // unconditional 8-byte reads: slots past the lane's run stay inside the stage (the window is followed by the
-    // index rows and the tile record) and are masked by t < tmax
-    const int2* sde = reinterpret_cast<const int2*>(sd + eb);
-    unsigned hm = 0u;
+    const int target = static_cast<int>(st.ptrs[0][gl]) + il;
+    const int* sde = reinterpret_cast<const int*>(sd + eb);
+    // four independent accumulator pairs (slot mod 4): the predicated ORs of consecutive slots do not chain
+    unsigned em[4] = {0u, 0u, 0u, 0u}, lm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int t4 = 0; t4 < 32; t4 += 4) {
       if (t4 < cmax) {
@@ -284,60 +382,135 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
         for (int i = 0; i < 4; ++i) {
           const int t = t4 + i;
           if (t < 31) {
-            const int2 d = sde[t];
-            asm("{ .reg .pred p;\n\t"
-                "setp.eq.s32 p, %1, %3;\n\t"
-                "setp.eq.and.s32 p, %2, %4, p;\n\t"
-                "@p or.b32 %0, %0, %5; }"
-                : "+r"(hm) : "r"(d.x), "r"(d.y), "r"(tlo), "r"(thi), "r"(1u << t));
+            const int d = sde[2 * t];                  // masked below: slots past the run stay inside the block's memory
+            asm("{ .reg .pred p, q;\n\t"
+                "setp.eq.s32 p, %2, %3;\n\t"
+                "setp.lt.s32 q, %2, %3;\n\t"
+                "@p or.b32 %0, %0, %4;\n\t"
+                "@q or.b32 %1, %1, %4; }"
+                : "+r"(em[i]), "+r"(lm[i]) : "r"(d), "r"(target), "r"(1u << t));
           }
         }
       }
     }
-    hm &= (1u << max(tmax, 0)) - 1u;                   // tmax <= 31
-    const int h = __popc(hm);
-    int incl = h;
+    const unsigned vm = (1u << max(tmax, 0)) - 1u;     // tmax <= 31
+    int pack = __popc((em[0] | em[1] | em[2] | em[3]) & vm) | (__popc((lm[0] | lm[1] | lm[2] | lm[3]) & vm) << 16);
 #pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-      const int up = __shfl_up_sync(kFull, incl, o, 8);
-      if (sl >= o) incl += up;
-    }
-    mc = __shfl_sync(kFull, incl, base + 7);
-    int pos = incl - h;
-    while (hm) {
-      const int t = __ffs(hm) - 1;
-      hm &= hm - 1u;
-      if (pos < kSubMsg - 1) msg[pos] = eb + t;
-      ++pos;
-    }
-  }
-  if (mc > kSubMsg - 1) ok = false;                    // hub row: generic path
-  __syncwarp();
-  // ---- sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
-  {
-    int kept = 0;
-    bool outside = false;
-    const int64_t* __restrict__ esrc = ti.esrc;
-#pragma unroll
-    for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
-      if (__any_sync(kFull, ok && t0 < mc)) {
-        const int t = t0 + sl;
-        long long sj = -1;
-        if (ok && t < mc) sj = esrc[e0 + msg[t]];
-        const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
-        const long long sloc = sj - n0;
-        const bool inslab = sloc >= 0 && sloc < n;
-        const bool keep = inslab && sloc != il;
-        outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
-        const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
-        __syncwarp();
-        if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
-        kept += __popc(sub);
-        __syncwarp();
+    for (int o = 1; o <= 4; o <<= 1) pack += __shfl_xor_sync(kFull, pack, o);
+    const int deg = pack & 0xffff, start = pack >> 16;
+    if (deg > kSubMsg - 1) ok = false;                 // hub row: generic path
+    // the out-run of il: <= 15 destinations, two per lane; self loops dropped, ascending order by ranking
+    int* raw = gs.raw[sg];
+    int v0 = 0x7fffffff, v1 = 0x7fffffff;
+    bool bad = false;
+    if (ok) {
+      const int n0i = target - il;
+      if (sl < deg) {
+        const int w = static_cast<int>(sd[start + sl]) - n0i;
+        bad |= w < 0 || w >= n;
+        if (w != il) v0 = w;
+      }
+      if (sl + 8 < deg) {
+        const int w = static_cast<int>(sd[start + sl + 8]) - n0i;
+        bad |= w < 0 || w >= n;
+        if (w != il) v1 = w;
       }
     }
-    if (outside) ok = false;                           // a source outside the graph's node range: generic path
-    mc = kept;
+    raw[sl] = v0;
+    raw[sl + 8] = v1;
+    if (((__ballot_sync(kFull, bad) >> (8 * sg)) & 0xffu) != 0u) ok = false;   // not a node of this graph: generic path
+    const int dmax = __reduce_max_sync(kFull, ok ? deg : 0);
+    __syncwarp();
+    if (lane == 0) st_arrive(dbar);                    // last read of the destination window: its stage may be refilled
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < dmax; ++j) {
+      const int w = raw[j];                             // entries past deg hold INT_MAX: they rank nobody down
+      r0 += w < v0;
+      r1 += w < v1;
+    }
+    const bool k0 = ok && v0 != 0x7fffffff, k1 = ok && v1 != 0x7fffffff;
+    if (k0) msg[r0] = v0;
+    if (k1) msg[r1] = v1;
+    const unsigned kb0 = (__ballot_sync(kFull, k0) >> (8 * sg)) & 0xffu, kb1 = (__ballot_sync(kFull, k1) >> (8 * sg)) & 0xffu;
+    mc = __popc(kb0) + __popc(kb1);
+  } else {
+    // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph (c odd: the 8-byte reads of
+    // the 8 lanes fall into distinct banks); one predicate per slot
+    {
+      const int c = ((ne + 7) >> 3) | 1;
+      const int eb = sl * c;
+      const int tmax = ok ? min(c, ne - eb) : 0;
+      const int cmax = __reduce_max_sync(kFull, tmax);
+      const long long target = st.ptrs[0][gl] + il;
+      const int tlo = static_cast<int>(target), thi = static_cast<int>(target >> 32);
+      // unconditional 8-byte reads: slots past the lane's run stay inside the block's shared memory and are masked
+      // by t < tmax
+      const int2* sde = reinterpret_cast<const int2*>(sd + eb);
+      unsigned hm = 0u;
+#pragma unroll
+      for (int t4 = 0; t4 < 32; t4 += 4) {
+        if (t4 < cmax) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int t = t4 + i;
+            if (t < 31) {
+              const int2 d = sde[t];
+              asm("{ .reg .pred p;\n\t"
+                  "setp.eq.s32 p, %1, %3;\n\t"
+                  "setp.eq.and.s32 p, %2, %4, p;\n\t"
+                  "@p or.b32 %0, %0, %5; }"
+                  : "+r"(hm) : "r"(d.x), "r"(d.y), "r"(tlo), "r"(thi), "r"(1u << t));
+            }
+          }
+        }
+      }
+      hm &= (1u << max(tmax, 0)) - 1u;                   // tmax <= 31
+      const int h = __popc(hm);
+      int incl = h;
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o, 8);
+        if (sl >= o) incl += up;
+      }
+      mc = __shfl_sync(kFull, incl, (lane & ~7) + 7);
+      int pos = incl - h;
+      while (hm) {
+        const int t = __ffs(hm) - 1;
+        hm &= hm - 1u;
+        if (pos < kSubMsg - 1) msg[pos] = eb + t;
+        ++pos;
+      }
+    }
+    if (mc > kSubMsg - 1) ok = false;                    // hub row: generic path
+    __syncwarp();
+    if (lane == 0) st_arrive(dbar);                      // last read of the destination window: its stage may be refilled
+    // ---- sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
+    {
+      int kept = 0;
+      bool outside = false;
+      const int64_t* __restrict__ esrc = ti.d.edge_index + st.ptrs[1][gl];
+      const int64_t n0 = st.ptrs[0][gl], N = ti.d.N;
+#pragma unroll
+      for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
+        if (__any_sync(kFull, ok && t0 < mc)) {
+          const int t = t0 + sl;
+          long long sj = -1;
+          if (ok && t < mc) sj = esrc[msg[t]];
+          const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
+          const long long sloc = sj - n0;
+          const bool inslab = sloc >= 0 && sloc < n;
+          const bool keep = inslab && sloc != il;
+          outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
+          const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
+          __syncwarp();
+          if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
+          kept += __popc(sub);
+          __syncwarp();
+        }
+      }
+      if (outside) ok = false;                           // a source outside the graph's node range: generic path
+      mc = kept;
+    }
   }
   if (ok && sl == 0) msg[mc] = il;                     // the appended self loop comes last
   ++mc;
@@ -354,8 +527,9 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
       const float xi = sx[ils * kF + k];
-#pragma unroll
-      for (int i = 0; i < kHeads; ++i) d[i] = fmaf(xi, lc.AdP[k][i], d[i]);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + hx * kF + k);
+      d[0] = fmaf(xi, b.x, d[0]); d[1] = fmaf(xi, b.y, d[1]);
+      d[2] = fmaf(xi, b.z, d[2]); d[3] = fmaf(xi, b.w, d[3]);
     }
     float mx[kHeads], acc3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -373,11 +547,16 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
         q[5] = odd ? x2 : 1.0f;
         float a[kHeads], mr[kHeads], m2[kHeads];
 #pragma unroll
-        for (int i = 0; i < kHeads; ++i) {
-          float t = d[i];
+        for (int i = 0; i < kHeads; ++i) a[i] = d[i];
 #pragma unroll
-          for (int m = 0; m < 6; ++m) t = fmaf(q[m], lc.AsP[m][i], t);    // the ONE slot carries weight 0
-          t = t > 0.f ? t : 0.2f * t;
+        for (int m = 0; m < 6; ++m) {                       // the ONE slot carries weight 0
+          const float4 w = asp[sl][m];
+          a[0] = fmaf(q[m], w.x, a[0]); a[1] = fmaf(q[m], w.y, a[1]);
+          a[2] = fmaf(q[m], w.z, a[2]); a[3] = fmaf(q[m], w.w, a[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < kHeads; ++i) {
+          const float t = a[i] > 0.f ? a[i] : 0.2f * a[i];
           a[i] = valid ? t : -INFINITY;
         }
 #pragma unroll
@@ -413,67 +592,37 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, StGroupScratch& gs,
     const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
     const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
     if (ok) {
-      st_emit_z<kHeadInKernel>(ti, l0, hx, o0, odd, acc3, inv);
+      const int64_t l0 = st.ptrs[2][gl];
+      float* zr = ti.d.z + l0 * (kHeads * kF) + hx * kF + o0;
+      zr[0] = acc3[0] * inv;
+      zr[1] = acc3[1] * inv;
+      if (!odd) zr[2] = acc3[2] * inv;
       if (sl == 0) {
-        ti.lut_batch[l0] = g;
-        ti.lut_node[l0] = static_cast<int32_t>(n0 + il);
+        ti.d.lut_batch[l0] = ti.g0 + gl;
+        ti.d.lut_node[l0] = static_cast<int32_t>(st.ptrs[0][gl]) + il;
       }
     }
   }
-  const int my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
-  // pointers the generic path needs, read before the stage is handed back
-  const float* gx = ti.x;
-  const int64_t* gesrc = ti.esrc;
-  const int64_t* gedst = ti.edst;
-  float* gz = ti.z;
-  int64_t* glb = ti.lut_batch;
-  int32_t* gln = ti.lut_node;
-  int32_t* gstatus = ti.status;
-  const int64_t tg0 = ti.g0;
-  const bool any_generic = __any_sync(kFull, my_state == 2);
-  __syncwarp();
-  if (lane == 0) st_arrive(ebar);                      // the slabs are dead: the producer may refill the stage
-
-  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
-  if (any_generic) {
-#pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-      if (__shfl_sync(kFull, my_state, 8 * s) != 2) continue;
-      const int64_t gn0 = __shfl_sync(kFull, n0, 8 * s), gn1 = __shfl_sync(kFull, n1, 8 * s);
-      const int64_t ge0 = __shfl_sync(kFull, e0, 8 * s), ge1 = __shfl_sync(kFull, e1, 8 * s);
-      const int64_t gl0 = __shfl_sync(kFull, l0, 8 * s), gl1 = __shfl_sync(kFull, l1, 8 * s);
-      float* s_z = gs.gen[gw];
-      int* s_m = reinterpret_cast<int*>(gs.gen[gw] + 32);
-      int64_t orow = gl0;
-      int found = 0;
-      if (gn0 >= 0 && gn1 <= N && ge0 >= 0 && ge1 <= ti.E) {
-        for (int64_t nbq = gn0; nbq < gn1; nbq += 32) {
-          const int64_t node = nbq + lane;
-          unsigned mask = __ballot_sync(kFull, node < gn1 && gx[node * kF + lut_col] == 1.0f);
-          while (mask) {
-            const int bit = __ffs(mask) - 1;
-            mask &= mask - 1;
-            ++found;
-            if (orow < gl1) {                                      // never write past this graph's rows
-              const int64_t i = nbq + bit;
-              lut_row_global<false>(gx, gesrc, gedst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
-              if (lane < kHeads * kF) gz[orow * (kHeads * kF) + lane] = s_z[(lane / kF) * 8 + lane % kF];
-              if (lane == 0) {
-                glb[orow] = tg0 + gw * 4 + s;
-                gln[orow] = static_cast<int32_t>(i);
-              }
-              __syncwarp();
-              ++orow;
-            }
-          }
-        }
-      }
-      if (lane == 0 && found != gl1 - gl0) atomicOr(gstatus, 1);
+  const bool generic = !ok && active && (!fits || (cnt == lrows && cnt > 0));
+  const unsigned todo = __ballot_sync(kFull, generic && sl == 0);      // bit 8*s: graph s of this warp
+  if (todo) {
+    StGenericArgs& ga = gs.gargs;
+    if (lane == 0) {
+      ga.x = ti.d.x; ga.esrc = ti.d.edge_index; ga.edst = ti.d.edge_index + ti.d.E; ga.z = ti.d.z;
+      ga.lut_batch = ti.d.lut_batch; ga.lut_node = ti.d.lut_node; ga.status = ti.d.status;
+      ga.N = ti.d.N; ga.E = ti.d.E; ga.g0 = ti.g0 + gw * 4;
     }
+    if (sl < 6) ga.p[sg][sl] = st.ptrs[sl >> 1][gl + (sl & 1)];
+  }
+  __syncwarp();
+  if (lane == 0) st_arrive(ebar);                      // the x window is dead: the producer may refill the stage
+  if (todo) {
+    const unsigned t4 = (todo & 1u) | ((todo >> 7) & 2u) | ((todo >> 14) & 4u) | ((todo >> 21) & 8u);
+    st_generic(gs.gargs, gs.gen, t4, prep, lut_col, lane);
   }
 }
 
-template <bool kHeadInKernel>
+template <bool kHeadInKernel, bool kSym>
 __global__ void __launch_bounds__(kStThreads, 1)
 lp_stream_kernel(const qot_lp_batch_t* __restrict__ batches, int n_batches, int64_t tiles_per_batch,
                  int64_t total_tiles, const float* __restrict__ prep, int lut_col) {
@@ -485,38 +634,45 @@ lp_stream_kernel(const qot_lp_batch_t* __restrict__ batches, int n_batches, int6
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.full[s])), "r"(33) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.empty[s])), "r"(kStGroupWarps) : "memory");
     }
+    for (int s = 0; s < kStDStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.dempty[s])), "r"(kStGroupWarps) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid == 0) sm.next_unit = 0;
+  if (tid < 48) (&sm.asp[0][0])[tid] = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + tid);
   __syncthreads();
   if (warp == 0) {
-    st_producer(sm, batches, n_batches, tiles_per_batch, total_tiles, lane);
+    st_producer(sm, batches, n_batches, tiles_per_batch, batches[0].tile0, total_tiles, lane);
     return;
   }
-  // ---- consumers
-  const int cw = warp - 1, q = cw / kStGroupWarps, gw = cw % kStGroupWarps;
-  const int sl = lane & 7;
-  StLaneConst lc;
-#pragma unroll
-  for (int m = 0; m < 6; ++m) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + sl * 6 + m);
-    lc.AsP[m][0] = a.x; lc.AsP[m][1] = a.y; lc.AsP[m][2] = a.z; lc.AsP[m][3] = a.w;
-  }
-#pragma unroll
-  for (int k = 0; k < kF; ++k) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + (sl >> 1) * kF + k);
-    lc.AdP[k][0] = b.x; lc.AdP[k][1] = b.y; lc.AdP[k][2] = b.z; lc.AdP[k][3] = b.w;
-  }
-  const int64_t G = gridDim.x;
-  const int64_t my_tiles = (total_tiles - blockIdx.x + G - 1) / G;
-  for (int64_t k = q; k < my_tiles; k += kStGroups) {
-    const int s = static_cast<int>(k % kStStages);
+  // ---- consumers: every warp claims quarter-tiles (4 graphs) in order from one counter -- no static assignment,
+  // so a slow quarter never idles another warp while stages hold data
+  const int cw = warp - 1;
+  const int my_tiles = static_cast<int>((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  ST_DECL();
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
+    u = __shfl_sync(kFull, u, 0);
+    const int k = u >> 2, gw = u & 3;
+    if (k >= my_tiles) break;
+    const int s = k % kStStages;
     const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
-    if (!st_wait(st_smem_u32(&sm.full[s]), ph)) {
-      if (lane == 0) atomicOr(batches[0].status, 4);
-      return;
+    {
+      ST_T0();
+      if (!st_wait(st_smem_u32(&sm.full[s]), ph)) {
+        if (lane == 0) atomicOr(batches[0].status, 4);
+        return;
+      }
+      ST_ACC(2);
     }
-    st_consume_tile<kHeadInKernel>(sm.stage[s], sm.grp[q], lc, prep, lut_col, gw, lane, st_smem_u32(&sm.empty[s]));
+    const int sd_ = k % kStDStages;
+    ST_T0();
+    st_consume_tile<kHeadInKernel, kSym>(sm.stage[s], sm.dstage[sd_], sm.wsc[cw], sm.asp, prep, lut_col, gw, lane,
+                                         st_smem_u32(&sm.empty[s]), st_smem_u32(&sm.dempty[sd_]));
+    ST_ACC(3);
   }
+  ST_FLUSH();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,16 +791,23 @@ lp_stream_head_kernel(const qot_lp_batch_t* __restrict__ batches, const float* _
 
 using namespace qot;
 
+#ifdef QOT_ST_TRACE
+extern "C" int qot_debug_set_st_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_st_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 extern "C" int64_t qot_lightpath_stream_tiles(int64_t B) { return B > 0 ? cdiv(B, kTG) : 0; }
 
-// `batches`: DEVICE array of n_batches descriptors with tile0 filled (tile0[0] = 0, tile0[b+1] = tile0[b] +
-// qot_lightpath_stream_tiles(B_b)); total_tiles = their sum; uniform_tiles = tiles per batch when every batch
-// but the last has the same count (0: the kernel searches tile0).  max_rows = the largest lut_ptr[B] over
+// `batches`: DEVICE array of n_batches descriptors with tile0 filled (tile0[b+1] = tile0[b] +
+// qot_lightpath_stream_tiles(B_b); tile0[0] is arbitrary, so a sub-range of a longer array can be launched);
+// total_tiles = the tiles of these batches; uniform_tiles = tiles per batch when every batch but the last has
+// the same count (0: the kernel searches tile0).  max_rows = the largest lut_ptr[B] over
 // the batches (an upper bound such as max N is fine): sizes the head grid.  The status words of the batches
 // must be zero on entry (one cudaMemsetAsync over a pooled array does it).
 extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches, int64_t total_tiles,
                                           int64_t uniform_tiles, int64_t max_rows, const float* prepared,
-                                          int32_t is_lut_index, void* stream_) {
+                                          int32_t is_lut_index, int32_t flags, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   QOT_REQUIRE(batches && n_batches > 0 && total_tiles >= 0 && uniform_tiles >= 0 && max_rows >= 0,
               "qot_lightpath_infer_stream: bad argument");
@@ -652,16 +815,22 @@ extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t
               "qot_lightpath_infer_stream: prepared must be 16-byte aligned");
   QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_stream: is_lut_index out of range");
   if (total_tiles == 0) return QOT_OK;
+  QOT_REQUIRE((flags & ~QOT_LP_SYMMETRIC_BY_SOURCE) == 0, "qot_lightpath_infer_stream: unknown flag");
   static std::atomic<unsigned long long> done{0};
   const int smem = static_cast<int>(sizeof(StSmem) + 128);
   if (int rc = once_per_device(done, [smem] {
-        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         return static_cast<int>(QOT_OK);
       }))
     return rc;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(kNumSMs, total_tiles));
-  lp_stream_kernel<false><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles, prepared,
-                                                            is_lut_index);
+  if (flags & QOT_LP_SYMMETRIC_BY_SOURCE)
+    lp_stream_kernel<false, true><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles,
+                                                                    prepared, is_lut_index);
+  else
+    lp_stream_kernel<false, false><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles,
+                                                                     prepared, is_lut_index);
   QOT_LAUNCH_CHECK();
   const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(max_rows, 64), 4 * kNumSMs));
   lp_stream_head_kernel<<<dim3(static_cast<unsigned>(hb), static_cast<unsigned>(n_batches)), 128, 0, stream>>>(batches, prepared);

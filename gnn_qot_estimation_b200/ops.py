@@ -236,6 +236,92 @@ def lightpath_infer(x, edge_index, gptr, eptr, lut_ptr, prepared, is_lut_index: 
 # --------------------------------------------------------------------------- #
 # graph index shared by the layers of one forward/backward
 # --------------------------------------------------------------------------- #
+class LightpathStreamPlan:
+    """Many resident batches evaluated by ONE launch of the persistent kernel (qot_lightpath_infer_stream).
+
+    Built once for a list of batches (each carrying ptr / edge_ptr / lut_ptr): pooled output buffers sized by
+    the batches' readout-row counts (one device->host read of the nb counts here, none afterwards), one
+    status word and one row count per batch, and the DEVICE array of batch descriptors the kernel walks.
+    ``launch(prepared, first, count)`` enqueues batches [first, first+count) on the current stream: no
+    synchronisation, CUDA-graph capturable.  ``result(i)`` gives views of batch i's outputs."""
+
+    def __init__(self, batches, is_lut_index: int):
+        L = _lib.lib()
+        if not batches:
+            raise ValueError("LightpathStreamPlan: no batches")
+        dev = batches[0].x.device
+        for b in batches:
+            if b.ptr is None or b.edge_ptr is None or b.lut_ptr is None or getattr(b, "lut_col", None) != is_lut_index:
+                raise RuntimeError("LightpathStreamPlan needs batches carrying ptr, edge_ptr and lut_ptr for "
+                                   "is_lut_index (PackedGraphStore.collate provides them)")
+            _require_cuda(b.x, b.edge_index, b.ptr, b.edge_ptr, b.lut_ptr)
+        self.batches = list(batches)                 # keeps the input tensors alive
+        self.is_lut_index = int(is_lut_index)
+        # QOT_LP_SYMMETRIC_BY_SOURCE only when EVERY batch carries the verified-layout mark
+        self.flags = 1 if all(getattr(b, "sym_by_src", False) for b in batches) else 0
+        nb = len(batches)
+        rows = torch.stack([b.lut_ptr[-1] for b in batches]).tolist()          # the one sync
+        self.rows = [int(r) for r in rows]
+        cap = [max(r, 1) for r in self.rows]
+        off = [0]
+        for c in cap:
+            off.append(off[-1] + c)
+        tot = off[-1]
+        self.out = torch.empty(tot, 3, dtype=torch.float32, device=dev)
+        self.lut_batch = torch.empty(tot, dtype=torch.int64, device=dev)
+        self.lut_node = torch.empty(tot, dtype=torch.int32, device=dev)
+        self.z = torch.empty(tot, 20, dtype=torch.float32, device=dev)
+        self.n_lut = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.off = off
+        self.keep = []
+        descs = (_lib.QotLpBatch * nb)()
+        tile0 = [0]
+        for i, b in enumerate(batches):
+            x, ei = _f32(b.x), _i64(b.edge_index)
+            gp, ep, lp = _i64(b.ptr), _i64(b.edge_ptr), _i64(b.lut_ptr)
+            self.keep += [x, ei, gp, ep, lp]
+            d = descs[i]
+            d.x, d.edge_index, d.ptr, d.edge_ptr, d.lut_ptr = ptr(x), ptr(ei), ptr(gp), ptr(ep), ptr(lp)
+            d.N, d.E, d.B = int(x.shape[0]), int(ei.shape[1]), int(gp.numel() - 1)
+            o = off[i]
+            d.out = self.out.data_ptr() + o * 12
+            d.lut_batch = self.lut_batch.data_ptr() + o * 8
+            d.lut_node = self.lut_node.data_ptr() + o * 4
+            d.n_lut = self.n_lut.data_ptr() + i * 4
+            d.status = self.status.data_ptr() + i * 4
+            d.z = self.z.data_ptr() + o * 80
+            d.tile0 = tile0[-1]
+            tile0.append(tile0[-1] + int(L.qot_lightpath_stream_tiles(d.B)))
+        self.tile0 = tile0
+        self.desc_size = C.sizeof(_lib.QotLpBatch)
+        raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+        self.descs = raw.to(dev)
+        _track_status("qot_lightpath_infer_stream (lut_ptr does not describe x, or a pipeline barrier timed out)",
+                      self.status)
+
+    def __len__(self):
+        return len(self.batches)
+
+    def launch(self, prepared: torch.Tensor, first: int = 0, count: Optional[int] = None) -> None:
+        nb = len(self.batches)
+        count = nb - first if count is None else count
+        if first < 0 or count <= 0 or first + count > nb:
+            raise ValueError(f"LightpathStreamPlan.launch: range [{first}, {first + count}) outside [0, {nb})")
+        tiles = [self.tile0[i + 1] - self.tile0[i] for i in range(first, first + count)]
+        uniform = tiles[0] if all(t == tiles[0] for t in tiles[:-1]) and tiles[-1] <= tiles[0] else 0
+        self.status[first:first + count].zero_()
+        check(_lib.lib().qot_lightpath_infer_stream(
+            self.descs.data_ptr() + first * self.desc_size, count, self.tile0[first + count] - self.tile0[first],
+            uniform, max(self.rows[first:first + count]), ptr(prepared), self.is_lut_index, self.flags, stream()),
+            "qot_lightpath_infer_stream")
+
+    def result(self, i: int) -> LightpathInferOut:
+        a, b = self.off[i], self.off[i + 1]
+        return LightpathInferOut(self.out[a:b], self.lut_batch[a:b], self.lut_node[a:b], self.n_lut[i:i + 1],
+                                 self.status[i:i + 1])
+
+
 class GraphIndex:
     """Lazily built, cached index structures of one batch: the destination-sorted CSR
     (forward), its GAT variant (self loops replaced) and the source-sorted transposed

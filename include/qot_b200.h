@@ -305,6 +305,47 @@ int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
                         float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
                         int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
+/* The same forward over MANY batches in ONE launch of a persistent, warp-specialised kernel
+ * (lp_stream_kernel, csrc/lightpath_stream.cu): the streaming form of the evaluation loop
+ * lightpath_training/test.py:77-94 for batches already resident in HBM.  A batch is described by a
+ * qot_lp_batch_t (reference layout, every pointer a device pointer); the caller keeps an array of them
+ * in DEVICE memory, 16-byte aligned.  Work is cut into tiles of 16 consecutive graphs; tile0 of descriptor b is the number
+ * of tiles before it (tile0[0] = 0, tile0[b+1] = tile0[b] + qot_lightpath_stream_tiles(B_b)).
+ *   z       per-batch scratch of at least 20 floats per readout row (qot_lightpath_infer_workspace_bytes(N));
+ *   status  one int32 per batch, ZERO on entry (pool them and clear the pool with one memset);
+ *           bit 0: lut_ptr does not describe x, bit 2: a pipeline barrier timed out.
+ * uniform_tiles: tiles per batch when every batch but the last has the same count, else 0 (the kernel
+ * then searches tile0).  max_rows: an upper bound of lut_ptr[B] over the batches.  Outputs per batch as
+ * qot_lightpath_infer.  Values equal qot_lightpath_infer's to fp32 round-off (same attention
+ * arithmetic; the readout head sums in a different order). */
+typedef struct qot_lp_batch {
+  const float* x;              /* [N,5]                                       */
+  const int64_t* edge_index;   /* [2,E]: source row, destination row          */
+  const int64_t* ptr;          /* [B+1] node offsets                          */
+  const int64_t* edge_ptr;     /* [B+1] edge offsets                          */
+  const int64_t* lut_ptr;      /* [B+1] readout-row offsets                   */
+  int64_t N, E, B;
+  float* out;                  /* [>= L,3]                                    */
+  int64_t* lut_batch;          /* [>= L]                                      */
+  int32_t* lut_node;           /* [>= L]                                      */
+  int32_t* n_lut;              /* [1]                                         */
+  int32_t* status;             /* [1]                                         */
+  float* z;                    /* [>= L,20] scratch                           */
+  int64_t tile0;               /* first tile of this batch inside the launch  */
+  int64_t reserved;            /* pads the descriptor to 128 bytes (it is copied as eight 16-byte pieces); 0 */
+} qot_lp_batch_t;
+/* flags: QOT_LP_SYMMETRIC_BY_SOURCE -- the caller has VERIFIED, for every graph of every batch of the launch,
+ * the layout torch_geometric.utils.from_networkx gives an undirected nx.Graph (lightpath_training/dataset.py:86,
+ * SURVEY.md A.6): edges grouped by source node ascending, every edge present in both directions, no duplicate
+ * (source, destination) pair (PackedGraphStore.verify_layout does the check once per store).  The sources of a
+ * node's in-edges are then the destinations of its own out-run, which the kernel locates by counting over the
+ * destination row alone: the source row of edge_index is never read.  Same rows, bit-identical values. */
+#define QOT_LP_SYMMETRIC_BY_SOURCE 1
+int64_t qot_lightpath_stream_tiles(int64_t B);
+int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches, int64_t total_tiles,
+                               int64_t uniform_tiles, int64_t max_rows, const float* prepared,
+                               int32_t is_lut_index, int32_t flags, void* stream);
+
 /* Kernel variant behind qot_lightpath_infer[_host]: 0 = one warp per graph, 1 = 8 lanes per graph in
  * the scan / attention phase + block-wide two-row heads, 2 (default) = 8 lanes per graph with the
  * block's node / destination slabs moved by bulk async copies and the readout head on the tensor

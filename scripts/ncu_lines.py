@@ -4,7 +4,7 @@ import collections, csv, io, re, subprocess, sys, tempfile, os
 rep, cubin_sub, kern_sub, srcfile = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath("gnn_qot_estimation_b200/libqot_b200.so")], cwd=tmp, check=True, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("NCU_LINES_SO", os.path.abspath("gnn_qot_estimation_b200/libqot_b200.so"))], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if cubin_sub in f][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 starts = [i for i, l in enumerate(sass) if l.startswith(".text.")]

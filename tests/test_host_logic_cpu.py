@@ -180,3 +180,34 @@ def test_sources_follow_from_the_destination_histogram_on_from_networkx_layouts(
         src, dst = st.edge_src[e0:e1].numpy(), st.edge_dst[e0:e1].numpy()
         outptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=n))])
         assert np.array_equal(np.searchsorted(outptr, np.arange(e1 - e0), side="right") - 1, src)
+
+
+def test_verify_layout_accepts_from_networkx_order_and_rejects_violations():
+    """PackedGraphStore.verify_layout: the synthetic generators emit the from_networkx layout (grouped by
+    source ascending, symmetric, simple); a swapped pair, a dropped direction or a duplicate must fail."""
+    import torch
+    from gnn_qot_estimation_b200 import synthetic
+    from gnn_qot_estimation_b200.batch import PackedGraphStore
+    st = synthetic.lightpath_store(50, seed=3)
+    assert st.verify_layout() and st.sym_by_src
+    assert st.host_batch(0, 10).sym_by_src
+    assert synthetic.nsfnet_store(4).verify_layout()
+
+    def clone(**kw):
+        f = dict(node_ptr=st.node_ptr, edge_ptr=st.edge_ptr, edge_src=st.edge_src.clone(), edge_dst=st.edge_dst.clone(),
+                 node_feat=st.node_feat, y=st.y, lut_col=1)
+        f.update(kw)
+        return PackedGraphStore(f["node_ptr"], f["edge_ptr"], f["edge_src"], f["edge_dst"], f["node_feat"], None, f["y"], f["lut_col"])
+    e0, e1 = int(st.edge_ptr[0]), int(st.edge_ptr[1])
+    # not grouped by source: reverse the edge order of graph 0
+    s, d = st.edge_src.clone(), st.edge_dst.clone()
+    s[e0:e1], d[e0:e1] = st.edge_src[e0:e1].flip(0), st.edge_dst[e0:e1].flip(0)
+    assert not clone(edge_src=s, edge_dst=d).verify_layout()
+    # one direction rewired: no longer symmetric
+    d = st.edge_dst.clone()
+    d[e0] = (d[e0] + 1) % int(st.node_ptr[1])
+    assert not clone(edge_dst=d).verify_layout()
+    # endpoint outside the graph
+    d = st.edge_dst.clone()
+    d[e0] = 1000
+    assert not clone(edge_dst=d).verify_layout()

@@ -1,0 +1,175 @@
+"""GPU parity of the persistent multi-batch LightpathGNN eval kernel (csrc/lightpath_stream.cu,
+qot_lightpath_infer_stream through LightpathGNN.stream_plan / forward_stream) against the fp64 oracle
+(1e-5 relative, BASELINE.json north_star; element-wise with an absolute floor of 1e-6) and against the
+one-launch-per-batch module path (same rows, same order, values equal to fp32 round-off)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _model(dev, name="ckpt_lightpath_model_1.pt"):
+    from gnn_qot_estimation_b200 import LightpathGNN
+    sd = load_golden(name)["model_state_dict"]
+    m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0)
+    m.load_state_dict(sd, strict=True)
+    return m.to(dev).eval(), sd
+
+
+def _oracle64(sd):
+    from oracle import LightpathGNNOracle
+    m = LightpathGNNOracle(5, 32, 3, is_lut_index=1, dropout_p=0.0).double()
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def _to64(b):
+    bb = b.to("cpu")
+    bb.x = bb.x.double()
+    return bb
+
+
+def _check(plan, i, model, oracle, hb, dev):
+    r = plan.result(i)
+    n = int(r.n_lut.item())
+    assert int(r.status.item()) == 0
+    with torch.no_grad():
+        eo, el = oracle(_to64(hb))
+        mo, ml = model(hb.to(dev))
+    assert n == el.numel()
+    assert torch.equal(r.lut_batch[:n].cpu(), el)                           # bit-exact indexing
+    assert torch.equal(r.lut_batch[:n], ml)
+    assert rel_err(r.out[:n], eo) <= RTOL
+    torch.testing.assert_close(r.out[:n].cpu().double(), eo, rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(r.out[:n], mo, rtol=2e-6, atol=1e-6)         # same arithmetic up to the head's sum order
+
+
+@pytest.mark.parametrize("verified", [False, True])
+@pytest.mark.parametrize("sizes", [[1], [16], [17, 1, 300], [512, 512, 512, 100], [4096, 4096, 333]])
+def test_stream_vs_oracle_and_module(cuda, sizes, verified):
+    """`verified`: the store checked the from_networkx layout once (PackedGraphStore.verify_layout), the kernel
+    then derives the sources of the LUT row from the destination row alone (QOT_LP_SYMMETRIC_BY_SOURCE) --
+    bit-identical to the launch that reads the source row."""
+    from gnn_qot_estimation_b200 import synthetic
+    m, sd = _model(cuda)
+    o = _oracle64(sd)
+    G = sum(sizes)
+    store = synthetic.lightpath_store(G, seed=7 + len(sizes), device="cpu", lut_per_graph=1)
+    dstore = store.to(cuda)
+    if verified:
+        assert dstore.verify_layout()
+    hbs, dbs, g0 = [], [], 0
+    for s in sizes:
+        hbs.append(store.host_batch(g0, g0 + s))
+        dbs.append(dstore.collate(range(g0, g0 + s)))
+        g0 += s
+    plan = m.stream_plan(dbs)
+    assert plan.flags == (1 if verified else 0)
+    m.forward_stream(plan)
+    torch.cuda.synchronize()
+    for i in range(len(sizes)):
+        _check(plan, i, m, o, hbs[i], cuda)
+    if verified:                                   # same bits as the launch that gathers from the source row
+        for b in dbs:
+            b.sym_by_src = False
+        plan2 = m.stream_plan(dbs)
+        m.forward_stream(plan2)
+        torch.cuda.synchronize()
+        assert torch.equal(plan.out, plan2.out) and torch.equal(plan.lut_batch, plan2.lut_batch)
+        assert torch.equal(plan.lut_node, plan2.lut_node)
+    # a sub-range launch (non-zero first tile) rewrites only its own batches, identically
+    if len(sizes) > 2:
+        before = plan.out.clone()
+        plan.out[plan.off[1]:plan.off[3]].fill_(float("nan"))
+        m.forward_stream(plan, 1, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(plan.out, before)
+
+
+def test_stream_multi_lut_and_replay_determinism(cuda):
+    from gnn_qot_estimation_b200 import synthetic
+    m, sd = _model(cuda, "ckpt_lightpath_model_0.pt")
+    o = _oracle64(sd)
+    store = synthetic.lightpath_store(700, seed=21, device="cpu", lut_per_graph=2)   # generic path: 2 rows per graph
+    dstore = store.to(cuda)
+    hbs = [store.host_batch(0, 400), store.host_batch(400, 700)]
+    dbs = [dstore.collate(range(0, 400)), dstore.collate(range(400, 700))]
+    plan = m.stream_plan(dbs)
+    m.forward_stream(plan)
+    torch.cuda.synchronize()
+    first = plan.out.clone()
+    for i in range(2):
+        _check(plan, i, m, o, hbs[i], cuda)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        m.forward_stream(plan)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            m.forward_stream(plan)
+        plan.out.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.out, first)                                     # capturable and bit-reproducible
+
+
+def test_stream_edge_cases(cuda):
+    """Graphs over the fast-path caps (n > 64), zero-edge graphs, self loops / duplicate edges, a LUT row with
+    more in-edges than the fast path keeps (hub), graphs without a LUT node, several LUT nodes: the generic
+    path inside the same launch; rows stay in ascending node order."""
+    from gnn_qot_estimation_b200 import Batch, ops
+    m, sd = _model(cuda, "ckpt_lightpath_model_0.pt")
+    o = _oracle64(sd)
+    g = torch.Generator().manual_seed(0)
+    sizes = [1, 3, 70, 40, 2, 30, 25, 9] + [12] * 20
+    xs, eis, bts, ptr, eptr = [], [], [], [0], [0]
+    off = 0
+    for gi, n in enumerate(sizes):
+        x = torch.rand(n, 5, generator=g)
+        x[:, 1] = 0.0
+        if gi != 5:
+            x[n // 2, 1] = 1.0                  # graph 5: no LUT node at all
+        if gi == 2:
+            x[5, 1] = 1.0
+            x[66, 1] = 1.0
+        E = 0 if gi in (0, 4) else 6 * n
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = torch.randint(0, n, (E,), generator=g)   # includes self loops and duplicates
+        if gi == 6:
+            dst[:60] = n // 2                   # hub: 60 in-edges on the LUT row
+        eis.append(torch.stack([src, dst]) + off)
+        xs.append(x)
+        bts.append(torch.full((n,), gi, dtype=torch.int64))
+        off += n
+        ptr.append(off)
+        eptr.append(eptr[-1] + E)
+    x = torch.cat(xs)
+    hb = Batch(x=x, edge_index=torch.cat(eis, 1), batch=torch.cat(bts), num_graphs=len(sizes),
+               ptr=torch.tensor(ptr), edge_ptr=torch.tensor(eptr), lut_col=1)
+    db = hb.to(cuda)
+    db.lut_ptr = ops.lightpath_lut_ptr(db.x, db.ptr, 1)
+    hb.lut_ptr = db.lut_ptr.cpu()
+    plan = m.stream_plan([db])
+    m.forward_stream(plan)
+    torch.cuda.synchronize()
+    _check(plan, 0, m, o, hb, cuda)
+
+
+def test_stream_flags_stale_lut_ptr_and_clears(cuda):
+    from gnn_qot_estimation_b200 import synthetic
+    m, _ = _model(cuda)
+    store = synthetic.lightpath_store(64, seed=3, device="cpu").to(cuda)
+    db = store.collate(range(0, 64))
+    plan = m.stream_plan([db])
+    saved = db.x[:, 1].clone()
+    db.x[:, 1] = 0.0                            # x edited after the collate: lut_ptr is stale
+    m.forward_stream(plan)
+    torch.cuda.synchronize()
+    assert int(plan.status[0].item()) & 1
+    db.x[:, 1] = saved
+    m.forward_stream(plan)                      # the status word is cleared by the next launch
+    torch.cuda.synchronize()
+    assert int(plan.status[0].item()) == 0
