@@ -31,7 +31,12 @@ constexpr int kOffB2f = kOffB1f + 16 * 32 * 4;          // [ktile 16][ntile 4][l
 // attention vectors in the per-lane slot order of lp_attn_kernel (see there)
 constexpr int kOffAsP = kOffB2f + 16 * 4 * 32 * 4;      // [sl 8][slot 6][head slot 4]
 constexpr int kOffAdP = kOffAsP + 8 * 6 * 4;            // [sl>>1 4][f 5][head slot 4]
-constexpr int kPreparedFloats = kOffAdP + 4 * kF * 4;
+// mlp.0 weight as the B operand of tcgen05.mma kind::tf32 (lp_stream_kernel's readout head): [hi | lo][k-block 4]
+// [row n 32][32 floats], K-major with the 128-byte swizzle the UMMA shared-memory descriptor names (16-byte chunk c of
+// row n stored at chunk c ^ (n & 7)); hi = round-to-TF32, lo = TF32 of the residual.  4096-byte aligned in `prepared`.
+constexpr int kOffB2sw = ((kOffAdP + 4 * kF * 4 + 1023) / 1024) * 1024;
+constexpr int kB2swFloats = 2 * 4 * 32 * 32;
+constexpr int kPreparedFloats = kOffB2sw + kB2swFloats;
 
 __device__ __forceinline__ unsigned tf32_rna(float v) {
   unsigned r;

@@ -73,6 +73,16 @@ lp_prepare_kernel(qot_lightpath_params_t p, float* __restrict__ out) {
     const float b1 = (t4 == 0) ? p.lin_w[c * kF + 4] * scale : (t4 == 1) ? shift : 0.f;
     reinterpret_cast<float4*>(out + kOffB1f)[i] = tf32_split2(b0, b1);
   }
+  // mlp.0 weight in the swizzled K-major tcgen05 operand layout (lightpath_common.cuh: kOffB2sw)
+  for (int i = t; i < 4 * 32 * 32; i += blockDim.x) {
+    const int kb = i >> 10, n = (i >> 5) & 31, kk = i & 31;       // k = 32 kb + kk
+    const int c = kk >> 2, j = kk & 3;
+    const float w = p.mlp_w1[n * kHC + kb * 32 + kk];
+    const float hi = __uint_as_float(tf32_rna(w));
+    const int o = kb * 1024 + n * 32 + ((c ^ (n & 7)) << 2) + j;
+    out[kOffB2sw + o] = hi;
+    out[kOffB2sw + 4096 + o] = __uint_as_float(tf32_rna(w - hi));
+  }
   for (int i = t; i < 16 * 4 * 32; i += blockDim.x) {
     const int j = i >> 7, q = (i >> 5) & 3, ln = i & 31, g8 = ln >> 2, t4 = ln & 3;
     // k slot t4 <-> channel 8j + 2*t4, slot t4 + 4 <-> channel 8j + 2*t4 + 1: the C fragment of the

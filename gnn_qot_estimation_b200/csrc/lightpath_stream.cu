@@ -25,6 +25,7 @@
 // one-launch-per-batch kernel (extents -> slabs -> sources) overlap across tiles instead of
 // serialising inside a CTA.  Deterministic: edges of a row are consumed in edge order, fixed trees.
 #include <algorithm>
+#include <type_traits>
 
 #include "lightpath_common.cuh"
 
@@ -34,6 +35,9 @@ constexpr int kTG = 16;                    // graphs per tile
 constexpr int kTNodes = 704;               // x window: mean 512 nodes + 3.4 sigma (sigma = 4 * 14.1)
 constexpr int kTEdges = 2688;              // destination window: mean 1984 edges + 3.1 sigma
 constexpr int kTMaxE = 248;                // per graph: 8 lanes x 31 contiguous edges (bit mask per lane)
+// Two builds of the kernel.  kHead = false: consumers write z rows to the batch's workspace and lp_stream_head_kernel
+// finishes them (one more launch).  kHead = true (default): the readout head runs INSIDE the kernel on the 5th-generation
+// tensor cores -- four epilogue warps + one MMA-issuing warp per CTA, accumulators in TMEM (see st_head_epilogue).
 #ifndef QOT_ST_WARPS
 #define QOT_ST_WARPS 15
 #endif
@@ -43,15 +47,32 @@ constexpr int kTMaxE = 248;                // per graph: 8 lanes x 31 contiguous
 #ifndef QOT_ST_DSTAGES
 #define QOT_ST_DSTAGES 4
 #endif
-constexpr int kStStages = QOT_ST_XSTAGES;  // x ring: a stage lives until its tile's attention rows are out
-constexpr int kStDStages = QOT_ST_DSTAGES; // destination ring: a stage is dead as soon as the tile has been scanned
+#ifndef QOT_STH_WARPS
+#define QOT_STH_WARPS 14
+#endif
+#ifndef QOT_STH_XSTAGES
+#define QOT_STH_XSTAGES 6
+#endif
+#ifndef QOT_STH_DSTAGES
+#define QOT_STH_DSTAGES 3
+#endif
+template <bool kHead> struct StCfg;
+template <> struct StCfg<false> {
+  static constexpr int kX = QOT_ST_XSTAGES;      // x ring: a stage lives until its tile's attention rows are out
+  static constexpr int kD = QOT_ST_DSTAGES;      // destination ring: a stage is dead as soon as the tile has been scanned
+  static constexpr int kConsumers = QOT_ST_WARPS;
+  static constexpr int kThreads = 32 * (1 + kConsumers);          // warp 0 producer, the rest consumers
+};
+template <> struct StCfg<true> {
+  static constexpr int kX = QOT_STH_XSTAGES;
+  static constexpr int kD = QOT_STH_DSTAGES;
+  static constexpr int kConsumers = QOT_STH_WARPS;
+  // warp 0 producer, 1 MMA issuer, 2-3 consumers, 4-7 epilogue (TMEM lane quarter = warp - 4), 8.. consumers
+  static constexpr int kThreads = 32 * (8 + kConsumers - 2);
+};
 constexpr int kStGroupWarps = 4;           // a tile = 4 quarter-tiles of 4 graphs; a consumer warp takes one at a time
-constexpr int kStConsumerWarps = QOT_ST_WARPS;
-constexpr int kStThreads = 32 * (1 + kStConsumerWarps);
 constexpr int kStXBytes = kTNodes * kF * 4;
 constexpr int kStDBytes = kTEdges * 8;
-constexpr unsigned kStSpin = 1u << 22;     // polls (each may sleep up to the suspend hint): a wedged barrier ends the kernel
-                                           // (status bit 4), never hangs it
 
 struct alignas(16) StTileInfo {
   qot_lp_batch_t d;                        // the batch descriptor, copied asynchronously with the index rows
@@ -78,6 +99,7 @@ struct StGenericArgs {                     // tile fields the generic path needs
   const int64_t* esrc;
   const int64_t* edst;
   float* z;
+  float* out;
   int64_t* lut_batch;
   int32_t* lut_node;
   int32_t* status;
@@ -89,32 +111,77 @@ struct StWarpScratch {                     // per consumer warp
   StGenericArgs gargs;
   int msg[4][kSubMsg];
   int raw[4][kSubMsg];                     // kSym: the LUT node's out-run before ranking
-  float gen[128];                          // generic path: z (32 floats) + message list (64 ints)
 };
 
-struct StSmem {
-  StDStage dstage[kStDStages];             // first: the scan's masked over-reads past a window stay inside the block
-  StStage stage[kStStages];
-  float4 asp[8][6];                        // attention source vectors per lane slot (lp_prepare_kernel's kOffAsP table)
-  StWarpScratch wsc[kStConsumerWarps];
-  alignas(8) unsigned long long full[kStStages];    // x window + destination window + index rows of a tile landed
-  alignas(8) unsigned long long empty[kStStages];   // x stage released (4 consumer warps)
-  alignas(8) unsigned long long dempty[kStDStages]; // destination stage released (4 consumer warps)
-  int next_unit;                                    // quarter-tiles handed out so far (consumer warps claim them in order)
+constexpr int kZPitch = 21;                // floats per staged z row (odd: the epilogue's row-per-lane reads hit 32 banks)
+constexpr int kGroupTiles = 8;             // tiles per readout group: 8 x 16 graphs = the 128 rows of one MMA
+// shared memory of the in-kernel readout head
+struct StHeadSmem {
+  alignas(1024) float b2[2][4][32 * 32];   // mlp.0 weight, tcgen05 B operand: [hi | lo][k-block][row n][32 floats], swizzled
+  float zrow[2][128 * kZPitch];            // z rows of a group (double buffered), row = (tile % 8) * 16 + graph slot
+  float* optr[2][128];                     // where the row's 3 outputs go; nullptr: the slot holds no row
+  alignas(8) unsigned long long zfull[2];  // 32 quarter-tile arrivals: the group's rows are staged
+  alignas(8) unsigned long long zfree[2];  // 4 epilogue warps: the buffer has been read
+  alignas(8) unsigned long long aready;    // 4 epilogue warps: the A operand (hidden activations) is in TMEM
+  alignas(8) unsigned long long dready;    // tcgen05.commit: the accumulator is complete
+  unsigned tmem_base;
+  // readout-head parameters read by every epilogue thread (broadcast): with ~225 KB of the SM's 256 KB configured as
+  // shared memory almost no L1 is left, so nothing on a hot path may depend on cached global loads
+  alignas(16) float wf[kHC * kF];          // [h][f][32]: folded GAT projection (BN scale inside)
+  alignas(16) float shift[kHC];
+  alignas(16) float b1[kHid];
+  alignas(16) float w2[QOT_OUT * kHid];
+  float bo[4];
 };
-static_assert(sizeof(StSmem) + 1024 <= 227 * 1024, "lp_stream_kernel: shared memory over the 227 KB block limit");
+struct StNoHead {};
+
+template <bool kHead>
+struct StSmemT {
+  typename std::conditional<kHead, StHeadSmem, StNoHead>::type head;   // first: 1024-byte aligned operand tiles
+  StDStage dstage[StCfg<kHead>::kD];       // before the x ring: the scan's masked over-reads past a window stay inside the block
+  StStage stage[StCfg<kHead>::kX];
+  float4 asp[8][6];                        // attention source vectors per lane slot (lp_prepare_kernel's kOffAsP table)
+  float4 adp[4][kF];                       // attention destination vectors per head-slot group (kOffAdP table)
+  StWarpScratch wsc[StCfg<kHead>::kConsumers];
+  float gen[256];                          // generic path scratch (one graph at a time per CTA, under gen_lock)
+  alignas(8) unsigned long long full[StCfg<kHead>::kX];    // x window + destination window + index rows of a tile landed
+  alignas(8) unsigned long long empty[StCfg<kHead>::kX];   // x stage released (4 quarter-tiles)
+  alignas(8) unsigned long long dempty[StCfg<kHead>::kD];  // destination stage released (4 quarter-tiles)
+  int next_unit;                           // quarter-tiles handed out so far (consumer warps claim them in order)
+  int gen_lock;
+};
+// Every function reaches the block's shared memory through this accessor (not through a reference parameter): the
+// address then provably lies in the shared window and the compiler emits LDS / STS / ATOMS instead of generic
+// LD / ST / ATOM, which cost an address-space check and the long-scoreboard path on every access.
+extern __shared__ __align__(1024) char st_smem_raw[];
+template <bool kHead>
+__device__ __forceinline__ StSmemT<kHead>& st_smem() {
+  const unsigned off = (1024u - (static_cast<unsigned>(__cvta_generic_to_shared(st_smem_raw)) & 1023u)) & 1023u;
+  return *reinterpret_cast<StSmemT<kHead>*>(st_smem_raw + off);
+}
+static_assert(sizeof(StSmemT<false>) + 1024 <= 227 * 1024, "lp_stream_kernel: shared memory over the 227 KB block limit");
+static_assert(sizeof(StSmemT<true>) + 1024 <= 227 * 1024, "lp_stream_kernel<head>: shared memory over the 227 KB block limit");
 
 #ifdef QOT_ST_TRACE
 // debug build only (scripts/build_variant.sh ... -DQOT_ST_TRACE): per-CTA cycle sums, 8 slots per CTA:
-// 0 producer wait-empty, 1 producer issue, 2 consumer wait-full (all warps), 3 consumer work, 4 tiles, 5 total
+// 0 producer wait-empty, 1 producer issue, 2 consumer wait-full (all warps), 3 consumer work (incl. 4), 4 consumer wait for
+// a free z buffer, 5 epilogue wait for a staged group, 6 epilogue wait for the MMAs, 7 epilogue total
 __device__ unsigned long long* g_st_trace = nullptr;
-#define ST_DECL() long long st_acc_[4] = {0, 0, 0, 0}
+#define ST_DECL() long long st_acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define ST_T0() const long long st_t0_ = clock64()
+#define ST_T1() const long long st_t1_ = clock64()
+#define ST_PARAM , long long* st_acc_
+#define ST_ARG , st_acc_
+#define ST_ACC1(slot) do { st_acc_[slot] += clock64() - st_t1_; } while (0)
 #define ST_ACC(slot) do { st_acc_[slot] += clock64() - st_t0_; } while (0)
-#define ST_FLUSH() do { if (g_st_trace && lane == 0) for (int i_ = 0; i_ < 4; ++i_) if (st_acc_[i_]) atomicAdd(g_st_trace + blockIdx.x * 8 + i_, static_cast<unsigned long long>(st_acc_[i_])); } while (0)
+#define ST_FLUSH() do { if (g_st_trace && lane == 0) for (int i_ = 0; i_ < 8; ++i_) if (st_acc_[i_]) atomicAdd(g_st_trace + blockIdx.x * 8 + i_, static_cast<unsigned long long>(st_acc_[i_])); } while (0)
 #else
 #define ST_DECL() do {} while (0)
 #define ST_T0() do {} while (0)
+#define ST_T1() do {} while (0)
+#define ST_PARAM
+#define ST_ARG
+#define ST_ACC1(slot) do {} while (0)
 #define ST_ACC(slot) do {} while (0)
 #define ST_FLUSH() do {} while (0)
 #endif
@@ -132,13 +199,25 @@ __device__ __forceinline__ bool st_try_wait(unsigned bar, unsigned parity) {
       : "=r"(ok) : "r"(bar), "r"(parity), "r"(QOT_ST_SUSPEND_NS) : "memory");
   return ok != 0u;
 }
+// bounded wait: a wedged barrier ends the kernel after ~2 s of wall clock (status bit 2), it never hangs the GPU
 __device__ __forceinline__ bool st_wait(unsigned bar, unsigned parity) {
-  for (unsigned spin = 0; spin < kStSpin; ++spin)
-    if (st_try_wait(bar, parity)) return true;
-  return false;
+  if (st_try_wait(bar, parity)) return true;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i)
+      if (st_try_wait(bar, parity)) return true;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) return false;
+  }
 }
 __device__ __forceinline__ void st_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count) : "memory");
 }
 
 // descriptor of the batch tile T of the launch belongs to (uniform tile count per batch, or prefix search)
@@ -156,8 +235,10 @@ __device__ __forceinline__ int st_batch_of(const qot_lp_batch_t* __restrict__ bt
 // ------------------------------------------------------------------------------------------------
 // producer: one warp
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb,
+template <bool kHead>
+__device__ __noinline__ void st_producer(const qot_lp_batch_t* __restrict__ bt, int nb, int64_t tpb,
                                          int64_t tile_base, int64_t total_tiles, int lane) {
+  StSmemT<kHead>& sm = st_smem<kHead>();
   const int64_t G = gridDim.x;
   const int64_t my_tiles = (total_tiles - blockIdx.x + G - 1) / G;
   ST_DECL();
@@ -183,6 +264,7 @@ __device__ __noinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __res
     const int cnt = static_cast<int>(min(static_cast<int64_t>(32), my_tiles - kb));
     for (int j = 0; j < cnt; ++j) {
       const int64_t k = kb + j;
+      constexpr int kStStages = StCfg<kHead>::kX, kStDStages = StCfg<kHead>::kD;
       const int s = static_cast<int>(k % kStStages);
       const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
       StStage& st = sm.stage[s];
@@ -263,17 +345,27 @@ __device__ __noinline__ void st_producer(StSmem& sm, const qot_lp_batch_t* __res
 }
 
 // generic path: graphs of this warp the fast path declined (over the caps, several / no LUT rows, hub rows,
-// foreign ids): one warp per graph, straight from global memory, z rows into the batch's workspace
-__device__ __noinline__ void st_generic(const StGenericArgs& ga, float* scratch, unsigned todo,
-                                        const float* __restrict__ prep, int lut_col, int lane) {
+// foreign ids): one warp per graph, straight from global memory.  kHead: the FP32 readout head of the row runs here
+// too and writes `out`; otherwise the z row goes to the batch's workspace for lp_stream_head_kernel.  The scratch is
+// one per CTA (these graphs are rare), taken under a lock.
+template <bool kHead>
+__device__ __noinline__ void st_generic(int cw, unsigned todo, const float* __restrict__ prep, int lut_col, int lane) {
+  StSmemT<kHead>& sm = st_smem<kHead>();
+  const StGenericArgs& ga = sm.wsc[cw].gargs;
+  float* scratch = sm.gen;
+  int* lock = &sm.gen_lock;
   const float* gx = ga.x;
   const int64_t N = ga.N;
+  if (lane == 0)
+    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(200);
+  __syncwarp();
+  float* s_y = scratch;                    // 128 floats (kHead)
+  float* s_z = scratch + 128;              // 32
+  int* s_m = reinterpret_cast<int*>(scratch + 160);   // 64
 #pragma unroll 1
   for (int s = 0; s < 4; ++s) {
     if (!((todo >> s) & 1u)) continue;
     const int64_t gn0 = ga.p[s][0], gn1 = ga.p[s][1], ge0 = ga.p[s][2], ge1 = ga.p[s][3], gl0 = ga.p[s][4], gl1 = ga.p[s][5];
-    float* s_z = scratch;
-    int* s_m = reinterpret_cast<int*>(scratch + 32);
     int64_t orow = gl0;
     int found = 0;
     if (gn0 >= 0 && gn1 <= N && ge0 >= 0 && ge1 <= ga.E) {
@@ -286,8 +378,13 @@ __device__ __noinline__ void st_generic(const StGenericArgs& ga, float* scratch,
           ++found;
           if (orow < gl1) {                                      // never write past this graph's rows
             const int64_t i = nbq + bit;
-            lut_row_global<false>(gx, ga.esrc, ga.edst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
-            if (lane < kHeads * kF) ga.z[orow * (kHeads * kF) + lane] = s_z[(lane / kF) * 8 + lane % kF];
+            if constexpr (kHead) {
+              const float ov = lut_row_global<true>(gx, ga.esrc, ga.edst, ge0, ge1, N, i, prep, prep + kOffWf, s_m, s_z, s_y, lane);
+              if (lane < QOT_OUT) ga.out[orow * QOT_OUT + lane] = ov;
+            } else {
+              lut_row_global<false>(gx, ga.esrc, ga.edst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
+              if (lane < kHeads * kF) ga.z[orow * (kHeads * kF) + lane] = s_z[(lane / kF) * 8 + lane % kF];
+            }
             if (lane == 0) {
               ga.lut_batch[orow] = ga.g0 + s;
               ga.lut_node[orow] = static_cast<int32_t>(i);
@@ -300,14 +397,24 @@ __device__ __noinline__ void st_generic(const StGenericArgs& ga, float* scratch,
     }
     if (lane == 0 && found != gl1 - gl0) atomicOr(ga.status, 1);
   }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicExch(lock, 0);
+  }
 }
 
 // One tile.  Everything per graph is kept as 32-bit offsets inside the tile's windows (the 64-bit index rows stay in
 // the stage and are re-read where a global index is needed): registers are what bounds the consumer-warp count.
-template <bool kHeadInKernel, bool kSym>
-__device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dstg, StWarpScratch& gs,
-                                                const float4 (*__restrict__ asp)[6], const float* __restrict__ prep,
-                                                int lut_col, int gw, int lane, unsigned ebar, unsigned dbar) {
+template <bool kHead, bool kSym>
+__device__ __forceinline__ void st_consume_tile(int k, int cw, const float* __restrict__ prep, int lut_col, int gw,
+                                                int lane ST_PARAM) {
+  StSmemT<kHead>& sm = st_smem<kHead>();
+  StWarpScratch& gs = sm.wsc[cw];
+  StStage& st = sm.stage[k % StCfg<kHead>::kX];
+  const StDStage& dstg = sm.dstage[k % StCfg<kHead>::kD];
+  const unsigned ebar = st_smem_u32(&sm.empty[k % StCfg<kHead>::kX]), dbar = st_smem_u32(&sm.dempty[k % StCfg<kHead>::kD]);
+  const float4 (*__restrict__ asp)[6] = sm.asp;
   const int sg = lane >> 3, sl = lane & 7;
   const int gl = gw * 4 + sg;                          // graph slot inside the tile
   const StTileInfo& ti = st.info;
@@ -527,7 +634,7 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dst
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
       const float xi = sx[ils * kF + k];
-      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + hx * kF + k);
+      const float4 b = sm.adp[hx][k];
       d[0] = fmaf(xi, b.x, d[0]); d[1] = fmaf(xi, b.y, d[1]);
       d[2] = fmaf(xi, b.z, d[2]); d[3] = fmaf(xi, b.w, d[3]);
     }
@@ -591,15 +698,41 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dst
     // even lane: sums x0..x2 of head sl>>1; odd lane: x3, x4 and the softmax denominator
     const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
     const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
-    if (ok) {
-      const int64_t l0 = st.ptrs[2][gl];
-      float* zr = ti.d.z + l0 * (kHeads * kF) + hx * kF + o0;
-      zr[0] = acc3[0] * inv;
-      zr[1] = acc3[1] * inv;
-      if (!odd) zr[2] = acc3[2] * inv;
-      if (sl == 0) {
-        ti.d.lut_batch[l0] = ti.g0 + gl;
-        ti.d.lut_node[l0] = static_cast<int32_t>(st.ptrs[0][gl]) + il;
+    if constexpr (kHead) {
+      // the row goes to the readout head of this CTA: slot (tile % 8) * 16 + graph of the group's buffer
+      const int grp = k / kGroupTiles, buf = grp & 1, slot = (k % kGroupTiles) * kTG + gl;
+      {
+        ST_T1();
+        st_wait(st_smem_u32(&sm.head.zfree[buf]), static_cast<unsigned>((grp >> 1) & 1) ^ 1u);   // group grp - 2 has been read
+        ST_ACC1(4);
+      }
+      if (ok) {
+        const int64_t l0 = st.ptrs[2][gl];
+        float* zr = sm.head.zrow[buf] + slot * kZPitch + hx * kF + o0;
+        zr[0] = acc3[0] * inv;
+        zr[1] = acc3[1] * inv;
+        if (!odd) zr[2] = acc3[2] * inv;
+        if (sl == 0) {
+          ti.d.lut_batch[l0] = ti.g0 + gl;
+          ti.d.lut_node[l0] = static_cast<int32_t>(st.ptrs[0][gl]) + il;
+          sm.head.optr[buf][slot] = ti.d.out + l0 * QOT_OUT;
+        }
+      } else if (sl == 0) {
+        sm.head.optr[buf][slot] = nullptr;
+      }
+      __syncwarp();
+      if (lane == 0) st_arrive(st_smem_u32(&sm.head.zfull[buf]));
+    } else {
+      if (ok) {
+        const int64_t l0 = st.ptrs[2][gl];
+        float* zr = ti.d.z + l0 * (kHeads * kF) + hx * kF + o0;
+        zr[0] = acc3[0] * inv;
+        zr[1] = acc3[1] * inv;
+        if (!odd) zr[2] = acc3[2] * inv;
+        if (sl == 0) {
+          ti.d.lut_batch[l0] = ti.g0 + gl;
+          ti.d.lut_node[l0] = static_cast<int32_t>(st.ptrs[0][gl]) + il;
+        }
       }
     }
   }
@@ -608,7 +741,7 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dst
   if (todo) {
     StGenericArgs& ga = gs.gargs;
     if (lane == 0) {
-      ga.x = ti.d.x; ga.esrc = ti.d.edge_index; ga.edst = ti.d.edge_index + ti.d.E; ga.z = ti.d.z;
+      ga.x = ti.d.x; ga.esrc = ti.d.edge_index; ga.edst = ti.d.edge_index + ti.d.E; ga.z = ti.d.z; ga.out = ti.d.out;
       ga.lut_batch = ti.d.lut_batch; ga.lut_node = ti.d.lut_node; ga.status = ti.d.status;
       ga.N = ti.d.N; ga.E = ti.d.E; ga.g0 = ti.g0 + gw * 4;
     }
@@ -618,58 +751,300 @@ __device__ __forceinline__ void st_consume_tile(StStage& st, const StDStage& dst
   if (lane == 0) st_arrive(ebar);                      // the x window is dead: the producer may refill the stage
   if (todo) {
     const unsigned t4 = (todo & 1u) | ((todo >> 7) & 2u) | ((todo >> 14) & 4u) | ((todo >> 21) & 8u);
-    st_generic(gs.gargs, gs.gen, t4, prep, lut_col, lane);
+    st_generic<kHead>(cw, t4, prep, lut_col, lane);
   }
 }
 
-template <bool kHeadInKernel, bool kSym>
-__global__ void __launch_bounds__(kStThreads, 1)
+// ------------------------------------------------------------------------------------------------
+// in-kernel readout head (kHead): folded projection + BN + ReLU -> mlp.0 -> LeakyReLU -> mlp.3 for groups of 128 rows
+//   epilogue warps 4..7: thread = row.  z (20 floats) from the staging buffer -> y = relu(z_h Wf_h + shift) on the FP32
+//     pipe (640 FMA) -> split y = hi + lo (hi = the TF32 bits, lo = the exact remainder) -> tcgen05.st into TMEM as the
+//     A operand of the next product: columns [0,128) hi, [128,256) lo.
+//   MMA warp 1: one thread issues D[128x32] = A[128x128] * W1^T as 48 tcgen05.mma kind::tf32 (A from TMEM, B = the
+//     swizzled mlp.0 weight in shared memory): hi*lo + lo*hi + hi*hi, fp32 accumulation in TMEM columns [256,288),
+//     tcgen05.commit onto an mbarrier.
+//   epilogue again: tcgen05.ld of the row's 32 hidden units, + b1, LeakyReLU, mlp.3 (96 FMA), 3 floats to out.
+// The tensor pipe runs asynchronously beside the consumer warps: the head costs issue slots only for the epilogue.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long st_umma_desc_sw128(unsigned smem_addr) {
+  // K-major, SWIZZLE_128B shared-memory matrix descriptor (as gemm_tc.cu): start address, LBO = 1, SBO = 1024 B,
+  // version 1, layout type 2
+  unsigned long long d = 0;
+  d |= static_cast<unsigned long long>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<unsigned long long>(1u) << 16;
+  d |= static_cast<unsigned long long>(1024u >> 4) << 32;
+  d |= static_cast<unsigned long long>(1u) << 46;
+  d |= static_cast<unsigned long long>(2u) << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N, M
+constexpr unsigned st_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<unsigned>(N >> 3) << 17) | (static_cast<unsigned>(M >> 4) << 24);
+}
+__device__ __forceinline__ void st_umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
+                                                unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+      "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void st_tmem_st32(unsigned taddr, const unsigned (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void st_tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+constexpr unsigned kTmemCols = 512;        // columns [0,128) A hi, [128,256) A lo, [256,352) three accumulators
+constexpr unsigned kTmemALo = 128, kTmemD = 256;
+
+__device__ __noinline__ void st_head_mma(int ngroups, int lane) {
+  StHeadSmem& hs = st_smem<true>().head;
+  const unsigned tb = hs.tmem_base;
+  constexpr unsigned idesc = st_idesc(128, 32);
+  const unsigned b_hi = st_smem_u32(hs.b2[0]), b_lo = st_smem_u32(hs.b2[1]);
+  for (int g = 0; g < ngroups; ++g) {
+    if (!st_wait(st_smem_u32(&hs.aready), static_cast<unsigned>(g & 1))) break;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (lane == 0) {
+      // three accumulators, summed in fp32 by the epilogue: the tensor core adds into a running accumulator without
+      // round-to-nearest, so the large hi*hi terms go to two short chains (8 steps each) and the two compensation
+      // products (2^-11 of the magnitude) to a third
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {                   // hi*lo, lo*hi -> D2; hi*hi -> D0 (k < 64) / D1 (k >= 64)
+        const unsigned a_col = (p == 1) ? kTmemALo : 0u;
+        const unsigned b_base = (p == 0) ? b_lo : b_hi;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {               // UMMA_K = 8 for tf32: 8 TMEM columns / 32 bytes of a swizzled row
+            const unsigned d_col = p < 2 ? kTmemD + 64u : (kb < 2 ? kTmemD : kTmemD + 32u);
+            const unsigned acc = p < 2 ? ((p | kb | s) != 0 ? 1u : 0u) : (((kb & 1) | s) != 0 ? 1u : 0u);
+            st_umma_tf32_ts(tb + d_col, tb + a_col + static_cast<unsigned>(kb * 32 + s * 8),
+                            st_umma_desc_sw128(b_base + static_cast<unsigned>(kb * 4096 + s * 32)), idesc, acc);
+          }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       st_smem_u32(&hs.dready))
+                   : "memory");
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __noinline__ void st_head_epilogue(int my_tiles, int ngroups, int eq, int lane) {
+  StHeadSmem& hs = st_smem<true>().head;
+  const int row = eq * 32 + lane;
+  const unsigned tb = hs.tmem_base + (static_cast<unsigned>(eq * 32) << 16);
+  const float4* __restrict__ wf4 = reinterpret_cast<const float4*>(hs.wf);       // [h][f][32 channels]
+  const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(hs.shift);    // [128]
+  ST_DECL();
+  ST_T0();
+  for (int g = 0; g < ngroups; ++g) {
+    const int buf = g & 1;
+    {
+      ST_T1();
+      if (!st_wait(st_smem_u32(&hs.zfull[buf]), static_cast<unsigned>((g >> 1) & 1))) break;
+      ST_ACC1(5);
+    }
+    float z[kHeads * kF];
+    float* op = hs.optr[buf][row];
+    if (g * kGroupTiles + (row >> 4) >= my_tiles) op = nullptr;      // slot of a tile past the CTA's last one
+#pragma unroll
+    for (int i = 0; i < kHeads * kF; ++i) z[i] = op ? hs.zrow[buf][row * kZPitch + i] : 0.f;
+    __syncwarp();
+    if (lane == 0) st_arrive(st_smem_u32(&hs.zfree[buf]));
+#pragma unroll 1
+    for (int h = 0; h < kHeads; ++h) {
+      unsigned hi[32], lo[32];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 acc = sh4[h * 8 + c4];
+#pragma unroll
+        for (int f = 0; f < kF; ++f) {
+          const float4 w = wf4[(h * kF + f) * 8 + c4];
+          const float zf = z[h * kF + f];
+          acc.x = fmaf(zf, w.x, acc.x); acc.y = fmaf(zf, w.y, acc.y);
+          acc.z = fmaf(zf, w.z, acc.z); acc.w = fmaf(zf, w.w, acc.w);
+        }
+        const float y[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // hi = the TF32 bits of y (truncation, exact: lo carries the rest); lo = the remainder + half a TF32 ulp,
+          // so that the tensor core's own truncation of its low 13 bits rounds it to nearest instead of down
+          const unsigned hb = __float_as_uint(y[j]) & 0xffffe000u;
+          hi[c4 * 4 + j] = hb;
+          lo[c4 * 4 + j] = __float_as_uint(y[j] - __uint_as_float(hb)) + 0x1000u;
+        }
+      }
+      st_tmem_st32(tb + static_cast<unsigned>(h * 32), hi);
+      st_tmem_st32(tb + kTmemALo + static_cast<unsigned>(h * 32), lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) st_arrive(st_smem_u32(&hs.aready));
+    {
+      ST_T1();
+      if (!st_wait(st_smem_u32(&hs.dready), static_cast<unsigned>(g & 1))) break;
+      ST_ACC1(6);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    unsigned r[32];
+    {
+      unsigned r1[32], r2[32];
+      st_tmem_ld32(tb + kTmemD, r);
+      st_tmem_ld32(tb + kTmemD + 32u, r1);
+      st_tmem_ld32(tb + kTmemD + 64u, r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]));
+    }
+    float o3[QOT_OUT];
+#pragma unroll
+    for (int k = 0; k < QOT_OUT; ++k) o3[k] = hs.bo[k];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 b1 = reinterpret_cast<const float4*>(hs.b1)[j4];
+      float hv[4] = {__uint_as_float(r[4 * j4]) + b1.x, __uint_as_float(r[4 * j4 + 1]) + b1.y,
+                     __uint_as_float(r[4 * j4 + 2]) + b1.z, __uint_as_float(r[4 * j4 + 3]) + b1.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hv[j] = hv[j] > 0.f ? hv[j] : 0.01f * hv[j];
+#pragma unroll
+      for (int k = 0; k < QOT_OUT; ++k) {
+        const float4 w2 = reinterpret_cast<const float4*>(hs.w2 + k * kHid)[j4];
+        o3[k] = fmaf(hv[0], w2.x, o3[k]); o3[k] = fmaf(hv[1], w2.y, o3[k]);
+        o3[k] = fmaf(hv[2], w2.z, o3[k]); o3[k] = fmaf(hv[3], w2.w, o3[k]);
+      }
+    }
+    if (op) {
+      op[0] = o3[0]; op[1] = o3[1]; op[2] = o3[2];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // this group's TMEM reads precede the next MMAs
+  }
+  ST_ACC(7);
+  ST_FLUSH();
+}
+
+template <bool kHead, bool kSym>
+__global__ void __launch_bounds__(StCfg<kHead>::kThreads, 1)
 lp_stream_kernel(const qot_lp_batch_t* __restrict__ batches, int n_batches, int64_t tiles_per_batch,
                  int64_t total_tiles, const float* __restrict__ prep, int lut_col) {
-  extern __shared__ __align__(128) char st_smem_raw[];
-  StSmem& sm = *reinterpret_cast<StSmem*>((reinterpret_cast<uintptr_t>(st_smem_raw) + 127) & ~uintptr_t(127));
+  StSmemT<kHead>& sm = st_smem<kHead>();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int my_tiles = static_cast<int>((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const int ngroups = (my_tiles + kGroupTiles - 1) / kGroupTiles;
   if (tid == 0) {
-    for (int s = 0; s < kStStages; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.full[s])), "r"(33) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.empty[s])), "r"(kStGroupWarps) : "memory");
+    for (int s = 0; s < StCfg<kHead>::kX; ++s) {
+      st_mbar_init(&sm.full[s], 33);
+      st_mbar_init(&sm.empty[s], kStGroupWarps);
     }
-    for (int s = 0; s < kStDStages; ++s)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&sm.dempty[s])), "r"(kStGroupWarps) : "memory");
+    for (int s = 0; s < StCfg<kHead>::kD; ++s) st_mbar_init(&sm.dempty[s], kStGroupWarps);
+    if constexpr (kHead) {
+      for (int i = 0; i < 2; ++i) {
+        st_mbar_init(&sm.head.zfull[i], kGroupTiles * kStGroupWarps);
+        st_mbar_init(&sm.head.zfree[i], 4);
+      }
+      st_mbar_init(&sm.head.aready, 4);
+      st_mbar_init(&sm.head.dready, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sm.next_unit = 0;
+    sm.gen_lock = 0;
   }
-  if (tid == 0) sm.next_unit = 0;
   if (tid < 48) (&sm.asp[0][0])[tid] = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + tid);
+  if (tid >= 64 && tid < 64 + 4 * kF) (&sm.adp[0][0])[tid - 64] = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + tid - 64);
+  if constexpr (kHead) {
+    float4* b2 = reinterpret_cast<float4*>(&sm.head.b2[0][0][0]);
+    for (int i = tid; i < kB2swFloats / 4; i += StCfg<kHead>::kThreads)
+      b2[i] = __ldg(reinterpret_cast<const float4*>(prep + kOffB2sw) + i);
+    for (int i = tid; i < kHC * kF; i += StCfg<kHead>::kThreads) sm.head.wf[i] = __ldg(prep + kOffWf + i);
+    if (tid < kHC) sm.head.shift[tid] = __ldg(prep + kOffShift + tid);
+    if (tid < kHid) sm.head.b1[tid] = __ldg(prep + kOffB1 + tid);
+    if (tid < QOT_OUT * kHid) sm.head.w2[tid] = __ldg(prep + kOffW2 + tid);
+    if (tid < QOT_OUT) sm.head.bo[tid] = __ldg(prep + kOffB2 + tid);
+    if (warp == 4) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(st_smem_u32(&sm.head.tmem_base)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the operand tile written above -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  if constexpr (kHead) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp == 0) {
-    st_producer(sm, batches, n_batches, tiles_per_batch, batches[0].tile0, total_tiles, lane);
+    st_producer<kHead>(batches, n_batches, tiles_per_batch, batches[0].tile0, total_tiles, lane);
     return;
+  }
+  int cw = warp - 1;
+  if constexpr (kHead) {
+    if (warp == 1) {
+      st_head_mma(ngroups, lane);
+      return;
+    }
+    if (warp >= 4 && warp < 8) {
+      st_head_epilogue(my_tiles, ngroups, warp - 4, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps: all TMEM reads done
+      if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.head.tmem_base), "r"(kTmemCols) : "memory");
+      return;
+    }
+    cw = warp < 4 ? warp - 2 : warp - 6;
   }
   // ---- consumers: every warp claims quarter-tiles (4 graphs) in order from one counter -- no static assignment,
   // so a slow quarter never idles another warp while stages hold data
-  const int cw = warp - 1;
-  const int my_tiles = static_cast<int>((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const int tiles_padded = kHead ? ngroups * kGroupTiles : my_tiles;
   ST_DECL();
   for (;;) {
     int u = 0;
     if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
     u = __shfl_sync(kFull, u, 0);
     const int k = u >> 2, gw = u & 3;
-    if (k >= my_tiles) break;
-    const int s = k % kStStages;
-    const unsigned ph = static_cast<unsigned>((k / kStStages) & 1);
+    if (k >= tiles_padded) break;
+    if constexpr (kHead) {
+      if (k >= my_tiles) {
+        // quarter of a tile past the last one: only the group protocol (its slots hold no rows)
+        const int grp = k / kGroupTiles, buf = grp & 1;
+        if (!st_wait(st_smem_u32(&sm.head.zfree[buf]), static_cast<unsigned>((grp >> 1) & 1) ^ 1u)) break;
+        if (lane < 4) sm.head.optr[buf][(k % kGroupTiles) * kTG + gw * 4 + lane] = nullptr;
+        __syncwarp();
+        if (lane == 0) st_arrive(st_smem_u32(&sm.head.zfull[buf]));
+        continue;
+      }
+    }
+    const int s = k % StCfg<kHead>::kX;
+    const unsigned ph = static_cast<unsigned>((k / StCfg<kHead>::kX) & 1);
     {
       ST_T0();
       if (!st_wait(st_smem_u32(&sm.full[s]), ph)) {
         if (lane == 0) atomicOr(batches[0].status, 4);
-        return;
+        break;
       }
       ST_ACC(2);
     }
-    const int sd_ = k % kStDStages;
     ST_T0();
-    st_consume_tile<kHeadInKernel, kSym>(sm.stage[s], sm.dstage[sd_], sm.wsc[cw], sm.asp, prep, lut_col, gw, lane,
-                                         st_smem_u32(&sm.empty[s]), st_smem_u32(&sm.dempty[sd_]));
+    st_consume_tile<kHead, kSym>(k, cw, prep, lut_col, gw, lane ST_ARG);
     ST_ACC(3);
   }
   ST_FLUSH();
@@ -815,22 +1190,35 @@ extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t
               "qot_lightpath_infer_stream: prepared must be 16-byte aligned");
   QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_stream: is_lut_index out of range");
   if (total_tiles == 0) return QOT_OK;
-  QOT_REQUIRE((flags & ~QOT_LP_SYMMETRIC_BY_SOURCE) == 0, "qot_lightpath_infer_stream: unknown flag");
+  QOT_REQUIRE((flags & ~(QOT_LP_SYMMETRIC_BY_SOURCE | QOT_LP_SPLIT_HEAD)) == 0, "qot_lightpath_infer_stream: unknown flag");
+  const bool sym = (flags & QOT_LP_SYMMETRIC_BY_SOURCE) != 0, split = (flags & QOT_LP_SPLIT_HEAD) != 0;
   static std::atomic<unsigned long long> done{0};
-  const int smem = static_cast<int>(sizeof(StSmem) + 128);
-  if (int rc = once_per_device(done, [smem] {
-        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  constexpr int smem_split = static_cast<int>(sizeof(StSmemT<false>) + 1024), smem_head = static_cast<int>(sizeof(StSmemT<true>) + 1024);
+  if (int rc = once_per_device(done, [] {
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split));
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split));
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_head));
+        QOT_CUDA(cudaFuncSetAttribute(lp_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_head));
         return static_cast<int>(QOT_OK);
       }))
     return rc;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(kNumSMs, total_tiles));
-  if (flags & QOT_LP_SYMMETRIC_BY_SOURCE)
-    lp_stream_kernel<false, true><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles,
-                                                                    prepared, is_lut_index);
+  if (!split) {
+    if (sym)
+      lp_stream_kernel<true, true><<<grid, StCfg<true>::kThreads, smem_head, stream>>>(batches, n_batches, uniform_tiles,
+                                                                                   total_tiles, prepared, is_lut_index);
+    else
+      lp_stream_kernel<true, false><<<grid, StCfg<true>::kThreads, smem_head, stream>>>(batches, n_batches, uniform_tiles,
+                                                                                    total_tiles, prepared, is_lut_index);
+    QOT_LAUNCH_CHECK();
+    return QOT_OK;
+  }
+  if (sym)
+    lp_stream_kernel<false, true><<<grid, StCfg<false>::kThreads, smem_split, stream>>>(batches, n_batches, uniform_tiles,
+                                                                                     total_tiles, prepared, is_lut_index);
   else
-    lp_stream_kernel<false, false><<<grid, kStThreads, smem, stream>>>(batches, n_batches, uniform_tiles, total_tiles,
-                                                                     prepared, is_lut_index);
+    lp_stream_kernel<false, false><<<grid, StCfg<false>::kThreads, smem_split, stream>>>(batches, n_batches, uniform_tiles,
+                                                                                      total_tiles, prepared, is_lut_index);
   QOT_LAUNCH_CHECK();
   const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(max_rows, 64), 4 * kNumSMs));
   lp_stream_head_kernel<<<dim3(static_cast<unsigned>(hb), static_cast<unsigned>(n_batches)), 128, 0, stream>>>(batches, prepared);

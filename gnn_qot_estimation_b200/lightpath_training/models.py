@@ -94,11 +94,11 @@ class LightpathGNN(torch.nn.Module):
         return ops.lightpath_infer(data.x, data.edge_index, gptr, eptr, lut_ptr, self.prepared(),
                                    self.is_lut_index, out)
 
-    def stream_plan(self, batches) -> "ops.LightpathStreamPlan":
+    def stream_plan(self, batches, split_head: bool = False) -> "ops.LightpathStreamPlan":
         """Plan for evaluating many resident batches with one launch of the persistent kernel each time
         ``forward_stream`` is called (the streaming form of lightpath_training/test.py:77-94)."""
         self._check_supported()
-        return ops.LightpathStreamPlan(batches, self.is_lut_index)
+        return ops.LightpathStreamPlan(batches, self.is_lut_index, split_head)
 
     @_lib.on_tensor_device
     def forward_stream(self, plan, first: int = 0, count=None) -> None:

@@ -245,7 +245,8 @@ class LightpathStreamPlan:
     ``launch(prepared, first, count)`` enqueues batches [first, first+count) on the current stream: no
     synchronisation, CUDA-graph capturable.  ``result(i)`` gives views of batch i's outputs."""
 
-    def __init__(self, batches, is_lut_index: int):
+    def __init__(self, batches, is_lut_index: int, split_head: bool = False):
+        """``split_head``: QOT_LP_SPLIT_HEAD -- the readout head as a second launch instead of inside the kernel."""
         L = _lib.lib()
         if not batches:
             raise ValueError("LightpathStreamPlan: no batches")
@@ -258,7 +259,7 @@ class LightpathStreamPlan:
         self.batches = list(batches)                 # keeps the input tensors alive
         self.is_lut_index = int(is_lut_index)
         # QOT_LP_SYMMETRIC_BY_SOURCE only when EVERY batch carries the verified-layout mark
-        self.flags = 1 if all(getattr(b, "sym_by_src", False) for b in batches) else 0
+        self.flags = (1 if all(getattr(b, "sym_by_src", False) for b in batches) else 0) | (2 if split_head else 0)
         nb = len(batches)
         rows = torch.stack([b.lut_ptr[-1] for b in batches]).tolist()          # the one sync
         self.rows = [int(r) for r in rows]

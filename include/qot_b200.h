@@ -341,6 +341,9 @@ typedef struct qot_lp_batch {
  * node's in-edges are then the destinations of its own out-run, which the kernel locates by counting over the
  * destination row alone: the source row of edge_index is never read.  Same rows, bit-identical values. */
 #define QOT_LP_SYMMETRIC_BY_SOURCE 1
+/* QOT_LP_SPLIT_HEAD: run the readout head as a second launch (lp_stream_head_kernel, mma.sync) over z rows
+ * written to the batches' workspaces, instead of inside the persistent kernel on tcgen05 / TMEM (the default). */
+#define QOT_LP_SPLIT_HEAD 2
 int64_t qot_lightpath_stream_tiles(int64_t B);
 int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches, int64_t total_tiles,
                                int64_t uniform_tiles, int64_t max_rows, const float* prepared,

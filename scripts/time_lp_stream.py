@@ -14,7 +14,8 @@ store = synthetic.lightpath_store(nb * 4096, seed=1, device=dev)
 if sym:
     assert store.verify_layout()
 bs = [store.collate(range(i * 4096, (i + 1) * 4096)) for i in range(nb)]
-plan = m.stream_plan(bs)
+split = (sys.argv[4] != "0") if len(sys.argv) > 4 else False
+plan = m.stream_plan(bs, split_head=split)
 for _ in range(3):
     m.forward_stream(plan)
 torch.cuda.synchronize()
@@ -31,5 +32,5 @@ with torch.cuda.stream(s):
     e1.record(s); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (reps * nb)
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6533.5
-print(json.dumps({"n_batches": nb, "verified_layout": sym, "us_per_batch": us, "graphs_per_s": 4096 / us * 1e6, "alg_bytes_per_batch": alg,
+print(json.dumps({"n_batches": nb, "verified_layout": sym, "split_head": split, "us_per_batch": us, "graphs_per_s": 4096 / us * 1e6, "alg_bytes_per_batch": alg,
                   "frac": alg / (us * 1e-6) / 1e9 / peak, "status": int(plan.status.max().item())}))

@@ -9,7 +9,8 @@ sd = torch.load("tests/golden/ckpt_lightpath_model_1.pt", map_location="cpu", we
 m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0); m.load_state_dict(sd); m.to(dev).eval()
 store = synthetic.lightpath_store(nb * 4096, seed=1, device=dev); store.verify_layout()
 bs = [store.collate(range(i * 4096, (i + 1) * 4096)) for i in range(nb)]
-plan = m.stream_plan(bs)
+split = len(sys.argv) > 2 and sys.argv[2] == "1"
+plan = m.stream_plan(bs, split_head=split)
 m.forward_stream(plan); torch.cuda.synchronize()
 buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
 L = _lib.lib()
@@ -20,6 +21,7 @@ e0.record(); m.forward_stream(plan); e1.record(); torch.cuda.synchronize()
 t = buf.view(148, 8).double()
 tiles = nb * 256 / 148
 print(f"launch {e0.elapsed_time(e1) * 1e3:.1f} us for {nb} batches ({e0.elapsed_time(e1) * 1e3 / nb:.2f} us/batch incl. head kernel)")
-names = ["producer wait-empty", "producer issue", "consumer wait-full (sum over warps)", "consumer work (sum over warps)"]
+names = ["producer wait-empty", "producer issue", "consumer wait-full (sum over warps)", "consumer work (sum over warps)",
+         "consumer wait free z buffer (sum)", "epilogue wait staged group (4 warps)", "epilogue wait MMAs (4 warps)", "epilogue total (4 warps)"]
 for i, n in enumerate(names):
     print(f"{n:40s} mean {t[:, i].mean():12.0f} cycles/CTA  = {t[:, i].mean() / tiles:9.0f} per tile   (min {t[:, i].min():.0f} max {t[:, i].max():.0f})")
