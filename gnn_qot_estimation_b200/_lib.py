@@ -51,9 +51,9 @@ class QotLpBatch(C.Structure):
                 ("tile0", i64), ("reserved", i64)]
 
 
-class QotLpSlot(C.Structure):
-    _fields_ = [("x", P), ("edge_src", P), ("edge_dst", P), ("ptrs", P), ("out", P), ("lut_batch", P),
-                ("lut_node", P), ("n_lut", P), ("status", P), ("z", P), ("arena", P),
+class QotLpWireSlot(C.Structure):
+    _fields_ = [("arena", P), ("edge_index", P), ("ptrs", P), ("desc", P), ("out", P), ("lut_batch", P),
+                ("lut_node", P), ("n_lut", P), ("status", P),
                 ("cap_nodes", i64), ("cap_edges", i64), ("cap_graphs", i64)]
 
 
@@ -94,7 +94,6 @@ SIGNATURES = {
     "qot_lightpath_prepared_floats": (sz, []),
     "qot_lightpath_prepare": (C.c_int, [C.POINTER(QotLightpathParams), P, vp]),
     "qot_lightpath_infer_workspace_bytes": (sz, [i64]),
-    "qot_lightpath_infer": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, P, P, P, P, P, P, sz, vp]),
     "qot_lightpath_graph_scratch_bytes": (sz, [i64]),
     "qot_lightpath_graph_count": (C.c_int, [P, P, P, i64, C.POINTER(QotLpGraphCfg), P, P, P, sz, P, vp]),
     "qot_lightpath_graph_fill": (C.c_int, [P, i64, P, P, P, P, P, P, P, vp]),
@@ -110,10 +109,9 @@ SIGNATURES = {
     "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, vp]),
     "qot_lightpath_stream_tiles": (i64, [i64]),
     "qot_lightpath_infer_stream": (C.c_int, [P, i32, i64, i64, i64, P, i32, i32, vp]),
-    "qot_lightpath_set_variant": (C.c_int, [C.c_int]),
-    "qot_lightpath_get_variant": (C.c_int, []),
-    "qot_lightpath_infer_host": (C.c_int, [P, P, i64, P, P, P, i64, i64, P, i32, C.POINTER(QotLpSlot), P, P, P,
-                                           C.POINTER(i64), C.POINTER(i64), vp]),
+    "qot_lightpath_wire_bytes": (sz, [i64, i64, i64]),
+    "qot_lightpath_infer_wire_host": (C.c_int, [P, i64, i64, i64, i64, P, i32, C.POINTER(QotLpWireSlot), P, P, P,
+                                                C.POINTER(i64), C.POINTER(i64), vp]),
     "qot_gat_fwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_gat_bwd_workspace_bytes": (sz, [i64]),
     "qot_gat_bwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, P, P, P, P, sz, vp]),
@@ -151,8 +149,6 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if _os.environ.get("QOT_LP_VARIANT"):
-        handle.qot_lightpath_set_variant(int(_os.environ["QOT_LP_VARIANT"]))
     _lib = handle
     return handle
 

@@ -76,6 +76,27 @@ class Batch:
         return f"Batch(num_graphs={self.num_graphs}, " + ", ".join(parts) + ")"
 
 
+class WireBatch:
+    """A batch in the compact wire format of include/qot_b200.h (qot_lightpath_infer_wire_host): ONE contiguous
+    (pinned) host arena  int32 ptr | int32 edge_ptr | int32 lut_ptr | x fp32 [N,5] | uint8 dst [E]  -- destinations
+    as graph-local ids, no source row (verified from_networkx layout only).  ~0.78 KB per 32-node graph instead of
+    the 3.4 KB of the reference tensors (x + int64 edge_index [2,E] + offsets)."""
+
+    def __init__(self, arena: torch.Tensor, N: int, E: int, B: int, L: int, lut_col: int):
+        self.arena, self.num_nodes, self.num_edges, self.num_graphs, self.rows, self.lut_col = arena, N, E, B, L, lut_col
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.arena.numel())
+
+    @staticmethod
+    def offsets(N: int, E: int, B: int):
+        a16 = lambda v: (v + 15) & ~15
+        o_x = a16(12 * (B + 1))
+        o_d = o_x + a16(20 * N)
+        return o_x, o_d, o_d + a16(E)
+
+
 class PackedGraphStore:
     """All graphs of a dataset as flat arrays.
 
@@ -208,6 +229,37 @@ class PackedGraphStore:
         b.max_nodes = int(dn.max()) if B else 0
         b.max_edges = int(de.max()) if B else 0
         return b
+
+    # -- the same range in the compact wire format (what travels to the GPU in LightpathInferencePipeline)
+    def host_wire_batch(self, g0: int, g1: int, pin: bool = True) -> WireBatch:
+        """Graphs [g0, g1) packed for qot_lightpath_infer_wire_host.  Needs a host-resident store whose layout has
+        been verified (``verify_layout()``: the format carries no source row) and graphs of <= 255 nodes."""
+        if self.device.type != "cpu":
+            raise RuntimeError("host_wire_batch needs a host-resident store")
+        if not self.sym_by_src:
+            raise RuntimeError("host_wire_batch: call verify_layout() first -- the wire format has no source row and is "
+                               "only defined for the verified from_networkx layout")
+        if self.lut_col is None or self.node_feat is None or self.node_feat.shape[1] != 5:
+            raise RuntimeError("host_wire_batch packs lightpath graphs (x [N,5] with a LUT flag column)")
+        n0, n1 = int(self._node_ptr_host[g0]), int(self._node_ptr_host[g1])
+        e0, e1 = int(self._edge_ptr_host[g0]), int(self._edge_ptr_host[g1])
+        B, N, E = g1 - g0, n1 - n0, e1 - e0
+        ptr = (self.node_ptr[g0:g1 + 1] - n0)
+        if int((ptr[1:] - ptr[:-1]).max()) > 255:
+            raise RuntimeError("host_wire_batch: a graph has more than 255 nodes (uint8 destination ids)")
+        x = self.node_feat[n0:n1]
+        bt = torch.repeat_interleave(torch.arange(B, dtype=torch.int64), ptr[1:] - ptr[:-1])
+        lut = torch.zeros(B + 1, dtype=torch.int64)
+        torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, (x[:, self.lut_col] == 1.0).to(torch.int64)), 0, out=lut[1:])
+        o_x, o_d, nbytes = WireBatch.offsets(N, E, B)
+        arena = torch.zeros(nbytes, dtype=torch.uint8)
+        if pin:
+            arena = arena.pin_memory()
+        ptrs = arena[:12 * (B + 1)].view(torch.int32).view(3, B + 1)
+        ptrs[0].copy_(ptr); ptrs[1].copy_(self.edge_ptr[g0:g1 + 1] - e0); ptrs[2].copy_(lut)
+        arena[o_x:o_x + 20 * N].view(torch.float32).view(N, 5).copy_(x)
+        arena[o_d:o_d + E].copy_(self.edge_dst[e0:e1].to(torch.uint8))
+        return WireBatch(arena, N, E, B, int(lut[-1]), self.lut_col)
 
     # -- host-side view of a contiguous range (what a host DataLoader would hand over)
     def host_batch(self, g0: int, g1: int, pin: bool = False) -> Batch:

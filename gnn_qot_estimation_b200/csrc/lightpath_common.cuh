@@ -1,5 +1,5 @@
-// Device helpers shared by the LightpathGNN eval kernels (lightpath_infer.cu: the current fused /
-// split kernels; lightpath_infer_legacy.cu: the first two generations kept for comparison):
+// Device helpers shared by the LightpathGNN eval sources (lightpath_infer.cu: parameter folding and lut_ptr;
+// lightpath_stream.cu: the persistent kernel):
 // layout of the prepared parameter block, TF32 split helpers, the warp-per-row attention used by
 // the generic path, the FP32 readout head of one row.
 #pragma once
@@ -50,17 +50,8 @@ __device__ __forceinline__ float4 tf32_split2(float b0, float b1) {
   return make_float4(h0, h1, __uint_as_float(tf32_rna(b0 - h0)), __uint_as_float(tf32_rna(b1 - h1)));
 }
 
-#ifndef QOT_LP_OCC
-#define QOT_LP_OCC 4                      // resident blocks per SM the register budget is sized for
-#endif
-constexpr int kIW = 8;                    // warps (= graphs) per block
-constexpr int kThreads = kIW * 32;
-constexpr int kMaxN = 64;                 // fast path: nodes staged in shared memory
-constexpr int kXF = kMaxN * kF;           // 320 floats per graph
-constexpr int kXR = kXF / 32;             // 10 slab loads per lane
-constexpr int kEC = 8;                    // fast path: 8 x 32 = 256 edges held in registers
+constexpr int kMaxN = 64;                 // fast path: nodes of a graph staged in shared memory
 constexpr int kMsgCap = 64;               // message list per warp (sources of one row + its self loop)
-constexpr int kWeightFloats = kPreparedBase - kOffWf;   // projection + head weights staged per block
 
 __device__ __forceinline__ float pick5(const float (&v)[kF], int f) {
   return (f == 0) ? v[0] : (f == 1) ? v[1] : (f == 2) ? v[2] : (f == 3) ? v[3] : v[4];
@@ -226,18 +217,6 @@ __device__ __noinline__ float lut_row_global(const float* __restrict__ x, const 
   return ov;
 }
 
-constexpr int kGPB = 32;                  // graphs per block
-constexpr int kSubMsg = 16;               // sources of the LUT row + its self loop
-
-struct SubMeta {
-  int64_t n0, n1, e0, e1, l0, l1;
-  int il, state;                          // state: 0 nothing to do, 1 fast row ready (z staged), 2 generic path
-};
-
-// variants 0 / 1 (lightpath_infer_legacy.cu)
-int lp_infer_launch_legacy(int variant, const float* x, const int64_t* esrc, const int64_t* edst, const int64_t* gptr,
-                           const int64_t* eptr, const int64_t* lut_ptr, int64_t N, int64_t B, const float* prepared,
-                           int32_t is_lut_index, float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                           int32_t* status, cudaStream_t stream);
+constexpr int kSubMsg = 16;               // fast path: sources of the LUT row + its self loop
 
 }  // namespace qot

@@ -1,4 +1,5 @@
-// LightpathGNN eval-mode forward, fully fused:
+// LightpathGNN eval-mode forward -- parameter folding and the lut_ptr index array; the kernel itself is
+// lp_stream_kernel (lightpath_stream.cu).  The forward, fully fused:
 //   GATConv(5 -> 4x32, self loops replaced) -> BatchNorm(running stats) -> ReLU
 //   -> LUT-row readout -> Linear(128,32) -> LeakyReLU -> Linear(32,3)
 // (lightpath_training/models.py:26-45 under model.eval(); PyG semantics per
@@ -13,9 +14,7 @@
 // whole batch (x[lut_mask]) because every graph writes at lut_ptr[g], an index array the collate
 // builds like ptr.  Deterministic: edges of a row are consumed in edge order, reductions use
 // fixed trees, no atomics on floats.
-// This file: parameter folding, lut_ptr, the current kernels (lp_attn_kernel fused / split,
-// lp_head_kernel) and the C ABI; generations 0 and 1 live in lightpath_infer_legacy.cu, shared
-// device helpers in lightpath_common.cuh.
+// This file: lp_prepare_kernel (folded / pre-split / swizzled parameters), lp_count_kernel + scan (lut_ptr).
 #include <algorithm>
 #include <cstdlib>
 
@@ -92,11 +91,6 @@ lp_prepare_kernel(qot_lightpath_params_t p, float* __restrict__ out) {
   }
 }
 
-#ifdef QOT_LP_TRACE
-// debug build only (scripts/trace_lp_bulk.py): per-block phase stamps, 8 slots per block
-__device__ unsigned long long* g_lp_trace = nullptr;
-#endif
-
 // lut_cnt[g] = number of nodes of graph g whose LUT flag is 1.0 (feeds the lut_ptr scan)
 __global__ void __launch_bounds__(256)
 lp_count_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int64_t B,
@@ -120,775 +114,14 @@ __global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t n, int6
   if (i < n) out[i] = in[i];
 }
 
-// =====================================================================================
-// Shared pieces of variants 2 and 3 (lp_attn_kernel, lp_head_kernel): bulk-copied slabs, tensor-core head.
-// =====================================================================================
-#ifdef QOT_LP_TRACE
-#define LPB_TRACE_DECL long long lpb_tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define LPB_TRACE(slot) do { if (threadIdx.x == 0) lpb_tr[slot] = clock64(); } while (0)
-#define LPB_TRACE_FLUSH()                                                                        \
-  do {                                                                                           \
-    if (g_lp_trace && threadIdx.x == 0)                                                          \
-      for (int i_ = 0; i_ < 8; ++i_) g_lp_trace[blockIdx.x * 8 + i_] = lpb_tr[i_];               \
-  } while (0)
-#else
-#define LPB_TRACE_DECL do {} while (0)
-#define LPB_TRACE(slot) do {} while (0)
-#define LPB_TRACE_FLUSH() do {} while (0)
-#endif
-#ifndef QOT_LP_BULK_OCC
-#define QOT_LP_BULK_OCC 3
-#endif
-constexpr int kBNodes = 1216;             // nodes of one block's 32 graphs (mean 1024, +2.4 sigma)
-constexpr int kBEdges = 4608;             // edges of one block's 32 graphs (mean 3844, +2.4 sigma)
-constexpr int kBMaxE = 248;               // per graph: 8 lanes x 31 contiguous edges (bit mask per lane)
-constexpr int kBXBytes = kBNodes * kF * 4;
-constexpr int kBDBytes = kBEdges * 8;
-constexpr int kBDOff = kBXBytes + 16;     // destination slab offset inside BulkSmem::slab
-constexpr int kZStride = 36;              // floats per graph row of z (4 heads x 8, padded: conflict-free fragments)
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], float b0, float b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0u;
-}
-
-// =====================================================================================
-// variant 3 (default): two kernels per batch, the decomposition BASELINE.json's north_star names --
-//   lp_attn_kernel : collate arrays -> gather -> attention softmax -> z rows [L,20] (+ lut_batch / lut_node)
-//   lp_head_kernel : z rows -> folded projection + BN + ReLU -> mlp.0 -> LeakyReLU -> mlp.3 on tensor cores
-// Splitting the readout head off means a block of lp_attn_kernel gives its 64 KB of shared memory
-// back as soon as its attention rows are written: no block-wide barrier, no tensor-pipe phase and no
-// straggler wait while the slabs sit idle (per-block phase trace: 5 000 of 18 400 cycles in variant 2).
-// z is 80 bytes per LUT row (0.33 MB per 4096-graph batch, L2-resident between the two launches).
-// lp_attn_kernel differs from variant 2's first phase in three more ways: the edge scan is fully
-// unrolled with one compare per slot; the message sums use per-lane PERMUTED head / feature slots so
-// the reduce-scatter needs no selects (tables built once by lp_prepare_kernel); graphs the fast path
-// declines are evaluated by their own warp without any block-level bookkeeping.
-// =====================================================================================
-constexpr int kZRow = kHeads * kF;        // floats per z row in the workspace
-
-template <bool kXG, bool kFused>
-struct AttnSmem {
-  alignas(128) unsigned char slab[(kXG ? 0 : kBXBytes + 16) + kBDBytes + 16];   // [x window,] destination window; kFused: later the H partials
-  float zhi[kFused ? kGPB * kZStride : 4];   // kFused: attention rows stay on chip, already split for the tensor cores
-  float zlo[kFused ? kGPB * kZStride : 4];
-  SubMeta meta[kFused ? kGPB : 1];
-  int msg[kGPB][kSubMsg];
-  float gen[kFused ? 1 : 8][128];          // split form: generic path scratch per warp, z (32 floats) + message list (64)
-  alignas(8) unsigned long long mbar;
-};
-
-// kXG: the node features are NOT staged -- flags and the handful of rows a graph needs are read from
-// global memory (L1 / L2), which leaves 39 KB of shared memory per block: 4 resident blocks per SM
-#ifndef QOT_LP_ATTN_OCC
-#define QOT_LP_ATTN_OCC 4                 // register budget: 64 per thread, so that lp_head_kernel blocks fit beside 3 resident blocks
-#endif
-template <bool kXG, bool kFused, bool kTC = true>
-__global__ void __launch_bounds__(256, kFused ? QOT_LP_BULK_OCC : QOT_LP_ATTN_OCC)
-lp_attn_kernel(const float* __restrict__ x, const int64_t* __restrict__ esrc,   // static_assert below: 3 fused blocks per SM
-               const int64_t* __restrict__ edst, const int64_t* __restrict__ gptr,
-               const int64_t* __restrict__ eptr, const int64_t* __restrict__ lptr, int64_t N,
-               int64_t E, int64_t B, const float* __restrict__ prep, int lut_col,
-               float* __restrict__ zbuf, float* __restrict__ out, int64_t* __restrict__ lut_batch,
-               int32_t* __restrict__ lut_node, int32_t* __restrict__ n_lut,
-               int32_t* __restrict__ status) {
-  extern __shared__ __align__(128) char attn_smem_raw[];
-  AttnSmem<kXG, kFused>& sm = *reinterpret_cast<AttnSmem<kXG, kFused>*>(attn_smem_raw);
-  constexpr int kDOff = kXG ? 0 : kBDOff;
-  LPB_TRACE_DECL;
-  LPB_TRACE(0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sg = lane >> 3, sl = lane & 7, base = lane & ~7;
-  const int gl = warp * 4 + sg;
-  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kGPB;
-  const int64_t g = g0 + gl;
-  const bool active = g < B;
-  const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&sm.mbar));
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();                                   // barrier word initialised before anyone polls it
-
-  // ---- extents of the block's tile (every thread: broadcast loads) and of the sub-group's graph
-  const int64_t gE = min(g0 + kGPB, B);
-  const int64_t nb0 = gptr[g0], nb1 = gptr[gE], eb0 = eptr[g0], eb1 = eptr[gE];
-  long long pv = 0;
-  if (active && sl < 6) pv = (sl < 2) ? gptr[g + sl] : (sl < 4) ? eptr[g + sl - 2] : lptr[g + sl - 4];
-  // windows staged: nodes [nb0, nb0 + xn), edges [eb0, eb0 + en), 16-byte aligned in global memory
-  int xn = 0, en = 0;
-  if (!kXG && nb0 >= 0 && nb1 >= nb0 && nb0 <= N) xn = static_cast<int>(min(min(nb1, N) - nb0, static_cast<int64_t>(kBNodes)));
-  if (eb0 >= 0 && eb1 >= eb0 && eb0 <= E) en = static_cast<int>(min(min(eb1, E) - eb0, static_cast<int64_t>(kBEdges)));
-  const uintptr_t xa = reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(xn > 0 ? nb0 : 0) * (kF * 4);
-  const uintptr_t da = reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(en > 0 ? eb0 : 0) * 8;
-  const unsigned xlead = static_cast<unsigned>(xa & 15), dlead = static_cast<unsigned>(da & 15);
-  if (tid == 0) {
-    // one thread sizes the two windows, copies by hand the few bytes a rounded-up window would read
-    // past the end of its tensor, and issues the bulk copies
-    const uintptr_t xs0 = xa - xlead, ds0 = da - dlead;
-    const unsigned xspan = xlead + static_cast<unsigned>(xn) * (kF * 4), dspan = dlead + static_cast<unsigned>(en) * 8;
-    unsigned xbytes = (xspan + 15u) & ~15u, dbytes = (dspan + 15u) & ~15u;
-    if (xs0 + xbytes > reinterpret_cast<uintptr_t>(x) + static_cast<uintptr_t>(N) * (kF * 4)) xbytes = xspan & ~15u;
-    if (ds0 + dbytes > reinterpret_cast<uintptr_t>(edst) + static_cast<uintptr_t>(E) * 8) dbytes = dspan & ~15u;
-    if (xn == 0) xbytes = 0;
-    if (en == 0) dbytes = 0;
-    if (xn > 0)
-      for (unsigned o = xbytes; o < xspan; o += 4)
-        *reinterpret_cast<float*>(sm.slab + o) = *reinterpret_cast<const float*>(xs0 + o);
-    if (en > 0 && dspan > dbytes)
-      *reinterpret_cast<long long*>(sm.slab + kDOff + dbytes) = *reinterpret_cast<const long long*>(ds0 + dbytes);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes + dbytes) : "memory");
-    if (xbytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab))), "l"(xs0), "r"(xbytes), "r"(bar) : "memory");
-    if (dbytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sm.slab + kDOff))), "l"(ds0), "r"(dbytes), "r"(bar) : "memory");
-  }
-  LPB_TRACE(1);
-
-  const int64_t n0 = __shfl_sync(kFull, pv, base + 0), n1 = __shfl_sync(kFull, pv, base + 1);
-  const int64_t e0 = __shfl_sync(kFull, pv, base + 2), e1 = __shfl_sync(kFull, pv, base + 3);
-  const int64_t l0 = __shfl_sync(kFull, pv, base + 4), l1 = __shfl_sync(kFull, pv, base + 5);
-  const bool fits = active && n1 >= n0 && e1 >= e0 && (n1 - n0) <= kMaxN && (e1 - e0) <= kBMaxE &&
-                    (kXG ? (n0 >= 0 && n1 <= N) : (n0 >= nb0 && (n1 - nb0) <= xn)) && e0 >= eb0 && (e1 - eb0) <= en;
-  const int n = fits ? static_cast<int>(n1 - n0) : 0;
-  const int ne = fits ? static_cast<int>(e1 - e0) : 0;
-  if (g == B - 1 && sl == 0) n_lut[0] = static_cast<int32_t>(l1);
-  const float* sx = kXG ? x + (fits ? n0 : 0) * kF
-                        : reinterpret_cast<const float*>(sm.slab + xlead) + (fits ? static_cast<int>(n0 - nb0) : 0) * kF;
-  const long long* sd = reinterpret_cast<const long long*>(sm.slab + kDOff + dlead) + (fits ? static_cast<int>(e0 - eb0) : 0);
-  // kXG: the LUT flags of the graph, all requested before anything waits (8 nodes per load round)
-  float flag[kMaxN / 8];
-  if (kXG) {
-#pragma unroll
-    for (int r = 0; r < kMaxN / 8; ++r) {
-      const int node = sl + 8 * r;
-      flag[r] = node < n ? __ldg(sx + node * kF + lut_col) : 0.f;
-    }
-  }
-
-  // attention vectors in this lane's slot order while the copies fly: local head slot i is head
-  // i ^ (sl >> 1); local feature slot m is (x0 x1 x2 x3 x4 ONE) on even lanes, (x3 x4 ONE x0 x1 x2) on odd
-  const int hx = sl >> 1;
-  const bool odd = (sl & 1) != 0;
-  float AsP[6][kHeads];
-#pragma unroll
-  for (int m = 0; m < 6; ++m) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(prep + kOffAsP) + sl * 6 + m);
-    AsP[m][0] = a.x; AsP[m][1] = a.y; AsP[m][2] = a.z; AsP[m][3] = a.w;
-  }
-  while (!mbar_try_wait(bar, 0u)) {}
-  LPB_TRACE(2);
-
-  // ---- LUT node(s) of the graph: a per-lane bit per node, then one count and one minimum over the 8 lanes
-  int cnt = 0, il = -1;
-  {
-    unsigned m = 0u;
-#pragma unroll
-    for (int r = 0; r < kMaxN / 8; ++r) {
-      const int node = sl + 8 * r;
-      if (node < n && (kXG ? flag[r] : sx[node * kF + lut_col]) == 1.0f) m |= 1u << r;
-    }
-    cnt = __popc(m);
-    int first = m ? 8 * (__ffs(m) - 1) + sl : 0x7fff;
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-      cnt += __shfl_xor_sync(kFull, cnt, o);
-      first = min(first, __shfl_xor_sync(kFull, first, o));
-    }
-    if (cnt) il = first;
-  }
-  bool ok = fits && cnt == 1 && (l1 - l0) == 1;      // fast row: exactly one LUT node, as lut_ptr says
-  if (fits && sl == 0 && cnt != l1 - l0) atomicOr(status, 1);   // lut_ptr does not describe this x
-
-  // ---- in-edges of the LUT node: lane sl scans edges [sl*c, sl*c + c) of its graph (c odd: the
-  // 8-byte reads of the 8 lanes fall into distinct banks); one predicate per slot
-  int* msg = sm.msg[gl];
-  int mc = 0;
-  {
-    const int c = ((ne + 7) >> 3) | 1;
-    const int eb = sl * c;
-    const int tmax = ok ? min(c, ne - eb) : 0;
-    const int cmax = __reduce_max_sync(kFull, tmax);
-    const long long target = n0 + il;
-    const int tlo = static_cast<int>(target), thi = static_cast<int>(target >> 32);
-    // unconditional 8-byte reads: slots past the lane's run stay inside the block's shared memory (the
-    // window is followed by the z rows) and are masked by t < tmax
-    const int2* sde = reinterpret_cast<const int2*>(sd + eb);
-    unsigned hm = 0u;
-#pragma unroll
-    for (int t4 = 0; t4 < 32; t4 += 4) {
-      if (t4 < cmax) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int t = t4 + i;
-          if (t < 31) {
-            const int2 d = sde[t];
-            // two chained predicates and one predicated OR per slot (the compiler's own select chain
-            // costs twice that); slots past the run are masked once, below
-            asm("{ .reg .pred p;\n\t"
-                "setp.eq.s32 p, %1, %3;\n\t"
-                "setp.eq.and.s32 p, %2, %4, p;\n\t"
-                "@p or.b32 %0, %0, %5; }"
-                : "+r"(hm) : "r"(d.x), "r"(d.y), "r"(tlo), "r"(thi), "r"(1u << t));
-          }
-        }
-      }
-    }
-    hm &= (1u << max(tmax, 0)) - 1u;                   // tmax <= 31
-    const int h = __popc(hm);
-    int incl = h;
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-      const int up = __shfl_up_sync(kFull, incl, o, 8);
-      if (sl >= o) incl += up;
-    }
-    mc = __shfl_sync(kFull, incl, base + 7);
-    int pos = incl - h;
-    while (hm) {
-      const int t = __ffs(hm) - 1;
-      hm &= hm - 1u;
-      if (pos < kSubMsg - 1) msg[pos] = eb + t;
-      ++pos;
-    }
-  }
-  if (mc > kSubMsg - 1) ok = false;                  // hub row: generic path
-  __syncwarp();
-  // sources of those edges (one gather per 8); self loops / out-of-range ids dropped, order kept
-  {
-    int kept = 0;
-    bool outside = false;
-#pragma unroll
-    for (int t0 = 0; t0 < kSubMsg; t0 += 8) {
-      if (__any_sync(kFull, ok && t0 < mc)) {
-        const int t = t0 + sl;
-        long long sj = -1;
-        if (ok && t < mc) sj = esrc[e0 + msg[t]];
-        const bool inN = static_cast<uint64_t>(sj) < static_cast<uint64_t>(N);
-        const long long sloc = sj - n0;
-        const bool inslab = sloc >= 0 && sloc < n;
-        const bool keep = inslab && sloc != il;
-        outside |= ((__ballot_sync(kFull, inN && !inslab) >> (8 * sg)) & 0xffu) != 0u;
-        const unsigned sub = (__ballot_sync(kFull, keep) >> (8 * sg)) & 0xffu;
-        __syncwarp();
-        if (keep) msg[kept + __popc(sub & ((1u << sl) - 1u))] = static_cast<int>(sloc);
-        kept += __popc(sub);
-        __syncwarp();
-      }
-    }
-    if (outside) ok = false;                          // a source outside the slab: generic path
-    mc = kept;
-  }
-  if (ok && sl == 0) msg[mc] = il;                    // the appended self loop comes last
-  ++mc;
-  __syncwarp();
-  LPB_TRACE(3);
-
-  // ---- attention: lane = message slot, all 4 heads per lane.  The 24 sums per graph (4 heads x
-  // (x0..x4, 1)) are reduce-scattered: three exchange steps, each lane sends the half it does not
-  // keep -- statically the upper half of its registers thanks to the slot permutation
-  {
-    float d[kHeads];
-    const int ils = ok ? il : 0;
-#pragma unroll
-    for (int i = 0; i < kHeads; ++i) d[i] = 0.f;
-#pragma unroll
-    for (int k = 0; k < kF; ++k) {
-      const float xi = sx[ils * kF + k];
-      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffAdP) + hx * kF + k);
-      d[0] = fmaf(xi, b.x, d[0]); d[1] = fmaf(xi, b.y, d[1]);
-      d[2] = fmaf(xi, b.z, d[2]); d[3] = fmaf(xi, b.w, d[3]);
-    }
-    float mx[kHeads], acc3[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < kHeads; ++i) mx[i] = -INFINITY;
-    const int o0 = odd ? 3 : 0;
-#pragma unroll
-    for (int r0 = 0; r0 < kSubMsg; r0 += 8) {
-      if (__any_sync(kFull, ok && r0 < mc)) {
-        const bool valid = ok && r0 + sl < mc;
-        const float* xr = sx + (valid ? msg[r0 + sl] : 0) * kF;
-        float q[6];
-        const float x2 = xr[2];
-        q[0] = xr[o0]; q[1] = xr[o0 + 1]; q[3] = xr[3 - o0]; q[4] = xr[4 - o0];
-        q[2] = odd ? 1.0f : x2;
-        q[5] = odd ? x2 : 1.0f;
-        float a[kHeads], mr[kHeads], m2[kHeads];
-#pragma unroll
-        for (int i = 0; i < kHeads; ++i) {
-          float t = d[i];
-#pragma unroll
-          for (int m = 0; m < 6; ++m) t = fmaf(q[m], AsP[m][i], t);    // the ONE slot carries weight 0
-          t = t > 0.f ? t : 0.2f * t;
-          a[i] = valid ? t : -INFINITY;
-        }
-        // per-head maximum over the 8 lanes: the partner's slot for MY head i is i (xor 1: same
-        // permutation), i ^ 1 (xor 2) and i ^ 2 (xor 4) -- register renaming, no selects
-#pragma unroll
-        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(a[i], __shfl_xor_sync(kFull, a[i], 1));
-#pragma unroll
-        for (int i = 0; i < kHeads; ++i) m2[i] = fmaxf(mr[i], __shfl_xor_sync(kFull, mr[i ^ 1], 2));
-#pragma unroll
-        for (int i = 0; i < kHeads; ++i) mr[i] = fmaxf(m2[i], __shfl_xor_sync(kFull, m2[i ^ 2], 4));
-        float v[24];
-        float scarg = 0.f;
-#pragma unroll
-        for (int i = 0; i < kHeads; ++i) {
-          const float mn = fmaxf(fmaxf(mx[i], mr[i]), -1e30f);   // idle sub-groups stay finite
-          const float p = valid ? expf(a[i] - mn) : 0.f;
-#pragma unroll
-          for (int m = 0; m < 6; ++m) v[i * 6 + m] = p * q[m];
-          if (i == 0) scarg = mx[0] - mn;                     // -inf in the first round: exp -> 0
-          mx[i] = mn;
-        }
-        float u[12], s6[6], w3[3];
-#pragma unroll
-        for (int t = 0; t < 12; ++t) u[t] = v[t] + __shfl_xor_sync(kFull, v[t + 12], 4);
-#pragma unroll
-        for (int t = 0; t < 6; ++t) s6[t] = u[t] + __shfl_xor_sync(kFull, u[t + 6], 2);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) w3[t] = s6[t] + __shfl_xor_sync(kFull, s6[t + 3], 1);
-        const float sc = expf(scarg);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) acc3[t] = fmaf(acc3[t], sc, w3[t]);
-      }
-    }
-    // even lane: sums x0..x2 of head sl>>1; odd lane: x3, x4 and the softmax denominator
-    const float den_other = __shfl_xor_sync(kFull, acc3[2], 1);
-    const float inv = 1.0f / ((odd ? acc3[2] : den_other) + 1e-16f);
-    if (ok) {
-      if (kFused) {
-        float zv[3];
-        zv[0] = acc3[0] * inv;
-        zv[1] = acc3[1] * inv;
-        zv[2] = odd ? 1.0f : acc3[2] * inv;            // slot 5 of the head row multiplies the shift row
-        const int zo = gl * kZStride + hx * 8 + o0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float hi = kTC ? __uint_as_float(tf32_rna(zv[i])) : zv[i];
-          sm.zhi[zo + i] = hi;
-          if (kTC) sm.zlo[zo + i] = __uint_as_float(tf32_rna(zv[i] - hi));
-        }
-        if (kTC && odd) {
-          sm.zhi[zo + 3] = 0.f; sm.zhi[zo + 4] = 0.f;
-          sm.zlo[zo + 3] = 0.f; sm.zlo[zo + 4] = 0.f;
-        }
-      } else {
-        float* zr = zbuf + l0 * kZRow + hx * kF + o0;
-        zr[0] = acc3[0] * inv;
-        zr[1] = acc3[1] * inv;
-        if (!odd) zr[2] = acc3[2] * inv;
-      }
-      if (sl == 0) {
-        lut_batch[l0] = g;
-        lut_node[l0] = static_cast<int32_t>(n0 + il);
-      }
-    }
-  }
-  LPB_TRACE(4);
-
-  const int my_state = ok ? 1 : (active && (!fits || (cnt == l1 - l0 && cnt > 0)) ? 2 : 0);
-  if constexpr (kFused) {
-  if (sl == 0) {
-    SubMeta& mt = sm.meta[gl];
-    mt.n0 = n0; mt.n1 = n1; mt.e0 = e0; mt.e1 = e1; mt.l0 = l0; mt.l1 = l1;
-    mt.il = il;
-    mt.state = my_state;
-  }
-  const int any_generic = __syncthreads_or(sl == 0 && my_state == 2);   // z rows staged; the slab is dead from here
-  LPB_TRACE(5);
-
-  // ---- readout head.  kTC: on the tensor cores (mma.sync TF32 x3), warp w owns channels 16w .. 16w+15.
-  // !kTC: the same decomposition on the FP32 pipe -- exact fp32 arithmetic, and on this part (the
-  // legacy mma.sync path of sm_100 issues one m16n8k8 TF32 MMA per ~20 cycles per scheduler and holds
-  // the issue port meanwhile) also the faster of the two: measured in profiles/r1_summary.md
-  float* red = reinterpret_cast<float*>(sm.slab) + (kTC ? 0 : kHC * kZStride);
-  if constexpr (!kTC) {
-    float* ybuf = reinterpret_cast<float*>(sm.slab);          // y[c][row], row stride kZStride (16-byte aligned quads)
-    {
-      // y = relu(z_h Wf_h + shift): lane = (channel 16w + (lane & 15), 16 of the 32 rows)
-      const int c = 16 * warp + (lane & 15), hh = warp >> 1, rh = lane >> 4;
-      const float* __restrict__ wf = prep + kOffWf + hh * kF * kC + (c & 31);
-      const float w0 = __ldg(wf), w1 = __ldg(wf + kC), w2 = __ldg(wf + 2 * kC), w3 = __ldg(wf + 3 * kC),
-                  w4 = __ldg(wf + 4 * kC), sh = __ldg(prep + kOffShift + c);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = 16 * rh + i;
-        const float4 z4 = *reinterpret_cast<const float4*>(sm.zhi + r * kZStride + hh * 8);
-        const float z5 = sm.zhi[r * kZStride + hh * 8 + 4];
-        float y = sh;
-        y = fmaf(z4.x, w0, y); y = fmaf(z4.y, w1, y); y = fmaf(z4.z, w2, y); y = fmaf(z4.w, w3, y);
-        y = fmaf(z5, w4, y);
-        ybuf[c * kZStride + r] = fmaxf(y, 0.f);
-      }
-    }
-    __syncwarp();                                       // a warp consumes exactly the channels it produced
-    {
-      // partial h = y W1^T over the warp's 16 channels: lane tile = rows 4rq..4rq+3 x units 8uq..8uq+7
-      const int rq = lane & 7, uq = lane >> 3;
-      float acc[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-      for (int kk = 0; kk < 16; ++kk) {
-        const int c = 16 * warp + kk;
-        const float4 y4 = *reinterpret_cast<const float4*>(ybuf + c * kZStride + 4 * rq);
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(prep + kOffW1t + c * kHid + 8 * uq));
-        const float4 wb = __ldg(reinterpret_cast<const float4*>(prep + kOffW1t + c * kHid + 8 * uq + 4));
-        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(yv[i], wv[j], acc[i][j]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[(warp * 32 + i * 8 + j) * 32 + lane] = acc[i][j];
-    }
-    __syncthreads();
-    LPB_TRACE(6);
-    // warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp w finishes rows 4rq + w
-    if (warp < 4) {
-      const int rq = lane & 7, uq = lane >> 3;
-      float o3[QOT_OUT] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float h = 0.f;
-#pragma unroll
-        for (int pw = 0; pw < 8; ++pw) h += red[(pw * 32 + warp * 8 + j) * 32 + lane];
-        h += __ldg(prep + kOffB1 + 8 * uq + j);
-        h = h > 0.f ? h : 0.01f * h;
-#pragma unroll
-        for (int k = 0; k < QOT_OUT; ++k) o3[k] = fmaf(h, __ldg(prep + kOffW2 + k * kHid + 8 * uq + j), o3[k]);
-      }
-#pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-#pragma unroll
-        for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
-      }
-      const SubMeta& mt = sm.meta[4 * rq + warp];
-      if (mt.state == 1 && uq < QOT_OUT)
-        out[mt.l0 * QOT_OUT + uq] = (uq == 0 ? o3[0] : uq == 1 ? o3[1] : o3[2]) + __ldg(prep + kOffB2 + uq);
-    }
-  } else {
-  {
-    const int g8 = lane >> 2, t4 = lane & 3;
-    unsigned ahi[2][4], alo[2][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const int o = (16 * m + g8) * kZStride + (warp >> 1) * 8 + t4;
-      ahi[m][0] = __float_as_uint(sm.zhi[o]);
-      ahi[m][1] = __float_as_uint(sm.zhi[o + 8 * kZStride]);
-      ahi[m][2] = __float_as_uint(sm.zhi[o + 4]);
-      ahi[m][3] = __float_as_uint(sm.zhi[o + 8 * kZStride + 4]);
-      alo[m][0] = __float_as_uint(sm.zlo[o]);
-      alo[m][1] = __float_as_uint(sm.zlo[o + 8 * kZStride]);
-      alo[m][2] = __float_as_uint(sm.zlo[o + 4]);
-      alo[m][3] = __float_as_uint(sm.zlo[o + 8 * kZStride + 4]);
-    }
-    float H[2][4][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) H[m][q][i] = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = 2 * warp + jj;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + j * 32 + lane);
-      unsigned yhi[2][4], ylo[2][4];
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(c, alo[m], b.x, b.y);
-        mma_tf32(c, ahi[m], b.z, b.w);
-        mma_tf32(c, ahi[m], b.x, b.y);
-        // ReLU, split, and C -> A fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3)
-        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          yhi[m][i] = tf32_rna_finite(y[i]);               // y >= 0; an Inf keeps hi = Inf, lo = NaN
-          ylo[m][i] = tf32_rna_finite(y[i] - __uint_as_float(yhi[m][i]));
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(prep + kOffB2f) + (j * 4 + q) * 32 + lane);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_tf32(H[m][q], ylo[m], b2.x, b2.y);
-          mma_tf32(H[m][q], yhi[m], b2.z, b2.w);
-          mma_tf32(H[m][q], yhi[m], b2.x, b2.y);
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) red[(warp * 32 + (m * 4 + q) * 4 + i) * 32 + lane] = H[m][q][i];
-  }
-  __syncthreads();
-  LPB_TRACE(6);
-  // ---- warps 0..3: fixed-order sum of the 8 partials, + b1, LeakyReLU, mlp.3; warp = (m-tile, row half)
-  if (warp < 4) {
-    const int g8 = lane >> 2, t4 = lane & 3, m = warp >> 1, upper = warp & 1;
-    float o3[QOT_OUT] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int o = 8 * q + 2 * t4;
-      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
-      float hv[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int reg = (m * 4 + q) * 4 + upper * 2 + p;
-        float h = 0.f;
-#pragma unroll
-        for (int pw = 0; pw < 8; ++pw) h += red[(pw * 32 + reg) * 32 + lane];
-        h += p ? b1.y : b1.x;
-        hv[p] = h > 0.f ? h : 0.01f * h;
-      }
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) {
-        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
-        o3[k] = fmaf(hv[0], w2.x, o3[k]);
-        o3[k] = fmaf(hv[1], w2.y, o3[k]);
-      }
-    }
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) o3[k] += __shfl_xor_sync(kFull, o3[k], o);
-    }
-    const int r = 16 * m + 8 * upper + g8;            // graph slot of this row
-    const SubMeta& mt = sm.meta[r];
-    if (mt.state == 1) {
-      if (t4 < QOT_OUT) {
-        const float ov = (t4 == 0 ? o3[0] : t4 == 1 ? o3[1] : o3[2]) + __ldg(prep + kOffB2 + t4);
-        out[mt.l0 * QOT_OUT + t4] = ov;
-      }
-    }
-  }
-
-  }
-
-  // ---- generic path for the graphs the fast path declined (one warp per graph)
-  if (any_generic) {
-    __syncthreads();                                  // the partial products have been consumed
-    const float* __restrict__ wh = prep + kOffWf;
-    for (int gs = warp; gs < kGPB; gs += 8) {
-      if (sm.meta[gs].state != 2) continue;
-      const SubMeta mt = sm.meta[gs];
-      const int64_t gg = g0 + gs;
-      float* s_y = red + warp * 256;
-      float* s_z = s_y + kHC;
-      int* s_m = reinterpret_cast<int*>(s_y + kHC + 32);
-      int64_t orow = mt.l0;
-      int found = 0;
-      for (int64_t nb = mt.n0; nb < mt.n1; nb += 32) {
-        const int64_t node = nb + lane;
-        unsigned mask = __ballot_sync(kFull, node < mt.n1 && x[node * kF + lut_col] == 1.0f);
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          ++found;
-          if (orow < mt.l1) {                                      // never write past this graph's rows
-            const int64_t i = nb + bit;
-            const float ov = lut_row_global(x, esrc, edst, mt.e0, mt.e1, N, i, prep, wh, s_m, s_z, s_y, lane);
-            if (lane < QOT_OUT) out[orow * QOT_OUT + lane] = ov;
-            if (lane == 0) {
-              lut_batch[orow] = gg;
-              lut_node[orow] = static_cast<int32_t>(i);
-            }
-            ++orow;
-          }
-        }
-      }
-      if (lane == 0 && found != mt.l1 - mt.l0) atomicOr(status, 1);
-    }
-  }
-  LPB_TRACE(7);
-  LPB_TRACE_FLUSH();
-  return;
-  }
-  // ---- generic path: graphs of this warp the fast path declined (one warp per graph, global memory)
-  if (__any_sync(kFull, my_state == 2)) {
-#pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-      if (__shfl_sync(kFull, my_state, 8 * s) != 2) continue;
-      const int64_t gn0 = __shfl_sync(kFull, n0, 8 * s), gn1 = __shfl_sync(kFull, n1, 8 * s);
-      const int64_t ge0 = __shfl_sync(kFull, e0, 8 * s), ge1 = __shfl_sync(kFull, e1, 8 * s);
-      const int64_t gl0 = __shfl_sync(kFull, l0, 8 * s), gl1 = __shfl_sync(kFull, l1, 8 * s);
-      float* s_z = sm.gen[warp];
-      int* s_m = reinterpret_cast<int*>(sm.gen[warp] + 32);
-      int64_t orow = gl0;
-      int found = 0;
-      for (int64_t nb = gn0; nb < gn1; nb += 32) {
-        const int64_t node = nb + lane;
-        unsigned mask = __ballot_sync(kFull, node < gn1 && x[node * kF + lut_col] == 1.0f);
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          ++found;
-          if (orow < gl1) {                                      // never write past this graph's rows
-            const int64_t i = nb + bit;
-            lut_row_global<false>(x, esrc, edst, ge0, ge1, N, i, prep, nullptr, s_m, s_z, nullptr, lane);
-            if (lane < kZRow) zbuf[orow * kZRow + lane] = s_z[(lane / kF) * 8 + lane % kF];
-            if (lane == 0) {
-              lut_batch[orow] = g0 + warp * 4 + s;
-              lut_node[orow] = static_cast<int32_t>(i);
-            }
-            __syncwarp();
-            ++orow;
-          }
-        }
-      }
-      if (lane == 0 && found != gl1 - gl0) atomicOr(status, 1);
-    }
-  }
-  LPB_TRACE(7);
-  LPB_TRACE_FLUSH();
-}
-
-// Readout head over the L = lut_ptr[B] rows of z: a block stages the 40 KB of pre-split B fragments in
-// shared memory once and each of its 4 warps takes 16 rows (64 rows per block: 64 blocks for a 4096-row
-// batch, so the fragments cross L2 -> SM 64 times per batch, not once per 16 rows); everything else
-// stays in registers, no block barrier after the staging.
-//   y = relu(z_h Wf_h + shift)  (16 n-tiles, K = 8 per head: x0..x4, the constant 1 against the shift row)
-//   h = y W1^T                  (each y tile is at once the next product's A fragment)
-//   out = leaky(h + b1) W2^T + b2
-// Accuracy: the tensor cores truncate when they add into a running accumulator, so the large
-// (hi x hi) terms are produced by stand-alone MMAs and added in fp32 on the CUDA cores; only the small
-// compensation terms (lo x hi + hi x lo) chain inside an accumulator.
-constexpr int kHeadFrag4 = (kOffAsP - kOffB1f) / 4;   // float4 entries of B1f | B2f (contiguous in `prepared`)
-__global__ void __launch_bounds__(128)
-lp_head_kernel(const float* __restrict__ zbuf, const int64_t* __restrict__ lptr, int64_t B,
-               const float* __restrict__ prep, float* __restrict__ out) {
-  __shared__ float4 frag[kHeadFrag4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
-  const int64_t L = lptr[B];
-  if (static_cast<int64_t>(blockIdx.x) * 64 >= L) return;
-  for (int i = tid; i < kHeadFrag4; i += 128) frag[i] = __ldg(reinterpret_cast<const float4*>(prep + kOffB1f) + i);
-  __syncthreads();
-  const float4* __restrict__ f1 = frag;
-  const float4* __restrict__ f2 = frag + 16 * 32;
-  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + warp; tile * 16 < L;
-       tile += static_cast<int64_t>(gridDim.x) * 4) {
-    const int64_t ra = tile * 16 + g8, rb = ra + 8;
-    const bool va = ra < L, vb = rb < L;
-    const float* za = zbuf + ra * kZRow;
-    const float* zb = zbuf + rb * kZRow;
-    float H[4][4], Hc[4][4];                           // fp32 sums of the hi x hi tiles; compensation chains
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) H[q][i] = Hc[q][i] = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < kHeads; ++h) {
-      // A fragment of head h: rows (g8, g8+8), k slots (t4, t4+4): x_t4 | x4, 1, 0, 0
-      unsigned ahi[4], alo[4];
-      {
-        float a[4];
-        a[0] = va ? za[h * kF + t4] : 0.f;
-        a[1] = vb ? zb[h * kF + t4] : 0.f;
-        a[2] = t4 == 0 ? (va ? za[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
-        a[3] = t4 == 0 ? (vb ? zb[h * kF + 4] : 0.f) : (t4 == 1 ? 1.0f : 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ahi[i] = tf32_rna(a[i]);
-          alo[i] = tf32_rna(a[i] - __uint_as_float(ahi[i]));
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = 4 * h + jj;
-        const float4 b = f1[j * 32 + lane];
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(c, alo, b.x, b.y);
-        mma_tf32(c, ahi, b.z, b.w);
-        mma_tf32(c, ahi, b.x, b.y);
-        // ReLU, split, and C -> A fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3)
-        const float y[4] = {fmaxf(c[0], 0.f), fmaxf(c[2], 0.f), fmaxf(c[1], 0.f), fmaxf(c[3], 0.f)};
-        unsigned yhi[4], ylo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          yhi[i] = tf32_rna_finite(y[i]);
-          ylo[i] = tf32_rna_finite(y[i] - __uint_as_float(yhi[i]));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b2 = f2[(j * 4 + q) * 32 + lane];
-          mma_tf32(Hc[q], ylo, b2.x, b2.y);
-          mma_tf32(Hc[q], yhi, b2.z, b2.w);
-          float t[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_tf32(t, yhi, b2.x, b2.y);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) H[q][i] += t[i];
-        }
-      }
-    }
-    // H[q]: rows (g8: regs 0,1 | g8+8: regs 2,3), hidden units 8q + 2*t4 + (0,1)
-    float oa[QOT_OUT] = {0.f, 0.f, 0.f}, ob[QOT_OUT] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int o = 8 * q + 2 * t4;
-      const float2 b1 = __ldg(reinterpret_cast<const float2*>(prep + kOffB1 + o));
-      float hv[4] = {H[q][0] + Hc[q][0] + b1.x, H[q][1] + Hc[q][1] + b1.y, H[q][2] + Hc[q][2] + b1.x,
-                     H[q][3] + Hc[q][3] + b1.y};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) hv[i] = hv[i] > 0.f ? hv[i] : 0.01f * hv[i];
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) {
-        const float2 w2 = __ldg(reinterpret_cast<const float2*>(prep + kOffW2 + k * kHid + o));
-        oa[k] = fmaf(hv[0], w2.x, oa[k]);
-        oa[k] = fmaf(hv[1], w2.y, oa[k]);
-        ob[k] = fmaf(hv[2], w2.x, ob[k]);
-        ob[k] = fmaf(hv[3], w2.y, ob[k]);
-      }
-    }
-#pragma unroll
-    for (int s = 1; s <= 2; s <<= 1) {
-#pragma unroll
-      for (int k = 0; k < QOT_OUT; ++k) {
-        oa[k] += __shfl_xor_sync(kFull, oa[k], s);
-        ob[k] += __shfl_xor_sync(kFull, ob[k], s);
-      }
-    }
-    if (t4 < QOT_OUT) {
-      const float b2 = __ldg(prep + kOffB2 + t4);
-      if (va) out[ra * QOT_OUT + t4] = (t4 == 0 ? oa[0] : t4 == 1 ? oa[1] : oa[2]) + b2;
-      if (vb) out[rb * QOT_OUT + t4] = (t4 == 0 ? ob[0] : t4 == 1 ? ob[1] : ob[2]) + b2;
-    }
-  }
-}
-
 }  // namespace qot
 
 using namespace qot;
 
-#ifdef QOT_LP_TRACE
-extern "C" int qot_debug_set_lp_trace(unsigned long long* buf) {
-  return cudaMemcpyToSymbol(g_lp_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
-}
-#endif
-
 extern "C" size_t qot_lightpath_prepared_floats(void) { return kPreparedFloats; }
+extern "C" size_t qot_lightpath_infer_workspace_bytes(int64_t N) {
+  return N > 0 ? align_up(static_cast<size_t>(N) * kHeads * kF * 4) : 256;
+}
 
 extern "C" int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -930,185 +163,3 @@ extern "C" int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_
   return QOT_OK;
 }
 
-// 0: one warp per graph (lp_infer_kernel); 1: 8 lanes per graph (lp_infer_sub_kernel);
-// 2 (default): lp_attn_kernel<.., kFused = true>: 8 lanes per graph, bulk-copied slabs, tensor-core readout
-// head in the same launch; 3: lp_attn_kernel<.., false> (z rows into the workspace) + lp_head_kernel
-static int g_lp_variant = 2;
-extern "C" int qot_lightpath_set_variant(int v) {
-  if (v < 0 || v > 4) return QOT_E_BADARG;
-  g_lp_variant = v;
-  return QOT_OK;
-}
-extern "C" int qot_lightpath_get_variant(void) { return g_lp_variant; }
-
-static_assert(3 * (sizeof(AttnSmem<false, true>) + 1024) <= 228 * 1024, "the fused kernel must keep 3 blocks per SM");
-static_assert(3 * (sizeof(AttnSmem<false, false>) + 1024) <= 228 * 1024, "the attention kernel must keep 3 blocks per SM");
-static_assert(sizeof(AttnSmem<true, true>::slab) >= 8 * 32 * 32 * 4, "slab is reused for the 8 partial [32x32] products");
-static_assert(sizeof(AttnSmem<false, true>::slab) >= (kHC * kZStride + 8 * 32 * 32) * 4, "slab is reused for y and the partial products");
-#ifndef QOT_LP_FUSED_XG
-#define QOT_LP_FUSED_XG 0                 // 1: the fused kernel reads node features from global memory (4 blocks per SM)
-#endif
-constexpr bool kFusedXG = QOT_LP_FUSED_XG != 0;
-static int lp_infer_launch(const float* x, const int64_t* esrc, const int64_t* edst,
-                           const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr, int64_t N,
-                           int64_t E, int64_t B, const float* prepared, int32_t is_lut_index, float* out,
-                           int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut, int32_t* status,
-                           float* zbuf, cudaStream_t stream) {
-  if (g_lp_variant == 3) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(AttnSmem<false, false>))));
-      // the head kernel uses no shared memory, but it runs between attention kernels that need the
-      // largest carve-out: asking for the same split keeps the SMs from reconfiguring (and draining)
-      QOT_CUDA(cudaFuncSetAttribute(lp_head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
-      attr_set = true;
-    }
-    const int64_t blocks = cdiv(B, kGPB);
-    lp_attn_kernel<false, false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false, false>), stream>>>(
-        x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, zbuf, out, lut_batch, lut_node, n_lut, status);
-    QOT_LAUNCH_CHECK();
-    // one block per 64 rows; L is only known on the device: the grid covers the common case (about one
-    // LUT row per graph) and the blocks stride over any further tiles
-    const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(std::min(N, B), 64), 4 * kNumSMs));
-    lp_head_kernel<<<static_cast<unsigned>(hb), 128, 0, stream>>>(zbuf, lut_ptr, B, prepared, out);
-    QOT_LAUNCH_CHECK();
-    return QOT_OK;
-  }
-  if (g_lp_variant == 2 || g_lp_variant == 4) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<kFusedXG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(AttnSmem<kFusedXG, true>))));
-      QOT_CUDA(cudaFuncSetAttribute(lp_attn_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(AttnSmem<false, true>))));
-      attr_set = true;
-    }
-    const int64_t blocks = cdiv(B, kGPB);
-    if (g_lp_variant == 4)
-      lp_attn_kernel<false, true, false><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<false, true>), stream>>>(
-          x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, nullptr, out, lut_batch, lut_node, n_lut, status);
-    else
-    lp_attn_kernel<kFusedXG, true, true><<<static_cast<unsigned>(blocks), 256, sizeof(AttnSmem<kFusedXG, true>), stream>>>(
-        x, esrc, edst, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, nullptr, out, lut_batch, lut_node, n_lut, status);
-    QOT_LAUNCH_CHECK();
-    return QOT_OK;
-  }
-  return lp_infer_launch_legacy(g_lp_variant, x, esrc, edst, gptr, eptr, lut_ptr, N, B, prepared, is_lut_index, out, lut_batch,
-                                lut_node, n_lut, status, stream);
-}
-
-extern "C" size_t qot_lightpath_infer_workspace_bytes(int64_t N) {
-  return N > 0 ? align_up(static_cast<size_t>(N) * kZRow * 4) : 256;
-}
-
-extern "C" int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
-                                   const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
-                                   int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
-                                   float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                                   int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(N >= 0 && B >= 0 && E >= 0, "qot_lightpath_infer: negative size");
-  QOT_REQUIRE(N < (1ll << 31) - 1, "qot_lightpath_infer: N exceeds int32 range");
-  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer: is_lut_index out of range");
-  QOT_REQUIRE(gptr && eptr && lut_ptr && prepared && n_lut && status, "qot_lightpath_infer: null argument");
-  QOT_REQUIRE(N == 0 || (x && out && lut_batch && lut_node), "qot_lightpath_infer: null buffer");
-  QOT_REQUIRE(E == 0 || edge_index, "qot_lightpath_infer: null edge_index");
-  QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer: prepared must be 16-byte aligned");
-  QOT_REQUIRE(ws && ws_bytes >= qot_lightpath_infer_workspace_bytes(N) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
-              "qot_lightpath_infer: workspace missing, misaligned or smaller than qot_lightpath_infer_workspace_bytes(N)");
-  if (B == 0) {
-    QOT_CUDA(cudaMemsetAsync(n_lut, 0, 4, stream));
-    return QOT_OK;
-  }
-  return lp_infer_launch(x, edge_index, edge_index + E, gptr, eptr, lut_ptr, N, E, B, prepared, is_lut_index, out,
-                         lut_batch, lut_node, n_lut, status, static_cast<float*>(ws), stream);
-}
-
-// Host-buffer form of the same call: the batch lives in PINNED HOST memory in the reference layout.
-// Enqueues, on `stream`: H2D of x, of the DESTINATION row of edge_index and of the three offset
-// arrays into the caller's device staging slot; the kernel (the source row is not copied -- the
-// few entries the readout needs, one 32-byte sector per in-edge of a LUT node, are read by the
-// kernel straight from the pinned host buffer over PCIe); D2H of out / lut_batch rows [0, L) and
-// the status word, L = lut_ptr_host[B].  Nothing synchronises: the caller waits on its own event.
-extern "C" int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,
-                                        const int64_t* gptr_host, const int64_t* eptr_host,
-                                        const int64_t* lut_ptr_host, int64_t N, int64_t B,
-                                        const float* prepared, int32_t is_lut_index,
-                                        const qot_lp_slot_t* slot, float* out_host,
-                                        int64_t* lut_batch_host, int32_t* status_host,
-                                        int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(N > 0 && B > 0 && E >= 0, "qot_lightpath_infer_host: empty batch");
-  QOT_REQUIRE(N < (1ll << 31) - 1, "qot_lightpath_infer_host: N exceeds int32 range");
-  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_host: is_lut_index out of range");
-  QOT_REQUIRE(x_host && gptr_host && eptr_host && lut_ptr_host && prepared && slot && out_host &&
-                  lut_batch_host && status_host && (E == 0 || edge_index_host),
-              "qot_lightpath_infer_host: null argument");
-  QOT_REQUIRE(slot->x && slot->edge_dst && slot->ptrs && slot->out && slot->lut_batch && slot->lut_node &&
-                  slot->n_lut && slot->status && slot->z, "qot_lightpath_infer_host: incomplete staging slot");
-  QOT_REQUIRE(N <= slot->cap_nodes && E <= slot->cap_edges && B <= slot->cap_graphs,
-              "qot_lightpath_infer_host: batch (N=%lld, E=%lld, B=%lld) exceeds the slot capacity",
-              (long long)N, (long long)E, (long long)B);
-  QOT_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, "qot_lightpath_infer_host: prepared must be 16-byte aligned");
-  const int64_t L = lut_ptr_host[B];
-  QOT_REQUIRE(L >= 0 && L <= N, "qot_lightpath_infer_host: lut_ptr_host[B] out of range");
-  // contiguous host batch [dst row | gptr | eptr | lut_ptr | x] and an arena in the slot: one copy
-  const bool merged = slot->arena && E > 0 && gptr_host == edge_index_host + 2 * E &&
-                      eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1) &&
-                      reinterpret_cast<const char*>(x_host) == reinterpret_cast<const char*>(lut_ptr_host + (B + 1));
-  // device view of the pinned source row (UVA: identical address; asked for explicitly so that
-  // unmapped host memory is refused instead of faulting in the kernel)
-  const int64_t* esrc_dev = nullptr;
-  int64_t copied = 0;
-  if (E > 0) {
-    void* dp = nullptr;
-    if (cudaHostGetDevicePointer(&dp, const_cast<int64_t*>(edge_index_host), 0) == cudaSuccess && dp) {
-      esrc_dev = static_cast<const int64_t*>(dp);
-    } else {
-      (void)cudaGetLastError();
-      QOT_REQUIRE(slot->edge_src, "qot_lightpath_infer_host: edge_index_host is not device-mapped pinned memory "
-                                  "and the slot has no edge_src staging buffer");
-      QOT_CUDA(cudaMemcpyAsync(slot->edge_src, edge_index_host, E * 8, cudaMemcpyHostToDevice, stream));
-      esrc_dev = slot->edge_src;
-      copied += E * 8;
-    }
-    if (!merged) QOT_CUDA(cudaMemcpyAsync(slot->edge_dst, edge_index_host + E, E * 8, cudaMemcpyHostToDevice, stream));
-  }
-  const float* x_dev = slot->x;
-  const int64_t* edst_dev = slot->edge_dst;
-  int64_t* gptr = slot->ptrs;
-  if (merged) {
-    char* a = static_cast<char*>(slot->arena);
-    QOT_CUDA(cudaMemcpyAsync(a, edge_index_host + E, E * 8 + 3 * (B + 1) * 8 + N * kF * 4, cudaMemcpyHostToDevice, stream));
-    edst_dev = reinterpret_cast<const int64_t*>(a);
-    gptr = reinterpret_cast<int64_t*>(a + E * 8);
-    x_dev = reinterpret_cast<const float*>(a + E * 8 + 3 * (B + 1) * 8);
-  } else {
-    QOT_CUDA(cudaMemcpyAsync(slot->x, x_host, N * kF * 4, cudaMemcpyHostToDevice, stream));
-  }
-  int64_t* eptr = gptr + (B + 1);
-  int64_t* lptr = eptr + (B + 1);
-  if (merged) {
-  } else if (eptr_host == gptr_host + (B + 1) && lut_ptr_host == eptr_host + (B + 1)) {
-    // the three offset arrays are adjacent on the host (PackedGraphStore.host_batch): one copy
-    QOT_CUDA(cudaMemcpyAsync(gptr, gptr_host, 3 * (B + 1) * 8, cudaMemcpyHostToDevice, stream));
-  } else {
-    QOT_CUDA(cudaMemcpyAsync(gptr, gptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
-    QOT_CUDA(cudaMemcpyAsync(eptr, eptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
-    QOT_CUDA(cudaMemcpyAsync(lptr, lut_ptr_host, (B + 1) * 8, cudaMemcpyHostToDevice, stream));
-  }
-  copied += N * kF * 4 + E * 8 + 3 * (B + 1) * 8;
-  int rc = lp_infer_launch(x_dev, esrc_dev, edst_dev, gptr, eptr, lptr, N, E, B, prepared, is_lut_index,
-                           slot->out, slot->lut_batch, slot->lut_node, slot->n_lut, slot->status, slot->z, stream);
-  if (rc) return rc;
-  if (L > 0) {
-    QOT_CUDA(cudaMemcpyAsync(out_host, slot->out, L * QOT_OUT * 4, cudaMemcpyDeviceToHost, stream));
-    QOT_CUDA(cudaMemcpyAsync(lut_batch_host, slot->lut_batch, L * 8, cudaMemcpyDeviceToHost, stream));
-  }
-  QOT_CUDA(cudaMemcpyAsync(status_host, slot->status, 4, cudaMemcpyDeviceToHost, stream));
-  if (h2d_bytes) *h2d_bytes = copied;
-  if (d2h_bytes) *d2h_bytes = L * (QOT_OUT * 4 + 8) + 4;
-  return QOT_OK;
-}

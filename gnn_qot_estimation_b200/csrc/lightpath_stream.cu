@@ -1162,6 +1162,71 @@ lp_stream_head_kernel(const qot_lp_batch_t* __restrict__ batches, const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Compact wire format of a verified-layout batch (what travels over PCIe; qot_lightpath_infer_wire_host):
+//   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad16 | float x[N,5] | pad16 | uint8 dst[E]
+// dst = the destination of every edge as a GRAPH-LOCAL id (graphs of <= 255 nodes); no source row: under the
+// verified from_networkx layout (QOT_LP_SYMMETRIC_BY_SOURCE) the out-run of node u is edges
+// [#{dst < u}, #{dst <= u}) of its graph, so the sources are the run index.  776 B/graph at n = 32, E_g = 124
+// against 1 754 B/graph for the int64 destination row + offsets + x.
+// lp_wire_unpack_kernel rebuilds the reference layout ON THE DEVICE (int64 edge_index [2,E] with batch-global ids,
+// int64 ptr / edge_ptr / lut_ptr) and fills the sizes of the slot's batch descriptor; the
+// batch then goes through the same lp_stream_kernel as a resident batch (bit-identical rows).  One warp per graph.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lp_wire_unpack_kernel(const int32_t* __restrict__ wptr, const int32_t* __restrict__ weptr, const int32_t* __restrict__ wlptr,
+                      const uint8_t* __restrict__ wdst, int64_t N, int64_t E, int64_t B, int64_t* __restrict__ ptrs,
+                      int64_t* __restrict__ edge_index, qot_lp_batch_t* __restrict__ desc, const float* __restrict__ x) {
+  __shared__ int hist[8][257];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t gtid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (int64_t i = gtid; i < 3 * (B + 1); i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t which = i / (B + 1), j = i % (B + 1);
+    ptrs[i] = (which == 0 ? wptr : which == 1 ? weptr : wlptr)[j];
+  }
+  if (gtid == 0) {
+    desc->x = x;
+    desc->edge_index = edge_index;
+    desc->ptr = ptrs; desc->edge_ptr = ptrs + (B + 1); desc->lut_ptr = ptrs + 2 * (B + 1);
+    desc->N = N; desc->E = E; desc->B = B;
+    desc->tile0 = 0;
+  }
+  int* h = hist[w];
+  for (int64_t g = blockIdx.x * 8ll + w; g < B; g += static_cast<int64_t>(gridDim.x) * 8) {
+    const int n0 = wptr[g], n = wptr[g + 1] - n0, e0 = weptr[g], ne = weptr[g + 1] - e0;
+    if (n < 0 || n > 255 || ne < 0 || e0 < 0 || static_cast<int64_t>(e0) + ne > E) {
+      if (lane == 0) atomicOr(desc->status, 1);                      // malformed offsets: nothing is written for the graph
+      continue;
+    }
+    for (int i = lane; i <= n; i += 32) h[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < ne; i += 32) {
+      const int d = wdst[e0 + i];
+      edge_index[E + e0 + i] = n0 + d;                               // destination row
+      if (d < n) atomicAdd(&h[d + 1], 1); else atomicOr(desc->status, 1);
+    }
+    __syncwarp();
+    // exclusive prefix of the in-degree (= out-degree) histogram: h[u] = first edge of node u's run
+    int carry = 0;
+    for (int b0 = 0; b0 <= n; b0 += 32) {
+      const int i = b0 + lane;
+      int v = i <= n ? h[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += up;
+      }
+      if (i <= n) h[i] = v + carry;
+      carry += __shfl_sync(kFull, v, 31);
+    }
+    __syncwarp();
+    for (int u = lane; u < n; u += 32)
+      for (int e = h[u]; e < h[u + 1] && e < ne; ++e) edge_index[e0 + e] = n0 + u;   // source row
+    __syncwarp();
+  }
+}
+
 }  // namespace qot
 
 using namespace qot;
@@ -1223,5 +1288,53 @@ extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t
   const int64_t hb = std::max<int64_t>(1, std::min<int64_t>(cdiv(max_rows, 64), 4 * kNumSMs));
   lp_stream_head_kernel<<<dim3(static_cast<unsigned>(hb), static_cast<unsigned>(n_batches)), 128, 0, stream>>>(batches, prepared);
   QOT_LAUNCH_CHECK();
+  return QOT_OK;
+}
+
+static inline size_t wire_align16(size_t v) { return (v + 15) & ~size_t(15); }
+extern "C" size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B) {
+  if (N < 0 || E < 0 || B < 0) return 0;
+  return wire_align16(12 * static_cast<size_t>(B + 1)) + wire_align16(20 * static_cast<size_t>(N)) + wire_align16(static_cast<size_t>(E));
+}
+
+// One batch from PINNED HOST memory in the compact wire format, end to end on `stream`: ONE host->device copy of the
+// arena, lp_wire_unpack_kernel, lp_stream_kernel over the slot's descriptor, device->host copies of rows [0, L) of
+// out / lut_batch and of the status word (L = the batch's readout rows, known on the host: lut_ptr[B]).  Nothing
+// synchronises; the caller waits on its own event.  The slot is caller-owned device memory (see qot_lp_wire_slot_t).
+extern "C" int qot_lightpath_infer_wire_host(const void* arena_host, int64_t N, int64_t E, int64_t B, int64_t L,
+                                             const float* prepared, int32_t is_lut_index, const qot_lp_wire_slot_t* slot,
+                                             float* out_host, int64_t* lut_batch_host, int32_t* status_host,
+                                             int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  QOT_REQUIRE(arena_host && slot && prepared && out_host && lut_batch_host && status_host, "qot_lightpath_infer_wire_host: null argument");
+  QOT_REQUIRE(N > 0 && B > 0 && E >= 0 && L >= 0 && L <= N, "qot_lightpath_infer_wire_host: bad size");
+  QOT_REQUIRE(slot->arena && slot->edge_index && slot->ptrs && slot->desc && slot->out && slot->lut_batch && slot->lut_node &&
+                  slot->n_lut && slot->status, "qot_lightpath_infer_wire_host: incomplete staging slot");
+  QOT_REQUIRE(N <= slot->cap_nodes && E <= slot->cap_edges && B <= slot->cap_graphs,
+              "qot_lightpath_infer_wire_host: batch (N=%lld, E=%lld, B=%lld) exceeds the slot capacity", (long long)N,
+              (long long)E, (long long)B);
+  QOT_REQUIRE((reinterpret_cast<uintptr_t>(slot->arena) & 15) == 0 && (reinterpret_cast<uintptr_t>(slot->desc) & 15) == 0,
+              "qot_lightpath_infer_wire_host: slot arena / descriptor must be 16-byte aligned");
+  const size_t nbytes = qot_lightpath_wire_bytes(N, E, B);
+  QOT_CUDA(cudaMemcpyAsync(slot->arena, arena_host, nbytes, cudaMemcpyHostToDevice, stream));
+  const char* a = static_cast<const char*>(slot->arena);
+  const int32_t* wptr = reinterpret_cast<const int32_t*>(a);
+  const float* x = reinterpret_cast<const float*>(a + wire_align16(12 * static_cast<size_t>(B + 1)));
+  const uint8_t* wdst = reinterpret_cast<const uint8_t*>(a + wire_align16(12 * static_cast<size_t>(B + 1)) + wire_align16(20 * static_cast<size_t>(N)));
+  QOT_CUDA(cudaMemsetAsync(slot->status, 0, 4, stream));
+  const unsigned ub = static_cast<unsigned>(std::min<int64_t>(cdiv(B, 8), 4 * kNumSMs));
+  lp_wire_unpack_kernel<<<ub, 256, 0, stream>>>(wptr, wptr + (B + 1), wptr + 2 * (B + 1), wdst, N, E, B, slot->ptrs,
+                                               slot->edge_index, slot->desc, x);
+  QOT_LAUNCH_CHECK();
+  const int64_t tiles = qot_lightpath_stream_tiles(B);
+  int rc = qot_lightpath_infer_stream(slot->desc, 1, tiles, tiles, L, prepared, is_lut_index, QOT_LP_SYMMETRIC_BY_SOURCE, stream_);
+  if (rc) return rc;
+  if (L > 0) {
+    QOT_CUDA(cudaMemcpyAsync(out_host, slot->out, L * QOT_OUT * 4, cudaMemcpyDeviceToHost, stream));
+    QOT_CUDA(cudaMemcpyAsync(lut_batch_host, slot->lut_batch, L * 8, cudaMemcpyDeviceToHost, stream));
+  }
+  QOT_CUDA(cudaMemcpyAsync(status_host, slot->status, 4, cudaMemcpyDeviceToHost, stream));
+  if (h2d_bytes) *h2d_bytes = static_cast<int64_t>(nbytes);
+  if (d2h_bytes) *d2h_bytes = L * (QOT_OUT * 4 + 8) + 4;
   return QOT_OK;
 }

@@ -6,7 +6,8 @@ the shipped checkpoints (``conv1.lin.weight``, ``conv1.att_src``, ``conv1.att_ds
 ``conv1.bias``, ``norm1.module.*``, ``mlp.0.*``, ``mlp.3.*``), so
 ``lightpath_training/test.py:63`` loads ``models/model_N.pth`` with strict=True.
 
-eval(): one fused launch chain (csrc/lightpath_infer.cu).
+eval(): one launch of the persistent kernel (csrc/lightpath_stream.cu) per batch -- or per MANY
+batches through ``stream_plan`` / ``forward_stream``.
 train(): GAT forward -> batch statistics -> LUT head, with the matching backward
 kernels (csrc/lightpath_train.cu) through ``torch.autograd.Function``.
 """
@@ -20,24 +21,7 @@ from ..nn import BatchNorm, GATConv
 
 
 class LightpathGNN(torch.nn.Module):
-    # kernels behind qot_lightpath_infer per qot_lightpath_set_variant() value (bench.py counts
-    # launches and names the dominant kernel with these)
-    _variant_kernels = ("lp_infer_kernel", "lp_infer_sub_kernel", "lp_attn_kernel<fused, tensor-core head>",
-                        "lp_attn_kernel + lp_head_kernel", "lp_attn_kernel<fused, fp32 head>")
-    _variant_launches = (1, 1, 1, 2, 1)    # variant 3: lp_attn_kernel + lp_head_kernel
-
-    @property
-    def launches_per_step(self):
-        from .. import _lib
-        return self._variant_launches[_lib.lib().qot_lightpath_get_variant()]
-
-    batches_per_launch = 1                 # qot_lightpath_infer: one launch per batch
-
-    @property
-    def dominant_kernel(self):
-        """Name of the kernel behind qot_lightpath_infer for the active qot_lightpath_set_variant()."""
-        from .. import _lib
-        return self._variant_kernels[_lib.lib().qot_lightpath_get_variant()]
+    dominant_kernel = "lp_stream_kernel"   # csrc/lightpath_stream.cu: eval forward, one launch for any number of batches
 
     def __init__(self, in_channels, hidden_channels, output_dim, is_lut_index, dropout_p=0.5):
         super().__init__()
@@ -74,25 +58,32 @@ class LightpathGNN(torch.nn.Module):
         return self._prepared
 
     @_lib.on_tensor_device
-    def forward_device(self, data, out=None) -> ops.LightpathInferOut:
-        """Eval forward without any host synchronisation: ONE kernel launch when the batch carries
-        ``ptr`` / ``edge_ptr`` / ``lut_ptr`` (every collate of this package provides them); returns
-        capacity-sized device buffers plus the device-side row count (CUDA-graph capturable)."""
-        gptr = ops.batch_graph_ptr(data)
+    def forward_device(self, data) -> ops.LightpathInferOut:
+        """Eval forward of ONE batch without reading anything back: one launch of the persistent kernel
+        (qot_lightpath_infer_stream, n_batches = 1) when the batch carries ``ptr`` / ``edge_ptr`` / ``lut_ptr``
+        (every collate of this package provides them; a foreign batch gets them from qot_graph_ptr / qot_edge_ptr /
+        qot_lightpath_lut_ptr first).  The plan (output buffers + device descriptor) is cached on the batch object."""
+        from ..batch import Batch
         cache = ops.batch_cache(data)
-        eptr = getattr(data, "edge_ptr", None)
-        if eptr is None:
-            if "eptr" not in cache:
-                cache["eptr"] = ops.edge_ptr(data.edge_index, data.batch, gptr.numel() - 1)
-            eptr = cache["eptr"][0]
-        lut_ptr = getattr(data, "lut_ptr", None)
-        if lut_ptr is None or getattr(data, "lut_col", None) != self.is_lut_index:
-            key = ("lut_ptr", self.is_lut_index)
-            if key not in cache:
-                cache[key] = ops.lightpath_lut_ptr(data.x, gptr, self.is_lut_index)
-            lut_ptr = cache[key]
-        return ops.lightpath_infer(data.x, data.edge_index, gptr, eptr, lut_ptr, self.prepared(),
-                                   self.is_lut_index, out)
+        key = ("stream_plan", self.is_lut_index, data.x.data_ptr(), data.edge_index.data_ptr(),
+               tuple(data.x.shape), tuple(data.edge_index.shape))
+        plan = cache.get(key)
+        if plan is None:
+            gptr = ops.batch_graph_ptr(data)
+            eptr = getattr(data, "edge_ptr", None)
+            if eptr is None:
+                if "eptr" not in cache:
+                    cache["eptr"] = ops.edge_ptr(data.edge_index, data.batch, gptr.numel() - 1)
+                eptr = cache["eptr"][0]
+            lut_ptr = getattr(data, "lut_ptr", None)
+            if lut_ptr is None or getattr(data, "lut_col", None) != self.is_lut_index:
+                lut_ptr = ops.lightpath_lut_ptr(data.x, gptr, self.is_lut_index)
+            view = Batch(x=data.x, edge_index=data.edge_index, ptr=gptr, edge_ptr=eptr, lut_ptr=lut_ptr,
+                         num_graphs=int(gptr.numel() - 1), lut_col=self.is_lut_index,
+                         sym_by_src=bool(getattr(data, "sym_by_src", False)))
+            plan = cache[key] = ops.LightpathStreamPlan([view], self.is_lut_index)
+        plan.launch(self.prepared())
+        return plan.result(0)
 
     def stream_plan(self, batches, split_head: bool = False) -> "ops.LightpathStreamPlan":
         """Plan for evaluating many resident batches with one launch of the persistent kernel each time
@@ -122,7 +113,7 @@ class LightpathGNN(torch.nn.Module):
                                "(stale or foreign index array)")
         if n_lut == 0:
             raise ValueError("No LUT node found in the batch.")
-        return res.out[:n_lut], res.lut_batch[:n_lut]
+        return res.out[:n_lut].clone(), res.lut_batch[:n_lut].clone()   # the plan's buffers are reused by the next call
 
     def _check_supported(self):
         c = self.conv1

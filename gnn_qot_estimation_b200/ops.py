@@ -192,15 +192,6 @@ class LightpathInferOut(NamedTuple):
     status: torch.Tensor      # [1] int32 on device; non-zero: lut_ptr did not match x
 
 
-def new_infer_out(capacity: int, device) -> LightpathInferOut:
-    cap = max(int(capacity), 1)
-    return LightpathInferOut(torch.empty(cap, 3, dtype=torch.float32, device=device),
-                             torch.empty(cap, dtype=torch.int64, device=device),
-                             torch.empty(cap, dtype=torch.int32, device=device),
-                             torch.empty(1, dtype=torch.int32, device=device),
-                             torch.zeros(1, dtype=torch.int32, device=device))
-
-
 def lightpath_lut_ptr(x, gptr, is_lut_index: int) -> torch.Tensor:
     """lut_ptr [B+1] int64: exclusive prefix of the per-graph LUT-node counts (device, no sync)."""
     _require_cuda(x, gptr)
@@ -211,25 +202,6 @@ def lightpath_lut_ptr(x, gptr, is_lut_index: int) -> torch.Tensor:
     ws = _lib.workspace(L.qot_lightpath_lut_ptr_workspace_bytes(B), x.device)
     check(L.qot_lightpath_lut_ptr(ptr(x), ptr(gptr), N, B, int(is_lut_index), ptr(out), ptr(ws), ws.numel(),
                                   stream()), "qot_lightpath_lut_ptr")
-    return out
-
-
-def lightpath_infer(x, edge_index, gptr, eptr, lut_ptr, prepared, is_lut_index: int,
-                    out: Optional[LightpathInferOut] = None) -> LightpathInferOut:
-    """Launches the fused eval forward (attention kernel + readout-head kernel; ONE kernel for the
-    older variants); returns device buffers without any host sync."""
-    _require_cuda(x, edge_index, gptr, eptr, lut_ptr, prepared)
-    x, edge_index = _f32(x), _i64(edge_index)
-    N, E, B = int(x.shape[0]), int(edge_index.shape[1]), int(gptr.numel() - 1)
-    if out is None:
-        out = new_infer_out(N, x.device)
-    L = _lib.lib()
-    ws = _lib.workspace(L.qot_lightpath_infer_workspace_bytes(N), x.device)
-    check(L.qot_lightpath_infer(ptr(x), ptr(edge_index), E, ptr(gptr), ptr(eptr), ptr(lut_ptr), N, B,
-                                ptr(prepared), int(is_lut_index), ptr(out.out), ptr(out.lut_batch),
-                                ptr(out.lut_node), ptr(out.n_lut), ptr(out.status), ptr(ws), ws.numel(),
-                                stream()),
-          "qot_lightpath_infer")
     return out
 
 

@@ -274,8 +274,8 @@ typedef struct {
 } qot_lightpath_params_t;
 
 /* Fused eval-mode forward: GATConv -> BatchNorm(running stats) -> ReLU -> LUT
- * readout -> MLP (lightpath_training/models.py:26-45 under model.eval()).
- * Graph-parallel, ONE launch, no cross-block dependency: graph g owns nodes
+ * readout -> MLP (lightpath_training/models.py:26-45 under model.eval()), entry point
+ * qot_lightpath_infer_stream below.  Graph-parallel, no cross-block dependency: graph g owns nodes
  * [gptr[g],gptr[g+1]) and edges [eptr[g],eptr[g+1]) of edge_index (as every collate produces
  * them; both endpoints of an edge lie in the graph that owns it), and its readout rows go to
  * [lut_ptr[g],lut_ptr[g+1]) -- lut_ptr [B+1] int64 is the exclusive prefix of the per-graph
@@ -295,15 +295,9 @@ int qot_lightpath_lut_ptr(const float* x, const int64_t* gptr, int64_t N, int64_
  * `prepared` (qot_lightpath_prepared_floats() floats, 16-byte aligned). */
 size_t qot_lightpath_prepared_floats(void);
 int qot_lightpath_prepare(const qot_lightpath_params_t* p, float* prepared, void* stream);
-/* `ws`: caller-provided scratch of qot_lightpath_infer_workspace_bytes(N) bytes, 16-byte aligned
- * (the attention rows z [L,20] handed from lp_attn_kernel to lp_head_kernel); the library keeps no
- * reference to it after the call's work has run on `stream`. */
+/* Bytes of the z scratch a batch descriptor needs (20 floats per readout row, rows <= N); only the
+ * QOT_LP_SPLIT_HEAD build of the kernel writes it. */
 size_t qot_lightpath_infer_workspace_bytes(int64_t N);
-int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
-                        const int64_t* gptr, const int64_t* eptr, const int64_t* lut_ptr,
-                        int64_t N, int64_t B, const float* prepared, int32_t is_lut_index,
-                        float* out, int64_t* lut_batch, int32_t* lut_node, int32_t* n_lut,
-                        int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
 /* The same forward over MANY batches in ONE launch of a persistent, warp-specialised kernel
  * (lp_stream_kernel, csrc/lightpath_stream.cu): the streaming form of the evaluation loop
@@ -315,9 +309,9 @@ int qot_lightpath_infer(const float* x, const int64_t* edge_index, int64_t E,
  *   status  one int32 per batch, ZERO on entry (pool them and clear the pool with one memset);
  *           bit 0: lut_ptr does not describe x, bit 2: a pipeline barrier timed out.
  * uniform_tiles: tiles per batch when every batch but the last has the same count, else 0 (the kernel
- * then searches tile0).  max_rows: an upper bound of lut_ptr[B] over the batches.  Outputs per batch as
- * qot_lightpath_infer.  Values equal qot_lightpath_infer's to fp32 round-off (same attention
- * arithmetic; the readout head sums in a different order). */
+ * then searches tile0).  max_rows: an upper bound of lut_ptr[B] over the batches.  Outputs per batch as described
+ * above (out / lut_batch / lut_node rows in ascending node order, n_lut[0] = L).  A single batch is a launch with
+ * n_batches = 1. */
 typedef struct qot_lp_batch {
   const float* x;              /* [N,5]                                       */
   const int64_t* edge_index;   /* [2,E]: source row, destination row          */
@@ -349,45 +343,35 @@ int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches,
                                int64_t uniform_tiles, int64_t max_rows, const float* prepared,
                                int32_t is_lut_index, int32_t flags, void* stream);
 
-/* Kernel variant behind qot_lightpath_infer[_host]: 0 = one warp per graph, 1 = 8 lanes per graph in
- * the scan / attention phase + block-wide two-row heads, 2 (default) = 8 lanes per graph with the
- * block's node / destination slabs moved by bulk async copies and the readout head on the tensor
- * cores (error-compensated TF32), 3 (default) = the same split into two launches (lp_attn_kernel
- * writes the attention rows into `ws`, lp_head_kernel runs the readout head over them).  Same rows,
- * values equal to fp32 round-off (the summation trees differ); process-wide, set before launching. */
-int qot_lightpath_set_variant(int variant);
-int qot_lightpath_get_variant(void);
-
-/* The same call for a batch in PINNED HOST memory (reference layout), into a caller-owned device
- * staging slot.  Enqueues on `stream`: H2D of x, of the DESTINATION row of edge_index and of the
- * three offset arrays; the kernel -- the source row is not copied: the few entries the readout
- * needs (one 32-byte sector per in-edge of a LUT node) are read by the kernel from the pinned
- * buffer over PCIe (if the buffer is not device-mapped, slot->edge_src must exist and the row is
- * copied); D2H of rows [0,L) of out / lut_batch and of the status word, L = lut_ptr_host[B].
- * No synchronisation: the caller waits on its own event before reading the host outputs.
+/* The evaluation loop of lightpath_training/test.py:77-94 for batches arriving from the HOST: one call per batch
+ * replaces `data.to(device)` -> `model(data)` -> `.cpu()`.  The batch travels in the COMPACT WIRE FORMAT of a
+ * verified-layout batch (see QOT_LP_SYMMETRIC_BY_SOURCE; PackedGraphStore.host_wire_batch packs it), one contiguous
+ * pinned arena of qot_lightpath_wire_bytes(N, E, B) bytes:
+ *   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad to 16 | float x[N,5] | pad to 16 | uint8 dst[E]
+ * (dst: graph-local destination id of every edge, graphs of <= 255 nodes; no source row).  On `stream`: ONE
+ * host->device copy of the arena; lp_wire_unpack_kernel rebuilds the reference layout in the slot (int64 edge_index
+ * [2,E], int64 offsets), fills the slot's descriptor and clears its status; lp_stream_kernel (the same kernel resident
+ * batches take: bit-identical rows); device->host copies of rows [0, L) of out / lut_batch and of the status word,
+ * L = lut_ptr[B] (known on the host).  No synchronisation: the caller waits on its own event.
  * h2d_bytes / d2h_bytes (optional, host): bytes this call copied in each direction. */
 typedef struct {
-  float* x;             /* [cap_nodes,5]                                   */
-  int64_t* edge_src;    /* [cap_edges] or NULL (only for unmapped host memory) */
-  int64_t* edge_dst;    /* [cap_edges]                                     */
-  int64_t* ptrs;        /* [3*(cap_graphs+1)]: gptr | eptr | lut_ptr       */
-  float* out;           /* [cap_nodes,3]                                   */
-  int64_t* lut_batch;   /* [cap_nodes]                                     */
-  int32_t* lut_node;    /* [cap_nodes]                                     */
-  int32_t* n_lut;       /* [1]                                             */
-  int32_t* status;      /* [1], zeroed by the caller once                  */
-  float* z;             /* qot_lightpath_infer_workspace_bytes(cap_nodes) bytes, 16-byte aligned */
-  void* arena;          /* optional: 8*cap_edges + 24*(cap_graphs+1) + 20*cap_nodes bytes.  When the host batch
-                           keeps [dst row | gptr | eptr | lut_ptr | x] contiguous (PackedGraphStore.host_batch(pin=True)
-                           does) the call moves that range with ONE copy into the arena instead of three */
+  void* arena;            /* qot_lightpath_wire_bytes(cap_nodes, cap_edges, cap_graphs) bytes, 16-byte aligned */
+  int64_t* edge_index;    /* [2, cap_edges] -- rebuilt on the device                                           */
+  int64_t* ptrs;          /* [3 * (cap_graphs + 1)]                                                            */
+  qot_lp_batch_t* desc;   /* ONE descriptor in device memory, 16-byte aligned; the caller sets out, lut_batch,
+                             lut_node, n_lut, status and z once (the slot's own buffers), the call fills the rest */
+  float* out;             /* [cap_rows, 3]  (same pointers as in desc)                                         */
+  int64_t* lut_batch;     /* [cap_rows]                                                                        */
+  int32_t* lut_node;      /* [cap_rows]                                                                        */
+  int32_t* n_lut;         /* [1]                                                                               */
+  int32_t* status;        /* [1]                                                                               */
   int64_t cap_nodes, cap_edges, cap_graphs;
-} qot_lp_slot_t;
-int qot_lightpath_infer_host(const float* x_host, const int64_t* edge_index_host, int64_t E,
-                             const int64_t* gptr_host, const int64_t* eptr_host,
-                             const int64_t* lut_ptr_host, int64_t N, int64_t B,
-                             const float* prepared, int32_t is_lut_index, const qot_lp_slot_t* slot,
-                             float* out_host, int64_t* lut_batch_host, int32_t* status_host,
-                             int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream);
+} qot_lp_wire_slot_t;
+size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B);
+int qot_lightpath_infer_wire_host(const void* arena_host, int64_t N, int64_t E, int64_t B, int64_t L,
+                                  const float* prepared, int32_t is_lut_index, const qot_lp_wire_slot_t* slot,
+                                  float* out_host, int64_t* lut_batch_host, int32_t* status_host,
+                                  int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream);
 
 /* General GATConv forward over a destination-sorted CSR built with flags=3
  * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.

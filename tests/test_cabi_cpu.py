@@ -31,7 +31,7 @@ def test_header_declares_the_documented_families():
     for fam in ("qot_collate", "qot_build_csr", "qot_tconv_fwd", "qot_tconv_bwd", "qot_nnconv_fwd",
                 "qot_nnconv_bwd", "qot_gat_fwd", "qot_gat_bwd", "qot_bn_stats", "qot_bn_bwd_sparse",
                 "qot_pool_mlp_fwd", "qot_pool_mlp_bwd", "qot_lut_head_fwd", "qot_lut_head_bwd",
-                "qot_lightpath_infer", "qot_last_error"):
+                "qot_lightpath_infer_stream", "qot_lightpath_infer_wire_host", "qot_last_error"):
         assert fam in syms, fam
 
 

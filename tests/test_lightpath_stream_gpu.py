@@ -6,11 +6,11 @@ one-launch-per-batch module path (same rows, same order, values equal to fp32 ro
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import ABS_FLOOR, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
-ATOL = 2e-6
+ATOL = ABS_FLOOR
 
 
 def _model(dev, name="ckpt_lightpath_model_1.pt"):
