@@ -147,7 +147,9 @@ def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20
     model = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev)
     ddp = GraphDataParallel(model)
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
-    crit = torch.nn.SmoothL1Loss()
+    # SmoothL1Loss (topological_training/train.py:69) as the fused loss + gradient kernel (qot_smooth_l1)
+    from gnn_qot_estimation_b200 import ops
+    crit = ops.smooth_l1_loss
     nb = 16
     store = synthetic.nsfnet_store(B * nb, seed=rank).to(dev)
     batches = [store.collate(range(i * B, (i + 1) * B)) for i in range(nb)]

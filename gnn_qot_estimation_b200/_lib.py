@@ -51,6 +51,15 @@ class QotLpBatch(C.Structure):
                 ("tile0", i64), ("reserved", i64)]
 
 
+class QotParamSeg(C.Structure):
+    _fields_ = [("param", P), ("offset", i64), ("numel", i64)]
+
+
+class QotSgdHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("momentum", C.c_float), ("dampening", C.c_float), ("weight_decay", C.c_float),
+                ("nesterov", i32), ("maximize", i32), ("reserved", i32 * 2)]
+
+
 class QotLpWireSlot(C.Structure):
     _fields_ = [("arena", P), ("edge_index", P), ("ptrs", P), ("desc", P), ("out", P), ("lut_batch", P),
                 ("lut_node", P), ("n_lut", P), ("status", P),
@@ -107,6 +116,8 @@ SIGNATURES = {
     "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, vp]),
     "qot_topo_fused_bwd_workspace_bytes": (sz, [i32]),
     "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, vp]),
+    "qot_ddp_exchange_bytes": (sz, [i64]),
+    "qot_ddp_sgd_step": (C.c_int, [P, P, i32, i32, i64, P, i32, P, P, P, P, vp]),
     "qot_lightpath_stream_tiles": (i64, [i64]),
     "qot_lightpath_infer_stream": (C.c_int, [P, i32, i64, i64, i64, P, i32, i32, vp]),
     "qot_lightpath_wire_bytes": (sz, [i64, i64, i64]),

@@ -121,6 +121,115 @@ class GraphDataParallel(torch.nn.Module):
         self.grads.all_reduce_mean()
 
 
+class PeerExchange:
+    """Exchange buffers for the one-shot gradient all-reduce of ``qot_ddp_sgd_step``: one buffer per rank in memory
+    every peer of the box has mapped (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged through the
+    process group's store, peer access over NVLink), plus the DEVICE array of the peers' addresses the kernel walks.
+    Raises if the ranks cannot map each other's memory (callers fall back to the NCCL all-reduce)."""
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        rank, world = world_info()
+        self.rank, self.world = rank, world
+        nbytes = int(_lib.lib().qot_ddp_exchange_bytes(int(numel)))
+        if world == 1:
+            self.buf, self.peers, self.handle = None, None, None
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous did not return a mapping for every rank")
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                             # every rank's buffer is zeroed before anyone's first step
+
+
+class FusedSGDStep:
+    """``optimizer.step()`` of a plain ``torch.optim.SGD`` (one parameter group, fp32 CUDA parameters -- what
+    topological_training/train.py:66 builds) fused with the data-parallel gradient exchange into ONE launch
+    (``qot_ddp_sgd_step``, csrc/ddp_step.cu).  Reads the hyper-parameters from device memory: ``sync_hyper()`` uploads
+    them when a scheduler changed ``param_groups`` (a few bytes, no re-capture).  The optimizer's ``momentum_buffer``
+    state entries become views of one flat buffer, so ``optimizer.state_dict()`` keeps working."""
+
+    @staticmethod
+    def supports(optimizer) -> bool:
+        if type(optimizer) is not torch.optim.SGD or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        if not all(isinstance(g[k], (int, float)) for k in ("lr", "momentum", "dampening", "weight_decay")):
+            return False
+        ps = [p for p in g["params"] if p.requires_grad]
+        return bool(ps) and all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps)
+
+    def __init__(self, optimizer, grads: FlatGradBuffer, group=None):
+        import ctypes as C
+        from . import _lib
+        self.opt, self.grads = optimizer, grads
+        params = grads.params
+        if [id(p) for p in optimizer.param_groups[0]["params"] if p.requires_grad] != [id(p) for p in params]:
+            raise RuntimeError("FusedSGDStep: the optimizer and the flat gradient buffer must hold the same parameters in the same order")
+        dev = grads.flat.device
+        self.dev, self.n = dev, int(grads.flat.numel())
+        self.rank, self.world = world_info()
+        self.exchange = PeerExchange(self.n, dev, group)
+        segs = (_lib.QotParamSeg * len(params))()
+        for i, p in enumerate(params):
+            segs[i].param, segs[i].offset, segs[i].numel = p.data_ptr(), grads.offsets[i], p.numel()
+        self.segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(dev)
+        self.nseg = len(params)
+        self.momentum = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        had = False
+        for i, p in enumerate(params):
+            view = self.momentum[grads.offsets[i]: grads.offsets[i] + p.numel()].view_as(p)
+            st = optimizer.state[p]
+            if torch.is_tensor(st.get("momentum_buffer")):
+                view.copy_(st["momentum_buffer"])
+                had = True
+            st["momentum_buffer"] = view
+        self.had_state = had
+        if had:
+            self.state[1] = 1
+        self._hyper_host = torch.zeros(C.sizeof(_lib.QotSgdHyper), dtype=torch.uint8).pin_memory()
+        self.hyper = torch.zeros(C.sizeof(_lib.QotSgdHyper), dtype=torch.uint8, device=dev)
+        self._hyper_key = None
+        self.sync_hyper()
+
+    def mark_fresh(self) -> None:
+        """The next step clones the gradient into the momentum buffer (torch's rule for a fresh optimizer)."""
+        self.momentum.zero_()
+        self.state[1] = 0
+
+    def sync_hyper(self) -> None:
+        import ctypes as C
+        from . import _lib
+        g = self.opt.param_groups[0]
+        key = (float(g["lr"]), float(g["momentum"]), float(g["dampening"]), float(g["weight_decay"]),
+               bool(g["nesterov"]), bool(g.get("maximize", False)))
+        if key == self._hyper_key:
+            return
+        h = _lib.QotSgdHyper(key[0], key[1], key[2], key[3], int(key[4]), int(key[5]))
+        self._hyper_host.copy_(torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8))
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        self._hyper_key = key
+
+    def step(self) -> None:
+        """Enqueues the exchange + update on the current stream (capturable).  ``p.grad`` must be the views of the flat
+        gradient buffer (``FlatGradBuffer.gather()``)."""
+        from . import _lib
+        _lib.check(_lib.lib().qot_ddp_sgd_step(
+            self.grads.flat.data_ptr(), None if self.exchange.peers is None else self.exchange.peers.data_ptr(),
+            self.world, self.rank, self.n, self.segs.data_ptr(), self.nseg, self.momentum.data_ptr(),
+            self.hyper.data_ptr(), self.state.data_ptr(), self.status.data_ptr(),
+            torch.cuda.current_stream(self.dev).cuda_stream), "qot_ddp_sgd_step")
+
+
 def bind_to_gpu_numa_node(device_index: int) -> str:
     """Pins the calling process to the CPU cores NVML reports as local to GPU `device_index`, so that
     the pinned host buffers it allocates afterwards (first-touch) and its copy-submitting threads sit on

@@ -9,7 +9,11 @@ optimizer update -- is captured once and replayed per batch.
 
 Gradient exchange under data parallelism (``ddp=GraphDataParallel(model)``), ``exchange=``:
 
-* ``"graph"`` (default): the flat NCCL all-reduce is captured INSIDE the step graph -- one replay per
+* ``"peer"`` (default for a plain ``torch.optim.SGD``): the exchange AND the optimizer update are ONE
+  native launch inside the step graph -- a one-shot all-reduce over NVLink peer memory fused with the
+  SGD rule, hyper-parameters read from device memory (``distributed.FusedSGDStep``, csrc/ddp_step.cu);
+  also used single-GPU (no peers), where it replaces the optimizer's three foreach launches;
+* ``"graph"``: the flat NCCL all-reduce is captured INSIDE the step graph -- one replay per
   step, no eager launch between kernels;
 * ``"eager"``: graph A (zero -> forward -> loss -> backward -> gather) / eager all-reduce / graph B
   (optimizer), the round-1 arrangement, kept for NCCL builds that refuse capture.
@@ -53,11 +57,25 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs a CUDA batch (no CPU path)")
         self.model, self.opt, self.crit, self.ddp = model, optimizer, criterion, ddp
         self.target_of = target_of or (lambda b: b.y.view(-1, 3))
-        exchange = exchange or os.environ.get("QOT_DDP_EXCHANGE", "graph")
-        if exchange not in ("graph", "eager"):
-            raise ValueError(f"exchange must be 'graph' or 'eager', got {exchange!r}")
-        from .distributed import world_info
-        self.exchange = exchange if (ddp is not None and world_info()[1] > 1) else "none"
+        from .distributed import FlatGradBuffer, FusedSGDStep, world_info
+        exchange = exchange or os.environ.get("QOT_DDP_EXCHANGE", "peer")
+        if exchange not in ("peer", "graph", "eager"):
+            raise ValueError(f"exchange must be 'peer', 'graph' or 'eager', got {exchange!r}")
+        multi = ddp is not None and world_info()[1] > 1
+        self.fused = None
+        if exchange == "peer":
+            if FusedSGDStep.supports(optimizer):
+                try:
+                    self._grads = ddp.grads if ddp is not None else FlatGradBuffer(model.parameters())
+                    self.fused = FusedSGDStep(optimizer, self._grads)
+                except Exception as e:                # noqa: BLE001 -- e.g. no peer mapping between the ranks
+                    if multi:
+                        import warnings
+                        warnings.warn(f"GraphedTrainStep: peer exchange unavailable ({e}); using the captured NCCL all-reduce")
+                    self.fused = None
+            if self.fused is None:
+                exchange = "graph"
+        self.exchange = exchange if (multi or self.fused is not None) else "none"
         self.static = Batch(num_graphs=example.num_graphs, lut_col=example.lut_col,
                             **{k: (getattr(example, k).clone() if getattr(example, k) is not None else None)
                                for k in _FIELDS})
@@ -71,12 +89,11 @@ class GraphedTrainStep:
         # ---- snapshot: the warm-up below takes real optimizer steps
         model_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         opt_sd = copy.deepcopy(optimizer.state_dict())
-        had_state = len(optimizer.state) > 0
+        had_state = self.fused.had_state if self.fused is not None else len(optimizer.state) > 0
         with torch.cuda.stream(self.stream):
             for _ in range(max(warmup, 1)):          # allocates workspaces / optimizer state eagerly
                 self._front()
-                self._exchange()
-                self.opt.step()
+                self._tail()
             torch.cuda.synchronize()
             self._capture()
             torch.cuda.synchronize()
@@ -90,6 +107,8 @@ class GraphedTrainStep:
                         for name, val in st.items():
                             if torch.is_tensor(val):
                                 cur[idx][name].copy_(val)
+                elif self.fused is not None:
+                    self.fused.mark_fresh()          # next step: buffer = gradient, torch's rule for a fresh optimizer
                 else:
                     # fresh optimizer: zeroed buffers reproduce the first-step rule of SGD / Adam exactly
                     # (buf = 0 * momentum + grad), except for SGD with dampening != 0
@@ -113,12 +132,11 @@ class GraphedTrainStep:
                 self.loss = self._front()
             self._capture_update()
         else:
-            # one graph: zero -> forward -> loss -> backward (-> gather -> all-reduce) -> optimizer
+            # one graph: zero -> forward -> loss -> backward (-> gather) -> exchange + optimizer
             self.graph_a = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_a, stream=self.stream):
                 self.loss = self._front()
-                self._exchange()
-                self.opt.step()
+                self._tail()
 
     def _capture_update(self) -> None:
         self.graph_b = torch.cuda.CUDAGraph()
@@ -127,12 +145,25 @@ class GraphedTrainStep:
 
     def _front(self) -> torch.Tensor:
         self.static._cache = {}                      # the CSR of the batch is rebuilt inside the step
-        (self.ddp or self.opt).zero_grad(set_to_none=True)   # backward writes fresh gradients
+        if self.fused is not None:
+            self._grads.zero()
+        else:
+            (self.ddp or self.opt).zero_grad(set_to_none=True)   # backward writes fresh gradients
         loss = self.crit((self.ddp or self.model)(self.static), self.target_of(self.static))
         loss.backward()
-        if self.ddp is not None:
-            self.ddp.grads.gather()                  # one concatenation kernel; p.grad -> flat views
+        if self.fused is not None:
+            self._grads.gather()                     # one concatenation kernel; p.grad -> flat views
+        elif self.ddp is not None:
+            self.ddp.grads.gather()
         return loss.detach()
+
+    def _tail(self) -> None:
+        """Gradient exchange + optimizer update."""
+        if self.fused is not None:
+            self.fused.step()
+        else:
+            self._exchange()
+            self.opt.step()
 
     def _exchange(self) -> None:
         if self.ddp is not None:
@@ -141,6 +172,10 @@ class GraphedTrainStep:
     def _check_hyper(self) -> None:
         """A scheduler (``StepLR.step()``) changes ``param_groups``; the captured update holds the old
         values as host scalars: re-capture it (the whole step when it is one graph)."""
+        if self.fused is not None:
+            with torch.cuda.stream(self.stream):
+                self.fused.sync_hyper()              # a few bytes to the device; the captured kernel reads them there
+            return
         if _hyper(self.opt) == self.hyper:
             return
         with torch.cuda.stream(self.stream):
@@ -153,8 +188,7 @@ class GraphedTrainStep:
                 self.graph_a = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph_a, stream=self.stream):
                     self.loss_new = self._front()
-                    self._exchange()
-                    self.opt.step()
+                    self._tail()
                 self.loss = self.loss_new
 
     def step(self, batch: Batch) -> torch.Tensor:

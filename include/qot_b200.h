@@ -538,6 +538,39 @@ int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* n
                        int32_t emax, int32_t num_nodes, const float* dout, const float* saved, float* gflat,
                        float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------ */
+/* Data-parallel training tail: gradient exchange + optimizer update, ONE launch.     */
+/* The reference trains single-process (topological_training/train.py:107-116:        */
+/* loss.backward(); optimizer.step(), torch.optim.SGD at :66); the multi-GPU split    */
+/* with a gradient all-reduce is what BASELINE.json's north_star adds.                */
+/* ------------------------------------------------------------------------ */
+/* Flat gradient `grad` [n] of this rank (FlatGradBuffer order) -> one-shot all-reduce over NVLink peer memory ->
+ * averaged gradient written back to `grad` -> torch.optim.SGD's update (weight decay, momentum, dampening, nesterov,
+ * maximize) on `momentum_buf` [n] and the parameter tensors named by `segs`.
+ *   peers   DEVICE array of `world` pointers: peers[r] = rank r's exchange buffer as mapped in THIS process (CUDA IPC
+ *           or torch symmetric memory), qot_ddp_exchange_bytes(n) bytes each, zero-initialised once; NULL when
+ *           world == 1.  Every rank must call with the same n and launch once per step.
+ *   hyper   DEVICE struct: a captured step follows an lr schedule by updating it between replays.
+ *   state   DEVICE, two 64-bit words, zero-initialised once: [0] steps taken (the flag value of the exchange -- never
+ *           reset it on one rank only), [1] != 0 once the momentum buffer holds a gradient (clear it to make the next
+ *           step clone the gradient into the buffer, as torch does for a fresh optimizer).
+ *   status  bit 0: a peer did not arrive within 4 s (no update was applied).
+ * Sums in rank order on every rank: the replicas stay bit-identical. */
+typedef struct {
+  float* param;          /* the parameter tensor (fp32, contiguous)           */
+  int64_t offset;        /* its first element in the flat gradient            */
+  int64_t numel;
+} qot_param_seg_t;
+typedef struct {
+  float lr, momentum, dampening, weight_decay;
+  int32_t nesterov, maximize;
+  int32_t reserved[2];
+} qot_sgd_hyper_t;
+size_t qot_ddp_exchange_bytes(int64_t n);
+int qot_ddp_sgd_step(float* grad, float* const* peers, int32_t world, int32_t rank, int64_t n,
+                     const qot_param_seg_t* segs, int32_t nseg, float* momentum_buf,
+                     const qot_sgd_hyper_t* hyper, unsigned long long* state, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,7 @@ err = float((got - ref).abs().max() / ref.abs().max())
 opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
 opt.step()
 g = GraphedTrainStep(model, opt, crit, b, ddp=ddp, warmup=2)
-mark('graphs captured')
+mark(f'graphs captured exchange={g.exchange}')
 for _ in range(5):
     loss = g.step(b)
 mark('graphed steps done')
@@ -46,6 +46,7 @@ same = bool(torch.equal(flat, ref0))
 res = torch.tensor([err, 0.0 if same else 1.0], device=dev, dtype=torch.float64)
 dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:
+    print(f"exchange={g.exchange}")
     print(f"ddp_check world={world}: grad rel err vs concatenated batch {float(res[0]):.3e} (bar 1e-5); "
           f"replicas identical after graphed steps: {float(res[1]) == 0.0}; loss {float(loss):.6f}")
     assert float(res[0]) <= 1e-5 and float(res[1]) == 0.0

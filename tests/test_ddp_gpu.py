@@ -1,8 +1,13 @@
-"""GPU, >= 2 devices: over NCCL, averaged per-rank gradients of the B200 TopologicalGNN equal the
-gradients of the concatenated batch, and the replicas stay bit-identical after CUDA-graphed DDP
+"""GPU, >= 2 devices: over NCCL / NVLink peer memory, averaged per-rank gradients of the B200 TopologicalGNN
+equal the gradients of the concatenated batch, and the replicas stay bit-identical after CUDA-graphed DDP
 steps (scripts/ddp_check.py under torchrun, one process per GPU).  Skipped on a 1-GPU box; the
-host-side logic is covered by tests/test_distributed_cpu.py (gloo, world 2)."""
+host-side logic is covered by tests/test_distributed_cpu.py (gloo, world 2).
+
+exchange = "peer": gradient exchange + SGD in one native launch (one-shot all-reduce over peer memory,
+csrc/ddp_step.cu); "eager": flat NCCL all-reduce between two captured graphs.  (The third mode, "graph" --
+the NCCL call captured inside the step graph -- is exercised by bench.py's cfg 3 block, not here.)"""
 import os
+import signal
 import subprocess
 import sys
 from pathlib import Path
@@ -14,15 +19,24 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-@pytest.mark.parametrize("exchange", ["graph", "eager"])
-def test_ddp_over_nccl(exchange):
+@pytest.mark.parametrize("exchange", ["peer", "eager"])
+def test_ddp_over_nvlink(exchange):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
     env = dict(os.environ, QOT_DDP_EXCHANGE=exchange, MASTER_ADDR="127.0.0.1")
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(ROOT / "scripts" / "ddp_check.py")],
-                         capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
-    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
-    assert "replicas identical after graphed steps: True" in out.stdout
+    port = 29533 + (0 if exchange == "peer" else 1)
+    proc = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                             "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "scripts" / "ddp_check.py")],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=str(ROOT),
+                            start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=150)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)                   # the whole torchrun group: a hung rank must not outlive the test
+        out, err = proc.communicate()
+        pytest.fail(f"ddp_check ({exchange}) did not finish in 150 s\n{out[-1500:]}\n{err[-1500:]}")
+    assert proc.returncode == 0, (out[-2000:], err[-3000:])
+    assert "replicas identical after graphed steps: True" in out
+    assert f"exchange={exchange}" in out, out[-1500:]          # no silent fallback to another exchange
