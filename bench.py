@@ -336,9 +336,14 @@ def run_b200(args):
     timed_steps = n_units * runner.unit_steps
     graphs_done = runner.graphs_in(n_units)
     barrier()
+    prof = bool(os.environ.get("QOT_PROFILE_TIMED_REGION"))      # `ncu --profile-from-start off`: only the timed launches
+    if prof:
+        torch.cuda.profiler.start()
     with ClockSampler(local) as clk:
         runner.timed(n_units, ev0, ev1)
         torch.cuda.synchronize()
+    if prof:
+        torch.cuda.profiler.stop()
     barrier()
     ms = ev0.elapsed_time(ev1)
     per_rank_ms = all_ranks(ms)
