@@ -113,9 +113,10 @@ SIGNATURES = {
     "qot_topo_fused_prepared_floats": (C.c_int, []),
     "qot_topo_fused_prepare": (C.c_int, [P, P, vp]),
     "qot_topo_fused_saved_floats": (sz, [i64, i64, i64]),
-    "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, vp]),
+    "qot_topo_fused_fwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, C.c_float, C.c_float, vp]),
     "qot_topo_fused_bwd_workspace_bytes": (sz, [i32]),
-    "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, vp]),
+    "qot_topo_fused_bwd": (C.c_int, [P, P, P, P, i64, P, P, P, i64, i64, i32, i32, i32, P, P, P, P, P, sz, P, P, C.c_float,
+                                     C.c_float, vp]),
     "qot_ddp_exchange_bytes": (sz, [i64]),
     "qot_ddp_sgd_step": (C.c_int, [P, P, i32, i32, i64, P, i32, P, P, P, P, vp]),
     "qot_lightpath_stream_tiles": (i64, [i64]),

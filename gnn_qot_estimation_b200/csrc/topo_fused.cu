@@ -41,6 +41,24 @@ struct TfPtrs {                  // par..Wm1T: the prepared GLOBAL buffer (16 KB
   float *small;                                            // pool[16] pre1[16] z1[16] out[4] dpool[16] dpre1[16] dout[4]
 };
 
+// Dropout of one graph (topological_training/models.py:55,59 on the node features, :36-41 inside the head): the
+// masks are kernel INPUTS -- one byte per element, drawn by the caller with torch's generator (so CUDA-graph replays
+// advance it and a test can replay the same masks through the oracle) -- 1 keeps the element and scales it by
+// 1 / (1 - p).  m1 / m2: [n,16] after conv1 / conv2, m3: [16] inside the head; all NULL = no dropout.
+struct TfDrop {
+  const uint8_t *m1, *m2, *m3;
+  float scale, scale_h;
+};
+__device__ __forceinline__ TfDrop tf_drop_of(const uint8_t* mask, float scale, float scale_h, int64_t Ntot, int64_t n0, int64_t g) {
+  TfDrop d;
+  d.m1 = mask ? mask + n0 * TF_H : nullptr;
+  d.m2 = mask ? mask + (Ntot + n0) * TF_H : nullptr;
+  d.m3 = mask ? mask + 2 * Ntot * TF_H + g * TF_H : nullptr;
+  d.scale = scale; d.scale_h = scale_h;
+  return d;
+}
+__device__ __forceinline__ float tf_keep(const uint8_t* m, int idx, float scale) { return m ? (m[idx] ? scale : 0.f) : 1.f; }
+
 __host__ __device__ inline size_t tf_smem_bytes(int nmax, int emax, int num_nodes, bool bwd) {
   size_t f = 0;
   if (bwd) f += kTfParams + static_cast<size_t>(num_nodes) * TF_H;
@@ -116,7 +134,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
                                  const float* __restrict__ eattr, int64_t n0, int n, int64_t e0, int E, int num_nodes,
                                  float* __restrict__ save_n, float* __restrict__ save_e, float* __restrict__ save_g,
                                  const float* __restrict__ rest_n, const float* __restrict__ rest_e,
-                                 const float* __restrict__ rest_g, int32_t* __restrict__ status) {
+                                 const float* __restrict__ rest_g, int32_t* __restrict__ status, const TfDrop& dr) {
   const int tid = threadIdx.x;
   const float* __restrict__ par = p.par;
   // ---- inputs.  Out-of-range ids / endpoints are clamped for memory safety AND reported (status bit 2: the
@@ -257,7 +275,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     __syncwarp();
     if (c == 0)
       for (int r = r0; r < r1; ++r) { const int e = p.permd[r]; p.alpha[e] = expf(p.alpha[e] - mx) * inv; }
-    if (valid) p.H1[idx] = tf_lk(fmaf(acc, inv, p.B2[idx]));
+    if (valid) p.H1[idx] = tf_lk(fmaf(acc, inv, p.B2[idx])) * tf_keep(dr.m1, idx, dr.scale);
   }
   __syncthreads();
   TF_STAMP(4);
@@ -289,7 +307,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
     float v = m / static_cast<float>(max(r1 - r0, 1)) + par[obias2 + o];
 #pragma unroll
     for (int c = 0; c < TF_H; ++c) v = fmaf(p.H1[i * TF_H + c], p.WrootT[c * 16 + o], v);
-    p.B1[idx] = tf_lk(v);
+    p.B1[idx] = tf_lk(v) * tf_keep(dr.m2, idx, dr.scale);
   }
   __syncthreads();
   TF_STAMP(5);
@@ -306,7 +324,7 @@ __device__ void tf_graph_forward(const TfPtrs& p, const float* __restrict__ emb,
 #pragma unroll
     for (int o = 0; o < TF_H; ++o) h = fmaf(pool[o], p.Wm1T[o * 16 + tid], h);
     pre1[tid] = h;
-    z1[tid] = tf_lk(h);
+    z1[tid] = tf_lk(h) * tf_keep(dr.m3, tid, dr.scale_h);
   }
   __syncthreads();
   if (tid < QOT_OUT) {
@@ -334,7 +352,8 @@ topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
                       int num_nodes, float* __restrict__ out, float* __restrict__ saved, int64_t Ntot,
-                      int32_t* __restrict__ status) {
+                      int32_t* __restrict__ status, const uint8_t* __restrict__ drop_mask, float drop_scale,
+                      float drop_scale_head) {
   extern __shared__ __align__(16) char tf_smem[];
   const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, false);
   float* sv_e = saved ? saved + Ntot * kTfSaveNode : nullptr;
@@ -349,7 +368,8 @@ topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
     }
     tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
                      saved ? saved + n0 * kTfSaveNode : nullptr, saved ? sv_e + e0 * kTfSaveEdge : nullptr,
-                     saved ? sv_g + g * kTfSaveGraph : nullptr, nullptr, nullptr, nullptr, status);
+                     saved ? sv_g + g * kTfSaveGraph : nullptr, nullptr, nullptr, nullptr, status,
+                     tf_drop_of(drop_mask, drop_scale, drop_scale_head, Ntot, n0, g));
     if (threadIdx.x < QOT_OUT) out[g * QOT_OUT + threadIdx.x] = p.small[48 + threadIdx.x];
     __syncthreads();
   }
@@ -358,7 +378,7 @@ topo_fused_fwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
 // forward recomputed, then the backward of one graph given d loss / d out; gradients accumulate in p.grad
 // (flat layout, P layout for W2 | b2) and p.gemb
 __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ node_ids, int64_t n0, int n, int E,
-                                  int num_nodes) {
+                                  int num_nodes, const TfDrop& dr) {
   const int tid = threadIdx.x;
   const float* par = p.par;
   float* g = p.grad;
@@ -370,7 +390,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
     float dz = 0.f;
 #pragma unroll
     for (int k = 0; k < QOT_OUT; ++k) dz = fmaf(par[oWm2 + k * TF_H + tid], dout[k], dz);
-    dpre1[tid] = dz * (pre1[tid] > 0.f ? 1.f : kTfSlope);
+    dpre1[tid] = dz * tf_keep(dr.m3, tid, dr.scale_h) * (pre1[tid] > 0.f ? 1.f : kTfSlope);
 #pragma unroll
     for (int k = 0; k < QOT_OUT; ++k) g[oWm2 + k * TF_H + tid] += dout[k] * z1[tid];
     if (tid < QOT_OUT) g[obm2 + tid] += dout[tid];
@@ -387,7 +407,8 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
   __syncthreads();
   TF_STAMP(7);
   // ---- dO2 (in place of H2 in B1); dH1 starts in B2
-  for (int idx = tid; idx < n * TF_H; idx += kTfThreads) p.B1[idx] = dpool[idx & 15] * tf_dlk_from_act(p.B1[idx]);
+  for (int idx = tid; idx < n * TF_H; idx += kTfThreads)
+    p.B1[idx] = dpool[idx & 15] * tf_keep(dr.m2, idx, dr.scale) * tf_dlk_from_act(p.B1[idx]);
   __syncthreads();
   if (tid < TF_H) {
     float s = 0.f;
@@ -482,7 +503,7 @@ __device__ void tf_graph_backward(const TfPtrs& p, const int64_t* __restrict__ n
       const float4 w = __ldg(pr + r), v = t[r];
       d0 = fmaf(w.x, v.x, d0); d1 = fmaf(w.y, v.y, d1); d2 = fmaf(w.z, v.z, d2); d3 = fmaf(w.w, v.w, d3);
     }
-    p.B2[idx] = (p.B2[idx] + ((d0 + d1) + (d2 + d3))) * tf_dlk_from_act(p.H1[idx]);
+    p.B2[idx] = (p.B2[idx] + ((d0 + d1) + (d2 + d3))) * tf_keep(dr.m1, idx, dr.scale) * tf_dlk_from_act(p.H1[idx]);
   }
   __syncthreads();
   TF_STAMP(11);
@@ -619,7 +640,8 @@ topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
                       const int64_t* __restrict__ edge_index, int64_t Etot, const float* __restrict__ eattr,
                       const int64_t* __restrict__ gptr, const int64_t* __restrict__ eptr, int64_t B, int nmax, int emax,
                       int num_nodes, const float* __restrict__ dout, const float* __restrict__ saved, int64_t Ntot,
-                      float* __restrict__ partial, int32_t* __restrict__ status) {
+                      float* __restrict__ partial, int32_t* __restrict__ status, const uint8_t* __restrict__ drop_mask,
+                      float drop_scale, float drop_scale_head) {
   extern __shared__ __align__(16) char tf_smem[];
   const TfPtrs p = tf_carve(tf_smem, prep, nmax, emax, num_nodes, true);
   const float* sv_e = saved ? saved + Ntot * kTfSaveNode : nullptr;
@@ -637,10 +659,12 @@ topo_fused_bwd_kernel(const float* __restrict__ prep, const float* __restrict__ 
     TF_STAMP(0);
     tf_graph_forward(p, emb, node_ids, edge_index, edge_index + Etot, eattr, n0, static_cast<int>(n), e0, static_cast<int>(E), num_nodes,
                      nullptr, nullptr, nullptr, saved ? saved + n0 * kTfSaveNode : nullptr,
-                     saved ? sv_e + e0 * kTfSaveEdge : nullptr, saved ? sv_g + g * kTfSaveGraph : nullptr, status);
+                     saved ? sv_e + e0 * kTfSaveEdge : nullptr, saved ? sv_g + g * kTfSaveGraph : nullptr, status,
+                     tf_drop_of(drop_mask, drop_scale, drop_scale_head, Ntot, n0, g));
     if (threadIdx.x < QOT_OUT) p.small[52 + threadIdx.x] = dout[g * QOT_OUT + threadIdx.x];
     __syncthreads();
-    tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes);
+    tf_graph_backward(p, node_ids, n0, static_cast<int>(n), static_cast<int>(E), num_nodes,
+                      tf_drop_of(drop_mask, drop_scale, drop_scale_head, Ntot, n0, g));
     TF_STAMP(16);
   }
   float* dst = partial + static_cast<size_t>(blockIdx.x) * gsz;
@@ -711,7 +735,8 @@ extern "C" size_t qot_topo_fused_saved_floats(int64_t N, int64_t E, int64_t B) {
 extern "C" int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* node_ids, const int64_t* edge_index,
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
                                   int64_t B, int64_t N, int32_t nmax, int32_t emax, int32_t num_nodes, float* out,
-                                  float* saved, int32_t* status, void* stream_) {
+                                  float* saved, int32_t* status, const uint8_t* drop_mask, float drop_scale,
+                                  float drop_scale_head, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_fwd");
   if (rc) return rc;
@@ -722,7 +747,8 @@ extern "C" int qot_topo_fused_fwd(const float* prepared, const float* emb, const
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = tf_blocks(B, smem);
   topo_fused_fwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
-                                                             nmax, emax, num_nodes, out, saved, N, status);
+                                                             nmax, emax, num_nodes, out, saved, N, status, drop_mask, drop_scale,
+                                                             drop_scale_head);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -735,7 +761,8 @@ extern "C" int qot_topo_fused_bwd(const float* prepared, const float* emb, const
                                   int64_t Etot, const float* edge_attr, const int64_t* gptr, const int64_t* eptr,
                                   int64_t B, int64_t N, int32_t nmax, int32_t emax, int32_t num_nodes, const float* dout,
                                   const float* saved, float* gflat, float* gemb, void* ws, size_t ws_bytes,
-                                  int32_t* status, void* stream_) {
+                                  int32_t* status, const uint8_t* drop_mask, float drop_scale, float drop_scale_head,
+                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = tf_check(B, nmax, emax, num_nodes, "qot_topo_fused_bwd");
   if (rc) return rc;
@@ -752,7 +779,8 @@ extern "C" int qot_topo_fused_bwd(const float* prepared, const float* emb, const
   QOT_CUDA(cudaFuncSetAttribute(topo_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = tf_blocks(B, smem);
   topo_fused_bwd_kernel<<<blocks, kTfThreads, smem, stream>>>(prepared, emb, node_ids, edge_index, Etot, edge_attr, gptr, eptr, B,
-                                                             nmax, emax, num_nodes, dout, saved, N, static_cast<float*>(ws), status);
+                                                             nmax, emax, num_nodes, dout, saved, N, static_cast<float*>(ws), status,
+                                                             drop_mask, drop_scale, drop_scale_head);
   QOT_LAUNCH_CHECK();
   topo_fused_reduce_kernel<<<(gsz + 31) / 32, 256, 0, stream>>>(static_cast<const float*>(ws), blocks, num_nodes, gflat, gemb);
   QOT_LAUNCH_CHECK();

@@ -823,7 +823,8 @@ def batch_max_sizes(data):
 
 class _TopoFusedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax: int, emax: int):
+    def forward(ctx, flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax: int, emax: int,
+                drop_mask=None, drop_scale: float = 1.0, drop_scale_head: float = 1.0):
         L = _lib.lib()
         B = int(gptr.numel() - 1)
         dev = flat.device
@@ -840,16 +841,17 @@ class _TopoFusedFn(torch.autograd.Function):
             saved = torch.empty(L.qot_topo_fused_saved_floats(N, E, B), dtype=torch.float32, device=dev)
         check(L.qot_topo_fused_fwd(ptr(prep), ptr(emb_), ptr(node_ids), ptr(edge_index), E,
                                    ptr(edge_attr), ptr(gptr), ptr(eptr), B, N, int(nmax), int(emax), int(emb_.shape[0]),
-                                   ptr(out), ptr(saved), ptr(status), stream()), "qot_topo_fused_fwd")
-        ctx.save_for_backward(prep, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status, saved)
-        ctx.sizes = (int(nmax), int(emax))
+                                   ptr(out), ptr(saved), ptr(status), ptr(drop_mask), float(drop_scale),
+                                   float(drop_scale_head), stream()), "qot_topo_fused_fwd")
+        ctx.save_for_backward(prep, emb_, node_ids, edge_index, edge_attr, gptr, eptr, status, saved, drop_mask)
+        ctx.sizes = (int(nmax), int(emax), float(drop_scale), float(drop_scale_head))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        prep, emb, node_ids, edge_index, edge_attr, gptr, eptr, status, saved = ctx.saved_tensors
-        nmax, emax = ctx.sizes
+        prep, emb, node_ids, edge_index, edge_attr, gptr, eptr, status, saved, drop_mask = ctx.saved_tensors
+        nmax, emax, drop_scale, drop_scale_head = ctx.sizes
         B = int(gptr.numel() - 1)
         dev = prep.device
         gflat = torch.empty(L.qot_topo_fused_params(), dtype=torch.float32, device=dev)
@@ -858,9 +860,9 @@ class _TopoFusedFn(torch.autograd.Function):
         check(L.qot_topo_fused_bwd(ptr(prep), ptr(emb), ptr(node_ids), ptr(edge_index), int(edge_index.shape[1]),
                                    ptr(edge_attr), ptr(gptr), ptr(eptr), B, int(node_ids.shape[0]), nmax, emax,
                                    int(emb.shape[0]), ptr(_f32(dout)), ptr(saved), ptr(gflat), ptr(gemb), ptr(ws),
-                                   ws.numel(), ptr(status), stream()),
+                                   ws.numel(), ptr(status), ptr(drop_mask), drop_scale, drop_scale_head, stream()),
               "qot_topo_fused_bwd")
-        return gflat, gemb, None, None, None, None, None, None, None
+        return gflat, gemb, None, None, None, None, None, None, None, None, None, None
 
 
 TOPO_FUSED_SMEM_LIMIT = 227 * 1024
@@ -874,12 +876,28 @@ def topo_fused_fits(nmax: int, emax: int, num_nodes: int) -> bool:
     return nmax <= 4096 and emax <= 512 and nbytes <= TOPO_FUSED_SMEM_LIMIT
 
 
+def topo_fused_dropout_mask(num_nodes: int, num_graphs: int, p: float, p_head: float, device):
+    """Masks for the fused training step, one byte per element: [N,16] after conv1 | [N,16] after conv2 | [B,16] in
+    the head (1 = keep), drawn with torch's generator (graph-capture safe); returns (mask, scale, scale_head)."""
+    n1 = 2 * num_nodes * 16
+    mask = torch.empty(n1 + num_graphs * 16, dtype=torch.uint8, device=device)
+    if p == p_head:
+        mask.bernoulli_(1.0 - p)
+    else:
+        mask[:n1].bernoulli_(1.0 - p)
+        mask[n1:].bernoulli_(1.0 - p_head)
+    inv = lambda q: 0.0 if q >= 1.0 else 1.0 / (1.0 - q)
+    return mask, inv(p), inv(p_head)
+
+
 def topological_fused(params: Sequence[torch.Tensor], emb, node_ids, edge_index, edge_attr, gptr, eptr,
-                      nmax: int, emax: int):
+                      nmax: int, emax: int, drop_mask=None, drop_scale: float = 1.0, drop_scale_head: float = 1.0):
     """out [B,3] of TopologicalGNN (reference shape) with one launch forward / two backward.  `params` in the
-    order of include/qot_b200.h (qot_topo_fused_fwd)."""
+    order of include/qot_b200.h (qot_topo_fused_fwd).  `drop_mask` (see topo_fused_dropout_mask): training-mode
+    dropout inside the kernels."""
     flat = torch.cat([p.reshape(-1) for p in params] + [params[0].new_zeros(1)])
-    return _TopoFusedFn.apply(flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax, emax)
+    return _TopoFusedFn.apply(flat, emb, node_ids, edge_index, edge_attr, gptr, eptr, nmax, emax,
+                              drop_mask, drop_scale, drop_scale_head)
 
 
 # --------------------------------------------------------------------------- #

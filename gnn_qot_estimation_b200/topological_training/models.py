@@ -44,15 +44,14 @@ class TopologicalGNN(torch.nn.Module):
         )
         self.dropout = torch.nn.Dropout(p=dropout_p)
 
-    # one block per graph (csrc/topo_fused.cu): the reference shape, embedding branch, dropout inactive, every
-    # graph of the batch small enough for one block's shared memory.  QOT_TOPO_FUSED=0 switches it off.
+    # one block per graph (csrc/topo_fused.cu): the reference shape, embedding branch, every graph of the batch small
+    # enough for one block's shared memory; training-mode dropout runs inside the kernels (masks drawn by torch's
+    # generator, one byte per element).  QOT_TOPO_FUSED=0 switches it off.
     use_fused = os.environ.get("QOT_TOPO_FUSED", "1") != "0"
 
     def _fused_path(self, data, node_ids, edge_index, edge_attr):
         c1, c2 = self.conv1, self.conv2
         if not self.use_fused or node_ids is None or edge_attr is None:
-            return None
-        if (self.training and (self.dropout.p > 0 or self.mlp[2].p > 0)):
             return None
         if (c1.in_channels, c1.out_channels, c1.lin_edge.in_features) != (16, 16, 4) or self.mlp[3].out_features != 3 \
                 or c2.nn[0].out_features != 8 or self.mlp[0].out_features != 16:
@@ -68,8 +67,13 @@ class TopologicalGNN(torch.nn.Module):
                   c1.lin_value.bias, c1.lin_skip.weight, c1.lin_skip.bias, c1.lin_edge.weight,
                   c2.nn[0].weight, c2.nn[0].bias, c2.nn[2].weight, c2.nn[2].bias, c2.lin.weight, c2.bias,
                   self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias]
+        drop = (None, 1.0, 1.0)
+        if self.training and (self.dropout.p > 0 or self.mlp[2].p > 0):      # models.py:55,59 and :36-41 (train.py: p = 0.5)
+            drop = getattr(data, "dropout_mask", None) or ops.topo_fused_dropout_mask(
+                int(node_ids.shape[0]), int(gptr.numel() - 1), float(self.dropout.p), float(self.mlp[2].p), node_ids.device)
+            self.last_dropout_mask = drop[0]      # tests replay it through the oracle
         return ops.topological_fused(params, self.node_embeddings.weight, node_ids, edge_index, edge_attr, gptr, eptr,
-                                     nmax, emax)
+                                     nmax, emax, *drop)
 
     @_lib.on_tensor_device
     def forward(self, data):

