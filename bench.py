@@ -6,9 +6,12 @@ lightpath_training/models/model_1.pth) over 1,000,000 synthetic lightpath graphs
 batches of 4096.  One STEP = one pass of the fused eval kernel chain over one batch.
 
   value   graphs/s, whole job, batches already resident in HBM (reference tensor layout:
-          fp32 x, int64 edge_index), steps replayed from a CUDA graph, timed with CUDA events
+          fp32 x, int64 edge_index), evaluated by LightpathGNN.forward_stream (one launch of the
+          persistent kernel per run of batches), replayed from CUDA graphs, timed with CUDA events
+          over a region of >= 100 ms whatever --steps is (`repeats`)
   e2e     graphs/s through the public host-facing API (LightpathInferencePipeline): pinned HOST
-          batches -> H2D -> kernels -> D2H of (out, lut_batch) every step
+          batches (compact wire format) -> H2D -> kernels -> D2H of (out, lut_batch) every step
+  secondary  time-boxed cfg 3 (DDP training step) and cfg 5 (stress graph) blocks
   roofline  algorithmic bytes of the dominant kernel / its measured duration vs MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (pure-PyTorch port of the reference's PyG path) on the host cores
 
@@ -445,6 +448,9 @@ def run_b200(args):
         secondary = {}
         try:
             secondary["cfg3_topo_train"] = bench_topological.measure_train(world, rank, dev, steps=300, warmup=20)
+            # the reference trains with dropout 0.5 (topological_training/train.py:54-60): same step, masks drawn per step
+            d5 = bench_topological.measure_train(world, rank, dev, steps=300, warmup=20, dropout_p=0.5, min_timed_ms=30.0)
+            secondary["cfg3_topo_train"]["dropout_0.5"] = {k: d5[k] for k in ("value", "ms_per_step", "steps")}
         except Exception as e:                                    # noqa: BLE001 -- a secondary block never kills the headline
             secondary["cfg3_topo_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if rank == 0:

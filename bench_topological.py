@@ -135,7 +135,7 @@ def run_train(args):
 
 
 def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20, graph: bool = True,
-                  min_timed_ms: float = 60.0) -> dict:
+                  min_timed_ms: float = 60.0, dropout_p: float = 0.0) -> dict:
     """BASELINE cfg 3: TopologicalGNN(14,16,3) train step (zero_grad -> forward -> SmoothL1 -> backward ->
     gradient all-reduce -> SGD(0.1, 0.9)) on 1024 NSFNET graphs per GPU, the process group (if any) already
     initialised.  Returns the JSON fields; every rank must call it (the step holds a collective at N > 1)."""
@@ -144,7 +144,7 @@ def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20
     from gnn_qot_estimation_b200.distributed import GraphDataParallel
     B = 1024
     torch.manual_seed(0)
-    model = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev)
+    model = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=dropout_p).to(dev).train()
     ddp = GraphDataParallel(model)
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
     # SmoothL1Loss (topological_training/train.py:69) as the fused loss + gradient kernel (qot_smooth_l1)
@@ -199,7 +199,7 @@ def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20
     out = {"value": world * n * B / (ms * 1e-3), "steps": n, "warmup": max(warmup, 3), "ms_per_step": ms / n,
            "final_loss": float(loss),
            "config": {"workload": "BASELINE cfg3: TopologicalGNN(14,16,3) train step, NSFNET graphs, "
-                                  f"batch {B}/GPU, SGD(0.1, 0.9), flat grad all-reduce x{world}",
+                                  f"batch {B}/GPU, SGD(0.1, 0.9), dropout {dropout_p}, flat grad all-reduce x{world}",
                       "cuda_graph": graphed is not None,
                       "exchange": (graphed.exchange if graphed is not None else ("eager" if world > 1 else "none"))}}
     # the collective alone: the flat gradient all-reduce as the step issues it, back to back
