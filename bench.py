@@ -455,6 +455,10 @@ def run_b200(args):
             secondary["cfg3_topo_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if rank == 0:
             try:
+                secondary["lightpath_train_step"] = bench_topological.measure_lightpath_train(dev, 512, 200, 5)
+            except Exception as e:                                # noqa: BLE001
+                secondary["lightpath_train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
                 secondary["cfg5_topo_stress"] = bench_topological.measure_stress(dev, reps=10)
             except Exception as e:                                # noqa: BLE001
                 secondary["cfg5_topo_stress"] = {"error": f"{type(e).__name__}: {e}"[:300]}

@@ -39,6 +39,9 @@ class Batch:
         # graph (edges grouped by source ascending, both directions present, no duplicate pair):
         # PackedGraphStore.verify_layout().  Lets the eval kernels skip the source row of edge_index.
         self.sym_by_src = bool(sym_by_src)
+        # number of readout rows (lut_ptr[-1]) when the producer of the batch knows it on the HOST (collates of a
+        # PackedGraphStore do): the training path then needs no device->host read and can be captured in a CUDA graph
+        self.lut_rows = None
         self._cache = {}          # per-batch CSR etc. built lazily by the ops layer
 
     # -- PyG-like conveniences ------------------------------------------------
@@ -57,7 +60,12 @@ class Batch:
     def to(self, device, non_blocking: bool = False) -> "Batch":
         kw = {k: (getattr(self, k).to(device, non_blocking=non_blocking)
                   if getattr(self, k) is not None else None) for k in _FIELDS}
-        return Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, sym_by_src=self.sym_by_src, **kw)
+        b = Batch(num_graphs=self.num_graphs, lut_col=self.lut_col, sym_by_src=self.sym_by_src, **kw)
+        b.lut_rows = self.lut_rows
+        for k in ("max_nodes", "max_edges"):
+            if hasattr(self, k):
+                setattr(b, k, getattr(self, k))
+        return b
 
     def pin_memory(self) -> "Batch":
         kw = {k: (getattr(self, k).pin_memory() if getattr(self, k) is not None else None)
@@ -116,6 +124,7 @@ class PackedGraphStore:
         self._edge_ptr_host = self.edge_ptr.cpu().numpy()
         self._arange = None
         self.sym_by_src = False      # set by verify_layout()
+        self._lut_count_host = None  # per-graph LUT-node counts (host), built once on first collate
 
     @property
     def num_graphs(self) -> int:
@@ -228,6 +237,13 @@ class PackedGraphStore:
             dn, de = nph[ids_np + 1] - nph[ids_np], eph[ids_np + 1] - eph[ids_np]
         b.max_nodes = int(dn.max()) if B else 0
         b.max_edges = int(de.max()) if B else 0
+        if lut_ptr is not None:
+            if self._lut_count_host is None:             # once per store: one device->host read
+                flags = (self.node_feat[:, self.lut_col] == 1.0).to(torch.int64)
+                gid = torch.repeat_interleave(torch.arange(self.num_graphs, device=dev), self.node_ptr[1:] - self.node_ptr[:-1])
+                self._lut_count_host = torch.zeros(self.num_graphs, dtype=torch.int64, device=dev).index_add_(0, gid, flags).cpu().numpy()
+            c = self._lut_count_host
+            b.lut_rows = int(c[g0:g1].sum()) if isinstance(ids, range) and ids.step == 1 else int(c[ids_np].sum())
         return b
 
     # -- the same range in the compact wire format (what travels to the GPU in LightpathInferencePipeline)

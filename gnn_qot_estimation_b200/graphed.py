@@ -25,7 +25,10 @@ a captured update as host scalars, so ``step()`` compares them with the values c
 re-captures the update when a scheduler changed them.
 
 Static shapes only (N, E, B fixed, e.g. batches of one topology such as BASELINE cfg 1/3); a batch
-of another shape raises.  Dropout masks drawn with ``torch.rand`` inside the captured region advance
+of another shape raises (ragged batches: :class:`GraphedStepCache`, one captured graph per shape).  The step is
+captured on its own stream: do not keep the (non-detached) loss of an earlier EAGER step alive while constructing
+it -- a live autograd graph pins the parameters' AccumulateGrad nodes to the stream of that eager step, and the
+capture then fails with cudaErrorStreamCaptureImplicit.  Dropout masks drawn with ``torch.rand`` inside the captured region advance
 correctly on replay (torch's CUDA generator registers with the graph).
 """
 from __future__ import annotations
@@ -49,21 +52,28 @@ def _hyper(opt: torch.optim.Optimizer):
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, criterion: Callable,
                  example: Batch, target_of: Optional[Callable] = None, ddp=None, warmup: int = 3,
-                 exchange: Optional[str] = None):
-        """``model(batch)`` -> prediction; ``criterion(pred, target_of(batch))`` -> scalar loss.
-        ``ddp``: a :class:`~.distributed.GraphDataParallel` wrapping ``model``; ``None`` for
-        single-GPU training."""
+                 exchange: Optional[str] = None, loss_of: Optional[Callable] = None, shared=None, pool=None):
+        """``model(batch)`` -> prediction; ``criterion(pred, target_of(batch))`` -> scalar loss -- or, for models whose
+        output needs more than that (LightpathGNN returns ``(out, lut_batch)``), ``loss_of(model_or_ddp, batch)`` ->
+        scalar loss.  ``ddp``: a :class:`~.distributed.GraphDataParallel` wrapping ``model``; ``None`` for
+        single-GPU training.  ``shared`` / ``pool``: set by :class:`GraphedStepCache` (one flat gradient buffer,
+        one fused optimizer tail and one graph memory pool for all its captured shapes)."""
         if not example.edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs a CUDA batch (no CPU path)")
         self.model, self.opt, self.crit, self.ddp = model, optimizer, criterion, ddp
         self.target_of = target_of or (lambda b: b.y.view(-1, 3))
+        self.loss_of = loss_of
+        self.pool = pool
         from .distributed import FlatGradBuffer, FusedSGDStep, world_info
         exchange = exchange or os.environ.get("QOT_DDP_EXCHANGE", "peer")
         if exchange not in ("peer", "graph", "eager"):
             raise ValueError(f"exchange must be 'peer', 'graph' or 'eager', got {exchange!r}")
         multi = ddp is not None and world_info()[1] > 1
         self.fused = None
-        if exchange == "peer":
+        if shared is not None:
+            self._grads, self.fused = shared
+            exchange = "peer" if self.fused is not None else exchange
+        elif exchange == "peer":
             if FusedSGDStep.supports(optimizer):
                 try:
                     self._grads = ddp.grads if ddp is not None else FlatGradBuffer(model.parameters())
@@ -77,8 +87,10 @@ class GraphedTrainStep:
                 exchange = "graph"
         self.exchange = exchange if (multi or self.fused is not None) else "none"
         self.static = Batch(num_graphs=example.num_graphs, lut_col=example.lut_col,
+                            sym_by_src=getattr(example, "sym_by_src", False),
                             **{k: (getattr(example, k).clone() if getattr(example, k) is not None else None)
                                for k in _FIELDS})
+        self.static.lut_rows = getattr(example, "lut_rows", None)
         self.shapes = {k: tuple(getattr(example, k).shape) for k in _FIELDS if getattr(example, k) is not None}
         # largest graph of the batch: sizes the shared memory of the block-per-graph kernels; read once here
         # (one host sync for a foreign batch), a constant of the captured step afterwards
@@ -89,7 +101,10 @@ class GraphedTrainStep:
         # ---- snapshot: the warm-up below takes real optimizer steps
         model_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         opt_sd = copy.deepcopy(optimizer.state_dict())
-        had_state = self.fused.had_state if self.fused is not None else len(optimizer.state) > 0
+        if self.fused is not None:
+            had_state = bool(self.fused.had_state or int(self.fused.state[1].item()) != 0)
+        else:
+            had_state = len(optimizer.state) > 0
         with torch.cuda.stream(self.stream):
             for _ in range(max(warmup, 1)):          # allocates workspaces / optimizer state eagerly
                 self._front()
@@ -128,19 +143,19 @@ class GraphedTrainStep:
         self.graph_b = None
         if self.exchange == "eager":
             self.graph_a = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_a, stream=self.stream):
+            with torch.cuda.graph(self.graph_a, stream=self.stream, pool=self.pool, capture_error_mode="thread_local"):
                 self.loss = self._front()
             self._capture_update()
         else:
             # one graph: zero -> forward -> loss -> backward (-> gather) -> exchange + optimizer
             self.graph_a = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_a, stream=self.stream):
+            with torch.cuda.graph(self.graph_a, stream=self.stream, pool=self.pool, capture_error_mode="thread_local"):
                 self.loss = self._front()
                 self._tail()
 
     def _capture_update(self) -> None:
         self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, stream=self.stream):
+        with torch.cuda.graph(self.graph_b, stream=self.stream, capture_error_mode="thread_local"):
             self.opt.step()
 
     def _front(self) -> torch.Tensor:
@@ -149,7 +164,10 @@ class GraphedTrainStep:
             self._grads.zero()
         else:
             (self.ddp or self.opt).zero_grad(set_to_none=True)   # backward writes fresh gradients
-        loss = self.crit((self.ddp or self.model)(self.static), self.target_of(self.static))
+        if self.loss_of is not None:
+            loss = self.loss_of(self.ddp or self.model, self.static)
+        else:
+            loss = self.crit((self.ddp or self.model)(self.static), self.target_of(self.static))
         loss.backward()
         if self.fused is not None:
             self._grads.gather()                     # one concatenation kernel; p.grad -> flat views
@@ -186,7 +204,7 @@ class GraphedTrainStep:
             else:
                 # re-capturing runs nothing: parameters and optimizer state are untouched
                 self.graph_a = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph_a, stream=self.stream):
+                with torch.cuda.graph(self.graph_a, stream=self.stream, capture_error_mode="thread_local"):
                     self.loss_new = self._front()
                     self._tail()
                 self.loss = self.loss_new
@@ -217,3 +235,47 @@ class GraphedTrainStep:
                 self.graph_b.replay()
         torch.cuda.current_stream().wait_stream(self.stream)
         return self.loss
+
+
+class GraphedStepCache:
+    """CUDA-graphed training steps for RAGGED batches: one captured graph per distinct batch shape.
+
+    ``lightpath_training/train.py:77-132`` walks its training set in fixed chunks with ``shuffle=False``, so the same
+    batches -- the same (N, E, B, L) -- come back every ``num_chunks`` epochs; the step itself is ~45 small launches
+    (0.3 ms of GPU work inside ~1 ms of Python and launch overhead per 512-graph batch).  The first time a shape is
+    seen its step is captured (a few eager warm-up steps whose effect on the model and the optimizer is rolled back,
+    then the capture); every later batch of that shape is one graph replay.  All captures share one memory pool
+    (only one replays at a time), one flat gradient buffer and one fused optimizer tail, so the optimizer state is
+    the same whichever graph runs.  Needs batches that carry their row counts on the host (``lut_rows``, set by
+    ``PackedGraphStore.collate``) -- a device->host read inside a capture is an error."""
+
+    def __init__(self, model, optimizer, loss_of: Callable, ddp=None, warmup: int = 2, max_entries: int = 4096):
+        from .distributed import FlatGradBuffer, FusedSGDStep
+        self.model, self.opt, self.loss_of, self.ddp = model, optimizer, loss_of, ddp
+        self.warmup, self.max_entries = warmup, max_entries
+        self.entries = {}
+        self.pool = torch.cuda.graph_pool_handle()
+        self.shared = None
+        if FusedSGDStep.supports(optimizer):
+            grads = ddp.grads if ddp is not None else FlatGradBuffer(model.parameters())
+            self.shared = (grads, FusedSGDStep(optimizer, grads))
+        self.captures = self.replays = 0
+
+    @staticmethod
+    def key_of(batch) -> tuple:
+        return tuple((k, tuple(getattr(batch, k).shape)) for k in _FIELDS if getattr(batch, k) is not None) + \
+            (getattr(batch, "lut_rows", None), getattr(batch, "max_nodes", None), getattr(batch, "max_edges", None))
+
+    def step(self, batch: Batch) -> torch.Tensor:
+        key = self.key_of(batch)
+        g = self.entries.get(key)
+        if g is None:
+            if len(self.entries) >= self.max_entries:
+                self.entries.pop(next(iter(self.entries)))
+            g = GraphedTrainStep(self.model, self.opt, None, batch, ddp=self.ddp, warmup=self.warmup,
+                                 loss_of=self.loss_of, shared=self.shared, pool=self.pool,
+                                 exchange=None if self.shared is not None else "graph")
+            self.entries[key] = g
+            self.captures += 1
+        self.replays += 1
+        return g.step(batch)

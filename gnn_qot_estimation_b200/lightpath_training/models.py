@@ -129,7 +129,8 @@ class LightpathGNN(torch.nn.Module):
         out, lut_batch = ops.lut_bn_head(
             h, data.x, data.batch, self.is_lut_index, self.norm1.module,
             self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias,
-            self.training, self.mlp[2].p if self.training else 0.0)
+            self.training, self.mlp[2].p if self.training else 0.0,
+            getattr(data, "lut_rows", None) if getattr(data, "lut_col", None) == self.is_lut_index else None)
         return out, lut_batch
 
     @_lib.on_tensor_device

@@ -401,9 +401,10 @@ def bn_batch_stats(h, running_mean=None, running_var=None, momentum: float = 0.1
     return mean, var
 
 
-def lut_select(x, batch, is_lut_index: int):
-    """Ordered LUT compaction; one host sync for the row count (the reference's
-    boolean indexing synchronises twice)."""
+def lut_select(x, batch, is_lut_index: int, n_known: Optional[int] = None):
+    """Ordered LUT compaction; one host sync for the row count (the reference's boolean indexing synchronises
+    twice) -- none when the caller knows it (`n_known`: collates of this package record it on the host as
+    ``batch.lut_rows``), which is what makes the training step CUDA-graph capturable."""
     L = _lib.lib()
     x = _f32(x)
     N, F = x.shape
@@ -414,7 +415,7 @@ def lut_select(x, batch, is_lut_index: int):
     ws = _ws(L.qot_lut_select_workspace_bytes(N), dev)
     check(L.qot_lut_select(ptr(x), N, F, int(is_lut_index), ptr(_i64(batch)), ptr(node), ptr(lb), ptr(n_lut),
                            ptr(ws), ws.numel(), stream()), "qot_lut_select")
-    n = int(n_lut.item())
+    n = int(n_lut.item()) if n_known is None else int(n_known)
     return node[:n], lb[:n], n
 
 
@@ -461,11 +462,11 @@ class _LutHeadFn(torch.autograd.Function):
 
 
 def lut_bn_head(h, x_feat, batch, is_lut_index, bn: torch.nn.BatchNorm1d, W1, b1, W2, b2,
-                training: bool, dropout_p: float = 0.0):
+                training: bool, dropout_p: float = 0.0, n_known: Optional[int] = None):
     """norm1 -> relu -> LUT readout -> mlp of lightpath_training/models.py:31-43.
     Raises ``ValueError("No LUT node found in the batch.")`` like the reference."""
     _require_cuda(h, x_feat, batch)
-    lut_node, lut_batch, n = lut_select(x_feat, batch, is_lut_index)
+    lut_node, lut_batch, n = lut_select(x_feat, batch, is_lut_index, n_known)
     if n == 0:
         raise ValueError("No LUT node found in the batch.")
     if training:

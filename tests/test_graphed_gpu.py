@@ -69,6 +69,40 @@ def test_graphed_step_follows_lr_schedule(cuda):
         assert torch.equal(p1, p2), k
 
 
+def test_ragged_lightpath_training_through_the_graph_cache(cuda):
+    """LightpathGNN training (lightpath_training/train.py:109-132: out, lut_batch = model(data); loss on y[lut_batch];
+    SGD) over RAGGED batches through GraphedStepCache: one captured graph per batch shape, replayed when the shape
+    comes back (train.py:77-95 revisits its chunks with shuffle=False).  Same trajectory as the eager loop, bit for
+    bit, including BatchNorm running statistics; no device->host read inside a step."""
+    from gnn_qot_estimation_b200 import LightpathGNN, synthetic
+    from gnn_qot_estimation_b200.graphed import GraphedStepCache
+    torch.manual_seed(2)
+    m1 = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0).to(cuda).train()
+    m2 = copy.deepcopy(m1)
+    crit = torch.nn.SmoothL1Loss()
+    o1 = torch.optim.SGD(m1.parameters(), lr=0.1, momentum=0.9)
+    o2 = torch.optim.SGD(m2.parameters(), lr=0.1, momentum=0.9)
+    store = synthetic.lightpath_store(5 * 96, seed=6).to(cuda)
+    batches = [store.collate(range(i * 96, (i + 1) * 96)) for i in range(5)]
+    assert all(b.lut_rows == 96 for b in batches) and len({b.num_nodes for b in batches}) > 1   # ragged
+
+    def loss_of(model, b):
+        out, lb = model(b)
+        return crit(out, b.y[lb])
+    cache = GraphedStepCache(m2, o2, loss_of)
+    for epoch in range(3):                                   # epoch 0 captures, epochs 1-2 replay
+        for b in batches:
+            o1.zero_grad()
+            l1 = loss_of(m1, b)
+            l1.backward()
+            o1.step()
+            l2 = cache.step(b)
+            assert torch.equal(l1.detach(), l2), (epoch, float(l1), float(l2))
+    assert cache.captures == 5 and cache.replays == 15
+    for (k, p1), (_, p2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(p1, p2), k
+
+
 @pytest.mark.parametrize("sizes", [[3000], [700, 1, 1300, 40], [260] * 7])
 def test_pool_splits_large_graphs(cuda, sizes):
     """global_mean_pool + head on graphs large enough to be split across blocks (stage-1 partials)."""
