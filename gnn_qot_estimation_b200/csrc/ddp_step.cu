@@ -28,9 +28,10 @@ constexpr int kDdpMaxWorld = 16;
 constexpr int kDdpMaxSegs = 256;             // parameter tensors of one model (the reference models have 20 / 15)
 constexpr unsigned long long kDdpTimeoutNs = 4000000000ull;   // a peer that never arrives ends the kernel (status), not a hang
 
-__device__ __forceinline__ float ld_peer(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+// L1-bypassing 16-byte load of a peer's slot (the same addresses are rewritten every second step)
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 
@@ -81,33 +82,49 @@ ddp_sgd_step_kernel(float* __restrict__ grad, float* const* __restrict__ peers, 
   const bool nesterov = hyper->nesterov != 0, maximize = hyper->maximize != 0;
   const float inv_w = 1.0f / static_cast<float>(world);
   const bool first = mom != 0.f && state[1] == 0ull;             // torch: the first step clones the gradient into the buffer
-  for (int64_t i = tid; i < n; i += kDdpThreads) {
-    float g;
+  // four elements per thread and iteration; the W remote loads of an iteration are all in flight before the first is
+  // used (a dependent load-add chain over NVLink would cost one ~1 us round trip per peer and element)
+  for (int64_t u = tid; u < n_pad / 4; u += kDdpThreads) {
+    const int64_t i0 = 4 * u;
+    float gq[4];
     if (world > 1) {
-      g = 0.f;
-      for (int r = 0; r < world; ++r) g += ld_peer(peers[r] + (step & 1ull) * n_pad + i);   // fixed order: rank 0 .. W-1
-      g *= inv_w;
-      grad[i] = g;
+      float4 v[kDdpMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kDdpMaxWorld; ++r)
+        if (r < world) v[r] = ld_peer4(peers[r] + (step & 1ull) * n_pad + i0);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < kDdpMaxWorld; ++r)                      // fixed order: rank 0 .. W-1, the same on every rank
+        if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+      gq[0] = acc.x * inv_w; gq[1] = acc.y * inv_w; gq[2] = acc.z * inv_w; gq[3] = acc.w * inv_w;
     } else {
-      g = grad[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gq[j] = i0 + j < n ? grad[i0 + j] : 0.f;
     }
-    // segment of element i (parameters in FlatGradBuffer order)
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i0 + j;
+      if (i >= n) break;
+      float g = gq[j];
+      if (world > 1) grad[i] = g;
+      // segment of element i (parameters in FlatGradBuffer order)
+      int lo = 0, hi = nseg - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      float* pp = seg_ptr[lo] + (i - seg_off[lo]);
+      float p = *pp;
+      // torch.optim.SGD (torch/optim/sgd.py, _multi_tensor_sgd), rounding step by step as its foreach kernels do
+      if (maximize) g = -g;
+      if (wd != 0.f) g = fmaf(wd, p, g);
+      if (mom != 0.f) {
+        float b = first ? g : fmaf(1.0f - damp, g, __fmul_rn(momentum_buf[i], mom));
+        momentum_buf[i] = b;
+        g = nesterov ? fmaf(mom, b, g) : b;
+      }
+      *pp = fmaf(-lr, g, p);
     }
-    float* pp = seg_ptr[lo] + (i - seg_off[lo]);
-    float p = *pp;
-    // torch.optim.SGD (torch/optim/sgd.py, _multi_tensor_sgd), rounding step by step as its foreach kernels do
-    if (maximize) g = -g;
-    if (wd != 0.f) g = fmaf(wd, p, g);
-    if (mom != 0.f) {
-      float b = first ? g : fmaf(1.0f - damp, g, __fmul_rn(momentum_buf[i], mom));
-      momentum_buf[i] = b;
-      g = nesterov ? fmaf(mom, b, g) : b;
-    }
-    *pp = fmaf(-lr, g, p);
   }
   __syncthreads();
   if (tid == 0) {

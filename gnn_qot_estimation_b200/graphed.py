@@ -52,12 +52,15 @@ def _hyper(opt: torch.optim.Optimizer):
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, criterion: Callable,
                  example: Batch, target_of: Optional[Callable] = None, ddp=None, warmup: int = 3,
-                 exchange: Optional[str] = None, loss_of: Optional[Callable] = None, shared=None, pool=None):
+                 exchange: Optional[str] = None, loss_of: Optional[Callable] = None, shared=None, pool=None,
+                 borrow_inputs: bool = False):
         """``model(batch)`` -> prediction; ``criterion(pred, target_of(batch))`` -> scalar loss -- or, for models whose
         output needs more than that (LightpathGNN returns ``(out, lut_batch)``), ``loss_of(model_or_ddp, batch)`` ->
         scalar loss.  ``ddp``: a :class:`~.distributed.GraphDataParallel` wrapping ``model``; ``None`` for
         single-GPU training.  ``shared`` / ``pool``: set by :class:`GraphedStepCache` (one flat gradient buffer,
-        one fused optimizer tail and one graph memory pool for all its captured shapes)."""
+        one fused optimizer tail and one graph memory pool for all its captured shapes).  ``borrow_inputs``: capture
+        the step on the example batch's OWN tensors instead of private copies -- ``step`` then accepts only that very
+        batch (same storage) and copies nothing: for datasets resident in HBM whose batches come back unchanged."""
         if not example.edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs a CUDA batch (no CPU path)")
         self.model, self.opt, self.crit, self.ddp = model, optimizer, criterion, ddp
@@ -86,10 +89,12 @@ class GraphedTrainStep:
             if self.fused is None:
                 exchange = "graph"
         self.exchange = exchange if (multi or self.fused is not None) else "none"
+        self.borrow = bool(borrow_inputs)
         self.static = Batch(num_graphs=example.num_graphs, lut_col=example.lut_col,
                             sym_by_src=getattr(example, "sym_by_src", False),
-                            **{k: (getattr(example, k).clone() if getattr(example, k) is not None else None)
-                               for k in _FIELDS})
+                            **{k: ((getattr(example, k) if self.borrow else getattr(example, k).clone())
+                                   if getattr(example, k) is not None else None) for k in _FIELDS})
+        self.ptrs = {k: getattr(example, k).data_ptr() for k in _FIELDS if getattr(example, k) is not None}
         self.static.lut_rows = getattr(example, "lut_rows", None)
         self.shapes = {k: tuple(getattr(example, k).shape) for k in _FIELDS if getattr(example, k) is not None}
         # largest graph of the batch: sizes the shared memory of the block-per-graph kernels; read once here
@@ -225,10 +230,14 @@ class GraphedTrainStep:
             raise RuntimeError(f"GraphedTrainStep was captured for graphs of <= {self.static.max_nodes} nodes / "
                                f"{self.static.max_edges} edges; got {mn} / {me}")
         self._check_hyper()
+        if self.borrow and any(getattr(batch, k).data_ptr() != p for k, p in self.ptrs.items()):
+            raise RuntimeError("GraphedTrainStep(borrow_inputs=True) replays on the tensors it was captured on; "
+                               "this batch lives elsewhere")
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
-            for k in self.shapes:
-                getattr(self.static, k).copy_(getattr(batch, k), non_blocking=True)
+            if not self.borrow:
+                for k in self.shapes:
+                    getattr(self.static, k).copy_(getattr(batch, k), non_blocking=True)
             self.graph_a.replay()
             if self.graph_b is not None:
                 self._exchange()
@@ -249,10 +258,14 @@ class GraphedStepCache:
     the same whichever graph runs.  Needs batches that carry their row counts on the host (``lut_rows``, set by
     ``PackedGraphStore.collate``) -- a device->host read inside a capture is an error."""
 
-    def __init__(self, model, optimizer, loss_of: Callable, ddp=None, warmup: int = 2, max_entries: int = 4096):
+    def __init__(self, model, optimizer, loss_of: Callable, ddp=None, warmup: int = 2, max_entries: int = 4096,
+                 borrow_inputs: bool = False):
         from .distributed import FlatGradBuffer, FusedSGDStep
         self.model, self.opt, self.loss_of, self.ddp = model, optimizer, loss_of, ddp
         self.warmup, self.max_entries = warmup, max_entries
+        # borrow_inputs: key by the batch's STORAGE as well and capture on its own tensors -- a resident dataset whose
+        # batch objects come back unchanged is then replayed without a single input copy
+        self.borrow = bool(borrow_inputs)
         self.entries = {}
         self.pool = torch.cuda.graph_pool_handle()
         self.shared = None
@@ -268,13 +281,15 @@ class GraphedStepCache:
 
     def step(self, batch: Batch) -> torch.Tensor:
         key = self.key_of(batch)
+        if self.borrow:
+            key = key + tuple(getattr(batch, k).data_ptr() for k in _FIELDS if getattr(batch, k) is not None)
         g = self.entries.get(key)
         if g is None:
             if len(self.entries) >= self.max_entries:
                 self.entries.pop(next(iter(self.entries)))
             g = GraphedTrainStep(self.model, self.opt, None, batch, ddp=self.ddp, warmup=self.warmup,
                                  loss_of=self.loss_of, shared=self.shared, pool=self.pool,
-                                 exchange=None if self.shared is not None else "graph")
+                                 exchange=None if self.shared is not None else "graph", borrow_inputs=self.borrow)
             self.entries[key] = g
             self.captures += 1
         self.replays += 1
