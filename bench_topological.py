@@ -203,11 +203,16 @@ def measure_train(world: int, rank: int, dev, steps: int = 300, warmup: int = 20
     def timed(n):
         e0, e1 = _ev(), _ev()
         sync()
+        prof = bool(os.environ.get("QOT_PROFILE_TIMED_REGION"))   # `ncu --profile-from-start off`: only the timed steps
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(n):
             loss = step(i)
         e1.record()
         sync()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
