@@ -61,8 +61,8 @@ class QotSgdHyper(C.Structure):
 
 
 class QotLpWireSlot(C.Structure):
-    _fields_ = [("arena", P), ("edge_index", P), ("ptrs", P), ("desc", P), ("out", P), ("lut_batch", P),
-                ("lut_node", P), ("n_lut", P), ("status", P),
+    _fields_ = [("arena", P), ("x", P), ("edge_index", P), ("ptrs", P), ("desc", P), ("result", P),
+                ("lut_node", P), ("n_lut", P),
                 ("cap_nodes", i64), ("cap_edges", i64), ("cap_graphs", i64)]
 
 
@@ -121,8 +121,9 @@ SIGNATURES = {
     "qot_ddp_sgd_step": (C.c_int, [P, P, i32, i32, i64, P, i32, P, P, P, P, vp]),
     "qot_lightpath_stream_tiles": (i64, [i64]),
     "qot_lightpath_infer_stream": (C.c_int, [P, i32, i64, i64, i64, P, i32, i32, vp]),
-    "qot_lightpath_wire_bytes": (sz, [i64, i64, i64]),
-    "qot_lightpath_infer_wire_host": (C.c_int, [P, i64, i64, i64, i64, P, i32, C.POINTER(QotLpWireSlot), P, P, P,
+    "qot_lightpath_wire_bytes": (sz, [i64, i64, i64, i64]),
+    "qot_lightpath_wire_result_bytes": (sz, [i64]),
+    "qot_lightpath_infer_wire_host": (C.c_int, [P, i64, i64, i64, i64, P, i32, C.POINTER(QotLpWireSlot), P,
                                                 C.POINTER(i64), C.POINTER(i64), vp]),
     "qot_gat_fwd": (C.c_int, [P, P, P, i64, P, P, P, P, P, P, P, P, vp]),
     "qot_gat_bwd_workspace_bytes": (sz, [i64]),

@@ -86,9 +86,10 @@ class Batch:
 
 class WireBatch:
     """A batch in the compact wire format of include/qot_b200.h (qot_lightpath_infer_wire_host): ONE contiguous
-    (pinned) host arena  int32 ptr | int32 edge_ptr | int32 lut_ptr | x fp32 [N,5] | uint8 dst [E]  -- destinations
-    as graph-local ids, no source row (verified from_networkx layout only).  ~0.78 KB per 32-node graph instead of
-    the 3.4 KB of the reference tensors (x + int64 edge_index [2,E] + offsets)."""
+    (pinned) host arena  int32 ptr | int32 edge_ptr | int32 lut_ptr | x4 fp32 [N,4] | uint8 lut_local [L] | uint8 dst [E]
+    -- the node features without the LUT flag column (exactly 0.0 / 1.0: it travels as the graph-local position of
+    every readout row), destinations as graph-local ids, no source row (verified from_networkx layout only).
+    ~0.65 KB per 32-node graph instead of the 3.4 KB of the reference tensors (x + int64 edge_index [2,E] + offsets)."""
 
     def __init__(self, arena: torch.Tensor, N: int, E: int, B: int, L: int, lut_col: int):
         self.arena, self.num_nodes, self.num_edges, self.num_graphs, self.rows, self.lut_col = arena, N, E, B, L, lut_col
@@ -98,11 +99,12 @@ class WireBatch:
         return int(self.arena.numel())
 
     @staticmethod
-    def offsets(N: int, E: int, B: int):
+    def offsets(N: int, E: int, B: int, L: int):
         a16 = lambda v: (v + 15) & ~15
         o_x = a16(12 * (B + 1))
-        o_d = o_x + a16(20 * N)
-        return o_x, o_d, o_d + a16(E)
+        o_l = o_x + a16(16 * N)
+        o_d = o_l + a16(L)
+        return o_x, o_l, o_d, o_d + a16(E)
 
 
 class PackedGraphStore:
@@ -264,18 +266,26 @@ class PackedGraphStore:
         if int((ptr[1:] - ptr[:-1]).max()) > 255:
             raise RuntimeError("host_wire_batch: a graph has more than 255 nodes (uint8 destination ids)")
         x = self.node_feat[n0:n1]
+        flag = x[:, self.lut_col]
+        is_lut = flag == 1.0
+        if not bool((is_lut | (flag == 0.0)).all()):
+            raise RuntimeError("host_wire_batch: the LUT flag column must hold exactly 0.0 / 1.0 (it is shipped as positions)")
         bt = torch.repeat_interleave(torch.arange(B, dtype=torch.int64), ptr[1:] - ptr[:-1])
         lut = torch.zeros(B + 1, dtype=torch.int64)
-        torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, (x[:, self.lut_col] == 1.0).to(torch.int64)), 0, out=lut[1:])
-        o_x, o_d, nbytes = WireBatch.offsets(N, E, B)
+        torch.cumsum(torch.zeros(B, dtype=torch.int64).index_add_(0, bt, is_lut.to(torch.int64)), 0, out=lut[1:])
+        L = int(lut[-1])
+        rows = torch.nonzero(is_lut).view(-1)                         # readout rows in ascending node order
+        o_x, o_l, o_d, nbytes = WireBatch.offsets(N, E, B, L)
         arena = torch.zeros(nbytes, dtype=torch.uint8)
         if pin:
             arena = arena.pin_memory()
         ptrs = arena[:12 * (B + 1)].view(torch.int32).view(3, B + 1)
         ptrs[0].copy_(ptr); ptrs[1].copy_(self.edge_ptr[g0:g1 + 1] - e0); ptrs[2].copy_(lut)
-        arena[o_x:o_x + 20 * N].view(torch.float32).view(N, 5).copy_(x)
+        cols = [c for c in range(5) if c != self.lut_col]
+        arena[o_x:o_x + 16 * N].view(torch.float32).view(N, 4).copy_(x[:, cols])
+        arena[o_l:o_l + L].copy_((rows - ptr[bt[rows]]).to(torch.uint8))
         arena[o_d:o_d + E].copy_(self.edge_dst[e0:e1].to(torch.uint8))
-        return WireBatch(arena, N, E, B, int(lut[-1]), self.lut_col)
+        return WireBatch(arena, N, E, B, L, self.lut_col)
 
     # -- host-side view of a contiguous range (what a host DataLoader would hand over)
     def host_batch(self, g0: int, g1: int, pin: bool = False) -> Batch:

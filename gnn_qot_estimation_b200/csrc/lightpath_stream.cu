@@ -1170,19 +1170,24 @@ lp_stream_head_kernel(const qot_lp_batch_t* __restrict__ batches, const float* _
 
 // ------------------------------------------------------------------------------------------------
 // Compact wire format of a verified-layout batch (what travels over PCIe; qot_lightpath_infer_wire_host):
-//   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad16 | float x[N,5] | pad16 | uint8 dst[E]
+//   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad16 | float x4[N,4] | pad16 | uint8 lut_local[L] | pad16
+//   | uint8 dst[E]
+// x4 = the four node features other than the LUT flag (the flag column holds exactly 0.0 / 1.0 -- checked when the
+// batch is packed -- so it travels as lut_local: the graph-local node index of every readout row, in row order);
 // dst = the destination of every edge as a GRAPH-LOCAL id (graphs of <= 255 nodes); no source row: under the
 // verified from_networkx layout (QOT_LP_SYMMETRIC_BY_SOURCE) the out-run of node u is edges
-// [#{dst < u}, #{dst <= u}) of its graph, so the sources are the run index.  776 B/graph at n = 32, E_g = 124
+// [#{dst < u}, #{dst <= u}) of its graph, so the sources are the run index.  649 B/graph at n = 32, E_g = 124
 // against 1 754 B/graph for the int64 destination row + offsets + x.
-// lp_wire_unpack_kernel rebuilds the reference layout ON THE DEVICE (int64 edge_index [2,E] with batch-global ids,
-// int64 ptr / edge_ptr / lut_ptr) and fills the sizes of the slot's batch descriptor; the
+// lp_wire_unpack_kernel rebuilds the reference layout ON THE DEVICE (x [N,5], int64 edge_index [2,E] with batch-global
+// ids, int64 ptr / edge_ptr / lut_ptr) and fills the sizes of the slot's batch descriptor; the
 // batch then goes through the same lp_stream_kernel as a resident batch (bit-identical rows).  One warp per graph.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 lp_wire_unpack_kernel(const int32_t* __restrict__ wptr, const int32_t* __restrict__ weptr, const int32_t* __restrict__ wlptr,
-                      const uint8_t* __restrict__ wdst, int64_t N, int64_t E, int64_t B, int64_t* __restrict__ ptrs,
-                      int64_t* __restrict__ edge_index, qot_lp_batch_t* __restrict__ desc, const float* __restrict__ x) {
+                      const uint8_t* __restrict__ wdst, const float* __restrict__ x4, const uint8_t* __restrict__ wlut,
+                      int lut_col, int64_t N, int64_t E, int64_t B, int64_t L, int64_t* __restrict__ ptrs,
+                      int64_t* __restrict__ edge_index, qot_lp_batch_t* __restrict__ desc, float* __restrict__ x,
+                      char* __restrict__ result) {
   __shared__ int hist[8][257];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t gtid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -1196,20 +1201,34 @@ lp_wire_unpack_kernel(const int32_t* __restrict__ wptr, const int32_t* __restric
     desc->ptr = ptrs; desc->edge_ptr = ptrs + (B + 1); desc->lut_ptr = ptrs + 2 * (B + 1);
     desc->N = N; desc->E = E; desc->B = B;
     desc->tile0 = 0;
+    // result arena of the slot: [status, 16 bytes | out [L,3] | pad to 16 | lut_batch [L]] -- ONE device->host copy
+    desc->status = reinterpret_cast<int32_t*>(result);
+    desc->out = reinterpret_cast<float*>(result + 16);
+    desc->lut_batch = reinterpret_cast<int64_t*>(result + 16 + ((12 * L + 15) & ~15ll));
   }
   int* h = hist[w];
   for (int64_t g = blockIdx.x * 8ll + w; g < B; g += static_cast<int64_t>(gridDim.x) * 8) {
     const int n0 = wptr[g], n = wptr[g + 1] - n0, e0 = weptr[g], ne = weptr[g + 1] - e0;
     if (n < 0 || n > 255 || ne < 0 || e0 < 0 || static_cast<int64_t>(e0) + ne > E) {
-      if (lane == 0) atomicOr(desc->status, 1);                      // malformed offsets: nothing is written for the graph
+      if (lane == 0) atomicOr(reinterpret_cast<int32_t*>(result), 1);   // malformed offsets: nothing is written for the graph
       continue;
+    }
+    // node features: the four shipped columns around a LUT flag column of zeros, then 1.0 at the readout rows
+    for (int i = lane; i < n * kF; i += 32) {
+      const int node = i / kF, c = i % kF;
+      x[static_cast<int64_t>(n0) * kF + i] = c == lut_col ? 0.f : x4[(static_cast<int64_t>(n0) + node) * 4 + (c - (c > lut_col))];
+    }
+    __syncwarp();
+    for (int r = wlptr[g] + lane; r < wlptr[g + 1]; r += 32) {
+      const int li = wlut[r];
+      if (li < n) x[(static_cast<int64_t>(n0) + li) * kF + lut_col] = 1.0f; else atomicOr(reinterpret_cast<int32_t*>(result), 1);
     }
     for (int i = lane; i <= n; i += 32) h[i] = 0;
     __syncwarp();
     for (int i = lane; i < ne; i += 32) {
       const int d = wdst[e0 + i];
       edge_index[E + e0 + i] = n0 + d;                               // destination row
-      if (d < n) atomicAdd(&h[d + 1], 1); else atomicOr(desc->status, 1);
+      if (d < n) atomicAdd(&h[d + 1], 1); else atomicOr(reinterpret_cast<int32_t*>(result), 1);
     }
     __syncwarp();
     // exclusive prefix of the in-degree (= out-degree) histogram: h[u] = first edge of node u's run
@@ -1297,49 +1316,55 @@ extern "C" int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t
 }
 
 static inline size_t wire_align16(size_t v) { return (v + 15) & ~size_t(15); }
-extern "C" size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B) {
-  if (N < 0 || E < 0 || B < 0) return 0;
-  return wire_align16(12 * static_cast<size_t>(B + 1)) + wire_align16(20 * static_cast<size_t>(N)) + wire_align16(static_cast<size_t>(E));
+extern "C" size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B, int64_t L) {
+  if (N < 0 || E < 0 || B < 0 || L < 0) return 0;
+  return wire_align16(12 * static_cast<size_t>(B + 1)) + wire_align16(16 * static_cast<size_t>(N)) + wire_align16(static_cast<size_t>(L)) +
+         wire_align16(static_cast<size_t>(E));
+}
+
+extern "C" size_t qot_lightpath_wire_result_bytes(int64_t L) {
+  return L < 0 ? 0 : 16 + wire_align16(12 * static_cast<size_t>(L)) + 8 * static_cast<size_t>(L);
 }
 
 // One batch from PINNED HOST memory in the compact wire format, end to end on `stream`: ONE host->device copy of the
-// arena, lp_wire_unpack_kernel, lp_stream_kernel over the slot's descriptor, device->host copies of rows [0, L) of
-// out / lut_batch and of the status word (L = the batch's readout rows, known on the host: lut_ptr[B]).  Nothing
+// arena, lp_wire_unpack_kernel, lp_stream_kernel over the slot's descriptor, ONE device->host copy of the result arena
+// [status | out rows | lut_batch rows] (L = the batch's readout rows, known on the host: lut_ptr[B]).  Nothing
 // synchronises; the caller waits on its own event.  The slot is caller-owned device memory (see qot_lp_wire_slot_t).
 extern "C" int qot_lightpath_infer_wire_host(const void* arena_host, int64_t N, int64_t E, int64_t B, int64_t L,
                                              const float* prepared, int32_t is_lut_index, const qot_lp_wire_slot_t* slot,
-                                             float* out_host, int64_t* lut_batch_host, int32_t* status_host,
-                                             int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream_) {
+                                             void* result_host, int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  QOT_REQUIRE(arena_host && slot && prepared && out_host && lut_batch_host && status_host, "qot_lightpath_infer_wire_host: null argument");
+  QOT_REQUIRE(arena_host && slot && prepared && result_host, "qot_lightpath_infer_wire_host: null argument");
   QOT_REQUIRE(N > 0 && B > 0 && E >= 0 && L >= 0 && L <= N, "qot_lightpath_infer_wire_host: bad size");
-  QOT_REQUIRE(slot->arena && slot->edge_index && slot->ptrs && slot->desc && slot->out && slot->lut_batch && slot->lut_node &&
-                  slot->n_lut && slot->status, "qot_lightpath_infer_wire_host: incomplete staging slot");
+  QOT_REQUIRE(slot->arena && slot->x && slot->edge_index && slot->ptrs && slot->desc && slot->result && slot->lut_node &&
+                  slot->n_lut, "qot_lightpath_infer_wire_host: incomplete staging slot");
+  QOT_REQUIRE(is_lut_index >= 0 && is_lut_index < kF, "qot_lightpath_infer_wire_host: is_lut_index out of range");
   QOT_REQUIRE(N <= slot->cap_nodes && E <= slot->cap_edges && B <= slot->cap_graphs,
               "qot_lightpath_infer_wire_host: batch (N=%lld, E=%lld, B=%lld) exceeds the slot capacity", (long long)N,
               (long long)E, (long long)B);
-  QOT_REQUIRE((reinterpret_cast<uintptr_t>(slot->arena) & 15) == 0 && (reinterpret_cast<uintptr_t>(slot->desc) & 15) == 0,
-              "qot_lightpath_infer_wire_host: slot arena / descriptor must be 16-byte aligned");
-  const size_t nbytes = qot_lightpath_wire_bytes(N, E, B);
+  QOT_REQUIRE((reinterpret_cast<uintptr_t>(slot->arena) & 15) == 0 && (reinterpret_cast<uintptr_t>(slot->desc) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(slot->result) & 15) == 0,
+              "qot_lightpath_infer_wire_host: slot arena / descriptor / result must be 16-byte aligned");
+  const size_t nbytes = qot_lightpath_wire_bytes(N, E, B, L), rbytes = qot_lightpath_wire_result_bytes(L);
   QOT_CUDA(cudaMemcpyAsync(slot->arena, arena_host, nbytes, cudaMemcpyHostToDevice, stream));
   const char* a = static_cast<const char*>(slot->arena);
   const int32_t* wptr = reinterpret_cast<const int32_t*>(a);
-  const float* x = reinterpret_cast<const float*>(a + wire_align16(12 * static_cast<size_t>(B + 1)));
-  const uint8_t* wdst = reinterpret_cast<const uint8_t*>(a + wire_align16(12 * static_cast<size_t>(B + 1)) + wire_align16(20 * static_cast<size_t>(N)));
-  QOT_CUDA(cudaMemsetAsync(slot->status, 0, 4, stream));
+  const size_t o_x = wire_align16(12 * static_cast<size_t>(B + 1)), o_l = o_x + wire_align16(16 * static_cast<size_t>(N)),
+               o_d = o_l + wire_align16(static_cast<size_t>(L));
+  const float* x4 = reinterpret_cast<const float*>(a + o_x);
+  const uint8_t* wlut = reinterpret_cast<const uint8_t*>(a + o_l);
+  const uint8_t* wdst = reinterpret_cast<const uint8_t*>(a + o_d);
+  QOT_CUDA(cudaMemsetAsync(slot->result, 0, 16, stream));           // the status word
   const unsigned ub = static_cast<unsigned>(std::min<int64_t>(cdiv(B, 8), 4 * kNumSMs));
-  lp_wire_unpack_kernel<<<ub, 256, 0, stream>>>(wptr, wptr + (B + 1), wptr + 2 * (B + 1), wdst, N, E, B, slot->ptrs,
-                                               slot->edge_index, slot->desc, x);
+  lp_wire_unpack_kernel<<<ub, 256, 0, stream>>>(wptr, wptr + (B + 1), wptr + 2 * (B + 1), wdst, x4, wlut, is_lut_index, N, E, B, L,
+                                               slot->ptrs, slot->edge_index, slot->desc, slot->x,
+                                               static_cast<char*>(slot->result));
   QOT_LAUNCH_CHECK();
   const int64_t tiles = qot_lightpath_stream_tiles(B);
   int rc = qot_lightpath_infer_stream(slot->desc, 1, tiles, tiles, L, prepared, is_lut_index, QOT_LP_SYMMETRIC_BY_SOURCE, stream_);
   if (rc) return rc;
-  if (L > 0) {
-    QOT_CUDA(cudaMemcpyAsync(out_host, slot->out, L * QOT_OUT * 4, cudaMemcpyDeviceToHost, stream));
-    QOT_CUDA(cudaMemcpyAsync(lut_batch_host, slot->lut_batch, L * 8, cudaMemcpyDeviceToHost, stream));
-  }
-  QOT_CUDA(cudaMemcpyAsync(status_host, slot->status, 4, cudaMemcpyDeviceToHost, stream));
+  QOT_CUDA(cudaMemcpyAsync(result_host, slot->result, rbytes, cudaMemcpyDeviceToHost, stream));
   if (h2d_bytes) *h2d_bytes = static_cast<int64_t>(nbytes);
-  if (d2h_bytes) *d2h_bytes = L * (QOT_OUT * 4 + 8) + 4;
+  if (d2h_bytes) *d2h_bytes = static_cast<int64_t>(rbytes);
   return QOT_OK;
 }

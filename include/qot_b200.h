@@ -346,32 +346,36 @@ int qot_lightpath_infer_stream(const qot_lp_batch_t* batches, int32_t n_batches,
 /* The evaluation loop of lightpath_training/test.py:77-94 for batches arriving from the HOST: one call per batch
  * replaces `data.to(device)` -> `model(data)` -> `.cpu()`.  The batch travels in the COMPACT WIRE FORMAT of a
  * verified-layout batch (see QOT_LP_SYMMETRIC_BY_SOURCE; PackedGraphStore.host_wire_batch packs it), one contiguous
- * pinned arena of qot_lightpath_wire_bytes(N, E, B) bytes:
- *   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad to 16 | float x[N,5] | pad to 16 | uint8 dst[E]
- * (dst: graph-local destination id of every edge, graphs of <= 255 nodes; no source row).  On `stream`: ONE
- * host->device copy of the arena; lp_wire_unpack_kernel rebuilds the reference layout in the slot (int64 edge_index
- * [2,E], int64 offsets), fills the slot's descriptor and clears its status; lp_stream_kernel (the same kernel resident
- * batches take: bit-identical rows); device->host copies of rows [0, L) of out / lut_batch and of the status word,
+ * pinned arena of qot_lightpath_wire_bytes(N, E, B, L) bytes:
+ *   int32 ptr[B+1] | int32 edge_ptr[B+1] | int32 lut_ptr[B+1] | pad to 16 | float x4[N,4] | pad to 16 |
+ *   uint8 lut_local[L] | pad to 16 | uint8 dst[E]
+ * (x4: the node features without the LUT flag column, which must hold exactly 0.0 / 1.0 and travels as lut_local, the
+ * graph-local node index of every readout row in row order; dst: graph-local destination id of every edge, graphs of
+ * <= 255 nodes; no source row).  On `stream`: ONE host->device copy of the arena; lp_wire_unpack_kernel rebuilds the
+ * reference layout in the slot (x [N,5], int64 edge_index [2,E], int64 offsets) and fills the slot's descriptor; the
+ * status word is cleared; lp_stream_kernel (the same kernel resident
+ * batches take: bit-identical rows); ONE device->host copy of the result arena [status | out rows | lut_batch rows],
  * L = lut_ptr[B] (known on the host).  No synchronisation: the caller waits on its own event.
  * h2d_bytes / d2h_bytes (optional, host): bytes this call copied in each direction. */
 typedef struct {
-  void* arena;            /* qot_lightpath_wire_bytes(cap_nodes, cap_edges, cap_graphs) bytes, 16-byte aligned */
+  void* arena;            /* qot_lightpath_wire_bytes(cap_nodes, cap_edges, cap_graphs, cap_nodes) bytes, 16-byte aligned */
+  float* x;               /* [cap_nodes, 5] -- rebuilt on the device                                           */
   int64_t* edge_index;    /* [2, cap_edges] -- rebuilt on the device                                           */
   int64_t* ptrs;          /* [3 * (cap_graphs + 1)]                                                            */
-  qot_lp_batch_t* desc;   /* ONE descriptor in device memory, 16-byte aligned; the caller sets out, lut_batch,
-                             lut_node, n_lut, status and z once (the slot's own buffers), the call fills the rest */
-  float* out;             /* [cap_rows, 3]  (same pointers as in desc)                                         */
-  int64_t* lut_batch;     /* [cap_rows]                                                                        */
+  qot_lp_batch_t* desc;   /* ONE descriptor in device memory, 16-byte aligned; the caller sets lut_node, n_lut and z
+                             once (the slot's own buffers), the call fills the rest                             */
+  void* result;           /* qot_lightpath_wire_result_bytes(cap_nodes) bytes, 16-byte aligned:
+                             [status int32, 16 bytes | out [L,3] fp32 | pad to 16 | lut_batch [L] int64]         */
   int32_t* lut_node;      /* [cap_rows]                                                                        */
   int32_t* n_lut;         /* [1]                                                                               */
-  int32_t* status;        /* [1]                                                                               */
   int64_t cap_nodes, cap_edges, cap_graphs;
 } qot_lp_wire_slot_t;
-size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B);
+size_t qot_lightpath_wire_bytes(int64_t N, int64_t E, int64_t B, int64_t L);
+size_t qot_lightpath_wire_result_bytes(int64_t L);
+/* result_host: pinned, qot_lightpath_wire_result_bytes(L) bytes, same layout as slot->result (ONE device->host copy). */
 int qot_lightpath_infer_wire_host(const void* arena_host, int64_t N, int64_t E, int64_t B, int64_t L,
                                   const float* prepared, int32_t is_lut_index, const qot_lp_wire_slot_t* slot,
-                                  float* out_host, int64_t* lut_batch_host, int32_t* status_host,
-                                  int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream);
+                                  void* result_host, int64_t* h2d_bytes, int64_t* d2h_bytes, void* stream);
 
 /* General GATConv forward over a destination-sorted CSR built with flags=3
  * (self loops replaced): h [N,128] = concat_h sum_j alpha_ij W_h x_j + bias.

@@ -219,9 +219,9 @@ def test_pipeline_matches_module(cuda, lut_per_graph):
     assert store.verify_layout()
     wbs = [store.host_wire_batch(i * 128, (i + 1) * 128, pin=True) for i in range(7)]
     hbs = [store.host_batch(i * 128, (i + 1) * 128) for i in range(7)]
-    for wb, hb in zip(wbs, hbs):        # 12 B/graph + 20 B/node + 1 B/edge (+ alignment): a quarter of the reference tensors
-        assert wb.nbytes <= 12 * 129 + 20 * hb.num_nodes + hb.num_edges + 48
-        assert wb.nbytes < 0.25 * hb.nbytes(("x", "edge_index", "ptr", "edge_ptr", "lut_ptr"))
+    for wb, hb in zip(wbs, hbs):        # 12 B/graph + 16 B/node + 1 B/row + 1 B/edge (+ alignment): a quarter of the reference tensors at this graph size
+        assert wb.nbytes <= 12 * 129 + 16 * hb.num_nodes + wb.rows + hb.num_edges + 64
+        assert wb.nbytes < 0.26 * hb.nbytes(("x", "edge_index", "ptr", "edge_ptr", "lut_ptr"))
     pipe = LightpathInferencePipeline(m, max_nodes=max(b.num_nodes for b in hbs),
                                       max_edges=max(b.num_edges for b in hbs), max_graphs=128, depth=3)
     res = pipe.run(wbs)
@@ -231,13 +231,18 @@ def test_pipeline_matches_module(cuda, lut_per_graph):
             eo, el = m(hb.to(cuda))
             assert torch.equal(o, eo.cpu()) and torch.equal(l, el.cpu())
     assert pipe.steps == 7 and pipe.h2d_bytes == sum(wb.nbytes for wb in wbs) and pipe.d2h_bytes > 0
-    # the last batch is still unpacked in its slot: int64 edge_index [2,E] and offsets equal the reference tensors
+    # the last batch is still unpacked in its slot: x, int64 edge_index [2,E] and offsets equal the reference tensors
     slot, hb = pipe.slots[6 % 3], hbs[6]
     E = hb.num_edges
+    assert torch.equal(slot.x[:hb.num_nodes].cpu(), hb.x)                              # LUT column rebuilt from positions
     assert torch.equal(slot.edge_index.view(-1)[:E].cpu(), hb.edge_index[0])          # sources, rebuilt from the runs
     assert torch.equal(slot.edge_index.view(-1)[E:2 * E].cpu(), hb.edge_index[1])
     B = hb.num_graphs
     assert torch.equal(slot.ptrs[:3 * (B + 1)].view(3, B + 1).cpu(), torch.stack([hb.ptr, hb.edge_ptr, hb.lut_ptr]))
+    keep = [(o.clone(), l.clone()) for o, l in res]
+    res2 = pipe.run(wbs[:2])                                   # a second run must not overwrite results still alive
+    assert all(torch.equal(a, c) and torch.equal(b, d) for (a, b), (c, d) in zip(res, keep))
+    assert torch.equal(res2[0][0], res[0][0]) and torch.equal(res2[1][1], res[1][1])
 
 
 def test_stale_lut_ptr_is_reported(cuda):
