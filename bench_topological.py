@@ -305,6 +305,24 @@ def measure_stress(dev, reps: int = 20) -> dict:
         for _ in range(3):
             model(b)
         fwd_ms = timed(lambda: model(b))
+        # the same forward as ONE CUDA-graph replay (~25 launches of 3-70 us each: a third of the eager time is launch gaps)
+        fwd_graph_ms = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model(b)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    out_g = model(b)
+                g.replay()
+                torch.cuda.synchronize()
+            torch.cuda.current_stream().wait_stream(side)
+            assert torch.equal(out_g, model(b))
+            fwd_graph_ms = timed(lambda: g.replay())
+        except Exception as e:                                  # noqa: BLE001 -- the eager figure stands
+            fwd_graph_ms = f"capture failed: {type(e).__name__}"
     model.train()
 
     def fb():
@@ -314,7 +332,7 @@ def measure_stress(dev, reps: int = 20) -> dict:
         fb()
     fb_ms = timed(fb)
     conv_bytes = 8 * H * N + 4 * (N + 1) + 4 * E + 16 * E
-    return {"value": fwd_ms, "fwd_bwd_ms": fb_ms,
+    return {"value": fwd_ms, "fwd_cuda_graph_ms": fwd_graph_ms, "fwd_bwd_ms": fb_ms,
             "alg_bytes": {"conv_fwd_each": conv_bytes, "fwd_total": 2 * conv_bytes + 4 * H * N + 4 * 2 + 12},
             "config": {"workload": f"BASELINE cfg5: TopologicalGNN({N},{H},3), one graph, {N} nodes, {E} directed "
                                    "edges; L2 flushed between iterations"}}

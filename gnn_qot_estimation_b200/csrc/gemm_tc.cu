@@ -3,7 +3,7 @@
 // computed as three TF32 tcgen05.mma products per k-step on error-compensated operands
 //   a = a_hi + a_lo,  w = w_hi + w_lo   (hi = round-to-tf32, lo = tf32(a - hi)),
 //   a*w ~= a_hi*w_lo + a_lo*w_hi + a_hi*w_hi      (the dropped a_lo*w_lo term is ~2^-22 relative)
-// accumulated in fp32 in TMEM.  This is the one place on the path where the hidden width makes the
+// accumulated in fp32 -- short chains in TMEM, the chains summed round-to-nearest in registers.  This is the one place on the path where the hidden width makes the
 // projection a real contraction (BASELINE cfg 5: [10000,256] x [256,1024] and x [256,2560], 18 GFLOP);
 // at the reference widths (H = 16 / 32) the FFMA kernel in dense.cu stays in charge.
 //
@@ -14,8 +14,9 @@
 // (A_hi, A_lo, W_hi, W_lo; 64 KB) are copied global -> shared with cp.async (LDGSTS, zero-filled
 // past the matrix edge) straight into the 128-byte-swizzled K-major layout the UMMA shared-memory
 // descriptor expects, three stages deep; one elected thread issues the 12 MMAs of the block and
-// commits them to the stage's mbarrier, which gates the refill of that stage.  Epilogue:
-// tcgen05.ld (32 lanes x 32 columns per warp) + bias -> global.
+// commits them to the stage's mbarrier, which gates the refill of that stage.  Every TC_CHAIN k-blocks
+// the finished TMEM accumulator (one of two, 2 x 128 columns) is read with tcgen05.ld (32 lanes x 32
+// columns per warp) and added into registers; epilogue: registers + bias -> global.
 #include <algorithm>
 
 #include "common.cuh"
@@ -24,9 +25,14 @@ namespace qot {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 256;                               // warps 0-3: loads + MMA issue, warps 4-7: drain + epilogue
+#ifndef QOT_TC_CHAIN
+#define QOT_TC_CHAIN 2
+#endif
+constexpr int64_t TC_CHAIN = QOT_TC_CHAIN;                     // k-blocks per TMEM accumulation chain (see the main loop)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 64;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128;
 constexpr unsigned TC_SPIN_LIMIT = 1u << 26;                // a wedged barrier ends the kernel, never hangs it
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -71,6 +77,22 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return true;
+  }
+  return false;
+}
+// the same for a warp with nothing else to do (the drain warpgroup): a spinning try_wait takes issue slots from the
+// load warps on its scheduler, so back off between polls
+__device__ __forceinline__ bool mbar_wait_parked(unsigned bar, unsigned parity) {
+  for (unsigned spin = 0; spin < (TC_SPIN_LIMIT >> 4); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    __nanosleep(100);
   }
   return false;
 }
@@ -160,7 +182,7 @@ __device__ __forceinline__ void cp_async_tile(const float* __restrict__ src, int
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    const float* __restrict__ Whi, const float* __restrict__ Wlo,
                    const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M,
@@ -168,19 +190,25 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   extern __shared__ char tc_smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + TC_STAGES);
+  unsigned long long* chain_full = bars + TC_STAGES;              // [2] MMA thread -> drain warps: chain finished
+  unsigned long long* chain_free = chain_full + 2;                // [2] drain warps -> MMA thread: accumulator read out
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * TC_BM, n0 = static_cast<int64_t>(blockIdx.y) * TC_BN;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(static_cast<unsigned>(TC_BN))
+                 "r"(static_cast<unsigned>(2 * TC_BN))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(chain_full + s)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(chain_free + s)) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -194,107 +222,135 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   const int64_t kb0 = static_cast<int64_t>(blockIdx.z) * kb_per_split;
   const int64_t nkb = max(static_cast<int64_t>(0), min(K / TC_BK - kb0, kb_per_split));
   if (gridDim.z > 1) C += static_cast<int64_t>(blockIdx.z) * M * Nc;
-  auto issue_loads = [&](int64_t kb) {
-    char* base = smem + static_cast<int>(kb % TC_STAGES) * TC_STAGE_BYTES;
-    const int64_t k0 = (kb0 + kb) * TC_BK;
-    cp_async_tile(Ahi, K, m0, M, k0, base, tid);
-    cp_async_tile(Alo, K, m0, M, k0, base + TC_TILE_BYTES, tid);
-    cp_async_tile(Whi, K, n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
-    cp_async_tile(Wlo, K, n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
-  };
   bool ok = true;
-  for (int64_t kb = 0; kb < TC_STAGES - 1; ++kb) {                  // prologue: STAGES-1 blocks in flight
-    if (kb < nkb) issue_loads(kb);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (int64_t kb = 0; kb < nkb; ++kb) {
-    const int st = static_cast<int>(kb % TC_STAGES);
-    asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block kb landed
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
-      const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
-#pragma unroll
-      for (int s = 0; s < TC_BK / 8; ++s) {                         // UMMA_K = 8 for tf32: 32 bytes per step
-        const unsigned ko = s * 32;
-        umma_tf32(tmem_d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, (kb | s) != 0);
-        umma_tf32(tmem_d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-        umma_tf32(tmem_d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-      }
-      // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(bars + st))
-                   : "memory");
-    }
-    // refill the stage block kb-1 used, for block kb+STAGES-1.  Its MMAs are waited for only now, with
-    // the MMAs of block kb already queued behind them, so the tensor pipe never drains.
-    const int64_t nxt = kb + TC_STAGES - 1;
-    if (nxt < nkb) {
-      if (kb >= 1)
-        ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
-                        static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
-      issue_loads(nxt);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // the last commit covers all MMAs: wait for it before reading the accumulator
-  if (nkb > 0) {
-    const int64_t last = nkb - 1;
-    ok &= mbar_wait(smem_u32(bars + static_cast<int>(last % TC_STAGES)),
-                    static_cast<unsigned>((last / TC_STAGES) & 1));
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (!ok && status) atomicOr(status, 2);
 
-  // ---- epilogue: warp w reads TMEM lanes [32w, 32w+32) = tile rows, 32 columns at a time
-  const int64_t row = m0 + warp * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-    unsigned r[32];
-    const unsigned taddr = tmem_d + (static_cast<unsigned>(warp * 32) << 16) + static_cast<unsigned>(c0);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (nkb == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0u;                       // empty k-slice: the accumulator was never written
+  // Accumulation happens in two places.  The tensor core adds into TMEM with truncation, so the error of a chain of
+  // MMAs on one accumulator grows LINEARLY with its length (profiles/r2_tc_chain_accuracy.md: max error / max|C| of
+  // [10000,256]x[256,1024] is 3.1e-7, 5.5e-7, 1.1e-6, 2.5e-6 for chains of 1, 2, 4, 8 k-blocks; a weight gradient
+  // reduced over 80 000 rows in one chain per split-K slice sat at 9e-6, torch's fp32 GEMM at 8e-7).  So a TMEM
+  // accumulator only ever holds a CHAIN of TC_CHAIN k-blocks (2: 24 MMAs).  Two accumulators alternate; a second
+  // warpgroup (warps 4-7, TMEM lane quarter = warp % 4) reads each finished chain with tcgen05.ld and adds it,
+  // round-to-nearest, into fp32 registers (128 per thread: its row of the tile) while the load/MMA warpgroup runs
+  // ahead -- the drain is off the load -> MMA -> refill critical path.
+  if (warp < 4) {
+    // ================= load + MMA warpgroup =================
+    auto issue_loads = [&](int64_t kb) {
+      char* base = smem + static_cast<int>(kb % TC_STAGES) * TC_STAGE_BYTES;
+      const int64_t k0 = (kb0 + kb) * TC_BK;
+      cp_async_tile(Ahi, K, m0, M, k0, base, tid);
+      cp_async_tile(Alo, K, m0, M, k0, base + TC_TILE_BYTES, tid);
+      cp_async_tile(Whi, K, n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
+      cp_async_tile(Wlo, K, n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
+    };
+    for (int64_t kb = 0; kb < TC_STAGES - 1; ++kb) {                  // prologue: STAGES-1 blocks in flight
+      if (kb < nkb) issue_loads(kb);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (row < M) {
-      float* crow = C + row * ldc + n0 + c0;
-      if (n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      const int st = static_cast<int>(kb % TC_STAGES);
+      asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block kb landed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
+      asm volatile("bar.sync 1, 128;" ::: "memory");                   // ... and everybody else's (this warpgroup only)
+      if (tid == 0) {
+        const int64_t c = kb / TC_CHAIN;                               // chain of this block, accumulator c & 1
+        if (kb % TC_CHAIN == 0 && c >= 2)                              // chain c-2 must have been read out
+          ok &= mbar_wait(smem_u32(chain_free + (c & 1)), static_cast<unsigned>(((c >> 1) - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+        const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+        const unsigned d = tmem_d + static_cast<unsigned>((c & 1) * TC_BN);
+        const bool fresh = kb % TC_CHAIN == 0;                         // first block of a chain overwrites
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
-          if (bias) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          *reinterpret_cast<float4*>(crow + j) = o;
+        for (int s = 0; s < TC_BK / 8; ++s) {                          // UMMA_K = 8 for tf32: 32 bytes per step
+          const unsigned ko = s * 32;
+          umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, !(fresh && s == 0));
+          umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+          umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
         }
-      } else {
+        // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(bars + st))
+                     : "memory");
+        if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == nkb - 1)           // ... and on the chain barrier: accumulator complete
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(chain_full + (c & 1)))
+                       : "memory");
+      }
+      // refill the stage block kb-1 used, for block kb+STAGES-1.  Its MMAs are waited for only now, with
+      // the MMAs of block kb already queued behind them, so the tensor pipe never drains.
+      const int64_t nxt = kb + TC_STAGES - 1;
+      if (nxt < nkb) {
+        if (kb >= 1)
+          ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
+                          static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
+        issue_loads(nxt);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  } else {
+    // ================= drain + epilogue warpgroup =================
+    const int q = warp - 4;                                            // TMEM lanes [32q, 32q+32) = tile rows
+    float acc[TC_BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < Nc) crow[j] = __uint_as_float(r[j]) + (bias ? bias[n0 + c0 + j] : 0.f);
+    for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+    const int64_t nchains = (nkb + TC_CHAIN - 1) / TC_CHAIN;
+    for (int64_t c = 0; c < nchains; ++c) {
+      ok &= mbar_wait_parked(smem_u32(chain_full + (c & 1)), static_cast<unsigned>((c >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>((c & 1) * TC_BN);
+#pragma unroll
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        unsigned r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(base + static_cast<unsigned>(c0))
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + (c & 1))) : "memory");
+    }
+    // ---- epilogue: thread = tile row, its 128 columns are in registers (an empty k-slice writes zeros)
+    const int64_t row = m0 + q * 32 + lane;
+    if (row < M) {
+#pragma unroll
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        float* crow = C + row * ldc + n0 + c0;
+        if (n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+            if (bias) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < Nc) crow[j] = acc[c0 + j] + (bias ? bias[n0 + c0 + j] : 0.f);
+        }
       }
     }
   }
+  if (!ok && status) atomicOr(status, 2);
+  // the drain warpgroup leaves its loop only after the last chain barrier, i.e. after every MMA has finished
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
-                 "r"(static_cast<unsigned>(TC_BN))
+                 "r"(static_cast<unsigned>(2 * TC_BN))
                  : "memory");
 }
 
@@ -344,7 +400,7 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
   QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");
-  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K,
+  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K,
                                                             K / TC_BK, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
@@ -396,11 +452,11 @@ extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int
   QOT_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(cdiv(Mo, TC_BM)), static_cast<unsigned>(cdiv(No, TC_BN)), static_cast<unsigned>(splits));
   if (splits == 1) {
-    gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, status);
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, status);
     QOT_LAUNCH_CHECK();
     return QOT_OK;
   }
-  gemm_tf32x3_kernel<<<grid, 128, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, status);
+  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, status);
   QOT_LAUNCH_CHECK();
   const int64_t n = Mo * No;
   tc_reduce_splits_kernel<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, stream>>>(part, n, splits, C, No, ldc);

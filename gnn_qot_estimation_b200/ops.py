@@ -229,6 +229,7 @@ class LightpathStreamPlan:
                                    "is_lut_index (PackedGraphStore.collate provides them)")
             _require_cuda(b.x, b.edge_index, b.ptr, b.edge_ptr, b.lut_ptr)
         self.batches = list(batches)                 # keeps the input tensors alive
+        self.device = dev                            # (_lib.on_tensor_device makes it current around forward_stream)
         self.is_lut_index = int(is_lut_index)
         # QOT_LP_SYMMETRIC_BY_SOURCE only when EVERY batch carries the verified-layout mark
         self.flags = (1 if all(getattr(b, "sym_by_src", False) for b in batches) else 0) | (2 if split_head else 0)

@@ -40,3 +40,31 @@ def test_ddp_over_nvlink(exchange):
     assert proc.returncode == 0, (out[-2000:], err[-3000:])
     assert "replicas identical after graphed steps: True" in out
     assert f"exchange={exchange}" in out, out[-1500:]          # no silent fallback to another exchange
+
+
+def test_second_device_in_one_process():
+    """One process driving two GPUs (not the deployment shape -- one process per GPU is -- but it must work):
+    per-device kernel attributes (> 48 KB dynamic shared memory), workspaces and streams follow the tensors' device,
+    not the current one.  LightpathGNN eval and a TopologicalGNN train step on cuda:1 while cuda:0 is current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from gnn_qot_estimation_b200 import LightpathGNN, TopologicalGNN, synthetic
+    torch.cuda.set_device(0)
+    outs = {}
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        torch.manual_seed(0)
+        m = LightpathGNN(5, 32, 3, is_lut_index=1, dropout_p=0.0).to(dev).eval()
+        b = synthetic.lightpath_store(200, seed=4).to(dev).collate(range(0, 200))
+        with torch.no_grad():
+            o, lb = m(b)
+        t = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev)
+        tb = synthetic.nsfnet_store(32, seed=1).to(dev).collate(range(0, 32))
+        loss = torch.nn.SmoothL1Loss()(t(tb), tb.y.view(-1, 3))
+        loss.backward()
+        outs[d] = (o.cpu(), lb.cpu(), loss.detach().cpu(), t.conv1.lin_query.weight.grad.cpu())
+        assert o.device == dev and torch.cuda.current_device() == 0
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)                               # same bits on both devices

@@ -157,15 +157,13 @@ def test_stress_graph_cfg5_full_size(cuda):
     eo, el, eg = _step(o64, _b64(hb), torch.float64)
     _, _, eg32 = _step(o32, hb)
     assert rel_err(out, eo) <= RTOL and rel_err(loss, el) <= RTOL
-    # KNOWN GAP, reported not absorbed: at full size six weight gradients that pass through the split-TF32 tensor-core
-    # GEMMs (qot_gemm_tf32x3 / qot_wgrad_tf32x3: three TF32 products per term, the lo*lo term dropped) sit at
-    # 1.0e-5 .. 1.6e-5 of their tensor's scale, where the fp32 oracle sits at ~1e-6.  Forward, loss and the other
-    # gradients meet 1e-5; these are held to 2e-5 and printed (DESIGN.md section 4.2 says what would close the gap).
+    # every gradient at 1e-5 of its tensor's scale, like the small configurations: the split-TF32 tensor-core GEMMs
+    # (qot_gemm_tf32x3 / qot_wgrad_tf32x3) keep their TMEM accumulation chains short and sum the chains in fp32
+    # registers (csrc/gemm_tc.cu; one long chain per reduction left six weight gradients at 1.0e-5 .. 2.2e-5)
     ours, ref32 = grad_errs(grads, eg, exact_zero=ZERO), grad_errs(eg32, eg, exact_zero=ZERO)
-    over = {k: (e, ref32[k]) for k, e in ours.items() if e > RTOL}
-    print("cfg5 full size: gradients over 1e-5 (ours, fp32 oracle):", over)
+    print("cfg5 full size: worst gradient (ours, fp32 oracle):", max(ours.values()), max(ref32.values()))
     for k, e in ours.items():
-        assert e <= 2e-5, (k, e, ref32[k])
+        assert e <= RTOL, (k, e, ref32[k])
 
 
 def test_deterministic_fwd_bwd(cuda):
