@@ -818,7 +818,7 @@ __device__ __forceinline__ void st_tmem_ld32(unsigned taddr, unsigned (&r)[32]) 
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-constexpr unsigned kTmemCols = 512;        // columns [0,128) A hi, [128,256) A lo, [256,352) three accumulators
+constexpr unsigned kTmemCols = 512;        // columns [0,128) A hi, [128,256) A lo, [256,416) five accumulators
 constexpr unsigned kTmemALo = 128, kTmemD = 256;
 
 __device__ __noinline__ void st_head_mma(int ngroups, int lane) {
@@ -830,19 +830,20 @@ __device__ __noinline__ void st_head_mma(int ngroups, int lane) {
     if (!st_wait<200>(st_smem_u32(&hs.aready), static_cast<unsigned>(g & 1))) break;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (lane == 0) {
-      // three accumulators, summed in fp32 by the epilogue: the tensor core adds into a running accumulator without
-      // round-to-nearest, so the large hi*hi terms go to two short chains (8 steps each) and the two compensation
-      // products (2^-11 of the magnitude) to a third
+      // five accumulators, summed in fp32 by the epilogue: the tensor core's add into a running accumulator truncates,
+      // an error that grows linearly with the chain (csrc/gemm_tc.cu, profiles/r2_tc_chain_accuracy.md), so the large
+      // hi*hi terms go to four short chains (4 steps = one 32-wide k-block each) and the two compensation products
+      // (2^-11 of the magnitude, their truncation does not matter) to a fifth
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {                   // hi*lo, lo*hi -> D2; hi*hi -> D0 (k < 64) / D1 (k >= 64)
+      for (int p = 0; p < 3; ++p) {                   // hi*lo, lo*hi -> D4; hi*hi of k-block kb -> D[kb]
         const unsigned a_col = (p == 1) ? kTmemALo : 0u;
         const unsigned b_base = (p == 0) ? b_lo : b_hi;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
           for (int s = 0; s < 4; ++s) {               // UMMA_K = 8 for tf32: 8 TMEM columns / 32 bytes of a swizzled row
-            const unsigned d_col = p < 2 ? kTmemD + 64u : (kb < 2 ? kTmemD : kTmemD + 32u);
-            const unsigned acc = p < 2 ? ((p | kb | s) != 0 ? 1u : 0u) : (((kb & 1) | s) != 0 ? 1u : 0u);
+            const unsigned d_col = p < 2 ? kTmemD + 128u : kTmemD + static_cast<unsigned>(kb * 32);
+            const unsigned acc = p < 2 ? ((p | kb | s) != 0 ? 1u : 0u) : (s != 0 ? 1u : 0u);
             st_umma_tf32_ts(tb + d_col, tb + a_col + static_cast<unsigned>(kb * 32 + s * 8),
                             st_umma_desc_sw128(b_base + static_cast<unsigned>(kb * 4096 + s * 32)), idesc, acc);
           }
@@ -919,6 +920,11 @@ __device__ __noinline__ void st_head_epilogue(int my_tiles, int ngroups, int eq,
       st_tmem_ld32(tb + kTmemD, r);
       st_tmem_ld32(tb + kTmemD + 32u, r1);
       st_tmem_ld32(tb + kTmemD + 64u, r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]));
+      st_tmem_ld32(tb + kTmemD + 96u, r1);
+      st_tmem_ld32(tb + kTmemD + 128u, r2);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]));
