@@ -504,11 +504,14 @@ nnconv_bwd_src_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
 // ===========================================================================
 constexpr int kPoolWarps = 4;
 constexpr int kMaxH = 256;
-constexpr int kPoolMaxSplit = 64;
+constexpr int kPoolMaxSplit = 2 * kNumSMs;
 
+// chunks per graph: enough blocks to fill the machine when there are few big graphs (a single 10k-node graph
+// spreads over 296 blocks of ~34 rows), one chunk per graph when there are many small ones
 static int pool_split(int64_t N, int64_t B) {
   const int64_t avg = B > 0 ? cdiv(N, B) : 0;
-  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(kPoolMaxSplit, cdiv(avg, 256))));
+  const int64_t fill = cdiv(static_cast<int64_t>(kPoolMaxSplit), std::max<int64_t>(B, 1));
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(fill, kPoolMaxSplit), cdiv(avg, 32))));
 }
 
 __device__ __forceinline__ void pool_chunk(const int64_t* __restrict__ gptr, int64_t g, int s, int S,
@@ -519,24 +522,44 @@ __device__ __forceinline__ void pool_chunk(const int64_t* __restrict__ gptr, int
   r1 = min(r0 + per, n1);
 }
 
-__global__ void __launch_bounds__(256)
-pool_partial_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int H, int S,
-                    float* __restrict__ partial) {
-  __shared__ float s_acc[256];
-  const int64_t g = blockIdx.x;
-  const int s = blockIdx.y;
-  const int c = threadIdx.x % H, rl = threadIdx.x / H, RL = 256 / H;
-  int64_t r0, r1;
-  pool_chunk(gptr, g, s, S, r0, r1);
-  float a = 0.f;
-  for (int64_t r = r0 + rl; r < r1; r += RL) a += x[r * H + c];
+// sum of rows [r0, r1) of a row-major [*, H] matrix by one 256-thread block, H % 4 == 0: thread = (row lane, channel
+// quad), 128-bit loads, row lanes combined through shared memory in a fixed order.  Result: s_out[0..H) (valid after
+// the trailing __syncthreads).  s_acc: 256 float4 of scratch.
+__device__ __forceinline__ void pool_block_rowsum(const float* __restrict__ x, int64_t r0, int64_t r1, int H,
+                                                  float4* s_acc, float* s_out) {
+  const int C4 = H >> 2, RL = 256 / C4;
+  const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int64_t r = r0 + rl; r < r1; r += RL) {
+    const float4 v = x4[r * C4 + c4];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
   s_acc[threadIdx.x] = a;
   __syncthreads();
   if (rl == 0) {
-    float t = 0.f;
-    for (int k = 0; k < RL; ++k) t += s_acc[k * H + c];
-    partial[(g * S + s) * H + c] = t;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < RL; ++k) {
+      const float4 v = s_acc[k * C4 + c4];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(s_out)[c4] = t;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+pool_partial_kernel(const float* __restrict__ x, const int64_t* __restrict__ gptr, int H, int S,
+                    float* __restrict__ partial) {
+  __shared__ float4 s_acc[256];
+  __shared__ __align__(16) float s_out[kMaxH];
+  const int64_t g = blockIdx.x;
+  const int s = blockIdx.y;
+  int64_t r0, r1;
+  pool_chunk(gptr, g, s, S, r0, r1);
+  pool_block_rowsum(x, r0, r1, H, s_acc, s_out);
+  if (threadIdx.x < H) partial[(g * S + s) * H + threadIdx.x] = s_out[threadIdx.x];
 }
 
 // Head, one graph per TPG threads (TPG = 32: a warp per graph for H <= 32; TPG = 256: a block per
@@ -550,13 +573,23 @@ pool_mlp_fwd_kernel(const float* __restrict__ partial, int S, const int64_t* __r
                     const float* __restrict__ hmask, float* __restrict__ pooled,
                     float* __restrict__ hid, float* __restrict__ out) {
   constexpr int GPB = (kPoolWarps * 32 < TPG ? TPG : kPoolWarps * 32) / TPG;   // graphs per block
-  __shared__ float s_p[GPB][kMaxH];
+  __shared__ __align__(16) float s_p[GPB][kMaxH];
   __shared__ float s_a[GPB][kMaxH];
+  __shared__ float4 s_acc[TPG == 256 ? 256 : 1];
   const int gl = threadIdx.x / TPG, t = threadIdx.x % TPG;
   const int lane = threadIdx.x & 31;
   const int64_t g = static_cast<int64_t>(blockIdx.x) * GPB + gl;
   const bool live = g < B;
-  if (live) {
+  if (TPG == 256) {                                    // one graph per block: all threads add the S partial rows
+    const int64_t n0 = gptr[g], n1 = gptr[g + 1];
+    const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
+    pool_block_rowsum(partial + g * S * H, 0, S, H, s_acc, s_p[0]);
+    for (int c = t; c < H; c += TPG) {
+      const float a = s_p[0][c] * inv;
+      s_p[0][c] = a;
+      if (pooled) pooled[g * H + c] = a;
+    }
+  } else if (live) {
     const int64_t n0 = gptr[g], n1 = gptr[g + 1];
     const float inv = 1.0f / static_cast<float>(max(n1 - n0, static_cast<int64_t>(1)));
     for (int c = t; c < H; c += TPG) {
@@ -578,18 +611,41 @@ pool_mlp_fwd_kernel(const float* __restrict__ partial, int S, const int64_t* __r
         if (hmask) act *= hmask[g * H + u];
         s_a[gl][u] = act;
       }
-    } else {                                           // warp w owns units w, w+8, ...; lanes stride the row
-      const int w = t >> 5;
-      for (int u = w; u < H; u += TPG / 32) {
-        float part = 0.f;
-        for (int c = lane; c < H; c += 32) part = fmaf(W1[u * H + c], s_p[gl][c], part);
-        part = warp_sum(part);
-        if (lane == 0) {
-          const float hv = part + b1[u];
-          if (hid) hid[g * H + u] = hv;
-          float act = leaky(hv, 0.01f);
-          if (hmask) act *= hmask[g * H + u];
-          s_a[gl][u] = act;
+    } else {                                           // warp w owns units w, w+8, ...; lanes stride the row with
+      const int w = t >> 5;                            // 128-bit loads; eight units per round, all their weight-row
+      constexpr int NW = TPG / 32, UPR = 8;            // loads issued before the first is used (H >= 64: H / NW >= 8)
+      const float4* W4 = reinterpret_cast<const float4*>(W1);
+      const float4* p4 = reinterpret_cast<const float4*>(s_p[gl]);
+      const int C4 = H >> 2;
+      for (int u0 = w; u0 < H; u0 += UPR * NW) {
+        float4 wv[UPR][2];
+#pragma unroll
+        for (int q = 0; q < UPR; ++q)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c4 = lane + 32 * i;
+            wv[q][i] = c4 < C4 ? W4[static_cast<int64_t>(u0 + q * NW) * C4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        float4 pv[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) pv[i] = lane + 32 * i < C4 ? p4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < UPR; ++q) {
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            part = fmaf(wv[q][i].x, pv[i].x, part); part = fmaf(wv[q][i].y, pv[i].y, part);
+            part = fmaf(wv[q][i].z, pv[i].z, part); part = fmaf(wv[q][i].w, pv[i].w, part);
+          }
+          const float sum = warp_sum(part);
+          const int u = u0 + q * NW;
+          if (lane == 0) {
+            const float hv = sum + b1[u];
+            if (hid) hid[g * H + u] = hv;
+            float act = leaky(hv, 0.01f);
+            if (hmask) act *= hmask[g * H + u];
+            s_a[gl][u] = act;
+          }
         }
       }
     }
@@ -668,6 +724,17 @@ __global__ void pool_mean_final_kernel(const float* __restrict__ partial, int S,
   float a = 0.f;
   for (int s = 0; s < S; ++s) a += partial[(g * S + s) * H + c];
   pooled[i] = a / static_cast<float>(max(gptr[g + 1] - gptr[g], static_cast<int64_t>(1)));
+}
+// the same with one block per graph (few big graphs: S is large, the serial loop above would be latency-bound)
+__global__ void __launch_bounds__(256)
+pool_mean_final_block_kernel(const float* __restrict__ partial, int S, const int64_t* __restrict__ gptr, int H,
+                             float* __restrict__ pooled) {
+  __shared__ float4 s_acc[256];
+  __shared__ __align__(16) float s_out[kMaxH];
+  const int64_t g = blockIdx.x;
+  pool_block_rowsum(partial + g * S * H, 0, S, H, s_acc, s_out);
+  if (threadIdx.x < H)
+    pooled[g * H + threadIdx.x] = s_out[threadIdx.x] / static_cast<float>(max(gptr[g + 1] - gptr[g], static_cast<int64_t>(1)));
 }
 __global__ void pool_scale_kernel(const float* __restrict__ dpooled, const int64_t* __restrict__ gptr, int64_t B,
                                   int H, float* __restrict__ dscaled) {
@@ -836,6 +903,8 @@ extern "C" int qot_pool_mlp_fwd(const float* x, const int64_t* gptr, int64_t N, 
   QOT_REQUIRE(gptr && W1 && b1 && W2 && b2 && out && (N == 0 || x), "qot_pool_mlp_fwd: null argument");
   QOT_REQUIRE(ws && ws_bytes >= qot_pool_mlp_fwd_workspace_bytes(N, B, H), "qot_pool_mlp_fwd: workspace too small");
   QOT_REQUIRE(B <= 0x7fffffffll, "qot_pool_mlp_fwd: too many graphs for one launch");
+  QOT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W1)) & 15) == 0,
+              "qot_pool_mlp_fwd: x and W1 must be 16-byte aligned (128-bit loads)");
   const int S = pool_split(N, B);
   float* partial = static_cast<float*>(ws);
   pool_partial_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(x, gptr, static_cast<int>(H), S, partial);
@@ -908,11 +977,15 @@ extern "C" int qot_mean_pool_fwd(const float* x, const int64_t* gptr, int64_t N,
   QOT_REQUIRE(gptr && pooled && (N == 0 || x), "qot_mean_pool_fwd: null argument");
   QOT_REQUIRE(ws && ws_bytes >= qot_mean_pool_workspace_bytes(N, B, H), "qot_mean_pool_fwd: workspace too small");
   QOT_REQUIRE(B <= 0x7fffffffll, "qot_mean_pool_fwd: too many graphs for one launch");
+  QOT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "qot_mean_pool_fwd: x must be 16-byte aligned (128-bit loads)");
   const int S = pool_split(N, B);
   float* partial = static_cast<float*>(ws);
   pool_partial_kernel<<<dim3(static_cast<unsigned>(B), S), 256, 0, stream>>>(x, gptr, static_cast<int>(H), S, partial);
   QOT_LAUNCH_CHECK();
-  pool_mean_final_kernel<<<static_cast<unsigned>(cdiv(B * H, 256)), 256, 0, stream>>>(partial, S, gptr, B, static_cast<int>(H), pooled);
+  if (S > 8)
+    pool_mean_final_block_kernel<<<static_cast<unsigned>(B), 256, 0, stream>>>(partial, S, gptr, static_cast<int>(H), pooled);
+  else
+    pool_mean_final_kernel<<<static_cast<unsigned>(cdiv(B * H, 256)), 256, 0, stream>>>(partial, S, gptr, B, static_cast<int>(H), pooled);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }

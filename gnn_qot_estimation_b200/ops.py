@@ -8,6 +8,7 @@ torch only allocates the tensors.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Sequence, NamedTuple, Optional
 
 import torch
@@ -739,12 +740,35 @@ class _TConvEdgeFn(torch.autograd.Function):
         return dqkvs, None, dWe, None, None
 
 
+_derived_cache = {}
+
+
+def _derived(tag: str, srcs, make):
+    """A tensor that depends on parameters only (concatenated / re-laid-out weights).  While autograd records, it is
+    rebuilt every call (autograd routes its gradient back to the parameters); otherwise -- eval under no_grad, the
+    serving case -- it is cached: keyed by the sources' storage, shape and version counter (optimizer steps,
+    load_state_dict and .to() all change one of them) and validated against weak references to the source tensors,
+    so a recycled address never aliases an old entry."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in srcs):
+        return make()
+    key = (tag,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+    hit = _derived_cache.get(key)
+    if hit is not None and all(r() is t for r, t in zip(hit[0], srcs)):
+        return hit[1]
+    if len(_derived_cache) >= 64:
+        _derived_cache.clear()
+    with torch.no_grad():
+        val = make()
+    _derived_cache[key] = (tuple(weakref.ref(t) for t in srcs), val)
+    return val
+
+
 def transformer_conv(x, node_ids, graph: GraphIndex, edge_attr, Wq, bq, Wk, bk, Wv, bv, We, Ws, bs,
                      slope: float = 1.0):
     """TransformerConv (+ fused embedding lookup when ``node_ids`` is given and ``x`` is
     the embedding table; + fused leaky_relu when slope != 1)."""
-    Wcat = torch.cat([Wq, Wk, Wv, Ws], dim=0)          # [4H,H]; autograd splits the gradient
-    bcat = torch.cat([bq, bk, bv, bs], dim=0)
+    Wcat = _derived("tconv.W", (Wq, Wk, Wv, Ws), lambda: torch.cat([Wq, Wk, Wv, Ws], dim=0))   # [4H,H]; autograd splits the gradient
+    bcat = _derived("tconv.b", (bq, bk, bv, bs), lambda: torch.cat([bq, bk, bv, bs], dim=0))
     qkvs = node_linear(x, Wcat, bcat, ids=node_ids)
     return _TConvEdgeFn.apply(qkvs, edge_attr, We, graph, slope)
 
@@ -794,8 +818,9 @@ def nnconv_mean(x, graph: GraphIndex, edge_attr, W1, b1, W2, b2, Wroot, bias, sl
     K = EDGE_HID
     # Pcat[i, k*H+o] = W2[i*H+o, k];  slab K: b2[i*H+o];  slab K+1: Wroot[o,i]   (tensor
     # reshuffles only -- autograd routes dPcat back to W2 / b2 / Wroot)
-    Pcat = torch.cat([W2.view(H, H, K).permute(0, 2, 1).reshape(H, K * H), b2.view(H, H), Wroot.t()], dim=1)
-    yr = node_linear(x, Pcat.t().contiguous(), None)      # W argument is [out,in]
+    PcatT = _derived("nnconv.P", (W2, b2, Wroot), lambda: torch.cat(
+        [W2.view(H, H, K).permute(0, 2, 1).reshape(H, K * H), b2.view(H, H), Wroot.t()], dim=1).t().contiguous())
+    yr = node_linear(x, PcatT, None)                      # W argument is [out,in]
     return _NNConvEdgeFn.apply(yr, edge_attr, W1, b1, bias, graph, slope)
 
 

@@ -211,3 +211,30 @@ def test_verify_layout_accepts_from_networkx_order_and_rejects_violations():
     d = st.edge_dst.clone()
     d[e0] = 1000
     assert not clone(edge_dst=d).verify_layout()
+
+
+def test_derived_weight_cache_follows_parameter_updates():
+    """ops._derived: re-laid-out weights are cached only while autograd is not recording, and an in-place update of a
+    source (optimizer step, load_state_dict) or a new tensor at a recycled address invalidates the entry."""
+    from gnn_qot_estimation_b200 import ops
+    a, b = torch.nn.Parameter(torch.ones(2, 3)), torch.nn.Parameter(torch.zeros(2, 3))
+    calls = []
+
+    def make():
+        calls.append(1)
+        return torch.cat([a, b], dim=0)
+
+    with torch.no_grad():
+        c1 = ops._derived("t", (a, b), make)
+        c2 = ops._derived("t", (a, b), make)
+    assert c1 is c2 and len(calls) == 1 and not c1.requires_grad
+    c3 = ops._derived("t", (a, b), make)                      # autograd recording: rebuilt, differentiable
+    assert len(calls) == 2 and c3.requires_grad
+    with torch.no_grad():
+        a.add_(1.0)                                           # what optimizer.step() does
+        c4 = ops._derived("t", (a, b), make)
+    assert len(calls) == 3 and float(c4[0, 0]) == 2.0
+    a.requires_grad_(False); b.requires_grad_(False)
+    c5 = ops._derived("t", (a, b), make)                      # frozen weights: cached even with grad mode on
+    c6 = ops._derived("t", (a, b), make)
+    assert c5 is c6
