@@ -182,11 +182,36 @@ __device__ __forceinline__ void cp_async_tile(const float* __restrict__ src, int
   }
 }
 
+// One tile of the launch: output block (m0, n0) and, for split-K, the k-block slice [kb0, kb0 + nkb) and the
+// partial output it is written to.  Tiles are numbered n-block fastest, so the CTAs working side by side share a few
+// row blocks of A and all of W in L2.
+struct TcTile {
+  int64_t m0, n0, kb0, nkb;
+  float* C;
+};
+__device__ __forceinline__ TcTile tc_tile(int64_t t, int64_t tiles_m, int64_t tiles_n, int64_t kb_total,
+                                          int64_t kb_per_split, int64_t splits, float* C, int64_t M, int64_t Nc) {
+  TcTile ti;
+  const int64_t z = t / (tiles_m * tiles_n), r = t % (tiles_m * tiles_n);
+  ti.m0 = (r / tiles_n) * TC_BM;
+  ti.n0 = (r % tiles_n) * TC_BN;
+  ti.kb0 = z * kb_per_split;
+  ti.nkb = max(static_cast<int64_t>(0), min(kb_total - ti.kb0, kb_per_split));
+  ti.C = splits > 1 ? C + z * M * Nc : C;
+  return ti;
+}
+
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...  Two warpgroups:
+//   warps 0-3  load + MMA: cp.async the operand tiles of k-block after k-block through the three stages -- straight
+//              across tile boundaries, so the next tile's first blocks are in flight while this tile's last MMAs run
+//              -- and thread 0 issues the MMAs;
+//   warps 4-7  drain + epilogue: add each finished TMEM chain into registers, write the tile when its last chain is
+//              in, while the other warpgroup is already loading / multiplying the next tile.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    const float* __restrict__ Whi, const float* __restrict__ Wlo,
                    const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M,
-                   int64_t Nc, int64_t K, int64_t kb_per_split, int32_t* __restrict__ status) {
+                   int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits, int32_t* __restrict__ status) {
   extern __shared__ char tc_smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -194,7 +219,9 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   unsigned long long* chain_free = chain_full + 2;                // [2] drain warps -> MMA thread: accumulator read out
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * TC_BM, n0 = static_cast<int64_t>(blockIdx.y) * TC_BN;
+  const int64_t tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (Nc + TC_BN - 1) / TC_BN, kb_total = K / TC_BK;
+  const int64_t ntiles = tiles_m * tiles_n * splits;
+  auto tile = [&](int64_t t) { return tc_tile(t, tiles_m, tiles_n, kb_total, kb_per_split, splits, C, M, Nc); };
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -216,130 +243,146 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = *tmem_slot;
   constexpr unsigned idesc = tc_idesc(TC_BM, TC_BN);
-
-  // split-K (weight gradients: few output tiles, long reduction): slice z owns k-blocks
-  // [kb0, kb0 + nkb) and writes its own partial tile set C + z*M*Nc (ldc == Nc), summed afterwards
-  const int64_t kb0 = static_cast<int64_t>(blockIdx.z) * kb_per_split;
-  const int64_t nkb = max(static_cast<int64_t>(0), min(K / TC_BK - kb0, kb_per_split));
-  if (gridDim.z > 1) C += static_cast<int64_t>(blockIdx.z) * M * Nc;
   bool ok = true;
 
   // Accumulation happens in two places.  The tensor core adds into TMEM with truncation, so the error of a chain of
   // MMAs on one accumulator grows LINEARLY with its length (profiles/r2_tc_chain_accuracy.md: max error / max|C| of
   // [10000,256]x[256,1024] is 3.1e-7, 5.5e-7, 1.1e-6, 2.5e-6 for chains of 1, 2, 4, 8 k-blocks; a weight gradient
   // reduced over 80 000 rows in one chain per split-K slice sat at 9e-6, torch's fp32 GEMM at 8e-7).  So a TMEM
-  // accumulator only ever holds a CHAIN of TC_CHAIN k-blocks (2: 24 MMAs).  Two accumulators alternate; a second
-  // warpgroup (warps 4-7, TMEM lane quarter = warp % 4) reads each finished chain with tcgen05.ld and adds it,
-  // round-to-nearest, into fp32 registers (128 per thread: its row of the tile) while the load/MMA warpgroup runs
-  // ahead -- the drain is off the load -> MMA -> refill critical path.
+  // accumulator only ever holds a CHAIN of TC_CHAIN k-blocks (2: 24 MMAs).  Two accumulators alternate (chains are
+  // numbered through the whole tile sequence of the CTA); the drain warpgroup (TMEM lane quarter = warp % 4) reads
+  // each finished chain with tcgen05.ld and adds it, round-to-nearest, into fp32 registers (128 per thread: its row of
+  // the tile), off the load -> MMA -> refill critical path.
   if (warp < 4) {
     // ================= load + MMA warpgroup =================
-    auto issue_loads = [&](int64_t kb) {
-      char* base = smem + static_cast<int>(kb % TC_STAGES) * TC_STAGE_BYTES;
-      const int64_t k0 = (kb0 + kb) * TC_BK;
-      cp_async_tile(Ahi, K, m0, M, k0, base, tid);
-      cp_async_tile(Alo, K, m0, M, k0, base + TC_TILE_BYTES, tid);
-      cp_async_tile(Whi, K, n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
-      cp_async_tile(Wlo, K, n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
+    int64_t lt = blockIdx.x, lkb = 0;                                  // load cursor: next (tile, k-block) to fetch
+    TcTile lti = lt < ntiles ? tile(lt) : TcTile{0, 0, 0, 0, nullptr};
+    auto settle = [&]() {                                              // skip exhausted / empty tiles
+      while (lt < ntiles && lkb >= lti.nkb) {
+        lt += gridDim.x;
+        lkb = 0;
+        if (lt < ntiles) lti = tile(lt);
+      }
     };
-    for (int64_t kb = 0; kb < TC_STAGES - 1; ++kb) {                  // prologue: STAGES-1 blocks in flight
-      if (kb < nkb) issue_loads(kb);
+    int64_t gl = 0;                                                    // blocks fetched so far (stage = gl % STAGES)
+    auto fetch = [&]() {
+      char* base = smem + static_cast<int>(gl % TC_STAGES) * TC_STAGE_BYTES;
+      const int64_t k0 = (lti.kb0 + lkb) * TC_BK;
+      cp_async_tile(Ahi, K, lti.m0, M, k0, base, tid);
+      cp_async_tile(Alo, K, lti.m0, M, k0, base + TC_TILE_BYTES, tid);
+      cp_async_tile(Whi, K, lti.n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
+      cp_async_tile(Wlo, K, lti.n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
+      ++gl; ++lkb;
+    };
+    settle();
+    for (int i = 0; i < TC_STAGES - 1; ++i) {                          // prologue: STAGES-1 blocks in flight
+      if (lt < ntiles) { fetch(); settle(); }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int64_t kb = 0; kb < nkb; ++kb) {
-      const int st = static_cast<int>(kb % TC_STAGES);
-      asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block kb landed
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
-      asm volatile("bar.sync 1, 128;" ::: "memory");                   // ... and everybody else's (this warpgroup only)
-      if (tid == 0) {
-        const int64_t c = kb / TC_CHAIN;                               // chain of this block, accumulator c & 1
-        if (kb % TC_CHAIN == 0 && c >= 2)                              // chain c-2 must have been read out
-          ok &= mbar_wait(smem_u32(chain_free + (c & 1)), static_cast<unsigned>(((c >> 1) - 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
-        const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
-        const unsigned d = tmem_d + static_cast<unsigned>((c & 1) * TC_BN);
-        const bool fresh = kb % TC_CHAIN == 0;                         // first block of a chain overwrites
+    int64_t gk = 0, gc = 0;                                            // blocks multiplied / chains started so far
+    for (int64_t mt = blockIdx.x; mt < ntiles; mt += gridDim.x) {
+      const TcTile ti = tile(mt);
+      for (int64_t kb = 0; kb < ti.nkb; ++kb, ++gk) {
+        const int st = static_cast<int>(gk % TC_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block gk landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
+        asm volatile("bar.sync 1, 128;" ::: "memory");                   // ... and everybody else's (this warpgroup only)
+        if (tid == 0) {
+          const int64_t c = gc + kb / TC_CHAIN;                          // chain of this block, accumulator c & 1
+          if (kb % TC_CHAIN == 0 && c >= 2)                              // chain c-2 must have been read out
+            ok &= mbar_wait(smem_u32(chain_free + (c & 1)), static_cast<unsigned>(((c >> 1) - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+          const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+          const unsigned d = tmem_d + static_cast<unsigned>((c & 1) * TC_BN);
+          const bool fresh = kb % TC_CHAIN == 0;                         // first block of a chain overwrites
 #pragma unroll
-        for (int s = 0; s < TC_BK / 8; ++s) {                          // UMMA_K = 8 for tf32: 32 bytes per step
-          const unsigned ko = s * 32;
-          umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, !(fresh && s == 0));
-          umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-          umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-        }
-        // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(bars + st))
-                     : "memory");
-        if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == nkb - 1)           // ... and on the chain barrier: accumulator complete
+          for (int s = 0; s < TC_BK / 8; ++s) {                          // UMMA_K = 8 for tf32: 32 bytes per step
+            const unsigned ko = s * 32;
+            umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, !(fresh && s == 0));
+            umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+            umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+          }
+          // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(chain_full + (c & 1)))
+                           smem_u32(bars + st))
                        : "memory");
+          if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == ti.nkb - 1)        // ... and on the chain barrier: accumulator complete
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(chain_full + (c & 1)))
+                         : "memory");
+        }
+        // refill the stage block gk-1 used, with the next block of the CTA's sequence (possibly the next tile's).  Its
+        // MMAs are waited for only now, with the MMAs of block gk already queued behind them, so the tensor pipe never
+        // drains.
+        if (lt < ntiles) {
+          if (gk >= 1)
+            ok &= mbar_wait(smem_u32(bars + static_cast<int>((gk - 1) % TC_STAGES)),
+                            static_cast<unsigned>(((gk - 1) / TC_STAGES) & 1));
+          fetch();
+          settle();
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      // refill the stage block kb-1 used, for block kb+STAGES-1.  Its MMAs are waited for only now, with
-      // the MMAs of block kb already queued behind them, so the tensor pipe never drains.
-      const int64_t nxt = kb + TC_STAGES - 1;
-      if (nxt < nkb) {
-        if (kb >= 1)
-          ok &= mbar_wait(smem_u32(bars + static_cast<int>((kb - 1) % TC_STAGES)),
-                          static_cast<unsigned>(((kb - 1) / TC_STAGES) & 1));
-        issue_loads(nxt);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      gc += (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
     }
   } else {
     // ================= drain + epilogue warpgroup =================
     const int q = warp - 4;                                            // TMEM lanes [32q, 32q+32) = tile rows
-    float acc[TC_BN];
+    int64_t gc = 0;
+    for (int64_t mt = blockIdx.x; mt < ntiles; mt += gridDim.x) {
+      const TcTile ti = tile(mt);
+      float acc[TC_BN];
 #pragma unroll
-    for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-    const int64_t nchains = (nkb + TC_CHAIN - 1) / TC_CHAIN;
-    for (int64_t c = 0; c < nchains; ++c) {
-      ok &= mbar_wait_parked(smem_u32(chain_full + (c & 1)), static_cast<unsigned>((c >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>((c & 1) * TC_BN);
+      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+      const int64_t nchains = (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
+      for (int64_t cc = 0; cc < nchains; ++cc, ++gc) {
+        ok &= mbar_wait_parked(smem_u32(chain_full + (gc & 1)), static_cast<unsigned>((gc >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>((gc & 1) * TC_BN);
 #pragma unroll
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-        unsigned r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(base + static_cast<unsigned>(c0))
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          unsigned r[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(base + static_cast<unsigned>(c0))
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + (gc & 1))) : "memory");
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + (c & 1))) : "memory");
-    }
-    // ---- epilogue: thread = tile row, its 128 columns are in registers (an empty k-slice writes zeros)
-    const int64_t row = m0 + q * 32 + lane;
-    if (row < M) {
+      // ---- epilogue: thread = tile row, its 128 columns are in registers (an empty k-slice writes zeros)
+      const int64_t row = ti.m0 + q * 32 + lane;
+      if (row < M) {
 #pragma unroll
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-        float* crow = C + row * ldc + n0 + c0;
-        if (n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          float* crow = ti.C + row * ldc + ti.n0 + c0;
+          if (ti.n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
-            if (bias) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+              if (bias) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + ti.n0 + c0 + j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              *reinterpret_cast<float4*>(crow + j) = o;
             }
-            *reinterpret_cast<float4*>(crow + j) = o;
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < Nc) crow[j] = acc[c0 + j] + (bias ? bias[n0 + c0 + j] : 0.f);
+            for (int j = 0; j < 32; ++j)
+              if (ti.n0 + c0 + j < Nc) crow[j] = acc[c0 + j] + (bias ? bias[ti.n0 + c0 + j] : 0.f);
+          }
         }
       }
     }
@@ -398,10 +441,10 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_LAUNCH_CHECK();
   split_tf32_kernel<<<static_cast<unsigned>(cdiv(Nc, 32)), 256, 0, stream>>>(W, ldw, nullptr, Nc, K, w_hi, w_lo);
   QOT_LAUNCH_CHECK();
-  dim3 grid(static_cast<unsigned>(cdiv(M, TC_BM)), static_cast<unsigned>(cdiv(Nc, TC_BN)));
-  QOT_REQUIRE(grid.y <= 65535u, "qot_gemm_tf32x3: Nc too large for one launch");
+  const int64_t ntiles = cdiv(M, TC_BM) * cdiv(Nc, TC_BN);
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(ntiles, kNumSMs));      // persistent: one CTA per SM
   gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K,
-                                                            K / TC_BK, status);
+                                                                  K / TC_BK, 1, status);
   QOT_LAUNCH_CHECK();
   return QOT_OK;
 }
@@ -412,7 +455,8 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
 // cut into split-K slices so the few output tiles still fill the machine, and the slices are summed in a fixed
 // order -- deterministic.
 static int tc_wgrad_splits(int64_t tiles, int64_t nkb) {
-  const int64_t want = std::max<int64_t>(1, (2 * kNumSMs) / std::max<int64_t>(tiles, 1));
+  // persistent kernel, one CTA per SM: as many slices as give every SM one (tile, slice) -- one even wave
+  const int64_t want = std::max<int64_t>(1, kNumSMs / std::max<int64_t>(tiles, 1));
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, nkb / 4 + 1), 64)));
 }
 static int64_t tc_rpad(int64_t R) { return cdiv(R, TC_BK) * TC_BK; }
@@ -450,13 +494,13 @@ extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int
   QOT_LAUNCH_CHECK();
   split_tf32_transpose_kernel<<<gb, 256, 0, stream>>>(B, ldb, gather_b, R, No, rp, bt_hi, bt_lo);
   QOT_LAUNCH_CHECK();
-  dim3 grid(static_cast<unsigned>(cdiv(Mo, TC_BM)), static_cast<unsigned>(cdiv(No, TC_BN)), static_cast<unsigned>(splits));
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles * splits, kNumSMs));
   if (splits == 1) {
-    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, status);
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, 1, status);
     QOT_LAUNCH_CHECK();
     return QOT_OK;
   }
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, status);
+  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, splits, status);
   QOT_LAUNCH_CHECK();
   const int64_t n = Mo * No;
   tc_reduce_splits_kernel<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, stream>>>(part, n, splits, C, No, ldc);
