@@ -25,14 +25,14 @@ namespace qot {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 256;                               // warps 0-3: loads + MMA issue, warps 4-7: drain + epilogue
+constexpr int TC_THREADS = 192;                               // warp 0: bulk-copy producer, 1: MMA issue, 2-5: drain + epilogue
 #ifndef QOT_TC_CHAIN
 #define QOT_TC_CHAIN 2
 #endif
 constexpr int64_t TC_CHAIN = QOT_TC_CHAIN;                     // k-blocks per TMEM accumulation chain (see the main loop)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128;   // + barriers, TMEM slot
 constexpr unsigned TC_SPIN_LIMIT = 1u << 26;                // a wedged barrier ends the kernel, never hangs it
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -97,13 +97,24 @@ __device__ __forceinline__ bool mbar_wait_parked(unsigned bar, unsigned parity) 
   return false;
 }
 
-// hi = tf32(v), lo = tf32(v - hi) of rows [0, rows) of `src` (optional gather), K columns.
+// ---- operand images.  The pre-pass writes the hi / lo halves of an operand as a sequence of TILES: tile (rb, kb)
+// holds rows [128 rb, 128 rb + 128) x columns [32 kb, 32 kb + 32) as 16 KB in exactly the shared-memory image the
+// UMMA descriptor names (row r at r * 128 B, its 16-byte chunk j stored at chunk j ^ (r & 7): SWIZZLE_128B), tiles
+// ordered kb fastest.  The GEMM then fetches a tile with ONE bulk copy (cp.async.bulk, UBLKCP) -- no per-thread
+// address arithmetic, no tensor map.  Rows past the matrix edge are written as zeros (the image is padded to 128 rows).
+__device__ __forceinline__ int64_t tc_img_offset(int64_t r, int64_t chunk /* 16-byte chunk index along K */, int64_t KB) {
+  const int64_t rb = r >> 7, rr = r & 127, kb = chunk >> 3, j = chunk & 7;
+  return ((rb * KB + kb) * TC_BM + rr) * TC_BK + ((j ^ (rr & 7)) << 2);
+}
+
+// hi = tf32(v), lo = tf32(v - hi) of rows [0, rows) of `src` (optional gather), K columns; rows [rows, rows_pad) zero.
 // One warp per row per pass, four rows in flight per warp (independent 128-bit loads).
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ gather,
-                  int64_t rows, int64_t K, float* __restrict__ hi, float* __restrict__ lo) {
+                  int64_t rows, int64_t rows_pad, int64_t K, float* __restrict__ hi, float* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int kv = static_cast<int>(K / 4);
+  const int64_t KB = K / TC_BK;
   const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * 4;
   for (int c = lane; c < kv; c += 32) {
     float4 v[4];
@@ -116,26 +127,29 @@ split_tf32_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __re
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t r = r0 + i;
-      if (r < rows) {
+      if (r < rows_pad) {
         float4 h, l;
         h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
         l.x = to_tf32(v[i].x - h.x); l.y = to_tf32(v[i].y - h.y); l.z = to_tf32(v[i].z - h.z); l.w = to_tf32(v[i].w - h.w);
-        *reinterpret_cast<float4*>(hi + r * K + c * 4) = h;
-        *reinterpret_cast<float4*>(lo + r * K + c * 4) = l;
+        const int64_t o = tc_img_offset(r, c, KB);
+        *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = l;
       }
     }
   }
 }
 
-// Transposing variant for weight gradients: src [R, Cc] (optional row gather) -> hi / lo [Cc, Rpad],
-// i.e. the reduction dimension R becomes the contiguous (K-major) one; columns r in [R, Rpad) are zero.
+// Transposing variant for weight gradients: src [R, Cc] (optional row gather) -> images of the [Cc, Rpad] matrix,
+// i.e. the reduction dimension R becomes the contiguous (K-major) one; entries with r >= R or c >= Cc are zero
+// (Cpad = Cc rounded up to 128 rows, Rpad to 32 columns).
 __global__ void __launch_bounds__(256)
 split_tf32_transpose_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ gather,
-                            int64_t R, int64_t Cc, int64_t Rpad, float* __restrict__ hi,
+                            int64_t R, int64_t Cc, int64_t Rpad, int64_t Cpad, float* __restrict__ hi,
                             float* __restrict__ lo) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int64_t KB = Rpad / TC_BK;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
@@ -147,11 +161,12 @@ split_tf32_transpose_kernel(const float* __restrict__ src, int64_t ld, const int
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
-    if (c < Cc && r < Rpad) {
+    if (c < Cpad && r < Rpad) {
       const float v = tile[tx][ty + 8 * i];
       const float h = to_tf32(v);
-      hi[c * Rpad + r] = h;
-      lo[c * Rpad + r] = to_tf32(v - h);
+      const int64_t o = tc_img_offset(c, r >> 2, KB) + (r & 3);
+      hi[o] = h;
+      lo[o] = to_tf32(v - h);
     }
   }
 }
@@ -163,23 +178,6 @@ __global__ void tc_reduce_splits_kernel(const float* __restrict__ part, int64_t 
   float a = 0.f;
   for (int z = 0; z < splits; ++z) a += part[static_cast<int64_t>(z) * n + i];
   out[(i / ncols) * ld_out + (i % ncols)] = a;
-}
-
-// rows [r0, r0+128) x k [k0, k0+32) of a dense [nrows, K] matrix -> one swizzled shared tile with cp.async:
-// row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7); rows past nrows are zero-filled
-__device__ __forceinline__ void cp_async_tile(const float* __restrict__ src, int64_t K, int64_t r0,
-                                              int64_t nrows, int64_t k0, char* tile, int tid) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = tid + it * 128;                 // 1024 chunks of 16 bytes
-    const int r = idx >> 3, c = idx & 7;
-    const int64_t gr = r0 + r;
-    const bool in = gr < nrows;
-    const float* g = src + (in ? gr : 0) * K + k0 + c * 4;
-    const unsigned dst = smem_u32(tile + r * 128 + ((c ^ (r & 7)) << 4));
-    const unsigned bytes = in ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(bytes) : "memory");
-  }
 }
 
 // One tile of the launch: output block (m0, n0) and, for split-K, the k-block slice [kb0, kb0 + nkb) and the
@@ -201,12 +199,14 @@ __device__ __forceinline__ TcTile tc_tile(int64_t t, int64_t tiles_m, int64_t ti
   return ti;
 }
 
-// Persistent: CTA b works on tiles b, b + gridDim.x, ...  Two warpgroups:
-//   warps 0-3  load + MMA: cp.async the operand tiles of k-block after k-block through the three stages -- straight
-//              across tile boundaries, so the next tile's first blocks are in flight while this tile's last MMAs run
-//              -- and thread 0 issues the MMAs;
-//   warps 4-7  drain + epilogue: add each finished TMEM chain into registers, write the tile when its last chain is
-//              in, while the other warpgroup is already loading / multiplying the next tile.
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...  Warp roles:
+//   warp 0 (one lane)  producer: per k-block four bulk copies (A_hi, A_lo, W_hi, W_lo tiles, 16 KB each) into one of
+//                      three 64 KB stages, completing on the stage's `full` mbarrier -- straight across tile
+//                      boundaries, so the next tile's first blocks are in flight while this tile's last MMAs run;
+//   warp 1 (one lane)  MMA issue: waits `full`, issues the 12 tcgen05.mma of the block, commits them to the stage's
+//                      `empty` barrier (and, at the end of a chain, to the chain barrier);
+//   warps 2-5          drain + epilogue (TMEM lane quarter = warp % 4): add each finished TMEM chain into registers,
+//                      write the tile when its last chain is in, while the next tile is already being multiplied.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    const float* __restrict__ Whi, const float* __restrict__ Wlo,
@@ -214,8 +214,9 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits, int32_t* __restrict__ status) {
   extern __shared__ char tc_smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  unsigned long long* chain_full = bars + TC_STAGES;              // [2] MMA thread -> drain warps: chain finished
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  unsigned long long* empty = full + TC_STAGES;                   // [STAGES] MMAs that read the stage have finished
+  unsigned long long* chain_full = empty + TC_STAGES;             // [2] MMA thread -> drain warps: chain finished
   unsigned long long* chain_free = chain_full + 2;                // [2] drain warps -> MMA thread: accumulator read out
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -230,8 +231,10 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(empty + s)) : "memory");
+    }
     for (int s = 0; s < 2; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(chain_full + s)) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(chain_free + s)) : "memory");
@@ -253,82 +256,71 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   // numbered through the whole tile sequence of the CTA); the drain warpgroup (TMEM lane quarter = warp % 4) reads
   // each finished chain with tcgen05.ld and adds it, round-to-nearest, into fp32 registers (128 per thread: its row of
   // the tile), off the load -> MMA -> refill critical path.
-  if (warp < 4) {
-    // ================= load + MMA warpgroup =================
-    int64_t lt = blockIdx.x, lkb = 0;                                  // load cursor: next (tile, k-block) to fetch
-    TcTile lti = lt < ntiles ? tile(lt) : TcTile{0, 0, 0, 0, nullptr};
-    auto settle = [&]() {                                              // skip exhausted / empty tiles
-      while (lt < ntiles && lkb >= lti.nkb) {
-        lt += gridDim.x;
-        lkb = 0;
-        if (lt < ntiles) lti = tile(lt);
+  if (warp == 0) {
+    // ================= producer =================
+    if (lane == 0) {
+      const int64_t KB = kb_total;
+      int64_t g = 0;                                                   // blocks fetched so far (stage = g % STAGES)
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TcTile ti = tile(t);
+        const int64_t mb = ti.m0 / TC_BM, nb = ti.n0 / TC_BN;
+        for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
+          const int st = static_cast<int>(g % TC_STAGES);
+          if (g >= TC_STAGES)
+            ok &= mbar_wait(smem_u32(empty + st), static_cast<unsigned>(((g / TC_STAGES) - 1) & 1));
+          const unsigned fb = smem_u32(full + st);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(TC_STAGE_BYTES) : "memory");
+          const unsigned dst = smem_u32(smem + st * TC_STAGE_BYTES);
+          const int64_t ao = (mb * KB + ti.kb0 + kb) * (TC_BM * TC_BK), wo = (nb * KB + ti.kb0 + kb) * (TC_BN * TC_BK);
+          const float* srcs[4] = {Ahi + ao, Alo + ao, Whi + wo, Wlo + wo};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + i * TC_TILE_BYTES),
+                         "l"(srcs[i]), "r"(TC_TILE_BYTES), "r"(fb)
+                         : "memory");
+        }
       }
-    };
-    int64_t gl = 0;                                                    // blocks fetched so far (stage = gl % STAGES)
-    auto fetch = [&]() {
-      char* base = smem + static_cast<int>(gl % TC_STAGES) * TC_STAGE_BYTES;
-      const int64_t k0 = (lti.kb0 + lkb) * TC_BK;
-      cp_async_tile(Ahi, K, lti.m0, M, k0, base, tid);
-      cp_async_tile(Alo, K, lti.m0, M, k0, base + TC_TILE_BYTES, tid);
-      cp_async_tile(Whi, K, lti.n0, Nc, k0, base + 2 * TC_TILE_BYTES, tid);
-      cp_async_tile(Wlo, K, lti.n0, Nc, k0, base + 3 * TC_TILE_BYTES, tid);
-      ++gl; ++lkb;
-    };
-    settle();
-    for (int i = 0; i < TC_STAGES - 1; ++i) {                          // prologue: STAGES-1 blocks in flight
-      if (lt < ntiles) { fetch(); settle(); }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    int64_t gk = 0, gc = 0;                                            // blocks multiplied / chains started so far
-    for (int64_t mt = blockIdx.x; mt < ntiles; mt += gridDim.x) {
-      const TcTile ti = tile(mt);
-      for (int64_t kb = 0; kb < ti.nkb; ++kb, ++gk) {
-        const int st = static_cast<int>(gk % TC_STAGES);
-        asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");   // this thread's part of block gk landed
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
-        asm volatile("bar.sync 1, 128;" ::: "memory");                   // ... and everybody else's (this warpgroup only)
-        if (tid == 0) {
-          const int64_t c = gc + kb / TC_CHAIN;                          // chain of this block, accumulator c & 1
-          if (kb % TC_CHAIN == 0 && c >= 2)                              // chain c-2 must have been read out
+  } else if (warp == 1) {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      int64_t g = 0, gc = 0;                                           // blocks multiplied / chains started so far
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TcTile ti = tile(t);
+        for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
+          const int st = static_cast<int>(g % TC_STAGES);
+          const int64_t c = gc + kb / TC_CHAIN;                        // chain of this block, accumulator c & 1
+          if (kb % TC_CHAIN == 0 && c >= 2)                            // chain c-2 must have been read out
             ok &= mbar_wait(smem_u32(chain_free + (c & 1)), static_cast<unsigned>(((c >> 1) - 1) & 1));
+          ok &= mbar_wait(smem_u32(full + st), static_cast<unsigned>((g / TC_STAGES) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
           const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
           const unsigned d = tmem_d + static_cast<unsigned>((c & 1) * TC_BN);
-          const bool fresh = kb % TC_CHAIN == 0;                         // first block of a chain overwrites
+          const bool fresh = kb % TC_CHAIN == 0;                       // first block of a chain overwrites
 #pragma unroll
-          for (int s = 0; s < TC_BK / 8; ++s) {                          // UMMA_K = 8 for tf32: 32 bytes per step
+          for (int s = 0; s < TC_BK / 8; ++s) {                        // UMMA_K = 8 for tf32: 32 bytes per step
             const unsigned ko = s * 32;
             umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, !(fresh && s == 0));
             umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
             umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
           }
-          // arrives on the stage barrier when every MMA issued so far has finished reading shared memory
+          // arrives on the stage's `empty` barrier when every MMA issued so far has finished reading shared memory
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(bars + st))
+                           smem_u32(empty + st))
                        : "memory");
-          if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == ti.nkb - 1)        // ... and on the chain barrier: accumulator complete
+          if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == ti.nkb - 1)      // ... and on the chain barrier: accumulator complete
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              smem_u32(chain_full + (c & 1)))
                          : "memory");
         }
-        // refill the stage block gk-1 used, with the next block of the CTA's sequence (possibly the next tile's).  Its
-        // MMAs are waited for only now, with the MMAs of block gk already queued behind them, so the tensor pipe never
-        // drains.
-        if (lt < ntiles) {
-          if (gk >= 1)
-            ok &= mbar_wait(smem_u32(bars + static_cast<int>((gk - 1) % TC_STAGES)),
-                            static_cast<unsigned>(((gk - 1) / TC_STAGES) & 1));
-          fetch();
-          settle();
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        gc += (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
       }
-      gc += (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
     }
   } else {
     // ================= drain + epilogue warpgroup =================
-    const int q = warp - 4;                                            // TMEM lanes [32q, 32q+32) = tile rows
+    const int q = warp & 3;                                            // TMEM lanes [32q, 32q+32) = tile rows
     int64_t gc = 0;
     for (int64_t mt = blockIdx.x; mt < ntiles; mt += gridDim.x) {
       const TcTile ti = tile(mt);
@@ -413,9 +405,11 @@ static int tc_attr() {
   });
 }
 
+static int64_t tc_pad128(int64_t n) { return cdiv(n, static_cast<int64_t>(TC_BM)) * TC_BM; }   // operand images are whole 128-row tiles
+
 extern "C" size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K) {
   if (M < 0 || Nc < 0 || K < 0) return 0;
-  return 2 * align_up(static_cast<size_t>(M) * K * 4) + 2 * align_up(static_cast<size_t>(Nc) * K * 4) + 256;
+  return 2 * align_up(static_cast<size_t>(tc_pad128(M)) * K * 4) + 2 * align_up(static_cast<size_t>(tc_pad128(Nc)) * K * 4) + 256;
 }
 
 extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
@@ -433,13 +427,14 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_REQUIRE(ws && ws_bytes >= qot_gemm_tf32x3_workspace_bytes(M, Nc, K), "qot_gemm_tf32x3: workspace too small");
   if (int rc = tc_attr()) return rc;
   Carver c(ws);
-  float* a_hi = c.take<float>(M * K);
-  float* a_lo = c.take<float>(M * K);
-  float* w_hi = c.take<float>(Nc * K);
-  float* w_lo = c.take<float>(Nc * K);
-  split_tf32_kernel<<<static_cast<unsigned>(cdiv(M, 32)), 256, 0, stream>>>(A, lda, gather, M, K, a_hi, a_lo);
+  const int64_t Mp = tc_pad128(M), Np = tc_pad128(Nc);
+  float* a_hi = c.take<float>(Mp * K);
+  float* a_lo = c.take<float>(Mp * K);
+  float* w_hi = c.take<float>(Np * K);
+  float* w_lo = c.take<float>(Np * K);
+  split_tf32_kernel<<<static_cast<unsigned>(Mp / 32), 256, 0, stream>>>(A, lda, gather, M, Mp, K, a_hi, a_lo);
   QOT_LAUNCH_CHECK();
-  split_tf32_kernel<<<static_cast<unsigned>(cdiv(Nc, 32)), 256, 0, stream>>>(W, ldw, nullptr, Nc, K, w_hi, w_lo);
+  split_tf32_kernel<<<static_cast<unsigned>(Np / 32), 256, 0, stream>>>(W, ldw, nullptr, Nc, Np, K, w_hi, w_lo);
   QOT_LAUNCH_CHECK();
   const int64_t ntiles = cdiv(M, TC_BM) * cdiv(Nc, TC_BN);
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(ntiles, kNumSMs));      // persistent: one CTA per SM
@@ -465,7 +460,7 @@ extern "C" size_t qot_wgrad_tf32x3_workspace_bytes(int64_t R, int64_t Mo, int64_
   if (R < 0 || Mo < 0 || No < 0) return 0;
   const int64_t rp = tc_rpad(R);
   const int splits = tc_wgrad_splits(cdiv(Mo, TC_BM) * cdiv(No, TC_BN), rp / TC_BK);
-  return 2 * align_up(static_cast<size_t>(Mo) * rp * 4) + 2 * align_up(static_cast<size_t>(No) * rp * 4) +
+  return 2 * align_up(static_cast<size_t>(tc_pad128(Mo)) * rp * 4) + 2 * align_up(static_cast<size_t>(tc_pad128(No)) * rp * 4) +
          align_up(static_cast<size_t>(splits) * Mo * No * 4) + 256;
 }
 
@@ -482,17 +477,18 @@ extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int
   const int splits = tc_wgrad_splits(tiles, nkb);
   const int64_t kps = cdiv(nkb, splits);
   Carver c(ws);
-  float* at_hi = c.take<float>(Mo * rp);
-  float* at_lo = c.take<float>(Mo * rp);
-  float* bt_hi = c.take<float>(No * rp);
-  float* bt_lo = c.take<float>(No * rp);
+  const int64_t Mp = tc_pad128(Mo), Np = tc_pad128(No);
+  float* at_hi = c.take<float>(Mp * rp);
+  float* at_lo = c.take<float>(Mp * rp);
+  float* bt_hi = c.take<float>(Np * rp);
+  float* bt_lo = c.take<float>(Np * rp);
   float* part = c.take<float>(static_cast<size_t>(splits) * Mo * No);
-  dim3 ga(static_cast<unsigned>(rp / 32), static_cast<unsigned>(cdiv(Mo, 32)));
-  dim3 gb(static_cast<unsigned>(rp / 32), static_cast<unsigned>(cdiv(No, 32)));
+  dim3 ga(static_cast<unsigned>(rp / 32), static_cast<unsigned>(Mp / 32));
+  dim3 gb(static_cast<unsigned>(rp / 32), static_cast<unsigned>(Np / 32));
   QOT_REQUIRE(ga.y <= 65535u && gb.y <= 65535u, "qot_wgrad_tf32x3: operand too wide for one launch");
-  split_tf32_transpose_kernel<<<ga, 256, 0, stream>>>(A, lda, nullptr, R, Mo, rp, at_hi, at_lo);
+  split_tf32_transpose_kernel<<<ga, 256, 0, stream>>>(A, lda, nullptr, R, Mo, rp, Mp, at_hi, at_lo);
   QOT_LAUNCH_CHECK();
-  split_tf32_transpose_kernel<<<gb, 256, 0, stream>>>(B, ldb, gather_b, R, No, rp, bt_hi, bt_lo);
+  split_tf32_transpose_kernel<<<gb, 256, 0, stream>>>(B, ldb, gather_b, R, No, rp, Np, bt_hi, bt_lo);
   QOT_LAUNCH_CHECK();
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles * splits, kNumSMs));
   if (splits == 1) {
