@@ -24,11 +24,15 @@
 namespace qot {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
+#ifndef QOT_TC_STAGES
+#define QOT_TC_STAGES 3
+#endif
+constexpr int TC_STAGES = QOT_TC_STAGES;
 constexpr int TC_THREADS = 192;                               // warp 0: bulk-copy producer, 1: MMA issue, 2-5: drain + epilogue
 #ifndef QOT_TC_CHAIN
 #define QOT_TC_CHAIN 2
 #endif
+constexpr int TC_ACCS = 4;                                    // TMEM accumulators (4 x 128 columns = all of TMEM), used round-robin by the chains
 constexpr int64_t TC_CHAIN = QOT_TC_CHAIN;                     // k-blocks per TMEM accumulation chain (see the main loop)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
@@ -80,23 +84,6 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
   }
   return false;
 }
-// the same for a warp with nothing else to do (the drain warpgroup): a spinning try_wait takes issue slots from the
-// load warps on its scheduler, so back off between polls
-__device__ __forceinline__ bool mbar_wait_parked(unsigned bar, unsigned parity) {
-  for (unsigned spin = 0; spin < (TC_SPIN_LIMIT >> 4); ++spin) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return true;
-    __nanosleep(100);
-  }
-  return false;
-}
-
 // ---- operand images.  The pre-pass writes the hi / lo halves of an operand as a sequence of TILES: tile (rb, kb)
 // holds rows [128 rb, 128 rb + 128) x columns [32 kb, 32 kb + 32) as 16 KB in exactly the shared-memory image the
 // UMMA descriptor names (row r at r * 128 B, its 16-byte chunk j stored at chunk j ^ (r & 7): SWIZZLE_128B), tiles
@@ -183,28 +170,62 @@ __global__ void tc_reduce_splits_kernel(const float* __restrict__ part, int64_t 
 // One tile of the launch: output block (m0, n0) and, for split-K, the k-block slice [kb0, kb0 + nkb) and the
 // partial output it is written to.  Tiles are numbered n-block fastest, so the CTAs working side by side share a few
 // row blocks of A and all of W in L2.
+// Work is handed out in PAIRS of tiles to clusters of two CTAs.  The two tiles of a pair share one operand block --
+// the same rows of A (pair along n, `pair_n`) or the same rows of W (pair along m) -- and each CTA fetches only HALF
+// of the shared operand (rank 0 the hi image, rank 1 the lo image) and multicasts it into both CTAs' shared memory:
+// 48 KB instead of 64 KB through L2 per CTA and k-block.  A pair whose second tile falls off the matrix edge still
+// runs it (clamped onto the first, not stored): the partner needs its half of the shared operand.
 struct TcTile {
   int64_t m0, n0, kb0, nkb;
   float* C;
+  bool store;
 };
-__device__ __forceinline__ TcTile tc_tile(int64_t t, int64_t tiles_m, int64_t tiles_n, int64_t kb_total,
-                                          int64_t kb_per_split, int64_t splits, float* C, int64_t M, int64_t Nc) {
+struct TcGrid {
+  int64_t tiles_m, tiles_n, kb_total, kb_per_split, splits, npairs;
+  bool pair_n;
+};
+__host__ __device__ inline TcGrid tc_grid(int64_t M, int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits) {
+  TcGrid g;
+  g.tiles_m = (M + TC_BM - 1) / TC_BM;
+  g.tiles_n = (Nc + TC_BN - 1) / TC_BN;
+  g.kb_total = K / TC_BK;
+  g.kb_per_split = kb_per_split;
+  g.splits = splits;
+  g.pair_n = g.tiles_n % 2 == 0 || g.tiles_m % 2 != 0;              // prefer the dimension with an even tile count
+  g.npairs = splits * (g.pair_n ? g.tiles_m * ((g.tiles_n + 1) / 2) : ((g.tiles_m + 1) / 2) * g.tiles_n);
+  return g;
+}
+__device__ __forceinline__ TcTile tc_tile(const TcGrid& g, int64_t p, int rank, float* C, int64_t M, int64_t Nc) {
   TcTile ti;
-  const int64_t z = t / (tiles_m * tiles_n), r = t % (tiles_m * tiles_n);
-  ti.m0 = (r / tiles_n) * TC_BM;
-  ti.n0 = (r % tiles_n) * TC_BN;
-  ti.kb0 = z * kb_per_split;
-  ti.nkb = max(static_cast<int64_t>(0), min(kb_total - ti.kb0, kb_per_split));
-  ti.C = splits > 1 ? C + z * M * Nc : C;
+  int64_t z, mb, nb;
+  if (g.pair_n) {
+    const int64_t pn = (g.tiles_n + 1) / 2, per = g.tiles_m * pn, r = p % per;
+    z = p / per; mb = r / pn; nb = 2 * (r % pn) + rank;
+    ti.store = nb < g.tiles_n;
+    nb = min(nb, g.tiles_n - 1);
+  } else {
+    const int64_t pm = (g.tiles_m + 1) / 2, per = pm * g.tiles_n, r = p % per;
+    z = p / per; mb = 2 * (r / g.tiles_n) + rank; nb = r % g.tiles_n;
+    ti.store = mb < g.tiles_m;
+    mb = min(mb, g.tiles_m - 1);
+  }
+  ti.m0 = mb * TC_BM;
+  ti.n0 = nb * TC_BN;
+  ti.kb0 = z * g.kb_per_split;
+  ti.nkb = max(static_cast<int64_t>(0), min(g.kb_total - ti.kb0, g.kb_per_split));
+  ti.C = g.splits > 1 ? C + z * M * Nc : C;
   return ti;
 }
 
-// Persistent: CTA b works on tiles b, b + gridDim.x, ...  Warp roles:
-//   warp 0 (one lane)  producer: per k-block four bulk copies (A_hi, A_lo, W_hi, W_lo tiles, 16 KB each) into one of
-//                      three 64 KB stages, completing on the stage's `full` mbarrier -- straight across tile
-//                      boundaries, so the next tile's first blocks are in flight while this tile's last MMAs run;
+// Persistent, clusters of two CTAs: cluster c works on tile pairs c, c + #clusters, ...  Warp roles in each CTA:
+//   warp 0 (one lane)  producer: per k-block three bulk copies of 16 KB tile images into one of three 64 KB stages --
+//                      the two images of its own operand block and ONE image of the shared block, multicast to both
+//                      CTAs -- completing on the stage's `full` mbarrier (which also receives the partner's
+//                      multicast); it runs straight across tile boundaries, so the next tile's first blocks are in
+//                      flight while this tile's last MMAs run;
 //   warp 1 (one lane)  MMA issue: waits `full`, issues the 12 tcgen05.mma of the block, commits them to the stage's
-//                      `empty` barrier (and, at the end of a chain, to the chain barrier);
+//                      `empty` barrier of BOTH CTAs (the partner writes into this stage too) and, at the end of a
+//                      chain, to the chain barrier;
 //   warps 2-5          drain + epilogue (TMEM lane quarter = warp % 4): add each finished TMEM chain into registers,
 //                      write the tile when its last chain is in, while the next tile is already being multiplied.
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -213,29 +234,32 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                    const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M,
                    int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits, int32_t* __restrict__ status) {
   extern __shared__ char tc_smem_raw[];
+  unsigned rank_u;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+  const int rank = static_cast<int>(rank_u);
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + TC_STAGES * TC_STAGE_BYTES);
   unsigned long long* empty = full + TC_STAGES;                   // [STAGES] MMAs that read the stage have finished
-  unsigned long long* chain_full = empty + TC_STAGES;             // [2] MMA thread -> drain warps: chain finished
-  unsigned long long* chain_free = chain_full + 2;                // [2] drain warps -> MMA thread: accumulator read out
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + 2);
+  unsigned long long* chain_full = empty + TC_STAGES;             // [ACCS] MMA thread -> drain warps: chain finished
+  unsigned long long* chain_free = chain_full + TC_ACCS;          // [ACCS] drain warps -> MMA thread: accumulator read out
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + TC_ACCS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (Nc + TC_BN - 1) / TC_BN, kb_total = K / TC_BK;
-  const int64_t ntiles = tiles_m * tiles_n * splits;
-  auto tile = [&](int64_t t) { return tc_tile(t, tiles_m, tiles_n, kb_total, kb_per_split, splits, C, M, Nc); };
+  const TcGrid tg = tc_grid(M, Nc, K, kb_per_split, splits);
+  const int64_t npairs = tg.npairs, cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  auto tile = [&](int64_t pair) { return tc_tile(tg, pair, rank, C, M, Nc); };
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(static_cast<unsigned>(2 * TC_BN))
+                 "r"(static_cast<unsigned>(TC_ACCS * TC_BN))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(empty + s)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(empty + s)) : "memory");   // both CTAs' MMAs
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TC_ACCS; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(chain_full + s)) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(chain_free + s)) : "memory");
     }
@@ -243,6 +267,8 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  // both CTAs' barriers exist before either multicasts into / arrives on the other's
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = *tmem_slot;
   constexpr unsigned idesc = tc_idesc(TC_BM, TC_BN);
@@ -252,33 +278,40 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   // MMAs on one accumulator grows LINEARLY with its length (profiles/r2_tc_chain_accuracy.md: max error / max|C| of
   // [10000,256]x[256,1024] is 3.1e-7, 5.5e-7, 1.1e-6, 2.5e-6 for chains of 1, 2, 4, 8 k-blocks; a weight gradient
   // reduced over 80 000 rows in one chain per split-K slice sat at 9e-6, torch's fp32 GEMM at 8e-7).  So a TMEM
-  // accumulator only ever holds a CHAIN of TC_CHAIN k-blocks (2: 24 MMAs).  Two accumulators alternate (chains are
-  // numbered through the whole tile sequence of the CTA); the drain warpgroup (TMEM lane quarter = warp % 4) reads
+  // accumulator only ever holds a CHAIN of TC_CHAIN k-blocks (2: 24 MMAs).  Four accumulators take turns (chains are
+  // numbered through the whole tile sequence of the CTA; the MMA thread can run three chains ahead of the drain); the drain warpgroup (TMEM lane quarter = warp % 4) reads
   // each finished chain with tcgen05.ld and adds it, round-to-nearest, into fp32 registers (128 per thread: its row of
   // the tile), off the load -> MMA -> refill critical path.
   if (warp == 0) {
     // ================= producer =================
     if (lane == 0) {
-      const int64_t KB = kb_total;
+      const int64_t KB = tg.kb_total;
       int64_t g = 0;                                                   // blocks fetched so far (stage = g % STAGES)
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int64_t t = cluster; t < npairs; t += nclusters) {
         const TcTile ti = tile(t);
         const int64_t mb = ti.m0 / TC_BM, nb = ti.n0 / TC_BN;
         for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
           const int st = static_cast<int>(g % TC_STAGES);
-          if (g >= TC_STAGES)
+          if (g >= TC_STAGES)                                          // both CTAs are done reading the stage
             ok &= mbar_wait(smem_u32(empty + st), static_cast<unsigned>(((g / TC_STAGES) - 1) & 1));
           const unsigned fb = smem_u32(full + st);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(TC_STAGE_BYTES) : "memory");
-          const unsigned dst = smem_u32(smem + st * TC_STAGE_BYTES);
+          const unsigned dst = smem_u32(smem + st * TC_STAGE_BYTES);   // [A_hi | A_lo | W_hi | W_lo]
           const int64_t ao = (mb * KB + ti.kb0 + kb) * (TC_BM * TC_BK), wo = (nb * KB + ti.kb0 + kb) * (TC_BN * TC_BK);
-          const float* srcs[4] = {Ahi + ao, Alo + ao, Whi + wo, Wlo + wo};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dst + i * TC_TILE_BYTES),
-                         "l"(srcs[i]), "r"(TC_TILE_BYTES), "r"(fb)
-                         : "memory");
+          // own operand block: both images, this CTA only
+          const float* own_hi = tg.pair_n ? Whi + wo : Ahi + ao;
+          const float* own_lo = tg.pair_n ? Wlo + wo : Alo + ao;
+          const unsigned own_dst = dst + (tg.pair_n ? 2 * TC_TILE_BYTES : 0);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(own_dst),
+                       "l"(own_hi), "r"(TC_TILE_BYTES), "r"(fb) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           own_dst + TC_TILE_BYTES), "l"(own_lo), "r"(TC_TILE_BYTES), "r"(fb) : "memory");
+          // shared operand block: rank 0 fetches the hi image, rank 1 the lo image, each for both CTAs
+          const float* sh = tg.pair_n ? (rank == 0 ? Ahi + ao : Alo + ao) : (rank == 0 ? Whi + wo : Wlo + wo);
+          const unsigned sh_dst = dst + (tg.pair_n ? 0 : 2 * TC_TILE_BYTES) + rank * TC_TILE_BYTES;
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                  sh_dst), "l"(sh), "r"(TC_TILE_BYTES), "r"(fb), "h"(static_cast<unsigned short>(3)) : "memory");
         }
       }
     }
@@ -286,18 +319,19 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
     // ================= MMA issue =================
     if (lane == 0) {
       int64_t g = 0, gc = 0;                                           // blocks multiplied / chains started so far
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int64_t t = cluster; t < npairs; t += nclusters) {
         const TcTile ti = tile(t);
         for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
           const int st = static_cast<int>(g % TC_STAGES);
-          const int64_t c = gc + kb / TC_CHAIN;                        // chain of this block, accumulator c & 1
-          if (kb % TC_CHAIN == 0 && c >= 2)                            // chain c-2 must have been read out
-            ok &= mbar_wait(smem_u32(chain_free + (c & 1)), static_cast<unsigned>(((c >> 1) - 1) & 1));
+          const int64_t c = gc + kb / TC_CHAIN;                        // chain of this block, accumulator c % ACCS
+          const int ac = static_cast<int>(c % TC_ACCS);
+          if (kb % TC_CHAIN == 0 && c >= TC_ACCS)                      // chain c-ACCS must have been read out
+            ok &= mbar_wait(smem_u32(chain_free + ac), static_cast<unsigned>(((c / TC_ACCS) - 1) & 1));
           ok &= mbar_wait(smem_u32(full + st), static_cast<unsigned>((g / TC_STAGES) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
           const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
-          const unsigned d = tmem_d + static_cast<unsigned>((c & 1) * TC_BN);
+          const unsigned d = tmem_d + static_cast<unsigned>(ac * TC_BN);
           const bool fresh = kb % TC_CHAIN == 0;                       // first block of a chain overwrites
 #pragma unroll
           for (int s = 0; s < TC_BK / 8; ++s) {                        // UMMA_K = 8 for tf32: 32 bytes per step
@@ -306,13 +340,14 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
             umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
             umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
           }
-          // arrives on the stage's `empty` barrier when every MMA issued so far has finished reading shared memory
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(empty + st))
+          // arrives on the stage's `empty` barrier of both CTAs when every MMA issued so far has finished reading
+          // shared memory
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                           smem_u32(empty + st)), "h"(static_cast<unsigned short>(3))
                        : "memory");
           if (kb % TC_CHAIN == TC_CHAIN - 1 || kb == ti.nkb - 1)      // ... and on the chain barrier: accumulator complete
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             smem_u32(chain_full + (c & 1)))
+                             smem_u32(chain_full + ac))
                          : "memory");
         }
         gc += (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
@@ -322,16 +357,17 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
     // ================= drain + epilogue warpgroup =================
     const int q = warp & 3;                                            // TMEM lanes [32q, 32q+32) = tile rows
     int64_t gc = 0;
-    for (int64_t mt = blockIdx.x; mt < ntiles; mt += gridDim.x) {
+    for (int64_t mt = cluster; mt < npairs; mt += nclusters) {
       const TcTile ti = tile(mt);
       float acc[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
       const int64_t nchains = (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
       for (int64_t cc = 0; cc < nchains; ++cc, ++gc) {
-        ok &= mbar_wait_parked(smem_u32(chain_full + (gc & 1)), static_cast<unsigned>((gc >> 1) & 1));
+        const int ac = static_cast<int>(gc % TC_ACCS);
+        ok &= mbar_wait(smem_u32(chain_full + ac), static_cast<unsigned>((gc / TC_ACCS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>((gc & 1) * TC_BN);
+        const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>(ac * TC_BN);
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
           unsigned r[32];
@@ -352,11 +388,11 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0)
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + (gc & 1))) : "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + ac)) : "memory");
       }
       // ---- epilogue: thread = tile row, its 128 columns are in registers (an empty k-slice writes zeros)
       const int64_t row = ti.m0 + q * 32 + lane;
-      if (row < M) {
+      if (row < M && ti.store) {
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
           float* crow = ti.C + row * ldc + ti.n0 + c0;
@@ -380,12 +416,15 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
     }
   }
   if (!ok && status) atomicOr(status, 2);
-  // the drain warpgroup leaves its loop only after the last chain barrier, i.e. after every MMA has finished
+  // the drain warpgroup leaves its loop only after the last chain barrier, i.e. after every MMA has finished; the
+  // cluster barrier keeps this CTA's shared memory alive until the partner has stopped multicasting into it /
+  // arriving on its barriers
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
-                 "r"(static_cast<unsigned>(2 * TC_BN))
+                 "r"(static_cast<unsigned>(TC_ACCS * TC_BN))
                  : "memory");
 }
 
@@ -403,6 +442,40 @@ static int tc_attr() {
     QOT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     return static_cast<int>(QOT_OK);
   });
+}
+
+// Launch: clusters of two CTAs, as many clusters as the device holds at once (asked from the occupancy API once per
+// device: GPC boundaries decide how many SM pairs there are), each looping over the tile pairs.
+static int tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
+                     float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits,
+                     int32_t* status, cudaStream_t stream) {
+  static std::atomic<int> max_clusters[64];
+  int dev = 0;
+  QOT_CUDA(cudaGetDevice(&dev));
+  QOT_REQUIRE(dev >= 0 && dev < 64, "qot_gemm_tf32x3: device ordinal %d out of range", dev);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int mc = max_clusters[dev].load(std::memory_order_acquire);
+  if (mc == 0) {
+    cfg.gridDim = dim3(2 * kNumSMs);
+    QOT_CUDA(cudaOccupancyMaxActiveClusters(&mc, gemm_tf32x3_kernel, &cfg));
+    QOT_REQUIRE(mc > 0, "qot_gemm_tf32x3: no cluster of two CTAs fits on device %d", dev);
+    max_clusters[dev].store(mc, std::memory_order_release);
+  }
+  const TcGrid g = tc_grid(M, Nc, K, kb_per_split, splits);
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min<int64_t>(g.npairs, mc)));
+  QOT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel, a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K, kb_per_split,
+                              splits, status));
+  return QOT_OK;
 }
 
 static int64_t tc_pad128(int64_t n) { return cdiv(n, static_cast<int64_t>(TC_BM)) * TC_BM; }   // operand images are whole 128-row tiles
@@ -436,12 +509,7 @@ extern "C" int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gathe
   QOT_LAUNCH_CHECK();
   split_tf32_kernel<<<static_cast<unsigned>(Np / 32), 256, 0, stream>>>(W, ldw, nullptr, Nc, Np, K, w_hi, w_lo);
   QOT_LAUNCH_CHECK();
-  const int64_t ntiles = cdiv(M, TC_BM) * cdiv(Nc, TC_BN);
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(ntiles, kNumSMs));      // persistent: one CTA per SM
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K,
-                                                                  K / TC_BK, 1, status);
-  QOT_LAUNCH_CHECK();
-  return QOT_OK;
+  return tc_launch(a_hi, a_lo, w_hi, w_lo, bias, C, ldc, M, Nc, K, K / TC_BK, 1, status, stream);
 }
 
 // Weight gradient on the tensor cores: C[Mo,No] (ldc) = sum_r A[r,:Mo]^T B[r,:No] over R rows (row-major
@@ -490,14 +558,8 @@ extern "C" int qot_wgrad_tf32x3(const float* A, int64_t lda, const float* B, int
   QOT_LAUNCH_CHECK();
   split_tf32_transpose_kernel<<<gb, 256, 0, stream>>>(B, ldb, gather_b, R, No, rp, Np, bt_hi, bt_lo);
   QOT_LAUNCH_CHECK();
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles * splits, kNumSMs));
-  if (splits == 1) {
-    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, 1, status);
-    QOT_LAUNCH_CHECK();
-    return QOT_OK;
-  }
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, splits, status);
-  QOT_LAUNCH_CHECK();
+  if (splits == 1) return tc_launch(at_hi, at_lo, bt_hi, bt_lo, nullptr, C, ldc, Mo, No, rp, kps, 1, status, stream);
+  if (int rc = tc_launch(at_hi, at_lo, bt_hi, bt_lo, nullptr, part, No, Mo, No, rp, kps, splits, status, stream)) return rc;
   const int64_t n = Mo * No;
   tc_reduce_splits_kernel<<<static_cast<unsigned>(cdiv(n, 256)), 256, 0, stream>>>(part, n, splits, C, No, ldc);
   QOT_LAUNCH_CHECK();
