@@ -287,6 +287,15 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_start = time.perf_counter()
+
+    def mark(what):                                   # progress on stderr: where a stuck run was, per rank
+        print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {what}", file=sys.stderr, flush=True)
+
+    wd = float(os.environ.get("QOT_BENCH_STACKS_AFTER_S", "0"))
+    if wd > 0:                                        # debugging aid: dump every thread's stack and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -325,8 +334,10 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     K, W = max(1, args.steps), max(args.warmup, 3)
+    mark("shard resident; capturing")
     runner = ResidentRunner(model, plan, K)
     runner.capture(W)
+    mark("calibrating")
     # ---- calibrate: how many unit replays make the timed region >= --min-timed-ms (same count on every rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -348,6 +359,7 @@ def run_b200(args):
     if prof:
         torch.cuda.profiler.stop()
     barrier()
+    mark("timed region done")
     ms = ev0.elapsed_time(ev1)
     per_rank_ms = all_ranks(ms)
     ms_max = max(per_rank_ms)
@@ -406,7 +418,9 @@ def run_b200(args):
         Ke = max(1, min(args.e2e_steps, K))
         Ke = Ke * max(1, -(-1500 // Ke))
         seq = [hbs[i % n_host] for i in range(Ke)]
+        mark("e2e warm-up")
         pipe.run(seq)                                          # warm-up: same length, so the pinned result buffer of the timed run exists
+        mark("e2e timed")
         h2d0, zc0, d2h0, st0 = pipe.h2d_bytes, pipe.zero_copy_bytes, pipe.d2h_bytes, pipe.steps
         barrier()
         t0 = time.perf_counter()
@@ -446,13 +460,16 @@ def run_b200(args):
         torch.cuda.empty_cache()
         import bench_topological
         secondary = {}
+        mark("secondary: cfg3")
         try:
             secondary["cfg3_topo_train"] = bench_topological.measure_train(world, rank, dev, steps=300, warmup=20)
+            mark("secondary: cfg3 dropout")
             # the reference trains with dropout 0.5 (topological_training/train.py:54-60): same step, masks drawn per step
             d5 = bench_topological.measure_train(world, rank, dev, steps=300, warmup=20, dropout_p=0.5, min_timed_ms=30.0)
             secondary["cfg3_topo_train"]["dropout_0.5"] = {k: d5[k] for k in ("value", "ms_per_step", "steps")}
         except Exception as e:                                    # noqa: BLE001 -- a secondary block never kills the headline
             secondary["cfg3_topo_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        mark("secondary: rank-0 blocks")
         if rank == 0:
             try:
                 secondary["lightpath_train_step"] = bench_topological.measure_lightpath_train(dev, 512, 200, 5)
@@ -463,6 +480,7 @@ def run_b200(args):
             except Exception as e:                                # noqa: BLE001
                 secondary["cfg5_topo_stress"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         barrier()
+        mark("secondary done")
 
     if rank == 0:
         line = {

@@ -127,10 +127,10 @@ class PeerExchange:
     process group's store, peer access over NVLink), plus the DEVICE array of the peers' addresses the kernel walks.
     Raises if the ranks cannot map each other's memory (callers fall back to the NCCL all-reduce)."""
 
-    def __init__(self, numel: int, device, group=None):
+    def __init__(self, numel: int, device, group=None, local: bool = False):
         import ctypes as C
         from . import _lib
-        rank, world = world_info()
+        rank, world = (0, 1) if local else world_info()     # local: this trainer is not data-parallel (see FusedSGDStep)
         self.rank, self.world = rank, world
         nbytes = int(_lib.lib().qot_ddp_exchange_bytes(int(numel)))
         if world == 1:
@@ -166,7 +166,10 @@ class FusedSGDStep:
         ps = [p for p in g["params"] if p.requires_grad]
         return bool(ps) and all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps)
 
-    def __init__(self, optimizer, grads: FlatGradBuffer, group=None):
+    def __init__(self, optimizer, grads: FlatGradBuffer, group=None, distributed: bool = True):
+        """``distributed=False``: the update only, no exchange, even when a process group exists -- a model trained by
+        ONE rank of a multi-rank job (no ``GraphDataParallel`` around it) must not enter a collective its peers never
+        reach (the rendezvous below would wait for them forever)."""
         import ctypes as C
         from . import _lib
         self.opt, self.grads = optimizer, grads
@@ -175,8 +178,8 @@ class FusedSGDStep:
             raise RuntimeError("FusedSGDStep: the optimizer and the flat gradient buffer must hold the same parameters in the same order")
         dev = grads.flat.device
         self.dev, self.n = dev, int(grads.flat.numel())
-        self.rank, self.world = world_info()
-        self.exchange = PeerExchange(self.n, dev, group)
+        self.rank, self.world = world_info() if distributed else (0, 1)
+        self.exchange = PeerExchange(self.n, dev, group, local=not distributed)
         segs = (_lib.QotParamSeg * len(params))()
         for i, p in enumerate(params):
             segs[i].param, segs[i].offset, segs[i].numel = p.data_ptr(), grads.offsets[i], p.numel()

@@ -80,7 +80,7 @@ class GraphedTrainStep:
             if FusedSGDStep.supports(optimizer):
                 try:
                     self._grads = ddp.grads if ddp is not None else FlatGradBuffer(model.parameters())
-                    self.fused = FusedSGDStep(optimizer, self._grads)
+                    self.fused = FusedSGDStep(optimizer, self._grads, distributed=ddp is not None)
                 except Exception as e:                # noqa: BLE001 -- e.g. no peer mapping between the ranks
                     if multi:
                         import warnings
@@ -271,7 +271,7 @@ class GraphedStepCache:
         self.shared = None
         if FusedSGDStep.supports(optimizer):
             grads = ddp.grads if ddp is not None else FlatGradBuffer(model.parameters())
-            self.shared = (grads, FusedSGDStep(optimizer, grads))
+            self.shared = (grads, FusedSGDStep(optimizer, grads, distributed=ddp is not None))
         self.captures = self.replays = 0
 
     @staticmethod

@@ -50,4 +50,16 @@ if rank == 0:
     print(f"ddp_check world={world}: grad rel err vs concatenated batch {float(res[0]):.3e} (bar 1e-5); "
           f"replicas identical after graphed steps: {float(res[1]) == 0.0}; loss {float(loss):.6f}")
     assert float(res[0]) <= 1e-5 and float(res[1]) == 0.0
+# a trainer WITHOUT GraphDataParallel on one rank of the job (bench.py's rank-0-only blocks): its fused update must not
+# enter a collective -- the other rank is not there (it waits at the barrier below); this used to hang in the rendezvous
+if rank == 0:
+    from gnn_qot_estimation_b200.graphed import GraphedStepCache
+    solo = TopologicalGNN(14, 16, 3, edge_dim=4, dropout_p=0.0).to(dev).train()
+    sopt = torch.optim.SGD(solo.parameters(), lr=0.1, momentum=0.9)
+    cache = GraphedStepCache(solo, sopt, lambda m, bb: crit(m(bb), bb.y.view(-1, 3)))
+    for _ in range(3):
+        cache.step(b)
+    torch.cuda.synchronize()
+    print("solo trainer on rank 0 stepped without a collective: True")
+dist.barrier()
 dist.destroy_process_group()

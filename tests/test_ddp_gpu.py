@@ -40,6 +40,7 @@ def test_ddp_over_nvlink(exchange):
     assert proc.returncode == 0, (out[-2000:], err[-3000:])
     assert "replicas identical after graphed steps: True" in out
     assert f"exchange={exchange}" in out, out[-1500:]          # no silent fallback to another exchange
+    assert "solo trainer on rank 0 stepped without a collective: True" in out
 
 
 def test_second_device_in_one_process():
