@@ -59,6 +59,8 @@ def parse_args():
                          "(TopologicalGNN DDP training, batch 1024/GPU); topo_stress = configs[4] (10k nodes, hidden 256)")
     ap.add_argument("--min-timed-ms", type=float, default=100.0,
                     help="the K-step unit is repeated until the timed region is at least this long")
+    ap.add_argument("--secondary-box-s", type=float, default=150.0,
+                    help="wall-clock box of the secondary blocks; past it the headline line is printed without them")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the time-boxed cfg 3 (DDP training) and cfg 5 (stress graph) blocks of the default line")
     return ap.parse_args()
@@ -452,10 +454,38 @@ def run_b200(args):
                     "sample": f"{n_it} batches of {Bsz} graphs ({n_g} graphs), pure-PyTorch oracle of the "
                               f"PyG path (torch_geometric absent), fp32, {threads} threads"}
 
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "repeats": timed_steps / K, "timed_steps": timed_steps, "timed_region_ms": ms_max,
+            "per_rank_ms": per_rank_ms, "l2_cycled_bytes": l2_cycled_bytes, "host": numa,
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
+            "gpu_launches": n_launch, "clocks": clk.summary(), "secondary": None,
+        }
+
     # ---- secondary, time-boxed: BASELINE cfg 3 (DDP training step, exercises the gradient exchange at N > 1)
-    # and cfg 5 (stress graph, rank 0 only: replicas).  Not part of `value`.
+    # and cfg 5 (stress graph, rank 0 only: replicas).  Not part of `value`.  The headline line is complete at this
+    # point: if the secondary blocks do not finish inside their box (a rank that never reaches a collective), rank 0
+    # prints the line without them and every rank leaves -- a secondary block never costs the headline.
     secondary = None
     if not args.no_secondary:
+        printed = threading.Lock()
+
+        def give_up():
+            if not printed.acquire(blocking=False):
+                return
+            mark(f"secondary blocks exceeded {args.secondary_box_s:.0f} s: leaving without them")
+            if rank == 0:
+                line["secondary"] = {"error": f"not finished within {args.secondary_box_s:.0f} s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        box = threading.Timer(args.secondary_box_s, give_up)
+        box.daemon = True
+        box.start()
         del runner, plan, batches, store
         torch.cuda.empty_cache()
         import bench_topological
@@ -481,17 +511,12 @@ def run_b200(args):
                 secondary["cfg5_topo_stress"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         barrier()
         mark("secondary done")
+        if not printed.acquire(blocking=False):                   # the box fired while the last block was finishing
+            time.sleep(3600)
+        box.cancel()
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "repeats": timed_steps / K, "timed_steps": timed_steps, "timed_region_ms": ms_max,
-            "per_rank_ms": per_rank_ms, "l2_cycled_bytes": l2_cycled_bytes, "host": numa,
-            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
-            "gpu_launches": n_launch, "clocks": clk.summary(), "secondary": secondary,
-        }
+        line["secondary"] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
