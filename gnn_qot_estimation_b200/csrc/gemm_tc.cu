@@ -3,20 +3,21 @@
 // computed as three TF32 tcgen05.mma products per k-step on error-compensated operands
 //   a = a_hi + a_lo,  w = w_hi + w_lo   (hi = round-to-tf32, lo = tf32(a - hi)),
 //   a*w ~= a_hi*w_lo + a_lo*w_hi + a_hi*w_hi      (the dropped a_lo*w_lo term is ~2^-22 relative)
-// accumulated in fp32 -- short chains in TMEM, the chains summed round-to-nearest in registers.  This is the one place on the path where the hidden width makes the
-// projection a real contraction (BASELINE cfg 5: [10000,256] x [256,1024] and x [256,2560], 18 GFLOP);
-// at the reference widths (H = 16 / 32) the FFMA kernel in dense.cu stays in charge.
+// accumulated in fp32 -- short chains in TMEM, the chains summed round-to-nearest in registers.  This is the one
+// place on the path where the hidden width makes the projection a real contraction (BASELINE cfg 5:
+// [10000,256] x [256,1024] and x [256,2560], 18 GFLOP); at the reference widths (H = 16 / 32) the FFMA kernel in
+// dense.cu stays in charge.
 //
-// Two kernels.  split_tf32_kernel writes the hi / lo halves of an operand once (and performs the
-// embedding-row gather of topological_training/models.py:52 on the way), so the GEMM does not redo
-// the split in every tile.  gemm_tf32x3_kernel: one CTA (128 threads) owns a 128 x 128 output tile,
-// accumulator = 128 TMEM lanes x 128 columns.  Per 32-wide k-block the four operand tiles
-// (A_hi, A_lo, W_hi, W_lo; 64 KB) are copied global -> shared with cp.async (LDGSTS, zero-filled
-// past the matrix edge) straight into the 128-byte-swizzled K-major layout the UMMA shared-memory
-// descriptor expects, three stages deep; one elected thread issues the 12 MMAs of the block and
-// commits them to the stage's mbarrier, which gates the refill of that stage.  Every TC_CHAIN k-blocks
-// the finished TMEM accumulator (one of two, 2 x 128 columns) is read with tcgen05.ld (32 lanes x 32
-// columns per warp) and added into registers; epilogue: registers + bias -> global.
+// Two steps.  (1) split_tf32_kernel (and its transposing variant for weight gradients) writes the hi / lo halves of
+// an operand once -- performing the embedding-row gather of topological_training/models.py:52 on the way -- as a
+// sequence of 16 KB TILE IMAGES: 128 rows x 32 columns in exactly the 128-byte-swizzled K-major shared-memory layout
+// the UMMA descriptors name.  (2) gemm_tf32x3_kernel: persistent, clusters of two CTAs, 128 x 128 output tiles.
+// Per CTA one thread fetches tile images with bulk copies (cp.async.bulk: three per k-block, one of them multicast
+// to both CTAs of the cluster) through three 64 KB stages on full / empty mbarriers, one thread issues the 12 MMAs of
+// a k-block, and four warps drain: a TMEM accumulator (one of four, 128 lanes x 128 columns) only ever holds a chain
+// of TC_CHAIN k-blocks, which the drain warps read with tcgen05.ld and add into registers; epilogue: registers + bias
+// -> global while the next tile is already in the tensor pipe.  profiles/r2_cfg5_forward.md has the measurements
+// behind each of these choices.
 #include <algorithm>
 
 #include "common.cuh"

@@ -9,7 +9,11 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,Nc,K", [(128, 128, 32), (1000, 256, 64), (4097, 1024, 256), (10000, 2560, 256), (300, 68, 96)])
+# tile-pair shapes of the cluster kernel: 1x1 and 3x1 tiles (odd x odd: pair along n with an off-the-edge partner),
+# 8x2 / 33x8 / 79x20 (pair along n), 2x3 and 8x1 (n-tile count odd, m-tile count even: pair along m, W multicast),
+# and a long reduction (128 k-blocks = 64 TMEM chains per tile over the four accumulators)
+@pytest.mark.parametrize("M,Nc,K", [(128, 128, 32), (1000, 256, 64), (4097, 1024, 256), (10000, 2560, 256), (300, 68, 96),
+                                    (256, 384, 64), (1024, 100, 128), (200, 256, 4096)])
 @pytest.mark.parametrize("bias", [False, True])
 def test_gemm_tf32x3_matches_fp64(cuda, M, Nc, K, bias):
     from gnn_qot_estimation_b200 import ops
@@ -44,7 +48,8 @@ def test_gemm_tf32x3_deterministic(cuda):
     assert torch.equal(ops.gemm_tf32x3(A, W), ops.gemm_tf32x3(A, W))
 
 
-@pytest.mark.parametrize("R,Mo,No", [(1000, 128, 128), (10000, 2560, 256), (4099, 1024, 256), (2048, 70, 100)])
+@pytest.mark.parametrize("R,Mo,No", [(1000, 128, 128), (10000, 2560, 256), (4099, 1024, 256), (2048, 70, 100),
+                                     (3000, 256, 128), (80000, 256, 256), (37, 128, 384)])
 def test_wgrad_tf32x3_matches_fp64(cuda, R, Mo, No):
     """dW = dy^T x on the tensor cores (transposed split operands, split-K slices summed in fixed order)."""
     from gnn_qot_estimation_b200 import ops
