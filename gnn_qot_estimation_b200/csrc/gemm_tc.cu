@@ -37,8 +37,24 @@ constexpr int TC_ACCS = 4;                                    // TMEM accumulato
 constexpr int64_t TC_CHAIN = QOT_TC_CHAIN;                     // k-blocks per TMEM accumulation chain (see the main loop)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per (operand, hi|lo) tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, W_hi, W_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128;   // + barriers, TMEM slot
+constexpr int TC_EPI_PITCH = 36;                              // floats per row of an epilogue patch
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers, TMEM slot*/ +
+                              4 * 32 * TC_EPI_PITCH * 4 /*epilogue patches*/;
 constexpr unsigned TC_SPIN_LIMIT = 1u << 26;                // a wedged barrier ends the kernel, never hangs it
+
+// -DQOT_TC_TRACE: per-role cycle accounting (scripts/trace_gemm_tc.py): 8 counters per CTA
+#ifdef QOT_TC_TRACE
+__device__ unsigned long long* g_tc_trace = nullptr;
+#define TC_T() const long long tc_t_ = clock64()
+#define TC_ACC(slot) do { tc_acc_[slot] += clock64() - tc_t_; } while (0)
+#define TC_DECL() long long tc_acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TC_FLUSH() do { if (g_tc_trace) for (int i_ = 0; i_ < 8; ++i_) if (tc_acc_[i_]) atomicAdd(g_tc_trace + blockIdx.x * 8 + i_, static_cast<unsigned long long>(tc_acc_[i_])); } while (0)
+#else
+#define TC_T() do {} while (0)
+#define TC_ACC(slot) do {} while (0)
+#define TC_DECL() do {} while (0)
+#define TC_FLUSH() do {} while (0)
+#endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
@@ -64,12 +80,22 @@ constexpr unsigned tc_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<unsigned>(N >> 3) << 17) |
          (static_cast<unsigned>(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
+// The three products of one k-step (UMMA_K = 8 columns = 32 bytes of the swizzled rows) in one block:
+// D (+)= A_hi W_lo^T; D += A_lo W_hi^T; D += A_hi W_hi^T -- small terms first.  The descriptors differ from a per-stage
+// base only in the start-address field ((addr >> 4) & 0x3fff, the low bits), so the issuing thread forms them by
+// ADDING to the base (the one-thread issue path, not the tensor pipe, was the kernel's cycle time when every
+// descriptor was rebuilt from its address: 75 cycles per MMA, profiles/r2_cfg5_forward.md).
+__device__ __forceinline__ void umma_tf32_step(unsigned tmem_d, unsigned long long a_hi, unsigned long long a_lo,
+                                               unsigned long long w_hi, unsigned long long w_lo, unsigned idesc,
+                                               unsigned accumulate_first) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, t;\n\t}\n" ::"r"(tmem_d),
+      "l"(a_hi), "l"(a_lo), "l"(w_hi), "l"(w_lo), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
 __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
@@ -244,6 +270,7 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
   unsigned long long* chain_full = empty + TC_STAGES;             // [ACCS] MMA thread -> drain warps: chain finished
   unsigned long long* chain_free = chain_full + TC_ACCS;          // [ACCS] drain warps -> MMA thread: accumulator read out
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(chain_free + TC_ACCS);
+  float* epi = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + 128);   // 4 warps x 32 x 36 floats
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TcGrid tg = tc_grid(M, Nc, K, kb_per_split, splits);
   const int64_t npairs = tg.npairs, cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -287,14 +314,20 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
     // ================= producer =================
     if (lane == 0) {
       const int64_t KB = tg.kb_total;
+      TC_DECL();
       int64_t g = 0;                                                   // blocks fetched so far (stage = g % STAGES)
       for (int64_t t = cluster; t < npairs; t += nclusters) {
         const TcTile ti = tile(t);
         const int64_t mb = ti.m0 / TC_BM, nb = ti.n0 / TC_BN;
         for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
           const int st = static_cast<int>(g % TC_STAGES);
-          if (g >= TC_STAGES)                                          // both CTAs are done reading the stage
-            ok &= mbar_wait(smem_u32(empty + st), static_cast<unsigned>(((g / TC_STAGES) - 1) & 1));
+          {
+            TC_T();
+            if (g >= TC_STAGES)                                        // both CTAs are done reading the stage
+              ok &= mbar_wait(smem_u32(empty + st), static_cast<unsigned>(((g / TC_STAGES) - 1) & 1));
+            TC_ACC(0);
+          }
+          TC_T();
           const unsigned fb = smem_u32(full + st);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(TC_STAGE_BYTES) : "memory");
           const unsigned dst = smem_u32(smem + st * TC_STAGE_BYTES);   // [A_hi | A_lo | W_hi | W_lo]
@@ -313,34 +346,45 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
                   sh_dst), "l"(sh), "r"(TC_TILE_BYTES), "r"(fb), "h"(static_cast<unsigned short>(3)) : "memory");
+          TC_ACC(1);
         }
       }
+      TC_FLUSH();
     }
   } else if (warp == 1) {
     // ================= MMA issue =================
     if (lane == 0) {
       int64_t g = 0, gc = 0;                                           // blocks multiplied / chains started so far
+      const unsigned long long desc0 = umma_desc_sw128(smem_u32(smem));   // stage 0, A_hi, k-step 0
+      TC_DECL();
       for (int64_t t = cluster; t < npairs; t += nclusters) {
         const TcTile ti = tile(t);
         for (int64_t kb = 0; kb < ti.nkb; ++kb, ++g) {
           const int st = static_cast<int>(g % TC_STAGES);
           const int64_t c = gc + kb / TC_CHAIN;                        // chain of this block, accumulator c % ACCS
           const int ac = static_cast<int>(c % TC_ACCS);
-          if (kb % TC_CHAIN == 0 && c >= TC_ACCS)                      // chain c-ACCS must have been read out
-            ok &= mbar_wait(smem_u32(chain_free + ac), static_cast<unsigned>(((c / TC_ACCS) - 1) & 1));
-          ok &= mbar_wait(smem_u32(full + st), static_cast<unsigned>((g / TC_STAGES) & 1));
+          {
+            TC_T();
+            if (kb % TC_CHAIN == 0 && c >= TC_ACCS)                    // chain c-ACCS must have been read out
+              ok &= mbar_wait(smem_u32(chain_free + ac), static_cast<unsigned>(((c / TC_ACCS) - 1) & 1));
+            TC_ACC(2);
+          }
+          {
+            TC_T();
+            ok &= mbar_wait(smem_u32(full + st), static_cast<unsigned>((g / TC_STAGES) & 1));
+            TC_ACC(3);
+          }
+          TC_T();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned a_hi = smem_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
-          const unsigned w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+          // stage image [A_hi | A_lo | W_hi | W_lo]: descriptor = stage-0 base + (byte offset >> 4)
+          const unsigned long long a_hi = desc0 + static_cast<unsigned>(st * (TC_STAGE_BYTES >> 4));
+          const unsigned long long a_lo = a_hi + (TC_TILE_BYTES >> 4), w_hi = a_hi + 2 * (TC_TILE_BYTES >> 4),
+                                   w_lo = a_hi + 3 * (TC_TILE_BYTES >> 4);
           const unsigned d = tmem_d + static_cast<unsigned>(ac * TC_BN);
           const bool fresh = kb % TC_CHAIN == 0;                       // first block of a chain overwrites
 #pragma unroll
-          for (int s = 0; s < TC_BK / 8; ++s) {                        // UMMA_K = 8 for tf32: 32 bytes per step
-            const unsigned ko = s * 32;
-            umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, !(fresh && s == 0));
-            umma_tf32(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-            umma_tf32(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
-          }
+          for (int s = 0; s < TC_BK / 8; ++s)                          // UMMA_K = 8 for tf32: 32 bytes (2 x 16) per step
+            umma_tf32_step(d, a_hi + 2 * s, a_lo + 2 * s, w_hi + 2 * s, w_lo + 2 * s, idesc, !(fresh && s == 0));
           // arrives on the stage's `empty` barrier of both CTAs when every MMA issued so far has finished reading
           // shared memory
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -350,14 +394,17 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              smem_u32(chain_full + ac))
                          : "memory");
+          TC_ACC(4);
         }
         gc += (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
       }
+      TC_FLUSH();
     }
   } else {
     // ================= drain + epilogue warpgroup =================
     const int q = warp & 3;                                            // TMEM lanes [32q, 32q+32) = tile rows
     int64_t gc = 0;
+    TC_DECL();
     for (int64_t mt = cluster; mt < npairs; mt += nclusters) {
       const TcTile ti = tile(mt);
       float acc[TC_BN];
@@ -366,7 +413,12 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
       const int64_t nchains = (ti.nkb + TC_CHAIN - 1) / TC_CHAIN;
       for (int64_t cc = 0; cc < nchains; ++cc, ++gc) {
         const int ac = static_cast<int>(gc % TC_ACCS);
-        ok &= mbar_wait(smem_u32(chain_full + ac), static_cast<unsigned>((gc / TC_ACCS) & 1));
+        {
+          TC_T();
+          ok &= mbar_wait(smem_u32(chain_full + ac), static_cast<unsigned>((gc / TC_ACCS) & 1));
+          TC_ACC(5);
+        }
+        TC_T();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned base = tmem_d + (static_cast<unsigned>(q * 32) << 16) + static_cast<unsigned>(ac * TC_BN);
 #pragma unroll
@@ -390,31 +442,56 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
         __syncwarp();
         if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(chain_free + ac)) : "memory");
+        TC_ACC(6);
       }
-      // ---- epilogue: thread = tile row, its 128 columns are in registers (an empty k-slice writes zeros)
-      const int64_t row = ti.m0 + q * 32 + lane;
-      if (row < M && ti.store) {
+      TC_T();
+      // ---- epilogue: the thread holds ROW q*32+lane of the tile (an empty k-slice: zeros).  Written as it stands,
+      // one store instruction would touch 32 rows x 16 bytes (7 300 cycles per tile, as long as the whole mainloop);
+      // so each 32 x 32 chunk is turned through a per-warp shared-memory patch (pitch 36 floats: conflict-free both
+      // ways) and leaves as 8 instructions of 4 rows x 128 contiguous bytes.
+      if (ti.store) {
+        float* patch = epi + q * (32 * TC_EPI_PITCH);
+        const int pr = lane >> 3, pc = (lane & 7) * 4;                 // read side: row within a group of 4, column
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-          float* crow = ti.C + row * ldc + ti.n0 + c0;
-          if (ti.n0 + c0 + 32 <= Nc && (ldc & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
-              if (bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + ti.n0 + c0 + j);
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              *reinterpret_cast<float4*>(crow + j) = o;
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(patch + lane * TC_EPI_PITCH + j) =
+                make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+          __syncwarp();
+          const int64_t col = ti.n0 + c0 + pc;
+          const bool vec = (ldc & 3) == 0 && col + 4 <= Nc;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) {
+            if (vec) bv = *reinterpret_cast<const float4*>(bias + col);
+            else {
+              bv.x = col < Nc ? bias[col] : 0.f; bv.y = col + 1 < Nc ? bias[col + 1] : 0.f;
+              bv.z = col + 2 < Nc ? bias[col + 2] : 0.f; bv.w = col + 3 < Nc ? bias[col + 3] : 0.f;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ti.n0 + c0 + j < Nc) crow[j] = acc[c0 + j] + (bias ? bias[ti.n0 + c0 + j] : 0.f);
           }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + pr;
+            const int64_t row = ti.m0 + q * 32 + r;
+            float4 o = *reinterpret_cast<const float4*>(patch + r * TC_EPI_PITCH + pc);
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            if (row < M) {
+              float* cp = ti.C + row * ldc + col;
+              if (vec) *reinterpret_cast<float4*>(cp) = o;
+              else {
+                if (col < Nc) cp[0] = o.x;
+                if (col + 1 < Nc) cp[1] = o.y;
+                if (col + 2 < Nc) cp[2] = o.z;
+                if (col + 3 < Nc) cp[3] = o.w;
+              }
+            }
+          }
+          __syncwarp();
         }
       }
+      TC_ACC(7);
     }
+    if (warp == 2 && lane == 0) TC_FLUSH();
   }
   if (!ok && status) atomicOr(status, 2);
   // the drain warpgroup leaves its loop only after the last chain barrier, i.e. after every MMA has finished; the
@@ -480,6 +557,12 @@ static int tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, co
 }
 
 static int64_t tc_pad128(int64_t n) { return cdiv(n, static_cast<int64_t>(TC_BM)) * TC_BM; }   // operand images are whole 128-row tiles
+
+#ifdef QOT_TC_TRACE
+extern "C" int qot_debug_set_tc_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K) {
   if (M < 0 || Nc < 0 || K < 0) return 0;
