@@ -10,7 +10,7 @@ __global__ void stream_kernel(const float4* __restrict__ buf, size_t n4, int rep
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (int r = 0; r < reps; ++r)
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 v = buf[i];
+      const float4 v = __ldcg(buf + i);                    // L2 only: the per-SM slice would otherwise sit in L1
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
@@ -27,8 +27,8 @@ __global__ void gather_kernel(const float4* __restrict__ buf, unsigned nrows, in
     for (int j = 0; j < 4; ++j) {
       s = s * 1664525u + 1013904223u;
       const float4* row = buf + static_cast<size_t>(s % nrows) * 64;
-      v[j][0] = row[lane];
-      v[j][1] = row[lane + 32];
+      v[j][0] = __ldcg(row + lane);
+      v[j][1] = __ldcg(row + lane + 32);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc.x += v[j][0].x + v[j][1].x; acc.y += v[j][0].y + v[j][1].y; }
