@@ -59,6 +59,16 @@ __device__ unsigned long long* g_tc_trace = nullptr;
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
+// explicit shared-space accesses: the patch pointer is derived from an aligned-up generic address, so plain
+// dereferences compile to generic LD / ST (long-scoreboard latency) instead of LDS / STS
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float to_tf32(float v) {
   unsigned r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -450,14 +460,14 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
       // so each 32 x 32 chunk is turned through a per-warp shared-memory patch (pitch 36 floats: conflict-free both
       // ways) and leaves as 8 instructions of 4 rows x 128 contiguous bytes.
       if (ti.store) {
-        float* patch = epi + q * (32 * TC_EPI_PITCH);
+        const unsigned patch = smem_u32(epi) + static_cast<unsigned>(q * (32 * TC_EPI_PITCH * 4));   // byte address
         const int pr = lane >> 3, pc = (lane & 7) * 4;                 // read side: row within a group of 4, column
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(patch + lane * TC_EPI_PITCH + j) =
-                make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+            sts128(patch + static_cast<unsigned>((lane * TC_EPI_PITCH + j) * 4),
+                   make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]));
           __syncwarp();
           const int64_t col = ti.n0 + c0 + pc;
           const bool vec = (ldc & 3) == 0 && col + 4 <= Nc;
@@ -469,11 +479,11 @@ gemm_tf32x3_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
               bv.z = col + 2 < Nc ? bias[col + 2] : 0.f; bv.w = col + 3 < Nc ? bias[col + 3] : 0.f;
             }
           }
-#pragma unroll
+#pragma unroll 2
           for (int k = 0; k < 8; ++k) {
             const int r = 4 * k + pr;
             const int64_t row = ti.m0 + q * 32 + r;
-            float4 o = *reinterpret_cast<const float4*>(patch + r * TC_EPI_PITCH + pc);
+            float4 o = lds128(patch + static_cast<unsigned>((r * TC_EPI_PITCH + pc) * 4));
             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
             if (row < M) {
               float* cp = ti.C + row * ldc + col;
