@@ -77,6 +77,7 @@ SIGNATURES = {
     "qot_edge_ptr": (C.c_int, [P, i64, P, i64, i64, P, P, vp]),
     "qot_gemm": (C.c_int, [P, i64, i64, P, P, i64, i64, P, P, i64, i64, i64, i64, vp]),
     "qot_gemm_tf32x3_workspace_bytes": (sz, [i64, i64, i64]),
+    "qot_debug_gemm_tiles": (i64, [i64, i64, i64, i64, i64, P, i64]),
     "qot_gemm_tf32x3": (C.c_int, [P, i64, P, P, i64, P, P, i64, i64, i64, i64, P, P, sz, vp]),
     "qot_wgrad_tf32x3_workspace_bytes": (sz, [i64, i64, i64]),
     "qot_wgrad_tf32x3": (C.c_int, [P, i64, P, i64, P, i64, i64, i64, P, i64, P, P, sz, vp]),

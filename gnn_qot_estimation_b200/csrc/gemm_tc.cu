@@ -232,24 +232,25 @@ __host__ __device__ inline TcGrid tc_grid(int64_t M, int64_t Nc, int64_t K, int6
   g.npairs = splits * (g.pair_n ? g.tiles_m * ((g.tiles_n + 1) / 2) : ((g.tiles_m + 1) / 2) * g.tiles_n);
   return g;
 }
-__device__ __forceinline__ TcTile tc_tile(const TcGrid& g, int64_t p, int rank, float* C, int64_t M, int64_t Nc) {
+__host__ __device__ inline TcTile tc_tile(const TcGrid& g, int64_t p, int rank, float* C, int64_t M, int64_t Nc) {
   TcTile ti;
   int64_t z, mb, nb;
   if (g.pair_n) {
     const int64_t pn = (g.tiles_n + 1) / 2, per = g.tiles_m * pn, r = p % per;
     z = p / per; mb = r / pn; nb = 2 * (r % pn) + rank;
     ti.store = nb < g.tiles_n;
-    nb = min(nb, g.tiles_n - 1);
+    nb = nb < g.tiles_n ? nb : g.tiles_n - 1;
   } else {
     const int64_t pm = (g.tiles_m + 1) / 2, per = pm * g.tiles_n, r = p % per;
     z = p / per; mb = 2 * (r / g.tiles_n) + rank; nb = r % g.tiles_n;
     ti.store = mb < g.tiles_m;
-    mb = min(mb, g.tiles_m - 1);
+    mb = mb < g.tiles_m ? mb : g.tiles_m - 1;
   }
   ti.m0 = mb * TC_BM;
   ti.n0 = nb * TC_BN;
   ti.kb0 = z * g.kb_per_split;
-  ti.nkb = max(static_cast<int64_t>(0), min(g.kb_total - ti.kb0, g.kb_per_split));
+  const int64_t left = g.kb_total - ti.kb0;
+  ti.nkb = left < 0 ? 0 : (left < g.kb_per_split ? left : g.kb_per_split);
   ti.C = g.splits > 1 ? C + z * M * Nc : C;
   return ti;
 }
@@ -573,6 +574,25 @@ extern "C" int qot_debug_set_tc_trace(unsigned long long* buf) {
   return cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
 }
 #endif
+
+// Test hook (host only, no GPU): the tile decomposition of a launch -- for every (pair, cluster rank) the output
+// block, its k-block slice and whether the CTA stores it -- so that a CPU test can check that every output tile of
+// every split-K slice is written exactly once.  out: [2 * npairs][6] = m0, n0, kb0, nkb, store, slice.  Returns the
+// number of rows (2 * npairs); fills at most `cap` of them.
+extern "C" int64_t qot_debug_gemm_tiles(int64_t M, int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits,
+                                        int64_t* out, int64_t cap) {
+  if (M <= 0 || Nc <= 0 || K <= 0 || K % TC_BK || kb_per_split <= 0 || splits <= 0) return -1;
+  const TcGrid g = tc_grid(M, Nc, K, kb_per_split, splits);
+  int64_t n = 0;
+  for (int64_t p = 0; p < g.npairs; ++p)
+    for (int rank = 0; rank < 2; ++rank, ++n) {
+      if (!out || n >= cap) continue;
+      const TcTile t = tc_tile(g, p, rank, nullptr, M, Nc);
+      int64_t* o = out + n * 6;
+      o[0] = t.m0; o[1] = t.n0; o[2] = t.kb0; o[3] = t.nkb; o[4] = t.store ? 1 : 0; o[5] = t.kb0 / kb_per_split;
+    }
+  return n;
+}
 
 extern "C" size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K) {
   if (M < 0 || Nc < 0 || K < 0) return 0;

@@ -129,6 +129,11 @@ int qot_gemm(const float* A, int64_t a_rs, int64_t a_cs, const int64_t* gather,
  * timed out (result undefined).  ws: room for the hi / lo halves of both operands, which a small
  * pre-pass writes once (it also performs the row gather). */
 size_t qot_gemm_tf32x3_workspace_bytes(int64_t M, int64_t Nc, int64_t K);
+/* Test hook, host only: the tile decomposition of a qot_gemm_tf32x3 / qot_wgrad_tf32x3 launch (pairs of tiles handed
+ * to clusters of two CTAs).  out [rows][6] = m0, n0, first k-block, k-blocks, stores (0/1), split-K slice; returns the
+ * number of rows, fills at most cap. */
+int64_t qot_debug_gemm_tiles(int64_t M, int64_t Nc, int64_t K, int64_t kb_per_split, int64_t splits, int64_t* out,
+                             int64_t cap);
 int qot_gemm_tf32x3(const float* A, int64_t lda, const int64_t* gather, const float* W, int64_t ldw,
                     const float* bias, float* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K,
                     int32_t* status, void* ws, size_t ws_bytes, void* stream);

@@ -121,3 +121,41 @@ def test_no_triton_or_compile_in_product():
     for p in PKG.rglob("*.py"):
         t = p.read_text()
         assert "import triton" not in t and "torch.compile" not in t, p
+
+
+@pytest.mark.parametrize("M,Nc,K,splits", [(128, 128, 32, 1), (300, 68, 96, 1), (1000, 256, 64, 1), (256, 384, 64, 1),
+                                           (1024, 100, 128, 1), (10000, 2560, 256, 1), (4097, 1024, 256, 1),
+                                           (256, 256, 80000, 37), (2560, 256, 10016, 64), (128, 384, 64, 3)])
+def test_gemm_tile_pairs_cover_every_output_tile_once(lib_path, M, Nc, K, splits):
+    """Host-only hook of csrc/gemm_tc.cu: the cluster kernel hands out PAIRS of tiles; whatever the tile counts
+    (odd x odd: a partner off the matrix edge that computes but does not store; n-count odd and m-count even: pairs
+    along m) every 128 x 128 output tile of every split-K slice must be stored by exactly one CTA, the two CTAs of a pair
+    must share the operand block they multicast and walk the same k-blocks, and the slices must tile the reduction."""
+    import numpy as np
+    L = ctypes.CDLL(str(lib_path))
+    fn = L.qot_debug_gemm_tiles
+    fn.restype = ctypes.c_int64
+    fn.argtypes = [ctypes.c_int64] * 5 + [ctypes.c_void_p, ctypes.c_int64]
+    kb_total = K // 32
+    kps = -(-kb_total // splits)
+    n = fn(M, Nc, K, kps, splits, None, 0)
+    assert n > 0 and n % 2 == 0
+    out = np.zeros((n, 6), dtype=np.int64)
+    assert fn(M, Nc, K, kps, splits, out.ctypes.data, n) == n
+    tm, tn = -(-M // 128), -(-Nc // 128)
+    seen = {}
+    for p in range(0, n, 2):
+        a, b = out[p], out[p + 1]
+        assert a[4] == 1                                            # rank 0 always owns a real tile
+        assert tuple(a[2:4]) == tuple(b[2:4]) and a[5] == b[5]      # same k-blocks: the pair runs in lockstep
+        assert a[0] == b[0] or a[1] == b[1]                          # shared operand block: same A rows or same W rows
+        for t in (a, b):
+            assert 0 <= t[0] < tm * 128 and 0 <= t[1] < tn * 128 and t[0] % 128 == 0 and t[1] % 128 == 0
+            if t[4]:
+                key = (int(t[5]), int(t[0]), int(t[1]))
+                assert key not in seen, key
+                seen[key] = (int(t[2]), int(t[3]))
+    assert len(seen) == splits * tm * tn
+    for (z, m0, n0), (kb0, nkb) in seen.items():                     # slices tile [0, kb_total)
+        assert kb0 == z * kps and nkb == max(0, min(kps, kb_total - kb0))
+    assert sum(v[1] for k, v in seen.items() if k[1] == 0 and k[2] == 0) == kb_total
