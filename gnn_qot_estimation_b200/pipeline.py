@@ -54,7 +54,7 @@ class LightpathInferencePipeline:
                  "verified from_networkx layout), "
                  "unpacked to the reference layout on the device")
 
-    def __init__(self, model, max_nodes: int, max_edges: int, max_graphs: int, depth: int = 3):
+    def __init__(self, model, max_nodes: int, max_edges: int, max_graphs: int, depth: int = 6):
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("LightpathInferencePipeline needs the model on a CUDA device (no CPU path)")
